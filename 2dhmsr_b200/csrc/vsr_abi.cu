@@ -1,0 +1,705 @@
+// vsr_abi.cu -- the C ABI of include/vsr_b200.h: validation + host-side compilation of a
+// batch descriptor (what robot.reset()/assemble()/placement do in the reference,
+// Locomotion.java:172-191), upload, kernel launch, read-back.
+//
+// No CPU fallback: upload/run/results fail with VSR_ERR_NO_DEVICE / VSR_ERR_CUDA when
+// there is no usable GPU.  vsr_batch_create itself is host-only (so the argument
+// validation -- the reference's IllegalArgumentException cases -- is testable anywhere).
+#include "../../include/vsr_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "vsr_device.cuh"
+
+using namespace vsr;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? VSR_ERR_NO_DEVICE \
+                                                                               : VSR_ERR_CUDA,   \
+                  std::string(#x) + ": " + cudaGetErrorString(e_));                              \
+  } while (0)
+
+extern "C" const char* vsr_last_error(void) { return g_err.c_str(); }
+extern "C" int vsr_abi_version(void) { return VSR_ABI_VERSION; }
+extern "C" int vsr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" void vsr_default_settings(vsr_settings* s) {
+  memset(s, 0, sizeof *s);
+  s->step_frequency = 1.0 / 60.0;
+  s->velocity_iterations = 10;
+  s->position_iterations = 10;
+  s->linear_tolerance = 0.005;
+  s->angular_tolerance = 2.0 * M_PI / 180.0;
+  s->max_linear_correction = 0.2;
+  s->baumgarte = 0.2;
+  s->restitution_velocity = 1.0;
+  s->max_translation = 2.0;
+  s->max_rotation = 0.5 * M_PI;
+  s->gravity_x = 0.0;
+  s->gravity_y = -9.8;
+  s->ground_friction = 0.2;
+  s->ground_restitution = 0.0;
+  s->spring_mass_mode = VSR_SPRING_MASS_REDUCED;
+}
+
+extern "C" void vsr_default_material(vsr_material* m) {
+  memset(m, 0, sizeof *m);
+  m->side_length = 3.0;
+  m->mass_side_length_ratio = 0.35;
+  m->spring_f = 8.0;
+  m->spring_d = 0.3;
+  m->mass_linear_damping = 0.1;
+  m->mass_angular_damping = 0.1;
+  m->friction = 10.0;
+  m->restitution = 0.1;
+  m->mass = 1.0;
+  m->area_ratio_passive_min = -std::numeric_limits<double>::infinity();
+  m->area_ratio_passive_max = std::numeric_limits<double>::infinity();
+  m->area_ratio_active_min = 0.8;
+  m->area_ratio_active_max = 1.2;
+  m->spring_scaffoldings = VSR_SCAFFOLD_ALL;
+}
+
+// Locomotion.java:195-203 + AbstractTask.java:48: t = 0; while (t < finalT) t = t + dT;
+static std::vector<double> tick_times(double final_t, double dt) {
+  std::vector<double> t;
+  double tt = 0.0;
+  while (tt < final_t) {
+    tt = tt + dt;
+    t.push_back(tt);
+  }
+  return t;
+}
+extern "C" int vsr_tick_count(double final_t, double dt) {
+  if (!(dt > 0)) return 0;
+  return (int)tick_times(final_t, dt).size();
+}
+
+namespace {
+
+struct Bucket {
+  ShapeDev shape;
+  std::vector<int> robot_ids;  // batch indices, ascending
+  std::vector<double> params;  // device layout, double on the host
+  long long traj_robots = 0;
+  // device
+  ShapeDev* d_shape = nullptr;
+  int* d_ids = nullptr;
+  void* d_params = nullptr;
+  void* d_ring = nullptr;
+  void* d_traj = nullptr;
+};
+
+}  // namespace
+
+struct vsr_batch {
+  vsr_batch_desc desc;  // scalar fields only are valid after create
+  int precision = 0;
+  size_t n_robots = 0;
+  std::vector<Bucket> buckets;
+  std::vector<int> robot_bucket, robot_pos, robot_nvox;
+  std::vector<double> ticks;
+  std::vector<int16_t> win_first;  // [MAX_WINDOWS][n_ticks]
+  int ring_depth = 1;
+  std::vector<double> terr_x, terr_y;  // local frame
+  double base_y = 0, origin_x = 0;
+  double rng_min[3], rng_rest[3], rng_max[3];
+  double inv_m = 0, inv_i = 0, half = 0, red_mass = 0;
+  unsigned spring_mask = 0;
+  size_t voxel_steps = 0;
+  size_t upload_bytes = 0;
+  // device
+  int device = -1;
+  bool uploaded = false, ran = false;
+  cudaStream_t run_stream = nullptr;
+  double* d_ticks = nullptr;
+  int16_t* d_win = nullptr;
+  void* d_terr_x = nullptr;
+  void* d_terr_y = nullptr;
+  double* d_results = nullptr;
+  int last_launches = 0;
+};
+
+static int sensor_dim(const vsr_sensor& s) {
+  if (s.base == VSR_SENSOR_VELOCITY) return ((s.axes & VSR_AXIS_X) ? 1 : 0) + ((s.axes & VSR_AXIS_Y) ? 1 : 0);
+  return 1;
+}
+
+// Ground.yAt, Ground.java:104-111
+static double ground_y_at(const vsr_batch_desc* d, double x) {
+  for (int i = 1; i < d->terrain_n; i++)
+    if (d->terrain_xs[i - 1] <= x && x <= d->terrain_xs[i])
+      return (x - d->terrain_xs[i - 1]) * (d->terrain_ys[i] - d->terrain_ys[i - 1]) /
+                 (d->terrain_xs[i] - d->terrain_xs[i - 1]) +
+             d->terrain_ys[i - 1];
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
+static void free_device(vsr_batch* b) {
+  if (b->device >= 0) cudaSetDevice(b->device);
+  for (auto& k : b->buckets) {
+    cudaFree(k.d_shape); cudaFree(k.d_ids); cudaFree(k.d_params); cudaFree(k.d_ring); cudaFree(k.d_traj);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
+  }
+  cudaFree(b->d_ticks); cudaFree(b->d_win); cudaFree(b->d_terr_x); cudaFree(b->d_terr_y); cudaFree(b->d_results);
+  b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
+  b->uploaded = b->ran = false;
+}
+
+extern "C" void vsr_batch_destroy(vsr_batch* b) {
+  if (!b) return;
+  if (b->uploaded) free_device(b);
+  delete b;
+}
+
+extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
+  if (!d || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (d->abi_version != VSR_ABI_VERSION) return fail(VSR_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+  if (d->precision != VSR_PRECISION_F32 && d->precision != VSR_PRECISION_F64)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "unknown precision");
+  if (d->n_robots == 0) return fail(VSR_ERR_INVALID_ARGUMENT, "empty batch");
+  if (d->n_shapes <= 0 || !d->shapes) return fail(VSR_ERR_INVALID_ARGUMENT, "no shape classes");
+  if (!d->terrain_xs || !d->terrain_ys) return fail(VSR_ERR_INVALID_ARGUMENT, "no ground profile");
+  if (d->terrain_n < 2) return fail(VSR_ERR_INVALID_ARGUMENT, "There must be at least 2 points");  // Ground.java:52-54
+  for (int i = 1; i < d->terrain_n; i++)
+    if (d->terrain_xs[i] < d->terrain_xs[i - 1])
+      return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted");  // Ground.java:55-58
+  if (!d->params || !d->param_offsets) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
+  if (d->controller_kind < VSR_CTRL_PHASE_SIN || d->controller_kind > VSR_CTRL_MLP)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "unknown controller kind");
+  const vsr_material& m = d->material;
+  {
+    double lim = (2 * m.mass_side_length_ratio) * (2 * m.mass_side_length_ratio);
+    if (m.area_ratio_passive_min > -INFINITY && m.area_ratio_passive_min < lim)  // Voxel.java:132-140
+      return fail(VSR_ERR_INVALID_ARGUMENT, "Min of areaRatioPassiveRange cannot be lower than the value imposed by massSideLengthRatio");
+    if (m.area_ratio_passive_max < m.area_ratio_passive_min || m.area_ratio_active_max < m.area_ratio_active_min)
+      return fail(VSR_ERR_INVALID_ARGUMENT, "Max has to be lower or equal than min");  // DoubleRange.java:29-35
+    if (std::isfinite(m.area_ratio_passive_min) || std::isfinite(m.area_ratio_passive_max))
+      return fail(VSR_ERR_UNSUPPORTED, "finite areaRatioPassiveRange (DistanceJoint rope limits) is not on the accelerated path");
+    if (!(m.side_length > 0) || !(m.mass > 0) || !(m.mass_side_length_ratio > 0) || !(m.spring_f > 0))
+      return fail(VSR_ERR_INVALID_ARGUMENT, "non-positive voxel material parameter");
+  }
+  const vsr_settings& st = d->settings;
+  if (!(st.step_frequency > 0) || st.velocity_iterations < 0 || st.position_iterations < 0)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "invalid Settings");
+  if (st.spring_mass_mode != VSR_SPRING_MASS_REDUCED && st.spring_mass_mode != VSR_SPRING_MASS_EFFECTIVE)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "unknown spring mass mode");
+
+  vsr_batch* b = new vsr_batch();
+  b->desc = *d;
+  b->precision = (int)d->precision;
+  b->n_robots = d->n_robots;
+  b->ticks = tick_times(d->final_t, st.step_frequency);
+  const int nt = (int)b->ticks.size();
+  if (nt == 0) {
+    delete b;
+    return fail(VSR_ERR_INVALID_ARGUMENT, "finalT gives no tick");
+  }
+  if (nt > 32000) {
+    delete b;
+    return fail(VSR_ERR_UNSUPPORTED, "more than 32000 ticks");
+  }
+
+  // ---- material: Voxel.assemble constants, Voxel.java:241-301
+  const double L = m.side_length, ms = L * m.mass_side_length_ratio;
+  const double density = (m.mass / 4) / (ms * ms);
+  const double bmass = density * ms * ms, binertia = bmass * (ms * ms + ms * ms) / 12.0;
+  b->inv_m = 1.0 / bmass;
+  b->inv_i = 1.0 / binertia;
+  b->half = ms / 2.0;
+  b->red_mass = bmass * bmass / (bmass + bmass);
+  {
+    double amin = sqrt(L * L * m.area_ratio_active_min), amax = sqrt(L * L * m.area_ratio_active_max);
+    double sp_min = amin - 2.0 * ms, sp_rest = L - 2.0 * ms, sp_max = amax - 2.0 * ms;
+    b->rng_min[0] = sp_min; b->rng_rest[0] = sp_rest; b->rng_max[0] = sp_max;
+    b->rng_min[1] = sqrt(ms * ms + sp_min * sp_min);
+    b->rng_rest[1] = sqrt(ms * ms + sp_rest * sp_rest);
+    b->rng_max[1] = sqrt(ms * ms + sp_max * sp_max);
+    b->rng_min[2] = (amin - ms) * sqrt(2.0);
+    b->rng_rest[2] = (L - ms) * sqrt(2.0);
+    b->rng_max[2] = (amax - ms) * sqrt(2.0);
+    for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193
+      if (b->rng_min[c] > b->rng_rest[c] || b->rng_max[c] < b->rng_rest[c] || b->rng_min[c] < 0) {
+        delete b;
+        return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
+      }
+    unsigned mask = 0;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_INTERNAL) mask |= 0x000Fu;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_EXTERNAL) mask |= 0x00F0u;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_CROSS) mask |= 0xFF00u;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_CENTRAL_CROSS) mask |= 0x30000u;
+    b->spring_mask = mask;
+  }
+
+  // ---- terrain, local frame
+  b->origin_x = d->initial_placement;
+  double miny = INFINITY;
+  for (int i = 0; i < d->terrain_n; i++) {
+    b->terr_x.push_back(d->terrain_xs[i] - b->origin_x);
+    b->terr_y.push_back(d->terrain_ys[i]);
+    miny = std::min(miny, d->terrain_ys[i]);
+  }
+  b->base_y = miny - 50.0;  // Ground.MIN_Y_THICKNESS, Ground.java:37,61
+
+  // ---- aggregator windows (AggregatorSensor.java:56-66), one table per distinct interval
+  std::vector<double> intervals;
+  b->win_first.assign((size_t)MAX_WINDOWS * nt, 0);
+  auto window_id = [&](double iv) -> int {
+    for (size_t i = 0; i < intervals.size(); i++)
+      if (intervals[i] == iv) return (int)i;
+    if ((int)intervals.size() == MAX_WINDOWS) return -1;
+    intervals.push_back(iv);
+    int id = (int)intervals.size() - 1, f = 0;
+    for (int k = 0; k < nt; k++) {
+      while (b->ticks[f] < b->ticks[k] - iv) f++;
+      b->win_first[(size_t)id * nt + k] = (int16_t)f;
+      b->ring_depth = std::max(b->ring_depth, k - f + 1);
+    }
+    return id;
+  };
+
+  // ---- shape classes
+  std::vector<Bucket> buckets((size_t)d->n_shapes);
+  for (int si = 0; si < d->n_shapes; si++) {
+    const vsr_shape& sh = d->shapes[si];
+    ShapeDev& S = buckets[si].shape;
+    memset(&S, 0, sizeof S);
+    if (sh.w <= 0 || sh.h <= 0 || !sh.mask) {
+      delete b;
+      return fail(VSR_ERR_INVALID_ARGUMENT, "invalid shape grid");
+    }
+    std::vector<int> grid((size_t)sh.w * sh.h, -1), gx, gy;
+    for (int i = 0; i < sh.w * sh.h; i++)
+      if (sh.mask[i]) {
+        grid[i] = (int)gx.size();
+        gx.push_back(i % sh.w);
+        gy.push_back(i / sh.w);
+      }
+    const int nv = (int)gx.size();
+    if (nv == 0) {
+      delete b;
+      return fail(VSR_ERR_INVALID_ARGUMENT, "robot without voxels");
+    }
+    if (nv > MAX_VOX) {
+      delete b;
+      return fail(VSR_ERR_UNSUPPORTED, "robots with more than 32 voxels are not on the accelerated path yet");
+    }
+    S.nvox = nv;
+    auto at = [&](int x, int y) { return (x < 0 || y < 0 || x >= sh.w || y >= sh.h) ? -1 : grid[(size_t)y * sh.w + x]; };
+    for (int v = 0; v < nv; v++) {
+      S.nbr[0][v] = (int8_t)at(gx[v] - 1, gy[v]);
+      S.nbr[1][v] = (int8_t)at(gx[v] + 1, gy[v]);
+      S.nbr[2][v] = (int8_t)at(gx[v], gy[v] - 1);
+      S.nbr[3][v] = (int8_t)at(gx[v], gy[v] + 1);
+    }
+    // Voxel.java:253-256 + Robot.java:99 + placement Locomotion.java:180-187
+    static const double sx[4] = {-1, +1, +1, -1}, sy[4] = {+1, +1, -1, -1};
+    const double off = L / 2.0 - ms / 2.0, h = ms / 2.0;
+    std::vector<double> X((size_t)nv * 4), Y((size_t)nv * 4);
+    double minx = INFINITY;
+    for (int v = 0; v < nv; v++)
+      for (int k = 0; k < 4; k++) {
+        X[v * 4 + k] = sx[k] * off + (double)gx[v] * L;
+        Y[v * 4 + k] = sy[k] * off + (double)gy[v] * L;
+      }
+    for (int v = 0; v < nv; v++) {
+      minx = std::min(minx, X[v * 4 + 0] - h);
+      minx = std::min(minx, X[v * 4 + 3] - h);
+    }
+    const double dx = d->initial_placement - minx;
+    for (auto& xx : X) xx += dx;
+    double min_gap = INFINITY;
+    for (int v = 0; v < nv; v++) {
+      double cx = 0, mny = INFINITY;
+      for (int k = 0; k < 4; k++) {
+        cx += X[v * 4 + k];
+        mny = std::min(mny, Y[v * 4 + k] - h);
+      }
+      cx /= 4.0;
+      min_gap = std::min(min_gap, mny - ground_y_at(d, cx));
+    }
+    if (!std::isfinite(min_gap)) {
+      delete b;
+      return fail(VSR_ERR_INVALID_ARGUMENT, "initial placement outside the ground profile");
+    }
+    const double dy = 1.0 - min_gap;  // INITIAL_PLACEMENT_Y_GAP
+    for (int i = 0; i < nv * 4; i++) {
+      S.init_x[i] = X[i] - b->origin_x;
+      S.init_y[i] = Y[i] + dy;
+    }
+    // sensors
+    int ro = 0, maxch = 0;
+    for (int v = 0; v < nv; v++) {
+      int s0 = sh.sensor_offsets ? sh.sensor_offsets[v] : 0, s1 = sh.sensor_offsets ? sh.sensor_offsets[v + 1] : 0;
+      if (s1 - s0 > MAX_SENS) {
+        delete b;
+        return fail(VSR_ERR_UNSUPPORTED, "more than 4 sensors per voxel");
+      }
+      S.n_sens[v] = (int8_t)(s1 - s0);
+      S.read_off[v] = (int16_t)ro;
+      int ch = 0, nr = 0;
+      for (int k = s0; k < s1; k++) {
+        const vsr_sensor& q = sh.sensors[k];
+        SensorDev& D = S.sens[v][k - s0];
+        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_VELOCITY || q.aggregator < VSR_AGG_NONE ||
+            q.aggregator > VSR_AGG_TREND) {
+          delete b;
+          return fail(VSR_ERR_INVALID_ARGUMENT, "unknown sensor");
+        }
+        int dim = sensor_dim(q);
+        D.base = (int8_t)q.base; D.axes = (int8_t)q.axes; D.rotated = (int8_t)(q.rotated != 0);
+        D.agg = (int8_t)q.aggregator; D.soft = (int8_t)(q.soft_norm != 0); D.dim = (int8_t)dim;
+        D.max_norm = (float)q.max_velocity_norm; D.interval = (float)q.interval;
+        D.win = 0; D.ch = 0;
+        if (q.aggregator != VSR_AGG_NONE) {
+          if (!(q.interval > 0)) {
+            delete b;
+            return fail(VSR_ERR_INVALID_ARGUMENT, "aggregator interval must be positive");
+          }
+          int wid = window_id(q.interval);
+          if (wid < 0) {
+            delete b;
+            return fail(VSR_ERR_UNSUPPORTED, "more than 2 distinct aggregator intervals");
+          }
+          D.win = (int8_t)wid;
+          D.ch = (int8_t)ch;
+          ch += dim;
+        }
+        nr += dim;
+      }
+      if (nr > MAX_READ) {
+        delete b;
+        return fail(VSR_ERR_UNSUPPORTED, "more than 6 readings per voxel");
+      }
+      ro += nr;
+      maxch = std::max(maxch, ch);
+    }
+    S.n_readings = ro;
+    S.n_channels = maxch;
+    // controller layout
+    if (d->controller_kind == VSR_CTRL_PHASE_SIN) S.n_params = 2 + nv;
+    else if (d->controller_kind == VSR_CTRL_TABULATED) S.n_params = nt * nv;
+    else {
+      if (sh.n_hidden < 0 || sh.n_hidden + 2 > MAX_LAYERS) {
+        delete b;
+        return fail(VSR_ERR_UNSUPPORTED, "too many MLP layers");
+      }
+      S.n_layers = sh.n_hidden + 2;
+      S.neurons[0] = ro;  // CentralizedSensing.nOfInputs, :68-75
+      for (int i = 0; i < sh.n_hidden; i++) S.neurons[1 + i] = sh.hidden[i];
+      S.neurons[S.n_layers - 1] = nv;  // nOfOutputs, :77-83
+      int off = 0;
+      for (int i = 1; i < S.n_layers; i++) {
+        if (S.neurons[i] <= 0) {
+          delete b;
+          return fail(VSR_ERR_INVALID_ARGUMENT, "empty MLP layer");
+        }
+        S.layer_off[i] = off;
+        off += S.neurons[i] * (S.neurons[i - 1] + 1);
+      }
+      S.n_params = off;  // MultiLayerPerceptron.countWeights, :106-112
+    }
+  }
+  for (auto& k : buckets) k.shape.ring_depth = b->ring_depth;
+
+  // ---- robots -> buckets, parameters -> device layout
+  b->robot_bucket.resize(b->n_robots);
+  b->robot_pos.resize(b->n_robots);
+  b->robot_nvox.resize(b->n_robots);
+  for (size_t r = 0; r < b->n_robots; r++) {
+    int si = d->robot_shape ? d->robot_shape[r] : 0;
+    if (si < 0 || si >= d->n_shapes) {
+      delete b;
+      return fail(VSR_ERR_INVALID_ARGUMENT, "robot_shape out of range");
+    }
+    Bucket& k = buckets[si];
+    const ShapeDev& S = k.shape;
+    size_t np = d->param_offsets[r + 1] - d->param_offsets[r];
+    if (np != (size_t)S.n_params) {
+      delete b;
+      char msg[256];
+      if (d->controller_kind == VSR_CTRL_MLP)  // MultiLayerPerceptron.java:56-62
+        snprintf(msg, sizeof msg, "Wrong number of weights: %d expected, %zu found", S.n_params, np);
+      else
+        snprintf(msg, sizeof msg, "robot %zu: %d controller parameters expected, %zu found", r, S.n_params, np);
+      return fail(VSR_ERR_INVALID_ARGUMENT, msg);
+    }
+    const double* P = d->params + d->param_offsets[r];
+    b->robot_bucket[r] = si;
+    b->robot_pos[r] = (int)k.robot_ids.size();
+    b->robot_nvox[r] = S.nvox;
+    k.robot_ids.push_back((int)r);
+    if ((size_t)r < d->trajectory_robots) k.traj_robots++;
+    size_t base = k.params.size();
+    k.params.resize(base + np);
+    if (d->controller_kind == VSR_CTRL_MLP) {
+      // Java flat order [layer][neuron][bias, w_1..w_np] -> [layer][k][neuron] so that
+      // consecutive lanes (neurons) read consecutive addresses
+      size_t c = 0;
+      for (int i = 1; i < S.n_layers; i++) {
+        int nn = S.neurons[i], npv = S.neurons[i - 1] + 1;
+        for (int j = 0; j < nn; j++)
+          for (int q = 0; q < npv; q++) k.params[base + S.layer_off[i] + (size_t)q * nn + j] = P[c++];
+      }
+    } else {
+      for (size_t q = 0; q < np; q++) k.params[base + q] = P[q];
+    }
+    b->voxel_steps += (size_t)S.nvox * (size_t)nt;
+  }
+  for (auto& k : buckets)
+    if (!k.robot_ids.empty()) b->buckets.push_back(std::move(k));
+  // invalidate the caller's pointers in our copy of the descriptor
+  b->desc.shapes = nullptr; b->desc.robot_shape = nullptr; b->desc.params = nullptr;
+  b->desc.param_offsets = nullptr; b->desc.terrain_xs = nullptr; b->desc.terrain_ys = nullptr;
+  *out = b;
+  return VSR_OK;
+}
+
+template <typename real>
+static int upload_array(const std::vector<double>& src, void** dst, cudaStream_t s, size_t* bytes) {
+  std::vector<real> tmp(src.begin(), src.end());
+  CUDA_TRY(cudaMalloc(dst, std::max<size_t>(1, tmp.size()) * sizeof(real)));
+  if (!tmp.empty()) {
+    CUDA_TRY(cudaMemcpyAsync(*dst, tmp.data(), tmp.size() * sizeof(real), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // tmp is a local
+  }
+  *bytes += tmp.size() * sizeof(real);
+  return VSR_OK;
+}
+
+extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
+  if (!b) return fail(VSR_ERR_INVALID_ARGUMENT, "null batch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(VSR_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(VSR_ERR_INVALID_ARGUMENT, "device out of range");
+  if (b->uploaded) free_device(b);
+  CUDA_TRY(cudaSetDevice(device));
+  b->device = device;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool f64 = b->precision == VSR_PRECISION_F64;
+  const size_t esz = f64 ? 8 : 4;
+  const int nt = (int)b->ticks.size();
+  b->upload_bytes = 0;
+  CUDA_TRY(cudaMalloc((void**)&b->d_ticks, nt * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(b->d_ticks, b->ticks.data(), nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMalloc((void**)&b->d_win, b->win_first.size() * sizeof(int16_t)));
+  CUDA_TRY(cudaMemcpyAsync(b->d_win, b->win_first.data(), b->win_first.size() * sizeof(int16_t),
+                           cudaMemcpyHostToDevice, s));
+  b->upload_bytes += nt * sizeof(double) + b->win_first.size() * sizeof(int16_t);
+  int rc;
+  if (f64) {
+    if ((rc = upload_array<double>(b->terr_x, &b->d_terr_x, s, &b->upload_bytes))) return rc;
+    if ((rc = upload_array<double>(b->terr_y, &b->d_terr_y, s, &b->upload_bytes))) return rc;
+  } else {
+    if ((rc = upload_array<float>(b->terr_x, &b->d_terr_x, s, &b->upload_bytes))) return rc;
+    if ((rc = upload_array<float>(b->terr_y, &b->d_terr_y, s, &b->upload_bytes))) return rc;
+  }
+  CUDA_TRY(cudaMalloc((void**)&b->d_results, b->n_robots * sizeof(vsr_result)));
+  CUDA_TRY(cudaMemsetAsync(b->d_results, 0, b->n_robots * sizeof(vsr_result), s));
+  for (auto& k : b->buckets) {
+    const size_t nr = k.robot_ids.size();
+    CUDA_TRY(cudaMalloc((void**)&k.d_shape, sizeof(ShapeDev)));
+    CUDA_TRY(cudaMemcpyAsync(k.d_shape, &k.shape, sizeof(ShapeDev), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMalloc((void**)&k.d_ids, nr * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(k.d_ids, k.robot_ids.data(), nr * sizeof(int), cudaMemcpyHostToDevice, s));
+    b->upload_bytes += sizeof(ShapeDev) + nr * sizeof(int);
+    if (f64) rc = upload_array<double>(k.params, &k.d_params, s, &b->upload_bytes);
+    else rc = upload_array<float>(k.params, &k.d_params, s, &b->upload_bytes);
+    if (rc) return rc;
+    size_t ring = (size_t)k.shape.ring_depth * (size_t)std::max(1, k.shape.n_channels) * nr * (size_t)k.shape.nvox;
+    CUDA_TRY(cudaMalloc(&k.d_ring, ring * esz));
+    if (k.traj_robots > 0) {
+      size_t tb = (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz;
+      CUDA_TRY(cudaMalloc(&k.d_traj, tb));
+      CUDA_TRY(cudaMemsetAsync(k.d_traj, 0, tb, s));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  b->uploaded = true;
+  b->ran = false;
+  return VSR_OK;
+}
+
+template <typename real>
+static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
+  const vsr_batch_desc& d = b->desc;
+  const vsr_settings& st = d.settings;
+  const vsr_material& m = d.material;
+  Params<real> P;
+  memset(&P, 0, sizeof P);
+  P.shape = k.d_shape;
+  P.n_robots = (long long)k.robot_ids.size();
+  P.robot_ids = k.d_ids;
+  P.params = (const real*)k.d_params;
+  P.results = b->d_results;
+  P.ring = (real*)k.d_ring;
+  P.trajectory = (real*)k.d_traj;
+  P.traj_robots = k.traj_robots;
+  P.n_ticks = (int)b->ticks.size();
+  P.tick_t = b->d_ticks;
+  P.win_first = b->d_win;
+  P.terr_x = (const real*)b->d_terr_x;
+  P.terr_y = (const real*)b->d_terr_y;
+  P.terr_n = (int)b->terr_x.size();
+  P.base_y = (real)b->base_y;
+  P.origin_x = b->origin_x;
+  P.dt = (real)st.step_frequency;
+  P.grav_x = (real)st.gravity_x;
+  P.grav_y = (real)st.gravity_y;
+  P.lin_damp = (real)m.mass_linear_damping;
+  P.ang_damp = (real)m.mass_angular_damping;
+  P.inv_m = (real)b->inv_m;
+  P.inv_i = (real)b->inv_i;
+  P.half = (real)b->half;
+  P.side = (real)m.side_length;
+  P.lin_tol = (real)st.linear_tolerance;
+  P.ang_tol = (real)st.angular_tolerance;
+  P.max_corr = (real)st.max_linear_correction;
+  P.baumgarte = (real)st.baumgarte;
+  P.rest_vel = (real)st.restitution_velocity;
+  P.max_trans = (real)st.max_translation;
+  P.max_rot = (real)st.max_rotation;
+  P.mu = (real)sqrt(m.friction * st.ground_friction);               // CoefficientMixer: sqrt(f1 f2)
+  P.rest_e = (real)std::max(m.restitution, st.ground_restitution);  // max(e1, e2)
+  P.spring_w = (real)(2.0 * M_PI * m.spring_f);
+  P.spring_zeta = (real)m.spring_d;
+  P.red_mass = (real)b->red_mass;
+  for (int c = 0; c < 3; c++) {
+    P.rng_min[c] = (real)b->rng_min[c];
+    P.rng_rest[c] = (real)b->rng_rest[c];
+    P.rng_max[c] = (real)b->rng_max[c];
+  }
+  P.weld_len = (real)(2.0 * b->half);
+  P.vel_iters = st.velocity_iterations;
+  P.pos_iters = st.position_iterations;
+  P.spring_mode = st.spring_mass_mode;
+  P.spring_mask = b->spring_mask;
+  P.mlp_act = d.mlp_activation;
+  const int nvox = k.shape.nvox, G = 32 / nvox;
+  int maxn = 1;
+  for (int i = 0; i < k.shape.n_layers; i++) maxn = std::max(maxn, k.shape.neurons[i]);
+  int per_robot = 2 * ((maxn + 3) & ~3);
+  P.smem_per_warp = std::max(128, per_robot * G);
+  const int threads = 128, wpb = threads / 32;
+  const size_t smem = (size_t)wpb * P.smem_per_warp * sizeof(real);
+  void (*kern)(const Params<real>) = nullptr;
+  switch (d.controller_kind) {
+    case VSR_CTRL_PHASE_SIN: kern = vsr_episode_kernel<real, CTRL_PHASE_SIN>; break;
+    case VSR_CTRL_TABULATED: kern = vsr_episode_kernel<real, CTRL_TABULATED>; break;
+    default: kern = vsr_episode_kernel<real, CTRL_MLP>; break;
+  }
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0, sms = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+  if (occ < 1) return fail(VSR_ERR_CUDA, "episode kernel does not fit on an SM");
+  const long long groups = (P.n_robots + G - 1) / G;
+  const long long want = (groups + wpb - 1) / wpb;
+  // persistent grid: one wave of resident blocks (a multiple of the SM count), each warp
+  // strides over robot groups
+  const long long grid = std::max<long long>(1, std::min<long long>(want, (long long)occ * sms));
+  kern<<<(unsigned)grid, threads, smem, s>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  b->last_launches++;
+  return VSR_OK;
+}
+
+extern "C" int vsr_batch_run(vsr_batch* b, void* stream) {
+  if (!b) return fail(VSR_ERR_INVALID_ARGUMENT, "null batch");
+  if (!b->uploaded) return fail(VSR_ERR_STATE, "vsr_batch_run before vsr_batch_upload");
+  CUDA_TRY(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b->run_stream = s;
+  b->last_launches = 0;
+  for (auto& k : b->buckets) {
+    int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, s) : launch_bucket<float>(b, k, s);
+    if (rc) return rc;
+  }
+  b->ran = true;
+  return VSR_OK;
+}
+
+extern "C" int vsr_batch_results(vsr_batch* b, vsr_result* out, size_t n) {
+  if (!b || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->ran) return fail(VSR_ERR_STATE, "vsr_batch_results before vsr_batch_run");
+  if (n != b->n_robots) return fail(VSR_ERR_INVALID_ARGUMENT, "result count differs from n_robots");
+  static_assert(sizeof(vsr_result) == 11 * sizeof(double), "vsr_result layout");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaMemcpyAsync(out, b->d_results, n * sizeof(vsr_result), cudaMemcpyDeviceToHost, b->run_stream));
+  CUDA_TRY(cudaStreamSynchronize(b->run_stream));
+  return VSR_OK;
+}
+
+extern "C" int vsr_batch_results_device(vsr_batch* b, void** dptr, size_t* bytes) {
+  if (!b || !dptr) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->uploaded) return fail(VSR_ERR_STATE, "not uploaded");
+  *dptr = b->d_results;
+  if (bytes) *bytes = b->n_robots * sizeof(vsr_result);
+  return VSR_OK;
+}
+
+extern "C" long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* out, size_t capacity) {
+  if (!b || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->ran) return fail(VSR_ERR_STATE, "vsr_batch_trajectory before vsr_batch_run");
+  if (robot >= b->n_robots || robot >= b->desc.trajectory_robots)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "robot has no recorded trajectory");
+  // buckets were compacted after create: find the one holding this robot
+  Bucket* kb = nullptr;
+  int pos = -1;
+  for (auto& k : b->buckets)
+    for (size_t i = 0; i < k.robot_ids.size() && (long long)i < k.traj_robots; i++)
+      if ((size_t)k.robot_ids[i] == robot) {
+        kb = &k;
+        pos = (int)i;
+      }
+  if (!kb) return fail(VSR_ERR_STATE, "trajectory bucket not found");
+  const int nt = (int)b->ticks.size();
+  const size_t n = (size_t)nt * kb->shape.nvox * 4 * 6;
+  if (capacity < n) return fail(VSR_ERR_INVALID_ARGUMENT, "trajectory buffer too small");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->run_stream));
+  if (b->precision == VSR_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(out, (double*)kb->d_traj + (size_t)pos * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), (float*)kb->d_traj + (size_t)pos * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+  }
+  // world frame
+  for (size_t i = 0; i < n; i += 6) out[i] += b->origin_x;
+  return (long long)n;
+}
+
+extern "C" size_t vsr_batch_voxel_steps(const vsr_batch* b) { return b ? b->voxel_steps : 0; }
+extern "C" int vsr_batch_n_ticks(const vsr_batch* b) { return b ? (int)b->ticks.size() : 0; }
+extern "C" int vsr_batch_n_bodies(const vsr_batch* b, size_t robot) {
+  if (!b || robot >= b->n_robots) return 0;
+  return 4 * b->robot_nvox[robot];
+}
+extern "C" int vsr_batch_last_launches(const vsr_batch* b) { return b ? b->last_launches : 0; }
+extern "C" size_t vsr_batch_upload_bytes(const vsr_batch* b) { return b ? b->upload_bytes : 0; }

@@ -1,0 +1,1102 @@
+// vsr_device.cuh -- the episode kernel of the B200-native batched VSR stepper.
+//
+// Replaces, for N independent robots at once, the per-tick path
+//   AbstractTask.updateWorld (tasks/AbstractTask.java:41-64):
+//     World.step(1)  [org.dyn4j 4.2.1]  +  Robot.act(t) (core/objects/Robot.java:73-77)
+// inside Locomotion.apply's loop (tasks/locomotion/Locomotion.java:196-203).
+//
+// Mapping:
+//   * one LANE per voxel, floor(32 / n_voxels) robots per warp, a warp runs the whole
+//     episode (all ticks) of its robots; no block-level synchronisation at all;
+//   * the 4 masses of a voxel (pose + velocity) and its 18 spring-dampers
+//     (Voxel.java:239-479) live in that lane's registers: the 18 soft DistanceJoint
+//     solves of a velocity iteration are pure register arithmetic, fully unrolled;
+//   * the rigid WeldJoints between neighbouring voxels (Robot.java:91-114) are solved
+//     redundantly by both lanes after exchanging the partner mass' state with warp
+//     shuffles: first all left/right welds, then all up/down welds (each mass has at
+//     most one of each => a 2-colouring);
+//   * ground contact (Ground.java:64-70 polygons) is per mass: SAT + clipping manifold,
+//     sequential impulses with the 2-point block solver, Baumgarte position pass;
+//   * sensors (Touch/AreaRatio/Velocity with Average/Trend windows and
+//     SoftNormalization) and controllers (PhaseSin, tabulated TimeFunctions, per-robot
+//     MLP) run in the same kernel right after the step.
+// The resulting Gauss-Seidel order (springs -> horizontal welds -> vertical welds ->
+// contacts) is the oracle's VSR_ORACLE_ORDER_CANONICAL.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsr {
+
+constexpr int MAX_VOX = 32;    // voxels per robot on the one-warp path
+constexpr int MAX_SENS = 4;    // sensors per voxel
+constexpr int MAX_READ = 6;    // readings per voxel
+constexpr int MAXC = 2;        // simultaneous ground constraints per mass
+constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
+constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
+
+enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
+enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2 };
+enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
+enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2 };
+
+struct SensorDev {
+  int8_t base, axes, rotated, agg, soft, win, ch, dim;
+  float max_norm;
+  float interval;
+};
+
+// One shape class (Grid<Boolean> + sensor layout), compiled on the host.
+struct ShapeDev {
+  int nvox;
+  int n_readings;  // CentralizedSensing.nOfInputs
+  int n_channels;  // aggregator ring channels per voxel
+  int ring_depth;
+  int8_t nbr[4][MAX_VOX];  // neighbour voxel index: left, right, down, up (-1 = none)
+  double init_x[MAX_VOX * 4], init_y[MAX_VOX * 4];  // placed masses, local frame
+  int8_t n_sens[MAX_VOX];
+  int16_t read_off[MAX_VOX];
+  SensorDev sens[MAX_VOX][MAX_SENS];
+  int n_layers;
+  int neurons[MAX_LAYERS];
+  int layer_off[MAX_LAYERS];  // offset of layer i's (transposed) weights
+  int n_params;               // controller parameters per robot (device layout)
+};
+
+template <typename real>
+struct Params {
+  const ShapeDev* shape;
+  // robots of this bucket
+  long long n_robots;
+  const int* robot_ids;       // bucket index -> batch index
+  const real* params;         // [n_robots][n_params] (bucket order)
+  double* results;            // vsr_result records, batch order (11 doubles each)
+  real* ring;                 // [ring_depth][n_channels][n_robots * nvox]
+  real* trajectory;           // [traj_robots][n_ticks][nvox*4][6], bucket order, or null
+  long long traj_robots;
+  // time
+  int n_ticks;
+  const double* tick_t;       // [n_ticks] accumulated t
+  const int16_t* win_first;   // [MAX_WINDOWS][n_ticks] oldest kept tick
+  // terrain (local frame: x - origin_x)
+  const real* terr_x;
+  const real* terr_y;
+  int terr_n;
+  real base_y;
+  double origin_x;
+  // settings / material
+  real dt, grav_x, grav_y, lin_damp, ang_damp;
+  real inv_m, inv_i, half, side;
+  real lin_tol, ang_tol, max_corr, baumgarte, rest_vel, max_trans, max_rot;
+  real mu, rest_e;
+  real spring_w, spring_zeta, red_mass;
+  real rng_min[3], rng_rest[3], rng_max[3];  // side-parallel, side-cross, central-cross
+  real weld_len;                             // |localAnchor2| = mass side
+  int vel_iters, pos_iters;
+  int spring_mode;       // 0 reduced mass, 1 effective mass
+  unsigned spring_mask;  // bit s = spring s present (scaffoldings)
+  int mlp_act;
+  int smem_per_warp;     // reals of staging per warp
+};
+
+// ---------------------------------------------------------------- math wrappers
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ void r_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void r_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float r_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double r_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float r_exp(float x) { return expf(x); }
+__device__ __forceinline__ double r_exp(double x) { return exp(x); }
+__device__ __forceinline__ float r_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double r_sin(double x) { return sin(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
+template <typename real>
+__device__ __forceinline__ real r_clamp(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }
+
+template <typename real>
+__device__ __forceinline__ real shfl(real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// ---------------------------------------------------------------- contacts (per mass)
+template <typename real>
+struct CPoint {
+  real px, py, depth, jn, jt;  // persistent (warm start by id)
+  int id;
+  real r1x, r1y, l1x, l1y, massN, massT, vb;  // per step
+};
+template <typename real>
+struct CCon {
+  int seg, n, block;
+  real nx, ny;  // manifold normal: from the mass to the ground
+  CPoint<real> p[2];
+  real K00, K01, K11, iK00, iK01, iK11;
+};
+template <typename real>
+struct CBody {
+  int n;
+  CCon<real> c[MAXC];
+};
+
+template <typename real>
+struct Poly4 {
+  real vx[4], vy[4], nx[4], ny[4];
+};
+template <typename real>
+struct Edge {
+  real x1, y1, x2, y2, mx, my;
+  int i1, i2, index;
+};
+
+// Polygon.getFarthestFeature (dyn4j): farthest vertex along n, then the adjacent edge
+// that is most perpendicular to n, CCW winding kept.
+template <typename real>
+__device__ void farthest_edge(const Poly4<real>& P, real nx, real ny, Edge<real>& e) {
+  int idx = 0;
+  real best = P.vx[0] * nx + P.vy[0] * ny;
+#pragma unroll
+  for (int i = 1; i < 4; i++) {
+    real v = P.vx[i] * nx + P.vy[i] * ny;
+    if (v > best) {
+      best = v;
+      idx = i;
+    }
+  }
+  int prev = (idx + 3) & 3, next = (idx + 1) & 3;
+  real ln = P.nx[prev] * nx + P.ny[prev] * ny;
+  real rn = P.nx[idx] * nx + P.ny[idx] * ny;
+  e.mx = P.vx[idx];
+  e.my = P.vy[idx];
+  if (ln < rn) {
+    e.x1 = P.vx[idx]; e.y1 = P.vy[idx]; e.i1 = idx;
+    e.x2 = P.vx[next]; e.y2 = P.vy[next]; e.i2 = next;
+    e.index = idx + 1;
+  } else {
+    e.x1 = P.vx[prev]; e.y1 = P.vy[prev]; e.i1 = prev;
+    e.x2 = P.vx[idx]; e.y2 = P.vy[idx]; e.i2 = idx;
+    e.index = idx;
+  }
+}
+
+template <typename real>
+struct ClipPt {
+  real x, y;
+  int idx;
+};
+
+// ClippingManifoldSolver.clip (dyn4j)
+template <typename real>
+__device__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx, real ny, real offset,
+                         ClipPt<real>* out) {
+  int n = 0;
+  real d1 = nx * v1.x + ny * v1.y - offset, d2 = nx * v2.x + ny * v2.y - offset;
+  if (d1 <= real(0)) out[n++] = v1;
+  if (d2 <= real(0)) out[n++] = v2;
+  if (d1 * d2 < real(0)) {
+    real u = d1 / (d1 - d2);
+    ClipPt<real> p;
+    p.x = v1.x + (v2.x - v1.x) * u;
+    p.y = v1.y + (v2.y - v1.y) * u;
+    p.idx = d1 > real(0) ? v1.idx : v2.idx;
+    if (n < 2) out[n++] = p;
+  }
+  return n;
+}
+
+// Narrowphase (SAT == the EPA answer for two convex polygons) + clipping manifold for
+// one mass against one ground segment.  Returns 1 and fills c (n, normal, points) on
+// collision.
+template <typename real>
+__device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real bs, real half, real x0, real y0,
+                                                 real x1, real y1, real base_y, CCon<real>& c) {
+  Poly4<real> A, B;
+  const real lx[4] = {-1, 1, 1, -1}, ly[4] = {-1, -1, 1, 1};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    real px = lx[i] * half, py = ly[i] * half;
+    A.vx[i] = bx + bc * px - bs * py;
+    A.vy[i] = by + bs * px + bc * py;
+  }
+  A.nx[0] = bs; A.ny[0] = -bc;
+  A.nx[1] = bc; A.ny[1] = bs;
+  A.nx[2] = -bs; A.ny[2] = bc;
+  A.nx[3] = -bc; A.ny[3] = -bs;
+  B.vx[0] = x0; B.vy[0] = y0;
+  B.vx[1] = x0; B.vy[1] = base_y;
+  B.vx[2] = x1; B.vy[2] = base_y;
+  B.vx[3] = x1; B.vy[3] = y1;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int j = (i + 1) & 3;
+    real ex = B.vx[j] - B.vx[i], ey = B.vy[j] - B.vy[i];
+    real l = r_sqrt(ex * ex + ey * ey);
+    B.nx[i] = ey / l;
+    B.ny[i] = -ex / l;
+  }
+  // SAT: least-negative separation over the face normals of both polygons
+  real best = -1e30f, nx = 0, ny = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    real s = 1e30f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      real v = A.nx[i] * (B.vx[j] - A.vx[i]) + A.ny[i] * (B.vy[j] - A.vy[i]);
+      s = v < s ? v : s;
+    }
+    if (s > best) { best = s; nx = A.nx[i]; ny = A.ny[i]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    real s = 1e30f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      real v = B.nx[j] * (A.vx[i] - B.vx[j]) + B.ny[j] * (A.vy[i] - B.vy[j]);
+      s = v < s ? v : s;
+    }
+    if (s > best) { best = s; nx = -B.nx[j]; ny = -B.ny[j]; }
+  }
+  if (!(best < real(0))) return 0;
+  // ClippingManifoldSolver.getManifold (dyn4j)
+  Edge<real> ref, inc;
+  farthest_edge(A, nx, ny, ref);
+  farthest_edge(B, -nx, -ny, inc);
+  int flipped = 0;
+  real e1 = r_abs((ref.x2 - ref.x1) * nx + (ref.y2 - ref.y1) * ny);
+  real e2 = r_abs((inc.x2 - inc.x1) * nx + (inc.y2 - inc.y1) * ny);
+  if (e1 > e2) {
+    Edge<real> t = ref; ref = inc; inc = t;
+    flipped = 1;
+  }
+  real rx = ref.x2 - ref.x1, ry = ref.y2 - ref.y1;
+  real rl = r_sqrt(rx * rx + ry * ry);
+  rx /= rl;
+  ry /= rl;
+  ClipPt<real> a = {inc.x1, inc.y1, inc.i1}, b = {inc.x2, inc.y2, inc.i2}, c1[3], c2[3];
+  real o1 = -(rx * ref.x1 + ry * ref.y1);
+  if (clip_edge(a, b, -rx, -ry, o1, c1) < 2) return 0;
+  real o2 = rx * ref.x2 + ry * ref.y2;
+  if (clip_edge(c1[0], c1[1], rx, ry, o2, c2) < 2) return 0;
+  real fx = -ry, fy = rx;
+  real fo = fx * ref.mx + fy * ref.my;
+  c.nx = flipped ? fx : -fx;
+  c.ny = flipped ? fy : -fy;
+  c.n = 0;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    real depth = fx * c2[i].x + fy * c2[i].y - fo;
+    if (depth >= real(0)) {
+      CPoint<real>& p = c.p[c.n++];
+      p.px = c2[i].x;
+      p.py = c2[i].y;
+      p.depth = depth;
+      p.jn = 0;
+      p.jt = 0;
+      p.id = (ref.index & 7) | ((inc.index & 7) << 3) | ((c2[i].idx & 7) << 6) | (flipped << 9);
+    }
+  }
+  return c.n > 0;
+}
+
+// World.detect (dyn4j) for one mass: every ground segment its AABB overlaps; impulses of
+// points with the same id are carried over (ContactConstraint.update).
+template <typename real>
+__device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by, real bth, int& hint, CBody<real>& cb) {
+  real bs, bc;
+  r_sincos(bth, &bs, &bc);
+  real e = P.half * (r_abs(bc) + r_abs(bs));
+  real xlo = bx - e, xhi = bx + e, ylo = by - e;
+  int n = P.terr_n;
+  int s = hint;
+  while (s > 0 && P.terr_x[s] > xlo) --s;
+  while (s + 2 < n && P.terr_x[s + 1] < xlo) ++s;
+  hint = s;
+  const int old_n = cb.n;
+  CBody<real> old;
+  old.n = 0;
+  if (old_n > 0) old = cb;  // only masses already in contact need the warm-start match
+  cb.n = 0;
+  int overflow = 0;
+  for (int seg = s; seg + 1 < n && P.terr_x[seg] <= xhi; ++seg) {
+    real x0 = P.terr_x[seg], x1 = P.terr_x[seg + 1], y0 = P.terr_y[seg], y1 = P.terr_y[seg + 1];
+    if (x1 < xlo) continue;
+    if (!(x1 > x0)) continue;
+    if (ylo > r_max(y0, y1)) continue;
+    CCon<real> c;
+    if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, c)) continue;
+    if (cb.n == MAXC) { overflow = 1; break; }
+    c.seg = seg;
+    for (int i = 0; i < old.n; i++) {
+      if (old.c[i].seg != seg) continue;
+      for (int k = 0; k < c.n; k++)
+        for (int l = 0; l < old.c[i].n; l++)
+          if (old.c[i].p[l].id == c.p[k].id) {
+            c.p[k].jn = old.c[i].p[l].jn;
+            c.p[k].jt = old.c[i].p[l].jt;
+          }
+    }
+    cb.c[cb.n++] = c;
+  }
+  return overflow;
+}
+
+template <typename real>
+struct BodyState {
+  real x, y, th, vx, vy, w;
+};
+
+// SequentialImpulses.initialize (dyn4j) for the constraints of one mass (the ground is
+// static: invM2 = invI2 = 0), followed by their warm start.
+template <typename real>
+__device__ __noinline__ void contact_init_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
+  real bs, bc;
+  r_sincos(B.th, &bs, &bc);
+  const real im = P.inv_m, ii = P.inv_i;
+  for (int q = 0; q < cb.n; q++) {
+    CCon<real>& c = cb.c[q];
+    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+    for (int k = 0; k < c.n; k++) {
+      CPoint<real>& p = c.p[k];
+      p.r1x = p.px - B.x;
+      p.r1y = p.py - B.y;
+      p.l1x = bc * p.r1x + bs * p.r1y;
+      p.l1y = -bs * p.r1x + bc * p.r1y;
+      real rn1 = p.r1x * ny - p.r1y * nx;
+      p.massN = real(1) / (im + ii * rn1 * rn1);
+      real rt1 = p.r1x * ty - p.r1y * tx;
+      p.massT = real(1) / (im + ii * rt1 * rt1);
+      real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+      real rvn = nx * rvx + ny * rvy;
+      p.vb = real(0);
+      if (rvn < -P.rest_vel) p.vb += -P.rest_e * rvn;
+    }
+    c.block = 0;
+    if (c.n == 2) {
+      real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx;
+      real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx;
+      c.K00 = im + ii * rn1A * rn1A;
+      c.K01 = im + ii * rn1A * rn2A;
+      c.K11 = im + ii * rn2A * rn2A;
+      real det = c.K00 * c.K11 - c.K01 * c.K01;
+      if (c.K00 * c.K00 < real(1000) * det) {
+        c.block = 1;
+        real id = real(1) / det;
+        c.iK00 = id * c.K11;
+        c.iK01 = -id * c.K01;
+        c.iK11 = id * c.K00;
+      } else {
+        c.n = 1;
+      }
+    }
+  }
+  // the oracle warm-starts after ALL constraints are initialised; for one mass against a
+  // static ground the initialisation of other masses does not read this mass' velocity,
+  // so doing it per mass is identical -- but all constraints of THIS mass first.
+  for (int q = 0; q < cb.n; q++) {
+    CCon<real>& c = cb.c[q];
+    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+    for (int k = 0; k < c.n; k++) {
+      CPoint<real>& p = c.p[k];
+      real Px = nx * p.jn + tx * p.jt, Py = ny * p.jn + ty * p.jt;
+      B.vx -= im * Px;
+      B.vy -= im * Py;
+      B.w -= ii * (p.r1x * Py - p.r1y * Px);
+    }
+  }
+}
+
+// SequentialImpulses.solveVelocityConstraints (dyn4j) for the constraints of one mass.
+template <typename real>
+__device__ __noinline__ void contact_solve_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
+  const real im = P.inv_m, ii = P.inv_i;
+  for (int q = 0; q < cb.n; q++) {
+    CCon<real>& c = cb.c[q];
+    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+    for (int k = 0; k < c.n; k++) {
+      CPoint<real>& p = c.p[k];
+      real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+      real tn = tx * rvx + ty * rvy;
+      real jt = p.massT * (-tn);
+      real maxJt = P.mu * p.jn;
+      real Jt0 = p.jt;
+      p.jt = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
+      jt = p.jt - Jt0;
+      real Px = tx * jt, Py = ty * jt;
+      B.vx -= im * Px;
+      B.vy -= im * Py;
+      B.w -= ii * (p.r1x * Py - p.r1y * Px);
+    }
+    if (c.n == 1 || !c.block) {
+      for (int k = 0; k < c.n; k++) {
+        CPoint<real>& p = c.p[k];
+        real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+        real rvn = nx * rvx + ny * rvy;
+        real j = -p.massN * (rvn - p.vb);
+        real j0 = p.jn;
+        p.jn = r_max(j0 + j, real(0));
+        j = p.jn - j0;
+        real Px = nx * j, Py = ny * j;
+        B.vx -= im * Px;
+        B.vy -= im * Py;
+        B.w -= ii * (p.r1x * Py - p.r1y * Px);
+      }
+    } else {
+      CPoint<real>& p1 = c.p[0];
+      CPoint<real>& p2 = c.p[1];
+      real ax = p1.jn, ay = p2.jn;
+      real rvx = -(B.vx - B.w * p1.r1y), rvy = -(B.vy + B.w * p1.r1x);
+      real rvn1 = nx * rvx + ny * rvy;
+      rvx = -(B.vx - B.w * p2.r1y);
+      rvy = -(B.vy + B.w * p2.r1x);
+      real rvn2 = nx * rvx + ny * rvy;
+      real bx = rvn1 - p1.vb, by = rvn2 - p2.vb;
+      bx -= c.K00 * ax + c.K01 * ay;
+      by -= c.K01 * ax + c.K11 * ay;
+      real x = -(c.iK00 * bx + c.iK01 * by), y = -(c.iK01 * bx + c.iK11 * by);
+      bool ok = (x >= real(0) && y >= real(0));
+      if (!ok) {
+        x = -p1.massN * bx;
+        y = real(0);
+        real v2 = c.K01 * x + by;
+        ok = (x >= real(0) && v2 >= real(0));
+      }
+      if (!ok) {
+        x = real(0);
+        y = -p2.massN * by;
+        real v1 = c.K01 * y + bx;
+        ok = (y >= real(0) && v1 >= real(0));
+      }
+      if (!ok) {
+        x = real(0);
+        y = real(0);
+        ok = (bx >= real(0) && by >= real(0));
+      }
+      if (ok) {
+        real dx = x - ax, dy = y - ay;
+        real Px = nx * dx, Py = ny * dx;
+        B.vx -= im * Px;
+        B.vy -= im * Py;
+        B.w -= ii * (p1.r1x * Py - p1.r1y * Px);
+        Px = nx * dy;
+        Py = ny * dy;
+        B.vx -= im * Px;
+        B.vy -= im * Py;
+        B.w -= ii * (p2.r1x * Py - p2.r1y * Px);
+        p1.jn = x;
+        p2.jn = y;
+      }
+    }
+  }
+}
+
+// SequentialImpulses.solvePositionContraints (dyn4j) for one mass; returns min separation.
+template <typename real>
+__device__ __noinline__ real contact_position_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
+  const real im = P.inv_m, ii = P.inv_i;
+  real minSep = real(0);
+  for (int q = 0; q < cb.n; q++) {
+    CCon<real>& c = cb.c[q];
+    real nx = c.nx, ny = c.ny;
+    for (int k = 0; k < c.n; k++) {
+      CPoint<real>& p = c.p[k];
+      real bs, bc;
+      r_sincos(B.th, &bs, &bc);
+      real r1x = bc * p.l1x - bs * p.l1y, r1y = bs * p.l1x + bc * p.l1y;
+      real p1x = B.x + r1x, p1y = B.y + r1y;
+      real sep = (p.px - p1x) * nx + (p.py - p1y) * ny - p.depth;
+      minSep = sep < minSep ? sep : minSep;
+      real cl = r_clamp<real>(sep + P.lin_tol, -P.max_corr, real(0));
+      real cp = P.baumgarte * cl;
+      real rn1 = r1x * ny - r1y * nx;
+      real K = im + ii * rn1 * rn1;
+      real jp = -cp / K;
+      real Jx = nx * jp, Jy = ny * jp;
+      B.x -= Jx * im;
+      B.y -= Jy * im;
+      B.th -= ii * (r1x * Jy - r1y * Jx);
+    }
+  }
+  return minSep;
+}
+
+// ---------------------------------------------------------------- springs
+// The 18 DistanceJoints of a voxel in `allSpringJoints` order (Voxel.java:303-470):
+// X(index, body1, body2, anchor1 sign x,y, anchor2 sign x,y, range class)
+#define VSR_SPRINGS(X)               \
+  X(0, 0, 1, +1, -1, -1, -1, 0)      \
+  X(1, 1, 2, -1, -1, -1, +1, 0)      \
+  X(2, 2, 3, -1, +1, +1, +1, 0)      \
+  X(3, 3, 0, +1, +1, +1, -1, 0)      \
+  X(4, 0, 1, +1, +1, -1, +1, 0)      \
+  X(5, 1, 2, +1, -1, +1, +1, 0)      \
+  X(6, 2, 3, -1, -1, +1, -1, 0)      \
+  X(7, 3, 0, -1, +1, -1, -1, 0)      \
+  X(8, 0, 1, +1, +1, -1, -1, 1)      \
+  X(9, 0, 1, +1, -1, -1, +1, 1)      \
+  X(10, 1, 2, +1, -1, -1, +1, 1)     \
+  X(11, 1, 2, -1, -1, +1, +1, 1)     \
+  X(12, 2, 3, -1, +1, +1, -1, 1)     \
+  X(13, 2, 3, -1, -1, +1, +1, 1)     \
+  X(14, 3, 0, -1, +1, +1, -1, 1)     \
+  X(15, 3, 0, +1, +1, -1, -1, 1)     \
+  X(16, 0, 2, 0, 0, 0, 0, 2)         \
+  X(17, 1, 3, 0, 0, 0, 0, 2)
+
+template <typename real>
+__device__ __forceinline__ real activation(int a, real x) {
+  switch (a) {
+    case 0: return x < real(0) ? real(0) : x;
+    case 1: return real(1) / (real(1) + r_exp(-x));
+    case 2: return r_sin(x);
+    case 3: return r_tanh(x);
+    case 4: return x > real(0) ? real(1) : (x < real(0) ? real(-1) : x);
+    default: return x;
+  }
+}
+
+// WeldJoint rigid 3x3 solve with localAnchor1 = 0 (Robot.java:66-71 puts the anchor at
+// body1's centre).  K = [[2im + ii r2y^2, -ii r2x r2y, -ii r2y], [., 2im + ii r2x^2, ii r2x],
+// [., ., 2ii]]; K * lambda = -C solved in closed form (Schur complement on the angular row,
+// then Sherman-Morrison with p = (-r2y, r2x), |p| = weld_len): algebraically the
+// Matrix33.solve33 answer of dyn4j.  Used for velocities (C = Cdot) and positions (C = C).
+// ONE function for both lanes that own the two masses, so both compute identical bits.
+template <typename real>
+__device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x, real r2y, real ii,
+                                             real weld_alpha, real inv_two_im, real& lx, real& ly, real& lz) {
+  real px = -r2y, py = r2x;
+  real bx = -cx + real(0.5) * px * cz, by = -cy + real(0.5) * py * cz;
+  real pb = px * bx + py * by;
+  lx = (bx - weld_alpha * px * pb) * inv_two_im;
+  ly = (by - weld_alpha * py * pb) * inv_two_im;
+  lz = real(0.5) * (-cz / ii - (px * lx + py * ly));
+}
+
+// ---------------------------------------------------------------- the episode kernel
+template <typename real, int CTRL>
+__global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) {
+  extern __shared__ unsigned char smem_raw[];
+  const ShapeDev& S = *P.shape;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  real* stage = reinterpret_cast<real*>(smem_raw) + (size_t)wib * P.smem_per_warp;
+  const int nvox = S.nvox;
+  const int G = 32 / nvox;
+  const int slot = lane / nvox;
+  const int v = lane - slot * nvox;
+  const bool lane_ok = slot < G;
+  const int lane0 = slot * nvox;  // first lane of this lane's robot
+  // lanes of this robot, for robot-wide votes
+  const unsigned robot_mask = lane_ok ? (((nvox == 32) ? 0xffffffffu : ((1u << nvox) - 1u)) << lane0) : 0u;
+  // neighbour lanes (own lane when absent: the shuffled value is then ignored)
+  int nl[4];
+  bool has[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    int nb = lane_ok ? (int)S.nbr[s][v] : -1;
+    has[s] = nb >= 0;
+    nl[s] = has[s] ? lane0 + nb : lane;
+  }
+  const real im = P.inv_m, ii = P.inv_i, dt = P.dt;
+  const real two_im = real(2) * im;
+  const real L2w = P.weld_len * P.weld_len;
+  const real weld_alpha = (real(0.5) * ii) / (two_im + real(0.5) * ii * L2w);
+  const real inv_two_im = real(1) / two_im;
+  const real lin_f = r_clamp<real>(real(1) - dt * P.lin_damp, real(0), real(1));
+  const real ang_f = r_clamp<real>(real(1) - dt * P.ang_damp, real(0), real(1));
+  const real max_trans2 = P.max_trans * P.max_trans;
+
+  const long long n_groups = (P.n_robots + G - 1) / G;
+  for (long long group = (long long)blockIdx.x * wpb + wib; group < n_groups; group += (long long)gridDim.x * wpb) {
+    const long long rb = group * G + slot;  // bucket index of this lane's robot
+    const bool active = lane_ok && rb < P.n_robots;
+    const long long gl = rb * nvox + v;     // global voxel lane (ring addressing)
+    const long long n_gl = P.n_robots * (long long)nvox;
+    const real* par = P.params + (active ? rb : 0) * (long long)S.n_params;
+
+    // ---- Voxel.assemble / Robot.assemble / placement: masses at rest
+    real x[4], y[4], th[4], vx[4], vy[4], w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      x[k] = active ? (real)S.init_x[v * 4 + k] : real(0);
+      y[k] = active ? (real)S.init_y[v * 4 + k] : real(k);
+      th[k] = vx[k] = vy[k] = w[k] = real(0);
+    }
+    real simp[18];
+#pragma unroll
+    for (int s = 0; s < 18; s++) simp[s] = real(0);
+    real rest[3] = {P.rng_rest[0], P.rng_rest[1], P.rng_rest[2]};  // Voxel.reset: applyForce(0)
+    // weld impulses: [side L,R,D,U][pair][x,y,z]
+    real wix[4][2], wiy[4][2], wiz[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int k = 0; k < 2; k++) wix[s][k] = wiy[s][k] = wiz[s][k] = real(0);
+    CBody<real> cbody[4];
+    int hint[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      cbody[k].n = 0;
+      hint[k] = 0;
+    }
+    unsigned cmask = 0;  // masses with ground constraints
+    int status = 0;
+    real last_f = real(0), ar_energy = real(0), ctrl_energy = real(0);
+    real readings[MAX_READ];
+#pragma unroll
+    for (int q = 0; q < MAX_READ; q++) readings[q] = real(0);
+    double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
+
+    for (int tick = 0; tick < P.n_ticks; tick++) {
+      // =========================== World.step(1) ===========================
+      // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        vx[k] += dt * P.grav_x;
+        vy[k] += dt * P.grav_y;
+        vx[k] *= lin_f;
+        vy[k] *= lin_f;
+        w[k] *= ang_f;
+      }
+      // ---- contacts: initialise + warm start
+      if (cmask) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (cmask & (1u << k)) {
+            BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
+            contact_init_mass(P, B, cbody[k]);
+            vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
+          }
+        }
+      }
+      // ---- springs: DistanceJoint.initializeConstraints + warm start
+      real ch[4], sh[4], cs_[4], sn_[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        r_sincos(th[k], &sn_[k], &cs_[k]);
+        ch[k] = cs_[k] * P.half;
+        sh[k] = sn_[k] * P.half;
+      }
+      real snx[18], sny[18], scr1[18], scr2[18], ssoft[18], sbias[18], sgam[18];
+      const real sw = P.spring_w;
+#define VSR_SPRING_INIT(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                        \
+  if (P.spring_mask & (1u << s)) {                                                                 \
+    real r1x = real(a1x) * ch[b1] - real(a1y) * sh[b1], r1y = real(a1x) * sh[b1] + real(a1y) * ch[b1]; \
+    real r2x = real(a2x) * ch[b2] - real(a2y) * sh[b2], r2y = real(a2x) * sh[b2] + real(a2y) * ch[b2]; \
+    real dx = r1x + x[b1] - (r2x + x[b2]), dy = r1y + y[b1] - (r2y + y[b2]);                       \
+    real len = r_sqrt(dx * dx + dy * dy);                                                          \
+    real inv = len < P.lin_tol ? real(0) : real(1) / len;                                          \
+    real nx = dx * inv, ny = dy * inv;                                                             \
+    real cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;                                     \
+    real invMass = im + ii * cr1 * cr1;                                                            \
+    invMass += im + ii * cr2 * cr2;                                                                \
+    real m = P.spring_mode ? real(1) / invMass : P.red_mass;                                       \
+    real dc = real(2) * m * P.spring_zeta * sw;                                                    \
+    real kk = m * sw * sw;                                                                         \
+    real gamma = real(1) / (dt * (dc + dt * kk));                                                  \
+    real bias = (len - rest[cls]) * dt * kk * gamma;                                               \
+    real soft = real(1) / (invMass + gamma);                                                       \
+    snx[s] = nx; sny[s] = ny; scr1[s] = cr1; scr2[s] = cr2;                                        \
+    ssoft[s] = soft; sbias[s] = bias; sgam[s] = gamma;                                             \
+    real jx = nx * simp[s], jy = ny * simp[s];                                                     \
+    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * cr1 * simp[s];                             \
+    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * cr2 * simp[s];                             \
+  }
+      VSR_SPRINGS(VSR_SPRING_INIT)
+#undef VSR_SPRING_INIT
+
+      // ---- welds: WeldJoint.initializeConstraints + warm start.
+      // Side s of this voxel: 0 left (own masses 0,3 are body1; partner masses 1,2 body2),
+      // 1 right (own 1,2 are body2; partner 0,3 body1), 2 down (own 3,2 body1; partner 0,1
+      // body2), 3 up (own 0,1 body2; partner 3,2 body1).  localAnchor1 = 0 (Robot.java:66-71),
+      // localAnchor2 = (+len,0) for left/right pairs and (0,+len) for down/up pairs.
+      real wr2x[4][2], wr2y[4][2];
+      {
+        // body2's rotation: partner's for sides 0 and 2, own for sides 1 and 3
+        real pc, ps;
+        // side 0: partner masses 1, 2
+        pc = shfl(cs_[1], nl[0]); ps = shfl(sn_[1], nl[0]);
+        wr2x[0][0] = pc * P.weld_len; wr2y[0][0] = ps * P.weld_len;
+        pc = shfl(cs_[2], nl[0]); ps = shfl(sn_[2], nl[0]);
+        wr2x[0][1] = pc * P.weld_len; wr2y[0][1] = ps * P.weld_len;
+        // side 1: own masses 1, 2 are body2
+        wr2x[1][0] = cs_[1] * P.weld_len; wr2y[1][0] = sn_[1] * P.weld_len;
+        wr2x[1][1] = cs_[2] * P.weld_len; wr2y[1][1] = sn_[2] * P.weld_len;
+        // side 2: partner masses 0, 1; anchor (0, len) -> R*(0,len) = (-s*len, c*len)
+        pc = shfl(cs_[0], nl[2]); ps = shfl(sn_[0], nl[2]);
+        wr2x[2][0] = -ps * P.weld_len; wr2y[2][0] = pc * P.weld_len;
+        pc = shfl(cs_[1], nl[2]); ps = shfl(sn_[1], nl[2]);
+        wr2x[2][1] = -ps * P.weld_len; wr2y[2][1] = pc * P.weld_len;
+        // side 3: own masses 0, 1 are body2
+        wr2x[3][0] = -sn_[0] * P.weld_len; wr2y[3][0] = cs_[0] * P.weld_len;
+        wr2x[3][1] = -sn_[1] * P.weld_len; wr2y[3][1] = cs_[1] * P.weld_len;
+      }
+      // warm start: body1 += (imp) ; body2 -= (imp), r1 = 0
+#define VSR_WELD_WARM(side, k, own, is_b1)                                                     \
+  if (has[side]) {                                                                             \
+    if (is_b1) {                                                                               \
+      vx[own] += wix[side][k] * im; vy[own] += wiy[side][k] * im; w[own] += ii * wiz[side][k]; \
+    } else {                                                                                   \
+      vx[own] -= wix[side][k] * im; vy[own] -= wiy[side][k] * im;                              \
+      w[own] -= ii * (wr2x[side][k] * wiy[side][k] - wr2y[side][k] * wix[side][k] + wiz[side][k]); \
+    }                                                                                          \
+  }
+      VSR_WELD_WARM(0, 0, 0, true) VSR_WELD_WARM(0, 1, 3, true)
+      VSR_WELD_WARM(1, 0, 1, false) VSR_WELD_WARM(1, 1, 2, false)
+      VSR_WELD_WARM(2, 0, 3, true) VSR_WELD_WARM(2, 1, 2, true)
+      VSR_WELD_WARM(3, 0, 0, false) VSR_WELD_WARM(3, 1, 1, false)
+#undef VSR_WELD_WARM
+
+      // ---- velocity iterations: all joints, then all contacts
+      for (int it = 0; it < P.vel_iters; it++) {
+#define VSR_SPRING_SOLVE(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                          \
+  if (P.spring_mask & (1u << s)) {                                                                    \
+    real Jv = snx[s] * (vx[b1] - vx[b2]) + sny[s] * (vy[b1] - vy[b2]) + scr1[s] * w[b1] - scr2[s] * w[b2]; \
+    real j = -ssoft[s] * (Jv + sbias[s] + sgam[s] * simp[s]);                                         \
+    simp[s] += j;                                                                                     \
+    real jx = snx[s] * j, jy = sny[s] * j;                                                            \
+    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * scr1[s] * j;                                  \
+    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * scr2[s] * j;                                  \
+  }
+        VSR_SPRINGS(VSR_SPRING_SOLVE)
+#undef VSR_SPRING_SOLVE
+
+        // WeldJoint.solveVelocityConstraints.  All partner values of a phase are gathered
+        // BEFORE any lane applies an update, so the two lanes that own the two masses of a
+        // weld compute the very same impulse.
+#define VSR_GATHER_V(tag, part, side) \
+  const real tag##vx = shfl(vx[part], nl[side]), tag##vy = shfl(vy[part], nl[side]), tag##w = shfl(w[part], nl[side]);
+#define VSR_WELD_VEL(side, k, own, tag, is_b1)                                                  \
+  if (has[side]) {                                                                              \
+    real v1x = is_b1 ? vx[own] : tag##vx, v1y = is_b1 ? vy[own] : tag##vy, w1 = is_b1 ? w[own] : tag##w; \
+    real v2x = is_b1 ? tag##vx : vx[own], v2y = is_b1 ? tag##vy : vy[own], w2 = is_b1 ? tag##w : w[own]; \
+    real r2x = wr2x[side][k], r2y = wr2y[side][k];                                              \
+    real lx, ly, lz;                                                                            \
+    weld_solve33<real>(v1x - (v2x - w2 * r2y), v1y - (v2y + w2 * r2x), w1 - w2, r2x, r2y, ii,   \
+                       weld_alpha, inv_two_im, lx, ly, lz);                                     \
+    wix[side][k] += lx; wiy[side][k] += ly; wiz[side][k] += lz;                                 \
+    if (is_b1) {                                                                                \
+      vx[own] += lx * im; vy[own] += ly * im; w[own] += ii * lz;                                \
+    } else {                                                                                    \
+      vx[own] -= lx * im; vy[own] -= ly * im; w[own] -= ii * (r2x * ly - r2y * lx + lz);        \
+    }                                                                                           \
+  }
+        {  // horizontal welds (left/right sides): each mass has at most one
+          VSR_GATHER_V(l1, 1, 0) VSR_GATHER_V(l2, 2, 0) VSR_GATHER_V(r0, 0, 1) VSR_GATHER_V(r3, 3, 1)
+          VSR_WELD_VEL(0, 0, 0, l1, true) VSR_WELD_VEL(0, 1, 3, l2, true)
+          VSR_WELD_VEL(1, 0, 1, r0, false) VSR_WELD_VEL(1, 1, 2, r3, false)
+        }
+        {  // vertical welds (down/up sides)
+          VSR_GATHER_V(d0, 0, 2) VSR_GATHER_V(d1, 1, 2) VSR_GATHER_V(u3, 3, 3) VSR_GATHER_V(u2, 2, 3)
+          VSR_WELD_VEL(2, 0, 3, d0, true) VSR_WELD_VEL(2, 1, 2, d1, true)
+          VSR_WELD_VEL(3, 0, 0, u3, false) VSR_WELD_VEL(3, 1, 1, u2, false)
+        }
+#undef VSR_GATHER_V
+#undef VSR_WELD_VEL
+
+        if (cmask) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (cmask & (1u << k)) {
+              BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
+              contact_solve_mass(P, B, cbody[k]);
+              vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
+            }
+          }
+        }
+      }
+
+      // ---- integrate positions (integratePosition, dyn4j; translation/rotation caps)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        real tx = vx[k] * dt, ty = vy[k] * dt;
+        real m2 = tx * tx + ty * ty;
+        if (m2 > max_trans2) {
+          real ratio = P.max_trans / r_sqrt(m2);
+          vx[k] *= ratio; vy[k] *= ratio; tx *= ratio; ty *= ratio;
+        }
+        real rot = w[k] * dt;
+        if (r_abs(rot) > P.max_rot) {
+          real ratio = P.max_rot / r_abs(rot);
+          w[k] *= ratio; rot *= ratio;
+        }
+        x[k] += tx; y[k] += ty; th[k] += rot;
+      }
+
+      // ---- position iterations: contacts, then joints; stop when the whole robot
+      //      (= one island) reports solved
+      {
+        bool done = !active;
+        for (int it = 0; it < P.pos_iters; it++) {
+          if (__all_sync(0xffffffffu, done)) break;
+          bool solved = true;
+          if (!done && cmask) {
+            real minSep = real(0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if (cmask & (1u << k)) {
+                BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
+                real ms = contact_position_mass(P, B, cbody[k]);
+                minSep = ms < minSep ? ms : minSep;
+                x[k] = B.x; y[k] = B.y; th[k] = B.th;
+              }
+            }
+            solved = minSep >= real(-3) * P.lin_tol;
+          }
+          // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)
+#define VSR_GATHER_P(tag, part, side) \
+  const real tag##x = shfl(x[part], nl[side]), tag##y = shfl(y[part], nl[side]), tag##t = shfl(th[part], nl[side]);
+#define VSR_WELD_POS(side, own, tag, is_b1, horiz)                                             \
+  if (has[side] && !done) {                                                                    \
+    real x1 = is_b1 ? x[own] : tag##x, y1 = is_b1 ? y[own] : tag##y, t1 = is_b1 ? th[own] : tag##t; \
+    real x2 = is_b1 ? tag##x : x[own], y2 = is_b1 ? tag##y : y[own], t2 = is_b1 ? tag##t : th[own]; \
+    real s2, c2;                                                                               \
+    r_sincos(t2, &s2, &c2);                                                                    \
+    real r2x = horiz ? c2 * P.weld_len : -s2 * P.weld_len;                                     \
+    real r2y = horiz ? s2 * P.weld_len : c2 * P.weld_len;                                      \
+    real Cx = x1 - (x2 + r2x), Cy = y1 - (y2 + r2y), Cz = t1 - t2;                             \
+    const real PI_ = real(3.14159265358979323846);                                             \
+    if (Cz < -PI_) Cz += real(2) * PI_;                                                        \
+    if (Cz > PI_) Cz -= real(2) * PI_;                                                         \
+    real linErr = r_sqrt(Cx * Cx + Cy * Cy), angErr = r_abs(Cz);                               \
+    real lx, ly, lz;                                                                           \
+    weld_solve33<real>(Cx, Cy, Cz, r2x, r2y, ii, weld_alpha, inv_two_im, lx, ly, lz);          \
+    if (is_b1) {                                                                               \
+      x[own] += lx * im; y[own] += ly * im; th[own] += ii * lz;                                \
+    } else {                                                                                   \
+      x[own] -= lx * im; y[own] -= ly * im; th[own] -= ii * (r2x * ly - r2y * lx + lz);        \
+    }                                                                                          \
+    solved = solved && (linErr <= P.lin_tol) && (angErr <= P.ang_tol);                         \
+  }
+          {
+            VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0) VSR_GATHER_P(r0, 0, 1) VSR_GATHER_P(r3, 3, 1)
+            VSR_WELD_POS(0, 0, l1, true, true) VSR_WELD_POS(0, 3, l2, true, true)
+            VSR_WELD_POS(1, 1, r0, false, true) VSR_WELD_POS(1, 2, r3, false, true)
+          }
+          {
+            VSR_GATHER_P(d0, 0, 2) VSR_GATHER_P(d1, 1, 2) VSR_GATHER_P(u3, 3, 3) VSR_GATHER_P(u2, 2, 3)
+            VSR_WELD_POS(2, 3, d0, true, false) VSR_WELD_POS(2, 2, d1, true, false)
+            VSR_WELD_POS(3, 0, u3, false, false) VSR_WELD_POS(3, 1, u2, false, false)
+          }
+#undef VSR_GATHER_P
+#undef VSR_WELD_POS
+          // robot-wide (island-wide) vote
+          unsigned bal = __ballot_sync(0xffffffffu, solved || done);
+          if ((bal & robot_mask) == robot_mask) done = true;
+        }
+      }
+
+      // ---- World.detect: new manifolds for Touch and for the next step
+      cmask = 0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // cheap reject: far above the highest point of the terrain near this mass
+          int ov = detect_mass(P, x[k], y[k], th[k], hint[k], cbody[k]);
+          if (ov) status |= STATUS_CONTACT_OVERFLOW;
+          if (cbody[k].n > 0) cmask |= 1u << k;
+        }
+      }
+
+      // =========================== Robot.act(t) ===========================
+      // ---- Voxel.act: energies; geometry shared by the sensors
+      real s4[4], c4[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) r_sincos(th[k], &s4[k], &c4[k]);
+      // outer corners getIndexedVertex(k, 3-k): NW(-h,+h) NE(+h,+h) SE(+h,-h) SW(-h,-h)
+      real ox[4], oy[4];
+      {
+        const real h = P.half;
+        ox[0] = x[0] + c4[0] * (-h) - s4[0] * (+h); oy[0] = y[0] + s4[0] * (-h) + c4[0] * (+h);
+        ox[1] = x[1] + c4[1] * (+h) - s4[1] * (+h); oy[1] = y[1] + s4[1] * (+h) + c4[1] * (+h);
+        ox[2] = x[2] + c4[2] * (+h) - s4[2] * (-h); oy[2] = y[2] + s4[2] * (+h) + c4[2] * (-h);
+        ox[3] = x[3] + c4[3] * (-h) - s4[3] * (-h); oy[3] = y[3] + s4[3] * (-h) + c4[3] * (-h);
+      }
+      real area = real(0);
+#pragma unroll
+      for (int i = 0; i < 4; i++) area = area + ox[i] * (oy[(i + 1) & 3] - oy[(i + 3) & 3]);
+      area = real(0.5) * r_abs(area);
+      const real area_ratio = area / P.side / P.side;
+      ar_energy = ar_energy + area_ratio * area_ratio;
+      ctrl_energy = ctrl_energy + last_f * last_f;
+
+      // ---- sensors (CompositeSensor.act: inner first)
+      if (active && S.n_sens[v] > 0) {
+        real mvx = (((vx[0] + vx[1]) + vx[2]) + vx[3]) / real(4);
+        real mvy = (((vy[0] + vy[1]) + vy[2]) + vy[3]) / real(4);
+        real ang = (r_atan2(y[1] - y[0], x[1] - x[0]) + r_atan2(y[2] - y[3], x[2] - x[3])) / real(2);
+        int ro = 0;
+        const int ns = S.n_sens[v];
+        for (int si = 0; si < ns; si++) {
+          const SensorDev sd = S.sens[v][si];
+          real raw[2] = {0, 0}, dmin = real(0), dmax = real(1);
+          if (sd.base == SENSOR_TOUCH) {
+            raw[0] = cmask ? real(1) : real(0);
+          } else if (sd.base == SENSOR_AREA) {
+            raw[0] = area_ratio;
+            dmin = real(0.5);
+            dmax = real(1.5);
+          } else {
+            int c = 0;
+            real sa, ca;
+            r_sincos(ang, &sa, &ca);
+            if (sd.axes & 1) raw[c++] = sd.rotated ? mvx * ca + mvy * sa : mvx;
+            if (sd.axes & 2) {
+              real sb, cb2;
+              r_sincos(ang + real(1.5707963267948966), &sb, &cb2);
+              raw[c++] = sd.rotated ? mvx * cb2 + mvy * sb : mvy;
+            }
+            dmin = -sd.max_norm;
+            dmax = sd.max_norm;
+          }
+          real val[2] = {raw[0], raw[1]};
+          if (sd.agg != AGG_NONE) {
+            const int depth = S.ring_depth;
+            const int f = P.win_first[sd.win * P.n_ticks + tick];
+            for (int d = 0; d < sd.dim; d++) {
+              real* ring = P.ring + ((size_t)(sd.ch + d)) * n_gl + gl;
+              const size_t stride = (size_t)S.n_channels * n_gl;
+              ring[(size_t)(tick % depth) * stride] = raw[d];
+              if (sd.agg == AGG_AVERAGE) {
+                real sum = real(0);
+                for (int q = f; q < tick; q++) sum = sum + ring[(size_t)(q % depth) * stride];
+                sum = sum + raw[d];
+                val[d] = sum / (real)(tick - f + 1);
+              } else {
+                real li = (real)(P.tick_t[tick] - P.tick_t[f]);
+                real first = (f == tick) ? raw[d] : ring[(size_t)(f % depth) * stride];
+                val[d] = (f == tick) ? real(0) : (raw[d] - first) / li;
+              }
+            }
+            if (sd.agg == AGG_TREND) {
+              real ext = dmax - dmin;
+              dmin = -ext / sd.interval;
+              dmax = ext / sd.interval;
+            }
+          }
+          for (int d = 0; d < sd.dim; d++) {
+            real o = val[d];
+            if (sd.soft) {
+              real cl = r_min(r_max(o, dmin), dmax);
+              real nv = (cl - dmin) / (dmax - dmin);
+              o = r_tanh(((nv * real(2)) - real(1)) * real(2)) / real(2) + real(0.5);
+            }
+            // static indexing of the register array
+#pragma unroll
+            for (int q = 0; q < MAX_READ; q++)
+              if (q == ro) readings[q] = o;
+            ro++;
+          }
+        }
+      }
+
+      // ---- controller.control -> Voxel.applyForce
+      real f = real(0);
+      if (CTRL == CTRL_PHASE_SIN) {
+        // PhaseSin.java:61, evaluated in double on the accumulated double t
+        double fr = (double)par[0], am = (double)par[1], ph = (double)par[2 + (active ? v : 0)];
+        f = (real)(sin(2.0 * 3.14159265358979323846 * fr * P.tick_t[tick] + ph) * am);
+      } else if (CTRL == CTRL_TABULATED) {
+        f = par[(size_t)tick * nvox + (active ? v : 0)];
+      } else {
+        // CentralizedSensing + MultiLayerPerceptron.apply: inputs = readings of all voxels
+        // in voxel order; lane j of the robot evaluates neurons j, j+nvox, ...
+        const int per_robot = P.smem_per_warp / (G > 0 ? G : 1);
+        real* act0 = stage + (size_t)(lane_ok ? slot : 0) * per_robot;
+        real* act1 = act0 + per_robot / 2;
+        if (active) {
+          int base = S.read_off[v];
+          int nr = (v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base;
+#pragma unroll
+          for (int q = 0; q < MAX_READ; q++)
+            if (q < nr) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
+        }
+        __syncwarp();
+        real* a = act0;
+        real* b = act1;
+        for (int li = 1; li < S.n_layers; li++) {
+          const int np = S.neurons[li - 1], nn = S.neurons[li];
+          const real* W = par + S.layer_off[li];  // transposed: [k = 0..np][neuron]
+          if (active) {
+            for (int j = v; j < nn; j += nvox) {
+              real sum = W[j];
+              for (int k = 1; k < np + 1; k++) sum = sum + a[k - 1] * W[(size_t)k * nn + j];
+              b[j] = activation<real>(P.mlp_act, sum);
+            }
+          }
+          __syncwarp();
+          real* t = a; a = b; b = t;
+        }
+        f = active ? a[v] : real(0);
+        __syncwarp();
+      }
+      if (r_abs(f) > real(1)) f = f > real(0) ? real(1) : real(-1);
+      last_f = f;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        rest[c] = (f >= real(0)) ? P.rng_rest[c] - (P.rng_rest[c] - P.rng_min[c]) * f
+                                 : P.rng_rest[c] + (P.rng_max[c] - P.rng_rest[c]) * -f;
+
+      // ---- optional per-tick dump (SnapshotListener / Observation path)
+      if (P.trajectory && active && rb < P.traj_robots) {
+        real* o = P.trajectory + (((size_t)rb * P.n_ticks + tick) * (size_t)(nvox * 4) + (size_t)v * 4) * 6;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          o[6 * k + 0] = x[k]; o[6 * k + 1] = y[k]; o[6 * k + 2] = th[k];
+          o[6 * k + 3] = vx[k]; o[6 * k + 4] = vy[k]; o[6 * k + 5] = w[k];
+        }
+      }
+
+      // ---- Observation: first and last tick only (Outcome.java:152-166)
+      if (tick == 0 || tick == P.n_ticks - 1) {
+        // BehaviorUtils.center: mean over voxels of the mean of the 4 outer corners,
+        // summed by the robot's first lane in voxel order (the oracle's order)
+        real* st = stage;
+        __syncwarp();
+        if (lane_ok) {
+          st[lane * 4 + 0] = (((ox[0] + ox[1]) + ox[2]) + ox[3]) / real(4);
+          st[lane * 4 + 1] = (((oy[0] + oy[1]) + oy[2]) + oy[3]) / real(4);
+          st[lane * 4 + 2] = ar_energy;
+          st[lane * 4 + 3] = ctrl_energy;
+        }
+        __syncwarp();
+        if (active && v == 0) {
+          double sx = 0, sy = 0, sa = 0, sc = 0;
+          for (int q = 0; q < nvox; q++) {
+            sx = sx + (double)st[(lane0 + q) * 4 + 0];
+            sy = sy + (double)st[(lane0 + q) * 4 + 1];
+            sa += (double)st[(lane0 + q) * 4 + 2];
+            sc += (double)st[(lane0 + q) * 4 + 3];
+          }
+          double cx = sx / (double)nvox + P.origin_x, cy = sy / (double)nvox;
+          if (tick == 0) {
+            first_cx = cx; first_cy = cy; first_are = sa; first_ce = sc;
+          }
+          if (tick == P.n_ticks - 1) {
+            double* R = P.results + (size_t)P.robot_ids[rb] * 11;
+            R[0] = first_cx; R[1] = first_cy; R[2] = cx; R[3] = cy;
+            R[4] = P.tick_t[0]; R[5] = P.tick_t[tick];
+            R[6] = first_are; R[7] = sa; R[8] = first_ce; R[9] = sc;
+            int bad = !(isfinite(cx) && isfinite(cy));
+            // robot-wide status: gathered below
+            int2 tail;
+            tail.x = P.n_ticks;
+            tail.y = status | (bad ? STATUS_NONFINITE : 0);
+            *reinterpret_cast<int2*>(&R[10]) = tail;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // robot-wide OR of the per-voxel status bits into the record
+    if (active && status) atomicOr(reinterpret_cast<int*>(P.results + (size_t)P.robot_ids[rb] * 11 + 10) + 1, status);
+  }
+}
+
+}  // namespace vsr

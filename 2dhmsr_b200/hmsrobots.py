@@ -1,0 +1,873 @@
+"""Host-side mirror of the reference's Java API for the Locomotion hot path.
+
+Same names, argument meaning and error behaviour as
+``it.units.erallab.hmsrobots`` (file:line cited per item), restricted to what the
+hot path needs: describing robots / terrain / controllers and handing a *batch*
+of them to the CUDA stepper through the C ABI (``include/vsr_b200.h``).
+
+Nothing here steps physics: ``Locomotion.apply`` compiles a ``vsr_batch_desc``
+and calls ``libvsr_b200.so``.  ``IllegalArgumentException`` -> ``ValueError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import re
+from dataclasses import dataclass, field
+from typing import Callable, Generic, Iterable, Iterator, List, Optional, Sequence, Tuple, TypeVar
+
+import numpy as np
+
+from . import _abi as A
+
+T = TypeVar("T")
+
+
+# --------------------------------------------------------------------------- java.util.Random
+class JavaRandom:
+    """Bit-exact ``java.util.Random`` (48-bit LCG; polar-method nextGaussian).
+
+    Needed by Locomotion.createTerrain (Locomotion.java:76-117).  Java uses
+    StrictMath.log/sqrt in nextGaussian; ``math.log``/``math.sqrt`` (glibc) agree
+    to <= 1 ulp.
+    """
+
+    _MULT = 0x5DEECE66D
+    _MASK = (1 << 48) - 1
+
+    def __init__(self, seed: int):
+        self._seed = (int(seed) ^ self._MULT) & self._MASK
+        self._next_gaussian: Optional[float] = None
+
+    def _next(self, bits: int) -> int:
+        self._seed = (self._seed * self._MULT + 0xB) & self._MASK
+        v = self._seed >> (48 - bits)
+        if v >= 1 << (bits - 1) and bits == 32:
+            v -= 1 << 32
+        return v
+
+    def next_int(self, bound: Optional[int] = None) -> int:
+        if bound is None:
+            return self._next(32)
+        if bound <= 0:
+            raise ValueError("bound must be positive")
+        if (bound & -bound) == bound:
+            return (bound * self._next(31)) >> 31
+        while True:
+            bits = self._next(31)
+            val = bits % bound
+            if bits - val + (bound - 1) < (1 << 31):
+                return val
+
+    def next_double(self) -> float:
+        return ((self._next(26) << 27) + self._next(27)) * (1.0 / (1 << 53))
+
+    def next_gaussian(self) -> float:
+        if self._next_gaussian is not None:
+            g, self._next_gaussian = self._next_gaussian, None
+            return g
+        while True:
+            v1 = 2 * self.next_double() - 1
+            v2 = 2 * self.next_double() - 1
+            s = v1 * v1 + v2 * v2
+            if 0 < s < 1:
+                break
+        mul = math.sqrt(-2 * math.log(s) / s)
+        self._next_gaussian = v2 * mul
+        return v1 * mul
+
+
+# --------------------------------------------------------------------------- util.Grid
+class Grid(Generic[T]):
+    """util/Grid.java: storage ``ts[y*w+x]`` (:180-188); ``create(w,h,filler)`` calls
+    the filler x-outer / y-inner (:103-111) while iteration and ``values()`` are
+    row-major, y-outer (:69-75,268-270)."""
+
+    def __init__(self, w: int, h: int):
+        self.w, self.h = w, h
+        self._ts: List[Optional[T]] = [None] * (w * h)
+
+    @staticmethod
+    def create(w: int, h: int, filler=None) -> "Grid":
+        g = Grid(w, h)
+        for x in range(w):
+            for y in range(h):
+                g.set(x, y, filler(x, y) if callable(filler) else filler)
+        return g
+
+    @staticmethod
+    def create_from(other: "Grid", fn: Callable) -> "Grid":
+        g = Grid(other.w, other.h)
+        for (x, y), v in other:
+            g.set(x, y, fn(v))
+        return g
+
+    def get(self, x: int, y: int):
+        if x < 0 or x >= self.w or y < 0 or y >= self.h:
+            return None
+        return self._ts[y * self.w + x]
+
+    def set(self, x: int, y: int, v) -> None:
+        self._ts[y * self.w + x] = v
+
+    def values(self) -> list:
+        return list(self._ts)
+
+    def __iter__(self) -> Iterator[Tuple[Tuple[int, int], Optional[T]]]:
+        for c in range(self.w * self.h):
+            y, x = divmod(c, self.w)
+            yield (x, y), self._ts[c]
+
+    def count(self, pred) -> int:
+        return sum(1 for v in self._ts if pred(v))
+
+
+@dataclass(frozen=True)
+class DoubleRange:
+    """util/DoubleRange.java:29-58."""
+    min: float
+    max: float
+
+    def __post_init__(self):
+        if self.max < self.min:
+            raise ValueError(f"Max has to be lower or equal than min; {self.max} is not than {self.min}.")
+
+    def extent(self) -> float:
+        return self.max - self.min
+
+    def clip(self, v: float) -> float:
+        return min(max(v, self.min), self.max)
+
+    def normalize(self, v: float) -> float:
+        return (self.clip(v) - self.min) / (self.max - self.min)
+
+
+# --------------------------------------------------------------------------- sensors
+class Sensor:
+    """core/sensors/Sensor.java:26-34 (description only: readout runs on the device)."""
+
+    def domains(self) -> List[DoubleRange]:
+        raise NotImplementedError
+
+    def encode(self) -> A.vsr_sensor:
+        raise NotImplementedError
+
+
+class Touch(Sensor):  # sensors/Touch.java
+    def domains(self):
+        return [DoubleRange(0.0, 1.0)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_TOUCH
+        return s
+
+
+class AreaRatio(Sensor):  # sensors/AreaRatio.java:21-37
+    def domains(self):
+        return [DoubleRange(0.5, 1.5)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_AREA_RATIO
+        return s
+
+
+class Velocity(Sensor):  # sensors/Velocity.java:29-80
+    X, Y = "X", "Y"
+
+    def __init__(self, rotated: bool, max_velocity_norm: float, *axes: str):
+        self.rotated, self.max_velocity_norm = rotated, max_velocity_norm
+        self.axes = [a for a in (self.X, self.Y) if a in axes]  # EnumSet order
+
+    def domains(self):
+        return [DoubleRange(-self.max_velocity_norm, self.max_velocity_norm) for _ in self.axes]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_VELOCITY
+        s.axes = (A.VSR_AXIS_X if self.X in self.axes else 0) | (A.VSR_AXIS_Y if self.Y in self.axes else 0)
+        s.rotated = 1 if self.rotated else 0
+        s.max_velocity_norm = self.max_velocity_norm
+        return s
+
+
+class _Aggregator(Sensor):  # sensors/AggregatorSensor.java:31-66
+    KIND = A.VSR_AGG_NONE
+
+    def __init__(self, sensor: Sensor, interval: float):
+        if isinstance(sensor, (_Aggregator, SoftNormalization)):
+            raise NotImplementedError("nested aggregators are outside the hot path")
+        self.sensor, self.interval = sensor, interval
+
+    def encode(self):
+        s = self.sensor.encode()
+        s.aggregator = self.KIND
+        s.interval = self.interval
+        return s
+
+
+class Average(_Aggregator):  # sensors/Average.java
+    KIND = A.VSR_AGG_AVERAGE
+
+    def domains(self):
+        return self.sensor.domains()
+
+
+class Trend(_Aggregator):  # sensors/Trend.java:28-35
+    KIND = A.VSR_AGG_TREND
+
+    def domains(self):
+        return [DoubleRange(-d.extent() / self.interval, d.extent() / self.interval) for d in self.sensor.domains()]
+
+
+class SoftNormalization(Sensor):  # sensors/SoftNormalization.java
+    def __init__(self, sensor: Sensor):
+        if isinstance(sensor, SoftNormalization):
+            raise NotImplementedError("nested SoftNormalization is outside the hot path")
+        self.sensor = sensor
+
+    def domains(self):
+        return [DoubleRange(0.0, 1.0) for _ in self.sensor.domains()]
+
+    def encode(self):
+        s = self.sensor.encode()
+        s.soft_norm = 1
+        return s
+
+
+# --------------------------------------------------------------------------- Voxel / Robot
+class Voxel:
+    """core/objects/Voxel.java: the 13-argument constructor (:103-142) and the
+    default one (:144-160).  Holds only the description."""
+
+    SIDE_LENGTH = 3.0
+    MASS_SIDE_LENGTH_RATIO = 0.35
+    SPRING_F = 8.0
+    SPRING_D = 0.3
+    MASS_LINEAR_DAMPING = 0.1
+    MASS_ANGULAR_DAMPING = 0.1
+    FRICTION = 10.0
+    RESTITUTION = 0.1
+    MASS = 1.0
+
+    def __init__(self, sensors: Sequence[Sensor], material: Optional[A.vsr_material] = None):
+        self.sensors = list(sensors)
+        self.material = material if material is not None else A.default_material()
+        m = self.material
+        lim = (2 * m.mass_side_length_ratio) ** 2
+        if m.area_ratio_passive_min > -math.inf and m.area_ratio_passive_min < lim:  # Voxel.java:132-140
+            raise ValueError(
+                f"Min of areaRatioPassiveRange={m.area_ratio_passive_min} cannot be lower than the value "
+                f"({lim}) imposed by massSideLengthRatio={m.mass_side_length_ratio}"
+            )
+
+    def get_sensors(self) -> List[Sensor]:
+        return self.sensors
+
+
+class Controller:
+    """core/controllers/Controller.java:29 (description only)."""
+    KIND = -1
+
+    def params(self, voxels: Grid, tick_times: np.ndarray) -> np.ndarray:
+        raise NotImplementedError
+
+
+def _present(voxels: Grid) -> List[Tuple[int, int]]:
+    return [(x, y) for (x, y), v in voxels if v is not None]
+
+
+class TimeFunctions(Controller):
+    """controllers/TimeFunctions.java:49-64: opaque per-voxel lambdas of t.  The host
+    samples each lambda at the tick times (the only way to keep arbitrary lambdas)."""
+    KIND = A.VSR_CTRL_TABULATED
+
+    def __init__(self, functions: Grid):
+        self.functions = functions
+
+    def params(self, voxels, tick_times):
+        cells = _present(voxels)
+        out = np.empty((len(tick_times), len(cells)), dtype=np.float64)
+        for j, (x, y) in enumerate(cells):
+            f = self.functions.get(x, y)
+            if f is None:
+                raise ValueError(f"no time function for voxel ({x},{y})")
+            for k, t in enumerate(tick_times):
+                out[k, j] = f(float(t))
+        return out.reshape(-1)
+
+
+class PhaseSin(TimeFunctions):
+    """controllers/PhaseSin.java:50-66: sin(2*pi*frequency*t + phase) * amplitude."""
+    KIND = A.VSR_CTRL_PHASE_SIN
+
+    def __init__(self, frequency: float, amplitude: float, phases: Grid):
+        self.frequency, self.amplitude, self.phases = frequency, amplitude, phases
+
+    def params(self, voxels, tick_times):
+        cells = _present(voxels)
+        ph = []
+        for x, y in cells:
+            p = self.phases.get(x, y)
+            if p is None:
+                raise ValueError(f"no phase for voxel ({x},{y})")
+            ph.append(float(p))
+        return np.asarray([self.frequency, self.amplitude] + ph, dtype=np.float64)
+
+
+class MultiLayerPerceptron:
+    """controllers/MultiLayerPerceptron.java (flat weights, bias first, :139-151)."""
+
+    def __init__(self, activation: str, n_input: int, inner: Sequence[int], n_output: int,
+                 weights: Optional[Sequence[float]] = None):
+        if activation not in A.VSR_ACT:
+            raise ValueError(f"unknown activation {activation}")
+        self.activation = activation
+        self.neurons = [n_input, *inner, n_output]  # countNeurons :97-104
+        n = self.count_weights(self.neurons)
+        w = np.zeros(n) if weights is None else np.asarray(weights, dtype=np.float64)
+        if w.size != n:  # :56-62
+            raise ValueError(f"Wrong number of weights: {n} expected, {w.size} found")
+        self.weights = w
+
+    @staticmethod
+    def count_weights(neurons: Sequence[int]) -> int:  # :106-112
+        return sum(neurons[i] * (neurons[i - 1] + 1) for i in range(1, len(neurons)))
+
+    @staticmethod
+    def unflat(flat: Sequence[float], neurons: Sequence[int]):  # :153-166
+        out, c = [], 0
+        for i in range(1, len(neurons)):
+            layer = []
+            for _ in range(neurons[i]):
+                layer.append(list(flat[c:c + neurons[i - 1] + 1]))
+                c += neurons[i - 1] + 1
+            out.append(layer)
+        return out
+
+    @staticmethod
+    def flat(unflat, neurons: Sequence[int]):  # :139-151
+        return [w for i in range(1, len(neurons)) for j in range(neurons[i]) for w in unflat[i - 1][j]]
+
+    def get_params(self):
+        return self.weights
+
+    def get_input_dimension(self):
+        return self.neurons[0]
+
+    def get_output_dimension(self):
+        return self.neurons[-1]
+
+
+class CentralizedSensing(Controller):
+    """controllers/CentralizedSensing.java:68-127."""
+    KIND = A.VSR_CTRL_MLP
+
+    def __init__(self, voxels: Grid, function: MultiLayerPerceptron):
+        self.n_inputs = self.n_of_inputs(voxels)
+        self.n_outputs = self.n_of_outputs(voxels)
+        self.set_function(function)
+
+    @staticmethod
+    def n_of_inputs(voxels: Grid) -> int:
+        return sum(len(s.domains()) for v in voxels.values() if v is not None for s in v.get_sensors())
+
+    @staticmethod
+    def n_of_outputs(voxels: Grid) -> int:
+        return sum(1 for v in voxels.values() if v is not None)
+
+    def set_function(self, function: MultiLayerPerceptron) -> None:
+        if function.get_input_dimension() != self.n_inputs or function.get_output_dimension() != self.n_outputs:
+            raise ValueError(  # :121-127
+                "Wrong dimension of input or output in provided function: "
+                f"R^{self.n_inputs}->R^{self.n_outputs} expected, "
+                f"R^{function.get_input_dimension()}->R^{function.get_output_dimension()} found"
+            )
+        self.function = function
+
+    def params(self, voxels, tick_times):
+        return np.asarray(self.function.weights, dtype=np.float64)
+
+
+class Robot:
+    """core/objects/Robot.java:57-64 (controller + Grid<Voxel>)."""
+
+    def __init__(self, controller: Controller, voxels: Grid):
+        self.controller, self.voxels = controller, voxels
+
+    def get_voxels(self) -> Grid:
+        return self.voxels
+
+    def get_controller(self) -> Controller:
+        return self.controller
+
+
+# --------------------------------------------------------------------------- RobotUtils
+def _params(pattern: str, string: str):
+    """util/Utils.java:147-164 (named groups of a full match, else None)."""
+    m = re.fullmatch(pattern.replace("(?<", "(?P<"), string)
+    return None if m is None else m.groupdict()
+
+
+class RobotUtils:
+    """util/RobotUtils.java: body-shape and sensor-layout mini DSLs."""
+
+    PREDEFINED_SENSORS = {  # :38-60 (hot-path subset; TreeMap => sorted keys)
+        "a": lambda x, y: SoftNormalization(AreaRatio()),
+        "ax": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.X), 0.5)),
+        "axy": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.X, Velocity.Y), 0.5)),
+        "ay": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.Y), 0.5)),
+        "t": lambda x, y: Average(Touch(), 0.25),
+        "vx": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.X), 0.5)),
+        "vxy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.X, Velocity.Y), 0.5)),
+        "vy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.Y), 0.5)),
+    }
+    _OUT_OF_PATH = {"r", "px", "py", "m", "cpg", "l5", "l1"}
+
+    @staticmethod
+    def build_shape(name: str) -> Grid:  # :198-242
+        p = _params(r"(box|worm)-(?<w>\d+)x(?<h>\d+)", name)
+        if p is not None:
+            return Grid.create(int(p["w"]), int(p["h"]), True)
+        p = _params(r"biped-(?<w>\d+)x(?<h>\d+)", name)
+        if p is not None:
+            w, h = int(p["w"]), int(p["h"])
+            return Grid.create(w, h, lambda x, y: not (y < h // 2 and x >= w // 4 and x < w * 3 // 4))
+        p = _params(r"tripod-(?<w>\d+)x(?<h>\d+)", name)
+        if p is not None:
+            w, h = int(p["w"]), int(p["h"])
+            return Grid.create(w, h, lambda x, y: not (y < h // 2 and x != 0 and x != w - 1 and x != w // 2))
+        p = _params(r"ball-(?<d>\d+)", name)
+        if p is not None:
+            d = int(p["d"])
+            c = (d - 1) / 2.0
+
+            def inside(x, y):  # Math.round = floor(v + 0.5)
+                return math.floor(math.sqrt((x - c) ** 2 + (y - c) ** 2) + 0.5) <= int(math.floor(d / 2.0))
+
+            return Grid.create(d, d, inside)
+        p = _params(r"comb-(?<w>\d+)x(?<h>\d+)", name)
+        if p is not None:
+            w, h = int(p["w"]), int(p["h"])
+            return Grid.create(w, h, lambda x, y: (y >= h // 2 or x % 2 == 0))
+        p = _params(r"t-(?<w>\d+)x(?<h>\d+)", name)
+        if p is not None:
+            w, h = int(p["w"]), int(p["h"])
+            pad = int(math.floor(math.floor(w / 2.0) / 2.0))
+            return Grid.create(w, h, lambda x, y: (y == 0 or (x >= pad and x < h - pad - 1)))
+        raise ValueError(f"Unknown body name: {name}")
+
+    @staticmethod
+    def sensor(name: str, x: int, y: int, body: Grid) -> Sensor:  # :249-263
+        if name in RobotUtils._OUT_OF_PATH:
+            raise NotImplementedError(f"sensor '{name}' is outside the accelerated hot path")
+        w1, h1 = body.w - 1.0, body.h - 1.0
+        nx = x / w1 if w1 != 0 else math.nan
+        ny = y / h1 if h1 != 0 else math.nan
+        return RobotUtils.PREDEFINED_SENSORS[name](nx, ny)
+
+    @staticmethod
+    def build_sensorizing_function(name: str) -> Callable[[Grid], Grid]:  # :124-196
+        keys = "|".join(sorted(set(RobotUtils.PREDEFINED_SENSORS) | RobotUtils._OUT_OF_PATH))
+        p = _params(rf"uniform-(?<sensors>({keys})(\+({keys}))*)-(?<noiseSigma>\d+(\.\d+)?)", name)
+        if p is not None:
+            if float(p["noiseSigma"]) != 0:
+                raise NotImplementedError("Noisy sensors are outside the accelerated hot path")
+            names = p["sensors"].split("+")
+            return lambda body: Grid.create(
+                body.w, body.h,
+                lambda x, y: None if not body.get(x, y) else Voxel([RobotUtils.sensor(n, x, y, body) for n in names]),
+            )
+        if _params("empty", name) is not None:
+            return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else Voxel([]))
+        for out in (r"spinedTouch-.*", r"spinedTouchSighted-.*", r"uniformAll-.*"):
+            if _params(out, name) is not None:
+                raise NotImplementedError(f"sensorizing function '{name}' is outside the accelerated hot path")
+        raise ValueError(f"Unknown sensorizing function name: {name}")
+
+
+# --------------------------------------------------------------------------- Settings / Outcome
+class Settings:
+    """org.dyn4j.dynamics.Settings as a plain value holder (Locomotion.java:50)."""
+
+    def __init__(self):
+        self._s = A.default_settings()
+
+    def get_step_frequency(self) -> float:
+        return self._s.step_frequency
+
+    def __getattr__(self, k):
+        return getattr(self.__dict__["_s"], k)
+
+    def set(self, **kw) -> "Settings":
+        for k, v in kw.items():
+            setattr(self._s, k, v)
+        return self
+
+    def raw(self) -> A.vsr_settings:
+        return self._s
+
+
+class Outcome:
+    """tasks/locomotion/Outcome.java: only what the first and the last Observation give."""
+
+    def __init__(self, rec):
+        self.rec = rec
+
+    def get_distance(self) -> float:  # :152-166
+        return float(self.rec["last_center_x"] - self.rec["first_center_x"])
+
+    def get_time(self) -> float:  # :194-196
+        return float(self.rec["t_last"] - self.rec["t_first"])
+
+    def get_velocity(self) -> float:  # :198-200
+        return self.get_distance() / self.get_time()
+
+    def get_area_ratio_energy(self) -> float:  # :42-58
+        return float(self.rec["area_ratio_energy_last"] - self.rec["area_ratio_energy_first"])
+
+    def get_control_energy(self) -> float:  # :126-142
+        return float(self.rec["control_energy_last"] - self.rec["control_energy_first"])
+
+    def get_control_power(self) -> float:
+        return self.get_control_energy() / self.get_time()
+
+    def get_area_ratio_power(self) -> float:
+        return self.get_area_ratio_energy() / self.get_time()
+
+    def get_corrected_efficiency(self) -> float:  # :148-150
+        return self.get_distance() / (1.0 + self.get_control_power() * self.get_time())
+
+    def __repr__(self):
+        return f"Outcome{{distance={self.get_distance():.6f}, time={self.get_time():.3f}, velocity={self.get_velocity():.6f}}}"
+
+
+RESULT_DTYPE = np.dtype([
+    ("first_center_x", "<f8"), ("first_center_y", "<f8"), ("last_center_x", "<f8"), ("last_center_y", "<f8"),
+    ("t_first", "<f8"), ("t_last", "<f8"),
+    ("area_ratio_energy_first", "<f8"), ("area_ratio_energy_last", "<f8"),
+    ("control_energy_first", "<f8"), ("control_energy_last", "<f8"),
+    ("n_ticks", "<i4"), ("status", "<i4"),
+])
+assert RESULT_DTYPE.itemsize == C.sizeof(A.vsr_result)
+
+
+def tick_times(final_t: float, dt: float) -> np.ndarray:
+    """``t = 0; while (t < finalT) t = t + dT`` in double (Locomotion.java:195-203,
+    AbstractTask.java:48).  1200 ticks for finalT = 20, dt = 1/60."""
+    out, t = [], 0.0
+    while t < final_t:
+        t = t + dt
+        out.append(t)
+    return np.asarray(out, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- batch descriptor
+class BatchDesc:
+    """Owns the flat arrays behind a ``vsr_batch_desc`` (keeps them alive)."""
+
+    def __init__(self):
+        self.desc = A.vsr_batch_desc()
+        self._keep: list = []
+        self.n_voxels: List[int] = []       # per shape
+        self.n_readings: List[int] = []     # per shape
+        self.robot_shape: np.ndarray = np.zeros(0, np.int32)
+        self.n_ticks = 0
+
+    def ptr(self):
+        return C.byref(self.desc)
+
+    def voxel_steps(self) -> int:
+        nv = np.asarray(self.n_voxels, dtype=np.int64)
+        return int(nv[self.robot_shape].sum()) * self.n_ticks
+
+    def keep(self, arr):
+        self._keep.append(arr)
+        return arr
+
+
+def _np_ptr(arr: np.ndarray, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def compile_batch(
+    robots: Sequence[Robot],
+    final_t: float,
+    ground_profile: Sequence[Sequence[float]],
+    initial_placement: Optional[float],
+    settings: Settings,
+    precision: int = A.VSR_PRECISION_F32,
+    trajectory_robots: int = 0,
+) -> BatchDesc:
+    """Flatten a list of Robots + one Locomotion task into a ``vsr_batch_desc``."""
+    if len(robots) == 0:
+        raise ValueError("empty batch")
+    kinds = {r.controller.KIND for r in robots}
+    if len(kinds) != 1:
+        raise ValueError("one controller kind per batch")
+    kind = kinds.pop()
+    b = BatchDesc()
+    d = b.desc
+    d.abi_version = A.VSR_ABI_VERSION
+    d.precision = precision
+    d.n_robots = len(robots)
+    d.controller_kind = kind
+    d.settings = settings.raw()
+    d.final_t = final_t
+    xs = b.keep(np.ascontiguousarray(ground_profile[0], dtype=np.float64))
+    ys = b.keep(np.ascontiguousarray(ground_profile[1], dtype=np.float64))
+    if xs.size != ys.size:
+        raise ValueError("xs[] and ys[] must have the same length")  # Ground.java:49-51
+    d.terrain_xs, d.terrain_ys, d.terrain_n = _np_ptr(xs, C.c_double), _np_ptr(ys, C.c_double), xs.size
+    d.initial_placement = float(xs[1] + 1.0) if initial_placement is None else float(initial_placement)
+    d.trajectory_robots = trajectory_robots
+    ticks = tick_times(final_t, d.settings.step_frequency)
+    b.n_ticks = len(ticks)
+
+    # shape classes: (mask, per-voxel sensor encodings, hidden layers)
+    shape_keys: dict = {}
+    shapes_c: list = []
+    robot_shape = np.zeros(len(robots), dtype=np.int32)
+    material = None
+    activation = None
+    plist = []
+    for i, r in enumerate(robots):
+        vox = r.voxels
+        mask = bytes(1 if v is not None else 0 for v in vox.values())
+        sens = tuple(
+            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval)
+                  for s in (ss.encode() for ss in v.get_sensors()))
+            for v in vox.values() if v is not None
+        )
+        hidden: Tuple[int, ...] = ()
+        if kind == A.VSR_CTRL_MLP:
+            f = r.controller.function
+            hidden = tuple(f.neurons[1:-1])
+            act = A.VSR_ACT[f.activation]
+            if activation is None:
+                activation = act
+            elif activation != act:
+                raise ValueError("one MLP activation per batch")
+        for v in vox.values():
+            if v is None:
+                continue
+            mb = bytes(v.material)
+            if material is None:
+                material = mb
+            elif material != mb:
+                raise NotImplementedError("one voxel material per batch on the accelerated path")
+        key = (vox.w, vox.h, mask, sens, hidden)
+        if key not in shape_keys:
+            shape_keys[key] = len(shapes_c)
+            shapes_c.append(key)
+        robot_shape[i] = shape_keys[key]
+        plist.append(np.ascontiguousarray(r.controller.params(vox, ticks), dtype=np.float64))
+    if material is None:
+        raise ValueError("robot without voxels")
+    d.material = A.vsr_material.from_buffer_copy(material)
+    d.mlp_activation = activation if activation is not None else 0
+
+    arr = (A.vsr_shape * len(shapes_c))()
+    for k, (w, h, mask, sens, hidden) in enumerate(shapes_c):
+        m = b.keep(np.frombuffer(mask, dtype=np.uint8).copy())
+        offs = np.zeros(len(sens) + 1, dtype=np.int32)
+        flat = []
+        for j, vs in enumerate(sens):
+            flat.extend(vs)
+            offs[j + 1] = len(flat)
+        b.keep(offs)
+        sarr = (A.vsr_sensor * max(1, len(flat)))()
+        nread = 0
+        for j, t in enumerate(flat):
+            s = sarr[j]
+            s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval = t
+            nread += (bin(s.axes & 3).count("1") if s.base == A.VSR_SENSOR_VELOCITY else 1)
+        b.keep(sarr)
+        hid = b.keep(np.asarray(hidden if hidden else [0], dtype=np.int32))
+        arr[k].w, arr[k].h = w, h
+        arr[k].mask = _np_ptr(m, C.c_uint8)
+        arr[k].sensor_offsets = _np_ptr(offs, C.c_int32)
+        arr[k].sensors = C.cast(sarr, C.POINTER(A.vsr_sensor))
+        arr[k].n_hidden = len(hidden)
+        arr[k].hidden = _np_ptr(hid, C.c_int32)
+        b.n_voxels.append(len(sens))
+        b.n_readings.append(nread)
+    b.keep(arr)
+    d.shapes, d.n_shapes = C.cast(arr, C.POINTER(A.vsr_shape)), len(shapes_c)
+    b.robot_shape = b.keep(robot_shape)
+    d.robot_shape = _np_ptr(robot_shape, C.c_int32)
+    offs = np.zeros(len(robots) + 1, dtype=np.uint64)
+    np.cumsum([p.size for p in plist], out=offs[1:])
+    params = b.keep(np.concatenate(plist) if plist else np.zeros(1))
+    b.keep(offs)
+    d.params = _np_ptr(params, C.c_double)
+    d.param_offsets = C.cast(offs.ctypes.data, C.POINTER(C.c_size_t))
+    return b
+
+
+class VsrError(RuntimeError):
+    pass
+
+
+def _check(lib, rc: int) -> None:
+    if rc == 0:
+        return
+    msg = lib.vsr_last_error().decode()
+    if rc in (A.VSR_ERR_INVALID_ARGUMENT,):
+        raise ValueError(msg)
+    if rc == A.VSR_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise VsrError(f"vsr error {rc}: {msg}")
+
+
+class DeviceBatch:
+    """RAII wrapper of a ``vsr_batch*``."""
+
+    def __init__(self, bd: BatchDesc):
+        self.lib = A.load_library()
+        self.bd = bd
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.vsr_batch_create(bd.ptr(), C.byref(self.h)))
+
+    def upload(self, device: int = 0, stream: int = 0):
+        _check(self.lib, self.lib.vsr_batch_upload(self.h, device, C.c_void_p(stream)))
+        return self
+
+    def run(self, stream: int = 0):
+        _check(self.lib, self.lib.vsr_batch_run(self.h, C.c_void_p(stream)))
+        return self
+
+    def results(self) -> np.ndarray:
+        n = int(self.bd.desc.n_robots)
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        _check(self.lib, self.lib.vsr_batch_results(self.h, C.cast(out.ctypes.data, C.POINTER(A.vsr_result)), n))
+        return out
+
+    def results_device(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self.lib, self.lib.vsr_batch_results_device(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def trajectory(self, robot: int) -> np.ndarray:
+        nb = self.lib.vsr_batch_n_bodies(self.h, robot)
+        nt = self.lib.vsr_batch_n_ticks(self.h)
+        out = np.zeros((nt, nb, 6), dtype=np.float64)
+        got = self.lib.vsr_batch_trajectory(self.h, robot, _np_ptr(out, C.c_double), out.size)
+        if got < 0:
+            _check(self.lib, int(got))
+        return out
+
+    def voxel_steps(self) -> int:
+        return int(self.lib.vsr_batch_voxel_steps(self.h))
+
+    def last_launches(self) -> int:
+        return int(self.lib.vsr_batch_last_launches(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.vsr_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- Locomotion
+class Locomotion:
+    """tasks/locomotion/Locomotion.java.  ``apply`` takes one Robot or a list of them
+    (the batch entry the reference lacks: ``List<Outcome> apply(List<Robot>)``)."""
+
+    INITIAL_PLACEMENT_X_GAP = 1.0
+    INITIAL_PLACEMENT_Y_GAP = 1.0
+    TERRAIN_BORDER_HEIGHT = 100.0
+    TERRAIN_LENGTH = 2000
+    TERRAIN_BORDER_WIDTH = 10.0
+
+    def __init__(self, final_t: float, ground_profile, settings: Settings, initial_placement: Optional[float] = None):
+        self.final_t = final_t
+        self.ground_profile = [list(map(float, ground_profile[0])), list(map(float, ground_profile[1]))]
+        # :50-52: groundProfile[0][1] + INITIAL_PLACEMENT_X_GAP
+        self.initial_placement = (
+            self.ground_profile[0][1] + self.INITIAL_PLACEMENT_X_GAP if initial_placement is None else initial_placement
+        )
+        self.settings = settings
+        xs, ys = self.ground_profile
+        if len(xs) != len(ys):
+            raise ValueError("xs[] and ys[] must have the same length")  # Ground.java:49-51
+        if len(xs) < 2:
+            raise ValueError("There must be at least 2 points")  # Ground.java:52-54
+        if sorted(xs) != xs:
+            raise ValueError("x coordinates must be sorted")  # Ground.java:55-58
+
+    @staticmethod
+    def create_terrain(name: str):  # :61-146
+        L, BW, BH = Locomotion.TERRAIN_LENGTH, Locomotion.TERRAIN_BORDER_WIDTH, Locomotion.TERRAIN_BORDER_HEIGHT
+        num = r"[0-9]+(\.[0-9]+)?"
+        if _params("flat", name) is not None:
+            return [[0.0, BW, L - BW, float(L)], [BH, 5.0, 5.0, BH]]
+        p = _params(r"flatWithStart-(?<seed>[0-9]+)", name)
+        if p is not None:
+            rnd = JavaRandom(int(p["seed"]))
+            for _ in range(rnd.next_int(10) + 10):
+                rnd.next_double()
+            angle = math.pi / 18.0 * (rnd.next_double() * 2.0 - 1.0)
+            start = Voxel.SIDE_LENGTH * 8.0
+            return [[0.0, BW, BW + start, L - BW, float(L)], [BH, 5 + start * math.sin(angle), 5.0, 5.0, BH]]
+        p = _params(rf"hilly-(?<h>{num})-(?<w>{num})-(?<seed>[0-9]+)", name)
+        if p is not None:
+            h, w = float(p["h"]), float(p["w"])
+            rnd = JavaRandom(int(p["seed"]))
+            xs, ys = [0.0, BW], [BH, 0.0]
+            while xs[-1] < L - BW:
+                xs.append(xs[-1] + max(1.0, (rnd.next_gaussian() * 0.25 + 1) * w))
+                ys.append(ys[-1] + rnd.next_gaussian() * h)
+            xs.append(xs[-1] + BW)
+            ys.append(BH)
+            return [xs, ys]
+        p = _params(rf"steppy-(?<h>{num})-(?<w>{num})-(?<seed>[0-9]+)", name)
+        if p is not None:
+            h, w = float(p["h"]), float(p["w"])
+            rnd = JavaRandom(int(p["seed"]))
+            xs, ys = [0.0, BW], [BH, 0.0]
+            while xs[-1] < L - BW:
+                xs.append(xs[-1] + max(1.0, (rnd.next_gaussian() * 0.25 + 1) * w))
+                xs.append(xs[-1] + 0.5)
+                ys.append(ys[-1])
+                ys.append(ys[-1] + rnd.next_gaussian() * h)
+            xs.append(xs[-1] + BW)
+            ys.append(BH)
+            return [xs, ys]
+        p = _params(rf"downhill-(?<angle>{num})", name)
+        if p is not None:
+            dy = (L - 2 * BW) * math.sin(float(p["angle"]) / 180 * math.pi)
+            return [[0.0, BW, L - BW, float(L)], [BH + dy, 5 + dy, 5.0, BH]]
+        p = _params(rf"uphill-(?<angle>{num})", name)
+        if p is not None:
+            dy = (L - 2 * BW) * math.sin(float(p["angle"]) / 180 * math.pi)
+            return [[0.0, BW, L - BW, float(L)], [BH, 5.0, 5 + dy, BH + dy]]
+        raise ValueError(f"Unknown terrain name: {name}")
+
+    def compile(self, robots: Sequence[Robot], precision: int = A.VSR_PRECISION_F32,
+                trajectory_robots: int = 0) -> BatchDesc:
+        return compile_batch(robots, self.final_t, self.ground_profile, self.initial_placement, self.settings,
+                             precision, trajectory_robots)
+
+    def apply(self, robots, device: int = 0, precision: int = A.VSR_PRECISION_F32):
+        single = isinstance(robots, Robot)
+        rs = [robots] if single else list(robots)
+        bd = self.compile(rs, precision)
+        with DeviceBatch(bd) as db:
+            db.upload(device).run()
+            res = db.results()
+        outs = [Outcome(res[i]) for i in range(len(rs))]
+        return outs[0] if single else outs

@@ -1,0 +1,252 @@
+/*
+ * vsr_b200.h -- C ABI of the B200-native batched voxel-soft-robot (VSR) stepper.
+ *
+ * This is the drop-in boundary for ONE hot path of 2D-VSR-Sim (ericmedvet/2dhmsr):
+ *   Locomotion.apply(Robot)            tasks/locomotion/Locomotion.java:168-207
+ *     -> AbstractTask.updateWorld      tasks/AbstractTask.java:41-64
+ *          -> World.step(1)            (org.dyn4j:dyn4j:4.2.1, pom.xml:31-35)
+ *          -> Robot.act(t)             core/objects/Robot.java:73-77
+ * evaluated for MANY independent robots at once on one B200.
+ *
+ * The reference has no FFI seam; a Java maintainer binds these entry points with
+ * Panama (java.lang.foreign) or JNI from a batched `Locomotion.apply(List<Robot>)`
+ * (see INTEGRATION.md).  Everything here is plain C: pointers, sizes, doubles.
+ * The caller owns every host buffer; the library owns all device memory.
+ * Handles are opaque and NOT thread-safe (one handle per host thread / GPU).
+ * There is no CPU fallback: every entry point that computes needs a CUDA device.
+ *
+ * All `double` inputs mirror the reference's Java doubles; the device computes in
+ * fp32 (VSR_PRECISION_F32, the product path) or fp64 (VSR_PRECISION_F64, parity
+ * build of the very same kernel source).
+ */
+#ifndef VSR_B200_H
+#define VSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_ABI_VERSION 1
+
+/* ---- error codes (reference convention: unchecked IllegalArgumentException at
+ *      validation time, e.g. Voxel.java:132-140, Ground.java:46-56,
+ *      CentralizedSensing.java:121-127; the Java side maps <0 to exceptions) ---- */
+#define VSR_OK 0
+#define VSR_ERR_INVALID_ARGUMENT (-1) /* -> IllegalArgumentException */
+#define VSR_ERR_UNSUPPORTED (-2)      /* valid in the reference, not on this path yet */
+#define VSR_ERR_CUDA (-3)             /* -> IllegalStateException */
+#define VSR_ERR_STATE (-4)            /* call order (e.g. results before run) */
+#define VSR_ERR_NO_DEVICE (-5)        /* no CUDA device: there is NO CPU fallback */
+
+/* ---- dyn4j Settings + World gravity (Locomotion.java:50; AbstractTask.java:35).
+ *      Defaults = dyn4j 4.2.1 `new Settings()` / `new World<>()`.                ---- */
+typedef struct vsr_settings {
+  double step_frequency;        /* 1/60  Settings.getStepFrequency(), Locomotion.java:194,197 */
+  int32_t velocity_iterations;  /* 10 */
+  int32_t position_iterations;  /* 10 */
+  double linear_tolerance;      /* 0.005 */
+  double angular_tolerance;     /* 2 deg in rad */
+  double max_linear_correction; /* 0.2 */
+  double baumgarte;             /* 0.2 */
+  double restitution_velocity;  /* 1.0 */
+  double max_translation;       /* 2.0 */
+  double max_rotation;          /* pi/2 */
+  double gravity_x;             /* 0 */
+  double gravity_y;             /* -9.8 */
+  double ground_friction;       /* 0.2  BodyFixture default (Ground.java:72 passes none) */
+  double ground_restitution;    /* 0.0 */
+  int32_t spring_mass_mode;     /* VSR_SPRING_MASS_* : which mass turns (f, zeta) into (k, d) */
+  int32_t reserved;
+} vsr_settings;
+
+#define VSR_SPRING_MASS_REDUCED 0   /* m1*m2/(m1+m2)  (Box2D-2.4 lineage)            */
+#define VSR_SPRING_MASS_EFFECTIVE 1 /* 1/(J M^-1 J^T) (dyn4j 3.x/4.0 formula)         */
+
+/* ---- Voxel material: the 13-argument constructor, Voxel.java:103-118 ---- */
+typedef struct vsr_material {
+  double side_length;             /* 3.0   Voxel.java:57 */
+  double mass_side_length_ratio;  /* 0.35  :58 */
+  double spring_f;                /* 8.0   :59 */
+  double spring_d;                /* 0.3   :60 */
+  double mass_linear_damping;     /* 0.1   :61 */
+  double mass_angular_damping;    /* 0.1   :62 */
+  double friction;                /* 10.0  :63 */
+  double restitution;             /* 0.1   :64 */
+  double mass;                    /* 1.0   :65 */
+  double area_ratio_passive_min;  /* -inf  :66 (finite => rope limits: VSR_ERR_UNSUPPORTED) */
+  double area_ratio_passive_max;  /* +inf */
+  double area_ratio_active_min;   /* 0.8   :67 */
+  double area_ratio_active_max;   /* 1.2 */
+  uint32_t spring_scaffoldings;   /* bitmask of VSR_SCAFFOLD_*; :68 = all four */
+  uint32_t reserved;
+} vsr_material;
+
+#define VSR_SCAFFOLD_SIDE_EXTERNAL 1u
+#define VSR_SCAFFOLD_SIDE_INTERNAL 2u
+#define VSR_SCAFFOLD_SIDE_CROSS 4u
+#define VSR_SCAFFOLD_CENTRAL_CROSS 8u
+#define VSR_SCAFFOLD_ALL 15u
+
+/* ---- Sensors: every entry of RobotUtils.PREDEFINED_SENSORS on the hot path is
+ *      [SoftNormalization](  [Average|Trend]( Touch | AreaRatio | Velocity ) )
+ *      (RobotUtils.java:38-53).  One vsr_sensor encodes one such composition.     ---- */
+#define VSR_SENSOR_TOUCH 0      /* sensors/Touch.java:35-65, 1 reading, domain [0,1]   */
+#define VSR_SENSOR_AREA_RATIO 1 /* sensors/AreaRatio.java:21-37, domain [0.5,1.5]      */
+#define VSR_SENSOR_VELOCITY 2   /* sensors/Velocity.java:57-80, 1-2 readings           */
+
+#define VSR_AGG_NONE 0
+#define VSR_AGG_AVERAGE 1 /* sensors/Average.java:33-45 */
+#define VSR_AGG_TREND 2   /* sensors/Trend.java:28-50   */
+
+#define VSR_AXIS_X 1
+#define VSR_AXIS_Y 2
+
+typedef struct vsr_sensor {
+  int32_t base;             /* VSR_SENSOR_*                                   */
+  int32_t axes;             /* VELOCITY: VSR_AXIS_X | VSR_AXIS_Y              */
+  int32_t rotated;          /* VELOCITY: project on the voxel's own axes      */
+  int32_t aggregator;       /* VSR_AGG_*                                      */
+  int32_t soft_norm;        /* wrap in SoftNormalization.java:38-48           */
+  int32_t reserved;
+  double max_velocity_norm; /* VELOCITY domain [-m, m]                        */
+  double interval;          /* aggregator window, seconds (0.25 / 0.5)        */
+} vsr_sensor;
+
+/* ---- Shape class: a Grid<Boolean> body + its per-voxel sensor lists.
+ *      Voxels are enumerated in Grid.values() order, i.e. row-major y*w+x with
+ *      nulls skipped (Grid.java:180-188,268-270).                              ---- */
+typedef struct vsr_shape {
+  int32_t w, h;
+  const uint8_t* mask;            /* [w*h], index y*w+x, non-zero = voxel present       */
+  const int32_t* sensor_offsets;  /* [n_voxels+1] into `sensors`, per voxel in order    */
+  const vsr_sensor* sensors;      /* concatenated per-voxel sensor lists                */
+  /* MLP controllers only: hidden layer sizes for robots of this shape             */
+  int32_t n_hidden;
+  int32_t reserved;
+  const int32_t* hidden;          /* [n_hidden]                                         */
+} vsr_shape;
+
+/* ---- Controllers (one kind per batch; parameters per robot) ---- */
+#define VSR_CTRL_PHASE_SIN 0 /* controllers/PhaseSin.java:61: sin(2*pi*f*t + phi)*A.
+                                params = [f, A, phi_0 .. phi_{nv-1}]                       */
+#define VSR_CTRL_TABULATED 1 /* any TimeFunctions (TimeFunctions.java:49-64): the host
+                                samples each voxel's lambda at the tick times.
+                                params = signal[tick][voxel], n_ticks*nv values            */
+#define VSR_CTRL_MLP 2       /* CentralizedSensing.java:85-114 + MultiLayerPerceptron
+                                .java:168-189. params = flat weights in
+                                MultiLayerPerceptron.flat order (:139-151), bias first     */
+
+#define VSR_ACT_RELU 0 /* MultiLayerPerceptron.java:89-95, enum order */
+#define VSR_ACT_SIGMOID 1
+#define VSR_ACT_SIN 2
+#define VSR_ACT_TANH 3
+#define VSR_ACT_SIGN 4
+#define VSR_ACT_IDENTITY 5
+
+#define VSR_PRECISION_F32 0
+#define VSR_PRECISION_F64 1
+
+#define VSR_FLAG_ORDER_CANONICAL 0 /* graph-coloured Gauss-Seidel   */
+
+/* ---- The batch: N robots, one terrain, one Settings (one Locomotion task) ---- */
+typedef struct vsr_batch_desc {
+  uint32_t abi_version;  /* VSR_ABI_VERSION */
+  uint32_t precision;    /* VSR_PRECISION_*  */
+  size_t n_robots;
+  /* shape classes */
+  int32_t n_shapes;
+  int32_t controller_kind; /* VSR_CTRL_* */
+  const vsr_shape* shapes;
+  const int32_t* robot_shape; /* [n_robots] index into shapes (NULL => all 0) */
+  vsr_material material;      /* one material per batch (default Voxel) */
+  /* controller parameters, ragged per robot */
+  int32_t mlp_activation;      /* VSR_ACT_* */
+  int32_t reserved0;
+  const double* params;        /* concatenated per-robot parameter vectors */
+  const size_t* param_offsets; /* [n_robots+1] */
+  /* Locomotion task: Locomotion.java:50-59 */
+  double final_t;              /* 20: loop `while (t < finalT)` with t += dt, :196 */
+  const double* terrain_xs;    /* groundProfile[0] */
+  const double* terrain_ys;    /* groundProfile[1] */
+  int32_t terrain_n;
+  int32_t reserved1;
+  double initial_placement;    /* xs[1] + 1 by default, :51 */
+  vsr_settings settings;
+  /* optional per-tick body dump for the first `trajectory_robots` robots
+     (SnapshotListener / Observation path, Locomotion.java:198-202) */
+  size_t trajectory_robots;
+} vsr_batch_desc;
+
+/* ---- Per-robot result: what Outcome needs from the first and the last
+ *      Observation (Outcome.java:42-58,126-142,152-200).                     ---- */
+typedef struct vsr_result {
+  double first_center_x, first_center_y; /* BehaviorUtils.center at t = dt   */
+  double last_center_x, last_center_y;   /* ... at the last tick             */
+  double t_first, t_last;                /* observation keys (accumulated t) */
+  double area_ratio_energy_first, area_ratio_energy_last; /* sum over voxels  */
+  double control_energy_first, control_energy_last;
+  int32_t n_ticks;
+  int32_t status; /* 0 ok, 1 = non-finite state encountered */
+} vsr_result;
+
+typedef struct vsr_batch vsr_batch;
+
+/* Fill the dyn4j / Voxel defaults. */
+void vsr_default_settings(vsr_settings* out);
+void vsr_default_material(vsr_material* out);
+
+/* Number of ticks `while (t < finalT) t += dt` runs (Java double accumulation,
+   Locomotion.java:195-203) and the tick times themselves. */
+int vsr_tick_count(double final_t, double dt);
+
+/* Validate + compile the descriptor (host only; copies everything it needs).
+   Replaces: robot.reset() + world assembly, Locomotion.java:172-191.          */
+int vsr_batch_create(const vsr_batch_desc* desc, vsr_batch** out);
+
+/* Copy the compiled batch to `device` (cudaMemcpyAsync on `stream`, a cudaStream_t
+   passed as void*, NULL = legacy default stream). */
+int vsr_batch_upload(vsr_batch* b, int device, void* stream);
+
+/* Enqueue the whole episode (all ticks of every robot) on `stream`.
+   Replaces: the `while (t < finalT)` loop, Locomotion.java:196-203.            */
+int vsr_batch_run(vsr_batch* b, void* stream);
+
+/* Wait for the run and copy the per-robot records to `out[n]` (n = n_robots).
+   Replaces: new Outcome(observations), Locomotion.java:206.                    */
+int vsr_batch_results(vsr_batch* b, vsr_result* out, size_t n);
+
+/* Device pointer to the vsr_result[n_robots] array (the buffer a final NCCL
+   gather sends from without a staging copy). */
+int vsr_batch_results_device(vsr_batch* b, void** dptr, size_t* bytes);
+
+/* Per-tick body states of robot r (< trajectory_robots):
+   out[tick][body][6] = x, y, theta, vx, vy, omega (world frame), bodies in
+   world-insertion order (voxel order, then NW, NE, SE, SW).  Returns the number
+   of doubles written, or <0.                                                   */
+long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* out, size_t capacity);
+
+/* Facts about the compiled batch. */
+size_t vsr_batch_voxel_steps(const vsr_batch* b); /* sum over robots of voxels*ticks */
+int vsr_batch_n_ticks(const vsr_batch* b);
+int vsr_batch_n_bodies(const vsr_batch* b, size_t robot);
+/* kernels launched by the last vsr_batch_run (for bench.py's gpu_launches) */
+int vsr_batch_last_launches(const vsr_batch* b);
+/* host->device bytes copied by the last vsr_batch_upload */
+size_t vsr_batch_upload_bytes(const vsr_batch* b);
+
+void vsr_batch_destroy(vsr_batch* b);
+
+/* Thread-local message for the last non-zero return. */
+const char* vsr_last_error(void);
+
+/* Library facts. */
+int vsr_abi_version(void);
+int vsr_device_count(void); /* 0 if no CUDA device / driver */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSR_B200_H */

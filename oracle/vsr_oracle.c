@@ -1,0 +1,1511 @@
+/*
+ * vsr_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT.  See vsr_oracle.h.
+ *
+ * fp64, single-robot-at-a-time CPU restatement of the hot path of 2D-VSR-Sim:
+ *
+ *   Locomotion.apply            tasks/locomotion/Locomotion.java:168-207
+ *   AbstractTask.updateWorld    tasks/AbstractTask.java:41-64
+ *   Voxel.assemble/act/applyForce/getters  core/objects/Voxel.java:197-203,224-237,239-479,508-556
+ *   Robot.assemble/act          core/objects/Robot.java:66-114
+ *   Ground / yAt                core/objects/Ground.java:43-82,104-111
+ *   sensors                     core/sensors/{Touch,AreaRatio,Velocity,AggregatorSensor,Average,
+ *                                             Trend,SoftNormalization}.java
+ *   controllers                 core/controllers/{PhaseSin,TimeFunctions,CentralizedSensing,
+ *                                                 MultiLayerPerceptron}.java
+ *   Outcome                     tasks/locomotion/Outcome.java:42-58,126-142,152-200
+ *
+ * and, for World.step(1), the published algorithm of org.dyn4j:dyn4j:4.2.1
+ * (pom.xml:31-35; Box2D lineage; NOT in /root/reference, NOT runnable here):
+ * semi-implicit Euler, soft DistanceJoint, rigid WeldJoint, SAT/clipping manifolds,
+ * sequential impulses with a 2-point block solver, Baumgarte position pass.
+ * PARITY UNPINNED for that part (no golden vector exists anywhere in the reference).
+ *
+ * Each numbered dyn4j item of SURVEY.md Appendix C sits behind one function so it
+ * can be corrected if a dyn4j 4.2.1 run ever becomes available.
+ *
+ * Documented omissions: CCD/time-of-impact pass, at-rest sleeping
+ * (actuated robots are woken every tick by setRestDistance), DistanceJoint limits
+ * (disabled by the default passive range, Voxel.java:66,264-267,331-338).
+ */
+#include "vsr_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PI 3.14159265358979323846
+#define TWO_PI (2.0 * PI)
+#define EPS_E 2.220446049250313e-16 /* dyn4j Epsilon.E = machine epsilon of double */
+
+static __thread char g_err[512];
+const char* vsr_oracle_last_error(void) { return g_err; }
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+
+void vsr_oracle_default_opts(vsr_oracle_opts* o) {
+  memset(o, 0, sizeof *o);
+  o->order = VSR_ORACLE_ORDER_CANONICAL;
+  o->n_threads = 1;
+}
+
+/* ------------------------------------------------------------------ ticks */
+/* Locomotion.java:195-203 + AbstractTask.java:48: t = 0; while (t < finalT) t = t + dT. */
+int vsr_oracle_tick_times(double final_t, double dt, double* t, int n) {
+  double tt = 0.0;
+  int k = 0;
+  while (tt < final_t) {
+    tt = tt + dt;
+    if (t && k < n) t[k] = tt;
+    k++;
+  }
+  return k;
+}
+
+/* AggregatorSensor.java:56-66: put(t); while (firstKey < t - interval) remove(firstKey). */
+int vsr_oracle_window_first(double final_t, double dt, double interval, int32_t* first, int n) {
+  int nt = vsr_oracle_tick_times(final_t, dt, NULL, 0);
+  double* t = (double*)malloc(sizeof(double) * (size_t)(nt > 0 ? nt : 1));
+  vsr_oracle_tick_times(final_t, dt, t, nt);
+  int f = 0;
+  for (int k = 0; k < nt && k < n; k++) {
+    while (t[f] < t[k] - interval) f++;
+    first[k] = f;
+  }
+  free(t);
+  return nt;
+}
+
+/* ------------------------------------------------------------------ MLP */
+/* MultiLayerPerceptron.java:89-95 */
+static double act_fn(int a, double x) {
+  switch (a) {
+    case VSR_ACT_RELU: return (x < 0) ? 0.0 : x;
+    case VSR_ACT_SIGMOID: return 1.0 / (1.0 + exp(-x));
+    case VSR_ACT_SIN: return sin(x);
+    case VSR_ACT_TANH: return tanh(x);
+    case VSR_ACT_SIGN: return (x > 0) ? 1.0 : ((x < 0) ? -1.0 : x); /* Math.signum */
+    default: return x;
+  }
+}
+
+/* MultiLayerPerceptron.java:168-189: activation on the raw inputs too (:177);
+   weights[layer][neuron][0] is the bias (:181); flat order :139-151. */
+int vsr_oracle_mlp_apply(int activation, const int32_t* neurons, int n_layers,
+                         const double* w, const double* input, double* output) {
+  int maxn = 0;
+  for (int i = 0; i < n_layers; i++)
+    if (neurons[i] > maxn) maxn = neurons[i];
+  double* a = (double*)malloc(sizeof(double) * (size_t)maxn * 2);
+  double* b = a + maxn;
+  for (int k = 0; k < neurons[0]; k++) a[k] = act_fn(activation, input[k]);
+  size_t c = 0;
+  for (int i = 1; i < n_layers; i++) {
+    for (int j = 0; j < neurons[i]; j++) {
+      double sum = w[c++]; /* bias */
+      for (int k = 1; k < neurons[i - 1] + 1; k++) sum = sum + a[k - 1] * w[c++];
+      b[j] = act_fn(activation, sum);
+    }
+    double* t = a;
+    a = b;
+    b = t;
+  }
+  for (int j = 0; j < neurons[n_layers - 1]; j++) output[j] = a[j];
+  free(a < b ? a : b);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ model */
+typedef struct {
+  double x, y, th;     /* world centre + rotation angle (dyn4j keeps cos/sin; same map) */
+  double vx, vy, w;
+  double invM, invI;
+} OBody;
+
+typedef struct {
+  int b1, b2;
+  double a1x, a1y, a2x, a2y; /* body-local anchors */
+  double rmin, rrest, rmax;  /* active SpringRange, Voxel.java:287-301 */
+  double rest;               /* current rest distance (applyForce) */
+  double imp;                /* accumulated impulse (warm start) */
+  double nx, ny, cr1, cr2, gamma, bias, soft;
+} OSpring;
+
+typedef struct {
+  int b1, b2, horizontal;
+  double a1x, a1y, a2x, a2y, ref;
+  double ix, iy, iz;
+  double r1x, r1y, r2x, r2y;
+  double K[9];
+} OWeld;
+
+typedef struct {
+  double px, py, depth;
+  int id;
+  double jn, jt;
+  double r1x, r1y, r2x, r2y; /* world offsets from the body centres at initialise time */
+  double l1x, l1y, l2x, l2y; /* the same in body-local frames (position solver) */
+  double massN, massT, vb;
+} OCPoint;
+
+typedef struct {
+  int b1;  /* dynamic mass (convex1) */
+  int b2;  /* other mass for self collision, or -1 = ground */
+  int seg; /* ground segment when b2 == -1 */
+  int n;
+  double nx, ny; /* manifold normal, from body1 to body2 */
+  double mu, e;
+  OCPoint p[2];
+  int block;
+  double K00, K01, K11, iK00, iK01, iK11;
+} OContact;
+
+typedef struct {
+  int nv, nb, ns, nw;
+  int* vox_gx;
+  int* vox_gy;
+  OBody* bodies;
+  OSpring* springs;
+  OWeld* welds;
+  int* jorder; /* joint order: >=0 spring index, <0 -> weld index ~j */
+  int nj;
+  OContact* contacts;
+  int ncontacts, cap_contacts;
+  OContact* old;
+  int nold, cap_old;
+  /* per voxel */
+  double* last_force;
+  double* ar_energy;
+  double* ctrl_energy;
+  unsigned char* touch;
+  /* sensors */
+  int n_readings;
+  double* readings;
+  /* aggregator histories: per sensor instance, ticks x dim */
+  int n_sens;
+  const vsr_sensor** sens;
+  int* sens_voxel;
+  int* sens_off;    /* offset in readings */
+  double** hist;    /* [n_sens] -> [ticks][dim] */
+  int* hist_first;  /* index of the oldest kept tick */
+  /* MLP */
+  int n_layers;
+  int32_t* neurons;
+} ORobot;
+
+typedef struct {
+  const vsr_batch_desc* d;
+  vsr_oracle_opts o;
+  const vsr_oracle_probe* probe;
+  vsr_result* out;
+  int nticks;
+  double* ticks;
+  double half; /* half mass side */
+  double base_y;
+  volatile size_t next;
+  pthread_mutex_t mu;
+  int status;
+} ORun;
+
+static int shape_nvox(const vsr_shape* s) {
+  int n = 0;
+  for (int i = 0; i < s->w * s->h; i++) n += s->mask[i] ? 1 : 0;
+  return n;
+}
+static int sensor_dim(const vsr_sensor* s) {
+  if (s->base == VSR_SENSOR_VELOCITY) return ((s->axes & VSR_AXIS_X) ? 1 : 0) + ((s->axes & VSR_AXIS_Y) ? 1 : 0);
+  return 1;
+}
+
+/* Ground.yAt, Ground.java:104-111 */
+static double ground_y_at(const vsr_batch_desc* d, double x) {
+  for (int i = 1; i < d->terrain_n; i++) {
+    if (d->terrain_xs[i - 1] <= x && x <= d->terrain_xs[i])
+      return (x - d->terrain_xs[i - 1]) * (d->terrain_ys[i] - d->terrain_ys[i - 1]) /
+                 (d->terrain_xs[i] - d->terrain_xs[i - 1]) +
+             d->terrain_ys[i - 1];
+  }
+  return NAN;
+}
+
+static void add_spring(ORobot* r, int b1, int b2, double a1x, double a1y, double a2x, double a2y,
+                       double rmin, double rrest, double rmax) {
+  OSpring* s = &r->springs[r->ns++];
+  memset(s, 0, sizeof *s);
+  s->b1 = b1;
+  s->b2 = b2;
+  s->a1x = a1x;
+  s->a1y = a1y;
+  s->a2x = a2x;
+  s->a2y = a2y;
+  s->rmin = rmin;
+  s->rrest = rrest;
+  s->rmax = rmax;
+  s->rest = rrest; /* Voxel.java:473 */
+}
+
+/* Robot.join, Robot.java:66-71: anchor = body1's centre (sic). */
+static void add_weld(ORobot* r, int b1, int b2, int horizontal) {
+  OWeld* w = &r->welds[r->nw++];
+  memset(w, 0, sizeof *w);
+  w->b1 = b1;
+  w->b2 = b2;
+  w->horizontal = horizontal;
+  OBody* B1 = &r->bodies[b1];
+  OBody* B2 = &r->bodies[b2];
+  /* localAnchor_i = body_i.getLocalPoint(anchor); bodies are unrotated at assembly */
+  w->a1x = 0.0;
+  w->a1y = 0.0;
+  w->a2x = B1->x - B2->x;
+  w->a2y = B1->y - B2->y;
+  w->ref = B1->th - B2->th;
+}
+
+static int robot_build(ORun* R, ORobot* r, size_t ridx) {
+  const vsr_batch_desc* d = R->d;
+  const vsr_material* m = &d->material;
+  const vsr_shape* sh = &d->shapes[d->robot_shape ? d->robot_shape[ridx] : 0];
+  memset(r, 0, sizeof *r);
+  int nv = shape_nvox(sh);
+  r->nv = nv;
+  r->nb = 4 * nv;
+  r->vox_gx = (int*)malloc(sizeof(int) * nv);
+  r->vox_gy = (int*)malloc(sizeof(int) * nv);
+  int* grid = (int*)malloc(sizeof(int) * sh->w * sh->h);
+  int v = 0;
+  for (int i = 0; i < sh->w * sh->h; i++) {
+    grid[i] = -1;
+    if (sh->mask[i]) {
+      r->vox_gx[v] = i % sh->w;
+      r->vox_gy[v] = i / sh->w;
+      grid[i] = v++;
+    }
+  }
+  r->bodies = (OBody*)calloc((size_t)r->nb, sizeof(OBody));
+  r->springs = (OSpring*)calloc((size_t)nv * 18, sizeof(OSpring));
+  r->welds = (OWeld*)calloc((size_t)nv * 4 + 4, sizeof(OWeld));
+
+  /* --- Voxel.assemble, Voxel.java:239-479 --- */
+  double L = m->side_length;
+  double ms = L * m->mass_side_length_ratio;                /* :241 */
+  double density = (m->mass / 4) / (ms * ms);               /* :242 */
+  double bmass = density * ms * ms;                         /* Rectangle.createMass (dyn4j) */
+  double binertia = bmass * (ms * ms + ms * ms) / 12.0;
+  double off = L / 2.0 - ms / 2.0;                          /* :253-256 */
+  double h = ms / 2.0;
+  static const double sx[4] = {-1, +1, +1, -1}; /* NW NE SE SW */
+  static const double sy[4] = {+1, +1, -1, -1};
+  /* ranges :268-301 (passive range only gates the limits, which are disabled) */
+  double amin = sqrt(L * L * m->area_ratio_active_min), amax = sqrt(L * L * m->area_ratio_active_max);
+  double sp_min = amin - 2.0 * ms, sp_rest = L - 2.0 * ms, sp_max = amax - 2.0 * ms;
+  double sc_min = sqrt(ms * ms + sp_min * sp_min), sc_rest = sqrt(ms * ms + sp_rest * sp_rest),
+         sc_max = sqrt(ms * ms + sp_max * sp_max);
+  double cc_min = (amin - ms) * sqrt(2.0), cc_rest = (L - ms) * sqrt(2.0), cc_max = (amax - ms) * sqrt(2.0);
+  for (v = 0; v < nv; v++) {
+    int b0 = 4 * v;
+    for (int k = 0; k < 4; k++) {
+      OBody* B = &r->bodies[b0 + k];
+      /* Voxel.java:253-256 then Robot.java:99 translate by (gx*L, gy*L) */
+      B->x = sx[k] * off + (double)r->vox_gx[v] * L;
+      B->y = sy[k] * off + (double)r->vox_gy[v] * L;
+      B->th = 0.0;
+      B->invM = 1.0 / bmass;
+      B->invI = 1.0 / binertia;
+    }
+    uint32_t sc = m->spring_scaffoldings;
+    if (sc & VSR_SCAFFOLD_SIDE_INTERNAL) { /* :303-341 */
+      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, -h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 1, b0 + 2, -h, -h, -h, +h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, +h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 3, b0 + 0, +h, +h, +h, -h, sp_min, sp_rest, sp_max);
+    }
+    if (sc & VSR_SCAFFOLD_SIDE_EXTERNAL) { /* :342-380 */
+      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, +h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 1, b0 + 2, +h, -h, +h, +h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, -h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 3, b0 + 0, -h, +h, -h, -h, sp_min, sp_rest, sp_max);
+    }
+    if (sc & VSR_SCAFFOLD_SIDE_CROSS) { /* :381-443 */
+      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 1, b0 + 2, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 1, b0 + 2, -h, -h, +h, +h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, -h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, +h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 3, b0 + 0, -h, +h, +h, -h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 3, b0 + 0, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
+    }
+    if (sc & VSR_SCAFFOLD_CENTRAL_CROSS) { /* :444-470 */
+      add_spring(r, b0 + 0, b0 + 2, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
+      add_spring(r, b0 + 1, b0 + 3, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
+    }
+  }
+  /* --- Robot.assemble, Robot.java:91-114: gx outer, gy inner; left pair then lower pair --- */
+  for (int gx = 0; gx < sh->w; gx++) {
+    for (int gy = 0; gy < sh->h; gy++) {
+      int vv = grid[gy * sh->w + gx];
+      if (vv < 0) continue;
+      if (gx > 0 && grid[gy * sh->w + gx - 1] >= 0) {
+        int a = grid[gy * sh->w + gx - 1];
+        add_weld(r, 4 * vv + 0, 4 * a + 1, 1);
+        add_weld(r, 4 * vv + 3, 4 * a + 2, 1);
+      }
+      if (gy > 0 && grid[(gy - 1) * sh->w + gx] >= 0) {
+        int a = grid[(gy - 1) * sh->w + gx];
+        add_weld(r, 4 * vv + 3, 4 * a + 0, 0);
+        add_weld(r, 4 * vv + 2, 4 * a + 1, 0);
+      }
+    }
+  }
+  free(grid);
+
+  /* --- placement, Locomotion.java:180-187 --- */
+  /* robot.boundingBox(): voxel bbox = outer corners (Voxel.java:481-495), unrotated here */
+  double minx = INFINITY;
+  for (v = 0; v < nv; v++) {
+    double x0 = r->bodies[4 * v + 0].x - h; /* NW body's NW corner */
+    double x3 = r->bodies[4 * v + 3].x - h;
+    if (x0 < minx) minx = x0;
+    if (x3 < minx) minx = x3;
+  }
+  double dx = d->initial_placement - minx;
+  for (int b = 0; b < r->nb; b++) r->bodies[b].x += dx;
+  double min_gap = INFINITY;
+  for (v = 0; v < nv; v++) {
+    double cx = 0, miny = INFINITY;
+    for (int k = 0; k < 4; k++) {
+      cx += r->bodies[4 * v + k].x;
+      double yy = r->bodies[4 * v + k].y - h;
+      if (yy < miny) miny = yy;
+    }
+    cx /= 4.0; /* Voxel.center, Voxel.java:497-506 */
+    double gap = miny - ground_y_at(d, cx);
+    if (gap < min_gap) min_gap = gap;
+  }
+  if (nv == 0) min_gap = 0.0;
+  double dy = 1.0 /* INITIAL_PLACEMENT_Y_GAP */ - min_gap;
+  for (int b = 0; b < r->nb; b++) r->bodies[b].y += dy;
+
+  /* --- joint order --- */
+  r->nj = r->ns + r->nw;
+  r->jorder = (int*)malloc(sizeof(int) * (size_t)(r->nj > 0 ? r->nj : 1));
+  int c = 0;
+  for (int s = 0; s < r->ns; s++) r->jorder[c++] = s;
+  if (R->o.order == VSR_ORACLE_ORDER_CANONICAL) {
+    for (int w = 0; w < r->nw; w++)
+      if (r->welds[w].horizontal) r->jorder[c++] = ~w;
+    for (int w = 0; w < r->nw; w++)
+      if (!r->welds[w].horizontal) r->jorder[c++] = ~w;
+  } else {
+    for (int w = 0; w < r->nw; w++) r->jorder[c++] = ~w;
+    if (R->o.order == VSR_ORACLE_ORDER_SHUFFLED) {
+      uint64_t st = 0x9E3779B97F4A7C15ull ^ ((uint64_t)R->o.seed * 0xD1342543DE82EF95ull) ^ (uint64_t)ridx;
+      for (int i = r->nj - 1; i > 0; i--) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        int j = (int)((st >> 33) % (uint64_t)(i + 1));
+        int t = r->jorder[i];
+        r->jorder[i] = r->jorder[j];
+        r->jorder[j] = t;
+      }
+    }
+  }
+
+  /* --- per voxel state: Voxel.reset, Voxel.java:640-651 --- */
+  r->last_force = (double*)calloc((size_t)nv, sizeof(double));
+  r->ar_energy = (double*)calloc((size_t)nv, sizeof(double));
+  r->ctrl_energy = (double*)calloc((size_t)nv, sizeof(double));
+  r->touch = (unsigned char*)calloc((size_t)nv, 1);
+
+  /* --- sensors --- */
+  int ns = sh->sensor_offsets ? sh->sensor_offsets[nv] : 0;
+  r->n_sens = ns;
+  r->sens = (const vsr_sensor**)malloc(sizeof(void*) * (size_t)(ns + 1));
+  r->sens_voxel = (int*)malloc(sizeof(int) * (size_t)(ns + 1));
+  r->sens_off = (int*)malloc(sizeof(int) * (size_t)(ns + 1));
+  r->hist = (double**)calloc((size_t)(ns + 1), sizeof(double*));
+  r->hist_first = (int*)calloc((size_t)(ns + 1), sizeof(int));
+  int off_r = 0, si = 0;
+  for (v = 0; v < nv && ns > 0; v++) {
+    for (int k = sh->sensor_offsets[v]; k < sh->sensor_offsets[v + 1]; k++) {
+      r->sens[si] = &sh->sensors[k];
+      r->sens_voxel[si] = v;
+      r->sens_off[si] = off_r;
+      int dim = sensor_dim(&sh->sensors[k]);
+      if (sh->sensors[k].aggregator != VSR_AGG_NONE)
+        r->hist[si] = (double*)malloc(sizeof(double) * (size_t)R->nticks * (size_t)dim);
+      off_r += dim;
+      si++;
+    }
+  }
+  r->n_readings = off_r;
+  r->readings = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+
+  /* --- MLP topology: CentralizedSensing.nOfInputs/nOfOutputs, :68-83 --- */
+  if (d->controller_kind == VSR_CTRL_MLP) {
+    r->n_layers = 2 + sh->n_hidden;
+    r->neurons = (int32_t*)malloc(sizeof(int32_t) * (size_t)r->n_layers);
+    r->neurons[0] = r->n_readings;
+    for (int i = 0; i < sh->n_hidden; i++) r->neurons[1 + i] = sh->hidden[i];
+    r->neurons[r->n_layers - 1] = nv;
+  }
+  return 0;
+}
+
+static void robot_free(ORobot* r) {
+  free(r->vox_gx);
+  free(r->vox_gy);
+  free(r->bodies);
+  free(r->springs);
+  free(r->welds);
+  free(r->jorder);
+  free(r->contacts);
+  free(r->old);
+  free(r->last_force);
+  free(r->ar_energy);
+  free(r->ctrl_energy);
+  free(r->touch);
+  free(r->readings);
+  for (int i = 0; i < r->n_sens; i++) free(r->hist[i]);
+  free(r->hist);
+  free(r->hist_first);
+  free((void*)r->sens);
+  free(r->sens_voxel);
+  free(r->sens_off);
+  free(r->neurons);
+}
+
+/* ------------------------------------------------------------------ dyn4j C.2 */
+/* AbstractPhysicsBody.integrateVelocity (dyn4j): no user forces are ever applied. */
+static void integrate_velocity(const vsr_batch_desc* d, OBody* b, double dt) {
+  const vsr_settings* s = &d->settings;
+  b->vx += dt * s->gravity_x;
+  b->vy += dt * s->gravity_y;
+  double lin = 1.0 - dt * d->material.mass_linear_damping;
+  lin = lin < 0 ? 0 : (lin > 1 ? 1 : lin);
+  if (d->material.mass_linear_damping != 0.0) {
+    b->vx *= lin;
+    b->vy *= lin;
+  }
+  double ang = 1.0 - dt * d->material.mass_angular_damping;
+  ang = ang < 0 ? 0 : (ang > 1 ? 1 : ang);
+  b->w *= ang;
+}
+
+/* AbstractPhysicsBody.integratePosition (dyn4j), with maxTranslation/maxRotation caps. */
+static void integrate_position(const vsr_settings* s, OBody* b, double dt) {
+  double tx = b->vx * dt, ty = b->vy * dt;
+  double m2 = tx * tx + ty * ty;
+  if (m2 > s->max_translation * s->max_translation) {
+    double ratio = s->max_translation / sqrt(m2);
+    b->vx *= ratio;
+    b->vy *= ratio;
+    tx *= ratio;
+    ty *= ratio;
+  }
+  double rot = b->w * dt;
+  if (fabs(rot) > s->max_rotation) {
+    double ratio = s->max_rotation / fabs(rot);
+    b->w *= ratio;
+    rot *= ratio;
+  }
+  b->x += tx;
+  b->y += ty;
+  b->th += rot;
+}
+
+/* ------------------------------------------------------------------ dyn4j C.3 */
+/* Which mass turns (frequency, dampingRatio) into (k, d): the single switch point. */
+static double spring_mass(const vsr_settings* s, const OBody* B1, const OBody* B2, double eff_mass) {
+  if (s->spring_mass_mode == VSR_SPRING_MASS_EFFECTIVE) return eff_mass;
+  double m1 = B1->invM > 0 ? 1.0 / B1->invM : 0.0, m2 = B2->invM > 0 ? 1.0 / B2->invM : 0.0;
+  if (m1 > 0.0 && m2 > 0.0) return m1 * m2 / (m1 + m2);
+  return m1 > 0.0 ? m1 : m2;
+}
+
+/* DistanceJoint.initializeConstraints (dyn4j), soft (frequency > 0), limits off. */
+static void spring_init(const vsr_batch_desc* d, ORobot* r, OSpring* s, double dt) {
+  OBody* B1 = &r->bodies[s->b1];
+  OBody* B2 = &r->bodies[s->b2];
+  double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+  double r1x = c1 * s->a1x - s1 * s->a1y, r1y = s1 * s->a1x + c1 * s->a1y;
+  double r2x = c2 * s->a2x - s2 * s->a2y, r2y = s2 * s->a2x + c2 * s->a2y;
+  double nx = r1x + B1->x - (r2x + B2->x), ny = r1y + B1->y - (r2y + B2->y);
+  double len = sqrt(nx * nx + ny * ny);
+  if (len < d->settings.linear_tolerance) {
+    nx = 0;
+    ny = 0;
+  } else {
+    nx *= 1.0 / len;
+    ny *= 1.0 / len;
+  }
+  double cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;
+  double invMass = B1->invM + B1->invI * cr1 * cr1;
+  invMass += B2->invM + B2->invI * cr2 * cr2;
+  double mass = invMass <= EPS_E ? 0.0 : 1.0 / invMass;
+  double x = len - s->rest;
+  double w = TWO_PI * d->material.spring_f;
+  double m = spring_mass(&d->settings, B1, B2, mass);
+  double dc = 2.0 * m * d->material.spring_d * w;
+  double k = m * w * w;
+  double gamma = dt * (dc + dt * k);
+  gamma = gamma <= EPS_E ? 0.0 : 1.0 / gamma;
+  double bias = x * dt * k * gamma;
+  invMass += gamma;
+  s->soft = invMass <= EPS_E ? 0.0 : 1.0 / invMass;
+  s->gamma = gamma;
+  s->bias = bias;
+  s->nx = nx;
+  s->ny = ny;
+  s->cr1 = cr1;
+  s->cr2 = cr2;
+  /* warm start (dtRatio = 1) */
+  double jx = nx * s->imp, jy = ny * s->imp;
+  B1->vx += jx * B1->invM;
+  B1->vy += jy * B1->invM;
+  B1->w += B1->invI * cr1 * s->imp;
+  B2->vx -= jx * B2->invM;
+  B2->vy -= jy * B2->invM;
+  B2->w -= B2->invI * cr2 * s->imp;
+}
+
+/* DistanceJoint.solveVelocityConstraints (dyn4j): Jv = n.(v1 + w1 x r1 - v2 - w2 x r2),
+   and n.(w x r) = w (r x n). */
+static void spring_solve(ORobot* r, OSpring* s) {
+  OBody* B1 = &r->bodies[s->b1];
+  OBody* B2 = &r->bodies[s->b2];
+  double Jv = s->nx * (B1->vx - B2->vx) + s->ny * (B1->vy - B2->vy) + s->cr1 * B1->w - s->cr2 * B2->w;
+  double j = -s->soft * (Jv + s->bias + s->gamma * s->imp);
+  s->imp += j;
+  double jx = s->nx * j, jy = s->ny * j;
+  B1->vx += jx * B1->invM;
+  B1->vy += jy * B1->invM;
+  B1->w += B1->invI * s->cr1 * j;
+  B2->vx -= jx * B2->invM;
+  B2->vy -= jy * B2->invM;
+  B2->w -= B2->invI * s->cr2 * j;
+}
+
+/* ------------------------------------------------------------------ dyn4j C.4 */
+static void weld_K(const OBody* B1, const OBody* B2, double r1x, double r1y, double r2x, double r2y, double* K) {
+  double m = B1->invM + B2->invM, i1 = B1->invI, i2 = B2->invI;
+  K[0] = m + r1y * r1y * i1 + r2y * r2y * i2;
+  K[1] = -r1y * r1x * i1 - r2y * r2x * i2;
+  K[2] = -r1y * i1 - r2y * i2;
+  K[3] = K[1];
+  K[4] = m + r1x * r1x * i1 + r2x * r2x * i2;
+  K[5] = r1x * i1 + r2x * i2;
+  K[6] = K[2];
+  K[7] = K[5];
+  K[8] = i1 + i2;
+}
+/* Matrix33.solve33 (dyn4j): Cramer's rule. */
+static void solve33(const double* K, double bx, double by, double bz, double* x, double* y, double* z) {
+  double det = K[0] * (K[4] * K[8] - K[5] * K[7]) - K[1] * (K[3] * K[8] - K[5] * K[6]) +
+               K[2] * (K[3] * K[7] - K[4] * K[6]);
+  if (fabs(det) > EPS_E) det = 1.0 / det;
+  double m00 = K[4] * K[8] - K[5] * K[7], m01 = K[2] * K[7] - K[1] * K[8], m02 = K[1] * K[5] - K[2] * K[4];
+  double m10 = K[5] * K[6] - K[3] * K[8], m11 = K[0] * K[8] - K[2] * K[6], m12 = K[2] * K[3] - K[0] * K[5];
+  double m20 = K[3] * K[7] - K[4] * K[6], m21 = K[1] * K[6] - K[0] * K[7], m22 = K[0] * K[4] - K[1] * K[3];
+  *x = det * (m00 * bx + m01 * by + m02 * bz);
+  *y = det * (m10 * bx + m11 * by + m12 * bz);
+  *z = det * (m20 * bx + m21 * by + m22 * bz);
+}
+
+/* WeldJoint.initializeConstraints (dyn4j), frequency = 0. */
+static void weld_init(ORobot* r, OWeld* w) {
+  OBody* B1 = &r->bodies[w->b1];
+  OBody* B2 = &r->bodies[w->b2];
+  double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+  w->r1x = c1 * w->a1x - s1 * w->a1y;
+  w->r1y = s1 * w->a1x + c1 * w->a1y;
+  w->r2x = c2 * w->a2x - s2 * w->a2y;
+  w->r2y = s2 * w->a2x + c2 * w->a2y;
+  weld_K(B1, B2, w->r1x, w->r1y, w->r2x, w->r2y, w->K);
+  /* warm start */
+  B1->vx += w->ix * B1->invM;
+  B1->vy += w->iy * B1->invM;
+  B1->w += B1->invI * (w->r1x * w->iy - w->r1y * w->ix + w->iz);
+  B2->vx -= w->ix * B2->invM;
+  B2->vy -= w->iy * B2->invM;
+  B2->w -= B2->invI * (w->r2x * w->iy - w->r2y * w->ix + w->iz);
+}
+
+/* WeldJoint.solveVelocityConstraints (dyn4j), rigid 3x3. */
+static void weld_solve(ORobot* r, OWeld* w) {
+  OBody* B1 = &r->bodies[w->b1];
+  OBody* B2 = &r->bodies[w->b2];
+  /* v + w x r, with w x r = (-w r.y, w r.x) */
+  double cx = (B1->vx - B1->w * w->r1y) - (B2->vx - B2->w * w->r2y);
+  double cy = (B1->vy + B1->w * w->r1x) - (B2->vy + B2->w * w->r2x);
+  double cz = B1->w - B2->w;
+  double ix, iy, iz;
+  solve33(w->K, -cx, -cy, -cz, &ix, &iy, &iz);
+  w->ix += ix;
+  w->iy += iy;
+  w->iz += iz;
+  B1->vx += ix * B1->invM;
+  B1->vy += iy * B1->invM;
+  B1->w += B1->invI * (w->r1x * iy - w->r1y * ix + iz);
+  B2->vx -= ix * B2->invM;
+  B2->vy -= iy * B2->invM;
+  B2->w -= B2->invI * (w->r2x * iy - w->r2y * ix + iz);
+}
+
+static double wrap_pi(double rr) {
+  if (rr < -PI) rr += TWO_PI;
+  if (rr > PI) rr -= TWO_PI;
+  return rr;
+}
+
+/* WeldJoint.solvePositionConstraints (dyn4j). */
+static int weld_position(const vsr_settings* s, ORobot* r, OWeld* w) {
+  OBody* B1 = &r->bodies[w->b1];
+  OBody* B2 = &r->bodies[w->b2];
+  double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+  double r1x = c1 * w->a1x - s1 * w->a1y, r1y = s1 * w->a1x + c1 * w->a1y;
+  double r2x = c2 * w->a2x - s2 * w->a2y, r2y = s2 * w->a2x + c2 * w->a2y;
+  double Cx = (B1->x + r1x) - (B2->x + r2x), Cy = (B1->y + r1y) - (B2->y + r2y);
+  double Cz = wrap_pi(B1->th - B2->th - w->ref);
+  double linErr = sqrt(Cx * Cx + Cy * Cy), angErr = fabs(Cz);
+  double K[9];
+  weld_K(B1, B2, r1x, r1y, r2x, r2y, K);
+  double ix, iy, iz;
+  solve33(K, -Cx, -Cy, -Cz, &ix, &iy, &iz);
+  B1->x += ix * B1->invM;
+  B1->y += iy * B1->invM;
+  B1->th += B1->invI * (r1x * iy - r1y * ix + iz);
+  B2->x -= ix * B2->invM;
+  B2->y -= iy * B2->invM;
+  B2->th -= B2->invI * (r2x * iy - r2y * ix + iz);
+  return linErr <= s->linear_tolerance && angErr <= s->angular_tolerance;
+}
+
+/* ------------------------------------------------------------------ dyn4j C.5: collision */
+typedef struct {
+  int n;
+  double vx[4], vy[4]; /* CCW world vertices */
+  double nx[4], ny[4]; /* outward normal of edge i -> i+1 */
+} OPoly;
+
+static void poly_normals(OPoly* p) {
+  for (int i = 0; i < p->n; i++) {
+    int j = (i + 1) % p->n;
+    double ex = p->vx[j] - p->vx[i], ey = p->vy[j] - p->vy[i];
+    double l = sqrt(ex * ex + ey * ey);
+    p->nx[i] = ey / l; /* left() of the CCW edge = outward */
+    p->ny[i] = -ex / l;
+  }
+}
+
+/* dyn4j Rectangle vertex order: (-h,-h) (h,-h) (h,h) (-h,h) */
+static void mass_poly(const OBody* b, double h, OPoly* p) {
+  static const double lx[4] = {-1, 1, 1, -1}, ly[4] = {-1, -1, 1, 1};
+  double c = cos(b->th), s = sin(b->th);
+  p->n = 4;
+  for (int i = 0; i < 4; i++) {
+    double x = lx[i] * h, y = ly[i] * h;
+    p->vx[i] = b->x + c * x - s * y;
+    p->vy[i] = b->y + s * x + c * y;
+  }
+  /* normals are the rotated axis directions */
+  p->nx[0] = s;
+  p->ny[0] = -c;
+  p->nx[1] = c;
+  p->ny[1] = s;
+  p->nx[2] = -s;
+  p->ny[2] = c;
+  p->nx[3] = -c;
+  p->ny[3] = -s;
+}
+
+/* Ground.java:64-70: Polygon((0,ys[i-1]), (0,baseY), (w,baseY), (w,ys[i])) translated by xs[i-1] */
+static void ground_poly(const vsr_batch_desc* d, double base_y, int seg, OPoly* p) {
+  double x0 = d->terrain_xs[seg], x1 = d->terrain_xs[seg + 1];
+  p->n = 4;
+  p->vx[0] = x0;
+  p->vy[0] = d->terrain_ys[seg];
+  p->vx[1] = x0;
+  p->vy[1] = base_y;
+  p->vx[2] = x1;
+  p->vy[2] = base_y;
+  p->vx[3] = x1;
+  p->vy[3] = d->terrain_ys[seg + 1];
+  poly_normals(p);
+}
+
+/* Narrowphase.  dyn4j runs GJK + EPA; for two convex polygons the EPA result is the
+   minimum-translation vector, i.e. the face normal (of either polygon) with the
+   smallest overlap = the SAT answer restated here.  Normal points from A to B. */
+static int sat_penetration(const OPoly* A, const OPoly* B, double* nx, double* ny, double* depth) {
+  double best = -INFINITY, bx = 0, by = 0;
+  for (int i = 0; i < A->n; i++) {
+    double s = INFINITY;
+    for (int j = 0; j < B->n; j++) {
+      double v = A->nx[i] * (B->vx[j] - A->vx[i]) + A->ny[i] * (B->vy[j] - A->vy[i]);
+      if (v < s) s = v;
+    }
+    if (s > best) {
+      best = s;
+      bx = A->nx[i];
+      by = A->ny[i];
+    }
+  }
+  for (int j = 0; j < B->n; j++) {
+    double s = INFINITY;
+    for (int i = 0; i < A->n; i++) {
+      double v = B->nx[j] * (A->vx[i] - B->vx[j]) + B->ny[j] * (A->vy[i] - B->vy[j]);
+      if (v < s) s = v;
+    }
+    if (s > best) {
+      best = s;
+      bx = -B->nx[j];
+      by = -B->ny[j];
+    }
+  }
+  if (!(best < 0.0)) return 0;
+  *nx = bx;
+  *ny = by;
+  *depth = -best;
+  return 1;
+}
+
+typedef struct {
+  double x1, y1, x2, y2; /* CCW: vertex1 -> vertex2 */
+  int i1, i2;            /* vertex indices */
+  double mx, my;         /* the farthest vertex */
+  int index;             /* edge index */
+} OEdge;
+
+/* Polygon.getFarthestFeature (dyn4j): farthest vertex, then the adjacent edge most
+   perpendicular to n, keeping the CCW winding. */
+static void farthest_edge(const OPoly* P, double nx, double ny, OEdge* e) {
+  int idx = 0;
+  double best = P->vx[0] * nx + P->vy[0] * ny;
+  for (int i = 1; i < P->n; i++) {
+    double v = P->vx[i] * nx + P->vy[i] * ny;
+    if (v > best) {
+      best = v;
+      idx = i;
+    }
+  }
+  int prev = idx == 0 ? P->n - 1 : idx - 1, next = idx == P->n - 1 ? 0 : idx + 1;
+  double ln = P->nx[prev] * nx + P->ny[prev] * ny; /* edge prev->idx */
+  double rn = P->nx[idx] * nx + P->ny[idx] * ny;   /* edge idx->next */
+  e->mx = P->vx[idx];
+  e->my = P->vy[idx];
+  if (ln < rn) {
+    e->x1 = P->vx[idx];
+    e->y1 = P->vy[idx];
+    e->i1 = idx;
+    e->x2 = P->vx[next];
+    e->y2 = P->vy[next];
+    e->i2 = next;
+    e->index = idx + 1;
+  } else {
+    e->x1 = P->vx[prev];
+    e->y1 = P->vy[prev];
+    e->i1 = prev;
+    e->x2 = P->vx[idx];
+    e->y2 = P->vy[idx];
+    e->i2 = idx;
+    e->index = idx;
+  }
+}
+
+typedef struct {
+  double x, y;
+  int idx;
+} OClipPt;
+
+/* ClippingManifoldSolver.clip (dyn4j): keep what lies at n.p <= offset. */
+static int clip_edge(const OClipPt* v1, const OClipPt* v2, double nx, double ny, double offset, OClipPt* out) {
+  int n = 0;
+  double d1 = nx * v1->x + ny * v1->y - offset, d2 = nx * v2->x + ny * v2->y - offset;
+  if (d1 <= 0.0) out[n++] = *v1;
+  if (d2 <= 0.0) out[n++] = *v2;
+  if (d1 * d2 < 0.0) {
+    double u = d1 / (d1 - d2);
+    OClipPt p;
+    p.x = v1->x + (v2->x - v1->x) * u;
+    p.y = v1->y + (v2->y - v1->y) * u;
+    p.idx = d1 > 0.0 ? v1->idx : v2->idx;
+    if (n < 2) out[n++] = p;
+  }
+  return n;
+}
+
+/* ClippingManifoldSolver.getManifold (dyn4j), both features are edges. */
+static int manifold(const OPoly* A, const OPoly* B, double nx, double ny, OContact* c) {
+  OEdge ref, inc;
+  farthest_edge(A, nx, ny, &ref);
+  farthest_edge(B, -nx, -ny, &inc);
+  int flipped = 0;
+  double e1 = fabs((ref.x2 - ref.x1) * nx + (ref.y2 - ref.y1) * ny);
+  double e2 = fabs((inc.x2 - inc.x1) * nx + (inc.y2 - inc.y1) * ny);
+  if (e1 > e2) {
+    OEdge t = ref;
+    ref = inc;
+    inc = t;
+    flipped = 1;
+  }
+  double rx = ref.x2 - ref.x1, ry = ref.y2 - ref.y1;
+  double rl = sqrt(rx * rx + ry * ry);
+  rx /= rl;
+  ry /= rl;
+  OClipPt a = {inc.x1, inc.y1, inc.i1}, b = {inc.x2, inc.y2, inc.i2}, c1[3], c2[3];
+  double o1 = -(rx * ref.x1 + ry * ref.y1);
+  if (clip_edge(&a, &b, -rx, -ry, o1, c1) < 2) return 0;
+  double o2 = rx * ref.x2 + ry * ref.y2;
+  if (clip_edge(&c1[0], &c1[1], rx, ry, o2, c2) < 2) return 0;
+  /* inward normal of the CCW reference edge; a clipped point is a contact when it
+     lies behind the reference face */
+  double fx = -ry, fy = rx;
+  double fo = fx * ref.mx + fy * ref.my;
+  /* manifold normal: reference face's outward normal, oriented from A to B */
+  c->nx = flipped ? fx : -fx;
+  c->ny = flipped ? fy : -fy;
+  c->n = 0;
+  for (int i = 0; i < 2; i++) {
+    double depth = fx * c2[i].x + fy * c2[i].y - fo;
+    if (depth >= 0.0) {
+      OCPoint* p = &c->p[c->n++];
+      memset(p, 0, sizeof *p);
+      p->px = c2[i].x;
+      p->py = c2[i].y;
+      p->depth = depth;
+      /* IndexedManifoldPointId(referenceEdge, incidentEdge, incidentVertex, flipped) */
+      p->id = (ref.index & 7) | ((inc.index & 7) << 3) | ((c2[i].idx & 7) << 6) | (flipped << 9);
+    }
+  }
+  return c->n > 0;
+}
+
+static OContact* push_contact(ORobot* r) {
+  if (r->ncontacts == r->cap_contacts) {
+    r->cap_contacts = r->cap_contacts ? 2 * r->cap_contacts : 32;
+    r->contacts = (OContact*)realloc(r->contacts, sizeof(OContact) * (size_t)r->cap_contacts);
+  }
+  return &r->contacts[r->ncontacts++];
+}
+
+/* ContactConstraint.update (dyn4j): carry jn/jt over for points with the same id. */
+static void warm_match(ORobot* r, OContact* c) {
+  for (int i = 0; i < r->nold; i++) {
+    OContact* o = &r->old[i];
+    if (o->b1 != c->b1 || o->b2 != c->b2 || o->seg != c->seg) continue;
+    for (int k = 0; k < c->n; k++)
+      for (int l = 0; l < o->n; l++)
+        if (o->p[l].id == c->p[k].id) {
+          c->p[k].jn = o->p[l].jn;
+          c->p[k].jt = o->p[l].jt;
+        }
+    return;
+  }
+}
+
+/* World.detect (dyn4j) restricted to what can collide here: every mass against the
+   ground segments its AABB overlaps (and, optionally, other masses of the robot). */
+static void detect(ORun* R, ORobot* r) {
+  const vsr_batch_desc* d = R->d;
+  /* swap current -> old */
+  OContact* t = r->old;
+  int tc = r->cap_old;
+  r->old = r->contacts;
+  r->nold = r->ncontacts;
+  r->cap_old = r->cap_contacts;
+  r->contacts = t;
+  r->cap_contacts = tc;
+  r->ncontacts = 0;
+  double mu_g = sqrt(d->material.friction * d->settings.ground_friction); /* CoefficientMixer: sqrt(f1 f2) */
+  double e_g = fmax(d->material.restitution, d->settings.ground_restitution); /* max(e1,e2) */
+  memset(r->touch, 0, (size_t)r->nv);
+  for (int b = 0; b < r->nb; b++) {
+    OPoly A;
+    mass_poly(&r->bodies[b], R->half, &A);
+    double minx = INFINITY, maxx = -INFINITY, miny = INFINITY;
+    for (int i = 0; i < 4; i++) {
+      if (A.vx[i] < minx) minx = A.vx[i];
+      if (A.vx[i] > maxx) maxx = A.vx[i];
+      if (A.vy[i] < miny) miny = A.vy[i];
+    }
+    for (int seg = 0; seg + 1 < d->terrain_n; seg++) {
+      if (d->terrain_xs[seg + 1] < minx || d->terrain_xs[seg] > maxx) continue;
+      if (!(d->terrain_xs[seg + 1] > d->terrain_xs[seg])) continue; /* zero-width: no polygon */
+      if (miny > fmax(d->terrain_ys[seg], d->terrain_ys[seg + 1])) continue;
+      OPoly G;
+      ground_poly(d, R->base_y, seg, &G);
+      double nx, ny, depth;
+      if (!sat_penetration(&A, &G, &nx, &ny, &depth)) continue;
+      OContact c;
+      memset(&c, 0, sizeof c);
+      c.b1 = b;
+      c.b2 = -1;
+      c.seg = seg;
+      c.mu = mu_g;
+      c.e = e_g;
+      if (!manifold(&A, &G, nx, ny, &c)) continue;
+      warm_match(r, &c);
+      *push_contact(r) = c;
+      r->touch[b / 4] = 1; /* Touch.java:35-48: a body whose userData != this robot */
+    }
+  }
+  if (R->o.self_collision) {
+    /* masses of the same robot collide unless welded (Voxel.java:178-185,474) */
+    double mu_s = sqrt(d->material.friction * d->material.friction);
+    double e_s = d->material.restitution;
+    for (int a = 0; a < r->nb; a++) {
+      for (int b = a + 1; b < r->nb; b++) {
+        OBody* A0 = &r->bodies[a];
+        OBody* B0 = &r->bodies[b];
+        double rr = 2.0 * R->half * 1.4142135623730951;
+        if (fabs(A0->x - B0->x) > rr || fabs(A0->y - B0->y) > rr) continue;
+        int welded = 0;
+        for (int w = 0; w < r->nw && !welded; w++)
+          if ((r->welds[w].b1 == a && r->welds[w].b2 == b) || (r->welds[w].b1 == b && r->welds[w].b2 == a))
+            welded = 1;
+        if (welded) continue;
+        OPoly A, B;
+        mass_poly(A0, R->half, &A);
+        mass_poly(B0, R->half, &B);
+        double nx, ny, depth;
+        if (!sat_penetration(&A, &B, &nx, &ny, &depth)) continue;
+        OContact c;
+        memset(&c, 0, sizeof c);
+        c.b1 = a;
+        c.b2 = b;
+        c.seg = -1;
+        c.mu = mu_s;
+        c.e = e_s;
+        if (!manifold(&A, &B, nx, ny, &c)) continue;
+        warm_match(r, &c);
+        *push_contact(r) = c;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ dyn4j C.5: solver */
+static const OBody STATIC_BODY = {0, 0, 0, 0, 0, 0, 0, 0};
+
+/* SequentialImpulses.initialize (dyn4j) for one constraint, then its warm start.
+   Convention: N points from body1 to body2; lambda >= 0 pushes body1 along -N and
+   body2 along +N (Box2D's A/B roles). */
+static void contact_init(const vsr_settings* s, ORobot* r, OContact* c) {
+  OBody* B1 = &r->bodies[c->b1];
+  const OBody* B2 = c->b2 >= 0 ? &r->bodies[c->b2] : &STATIC_BODY;
+  double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+  double nx = c->nx, ny = c->ny, tx = ny, ty = -nx; /* tangent = left-hand orthogonal of N */
+  for (int k = 0; k < c->n; k++) {
+    OCPoint* p = &c->p[k];
+    p->r1x = p->px - B1->x;
+    p->r1y = p->py - B1->y;
+    p->r2x = p->px - B2->x;
+    p->r2y = p->py - B2->y;
+    p->l1x = c1 * p->r1x + s1 * p->r1y;
+    p->l1y = -s1 * p->r1x + c1 * p->r1y;
+    p->l2x = c2 * p->r2x + s2 * p->r2y;
+    p->l2y = -s2 * p->r2x + c2 * p->r2y;
+    double rn1 = p->r1x * ny - p->r1y * nx, rn2 = p->r2x * ny - p->r2y * nx;
+    p->massN = 1.0 / (B1->invM + B2->invM + B1->invI * rn1 * rn1 + B2->invI * rn2 * rn2);
+    double rt1 = p->r1x * ty - p->r1y * tx, rt2 = p->r2x * ty - p->r2y * tx;
+    p->massT = 1.0 / (B1->invM + B2->invM + B1->invI * rt1 * rt1 + B2->invI * rt2 * rt2);
+    /* relative velocity of body2 w.r.t. body1 at the point, along N: < 0 = approaching */
+    double rvx = (B2->vx - B2->w * p->r2y) - (B1->vx - B1->w * p->r1y);
+    double rvy = (B2->vy + B2->w * p->r2x) - (B1->vy + B1->w * p->r1x);
+    double rvn = nx * rvx + ny * rvy;
+    p->vb = 0.0;
+    if (rvn < -s->restitution_velocity) p->vb += -c->e * rvn;
+  }
+  c->block = 0;
+  if (c->n == 2) {
+    double rn1A = c->p[0].r1x * ny - c->p[0].r1y * nx, rn1B = c->p[0].r2x * ny - c->p[0].r2y * nx;
+    double rn2A = c->p[1].r1x * ny - c->p[1].r1y * nx, rn2B = c->p[1].r2x * ny - c->p[1].r2y * nx;
+    double m = B1->invM + B2->invM;
+    c->K00 = m + B1->invI * rn1A * rn1A + B2->invI * rn1B * rn1B;
+    c->K01 = m + B1->invI * rn1A * rn2A + B2->invI * rn1B * rn2B;
+    c->K11 = m + B1->invI * rn2A * rn2A + B2->invI * rn2B * rn2B;
+    double det = c->K00 * c->K11 - c->K01 * c->K01;
+    const double maxCondition = 1000.0;
+    if (c->K00 * c->K00 < maxCondition * det) {
+      c->block = 1;
+      double id = 1.0 / det;
+      c->iK00 = id * c->K11;
+      c->iK01 = -id * c->K01;
+      c->iK11 = id * c->K00;
+    } else {
+      c->n = 1; /* ill conditioned: keep only the first point */
+    }
+  }
+}
+
+static void contact_apply(OBody* B1, OBody* B2m, const OCPoint* p, double Px, double Py) {
+  B1->vx -= B1->invM * Px;
+  B1->vy -= B1->invM * Py;
+  B1->w -= B1->invI * (p->r1x * Py - p->r1y * Px);
+  if (B2m) {
+    B2m->vx += B2m->invM * Px;
+    B2m->vy += B2m->invM * Py;
+    B2m->w += B2m->invI * (p->r2x * Py - p->r2y * Px);
+  }
+}
+
+static void contact_warm(ORobot* r, OContact* c) {
+  OBody* B1 = &r->bodies[c->b1];
+  OBody* B2 = c->b2 >= 0 ? &r->bodies[c->b2] : NULL;
+  double nx = c->nx, ny = c->ny, tx = ny, ty = -nx;
+  for (int k = 0; k < c->n; k++) {
+    OCPoint* p = &c->p[k];
+    contact_apply(B1, B2, p, nx * p->jn + tx * p->jt, ny * p->jn + ty * p->jt);
+  }
+}
+
+static void rel_vel(const OBody* B1, const OBody* B2, const OCPoint* p, double* rvx, double* rvy) {
+  *rvx = (B2->vx - B2->w * p->r2y) - (B1->vx - B1->w * p->r1y);
+  *rvy = (B2->vy + B2->w * p->r2x) - (B1->vy + B1->w * p->r1x);
+}
+
+/* SequentialImpulses.solveVelocityConstraints (dyn4j) for one constraint: friction of
+   every point first, then the normal constraint(s) (block solver for 2 points). */
+static void contact_solve(ORobot* r, OContact* c) {
+  OBody* B1 = &r->bodies[c->b1];
+  OBody* B2m = c->b2 >= 0 ? &r->bodies[c->b2] : NULL;
+  const OBody* B2 = B2m ? B2m : &STATIC_BODY;
+  double nx = c->nx, ny = c->ny, tx = ny, ty = -nx;
+  for (int k = 0; k < c->n; k++) {
+    OCPoint* p = &c->p[k];
+    double rvx, rvy;
+    rel_vel(B1, B2, p, &rvx, &rvy);
+    double tn = tx * rvx + ty * rvy;
+    double jt = p->massT * (-tn);
+    double maxJt = c->mu * p->jn;
+    double Jt0 = p->jt;
+    p->jt = fmax(-maxJt, fmin(Jt0 + jt, maxJt));
+    jt = p->jt - Jt0;
+    contact_apply(B1, B2m, p, tx * jt, ty * jt);
+  }
+  if (c->n == 1 || !c->block) {
+    for (int k = 0; k < c->n; k++) {
+      OCPoint* p = &c->p[k];
+      double rvx, rvy;
+      rel_vel(B1, B2, p, &rvx, &rvy);
+      double rvn = nx * rvx + ny * rvy;
+      double j = -p->massN * (rvn - p->vb);
+      double j0 = p->jn;
+      p->jn = fmax(j0 + j, 0.0);
+      j = p->jn - j0;
+      contact_apply(B1, B2m, p, nx * j, ny * j);
+    }
+  } else {
+    OCPoint* p1 = &c->p[0];
+    OCPoint* p2 = &c->p[1];
+    double ax = p1->jn, ay = p2->jn;
+    double rvx, rvy;
+    rel_vel(B1, B2, p1, &rvx, &rvy);
+    double rvn1 = nx * rvx + ny * rvy;
+    rel_vel(B1, B2, p2, &rvx, &rvy);
+    double rvn2 = nx * rvx + ny * rvy;
+    double bx = rvn1 - p1->vb, by = rvn2 - p2->vb;
+    bx -= c->K00 * ax + c->K01 * ay;
+    by -= c->K01 * ax + c->K11 * ay;
+    double x = 0, y = 0;
+    int ok = 0;
+    /* case 1: both active */
+    x = -(c->iK00 * bx + c->iK01 * by);
+    y = -(c->iK01 * bx + c->iK11 * by);
+    if (x >= 0.0 && y >= 0.0) ok = 1;
+    if (!ok) { /* case 2: x1 active, x2 = 0 */
+      x = -p1->massN * bx;
+      y = 0.0;
+      double v2 = c->K01 * x + by;
+      if (x >= 0.0 && v2 >= 0.0) ok = 1;
+    }
+    if (!ok) { /* case 3 */
+      x = 0.0;
+      y = -p2->massN * by;
+      double v1 = c->K01 * y + bx;
+      if (y >= 0.0 && v1 >= 0.0) ok = 1;
+    }
+    if (!ok) { /* case 4 */
+      x = 0.0;
+      y = 0.0;
+      if (bx >= 0.0 && by >= 0.0) ok = 1;
+    }
+    if (ok) {
+      double dx = x - ax, dy = y - ay;
+      contact_apply(B1, B2m, p1, nx * dx, ny * dx);
+      contact_apply(B1, B2m, p2, nx * dy, ny * dy);
+      p1->jn = x;
+      p2->jn = y;
+    }
+  }
+}
+
+/* SequentialImpulses.solvePositionContraints (dyn4j) for one constraint.
+   Returns the minimum separation seen. */
+static double contact_position(const vsr_settings* s, ORobot* r, OContact* c) {
+  OBody* B1 = &r->bodies[c->b1];
+  OBody* B2m = c->b2 >= 0 ? &r->bodies[c->b2] : NULL;
+  double minSep = 0.0;
+  double nx = c->nx, ny = c->ny;
+  for (int k = 0; k < c->n; k++) {
+    OCPoint* p = &c->p[k];
+    const OBody* B2 = B2m ? B2m : &STATIC_BODY;
+    double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+    double r1x = c1 * p->l1x - s1 * p->l1y, r1y = s1 * p->l1x + c1 * p->l1y;
+    double r2x = c2 * p->l2x - s2 * p->l2y, r2y = s2 * p->l2x + c2 * p->l2y;
+    double p1x = B1->x + r1x, p1y = B1->y + r1y;
+    double p2x = (B2m ? B2->x : p->px - p->r2x) + r2x, p2y = (B2m ? B2->y : p->py - p->r2y) + r2y;
+    double sep = (p2x - p1x) * nx + (p2y - p1y) * ny - p->depth;
+    if (sep < minSep) minSep = sep;
+    double cl = sep + s->linear_tolerance;
+    cl = cl < -s->max_linear_correction ? -s->max_linear_correction : (cl > 0.0 ? 0.0 : cl);
+    double cp = s->baumgarte * cl;
+    double rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
+    double K = B1->invM + B2->invM + B1->invI * rn1 * rn1 + B2->invI * rn2 * rn2;
+    double jp = (K > EPS_E) ? (-cp / K) : 0.0;
+    double Jx = nx * jp, Jy = ny * jp;
+    B1->x -= Jx * B1->invM;
+    B1->y -= Jy * B1->invM;
+    B1->th -= B1->invI * (r1x * Jy - r1y * Jx);
+    if (B2m) {
+      B2m->x += Jx * B2m->invM;
+      B2m->y += Jy * B2m->invM;
+      B2m->th += B2m->invI * (r2x * Jy - r2y * Jx);
+    }
+  }
+  return minSep;
+}
+
+/* ------------------------------------------------------------------ World.step(1) */
+static int world_step(ORun* R, ORobot* r, double dt) {
+  const vsr_batch_desc* d = R->d;
+  const vsr_settings* s = &d->settings;
+  /* Island.solve (dyn4j): integrate velocities */
+  for (int b = 0; b < r->nb; b++) integrate_velocity(d, &r->bodies[b], dt);
+  /* solver.initialize(contacts): all masses/biases first, then all warm starts */
+  for (int i = 0; i < r->ncontacts; i++) contact_init(s, r, &r->contacts[i]);
+  for (int i = 0; i < r->ncontacts; i++) contact_warm(r, &r->contacts[i]);
+  /* joints: initializeConstraints (+ warm start) */
+  for (int i = 0; i < r->nj; i++) {
+    int j = r->jorder[i];
+    if (j >= 0) spring_init(d, r, &r->springs[j], dt);
+    else weld_init(r, &r->welds[~j]);
+  }
+  /* velocity iterations: all joints, then all contacts */
+  for (int it = 0; it < s->velocity_iterations; it++) {
+    for (int i = 0; i < r->nj; i++) {
+      int j = r->jorder[i];
+      if (j >= 0) spring_solve(r, &r->springs[j]);
+      else weld_solve(r, &r->welds[~j]);
+    }
+    for (int i = 0; i < r->ncontacts; i++) contact_solve(r, &r->contacts[i]);
+  }
+  for (int b = 0; b < r->nb; b++) integrate_position(s, &r->bodies[b], dt);
+  /* position iterations: contacts, then joints; stop when both report solved */
+  int iters = 0;
+  for (int it = 0; it < s->position_iterations; it++) {
+    iters++;
+    double minSep = 0.0;
+    for (int i = 0; i < r->ncontacts; i++) {
+      double ms = contact_position(s, r, &r->contacts[i]);
+      if (ms < minSep) minSep = ms;
+    }
+    int contactsSolved = minSep >= -3.0 * s->linear_tolerance;
+    int jointsSolved = 1;
+    for (int i = 0; i < r->nj; i++) {
+      int j = r->jorder[i];
+      if (j >= 0) continue; /* DistanceJoint with frequency > 0: nothing to do, "solved" */
+      int ok = weld_position(s, r, &r->welds[~j]);
+      jointsSolved = jointsSolved && ok;
+    }
+    if (contactsSolved && jointsSolved) break;
+  }
+  /* new contacts for Touch and for the next step */
+  detect(R, r);
+  return iters;
+}
+
+/* ------------------------------------------------------------------ voxel getters */
+/* outer corner of body k: getIndexedVertex(k, 3-k), Voxel.java:536-542,596-603 */
+static void outer_corner(const ORun* R, const OBody* b, int k, double* x, double* y) {
+  static const double lx[4] = {-1, +1, +1, -1}, ly[4] = {+1, +1, -1, -1};
+  double c = cos(b->th), s = sin(b->th), px = lx[k] * R->half, py = ly[k] * R->half;
+  *x = b->x + c * px - s * py;
+  *y = b->y + s * px + c * py;
+}
+
+/* Voxel.area (:508-516) with Poly.area (Poly.java:40-49), Voxel.getAreaRatio (:524-526) */
+static double voxel_area_ratio(const ORun* R, const ORobot* r, int v) {
+  double X[4], Y[4];
+  for (int k = 0; k < 4; k++) outer_corner(R, &r->bodies[4 * v + k], k, &X[k], &Y[k]);
+  double a = 0.0;
+  for (int i = 0; i < 4; i++) a = a + X[i] * (Y[(4 + i + 1) % 4] - Y[(4 + i - 1) % 4]);
+  a = 0.5 * fabs(a);
+  double L = R->d->material.side_length;
+  return a / L / L;
+}
+
+/* VoxelPoly.center = Poly.center = mean of the 4 outer corners (VoxelPoly.java:109-112) */
+static void voxel_poly_center(const ORun* R, const ORobot* r, int v, double* cx, double* cy) {
+  double sx = 0, sy = 0;
+  for (int k = 0; k < 4; k++) {
+    double x, y;
+    outer_corner(R, &r->bodies[4 * v + k], k, &x, &y);
+    sx += x;
+    sy += y;
+  }
+  *cx = sx / 4.0;
+  *cy = sy / 4.0;
+}
+
+/* Voxel.getAngle, :518-522 */
+static double voxel_angle(const ORobot* r, int v) {
+  const OBody* b = &r->bodies[4 * v];
+  double up = atan2(b[1].y - b[0].y, b[1].x - b[0].x);
+  double down = atan2(b[2].y - b[3].y, b[2].x - b[3].x);
+  return (up + down) / 2.0;
+}
+
+/* DoubleRange.normalize + SoftNormalization.sense, SoftNormalization.java:38-48 */
+static double soft_norm(double x, double mn, double mx) {
+  double cl = fmin(fmax(x, mn), mx);
+  double v = (cl - mn) / (mx - mn);
+  return tanh(((v * 2.0) - 1.0) * 2.0) / 2.0 + 0.5;
+}
+
+/* Voxel.act (:197-203) for all voxels, then sensors (CompositeSensor.act: inner first). */
+static void robot_sense(ORun* R, ORobot* r, int tick) {
+  const double* T = R->ticks;
+  for (int v = 0; v < r->nv; v++) {
+    double ar = voxel_area_ratio(R, r, v);
+    r->ar_energy[v] = r->ar_energy[v] + ar * ar;
+    r->ctrl_energy[v] = r->ctrl_energy[v] + r->last_force[v] * r->last_force[v];
+  }
+  for (int si = 0; si < r->n_sens; si++) {
+    const vsr_sensor* S = r->sens[si];
+    int v = r->sens_voxel[si];
+    int dim = sensor_dim(S);
+    double raw[2] = {0, 0}, dmin = 0, dmax = 1;
+    if (S->base == VSR_SENSOR_TOUCH) {
+      raw[0] = r->touch[v] ? 1.0 : 0.0;
+    } else if (S->base == VSR_SENSOR_AREA_RATIO) {
+      raw[0] = voxel_area_ratio(R, r, v);
+      dmin = 0.5;
+      dmax = 1.5;
+    } else { /* Velocity.sense, Velocity.java:57-80 */
+      const OBody* b = &r->bodies[4 * v];
+      double vx = 0, vy = 0;
+      for (int k = 0; k < 4; k++) {
+        vx = vx + b[k].vx;
+        vy = vy + b[k].vy;
+      }
+      vx /= 4.0;
+      vy /= 4.0;
+      double ang = voxel_angle(r, v);
+      int c = 0;
+      if (S->axes & VSR_AXIS_X) raw[c++] = S->rotated ? vx * cos(ang) + vy * sin(ang) : vx;
+      if (S->axes & VSR_AXIS_Y) raw[c++] = S->rotated ? vx * cos(ang + PI / 2.0) + vy * sin(ang + PI / 2.0) : vy;
+      dmin = -S->max_velocity_norm;
+      dmax = S->max_velocity_norm;
+    }
+    double val[2] = {raw[0], raw[1]};
+    if (S->aggregator != VSR_AGG_NONE) {
+      double* H = r->hist[si];
+      for (int k = 0; k < dim; k++) H[(size_t)tick * dim + k] = raw[k];
+      int f = r->hist_first[si];
+      while (T[f] < T[tick] - S->interval) f++;
+      r->hist_first[si] = f;
+      if (S->aggregator == VSR_AGG_AVERAGE) {
+        for (int k = 0; k < dim; k++) {
+          double sum = 0.0;
+          for (int q = f; q <= tick; q++) sum = sum + H[(size_t)q * dim + k];
+          val[k] = sum / (double)(tick - f + 1);
+        }
+      } else { /* Trend.aggregate, Trend.java:37-50 */
+        double li = T[tick] - T[f];
+        for (int k = 0; k < dim; k++)
+          val[k] = (li == 0) ? 0.0 : (H[(size_t)tick * dim + k] - H[(size_t)f * dim + k]) / li;
+        double ext = dmax - dmin; /* Trend domain: +-extent/interval, Trend.java:31-33 */
+        dmin = -ext / S->interval;
+        dmax = ext / S->interval;
+      }
+    }
+    for (int k = 0; k < dim; k++)
+      r->readings[r->sens_off[si] + k] = S->soft_norm ? soft_norm(val[k], dmin, dmax) : val[k];
+  }
+}
+
+/* Voxel.applyForce, :224-237 */
+static void voxel_apply_force(ORobot* r, int v, double f) {
+  if (fabs(f) > 1.0) f = (f > 0) ? 1.0 : -1.0;
+  r->last_force[v] = f;
+  int per = r->ns / (r->nv > 0 ? r->nv : 1);
+  for (int k = 0; k < per; k++) {
+    OSpring* s = &r->springs[v * per + k];
+    if (f >= 0) s->rest = s->rrest - (s->rrest - s->rmin) * f;
+    else if (f < 0) s->rest = s->rrest + (s->rmax - s->rrest) * -f;
+  }
+}
+
+static void robot_control(ORun* R, ORobot* r, size_t ridx, int tick, double* sig_out) {
+  const vsr_batch_desc* d = R->d;
+  const double* P = d->params + d->param_offsets[ridx];
+  double t = R->ticks[tick];
+  double out_stack[64];
+  double* out = r->nv <= 64 ? out_stack : (double*)malloc(sizeof(double) * (size_t)r->nv);
+  if (d->controller_kind == VSR_CTRL_PHASE_SIN) {
+    for (int v = 0; v < r->nv; v++) out[v] = sin(2.0 * PI * P[0] * t + P[2 + v]) * P[1]; /* PhaseSin.java:61 */
+  } else if (d->controller_kind == VSR_CTRL_TABULATED) {
+    for (int v = 0; v < r->nv; v++) out[v] = P[(size_t)tick * (size_t)r->nv + v];
+  } else {
+    vsr_oracle_mlp_apply(d->mlp_activation, r->neurons, r->n_layers, P, r->readings, out);
+  }
+  for (int v = 0; v < r->nv; v++) {
+    voxel_apply_force(r, v, out[v]);
+    if (sig_out) sig_out[v] = r->last_force[v];
+  }
+  if (out != out_stack) free(out);
+}
+
+static void observe(ORun* R, ORobot* r, double* cx, double* cy, double* are, double* ce) {
+  double sx = 0, sy = 0, a = 0, c = 0;
+  for (int v = 0; v < r->nv; v++) { /* BehaviorUtils.center, :47-56 */
+    double x, y;
+    voxel_poly_center(R, r, v, &x, &y);
+    sx = sx + x;
+    sy = sy + y;
+    a += r->ar_energy[v];
+    c += r->ctrl_energy[v];
+  }
+  *cx = sx / (double)r->nv;
+  *cy = sy / (double)r->nv;
+  *are = a;
+  *ce = c;
+}
+
+static void run_robot(ORun* R, size_t ridx) {
+  const vsr_batch_desc* d = R->d;
+  size_t row = ridx - R->o.robot_begin;
+  ORobot rob;
+  robot_build(R, &rob, ridx);
+  ORobot* r = &rob;
+  vsr_result* res = &R->out[row];
+  memset(res, 0, sizeof *res);
+  double dt = d->settings.step_frequency;
+  int nt = R->nticks;
+  if (R->o.max_ticks > 0 && R->o.max_ticks < nt) nt = R->o.max_ticks;
+  const vsr_oracle_probe* pb = R->probe;
+  /* World is created with updateRequired = true: the first step() runs detect() first */
+  detect(R, r);
+  for (int k = 0; k < nt; k++) {
+    int iters = world_step(R, r, dt);  /* AbstractTask.java:49 */
+    robot_sense(R, r, k);              /* Robot.act: Voxel.act for every voxel ... */
+    double* sig = (pb && pb->signals) ? pb->signals + ((size_t)row * R->nticks + k) * pb->voxel_stride : NULL;
+    robot_control(R, r, ridx, k, sig); /* ... then controller.control, Robot.java:74-77 */
+    double cx, cy, are, ce;
+    observe(R, r, &cx, &cy, &are, &ce); /* Locomotion.java:198-202 */
+    if (k == 0) {
+      res->first_center_x = cx;
+      res->first_center_y = cy;
+      res->t_first = R->ticks[k];
+      res->area_ratio_energy_first = are;
+      res->control_energy_first = ce;
+    }
+    res->last_center_x = cx;
+    res->last_center_y = cy;
+    res->t_last = R->ticks[k];
+    res->area_ratio_energy_last = are;
+    res->control_energy_last = ce;
+    res->n_ticks = k + 1;
+    if (!isfinite(cx) || !isfinite(cy)) res->status = 1;
+    if (pb) {
+      if (pb->trajectory) {
+        double* o = pb->trajectory + ((size_t)row * R->nticks + k) * pb->body_stride * 6;
+        for (int b = 0; b < r->nb && (size_t)b < pb->body_stride; b++) {
+          o[6 * b + 0] = r->bodies[b].x;
+          o[6 * b + 1] = r->bodies[b].y;
+          o[6 * b + 2] = r->bodies[b].th;
+          o[6 * b + 3] = r->bodies[b].vx;
+          o[6 * b + 4] = r->bodies[b].vy;
+          o[6 * b + 5] = r->bodies[b].w;
+        }
+      }
+      if (pb->readings) {
+        double* o = pb->readings + ((size_t)row * R->nticks + k) * pb->reading_stride;
+        for (int q = 0; q < r->n_readings && (size_t)q < pb->reading_stride; q++) o[q] = r->readings[q];
+      }
+      if (pb->n_contacts) pb->n_contacts[(size_t)row * R->nticks + k] = r->ncontacts;
+      if (pb->pos_iters) pb->pos_iters[(size_t)row * R->nticks + k] = iters;
+    }
+  }
+  robot_free(r);
+}
+
+static void* worker(void* arg) {
+  ORun* R = (ORun*)arg;
+  size_t end = R->o.robot_end;
+  for (;;) {
+    pthread_mutex_lock(&R->mu);
+    size_t i = R->next++;
+    pthread_mutex_unlock(&R->mu);
+    if (i >= end) break;
+    run_robot(R, i);
+  }
+  return NULL;
+}
+
+static int validate(const vsr_batch_desc* d) {
+  if (!d) return fail(VSR_ERR_INVALID_ARGUMENT, "null descriptor");
+  if (d->abi_version != VSR_ABI_VERSION) return fail(VSR_ERR_INVALID_ARGUMENT, "abi version mismatch");
+  if (d->n_shapes <= 0 || !d->shapes) return fail(VSR_ERR_INVALID_ARGUMENT, "no shapes");
+  if (d->terrain_n < 2 || !d->terrain_xs || !d->terrain_ys)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "There must be at least 2 points"); /* Ground.java:52-54 */
+  for (int i = 1; i < d->terrain_n; i++)
+    if (d->terrain_xs[i] < d->terrain_xs[i - 1])
+      return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted"); /* Ground.java:55-58 */
+  if (isfinite(d->material.area_ratio_passive_min) || isfinite(d->material.area_ratio_passive_max))
+    return fail(VSR_ERR_UNSUPPORTED, "finite areaRatioPassiveRange (DistanceJoint limits) not restated");
+  if (!d->param_offsets || !d->params) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
+  return 0;
+}
+
+int vsr_oracle_run(const vsr_batch_desc* d, const vsr_oracle_opts* opts, vsr_result* out,
+                   const vsr_oracle_probe* probe) {
+  int rc = validate(d);
+  if (rc) return rc;
+  ORun R;
+  memset(&R, 0, sizeof R);
+  R.d = d;
+  if (opts) R.o = *opts;
+  else vsr_oracle_default_opts(&R.o);
+  if (R.o.robot_end == 0 || R.o.robot_end > d->n_robots) R.o.robot_end = d->n_robots;
+  if (R.o.robot_begin > R.o.robot_end) return fail(VSR_ERR_INVALID_ARGUMENT, "robot range");
+  R.probe = probe;
+  R.out = out;
+  double dt = d->settings.step_frequency;
+  R.nticks = vsr_oracle_tick_times(d->final_t, dt, NULL, 0);
+  R.ticks = (double*)malloc(sizeof(double) * (size_t)(R.nticks + 1));
+  vsr_oracle_tick_times(d->final_t, dt, R.ticks, R.nticks);
+  double miny = INFINITY;
+  for (int i = 0; i < d->terrain_n; i++)
+    if (d->terrain_ys[i] < miny) miny = d->terrain_ys[i];
+  R.base_y = miny - 50.0; /* Ground.MIN_Y_THICKNESS, Ground.java:37,61 */
+  R.half = d->material.side_length * d->material.mass_side_length_ratio / 2.0;
+  R.next = R.o.robot_begin;
+  pthread_mutex_init(&R.mu, NULL);
+  int nth = R.o.n_threads > 0 ? R.o.n_threads : 1;
+  if (nth == 1) {
+    worker(&R);
+  } else {
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nth);
+    for (int i = 0; i < nth; i++) pthread_create(&th[i], NULL, worker, &R);
+    for (int i = 0; i < nth; i++) pthread_join(th[i], NULL);
+    free(th);
+  }
+  pthread_mutex_destroy(&R.mu);
+  free(R.ticks);
+  return 0;
+}
