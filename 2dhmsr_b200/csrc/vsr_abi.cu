@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -605,13 +606,32 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   for (int i = 0; i < k.shape.n_layers; i++) maxn = std::max(maxn, k.shape.neurons[i]);
   int per_robot = 2 * ((maxn + 3) & ~3);
   P.smem_per_warp = std::max(128, per_robot * G);
-  const int threads = 128, wpb = threads / 32;
+  int wpb_env = getenv("VSR_WPB") ? atoi(getenv("VSR_WPB")) : 0;
+  const long long groups_all = ((long long)k.robot_ids.size() + G - 1) / G;
+  // Warps of a block walk the instruction stream together (see the barriers in the kernel), so
+  // the more warps per block the better, up to the register-file limit of 12.  A batch that does
+  // not fill the chip is spread as one block per SM with just enough warps each.
+  int wpb = 12;
+  {
+    int sms_ = 148;
+    cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, b->device);
+    if (groups_all <= (long long)sms_ * 12) wpb = (int)std::max<long long>(1, (groups_all + sms_ - 1) / sms_);
+  }
+  if (wpb_env > 0) wpb = std::min(12, wpb_env);
+  const int threads = 32 * wpb;
   const size_t smem = (size_t)wpb * P.smem_per_warp * sizeof(real);
   void (*kern)(const Params<real>) = nullptr;
+  const bool full = (b->spring_mask == 0x3FFFFu);
   switch (d.controller_kind) {
-    case VSR_CTRL_PHASE_SIN: kern = vsr_episode_kernel<real, CTRL_PHASE_SIN>; break;
-    case VSR_CTRL_TABULATED: kern = vsr_episode_kernel<real, CTRL_TABULATED>; break;
-    default: kern = vsr_episode_kernel<real, CTRL_MLP>; break;
+    case VSR_CTRL_PHASE_SIN:
+      kern = full ? vsr_episode_kernel<real, CTRL_PHASE_SIN, true> : vsr_episode_kernel<real, CTRL_PHASE_SIN, false>;
+      break;
+    case VSR_CTRL_TABULATED:
+      kern = full ? vsr_episode_kernel<real, CTRL_TABULATED, true> : vsr_episode_kernel<real, CTRL_TABULATED, false>;
+      break;
+    default:
+      kern = full ? vsr_episode_kernel<real, CTRL_MLP, true> : vsr_episode_kernel<real, CTRL_MLP, false>;
+      break;
   }
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0, sms = 0;

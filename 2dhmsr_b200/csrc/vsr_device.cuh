@@ -567,19 +567,25 @@ __device__ __forceinline__ real activation(int a, real x) {
 // Matrix33.solve33 answer of dyn4j.  Used for velocities (C = Cdot) and positions (C = C).
 // ONE function for both lanes that own the two masses, so both compute identical bits.
 template <typename real>
-__device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x, real r2y, real ii,
+__device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x, real r2y, real inertia,
                                              real weld_alpha, real inv_two_im, real& lx, real& ly, real& lz) {
   real px = -r2y, py = r2x;
   real bx = -cx + real(0.5) * px * cz, by = -cy + real(0.5) * py * cz;
   real pb = px * bx + py * by;
   lx = (bx - weld_alpha * px * pb) * inv_two_im;
   ly = (by - weld_alpha * py * pb) * inv_two_im;
-  lz = real(0.5) * (-cz / ii - (px * lx + py * ly));
+  lz = real(0.5) * (-cz * inertia - (px * lx + py * ly));
 }
 
 // ---------------------------------------------------------------- the episode kernel
-template <typename real, int CTRL>
-__global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) {
+#ifndef VSR_MAX_THREADS
+#define VSR_MAX_THREADS 384
+#endif
+// One warp per block: no block-level synchronisation exists, and 32-thread blocks give the
+// finest balance of robot groups over the 148 SMs.  FULLSPR = all four spring scaffoldings
+// present (the default voxel): the 18 solves then form one branch-free basic block.
+template <typename real, int CTRL, bool FULLSPR>
+__global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
   const int lane = threadIdx.x & 31;
@@ -603,17 +609,28 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
     has[s] = nb >= 0;
     nl[s] = has[s] ? lane0 + nb : lane;
   }
+  real hm[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) hm[s] = has[s] ? real(1) : real(0);
   const real im = P.inv_m, ii = P.inv_i, dt = P.dt;
   const real two_im = real(2) * im;
   const real L2w = P.weld_len * P.weld_len;
   const real weld_alpha = (real(0.5) * ii) / (two_im + real(0.5) * ii * L2w);
   const real inv_two_im = real(1) / two_im;
+  const real inertia = real(1) / ii;
   const real lin_f = r_clamp<real>(real(1) - dt * P.lin_damp, real(0), real(1));
   const real ang_f = r_clamp<real>(real(1) - dt * P.ang_damp, real(0), real(1));
   const real max_trans2 = P.max_trans * P.max_trans;
 
   const long long n_groups = (P.n_robots + G - 1) / G;
-  for (long long group = (long long)blockIdx.x * wpb + wib; group < n_groups; group += (long long)gridDim.x * wpb) {
+  // Every warp of a block runs the same number of passes (idle ones on a dummy robot) so that
+  // the block-wide barriers below are legal.  The barriers carry no data: they keep the warps of
+  // an SM inside the same stretch of the (large, fully unrolled) instruction stream, which turns
+  // instruction-cache misses of one warp into hits for the others.
+  const long long warps_total = (long long)gridDim.x * wpb;
+  const long long n_pass = (n_groups + warps_total - 1) / warps_total;
+  for (long long pass = 0; pass < n_pass; pass++) {
+    const long long group = pass * warps_total + (long long)blockIdx.x * wpb + wib;
     const long long rb = group * G + slot;  // bucket index of this lane's robot
     const bool active = lane_ok && rb < P.n_robots;
     const long long gl = rb * nvox + v;     // global voxel lane (ring addressing)
@@ -654,6 +671,7 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
 
     for (int tick = 0; tick < P.n_ticks; tick++) {
+      __syncthreads();
       // =========================== World.step(1) ===========================
       // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
 #pragma unroll
@@ -686,7 +704,7 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
       real snx[18], sny[18], scr1[18], scr2[18], ssoft[18], sbias[18], sgam[18];
       const real sw = P.spring_w;
 #define VSR_SPRING_INIT(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                        \
-  if (P.spring_mask & (1u << s)) {                                                                 \
+  if (FULLSPR || (P.spring_mask & (1u << s))) {                                                    \
     real r1x = real(a1x) * ch[b1] - real(a1y) * sh[b1], r1y = real(a1x) * sh[b1] + real(a1y) * ch[b1]; \
     real r2x = real(a2x) * ch[b2] - real(a2y) * sh[b2], r2y = real(a2x) * sh[b2] + real(a2y) * ch[b2]; \
     real dx = r1x + x[b1] - (r2x + x[b2]), dy = r1y + y[b1] - (r2y + y[b2]);                       \
@@ -739,7 +757,8 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
       }
       // warm start: body1 += (imp) ; body2 -= (imp), r1 = 0
 #define VSR_WELD_WARM(side, k, own, is_b1)                                                     \
-  if (has[side]) {                                                                             \
+  {                                                                                            \
+    /* impulses of absent welds stay exactly 0, so no branch is needed */                      \
     if (is_b1) {                                                                               \
       vx[own] += wix[side][k] * im; vy[own] += wiy[side][k] * im; w[own] += ii * wiz[side][k]; \
     } else {                                                                                   \
@@ -754,9 +773,11 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
 #undef VSR_WELD_WARM
 
       // ---- velocity iterations: all joints, then all contacts
+#pragma unroll 1
       for (int it = 0; it < P.vel_iters; it++) {
+        __syncthreads();
 #define VSR_SPRING_SOLVE(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                          \
-  if (P.spring_mask & (1u << s)) {                                                                    \
+  if (FULLSPR || (P.spring_mask & (1u << s))) {                                                       \
     real Jv = snx[s] * (vx[b1] - vx[b2]) + sny[s] * (vy[b1] - vy[b2]) + scr1[s] * w[b1] - scr2[s] * w[b2]; \
     real j = -ssoft[s] * (Jv + sbias[s] + sgam[s] * simp[s]);                                         \
     simp[s] += j;                                                                                     \
@@ -773,13 +794,15 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
 #define VSR_GATHER_V(tag, part, side) \
   const real tag##vx = shfl(vx[part], nl[side]), tag##vy = shfl(vy[part], nl[side]), tag##w = shfl(w[part], nl[side]);
 #define VSR_WELD_VEL(side, k, own, tag, is_b1)                                                  \
-  if (has[side]) {                                                                              \
+  {                                                                                             \
     real v1x = is_b1 ? vx[own] : tag##vx, v1y = is_b1 ? vy[own] : tag##vy, w1 = is_b1 ? w[own] : tag##w; \
     real v2x = is_b1 ? tag##vx : vx[own], v2y = is_b1 ? tag##vy : vy[own], w2 = is_b1 ? tag##w : w[own]; \
     real r2x = wr2x[side][k], r2y = wr2y[side][k];                                              \
     real lx, ly, lz;                                                                            \
-    weld_solve33<real>(v1x - (v2x - w2 * r2y), v1y - (v2y + w2 * r2x), w1 - w2, r2x, r2y, ii,   \
+    weld_solve33<real>(v1x - (v2x - w2 * r2y), v1y - (v2y + w2 * r2x), w1 - w2, r2x, r2y, inertia, \
                        weld_alpha, inv_two_im, lx, ly, lz);                                     \
+    /* branch-free: a voxel without a neighbour on this side scales the impulse by 0 */         \
+    lx *= hm[side]; ly *= hm[side]; lz *= hm[side];                                             \
     wix[side][k] += lx; wiy[side][k] += ly; wiz[side][k] += lz;                                 \
     if (is_b1) {                                                                                \
       vx[own] += lx * im; vy[own] += ly * im; w[own] += ii * lz;                                \
@@ -853,7 +876,7 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
 #define VSR_GATHER_P(tag, part, side) \
   const real tag##x = shfl(x[part], nl[side]), tag##y = shfl(y[part], nl[side]), tag##t = shfl(th[part], nl[side]);
 #define VSR_WELD_POS(side, own, tag, is_b1, horiz)                                             \
-  if (has[side] && !done) {                                                                    \
+  {                                                                                            \
     real x1 = is_b1 ? x[own] : tag##x, y1 = is_b1 ? y[own] : tag##y, t1 = is_b1 ? th[own] : tag##t; \
     real x2 = is_b1 ? tag##x : x[own], y2 = is_b1 ? tag##y : y[own], t2 = is_b1 ? tag##t : th[own]; \
     real s2, c2;                                                                               \
@@ -866,13 +889,15 @@ __global__ void __launch_bounds__(128) vsr_episode_kernel(const Params<real> P) 
     if (Cz > PI_) Cz -= real(2) * PI_;                                                         \
     real linErr = r_sqrt(Cx * Cx + Cy * Cy), angErr = r_abs(Cz);                               \
     real lx, ly, lz;                                                                           \
-    weld_solve33<real>(Cx, Cy, Cz, r2x, r2y, ii, weld_alpha, inv_two_im, lx, ly, lz);          \
+    weld_solve33<real>(Cx, Cy, Cz, r2x, r2y, inertia, weld_alpha, inv_two_im, lx, ly, lz);          \
+    const real pm = done ? real(0) : hm[side];                                                 \
+    lx *= pm; ly *= pm; lz *= pm;                                                              \
     if (is_b1) {                                                                               \
       x[own] += lx * im; y[own] += ly * im; th[own] += ii * lz;                                \
     } else {                                                                                   \
       x[own] -= lx * im; y[own] -= ly * im; th[own] -= ii * (r2x * ly - r2y * lx + lz);        \
     }                                                                                          \
-    solved = solved && (linErr <= P.lin_tol) && (angErr <= P.ang_tol);                         \
+    solved = solved && (!has[side] || ((linErr <= P.lin_tol) && (angErr <= P.ang_tol)));       \
   }
           {
             VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0) VSR_GATHER_P(r0, 0, 1) VSR_GATHER_P(r3, 3, 1)

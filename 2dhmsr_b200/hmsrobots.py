@@ -796,11 +796,6 @@ class Locomotion:
     def __init__(self, final_t: float, ground_profile, settings: Settings, initial_placement: Optional[float] = None):
         self.final_t = final_t
         self.ground_profile = [list(map(float, ground_profile[0])), list(map(float, ground_profile[1]))]
-        # :50-52: groundProfile[0][1] + INITIAL_PLACEMENT_X_GAP
-        self.initial_placement = (
-            self.ground_profile[0][1] + self.INITIAL_PLACEMENT_X_GAP if initial_placement is None else initial_placement
-        )
-        self.settings = settings
         xs, ys = self.ground_profile
         if len(xs) != len(ys):
             raise ValueError("xs[] and ys[] must have the same length")  # Ground.java:49-51
@@ -808,6 +803,9 @@ class Locomotion:
             raise ValueError("There must be at least 2 points")  # Ground.java:52-54
         if sorted(xs) != xs:
             raise ValueError("x coordinates must be sorted")  # Ground.java:55-58
+        # :50-52: groundProfile[0][1] + INITIAL_PLACEMENT_X_GAP
+        self.initial_placement = xs[1] + self.INITIAL_PLACEMENT_X_GAP if initial_placement is None else initial_placement
+        self.settings = settings
 
     @staticmethod
     def create_terrain(name: str):  # :61-146

@@ -1,0 +1,189 @@
+"""Parity proper: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerances, and why they are what they are:
+  * fp64 build of the kernel vs the fp64 oracle in the same (canonical) Gauss-Seidel order:
+    the two differ only by operation order / FMA contraction, so positions agree to 1e-8 over
+    5 s and the 20 s Outcome to 1e-2 (the dynamics is chaotic: ulp differences grow).
+  * fp32 product path vs the oracle: 2e-5 until the first contact; once contacts start, a
+    mass that touches one tick earlier/later is a discrete event, so the bound over the first
+    2 s is 0.25 units and full-episode agreement is checked at the distribution level.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+H = importlib.import_module("2dhmsr_b200")
+A = H.abi
+from oracle import oracle
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+F32, F64 = A.VSR_PRECISION_F32, A.VSR_PRECISION_F64
+
+
+def _both(loco, robots, precision, traj=None, **okw):
+    traj = len(robots) if traj is None else traj
+    bd = loco.compile(robots, precision=precision, trajectory_robots=traj)
+    res, tr = helpers.gpu_run(bd, trajectories=traj)
+    ores, pr = oracle.run(bd, trajectory=True, n_threads=8, **okw)
+    return bd, res, tr, ores, pr["trajectory"]
+
+
+def test_device_present_and_native_library_loaded():
+    lib = A.load_library()
+    assert lib.vsr_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libvsr_b200.so" in maps  # the in-tree CUDA library, not a fallback
+
+
+@pytest.mark.parametrize("shape,n", [("biped-4x3", 6), ("worm-8x2", 4), ("box-1x1", 3), ("box-3x3", 3), ("biped-6x4", 2)])
+def test_fp64_kernel_matches_oracle_bodies(shape, n):
+    bd, res, tr, ores, otr = _both(helpers.locomotion(5.0), helpers.phase_robots(n, shape=shape, seed=3), F64)
+    nb = 4 * bd.n_voxels[0]
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[:, :, :nb, :3] - otr[:, :, :nb, :3]).max() < 1e-8
+    assert np.abs(tr[:, :, :nb, 3:] - otr[:, :, :nb, 3:]).max() < 1e-6
+    for f in ("first_center_x", "first_center_y", "last_center_x", "last_center_y", "area_ratio_energy_last",
+              "control_energy_last", "t_first", "t_last"):
+        assert np.allclose(res[f], ores[f], rtol=1e-9, atol=1e-8), f
+    assert np.array_equal(res["n_ticks"], ores["n_ticks"])
+
+
+def test_fp64_config1_full_episode():
+    """BASELINE config 1 (Example.java:41-48), 1200 ticks, tabulated TimeFunctions."""
+    bd, res, tr, ores, otr = _both(helpers.locomotion(), [helpers.config1_robot()], F64)
+    assert np.abs(tr[0, :600, :, :2] - otr[0, :600, :40, :2]).max() < 1e-6
+    o, g = H.Outcome(ores[0]), H.Outcome(res[0])
+    assert g.get_time() == o.get_time() == pytest.approx(20 - 1 / 60, abs=1e-9)
+    assert g.get_distance() == pytest.approx(o.get_distance(), abs=1e-2)
+    assert g.get_velocity() == pytest.approx(o.get_velocity(), abs=1e-3)
+    assert g.get_control_energy() == pytest.approx(o.get_control_energy(), rel=1e-9)
+
+
+def test_fp64_effective_mass_mode_and_partial_scaffolding():
+    loco = helpers.locomotion(3.0, spring_mass_mode=A.VSR_SPRING_MASS_EFFECTIVE)
+    bd, res, tr, ores, otr = _both(loco, helpers.phase_robots(3, seed=9), F64)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-8
+    m = A.default_material()
+    m.spring_scaffoldings = A.VSR_SCAFFOLD_SIDE_EXTERNAL | A.VSR_SCAFFOLD_SIDE_CROSS | A.VSR_SCAFFOLD_CENTRAL_CROSS
+    shape = H.RobotUtils.build_shape("worm-3x2")
+    body = H.Grid.create(3, 2, lambda x, y: H.Voxel([H.Average(H.Touch(), 0.25)], m))
+    robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(3, 2, lambda x, y: 0.5 * x + y + s)), body) for s in (0.0, 1.0)]
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0), robots, F64)
+    assert np.abs(tr[..., :3] - otr[:, :, :24, :3]).max() < 1e-8 and np.all(res["status"] == 0)
+    assert shape.w == 3
+
+
+@pytest.mark.parametrize("terrain", ["hilly-1-10-0", "hilly-3-5-7", "steppy-1-6-2", "uphill-10", "flatWithStart-4"])
+def test_fp64_terrains(terrain):
+    """Ground polygons with slopes and internal vertical edges (Ground.java:64-70)."""
+    loco = helpers.locomotion(6.0, terrain=terrain)
+    bd, res, tr, ores, otr = _both(loco, helpers.phase_robots(4, seed=12), F64)
+    assert np.all((res["status"] & 1) == 0)
+    ok = (res["status"] == 0)  # robots that never had > MAXC simultaneous segment contacts on one mass
+    assert ok.sum() >= 3
+    assert np.abs(tr[ok][..., :3] - otr[ok][:, :, :40, :3]).max() < 1e-7
+    assert np.allclose(res["last_center_x"][ok], ores["last_center_x"][ok], atol=1e-6)
+
+
+@pytest.mark.parametrize("hidden,sensors,act", [((), "uniform-ax+t-0", "TANH"), ((21, 21), "uniform-ax+t-0", "TANH"),
+                                                ((7,), "uniform-t+vxy+a-0", "SIGMOID"), ((4,), "uniform-a+vx+ay-0", "SIN")])
+def test_fp64_centralized_mlp_with_sensors(hidden, sensors, act):
+    """BASELINE config 3: sensors feed the controller, so body parity here pins Touch / AreaRatio /
+    Velocity, the Average/Trend windows, SoftNormalization and MultiLayerPerceptron.apply on device."""
+    robots = helpers.mlp_robots(3, shape="worm-8x2", sensors=sensors, hidden=hidden, seed=5, activation=act)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(4.0), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :64, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+    assert np.all(res["control_energy_last"] > 0)
+
+
+def test_fp32_short_horizon_tolerances():
+    loco = helpers.locomotion(2.0)
+    robots = helpers.phase_robots(16, seed=21)
+    bd = loco.compile(robots, precision=F32, trajectory_robots=16)
+    res, tr = helpers.gpu_run(bd, trajectories=16)
+    ores, pr = oracle.run(bd, trajectory=True, stats=True, n_threads=8)
+    otr = pr["trajectory"]
+    first_contact = int(np.argmax(pr["n_contacts"].max(axis=0) > 0))
+    assert first_contact >= 5
+    pre = np.abs(tr[:, :first_contact, :, :2] - otr[:, :first_contact, :40, :2]).max()
+    assert pre < 2e-5, pre                       # stated fp32 tolerance before the first contact
+    full = np.abs(tr[..., :2] - otr[:, :, :40, :2]).max()
+    assert full < 0.25, full                     # stated fp32 tolerance over 2 s (121 ticks)
+    assert np.abs(res["first_center_x"] - ores["first_center_x"]).max() < 1e-5
+
+
+def test_fp32_mixed_shapes_in_one_batch():
+    """Robots of several shape classes in one descriptor are bucketed internally; results come back
+    in batch order and equal those of per-shape batches bit for bit."""
+    loco = helpers.locomotion(2.0)
+    a = helpers.phase_robots(5, shape="biped-4x3", seed=1)
+    b = helpers.phase_robots(4, shape="worm-8x2", seed=2)
+    c = helpers.phase_robots(3, shape="box-2x2", seed=3)
+    mixed = [a[0], b[0], c[0], a[1], b[1], a[2], c[1], b[2], a[3], c[2], b[3], a[4]]
+    rm, _ = helpers.gpu_run(loco.compile(mixed))
+    ra, _ = helpers.gpu_run(loco.compile(a))
+    rb, _ = helpers.gpu_run(loco.compile(b))
+    rc, _ = helpers.gpu_run(loco.compile(c))
+    assert rm[[0, 3, 5, 8, 11]].tobytes() == ra.tobytes()
+    assert rm[[1, 4, 7, 10]].tobytes() == rb.tobytes()
+    assert rm[[2, 6, 9]].tobytes() == rc.tobytes()
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (4096 x biped-4x3, 1200 ticks) through size-independent
+    properties: determinism, batch-composition independence, replication, finiteness, and
+    distribution-level agreement with the oracle on a 256-robot sample."""
+    loco = helpers.locomotion()
+    robots = helpers.phase_robots(4096, seed=0)
+    bd = loco.compile(robots)
+    r1, _ = helpers.gpu_run(bd)
+    r2, _ = helpers.gpu_run(bd)
+    assert r1.tobytes() == r2.tobytes()                       # deterministic
+    assert np.all(r1["status"] == 0) and np.all(r1["n_ticks"] == 1200)
+    d = r1["last_center_x"] - r1["first_center_x"]
+    assert np.all(np.isfinite(d)) and np.abs(d).max() < 400
+    assert np.allclose(r1["first_center_x"], 17.0, atol=0.5)  # bbox.min.x = 11 -> centre 17 at tick 1
+    pick = [5, 77, 1000, 4095]
+    rs, _ = helpers.gpu_run(loco.compile([robots[i] for i in pick]))
+    assert rs.tobytes() == r1[pick].tobytes()                 # independent of batch composition / packing
+    rr, _ = helpers.gpu_run(loco.compile([robots[3]] * 7))
+    assert all(rr[i].tobytes() == r1[3].tobytes() for i in range(7))  # replicas agree
+    # energies: control energy is a pure function of the phases -> matches the oracle tightly
+    ores, _ = oracle.run(bd, n_threads=8, robot_end=256)
+    assert np.allclose(r1["control_energy_last"][:256], ores["control_energy_last"], rtol=1e-5)
+    # chaotic per-robot outcomes: compare distributions (fp32 vs fp64 differ like two solver orders do)
+    od = ores["last_center_x"] - ores["first_center_x"]
+    se = np.sqrt(d[:256].var() / 256 + od.var() / 256)
+    assert abs(d[:256].mean() - od.mean()) < 4 * se + 0.5
+    assert abs(np.median(d[:256]) - np.median(od)) < 4 * 1.25 * se + 0.5
+    assert 0.5 < d[:256].std() / od.std() < 2.0
+
+
+def test_call_order_errors():
+    bd = helpers.locomotion(1.0).compile(helpers.phase_robots(2))
+    with H.DeviceBatch(bd) as db:
+        with pytest.raises(H.VsrError, match="before"):
+            db.run()
+        db.upload(0)
+        with pytest.raises(H.VsrError, match="before"):
+            db.results()
+        db.run()
+        assert db.last_launches() == 1 and db.voxel_steps() == 2 * 10 * bd.n_ticks
+        with pytest.raises(ValueError):
+            db.trajectory(0)  # none was requested
+
+
+def test_locomotion_apply_entry_point():
+    """The drop-in call: Locomotion.apply(Robot) -> Outcome, and the batched apply(list)."""
+    loco = helpers.locomotion(3.0)
+    robots = helpers.phase_robots(3, seed=8)
+    outs = loco.apply(robots)
+    one = loco.apply(robots[1])
+    assert one.get_distance() == outs[1].get_distance()
+    assert all(np.isfinite(o.get_velocity()) for o in outs)
+    assert outs[0].get_time() == pytest.approx(3.0 - 1 / 60, abs=1e-9) or outs[0].get_time() == pytest.approx(3.0, abs=1e-9)
