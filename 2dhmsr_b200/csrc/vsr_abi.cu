@@ -601,6 +601,13 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.spring_mode = st.spring_mass_mode;
   P.spring_mask = b->spring_mask;
   P.mlp_act = d.mlp_activation;
+  P.debug_robot = -1;
+  P.debug_tick = -1;
+  if (const char* dbg = getenv("VSR_DEBUG")) {  // "robot:tick" (bucket index)
+    long dr = -1, dk = -1, de = -1;
+    int got = sscanf(dbg, "%ld:%ld:%ld", &dr, &dk, &de);
+    if (got >= 2) { P.debug_robot = dr; P.debug_tick = (int)dk; P.debug_tick_end = (int)(got == 3 ? de : dk); }
+  }
   const int nvox = k.shape.nvox, G = 32 / nvox;
   int maxn = 1;
   for (int i = 0; i < k.shape.n_layers; i++) maxn = std::max(maxn, k.shape.neurons[i]);

@@ -26,6 +26,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace vsr {
 
@@ -98,6 +99,8 @@ struct Params {
   unsigned spring_mask;  // bit s = spring s present (scaffoldings)
   int mlp_act;
   int smem_per_warp;     // reals of staging per warp
+  long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
+  int debug_tick, debug_tick_end;
 };
 
 // ---------------------------------------------------------------- math wrappers
@@ -177,11 +180,11 @@ __device__ void farthest_edge(const Poly4<real>& P, real nx, real ny, Edge<real>
   if (ln < rn) {
     e.x1 = P.vx[idx]; e.y1 = P.vy[idx]; e.i1 = idx;
     e.x2 = P.vx[next]; e.y2 = P.vy[next]; e.i2 = next;
-    e.index = idx + 1;
+    e.index = next == 0 ? 4 : next;
   } else {
     e.x1 = P.vx[prev]; e.y1 = P.vy[prev]; e.i1 = prev;
     e.x2 = P.vx[idx]; e.y2 = P.vy[idx]; e.i2 = idx;
-    e.index = idx;
+    e.index = idx == 0 ? 4 : idx;  // one label per edge (see the oracle's farthest_edge)
   }
 }
 
@@ -926,6 +929,15 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           int ov = detect_mass(P, x[k], y[k], th[k], hint[k], cbody[k]);
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
           if (cbody[k].n > 0) cmask |= 1u << k;
+          if (rb == P.debug_robot && tick >= P.debug_tick && tick <= P.debug_tick_end)
+            for (int q = 0; q < cbody[k].n; q++) {
+              const CCon<real>& c = cbody[k].c[q];
+              printf("[kernel] tick %d body %d seg %d n %d normal (%.9g, %.9g) pose (%.9g %.9g %.9g)\n", tick, v * 4 + k,
+                     c.seg, c.n, (double)c.nx, (double)c.ny, (double)x[k] + P.origin_x, (double)y[k], (double)th[k]);
+              for (int z = 0; z < c.n; z++)
+                printf("           p (%.9g, %.9g) depth %.6e id %d jn %.6e jt %.6e\n", (double)c.p[z].px + P.origin_x,
+                       (double)c.p[z].py, (double)c.p[z].depth, c.p[z].id, (double)c.p[z].jn, (double)c.p[z].jt);
+            }
         }
       }
 

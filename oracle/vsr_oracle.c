@@ -803,7 +803,7 @@ static void farthest_edge(const OPoly* P, double nx, double ny, OEdge* e) {
     e->x2 = P->vx[next];
     e->y2 = P->vy[next];
     e->i2 = next;
-    e->index = idx + 1;
+    e->index = next == 0 ? P->n : next; /* dyn4j: idx + 1 */
   } else {
     e->x1 = P->vx[prev];
     e->y1 = P->vy[prev];
@@ -811,7 +811,10 @@ static void farthest_edge(const OPoly* P, double nx, double ny, OEdge* e) {
     e->x2 = P->vx[idx];
     e->y2 = P->vy[idx];
     e->i2 = idx;
-    e->index = idx;
+    /* dyn4j labels this edge `idx`, i.e. 0 for the wrap-around edge (n-1 -> 0) that the other
+       branch labels n.  When n is the edge's own normal both end points tie as "farthest" and the
+       label would flip with the rounding; one label per edge keeps the warm start deterministic. */
+    e->index = idx == 0 ? P->n : idx;
   }
 }
 
@@ -1402,6 +1405,21 @@ static void run_robot(ORun* R, size_t ridx) {
   detect(R, r);
   for (int k = 0; k < nt; k++) {
     int iters = world_step(R, r, dt);  /* AbstractTask.java:49 */
+    {
+      /* VSR_ORACLE_DEBUG="robot:tick": dump the manifolds found at the end of that tick */
+      const char* dbg = getenv("VSR_ORACLE_DEBUG");
+      long dr = -1, dk = -1, de = -1;
+      int got = dbg ? sscanf(dbg, "%ld:%ld:%ld", &dr, &dk, &de) : 0;
+      if (got == 2) de = dk;
+      if (got >= 2 && (size_t)dr == ridx && k >= dk && k <= de)
+        for (int i = 0; i < r->ncontacts; i++) {
+          OContact* c = &r->contacts[i];
+          fprintf(stderr, "[oracle] tick %d body %d seg %d n %d normal (%.9g, %.9g)\n", k, c->b1, c->seg, c->n, c->nx, c->ny);
+          for (int q = 0; q < c->n; q++)
+            fprintf(stderr, "           p (%.9g, %.9g) depth %.6e id %d jn %.6e jt %.6e\n", c->p[q].px, c->p[q].py,
+                    c->p[q].depth, c->p[q].id, c->p[q].jn, c->p[q].jt);
+        }
+    }
     robot_sense(R, r, k);              /* Robot.act: Voxel.act for every voxel ... */
     double* sig = (pb && pb->signals) ? pb->signals + ((size_t)row * R->nticks + k) * pb->voxel_stride : NULL;
     robot_control(R, r, ridx, k, sig); /* ... then controller.control, Robot.java:74-77 */
