@@ -625,21 +625,28 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     if (groups_all <= (long long)sms_ * 12) wpb = (int)std::max<long long>(1, (groups_all + sms_ - 1) / sms_);
   }
   if (wpb_env > 0) wpb = std::min(12, wpb_env);
+  // shared memory per thread: 18 spring 4-vectors (+ gamma); keep the block under ~200 KB
+  const bool eff_mode = st.spring_mass_mode == VSR_SPRING_MASS_EFFECTIVE;
+  if (sizeof(real) == 8) wpb = std::min(wpb, VSR_MAX_THREADS / 64);  // fp64: 32-byte vectors, half the stride
   const int threads = 32 * wpb;
-  const size_t smem = (size_t)wpb * P.smem_per_warp * sizeof(real);
+  // [18][stride] spring 4-vectors (+ [18][stride] gamma in effective-mass mode) + per-warp staging
+  const int stride = sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2;
+  const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) + (size_t)wpb * P.smem_per_warp * sizeof(real);
+  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 3;
   void (*kern)(const Params<real>) = nullptr;
-  const bool full = (b->spring_mask == 0x3FFFFu);
+  const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
   switch (d.controller_kind) {
     case VSR_CTRL_PHASE_SIN:
-      kern = full ? vsr_episode_kernel<real, CTRL_PHASE_SIN, true> : vsr_episode_kernel<real, CTRL_PHASE_SIN, false>;
+      kern = fast ? vsr_episode_kernel<real, CTRL_PHASE_SIN, true> : vsr_episode_kernel<real, CTRL_PHASE_SIN, false>;
       break;
     case VSR_CTRL_TABULATED:
-      kern = full ? vsr_episode_kernel<real, CTRL_TABULATED, true> : vsr_episode_kernel<real, CTRL_TABULATED, false>;
+      kern = fast ? vsr_episode_kernel<real, CTRL_TABULATED, true> : vsr_episode_kernel<real, CTRL_TABULATED, false>;
       break;
     default:
-      kern = full ? vsr_episode_kernel<real, CTRL_MLP, true> : vsr_episode_kernel<real, CTRL_MLP, false>;
+      kern = fast ? vsr_episode_kernel<real, CTRL_MLP, true> : vsr_episode_kernel<real, CTRL_MLP, false>;
       break;
   }
+  P.ctrl = d.controller_kind;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0, sms = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));

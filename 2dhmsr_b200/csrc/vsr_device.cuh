@@ -99,6 +99,8 @@ struct Params {
   unsigned spring_mask;  // bit s = spring s present (scaffoldings)
   int mlp_act;
   int smem_per_warp;     // reals of staging per warp
+  int ctrl;              // CTRL_*
+  int sync_mode;         // bit0: barrier per tick, bit1: per velocity iteration (code locality only)
   long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
   int debug_tick, debug_tick_end;
 };
@@ -106,7 +108,23 @@ struct Params {
 // ---------------------------------------------------------------- math wrappers
 __device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
-__device__ __forceinline__ void r_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+// fp32 sincos: Cody-Waite reduction by pi/2 (3 constants) + the classic degree-7/8 minimax
+// polynomials on [-pi/4, pi/4]; ~1 ulp for |a| < 1e4 rad (a mass never spins that far) in ~25
+// instructions -- sincosf() inlines ~85 with a slow path, and there are many call sites.
+__device__ __forceinline__ void r_sincos(float a, float* s, float* c) {
+  float q = rintf(a * 0.636619772f);
+  float r = fmaf(q, -1.57079601e+00f, a);
+  r = fmaf(q, -3.13916473e-07f, r);
+  r = fmaf(q, -5.39030253e-15f, r);
+  int i = (int)q;
+  float r2 = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2,
+                  fmaf(-0.5f, r2, 1.0f));
+  float ss = (i & 1) ? cp : sp, cc = (i & 1) ? sp : cp;
+  *s = (i & 2) ? -ss : ss;
+  *c = ((i + 1) & 2) ? -cc : cc;
+}
 __device__ __forceinline__ void r_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ float r_atan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double r_atan2(double y, double x) { return atan2(y, x); }
@@ -127,6 +145,14 @@ __device__ __forceinline__ real r_clamp(real x, real lo, real hi) { return r_min
 
 template <typename real>
 __device__ __forceinline__ real shfl(real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// 4-wide value for one 128-bit (fp32) shared-memory access per spring
+template <typename real> struct Real4T;
+template <> struct Real4T<float> { typedef float4 type; };
+template <> struct Real4T<double> { typedef double4 type; };
+template <typename real> struct Real2T;
+template <> struct Real2T<float> { typedef float2 type; };
+template <> struct Real2T<double> { typedef double2 type; };
 
 // ---------------------------------------------------------------- contacts (per mass)
 template <typename real>
@@ -310,9 +336,8 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
 // World.detect (dyn4j) for one mass: every ground segment its AABB overlaps; impulses of
 // points with the same id are carried over (ContactConstraint.update).
 template <typename real>
-__device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by, real bth, int& hint, CBody<real>& cb) {
-  real bs, bc;
-  r_sincos(bth, &bs, &bc);
+__device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by, real bc, real bs, int& hint,
+                                        CBody<real>& cb) {
   real e = P.half * (r_abs(bc) + r_abs(bs));
   real xlo = bx - e, xhi = bx + e, ylo = by - e;
   int n = P.terr_n;
@@ -357,9 +382,8 @@ struct BodyState {
 // SequentialImpulses.initialize (dyn4j) for the constraints of one mass (the ground is
 // static: invM2 = invI2 = 0), followed by their warm start.
 template <typename real>
-__device__ __noinline__ void contact_init_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
-  real bs, bc;
-  r_sincos(B.th, &bs, &bc);
+__device__ __noinline__ void contact_init_mass(const Params<real>& P, BodyState<real>& B, real bc, real bs,
+                                               CBody<real>& cb) {
   const real im = P.inv_m, ii = P.inv_i;
   for (int q = 0; q < cb.n; q++) {
     CCon<real>& c = cb.c[q];
@@ -587,14 +611,26 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // One warp per block: no block-level synchronisation exists, and 32-thread blocks give the
 // finest balance of robot groups over the 148 SMs.  FULLSPR = all four spring scaffoldings
 // present (the default voxel): the 18 solves then form one branch-free basic block.
-template <typename real, int CTRL, bool FULLSPR>
+// FAST = the default voxel (all four scaffoldings, reduced-mass springs): no per-spring branch,
+// constant gamma.  Everything else takes the generic instantiation.
+template <typename real, int CTRL, bool FAST>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
+  constexpr bool FULLSPR = FAST;
+  const bool EFFMASS = FAST ? false : (P.spring_mode != 0);
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
-  real* stage = reinterpret_cast<real*>(smem_raw) + (size_t)wib * P.smem_per_warp;
+  typedef typename Real4T<real>::type R4;
+  typedef typename Real2T<real>::type R2;
+  // compile-time stride (= the largest block) so that every access has an immediate offset
+  constexpr int SPR_STRIDE = sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2;
+  const int tid = threadIdx.x;
+  R4* spr = reinterpret_cast<R4*>(smem_raw);                                  // [18][SPR_STRIDE]
+  R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
+  real* sgam = reinterpret_cast<real*>(spr2 + 18 * SPR_STRIDE);               // [18][SPR_STRIDE], effective-mass mode only
+  real* stage = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)wib * P.smem_per_warp;
   const int nvox = S.nvox;
   const int G = 32 / nvox;
   const int slot = lane / nvox;
@@ -624,6 +660,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   const real lin_f = r_clamp<real>(real(1) - dt * P.lin_damp, real(0), real(1));
   const real ang_f = r_clamp<real>(real(1) - dt * P.ang_damp, real(0), real(1));
   const real max_trans2 = P.max_trans * P.max_trans;
+  // reduced-mass springs: k, d and gamma are constants (same expression as the per-spring one)
+  const real gam_c = real(1) / (dt * (real(2) * P.red_mass * P.spring_zeta * P.spring_w + dt * (P.red_mass * P.spring_w * P.spring_w)));
+  const int sync_mode = P.sync_mode;
 
   const long long n_groups = (P.n_robots + G - 1) / G;
   // Every warp of a block runs the same number of passes (idle ones on a dummy robot) so that
@@ -648,6 +687,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       y[k] = active ? (real)S.init_y[v * 4 + k] : real(k);
       th[k] = vx[k] = vy[k] = w[k] = real(0);
     }
+    // cos/sin of the 4 rotation angles, kept current across the tick (recomputed only where an
+    // angle changed and is about to be used)
+    real cs_[4] = {real(1), real(1), real(1), real(1)}, sn_[4] = {real(0), real(0), real(0), real(0)};
     real simp[18];
 #pragma unroll
     for (int s = 0; s < 18; s++) simp[s] = real(0);
@@ -674,7 +716,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
 
     for (int tick = 0; tick < P.n_ticks; tick++) {
-      __syncthreads();
+      if (sync_mode & 1) __syncthreads();
       // =========================== World.step(1) ===========================
       // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
 #pragma unroll
@@ -691,20 +733,21 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         for (int k = 0; k < 4; k++) {
           if (cmask & (1u << k)) {
             BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-            contact_init_mass(P, B, cbody[k]);
+            contact_init_mass(P, B, cs_[k], sn_[k], cbody[k]);
             vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
           }
         }
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
-      real ch[4], sh[4], cs_[4], sn_[4];
+      real ch[4], sh[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        r_sincos(th[k], &sn_[k], &cs_[k]);
         ch[k] = cs_[k] * P.half;
         sh[k] = sn_[k] * P.half;
       }
-      real snx[18], sny[18], scr1[18], scr2[18], ssoft[18], sbias[18], sgam[18];
+      // per-spring constants of this tick go to shared memory: (nx, ny, cr1, cr2) as one 4-vector and
+      // (softMass, bias) as one 2-vector per spring and thread ([spring][thread]: a warp reads
+      // consecutive 16- / 8-byte words, conflict-free).  That frees ~110 registers.
       const real sw = P.spring_w;
 #define VSR_SPRING_INIT(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                        \
   if (FULLSPR || (P.spring_mask & (1u << s))) {                                                    \
@@ -717,14 +760,19 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
     real cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;                                     \
     real invMass = im + ii * cr1 * cr1;                                                            \
     invMass += im + ii * cr2 * cr2;                                                                \
-    real m = P.spring_mode ? real(1) / invMass : P.red_mass;                                       \
+    real m = EFFMASS ? real(1) / invMass : P.red_mass;                                       \
     real dc = real(2) * m * P.spring_zeta * sw;                                                    \
     real kk = m * sw * sw;                                                                         \
     real gamma = real(1) / (dt * (dc + dt * kk));                                                  \
     real bias = (len - rest[cls]) * dt * kk * gamma;                                               \
     real soft = real(1) / (invMass + gamma);                                                       \
-    snx[s] = nx; sny[s] = ny; scr1[s] = cr1; scr2[s] = cr2;                                        \
-    ssoft[s] = soft; sbias[s] = bias; sgam[s] = gamma;                                             \
+    {                                                                                              \
+      R4 q_; q_.x = nx; q_.y = ny; q_.z = cr1; q_.w = cr2;                                         \
+      spr[s * SPR_STRIDE + tid] = q_;                                                              \
+      R2 p_; p_.x = soft; p_.y = bias;                                                             \
+      spr2[s * SPR_STRIDE + tid] = p_;                                                             \
+      if (EFFMASS) sgam[s * SPR_STRIDE + tid] = gamma;                                             \
+    }                                                                                              \
     real jx = nx * simp[s], jy = ny * simp[s];                                                     \
     vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * cr1 * simp[s];                             \
     vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * cr2 * simp[s];                             \
@@ -778,16 +826,32 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       // ---- velocity iterations: all joints, then all contacts
 #pragma unroll 1
       for (int it = 0; it < P.vel_iters; it++) {
-        __syncthreads();
+        if (sync_mode & 2) __syncthreads();
 #define VSR_SPRING_SOLVE(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                          \
+  /* software prefetch, one spring ahead (unconditional, so that an absent spring keeps the chain  \
+     intact); the fences stop ptxas from hoisting all 36 loads to the top of the loop, which costs  \
+     108 registers and spills them straight back to local memory */                                 \
+  const R4 q##s = qn_;                                                                                \
+  const R2 p##s = pn_;                                                                                \
+  asm volatile("" ::: "memory");                                                                      \
+  if (s + 1 < 18) {                                                                                   \
+    qn_ = spr[(s + 1 < 18 ? s + 1 : 0) * SPR_STRIDE + tid];                                           \
+    pn_ = spr2[(s + 1 < 18 ? s + 1 : 0) * SPR_STRIDE + tid];                                          \
+  }                                                                                                   \
+  asm volatile("" ::: "memory");                                                                      \
   if (FULLSPR || (P.spring_mask & (1u << s))) {                                                       \
-    real Jv = snx[s] * (vx[b1] - vx[b2]) + sny[s] * (vy[b1] - vy[b2]) + scr1[s] * w[b1] - scr2[s] * w[b2]; \
-    real j = -ssoft[s] * (Jv + sbias[s] + sgam[s] * simp[s]);                                         \
+    const R4 q_ = q##s;                                                                               \
+    const R2 p_ = p##s;                                                                               \
+    const real g_ = EFFMASS ? sgam[s * SPR_STRIDE + tid] : gam_c;                                     \
+    real Jv = q_.x * (vx[b1] - vx[b2]) + q_.y * (vy[b1] - vy[b2]) + q_.z * w[b1] - q_.w * w[b2];       \
+    real j = -p_.x * (Jv + p_.y + g_ * simp[s]);                                                      \
     simp[s] += j;                                                                                     \
-    real jx = snx[s] * j, jy = sny[s] * j;                                                            \
-    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * scr1[s] * j;                                  \
-    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * scr2[s] * j;                                  \
+    real jx = q_.x * j, jy = q_.y * j;                                                                \
+    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * q_.z * j;                                     \
+    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * q_.w * j;                                     \
   }
+        R4 qn_ = spr[tid];
+        R2 pn_ = spr2[tid];
         VSR_SPRINGS(VSR_SPRING_SOLVE)
 #undef VSR_SPRING_SOLVE
 
@@ -854,6 +918,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         }
         x[k] += tx; y[k] += ty; th[k] += rot;
       }
+      r_sincos(th[1], &sn_[1], &cs_[1]);
+      r_sincos(th[2], &sn_[2], &cs_[2]);
 
       // ---- position iterations: contacts, then joints; stop when the whole robot
       //      (= one island) reports solved
@@ -871,6 +937,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
                 real ms = contact_position_mass(P, B, cbody[k]);
                 minSep = ms < minSep ? ms : minSep;
                 x[k] = B.x; y[k] = B.y; th[k] = B.th;
+                if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
               }
             }
             solved = minSep >= real(-3) * P.lin_tol;
@@ -878,12 +945,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)
 #define VSR_GATHER_P(tag, part, side) \
   const real tag##x = shfl(x[part], nl[side]), tag##y = shfl(y[part], nl[side]), tag##t = shfl(th[part], nl[side]);
+#define VSR_GATHER_CS(tag, part, side) \
+  const real tag##c = shfl(cs_[part], nl[side]), tag##s = shfl(sn_[part], nl[side]);
+#define VSR_OWN_CS(tag, own) const real tag##c = cs_[own], tag##s = sn_[own];
 #define VSR_WELD_POS(side, own, tag, is_b1, horiz)                                             \
   {                                                                                            \
     real x1 = is_b1 ? x[own] : tag##x, y1 = is_b1 ? y[own] : tag##y, t1 = is_b1 ? th[own] : tag##t; \
     real x2 = is_b1 ? tag##x : x[own], y2 = is_b1 ? tag##y : y[own], t2 = is_b1 ? tag##t : th[own]; \
-    real s2, c2;                                                                               \
-    r_sincos(t2, &s2, &c2);                                                                    \
+    const real s2 = tag##s, c2 = tag##c; /* body2's rotation */                                \
     real r2x = horiz ? c2 * P.weld_len : -s2 * P.weld_len;                                     \
     real r2y = horiz ? s2 * P.weld_len : c2 * P.weld_len;                                      \
     real Cx = x1 - (x2 + r2x), Cy = y1 - (y2 + r2y), Cz = t1 - t2;                             \
@@ -904,31 +973,44 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   }
           {
             VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0) VSR_GATHER_P(r0, 0, 1) VSR_GATHER_P(r3, 3, 1)
+            VSR_GATHER_CS(l1, 1, 0) VSR_GATHER_CS(l2, 2, 0) VSR_OWN_CS(r0, 1) VSR_OWN_CS(r3, 2)
             VSR_WELD_POS(0, 0, l1, true, true) VSR_WELD_POS(0, 3, l2, true, true)
             VSR_WELD_POS(1, 1, r0, false, true) VSR_WELD_POS(1, 2, r3, false, true)
           }
+          // masses 0, 1 are body2 of the vertical welds: their angles just changed
+          r_sincos(th[0], &sn_[0], &cs_[0]);
+          r_sincos(th[1], &sn_[1], &cs_[1]);
           {
             VSR_GATHER_P(d0, 0, 2) VSR_GATHER_P(d1, 1, 2) VSR_GATHER_P(u3, 3, 3) VSR_GATHER_P(u2, 2, 3)
+            VSR_GATHER_CS(d0, 0, 2) VSR_GATHER_CS(d1, 1, 2) VSR_OWN_CS(u3, 0) VSR_OWN_CS(u2, 1)
             VSR_WELD_POS(2, 3, d0, true, false) VSR_WELD_POS(2, 2, d1, true, false)
             VSR_WELD_POS(3, 0, u3, false, false) VSR_WELD_POS(3, 1, u2, false, false)
           }
 #undef VSR_GATHER_P
+#undef VSR_GATHER_CS
+#undef VSR_OWN_CS
 #undef VSR_WELD_POS
+          // masses 1, 2 are body2 of the next iteration's horizontal welds
+          r_sincos(th[1], &sn_[1], &cs_[1]);
+          r_sincos(th[2], &sn_[2], &cs_[2]);
           // robot-wide (island-wide) vote
           unsigned bal = __ballot_sync(0xffffffffu, solved || done);
           if ((bal & robot_mask) == robot_mask) done = true;
         }
       }
 
+      r_sincos(th[0], &sn_[0], &cs_[0]);
+      r_sincos(th[3], &sn_[3], &cs_[3]);
       // ---- World.detect: new manifolds for Touch and for the next step
       cmask = 0;
       if (active) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           // cheap reject: far above the highest point of the terrain near this mass
-          int ov = detect_mass(P, x[k], y[k], th[k], hint[k], cbody[k]);
+          int ov = detect_mass(P, x[k], y[k], cs_[k], sn_[k], hint[k], cbody[k]);
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
           if (cbody[k].n > 0) cmask |= 1u << k;
+#ifdef VSR_DEBUG_DUMP
           if (rb == P.debug_robot && tick >= P.debug_tick && tick <= P.debug_tick_end)
             for (int q = 0; q < cbody[k].n; q++) {
               const CCon<real>& c = cbody[k].c[q];
@@ -938,14 +1020,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
                 printf("           p (%.9g, %.9g) depth %.6e id %d jn %.6e jt %.6e\n", (double)c.p[z].px + P.origin_x,
                        (double)c.p[z].py, (double)c.p[z].depth, c.p[z].id, (double)c.p[z].jn, (double)c.p[z].jt);
             }
+#endif
         }
       }
 
       // =========================== Robot.act(t) ===========================
       // ---- Voxel.act: energies; geometry shared by the sensors
-      real s4[4], c4[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) r_sincos(th[k], &s4[k], &c4[k]);
+      const real* s4 = sn_;
+      const real* c4 = cs_;
       // outer corners getIndexedVertex(k, 3-k): NW(-h,+h) NE(+h,+h) SE(+h,-h) SW(-h,-h)
       real ox[4], oy[4];
       {
@@ -985,9 +1067,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
             r_sincos(ang, &sa, &ca);
             if (sd.axes & 1) raw[c++] = sd.rotated ? mvx * ca + mvy * sa : mvx;
             if (sd.axes & 2) {
-              real sb, cb2;
-              r_sincos(ang + real(1.5707963267948966), &sb, &cb2);
-              raw[c++] = sd.rotated ? mvx * cb2 + mvy * sb : mvy;
+              // unit(angle + pi/2) = (-sin, cos) (Velocity.java:75 builds it numerically: same to 1 ulp)
+              raw[c++] = sd.rotated ? -mvx * sa + mvy * ca : mvy;
             }
             dmin = -sd.max_norm;
             dmax = sd.max_norm;
