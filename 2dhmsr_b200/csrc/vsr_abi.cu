@@ -110,6 +110,8 @@ struct Bucket {
   void* d_params = nullptr;
   void* d_ring = nullptr;
   void* d_traj = nullptr;
+  void* d_cbuf = nullptr;
+  size_t cbuf_bytes = 0;
 };
 
 }  // namespace
@@ -160,8 +162,8 @@ static double ground_y_at(const vsr_batch_desc* d, double x) {
 static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
   for (auto& k : b->buckets) {
-    cudaFree(k.d_shape); cudaFree(k.d_ids); cudaFree(k.d_params); cudaFree(k.d_ring); cudaFree(k.d_traj);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
+    cudaFree(k.d_shape); cudaFree(k.d_ids); cudaFree(k.d_params); cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_cbuf = nullptr; k.cbuf_bytes = 0;
   }
   cudaFree(b->d_ticks); cudaFree(b->d_win); cudaFree(b->d_terr_x); cudaFree(b->d_terr_y); cudaFree(b->d_results);
   b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
@@ -657,6 +659,16 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // persistent grid: one wave of resident blocks (a multiple of the SM count), each warp
   // strides over robot groups
   const long long grid = std::max<long long>(1, std::min<long long>(want, (long long)occ * sms));
+  {
+    size_t need = (size_t)grid * threads * 8 * sizeof(CBody<real>);
+    if (need > k.cbuf_bytes) {
+      cudaFree(k.d_cbuf);
+      k.d_cbuf = nullptr;
+      CUDA_TRY(cudaMalloc(&k.d_cbuf, need));
+      k.cbuf_bytes = need;
+    }
+    P.cbuf = k.d_cbuf;
+  }
   kern<<<(unsigned)grid, threads, smem, s>>>(P);
   CUDA_TRY(cudaGetLastError());
   b->last_launches++;

@@ -99,6 +99,7 @@ struct Params {
   unsigned spring_mask;  // bit s = spring s present (scaffoldings)
   int mlp_act;
   int smem_per_warp;     // reals of staging per warp
+  void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   int ctrl;              // CTRL_*
   int sync_mode;         // bit0: barrier per tick, bit1: per velocity iteration (code locality only)
   long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
@@ -337,7 +338,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
 // points with the same id are carried over (ContactConstraint.update).
 template <typename real>
 __device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by, real bc, real bs, int& hint,
-                                        CBody<real>& cb) {
+                                        const CBody<real>& old, int had_contact, CBody<real>& cb, int& n_out) {
   real e = P.half * (r_abs(bc) + r_abs(bs));
   real xlo = bx - e, xhi = bx + e, ylo = by - e;
   int n = P.terr_n;
@@ -345,11 +346,8 @@ __device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by,
   while (s > 0 && P.terr_x[s] > xlo) --s;
   while (s + 2 < n && P.terr_x[s + 1] < xlo) ++s;
   hint = s;
-  const int old_n = cb.n;
-  CBody<real> old;
-  old.n = 0;
-  if (old_n > 0) old = cb;  // only masses already in contact need the warm-start match
-  cb.n = 0;
+  const int old_n = had_contact ? old.n : 0;  // only masses already in contact need the warm-start match
+  int cn = 0;
   int overflow = 0;
   for (int seg = s; seg + 1 < n && P.terr_x[seg] <= xhi; ++seg) {
     real x0 = P.terr_x[seg], x1 = P.terr_x[seg + 1], y0 = P.terr_y[seg], y1 = P.terr_y[seg + 1];
@@ -358,9 +356,9 @@ __device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by,
     if (ylo > r_max(y0, y1)) continue;
     CCon<real> c;
     if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, c)) continue;
-    if (cb.n == MAXC) { overflow = 1; break; }
+    if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
-    for (int i = 0; i < old.n; i++) {
+    for (int i = 0; i < old_n; i++) {
       if (old.c[i].seg != seg) continue;
       for (int k = 0; k < c.n; k++)
         for (int l = 0; l < old.c[i].n; l++)
@@ -369,8 +367,10 @@ __device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by,
             c.p[k].jt = old.c[i].p[l].jt;
           }
     }
-    cb.c[cb.n++] = c;
+    cb.c[cn++] = c;
   }
+  if (cn > 0 || had_contact) cb.n = cn;
+  n_out = cn;
   return overflow;
 }
 
@@ -700,13 +700,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
     for (int s = 0; s < 4; s++)
 #pragma unroll
       for (int k = 0; k < 2; k++) wix[s][k] = wiy[s][k] = wiz[s][k] = real(0);
-    CBody<real> cbody[4];
+    // contact state of this thread's 4 masses: a dense, double-buffered arena in global memory
+    // (thread-local memory is lane-interleaved: one lane's 300-byte struct would touch 75 lines)
+    CBody<real>* const cbase = reinterpret_cast<CBody<real>*>(P.cbuf) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    unsigned flip = 0;
+#define CBODY(k) cbase[2 * (k) + ((flip >> (k)) & 1u)]
     int hint[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      cbody[k].n = 0;
-      hint[k] = 0;
-    }
+    for (int k = 0; k < 4; k++) hint[k] = 0;
     unsigned cmask = 0;  // masses with ground constraints
     int status = 0;
     real last_f = real(0), ar_energy = real(0), ctrl_energy = real(0);
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         for (int k = 0; k < 4; k++) {
           if (cmask & (1u << k)) {
             BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-            contact_init_mass(P, B, cs_[k], sn_[k], cbody[k]);
+            contact_init_mass(P, B, cs_[k], sn_[k], CBODY(k));
             vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
           }
         }
@@ -895,7 +896,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           for (int k = 0; k < 4; k++) {
             if (cmask & (1u << k)) {
               BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-              contact_solve_mass(P, B, cbody[k]);
+              contact_solve_mass(P, B, CBODY(k));
               vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
             }
           }
@@ -934,7 +935,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
             for (int k = 0; k < 4; k++) {
               if (cmask & (1u << k)) {
                 BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-                real ms = contact_position_mass(P, B, cbody[k]);
+                real ms = contact_position_mass(P, B, CBODY(k));
                 minSep = ms < minSep ? ms : minSep;
                 x[k] = B.x; y[k] = B.y; th[k] = B.th;
                 if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
@@ -1002,18 +1003,22 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       r_sincos(th[0], &sn_[0], &cs_[0]);
       r_sincos(th[3], &sn_[3], &cs_[3]);
       // ---- World.detect: new manifolds for Touch and for the next step
+      const unsigned old_cmask = cmask;
       cmask = 0;
       if (active) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           // cheap reject: far above the highest point of the terrain near this mass
-          int ov = detect_mass(P, x[k], y[k], cs_[k], sn_[k], hint[k], cbody[k]);
+          int cn = 0;
+          int ov = detect_mass(P, x[k], y[k], cs_[k], sn_[k], hint[k], CBODY(k), (int)((old_cmask >> k) & 1u),
+                               cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn);
+          flip ^= 1u << k;
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
-          if (cbody[k].n > 0) cmask |= 1u << k;
+          if (cn > 0) cmask |= 1u << k;
 #ifdef VSR_DEBUG_DUMP
           if (rb == P.debug_robot && tick >= P.debug_tick && tick <= P.debug_tick_end)
-            for (int q = 0; q < cbody[k].n; q++) {
-              const CCon<real>& c = cbody[k].c[q];
+            for (int q = 0; q < cn; q++) {
+              const CCon<real>& c = CBODY(k).c[q];
               printf("[kernel] tick %d body %d seg %d n %d normal (%.9g, %.9g) pose (%.9g %.9g %.9g)\n", tick, v * 4 + k,
                      c.seg, c.n, (double)c.nx, (double)c.ny, (double)x[k] + P.origin_x, (double)y[k], (double)th[k]);
               for (int z = 0; z < c.n; z++)
