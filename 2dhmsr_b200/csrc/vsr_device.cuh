@@ -334,10 +334,18 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   return c.n > 0;
 }
 
+// terrain description passed by value (registers) to detect_mass
+template <typename real>
+struct TPar {
+  const real* terr_x;
+  const real* terr_y;
+  int terr_n;
+  real half, base_y;
+};
 // World.detect (dyn4j) for one mass: every ground segment its AABB overlaps; impulses of
 // points with the same id are carried over (ContactConstraint.update).
 template <typename real>
-__device__ __noinline__ int detect_mass(const Params<real>& P, real bx, real by, real bc, real bs, int& hint,
+__device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, real bc, real bs, int& hint,
                                         const CBody<real>& old, int had_contact, CBody<real>& cb, int& n_out) {
   real e = P.half * (r_abs(bc) + r_abs(bs));
   real xlo = bx - e, xhi = bx + e, ylo = by - e;
@@ -378,13 +386,19 @@ template <typename real>
 struct BodyState {
   real x, y, th, vx, vy, w;
 };
+// the scalars the contact routines need, passed by value (registers): taking the kernel's
+// Params by reference would force a local-memory copy of the whole struct
+template <typename real>
+struct CPar {
+  real im, ii, mu, rest_vel, rest_e, lin_tol, max_corr, baumgarte;
+};
 
 // SequentialImpulses.initialize (dyn4j) for the constraints of one mass (the ground is
 // static: invM2 = invI2 = 0), followed by their warm start.
 template <typename real>
-__device__ __noinline__ void contact_init_mass(const Params<real>& P, BodyState<real>& B, real bc, real bs,
-                                               CBody<real>& cb) {
-  const real im = P.inv_m, ii = P.inv_i;
+__device__ __noinline__ BodyState<real> contact_init_mass(const CPar<real> P, BodyState<real> B, real bc, real bs,
+                                                          CBody<real>& cb) {
+  const real im = P.im, ii = P.ii;
   for (int q = 0; q < cb.n; q++) {
     CCon<real>& c = cb.c[q];
     real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
@@ -436,12 +450,13 @@ __device__ __noinline__ void contact_init_mass(const Params<real>& P, BodyState<
       B.w -= ii * (p.r1x * Py - p.r1y * Px);
     }
   }
+  return B;
 }
 
 // SequentialImpulses.solveVelocityConstraints (dyn4j) for the constraints of one mass.
 template <typename real>
-__device__ __noinline__ void contact_solve_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
-  const real im = P.inv_m, ii = P.inv_i;
+__device__ __noinline__ BodyState<real> contact_solve_mass(const CPar<real> P, BodyState<real> B, CBody<real>& cb) {
+  const real im = P.im, ii = P.ii;
   for (int q = 0; q < cb.n; q++) {
     CCon<real>& c = cb.c[q];
     real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
@@ -520,12 +535,14 @@ __device__ __noinline__ void contact_solve_mass(const Params<real>& P, BodyState
       }
     }
   }
+  return B;
 }
 
 // SequentialImpulses.solvePositionContraints (dyn4j) for one mass; returns min separation.
 template <typename real>
-__device__ __noinline__ real contact_position_mass(const Params<real>& P, BodyState<real>& B, CBody<real>& cb) {
-  const real im = P.inv_m, ii = P.inv_i;
+__device__ __noinline__ BodyState<real> contact_position_mass(const CPar<real> P, BodyState<real> B, CBody<real>& cb,
+                                                              real& minSepOut) {
+  const real im = P.im, ii = P.ii;
   real minSep = real(0);
   for (int q = 0; q < cb.n; q++) {
     CCon<real>& c = cb.c[q];
@@ -549,7 +566,8 @@ __device__ __noinline__ real contact_position_mass(const Params<real>& P, BodySt
       B.th -= ii * (r1x * Jy - r1y * Jx);
     }
   }
-  return minSep;
+  minSepOut = minSep;
+  return B;
 }
 
 // ---------------------------------------------------------------- springs
@@ -660,6 +678,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   const real lin_f = r_clamp<real>(real(1) - dt * P.lin_damp, real(0), real(1));
   const real ang_f = r_clamp<real>(real(1) - dt * P.ang_damp, real(0), real(1));
   const real max_trans2 = P.max_trans * P.max_trans;
+  const TPar<real> tpar = {P.terr_x, P.terr_y, P.terr_n, P.half, P.base_y};
+  const CPar<real> cpar = {P.inv_m, P.inv_i, P.mu, P.rest_vel, P.rest_e, P.lin_tol, P.max_corr, P.baumgarte};
   // reduced-mass springs: k, d and gamma are constants (same expression as the per-spring one)
   const real gam_c = real(1) / (dt * (real(2) * P.red_mass * P.spring_zeta * P.spring_w + dt * (P.red_mass * P.spring_w * P.spring_w)));
   const int sync_mode = P.sync_mode;
@@ -734,7 +754,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         for (int k = 0; k < 4; k++) {
           if (cmask & (1u << k)) {
             BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-            contact_init_mass(P, B, cs_[k], sn_[k], CBODY(k));
+            B = contact_init_mass(cpar, B, cs_[k], sn_[k], CBODY(k));
             vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
           }
         }
@@ -896,7 +916,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           for (int k = 0; k < 4; k++) {
             if (cmask & (1u << k)) {
               BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-              contact_solve_mass(P, B, CBODY(k));
+              B = contact_solve_mass(cpar, B, CBODY(k));
               vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
             }
           }
@@ -935,7 +955,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
             for (int k = 0; k < 4; k++) {
               if (cmask & (1u << k)) {
                 BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-                real ms = contact_position_mass(P, B, CBODY(k));
+                real ms;
+                B = contact_position_mass(cpar, B, CBODY(k), ms);
                 minSep = ms < minSep ? ms : minSep;
                 x[k] = B.x; y[k] = B.y; th[k] = B.th;
                 if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
@@ -1010,7 +1031,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         for (int k = 0; k < 4; k++) {
           // cheap reject: far above the highest point of the terrain near this mass
           int cn = 0;
-          int ov = detect_mass(P, x[k], y[k], cs_[k], sn_[k], hint[k], CBODY(k), (int)((old_cmask >> k) & 1u),
+          int ov = detect_mass(tpar, x[k], y[k], cs_[k], sn_[k], hint[k], CBODY(k), (int)((old_cmask >> k) & 1u),
                                cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn);
           flip ^= 1u << k;
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
