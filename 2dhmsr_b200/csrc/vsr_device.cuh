@@ -649,6 +649,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
   real* sgam = reinterpret_cast<real*>(spr2 + 18 * SPR_STRIDE);               // [18][SPR_STRIDE], effective-mass mode only
   real* stage = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)wib * P.smem_per_warp;
+  // contact exchange: the contact masses of a warp are solved one per lane; their owners post the
+  // mass state here ([field][item], conflict-free for the solving lanes) and read the result back
+  real* xb = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp + (size_t)wib * 288;
+  int* wl = reinterpret_cast<int*>(xb + 256);  // work list: (owner lane << 3) | (mass << 1) | buffer
+#define XB(j, item) xb[(j) * 32 + (item)]
   const int nvox = S.nvox;
   const int G = 32 / nvox;
   const int slot = lane / nvox;
@@ -729,6 +734,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #pragma unroll
     for (int k = 0; k < 4; k++) hint[k] = 0;
     unsigned cmask = 0;  // masses with ground constraints
+    int n_items = 0, item_base = 0;  // this warp's contact masses / this lane's first slot
+    bool xmode = true;               // all of them fit one round of 32 lanes
+    CBody<real>* cbp = nullptr;      // the contact mass this lane solves
     int status = 0;
     real last_f = real(0), ar_energy = real(0), ctrl_energy = real(0);
     real readings[MAX_READ];
@@ -749,7 +757,29 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         w[k] *= ang_f;
       }
       // ---- contacts: initialise + warm start
-      if (cmask) {
+#define VSR_SLOT(k) (item_base + __popc(cmask & ((1u << (k)) - 1u)))
+      if (n_items > 0 && xmode) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (cmask & (1u << k)) {
+            const int sl = VSR_SLOT(k);
+            XB(0, sl) = x[k]; XB(1, sl) = y[k]; XB(2, sl) = cs_[k]; XB(3, sl) = sn_[k];
+            XB(4, sl) = vx[k]; XB(5, sl) = vy[k]; XB(6, sl) = w[k];
+          }
+        __syncwarp();
+        if (lane < n_items) {
+          BodyState<real> B = {XB(0, lane), XB(1, lane), real(0), XB(4, lane), XB(5, lane), XB(6, lane)};
+          B = contact_init_mass(cpar, B, XB(2, lane), XB(3, lane), *cbp);
+          XB(4, lane) = B.vx; XB(5, lane) = B.vy; XB(6, lane) = B.w;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (cmask & (1u << k)) {
+            const int sl = VSR_SLOT(k);
+            vx[k] = XB(4, sl); vy[k] = XB(5, sl); w[k] = XB(6, sl);
+          }
+      } else if (cmask) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (cmask & (1u << k)) {
@@ -911,7 +941,27 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #undef VSR_GATHER_V
 #undef VSR_WELD_VEL
 
-        if (cmask) {
+        if (n_items > 0 && xmode) {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (cmask & (1u << k)) {
+              const int sl = VSR_SLOT(k);
+              XB(4, sl) = vx[k]; XB(5, sl) = vy[k]; XB(6, sl) = w[k];
+            }
+          __syncwarp();
+          if (lane < n_items) {
+            BodyState<real> B = {real(0), real(0), real(0), XB(4, lane), XB(5, lane), XB(6, lane)};
+            B = contact_solve_mass(cpar, B, *cbp);
+            XB(4, lane) = B.vx; XB(5, lane) = B.vy; XB(6, lane) = B.w;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (cmask & (1u << k)) {
+              const int sl = VSR_SLOT(k);
+              vx[k] = XB(4, sl); vy[k] = XB(5, sl); w[k] = XB(6, sl);
+            }
+        } else if (cmask) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             if (cmask & (1u << k)) {
@@ -949,7 +999,39 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         for (int it = 0; it < P.pos_iters; it++) {
           if (__all_sync(0xffffffffu, done)) break;
           bool solved = true;
-          if (!done && cmask) {
+          if (n_items > 0 && xmode) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (cmask & (1u << k)) {
+                const int sl = VSR_SLOT(k);
+                XB(0, sl) = x[k]; XB(1, sl) = y[k]; XB(2, sl) = th[k]; XB(7, sl) = done ? real(1) : real(0);
+              }
+            __syncwarp();
+            if (lane < n_items) {
+              real ms = real(0);
+              if (XB(7, lane) == real(0)) {
+                BodyState<real> B = {XB(0, lane), XB(1, lane), XB(2, lane), real(0), real(0), real(0)};
+                B = contact_position_mass(cpar, B, *cbp, ms);
+                XB(0, lane) = B.x; XB(1, lane) = B.y; XB(2, lane) = B.th;
+              }
+              XB(3, lane) = ms;
+            }
+            __syncwarp();
+            if (!done && cmask) {
+              real minSep = real(0);
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                if (cmask & (1u << k)) {
+                  const int sl = VSR_SLOT(k);
+                  x[k] = XB(0, sl); y[k] = XB(1, sl); th[k] = XB(2, sl);
+                  const real ms = XB(3, sl);
+                  minSep = ms < minSep ? ms : minSep;
+                  if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
+                }
+              solved = minSep >= real(-3) * P.lin_tol;
+            }
+            __syncwarp();
+          } else if (!done && cmask) {
             real minSep = real(0);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -1047,6 +1129,31 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
                        (double)c.p[z].py, (double)c.p[z].depth, c.p[z].id, (double)c.p[z].jn, (double)c.p[z].jt);
             }
 #endif
+        }
+      }
+
+      // ---- work list of this warp's contact masses (one per lane from the next tick on)
+      {
+        const int cnt = __popc(cmask);
+        int incl = cnt;
+#pragma unroll
+        for (int d2 = 1; d2 < 32; d2 <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d2);
+          if (lane >= d2) incl += t;
+        }
+        item_base = incl - cnt;
+        n_items = __shfl_sync(0xffffffffu, incl, 31);
+        xmode = n_items <= 32;
+        if (n_items > 0 && xmode) {
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (cmask & (1u << k)) wl[VSR_SLOT(k)] = (lane << 3) | (k << 1) | (int)((flip >> k) & 1u);
+          __syncwarp();
+          if (lane < n_items) {
+            const int code = wl[lane];
+            cbp = reinterpret_cast<CBody<real>*>(P.cbuf) + ((size_t)blockIdx.x * blockDim.x + (size_t)wib * 32 + (code >> 3)) * 8 + (code & 7);
+          }
         }
       }
 
