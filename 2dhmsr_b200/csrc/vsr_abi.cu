@@ -634,7 +634,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // [18][stride] spring 4-vectors (+ [18][stride] gamma in effective-mass mode) + per-warp staging
   const int stride = sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2;
   const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) + (size_t)wpb * (P.smem_per_warp + 288) * sizeof(real);
-  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 3;
+  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
   switch (d.controller_kind) {

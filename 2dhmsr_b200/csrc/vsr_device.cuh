@@ -831,6 +831,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       VSR_SPRINGS(VSR_SPRING_INIT)
 #undef VSR_SPRING_INIT
 
+      if (sync_mode & 4) __syncthreads();
       // ---- welds: WeldJoint.initializeConstraints + warm start.
       // Side s of this voxel: 0 left (own masses 0,3 are body1; partner masses 1,2 body2),
       // 1 right (own 1,2 are body2; partner 0,3 body1), 2 down (own 3,2 body1; partner 0,1
@@ -906,6 +907,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         VSR_SPRINGS(VSR_SPRING_SOLVE)
 #undef VSR_SPRING_SOLVE
 
+        if (sync_mode & 8) __syncthreads();
         // WeldJoint.solveVelocityConstraints.  All partner values of a phase are gathered
         // BEFORE any lane applies an update, so the two lanes that own the two masses of a
         // weld compute the very same impulse.
@@ -941,6 +943,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #undef VSR_GATHER_V
 #undef VSR_WELD_VEL
 
+        if (sync_mode & 8) __syncthreads();
         if (n_items > 0 && xmode) {
 #pragma unroll
           for (int k = 0; k < 4; k++)
@@ -973,6 +976,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         }
       }
 
+      if (sync_mode & 4) __syncthreads();
       // ---- integrate positions (integratePosition, dyn4j; translation/rotation caps)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -1105,6 +1109,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 
       r_sincos(th[0], &sn_[0], &cs_[0]);
       r_sincos(th[3], &sn_[3], &cs_[3]);
+      if (sync_mode & 4) __syncthreads();
       // ---- World.detect: new manifolds for Touch and for the next step
       const unsigned old_cmask = cmask;
       cmask = 0;
@@ -1158,6 +1163,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       }
 
       // =========================== Robot.act(t) ===========================
+      if (sync_mode & 4) __syncthreads();
       // ---- Voxel.act: energies; geometry shared by the sensors
       const real* s4 = sn_;
       const real* c4 = cs_;
