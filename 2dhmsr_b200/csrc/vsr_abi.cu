@@ -99,6 +99,12 @@ extern "C" int vsr_tick_count(double final_t, double dt) {
 
 namespace {
 
+struct Xfer {
+  void* h = nullptr;  // pinned staging copy, device precision
+  void* d = nullptr;
+  size_t bytes = 0;
+};
+
 struct Bucket {
   ShapeDev shape;
   std::vector<int> robot_ids;  // batch indices, ascending
@@ -142,6 +148,7 @@ struct vsr_batch {
   void* d_terr_y = nullptr;
   double* d_results = nullptr;
   int last_launches = 0;
+  std::vector<Xfer> xfers;  // not shared: one handle per host thread
 };
 
 static int sensor_dim(const vsr_sensor& s) {
@@ -159,13 +166,16 @@ static double ground_y_at(const vsr_batch_desc* d, double x) {
   return std::numeric_limits<double>::quiet_NaN();
 }
 
+static void free_xfers(vsr_batch* b);
 static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
+  free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_shape); cudaFree(k.d_ids); cudaFree(k.d_params); cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_cbuf = nullptr; k.cbuf_bytes = 0;
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
+    k.d_cbuf = nullptr; k.cbuf_bytes = 0;
   }
-  cudaFree(b->d_ticks); cudaFree(b->d_win); cudaFree(b->d_terr_x); cudaFree(b->d_terr_y); cudaFree(b->d_results);
+  cudaFree(b->d_results);
   b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
   b->uploaded = b->ran = false;
 }
@@ -480,16 +490,32 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
   return VSR_OK;
 }
 
-template <typename real>
-static int upload_array(const std::vector<double>& src, void** dst, cudaStream_t s, size_t* bytes) {
-  std::vector<real> tmp(src.begin(), src.end());
-  CUDA_TRY(cudaMalloc(dst, std::max<size_t>(1, tmp.size()) * sizeof(real)));
-  if (!tmp.empty()) {
-    CUDA_TRY(cudaMemcpyAsync(*dst, tmp.data(), tmp.size() * sizeof(real), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaStreamSynchronize(s));  // tmp is a local
-  }
-  *bytes += tmp.size() * sizeof(real);
+// One host->device transfer: a pinned staging copy (already in device precision) and its
+// device destination.  Built at the first upload; later uploads of the same batch only
+// re-issue the copies (no allocation, pinned source).
+
+static int add_xfer(std::vector<Xfer>& xs, const void* src, size_t bytes, void** dptr) {
+  Xfer x;
+  x.bytes = bytes;
+  CUDA_TRY(cudaMalloc(&x.d, std::max<size_t>(bytes, 16)));
+  CUDA_TRY(cudaHostAlloc(&x.h, std::max<size_t>(bytes, 16), cudaHostAllocDefault));
+  if (bytes) memcpy(x.h, src, bytes);
+  *dptr = x.d;
+  xs.push_back(x);
   return VSR_OK;
+}
+template <typename real>
+static int add_xfer_real(std::vector<Xfer>& xs, const std::vector<double>& src, void** dptr) {
+  std::vector<real> tmp(src.begin(), src.end());
+  return add_xfer(xs, tmp.data(), tmp.size() * sizeof(real), dptr);
+}
+
+static void free_xfers(vsr_batch* b) {
+  for (auto& x : b->xfers) {
+    cudaFree(x.d);
+    cudaFreeHost(x.h);
+  }
+  b->xfers.clear();
 }
 
 extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
@@ -500,48 +526,50 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
     return fail(VSR_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
   }
   if (device < 0 || device >= ndev) return fail(VSR_ERR_INVALID_ARGUMENT, "device out of range");
-  if (b->uploaded) free_device(b);
+  if (b->uploaded && b->device != device) free_device(b);
   CUDA_TRY(cudaSetDevice(device));
   b->device = device;
   cudaStream_t s = (cudaStream_t)stream;
   const bool f64 = b->precision == VSR_PRECISION_F64;
   const size_t esz = f64 ? 8 : 4;
   const int nt = (int)b->ticks.size();
-  b->upload_bytes = 0;
-  CUDA_TRY(cudaMalloc((void**)&b->d_ticks, nt * sizeof(double)));
-  CUDA_TRY(cudaMemcpyAsync(b->d_ticks, b->ticks.data(), nt * sizeof(double), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMalloc((void**)&b->d_win, b->win_first.size() * sizeof(int16_t)));
-  CUDA_TRY(cudaMemcpyAsync(b->d_win, b->win_first.data(), b->win_first.size() * sizeof(int16_t),
-                           cudaMemcpyHostToDevice, s));
-  b->upload_bytes += nt * sizeof(double) + b->win_first.size() * sizeof(int16_t);
-  int rc;
-  if (f64) {
-    if ((rc = upload_array<double>(b->terr_x, &b->d_terr_x, s, &b->upload_bytes))) return rc;
-    if ((rc = upload_array<double>(b->terr_y, &b->d_terr_y, s, &b->upload_bytes))) return rc;
-  } else {
-    if ((rc = upload_array<float>(b->terr_x, &b->d_terr_x, s, &b->upload_bytes))) return rc;
-    if ((rc = upload_array<float>(b->terr_y, &b->d_terr_y, s, &b->upload_bytes))) return rc;
-  }
-  CUDA_TRY(cudaMalloc((void**)&b->d_results, b->n_robots * sizeof(vsr_result)));
-  CUDA_TRY(cudaMemsetAsync(b->d_results, 0, b->n_robots * sizeof(vsr_result), s));
-  for (auto& k : b->buckets) {
-    const size_t nr = k.robot_ids.size();
-    CUDA_TRY(cudaMalloc((void**)&k.d_shape, sizeof(ShapeDev)));
-    CUDA_TRY(cudaMemcpyAsync(k.d_shape, &k.shape, sizeof(ShapeDev), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMalloc((void**)&k.d_ids, nr * sizeof(int)));
-    CUDA_TRY(cudaMemcpyAsync(k.d_ids, k.robot_ids.data(), nr * sizeof(int), cudaMemcpyHostToDevice, s));
-    b->upload_bytes += sizeof(ShapeDev) + nr * sizeof(int);
-    if (f64) rc = upload_array<double>(k.params, &k.d_params, s, &b->upload_bytes);
-    else rc = upload_array<float>(k.params, &k.d_params, s, &b->upload_bytes);
-    if (rc) return rc;
-    size_t ring = (size_t)k.shape.ring_depth * (size_t)std::max(1, k.shape.n_channels) * nr * (size_t)k.shape.nvox;
-    CUDA_TRY(cudaMalloc(&k.d_ring, ring * esz));
-    if (k.traj_robots > 0) {
-      size_t tb = (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz;
-      CUDA_TRY(cudaMalloc(&k.d_traj, tb));
-      CUDA_TRY(cudaMemsetAsync(k.d_traj, 0, tb, s));
+  if (!b->uploaded) {
+    std::vector<Xfer>& xs = b->xfers;
+    int rc;
+    if ((rc = add_xfer(xs, b->ticks.data(), nt * sizeof(double), (void**)&b->d_ticks))) return rc;
+    if ((rc = add_xfer(xs, b->win_first.data(), b->win_first.size() * sizeof(int16_t), (void**)&b->d_win))) return rc;
+    if (f64) {
+      if ((rc = add_xfer_real<double>(xs, b->terr_x, &b->d_terr_x))) return rc;
+      if ((rc = add_xfer_real<double>(xs, b->terr_y, &b->d_terr_y))) return rc;
+    } else {
+      if ((rc = add_xfer_real<float>(xs, b->terr_x, &b->d_terr_x))) return rc;
+      if ((rc = add_xfer_real<float>(xs, b->terr_y, &b->d_terr_y))) return rc;
+    }
+    CUDA_TRY(cudaMalloc((void**)&b->d_results, b->n_robots * sizeof(vsr_result)));
+    for (auto& k : b->buckets) {
+      const size_t nr = k.robot_ids.size();
+      if ((rc = add_xfer(xs, &k.shape, sizeof(ShapeDev), (void**)&k.d_shape))) return rc;
+      if ((rc = add_xfer(xs, k.robot_ids.data(), nr * sizeof(int), (void**)&k.d_ids))) return rc;
+      rc = f64 ? add_xfer_real<double>(xs, k.params, &k.d_params) : add_xfer_real<float>(xs, k.params, &k.d_params);
+      if (rc) return rc;
+      size_t ring = (size_t)k.shape.ring_depth * (size_t)std::max(1, k.shape.n_channels) * nr * (size_t)k.shape.nvox;
+      CUDA_TRY(cudaMalloc(&k.d_ring, ring * esz));
+      if (k.traj_robots > 0) {
+        size_t tb = (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz;
+        CUDA_TRY(cudaMalloc(&k.d_traj, tb));
+      }
     }
   }
+  // the copies proper: every input of the episode, from pinned memory
+  b->upload_bytes = 0;
+  for (auto& x : b->xfers) {
+    if (x.bytes) CUDA_TRY(cudaMemcpyAsync(x.d, x.h, x.bytes, cudaMemcpyHostToDevice, s));
+    b->upload_bytes += x.bytes;
+  }
+  CUDA_TRY(cudaMemsetAsync(b->d_results, 0, b->n_robots * sizeof(vsr_result), s));
+  for (auto& k : b->buckets)
+    if (k.traj_robots > 0)
+      CUDA_TRY(cudaMemsetAsync(k.d_traj, 0, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   b->uploaded = true;
   b->ran = false;

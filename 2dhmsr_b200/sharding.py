@@ -18,12 +18,29 @@ def shard_range(n_robots: int, rank: int, world_size: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+class _DevicePtr:
+    """Minimal ``__cuda_array_interface__`` holder for a raw device pointer."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def device_records(batch, device):
+    """The device-resident ``vsr_result[n]`` of a DeviceBatch as a torch float64 [n, 11] view
+    (no copy): the buffer the final NCCL gather sends from."""
+    import torch
+
+    ptr, nbytes = batch.results_device()
+    t = torch.as_tensor(_DevicePtr(ptr, nbytes // 8), device=device)
+    return t.view(-1, 11)
+
+
 def gather_results(local, n_robots: int, device=None):
     """all_gather the per-rank ``vsr_result`` records into batch order on every rank.
 
-    ``local`` is either a numpy structured array (host records) or a torch uint8/float64 tensor
-    viewing the device-resident records (``vsr_batch_results_device``), in which case NCCL sends
-    straight from that buffer.  Returns a numpy structured array of ``n_robots`` records.
+    ``local`` is a numpy structured array (host records) or a torch float64 [n, 11] tensor
+    (``device_records``: NCCL then sends straight from the library's result buffer).
+    Returns a numpy structured array of ``n_robots`` records.
     """
     import torch
     import torch.distributed as dist
@@ -41,10 +58,15 @@ def gather_results(local, n_robots: int, device=None):
     if ws == 1:
         return t.cpu().numpy().reshape(-1).view(RESULT_DTYPE).copy()
     sizes = [shard_range(n_robots, r, ws) for r in range(ws)]
-    maxn = max(e - b for b, e in sizes)
+    counts = [e - b for b, e in sizes]
+    if min(counts) == max(counts):  # equal shards: one collective into one buffer, one D2H
+        out = torch.empty((n_robots, words), dtype=torch.float64, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out.cpu().numpy().reshape(-1).view(RESULT_DTYPE).copy()
+    maxn = max(counts)
     pad = torch.zeros((maxn, words), dtype=torch.float64, device=t.device)
     pad[: t.shape[0]] = t
     out = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(out, pad)
-    parts = [o[: e - b].cpu().numpy() for o, (b, e) in zip(out, sizes)]
+    parts = [o[:c].cpu().numpy() for o, c in zip(out, counts)]
     return np.concatenate(parts).reshape(-1).view(RESULT_DTYPE).copy()

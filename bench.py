@@ -206,17 +206,22 @@ def main():
         launches += db.last_launches()
     barrier()
     # ---- end to end through the C ABI: host buffers -> H2D -> run -> D2H (+ final gather)
+    def e2e_step():
+        db.upload(local, sp)                      # H2D of every input of the episode (pinned staging)
+        db.run(sp)
+        if world > 1:                             # NCCL all_gather straight from the result buffer
+            torch.cuda.current_stream(dev).wait_stream(stream)
+            return sharding.gather_results(sharding.device_records(db, dev), n_total)
+        return db.results()                       # D2H of the Outcome records
+
+    e2e_step()                                    # untimed: NCCL communicator / pinned buffers
     h2d = None
     t_e2e = 0.0
     for _ in range(args.steps):
         flush.fill_(1)
         barrier()
         t0 = time.perf_counter()
-        db.upload(local, sp)
-        db.run(sp)
-        res = db.results()
-        if world > 1:
-            res = sharding.gather_results(res, n_total, device=dev)
+        res = e2e_step()
         torch.cuda.synchronize(dev)
         t_e2e += time.perf_counter() - t0
         launches += db.last_launches()
