@@ -317,7 +317,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     }
     if (nv > MAX_VOX) {
       delete b;
-      return fail(VSR_ERR_UNSUPPORTED, "robots with more than 32 voxels are not on the accelerated path yet");
+      return fail(VSR_ERR_UNSUPPORTED, "robots with more than 128 voxels are not on the accelerated path yet");
     }
     S.nvox = nv;
     auto at = [&](int x, int y) { return (x < 0 || y < 0 || x >= sh.w || y >= sh.h) ? -1 : grid[(size_t)y * sh.w + x]; };
@@ -638,11 +638,12 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     int got = sscanf(dbg, "%ld:%ld:%ld", &dr, &dk, &de);
     if (got >= 2) { P.debug_robot = dr; P.debug_tick = (int)dk; P.debug_tick_end = (int)(got == 3 ? de : dk); }
   }
-  const int nvox = k.shape.nvox, G = 32 / nvox;
+  const int nvox = k.shape.nvox;
+  const bool blk = nvox > 32;  // one block per robot (33..128 voxels)
+  const int G = blk ? 1 : 32 / nvox;
   int maxn = 1;
   for (int i = 0; i < k.shape.n_layers; i++) maxn = std::max(maxn, k.shape.neurons[i]);
   int per_robot = 2 * ((maxn + 3) & ~3);
-  P.smem_per_warp = std::max(128, per_robot * G);
   int wpb_env = getenv("VSR_WPB") ? atoi(getenv("VSR_WPB")) : 0;
   const long long groups_all = ((long long)k.robot_ids.size() + G - 1) / G;
   // Warps of a block walk the instruction stream together (see the barriers in the kernel), so
@@ -655,27 +656,29 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     if (groups_all <= (long long)sms_ * 12) wpb = (int)std::max<long long>(1, (groups_all + sms_ - 1) / sms_);
   }
   if (wpb_env > 0) wpb = std::min(12, wpb_env);
-  // shared memory per thread: 18 spring 4-vectors (+ gamma); keep the block under ~200 KB
   const bool eff_mode = st.spring_mass_mode == VSR_SPRING_MASS_EFFECTIVE;
   if (sizeof(real) == 8) wpb = std::min(wpb, VSR_MAX_THREADS / 64);  // fp64: 32-byte vectors, half the stride
+  if (blk) wpb = (nvox + 31) / 32;
   const int threads = 32 * wpb;
-  // [18][stride] spring 4-vectors (+ [18][stride] gamma in effective-mass mode) + per-warp staging
-  const int stride = sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2;
-  const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) + (size_t)wpb * (P.smem_per_warp + 288) * sizeof(real);
+  if (blk) P.smem_per_warp = std::max(128, (per_robot + wpb - 1) / wpb);  // block-wide staging = wpb * this
+  else P.smem_per_warp = std::max(128, per_robot * G);
+  // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
+  // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
+  const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
+                      (size_t)wpb * (P.smem_per_warp + 288) * sizeof(real) + (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
   P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
+#define VSR_PICK(C)                                                                                  \
+  kern = blk ? (fast ? vsr_episode_kernel<real, C, true, true> : vsr_episode_kernel<real, C, false, true>) \
+             : (fast ? vsr_episode_kernel<real, C, true, false> : vsr_episode_kernel<real, C, false, false>)
   switch (d.controller_kind) {
-    case VSR_CTRL_PHASE_SIN:
-      kern = fast ? vsr_episode_kernel<real, CTRL_PHASE_SIN, true> : vsr_episode_kernel<real, CTRL_PHASE_SIN, false>;
-      break;
-    case VSR_CTRL_TABULATED:
-      kern = fast ? vsr_episode_kernel<real, CTRL_TABULATED, true> : vsr_episode_kernel<real, CTRL_TABULATED, false>;
-      break;
-    default:
-      kern = fast ? vsr_episode_kernel<real, CTRL_MLP, true> : vsr_episode_kernel<real, CTRL_MLP, false>;
-      break;
+    case VSR_CTRL_PHASE_SIN: VSR_PICK(CTRL_PHASE_SIN); break;
+    case VSR_CTRL_TABULATED: VSR_PICK(CTRL_TABULATED); break;
+    default: VSR_PICK(CTRL_MLP); break;
   }
+#undef VSR_PICK
   P.ctrl = d.controller_kind;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0, sms = 0;
@@ -683,9 +686,9 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
   if (occ < 1) return fail(VSR_ERR_CUDA, "episode kernel does not fit on an SM");
   const long long groups = (P.n_robots + G - 1) / G;
-  const long long want = (groups + wpb - 1) / wpb;
+  const long long want = blk ? groups : (groups + wpb - 1) / wpb;
   // persistent grid: one wave of resident blocks (a multiple of the SM count), each warp
-  // strides over robot groups
+  // (or block, for big robots) strides over robot groups
   const long long grid = std::max<long long>(1, std::min<long long>(want, (long long)occ * sms));
   {
     size_t need = (size_t)grid * threads * 8 * sizeof(CBody<real>);

@@ -30,7 +30,7 @@
 
 namespace vsr {
 
-constexpr int MAX_VOX = 32;    // voxels per robot on the one-warp path
+constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
 constexpr int MAX_SENS = 4;    // sensors per voxel
 constexpr int MAX_READ = 6;    // readings per voxel
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
@@ -246,6 +246,9 @@ __device__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx
 template <typename real>
 __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real bs, real half, real x0, real y0,
                                                  real x1, real y1, real base_y, CCon<real>& c) {
+  // exact geometric ties (a mass lying flat on a flat segment) are decided by rule, with this
+  // margin, exactly as in the oracle: the mass' own face wins
+  const real tie_eps = sizeof(real) == 8 ? real(1e-12) : real(1e-6);
   Poly4<real> A, B;
   const real lx[4] = {-1, 1, 1, -1}, ly[4] = {-1, -1, 1, 1};
 #pragma unroll
@@ -290,7 +293,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
       real v = B.nx[j] * (A.vx[i] - B.vx[j]) + B.ny[j] * (A.vy[i] - B.vy[j]);
       s = v < s ? v : s;
     }
-    if (s > best) { best = s; nx = -B.nx[j]; ny = -B.ny[j]; }
+    if (s > best + tie_eps) { best = s; nx = -B.nx[j]; ny = -B.ny[j]; }
   }
   if (!(best < real(0))) return 0;
   // ClippingManifoldSolver.getManifold (dyn4j)
@@ -300,7 +303,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   int flipped = 0;
   real e1 = r_abs((ref.x2 - ref.x1) * nx + (ref.y2 - ref.y1) * ny);
   real e2 = r_abs((inc.x2 - inc.x1) * nx + (inc.y2 - inc.y1) * ny);
-  if (e1 > e2) {
+  if (e1 > e2 + tie_eps) {
     Edge<real> t = ref; ref = inc; inc = t;
     flipped = 1;
   }
@@ -631,7 +634,9 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // present (the default voxel): the 18 solves then form one branch-free basic block.
 // FAST = the default voxel (all four scaffoldings, reduced-mass springs): no per-spring branch,
 // constant gamma.  Everything else takes the generic instantiation.
-template <typename real, int CTRL, bool FAST>
+// BLK = one robot per block (33..128 voxels): neighbour exchange through shared memory and
+// block-wide votes instead of warp shuffles / ballots.
+template <typename real, int CTRL, bool FAST, bool BLK>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   typedef typename Real4T<real>::type R4;
   typedef typename Real2T<real>::type R2;
   // compile-time stride (= the largest block) so that every access has an immediate offset
-  constexpr int SPR_STRIDE = sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2;
+  constexpr int SPR_STRIDE = BLK ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   const int tid = threadIdx.x;
   R4* spr = reinterpret_cast<R4*>(smem_raw);                                  // [18][SPR_STRIDE]
   R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
@@ -654,12 +659,20 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   real* xb = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp + (size_t)wib * 288;
   int* wl = reinterpret_cast<int*>(xb + 256);  // work list: (owner lane << 3) | (mass << 1) | buffer
 #define XB(j, item) xb[(j) * 32 + (item)]
+  // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
+  real* const ex = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * (P.smem_per_warp + 288);
+  real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
+  int exsel = 0;
+#define EXP(slot_, value_) if (BLK) ex[(exsel * 20 + (slot_)) * 128 + tid] = (value_);
+#define EXSYNC() if (BLK) __syncthreads();
+#define EXG(slot_, value_, src_) (BLK ? ex[(exsel * 20 + (slot_)) * 128 + (src_)] : shfl(value_, src_))
+#define EXFLIP() if (BLK) exsel ^= 1;
   const int nvox = S.nvox;
-  const int G = 32 / nvox;
-  const int slot = lane / nvox;
-  const int v = lane - slot * nvox;
-  const bool lane_ok = slot < G;
-  const int lane0 = slot * nvox;  // first lane of this lane's robot
+  const int G = BLK ? 1 : 32 / nvox;
+  const int slot = BLK ? 0 : lane / nvox;
+  const int v = BLK ? tid : lane - slot * nvox;
+  const bool lane_ok = BLK ? (tid < nvox) : (slot < G);
+  const int lane0 = BLK ? 0 : slot * nvox;  // first lane (thread) of this lane's robot
   // lanes of this robot, for robot-wide votes
   const unsigned robot_mask = lane_ok ? (((nvox == 32) ? 0xffffffffu : ((1u << nvox) - 1u)) << lane0) : 0u;
   // neighbour lanes (own lane when absent: the shuffled value is then ignored)
@@ -669,7 +682,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   for (int s = 0; s < 4; s++) {
     int nb = lane_ok ? (int)S.nbr[s][v] : -1;
     has[s] = nb >= 0;
-    nl[s] = has[s] ? lane0 + nb : lane;
+    nl[s] = has[s] ? lane0 + nb : (BLK ? tid : lane);
   }
   real hm[4];
 #pragma unroll
@@ -694,10 +707,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
   // the block-wide barriers below are legal.  The barriers carry no data: they keep the warps of
   // an SM inside the same stretch of the (large, fully unrolled) instruction stream, which turns
   // instruction-cache misses of one warp into hits for the others.
-  const long long warps_total = (long long)gridDim.x * wpb;
+  const long long warps_total = BLK ? (long long)gridDim.x : (long long)gridDim.x * wpb;
   const long long n_pass = (n_groups + warps_total - 1) / warps_total;
   for (long long pass = 0; pass < n_pass; pass++) {
-    const long long group = pass * warps_total + (long long)blockIdx.x * wpb + wib;
+    const long long group = pass * warps_total + (BLK ? (long long)blockIdx.x : (long long)blockIdx.x * wpb + wib);
     const long long rb = group * G + slot;  // bucket index of this lane's robot
     const bool active = lane_ok && rb < P.n_robots;
     const long long gl = rb * nvox + v;     // global voxel lane (ring addressing)
@@ -842,21 +855,24 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         // body2's rotation: partner's for sides 0 and 2, own for sides 1 and 3
         real pc, ps;
         // side 0: partner masses 1, 2
-        pc = shfl(cs_[1], nl[0]); ps = shfl(sn_[1], nl[0]);
+        EXP(0, cs_[0]) EXP(1, sn_[0]) EXP(2, cs_[1]) EXP(3, sn_[1]) EXP(4, cs_[2]) EXP(5, sn_[2])
+        EXSYNC()
+        pc = EXG(2, cs_[1], nl[0]); ps = EXG(3, sn_[1], nl[0]);
         wr2x[0][0] = pc * P.weld_len; wr2y[0][0] = ps * P.weld_len;
-        pc = shfl(cs_[2], nl[0]); ps = shfl(sn_[2], nl[0]);
+        pc = EXG(4, cs_[2], nl[0]); ps = EXG(5, sn_[2], nl[0]);
         wr2x[0][1] = pc * P.weld_len; wr2y[0][1] = ps * P.weld_len;
         // side 1: own masses 1, 2 are body2
         wr2x[1][0] = cs_[1] * P.weld_len; wr2y[1][0] = sn_[1] * P.weld_len;
         wr2x[1][1] = cs_[2] * P.weld_len; wr2y[1][1] = sn_[2] * P.weld_len;
         // side 2: partner masses 0, 1; anchor (0, len) -> R*(0,len) = (-s*len, c*len)
-        pc = shfl(cs_[0], nl[2]); ps = shfl(sn_[0], nl[2]);
+        pc = EXG(0, cs_[0], nl[2]); ps = EXG(1, sn_[0], nl[2]);
         wr2x[2][0] = -ps * P.weld_len; wr2y[2][0] = pc * P.weld_len;
-        pc = shfl(cs_[1], nl[2]); ps = shfl(sn_[1], nl[2]);
+        pc = EXG(2, cs_[1], nl[2]); ps = EXG(3, sn_[1], nl[2]);
         wr2x[2][1] = -ps * P.weld_len; wr2y[2][1] = pc * P.weld_len;
         // side 3: own masses 0, 1 are body2
         wr2x[3][0] = -sn_[0] * P.weld_len; wr2y[3][0] = cs_[0] * P.weld_len;
         wr2x[3][1] = -sn_[1] * P.weld_len; wr2y[3][1] = cs_[1] * P.weld_len;
+        EXFLIP()
       }
       // warm start: body1 += (imp) ; body2 -= (imp), r1 = 0
 #define VSR_WELD_WARM(side, k, own, is_b1)                                                     \
@@ -911,8 +927,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         // WeldJoint.solveVelocityConstraints.  All partner values of a phase are gathered
         // BEFORE any lane applies an update, so the two lanes that own the two masses of a
         // weld compute the very same impulse.
-#define VSR_GATHER_V(tag, part, side) \
-  const real tag##vx = shfl(vx[part], nl[side]), tag##vy = shfl(vy[part], nl[side]), tag##w = shfl(w[part], nl[side]);
+#define VSR_PUBLISH_V()                                                                       \
+  EXP(0, vx[0]) EXP(1, vy[0]) EXP(2, w[0]) EXP(3, vx[1]) EXP(4, vy[1]) EXP(5, w[1])                \
+  EXP(6, vx[2]) EXP(7, vy[2]) EXP(8, w[2]) EXP(9, vx[3]) EXP(10, vy[3]) EXP(11, w[3]) EXSYNC()
+#define VSR_GATHER_V(tag, part, side)                                                         \
+  const real tag##vx = EXG(part * 3 + 0, vx[part], nl[side]), tag##vy = EXG(part * 3 + 1, vy[part], nl[side]), \
+             tag##w = EXG(part * 3 + 2, w[part], nl[side]);
 #define VSR_WELD_VEL(side, k, own, tag, is_b1)                                                  \
   {                                                                                             \
     real v1x = is_b1 ? vx[own] : tag##vx, v1y = is_b1 ? vy[own] : tag##vy, w1 = is_b1 ? w[own] : tag##w; \
@@ -931,16 +951,21 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
     }                                                                                           \
   }
         {  // horizontal welds (left/right sides): each mass has at most one
+          VSR_PUBLISH_V()
           VSR_GATHER_V(l1, 1, 0) VSR_GATHER_V(l2, 2, 0) VSR_GATHER_V(r0, 0, 1) VSR_GATHER_V(r3, 3, 1)
           VSR_WELD_VEL(0, 0, 0, l1, true) VSR_WELD_VEL(0, 1, 3, l2, true)
           VSR_WELD_VEL(1, 0, 1, r0, false) VSR_WELD_VEL(1, 1, 2, r3, false)
+          EXFLIP()
         }
         {  // vertical welds (down/up sides)
+          VSR_PUBLISH_V()
           VSR_GATHER_V(d0, 0, 2) VSR_GATHER_V(d1, 1, 2) VSR_GATHER_V(u3, 3, 3) VSR_GATHER_V(u2, 2, 3)
           VSR_WELD_VEL(2, 0, 3, d0, true) VSR_WELD_VEL(2, 1, 2, d1, true)
           VSR_WELD_VEL(3, 0, 0, u3, false) VSR_WELD_VEL(3, 1, 1, u2, false)
+          EXFLIP()
         }
 #undef VSR_GATHER_V
+#undef VSR_PUBLISH_V
 #undef VSR_WELD_VEL
 
         if (sync_mode & 8) __syncthreads();
@@ -999,9 +1024,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       // ---- position iterations: contacts, then joints; stop when the whole robot
       //      (= one island) reports solved
       {
-        bool done = !active;
+        bool done = BLK ? !(rb < P.n_robots) : !active;  // BLK: idle threads follow their block
         for (int it = 0; it < P.pos_iters; it++) {
-          if (__all_sync(0xffffffffu, done)) break;
+          if (BLK ? done : (bool)__all_sync(0xffffffffu, done)) break;  // BLK: done is block-uniform
           bool solved = true;
           if (n_items > 0 && xmode) {
 #pragma unroll
@@ -1051,10 +1076,15 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
             solved = minSep >= real(-3) * P.lin_tol;
           }
           // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)
-#define VSR_GATHER_P(tag, part, side) \
-  const real tag##x = shfl(x[part], nl[side]), tag##y = shfl(y[part], nl[side]), tag##t = shfl(th[part], nl[side]);
+#define VSR_PUBLISH_P()                                                                       \
+  EXP(0, x[0]) EXP(1, y[0]) EXP(2, th[0]) EXP(3, x[1]) EXP(4, y[1]) EXP(5, th[1])                  \
+  EXP(6, x[2]) EXP(7, y[2]) EXP(8, th[2]) EXP(9, x[3]) EXP(10, y[3]) EXP(11, th[3])                \
+  EXP(12, cs_[0]) EXP(13, sn_[0]) EXP(14, cs_[1]) EXP(15, sn_[1]) EXP(16, cs_[2]) EXP(17, sn_[2]) EXSYNC()
+#define VSR_GATHER_P(tag, part, side)                                                         \
+  const real tag##x = EXG(part * 3 + 0, x[part], nl[side]), tag##y = EXG(part * 3 + 1, y[part], nl[side]), \
+             tag##t = EXG(part * 3 + 2, th[part], nl[side]);
 #define VSR_GATHER_CS(tag, part, side) \
-  const real tag##c = shfl(cs_[part], nl[side]), tag##s = shfl(sn_[part], nl[side]);
+  const real tag##c = EXG(12 + part * 2, cs_[part], nl[side]), tag##s = EXG(13 + part * 2, sn_[part], nl[side]);
 #define VSR_OWN_CS(tag, own) const real tag##c = cs_[own], tag##s = sn_[own];
 #define VSR_WELD_POS(side, own, tag, is_b1, horiz)                                             \
   {                                                                                            \
@@ -1080,21 +1110,26 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
     solved = solved && (!has[side] || ((linErr <= P.lin_tol) && (angErr <= P.ang_tol)));       \
   }
           {
+            VSR_PUBLISH_P()
             VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0) VSR_GATHER_P(r0, 0, 1) VSR_GATHER_P(r3, 3, 1)
             VSR_GATHER_CS(l1, 1, 0) VSR_GATHER_CS(l2, 2, 0) VSR_OWN_CS(r0, 1) VSR_OWN_CS(r3, 2)
             VSR_WELD_POS(0, 0, l1, true, true) VSR_WELD_POS(0, 3, l2, true, true)
             VSR_WELD_POS(1, 1, r0, false, true) VSR_WELD_POS(1, 2, r3, false, true)
+            EXFLIP()
           }
           // masses 0, 1 are body2 of the vertical welds: their angles just changed
           r_sincos(th[0], &sn_[0], &cs_[0]);
           r_sincos(th[1], &sn_[1], &cs_[1]);
           {
+            VSR_PUBLISH_P()
             VSR_GATHER_P(d0, 0, 2) VSR_GATHER_P(d1, 1, 2) VSR_GATHER_P(u3, 3, 3) VSR_GATHER_P(u2, 2, 3)
             VSR_GATHER_CS(d0, 0, 2) VSR_GATHER_CS(d1, 1, 2) VSR_OWN_CS(u3, 0) VSR_OWN_CS(u2, 1)
             VSR_WELD_POS(2, 3, d0, true, false) VSR_WELD_POS(2, 2, d1, true, false)
             VSR_WELD_POS(3, 0, u3, false, false) VSR_WELD_POS(3, 1, u2, false, false)
+            EXFLIP()
           }
 #undef VSR_GATHER_P
+#undef VSR_PUBLISH_P
 #undef VSR_GATHER_CS
 #undef VSR_OWN_CS
 #undef VSR_WELD_POS
@@ -1102,8 +1137,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           r_sincos(th[1], &sn_[1], &cs_[1]);
           r_sincos(th[2], &sn_[2], &cs_[2]);
           // robot-wide (island-wide) vote
-          unsigned bal = __ballot_sync(0xffffffffu, solved || done);
-          if ((bal & robot_mask) == robot_mask) done = true;
+          if (BLK) {
+            if (__syncthreads_and(solved || done)) done = true;
+          } else {
+            unsigned bal = __ballot_sync(0xffffffffu, solved || done);
+            if ((bal & robot_mask) == robot_mask) done = true;
+          }
         }
       }
 
@@ -1264,8 +1303,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       } else {
         // CentralizedSensing + MultiLayerPerceptron.apply: inputs = readings of all voxels
         // in voxel order; lane j of the robot evaluates neurons j, j+nvox, ...
-        const int per_robot = P.smem_per_warp / (G > 0 ? G : 1);
-        real* act0 = stage + (size_t)(lane_ok ? slot : 0) * per_robot;
+        const int per_robot = BLK ? (blockDim.x >> 5) * P.smem_per_warp : P.smem_per_warp / (G > 0 ? G : 1);
+        real* act0 = BLK ? stage_blk : stage + (size_t)(lane_ok ? slot : 0) * per_robot;
         real* act1 = act0 + per_robot / 2;
         if (active) {
           int base = S.read_off[v];
@@ -1274,7 +1313,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           for (int q = 0; q < MAX_READ; q++)
             if (q < nr) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
         }
-        __syncwarp();
+        if (BLK) __syncthreads(); else __syncwarp();
         real* a = act0;
         real* b = act1;
         for (int li = 1; li < S.n_layers; li++) {
@@ -1287,11 +1326,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
               b[j] = activation<real>(P.mlp_act, sum);
             }
           }
-          __syncwarp();
+          if (BLK) __syncthreads(); else __syncwarp();
           real* t = a; a = b; b = t;
         }
         f = active ? a[v] : real(0);
-        __syncwarp();
+        if (BLK) __syncthreads(); else __syncwarp();
       }
       if (r_abs(f) > real(1)) f = f > real(0) ? real(1) : real(-1);
       last_f = f;
@@ -1314,15 +1353,16 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       if (tick == 0 || tick == P.n_ticks - 1) {
         // BehaviorUtils.center: mean over voxels of the mean of the 4 outer corners,
         // summed by the robot's first lane in voxel order (the oracle's order)
-        real* st = stage;
-        __syncwarp();
+        real* st = BLK ? stage_blk : stage;
+        const int sidx = BLK ? tid : lane;
+        if (BLK) __syncthreads(); else __syncwarp();
         if (lane_ok) {
-          st[lane * 4 + 0] = (((ox[0] + ox[1]) + ox[2]) + ox[3]) / real(4);
-          st[lane * 4 + 1] = (((oy[0] + oy[1]) + oy[2]) + oy[3]) / real(4);
-          st[lane * 4 + 2] = ar_energy;
-          st[lane * 4 + 3] = ctrl_energy;
+          st[sidx * 4 + 0] = (((ox[0] + ox[1]) + ox[2]) + ox[3]) / real(4);
+          st[sidx * 4 + 1] = (((oy[0] + oy[1]) + oy[2]) + oy[3]) / real(4);
+          st[sidx * 4 + 2] = ar_energy;
+          st[sidx * 4 + 3] = ctrl_energy;
         }
-        __syncwarp();
+        if (BLK) __syncthreads(); else __syncwarp();
         if (active && v == 0) {
           double sx = 0, sy = 0, sa = 0, sc = 0;
           for (int q = 0; q < nvox; q++) {
@@ -1348,7 +1388,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
             *reinterpret_cast<int2*>(&R[10]) = tail;
           }
         }
-        __syncwarp();
+        if (BLK) __syncthreads(); else __syncwarp();
       }
     }
     // robot-wide OR of the per-voxel status bits into the record

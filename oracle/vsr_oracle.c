@@ -38,6 +38,10 @@
 #define PI 3.14159265358979323846
 #define TWO_PI (2.0 * PI)
 #define EPS_E 2.220446049250313e-16 /* dyn4j Epsilon.E = machine epsilon of double */
+/* Exact geometric ties (a mass lying perfectly flat on a flat segment) are decided by rounding
+   in dyn4j's GJK/EPA; here they are decided by rule, with this margin, identically in the
+   oracle and in the CUDA kernel. */
+#define TIE_EPS 1e-12
 
 static __thread char g_err[512];
 const char* vsr_oracle_last_error(void) { return g_err; }
@@ -759,7 +763,7 @@ static int sat_penetration(const OPoly* A, const OPoly* B, double* nx, double* n
       double v = B->nx[j] * (A->vx[i] - B->vx[j]) + B->ny[j] * (A->vy[i] - B->vy[j]);
       if (v < s) s = v;
     }
-    if (s > best) {
+    if (s > best + TIE_EPS) { /* structural tie (flat mass on flat ground): keep the mass' own face */
       best = s;
       bx = -B->nx[j];
       by = -B->ny[j];
@@ -848,7 +852,7 @@ static int manifold(const OPoly* A, const OPoly* B, double nx, double ny, OConta
   int flipped = 0;
   double e1 = fabs((ref.x2 - ref.x1) * nx + (ref.y2 - ref.y1) * ny);
   double e2 = fabs((inc.x2 - inc.x1) * nx + (inc.y2 - inc.y1) * ny);
-  if (e1 > e2) {
+  if (e1 > e2 + TIE_EPS) { /* parallel edges tie: the reference stays on convex1 (the mass) */
     OEdge t = ref;
     ref = inc;
     inc = t;

@@ -83,9 +83,10 @@ def test_create_validates_like_the_reference():
     bd.desc.param_offsets = C.cast(offs.ctypes.data, C.POINTER(C.c_size_t))
     rc, msg = _create(bd)
     assert rc == A.VSR_ERR_INVALID_ARGUMENT and "Wrong number of weights" in msg  # MultiLayerPerceptron.java:56-62
-    big = helpers.locomotion(1.0).compile(helpers.phase_robots(1, shape="box-10x10"))
+    assert _create(helpers.locomotion(1.0).compile(helpers.phase_robots(1, shape="box-10x10")))[0] == 0
+    big = helpers.locomotion(1.0).compile(helpers.phase_robots(1, shape="box-12x12"))
     rc, msg = _create(big)
-    assert rc == A.VSR_ERR_UNSUPPORTED and "32 voxels" in msg
+    assert rc == A.VSR_ERR_UNSUPPORTED and "128 voxels" in msg
     with pytest.raises(ValueError):
         H.DeviceBatch(bd)
     with pytest.raises(NotImplementedError):

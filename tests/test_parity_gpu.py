@@ -51,6 +51,37 @@ def test_fp64_kernel_matches_oracle_bodies(shape, n):
     assert np.array_equal(res["n_ticks"], ores["n_ticks"])
 
 
+@pytest.mark.parametrize("shape,terrain,sensors", [("box-10x10", "flat", "uniform-ax+t-0"), ("biped-9x5", "hilly-1-10-0", "uniform-t+vxy+a-0"),
+                                                   ("worm-11x3", "flat", "uniform-a-0"), ("box-6x6", "steppy-1-6-2", "uniform-t-0")])
+def test_fp64_big_robots_one_block_per_robot(shape, terrain, sensors):
+    """33..128 voxels (BASELINE config 4 goes up to 10x10): the one-block-per-robot variant."""
+    robots = helpers.phase_robots(3, shape=shape, sensors=sensors, seed=17)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0, terrain=terrain), robots, F64)
+    nb = 4 * bd.n_voxels[0]
+    assert nb > 128 and np.all((res["status"] & 1) == 0)
+    ok = res["status"] == 0
+    assert ok.sum() >= 2
+    assert np.abs(tr[ok][:, :, :nb, :3] - otr[ok][:, :, :nb, :3]).max() < 1e-7
+    assert np.allclose(res["last_center_x"][ok], ores["last_center_x"][ok], atol=1e-6)
+    assert np.allclose(res["area_ratio_energy_last"][ok], ores["area_ratio_energy_last"][ok], rtol=1e-9)
+
+
+def test_fp64_big_robot_mlp_and_mixed_batch():
+    """A 48-voxel robot under CentralizedSensing (96 inputs), and big + small shapes in one batch."""
+    robots = helpers.mlp_robots(2, shape="worm-12x4", sensors="uniform-ax+t-0", hidden=(13,), seed=4)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(2.0), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :192, :3]).max() < 1e-7
+    loco = helpers.locomotion(2.0)
+    a = helpers.phase_robots(2, shape="box-10x10", seed=1)
+    b = helpers.phase_robots(3, shape="biped-4x3", seed=2)
+    mixed = [b[0], a[0], b[1], a[1], b[2]]
+    rm, _ = helpers.gpu_run(loco.compile(mixed))
+    ra, _ = helpers.gpu_run(loco.compile(a))
+    rb, _ = helpers.gpu_run(loco.compile(b))
+    assert rm[[1, 3]].tobytes() == ra.tobytes() and rm[[0, 2, 4]].tobytes() == rb.tobytes()
+
+
 def test_fp64_config1_full_episode():
     """BASELINE config 1 (Example.java:41-48), 1200 ticks, tabulated TimeFunctions."""
     bd, res, tr, ores, otr = _both(helpers.locomotion(), [helpers.config1_robot()], F64)
