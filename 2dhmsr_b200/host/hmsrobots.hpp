@@ -1,0 +1,742 @@
+// hmsrobots.hpp -- C++17 host-side mirror of the reference's Java API for the Locomotion hot
+// path, above the C ABI of include/vsr_b200.h.  Header only.
+//
+// Same class names, argument meaning and error behaviour as it.units.erallab.hmsrobots
+// (file:line cited per item); IllegalArgumentException -> std::invalid_argument,
+// "valid in the reference but not on the accelerated path" -> hmsrobots::Unsupported,
+// CUDA / call-order failures -> std::runtime_error.  Nothing here steps physics:
+// Locomotion::apply flattens the robots into a vsr_batch_desc and calls libvsr_b200.so.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
+#include <regex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../../include/vsr_b200.h"
+
+namespace hmsrobots {
+
+struct Unsupported : std::logic_error {
+  using std::logic_error::logic_error;
+};
+
+// ---------------------------------------------------------------- java.util.Random
+// Bit-exact LCG + polar nextGaussian; needed by Locomotion.createTerrain (Locomotion.java:76-117).
+class JavaRandom {
+ public:
+  explicit JavaRandom(int64_t seed) : seed_((uint64_t(seed) ^ kMult) & kMask) {}
+  int32_t nextInt() { return next(32); }
+  int32_t nextInt(int32_t bound) {
+    if (bound <= 0) throw std::invalid_argument("bound must be positive");
+    if ((bound & -bound) == bound) return int32_t((int64_t(bound) * int64_t(next(31))) >> 31);
+    for (;;) {
+      int32_t bits = next(31), val = bits % bound;
+      if (int64_t(bits) - val + (bound - 1) < (int64_t(1) << 31)) return val;
+    }
+  }
+  double nextDouble() { return double((int64_t(next(26)) << 27) + next(27)) * (1.0 / double(int64_t(1) << 53)); }
+  double nextGaussian() {
+    if (have_) {
+      have_ = false;
+      return nextNext_;
+    }
+    double v1, v2, s;
+    do {
+      v1 = 2 * nextDouble() - 1;
+      v2 = 2 * nextDouble() - 1;
+      s = v1 * v1 + v2 * v2;
+    } while (s >= 1 || s == 0);
+    double mul = std::sqrt(-2 * std::log(s) / s);
+    nextNext_ = v2 * mul;
+    have_ = true;
+    return v1 * mul;
+  }
+
+ private:
+  static constexpr uint64_t kMult = 0x5DEECE66DULL, kMask = (1ULL << 48) - 1;
+  int32_t next(int bits) {
+    seed_ = (seed_ * kMult + 0xBULL) & kMask;
+    return int32_t(int64_t(seed_ >> (48 - bits)));
+  }
+  uint64_t seed_;
+  bool have_ = false;
+  double nextNext_ = 0;
+};
+
+// ---------------------------------------------------------------- util.Grid
+// Storage ts[y*w+x] (Grid.java:180-188); create(w,h,filler) calls the filler x-outer / y-inner
+// (:103-111); iteration and values() are row-major (:69-75,268-270).  Null cells = empty optional.
+template <class T>
+class Grid {
+ public:
+  Grid(int w, int h) : w_(w), h_(h), ts_(size_t(w) * h) {}
+  static Grid create(int w, int h, const std::function<std::optional<T>(int, int)>& filler) {
+    Grid g(w, h);
+    for (int x = 0; x < w; x++)
+      for (int y = 0; y < h; y++) g.ts_[size_t(y) * w + x] = filler(x, y);
+    return g;
+  }
+  static Grid create(int w, int h, const T& v) {
+    return create(w, h, [&](int, int) { return std::optional<T>(v); });
+  }
+  int getW() const { return w_; }
+  int getH() const { return h_; }
+  const std::optional<T>& get(int x, int y) const {
+    static const std::optional<T> none;
+    if (x < 0 || x >= w_ || y < 0 || y >= h_) return none;
+    return ts_[size_t(y) * w_ + x];
+  }
+  void set(int x, int y, std::optional<T> v) { ts_[size_t(y) * w_ + x] = std::move(v); }
+  const std::vector<std::optional<T>>& values() const { return ts_; }
+  size_t count() const {
+    size_t n = 0;
+    for (auto& v : ts_) n += v.has_value();
+    return n;
+  }
+
+ private:
+  int w_, h_;
+  std::vector<std::optional<T>> ts_;
+};
+
+struct DoubleRange {  // util/DoubleRange.java:29-58
+  double min, max;
+  DoubleRange(double mn, double mx) : min(mn), max(mx) {
+    if (mx < mn) throw std::invalid_argument("Max has to be lower or equal than min");
+  }
+  double extent() const { return max - min; }
+  double clip(double v) const { return std::min(std::max(v, min), max); }
+  double normalize(double v) const { return (clip(v) - min) / (max - min); }
+};
+
+// ---------------------------------------------------------------- sensors (descriptions)
+struct Sensor {  // core/sensors/Sensor.java:26-34
+  virtual ~Sensor() = default;
+  virtual std::vector<DoubleRange> getDomains() const = 0;
+  virtual vsr_sensor encode() const = 0;
+  virtual bool isAggregator() const { return false; }
+  virtual bool isSoftNorm() const { return false; }
+};
+using SensorPtr = std::shared_ptr<const Sensor>;
+
+struct Touch : Sensor {  // sensors/Touch.java
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(0, 1)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_TOUCH;
+    return s;
+  }
+};
+struct AreaRatio : Sensor {  // sensors/AreaRatio.java:21-37
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(0.5, 1.5)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_AREA_RATIO;
+    return s;
+  }
+};
+struct Velocity : Sensor {  // sensors/Velocity.java:29-80
+  enum Axis { X = 1, Y = 2 };
+  bool rotated;
+  double maxVelocityNorm;
+  int axes;
+  Velocity(bool rotated_, double maxNorm, int axes_) : rotated(rotated_), maxVelocityNorm(maxNorm), axes(axes_) {}
+  std::vector<DoubleRange> getDomains() const override {
+    std::vector<DoubleRange> d;
+    for (int a : {X, Y})
+      if (axes & a) d.emplace_back(-maxVelocityNorm, maxVelocityNorm);
+    return d;
+  }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_VELOCITY;
+    s.axes = axes;
+    s.rotated = rotated;
+    s.max_velocity_norm = maxVelocityNorm;
+    return s;
+  }
+};
+struct AggregatorSensor : Sensor {  // sensors/AggregatorSensor.java:31-66
+  SensorPtr sensor;
+  double interval;
+  int kind;
+  AggregatorSensor(SensorPtr s, double i, int k) : sensor(std::move(s)), interval(i), kind(k) {
+    if (sensor->isAggregator() || sensor->isSoftNorm()) throw Unsupported("nested aggregators are outside the hot path");
+  }
+  bool isAggregator() const override { return true; }
+  vsr_sensor encode() const override {
+    vsr_sensor s = sensor->encode();
+    s.aggregator = kind;
+    s.interval = interval;
+    return s;
+  }
+};
+struct Average : AggregatorSensor {  // sensors/Average.java
+  Average(SensorPtr s, double i) : AggregatorSensor(std::move(s), i, VSR_AGG_AVERAGE) {}
+  std::vector<DoubleRange> getDomains() const override { return sensor->getDomains(); }
+};
+struct Trend : AggregatorSensor {  // sensors/Trend.java:28-35
+  Trend(SensorPtr s, double i) : AggregatorSensor(std::move(s), i, VSR_AGG_TREND) {}
+  std::vector<DoubleRange> getDomains() const override {
+    std::vector<DoubleRange> d;
+    for (auto& r : sensor->getDomains()) d.emplace_back(-r.extent() / interval, r.extent() / interval);
+    return d;
+  }
+};
+struct SoftNormalization : Sensor {  // sensors/SoftNormalization.java
+  SensorPtr sensor;
+  explicit SoftNormalization(SensorPtr s) : sensor(std::move(s)) {
+    if (sensor->isSoftNorm()) throw Unsupported("nested SoftNormalization is outside the hot path");
+  }
+  bool isSoftNorm() const override { return true; }
+  std::vector<DoubleRange> getDomains() const override {
+    return std::vector<DoubleRange>(sensor->getDomains().size(), DoubleRange(0, 1));
+  }
+  vsr_sensor encode() const override {
+    vsr_sensor s = sensor->encode();
+    s.soft_norm = 1;
+    return s;
+  }
+};
+
+// ---------------------------------------------------------------- Voxel
+class Voxel {  // core/objects/Voxel.java:103-160
+ public:
+  static constexpr double SIDE_LENGTH = 3.0;
+  explicit Voxel(std::vector<SensorPtr> sensors) : sensors_(std::move(sensors)) { vsr_default_material_(&material_); }
+  Voxel(std::vector<SensorPtr> sensors, const vsr_material& m) : sensors_(std::move(sensors)), material_(m) {
+    double lim = (2 * m.mass_side_length_ratio) * (2 * m.mass_side_length_ratio);
+    if (m.area_ratio_passive_min > -std::numeric_limits<double>::infinity() && m.area_ratio_passive_min < lim)
+      throw std::invalid_argument("Min of areaRatioPassiveRange cannot be lower than the value imposed by massSideLengthRatio");  // :132-140
+  }
+  const std::vector<SensorPtr>& getSensors() const { return sensors_; }
+  const vsr_material& material() const { return material_; }
+
+ private:
+  static void vsr_default_material_(vsr_material* m) {  // Voxel.java:57-68
+    *m = vsr_material{};
+    m->side_length = 3.0; m->mass_side_length_ratio = 0.35; m->spring_f = 8.0; m->spring_d = 0.3;
+    m->mass_linear_damping = 0.1; m->mass_angular_damping = 0.1; m->friction = 10.0; m->restitution = 0.1;
+    m->mass = 1.0;
+    m->area_ratio_passive_min = -std::numeric_limits<double>::infinity();
+    m->area_ratio_passive_max = std::numeric_limits<double>::infinity();
+    m->area_ratio_active_min = 0.8; m->area_ratio_active_max = 1.2;
+    m->spring_scaffoldings = VSR_SCAFFOLD_ALL;
+  }
+  std::vector<SensorPtr> sensors_;
+  vsr_material material_;
+};
+
+// ---------------------------------------------------------------- controllers
+// Locomotion.java:195-203 + AbstractTask.java:48: t = 0; while (t < finalT) t = t + dT
+inline std::vector<double> tickTimes(double finalT, double dT) {
+  std::vector<double> t;
+  for (double tt = 0.0; tt < finalT;) {
+    tt = tt + dT;
+    t.push_back(tt);
+  }
+  return t;
+}
+
+struct Controller {  // core/controllers/Controller.java:29 (description only)
+  virtual ~Controller() = default;
+  virtual int kind() const = 0;
+  virtual std::vector<double> params(const Grid<Voxel>& voxels, const std::vector<double>& ticks) const = 0;
+};
+using ControllerPtr = std::shared_ptr<const Controller>;
+
+class TimeFunctions : public Controller {  // controllers/TimeFunctions.java:49-64
+ public:
+  using Fn = std::function<double(double)>;
+  explicit TimeFunctions(Grid<Fn> functions) : functions_(std::move(functions)) {}
+  int kind() const override { return VSR_CTRL_TABULATED; }
+  std::vector<double> params(const Grid<Voxel>& voxels, const std::vector<double>& ticks) const override {
+    std::vector<std::pair<int, int>> cells;
+    for (int y = 0; y < voxels.getH(); y++)
+      for (int x = 0; x < voxels.getW(); x++)
+        if (voxels.get(x, y)) cells.emplace_back(x, y);
+    std::vector<double> out(ticks.size() * cells.size());
+    for (size_t j = 0; j < cells.size(); j++) {
+      const auto& f = functions_.get(cells[j].first, cells[j].second);
+      if (!f) throw std::invalid_argument("no time function for a voxel");
+      for (size_t k = 0; k < ticks.size(); k++) out[k * cells.size() + j] = (*f)(ticks[k]);
+    }
+    return out;
+  }
+
+ private:
+  Grid<Fn> functions_;
+};
+
+class PhaseSin : public Controller {  // controllers/PhaseSin.java:50-66
+ public:
+  PhaseSin(double frequency, double amplitude, Grid<double> phases)
+      : frequency_(frequency), amplitude_(amplitude), phases_(std::move(phases)) {}
+  int kind() const override { return VSR_CTRL_PHASE_SIN; }
+  std::vector<double> params(const Grid<Voxel>& voxels, const std::vector<double>&) const override {
+    std::vector<double> p = {frequency_, amplitude_};
+    for (int y = 0; y < voxels.getH(); y++)
+      for (int x = 0; x < voxels.getW(); x++)
+        if (voxels.get(x, y)) {
+          if (!phases_.get(x, y)) throw std::invalid_argument("no phase for a voxel");
+          p.push_back(*phases_.get(x, y));
+        }
+    return p;
+  }
+
+ private:
+  double frequency_, amplitude_;
+  Grid<double> phases_;
+};
+
+class MultiLayerPerceptron {  // controllers/MultiLayerPerceptron.java
+ public:
+  enum ActivationFunction { RELU = 0, SIGMOID, SIN, TANH, SIGN, IDENTITY };  // :89-95
+  MultiLayerPerceptron(ActivationFunction a, int nIn, std::vector<int> inner, int nOut, std::vector<double> weights)
+      : activation_(a), neurons_(countNeurons(nIn, inner, nOut)), weights_(std::move(weights)) {
+    if (int(weights_.size()) != countWeights(neurons_))  // :56-62
+      throw std::invalid_argument("Wrong number of weights: " + std::to_string(countWeights(neurons_)) + " expected, " +
+                                  std::to_string(weights_.size()) + " found");
+  }
+  static std::vector<int> countNeurons(int nIn, const std::vector<int>& inner, int nOut) {  // :97-104
+    std::vector<int> n = {nIn};
+    n.insert(n.end(), inner.begin(), inner.end());
+    n.push_back(nOut);
+    return n;
+  }
+  static int countWeights(const std::vector<int>& n) {  // :106-112
+    int c = 0;
+    for (size_t i = 1; i < n.size(); i++) c += n[i] * (n[i - 1] + 1);
+    return c;
+  }
+  // flat <-> [layer][neuron][bias, w...] (:139-166)
+  static std::vector<std::vector<std::vector<double>>> unflat(const std::vector<double>& flat, const std::vector<int>& n) {
+    std::vector<std::vector<std::vector<double>>> u(n.size() - 1);
+    size_t c = 0;
+    for (size_t i = 1; i < n.size(); i++) {
+      u[i - 1].assign(n[i], std::vector<double>(n[i - 1] + 1));
+      for (int j = 0; j < n[i]; j++)
+        for (int k = 0; k < n[i - 1] + 1; k++) u[i - 1][j][k] = flat[c++];
+    }
+    return u;
+  }
+  static std::vector<double> flat(const std::vector<std::vector<std::vector<double>>>& u, const std::vector<int>& n) {
+    std::vector<double> f;
+    for (size_t i = 1; i < n.size(); i++)
+      for (int j = 0; j < n[i]; j++)
+        for (int k = 0; k < n[i - 1] + 1; k++) f.push_back(u[i - 1][j][k]);
+    return f;
+  }
+  // MultiLayerPerceptron.apply (:168-189), host-side evaluation of the description (the batched
+  // episode evaluates the same function on the device): activation on the inputs too, bias first.
+  std::vector<double> apply(const std::vector<double>& input) const {
+    if (int(input.size()) != neurons_[0])
+      throw std::invalid_argument("Expected input length is " + std::to_string(neurons_[0]) + ": found " + std::to_string(input.size()));
+    std::vector<double> a(input.size());
+    for (size_t k = 0; k < input.size(); k++) a[k] = act(input[k]);
+    size_t c = 0;
+    for (size_t i = 1; i < neurons_.size(); i++) {
+      std::vector<double> b(neurons_[i]);
+      for (int j = 0; j < neurons_[i]; j++) {
+        double sum = weights_[c++];
+        for (int k = 1; k < neurons_[i - 1] + 1; k++) sum = sum + a[k - 1] * weights_[c++];
+        b[j] = act(sum);
+      }
+      a.swap(b);
+    }
+    return a;
+  }
+  int getInputDimension() const { return neurons_.front(); }
+  int getOutputDimension() const { return neurons_.back(); }
+  const std::vector<int>& getNeurons() const { return neurons_; }
+  const std::vector<double>& getParams() const { return weights_; }
+  ActivationFunction getActivation() const { return activation_; }
+
+ private:
+  double act(double x) const {
+    switch (activation_) {
+      case RELU: return x < 0 ? 0.0 : x;
+      case SIGMOID: return 1.0 / (1.0 + std::exp(-x));
+      case SIN: return std::sin(x);
+      case TANH: return std::tanh(x);
+      case SIGN: return x > 0 ? 1.0 : (x < 0 ? -1.0 : x);
+      default: return x;
+    }
+  }
+  ActivationFunction activation_;
+  std::vector<int> neurons_;
+  std::vector<double> weights_;
+};
+
+class CentralizedSensing : public Controller {  // controllers/CentralizedSensing.java:68-127
+ public:
+  CentralizedSensing(const Grid<Voxel>& voxels, MultiLayerPerceptron function)
+      : nOfInputs_(nOfInputs(voxels)), nOfOutputs_(nOfOutputs(voxels)), function_(std::move(function)) {
+    if (function_.getInputDimension() != nOfInputs_ || function_.getOutputDimension() != nOfOutputs_)  // :121-127
+      throw std::invalid_argument("Wrong dimension of input or output in provided function: R^" + std::to_string(nOfInputs_) + "->R^" +
+                                  std::to_string(nOfOutputs_) + " expected, R^" + std::to_string(function_.getInputDimension()) +
+                                  "->R^" + std::to_string(function_.getOutputDimension()) + " found");
+  }
+  static int nOfInputs(const Grid<Voxel>& voxels) {
+    int n = 0;
+    for (auto& v : voxels.values())
+      if (v)
+        for (auto& s : v->getSensors()) n += int(s->getDomains().size());
+    return n;
+  }
+  static int nOfOutputs(const Grid<Voxel>& voxels) { return int(voxels.count()); }
+  int kind() const override { return VSR_CTRL_MLP; }
+  std::vector<double> params(const Grid<Voxel>&, const std::vector<double>&) const override { return function_.getParams(); }
+  const MultiLayerPerceptron& getFunction() const { return function_; }
+
+ private:
+  int nOfInputs_, nOfOutputs_;
+  MultiLayerPerceptron function_;
+};
+
+class Robot {  // core/objects/Robot.java:57-64
+ public:
+  Robot(ControllerPtr controller, Grid<Voxel> voxels) : controller_(std::move(controller)), voxels_(std::move(voxels)) {}
+  const Controller& getController() const { return *controller_; }
+  const Grid<Voxel>& getVoxels() const { return voxels_; }
+
+ private:
+  ControllerPtr controller_;
+  Grid<Voxel> voxels_;
+};
+
+// ---------------------------------------------------------------- RobotUtils
+namespace RobotUtils {
+inline bool match(const std::string& pattern, const std::string& s, std::smatch& m) {  // util/Utils.java:147-164
+  return std::regex_match(s, m, std::regex(pattern));
+}
+inline Grid<bool> buildShape(const std::string& name) {  // util/RobotUtils.java:198-242
+  std::smatch m;
+  auto grid = [](int w, int h, const std::function<bool(int, int)>& f) {
+    return Grid<bool>::create(w, h, [&](int x, int y) { return std::optional<bool>(f(x, y)); });
+  };
+  if (match(R"((box|worm)-(\d+)x(\d+))", name, m)) return grid(std::stoi(m[2]), std::stoi(m[3]), [](int, int) { return true; });
+  if (match(R"(biped-(\d+)x(\d+))", name, m)) {
+    int w = std::stoi(m[1]), h = std::stoi(m[2]);
+    return grid(w, h, [=](int x, int y) { return !(y < h / 2 && x >= w / 4 && x < w * 3 / 4); });
+  }
+  if (match(R"(tripod-(\d+)x(\d+))", name, m)) {
+    int w = std::stoi(m[1]), h = std::stoi(m[2]);
+    return grid(w, h, [=](int x, int y) { return !(y < h / 2 && x != 0 && x != w - 1 && x != w / 2); });
+  }
+  if (match(R"(ball-(\d+))", name, m)) {
+    int d = std::stoi(m[1]);
+    double c = (d - 1) / 2.0;
+    return grid(d, d, [=](int x, int y) {
+      return std::floor(std::sqrt((x - c) * (x - c) + (y - c) * (y - c)) + 0.5) <= std::floor(d / 2.0);
+    });
+  }
+  if (match(R"(comb-(\d+)x(\d+))", name, m)) {
+    int w = std::stoi(m[1]), h = std::stoi(m[2]);
+    return grid(w, h, [=](int x, int y) { return y >= h / 2 || x % 2 == 0; });
+  }
+  if (match(R"(t-(\d+)x(\d+))", name, m)) {
+    int w = std::stoi(m[1]), h = std::stoi(m[2]);
+    int pad = int(std::floor(std::floor(w / 2.0) / 2.0));
+    return grid(w, h, [=](int x, int y) { return y == 0 || (x >= pad && x < h - pad - 1); });
+  }
+  throw std::invalid_argument("Unknown body name: " + name);
+}
+inline SensorPtr sensor(const std::string& n) {  // PREDEFINED_SENSORS, :38-53 (hot-path subset)
+  auto vel = [](double m, int axes) { return std::make_shared<Velocity>(true, m, axes); };
+  if (n == "t") return std::make_shared<Average>(std::make_shared<Touch>(), 0.25);
+  if (n == "a") return std::make_shared<SoftNormalization>(std::make_shared<AreaRatio>());
+  if (n == "vx") return std::make_shared<SoftNormalization>(std::make_shared<Average>(vel(8, Velocity::X), 0.5));
+  if (n == "vy") return std::make_shared<SoftNormalization>(std::make_shared<Average>(vel(8, Velocity::Y), 0.5));
+  if (n == "vxy") return std::make_shared<SoftNormalization>(std::make_shared<Average>(vel(8, Velocity::X | Velocity::Y), 0.5));
+  if (n == "ax") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::X), 0.5));
+  if (n == "ay") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::Y), 0.5));
+  if (n == "axy") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::X | Velocity::Y), 0.5));
+  for (const char* o : {"r", "px", "py", "m", "cpg", "l5", "l1"})
+    if (n == o) throw Unsupported("sensor '" + n + "' is outside the accelerated hot path");
+  throw std::invalid_argument("Unknown sensor name: " + n);
+}
+inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(const std::string& name) {  // :124-196
+  std::smatch m;
+  const std::string keys = "a|ax|axy|ay|cpg|l1|l5|m|px|py|r|t|vx|vxy|vy";
+  if (match("uniform-((" + keys + ")(\\+(" + keys + "))*)-(\\d+(\\.\\d+)?)", name, m)) {
+    if (std::stod(m[5]) != 0) throw Unsupported("Noisy sensors are outside the accelerated hot path");
+    std::vector<std::string> names;
+    std::string list = m[1], cur;
+    for (char c : list + "+") {
+      if (c == '+') {
+        names.push_back(cur);
+        cur.clear();
+      } else cur += c;
+    }
+    return [names](const Grid<bool>& body) {
+      return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
+        if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
+        std::vector<SensorPtr> ss;
+        for (auto& n : names) ss.push_back(sensor(n));
+        return Voxel(ss);
+      });
+    };
+  }
+  if (name == "empty")
+    return [](const Grid<bool>& body) {
+      return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
+        if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
+        return Voxel({});
+      });
+    };
+  for (const char* o : {"spinedTouch-", "spinedTouchSighted-", "uniformAll-"})
+    if (name.rfind(o, 0) == 0) throw Unsupported("sensorizing function '" + name + "' is outside the accelerated hot path");
+  throw std::invalid_argument("Unknown sensorizing function name: " + name);
+}
+}  // namespace RobotUtils
+
+// ---------------------------------------------------------------- Settings / Outcome
+class Settings {  // org.dyn4j.dynamics.Settings as a value holder (Locomotion.java:50)
+ public:
+  Settings() {
+    s_ = vsr_settings{};
+    s_.step_frequency = 1.0 / 60.0; s_.velocity_iterations = 10; s_.position_iterations = 10;
+    s_.linear_tolerance = 0.005; s_.angular_tolerance = 2.0 * M_PI / 180.0; s_.max_linear_correction = 0.2;
+    s_.baumgarte = 0.2; s_.restitution_velocity = 1.0; s_.max_translation = 2.0; s_.max_rotation = 0.5 * M_PI;
+    s_.gravity_x = 0.0; s_.gravity_y = -9.8; s_.ground_friction = 0.2; s_.ground_restitution = 0.0;
+    s_.spring_mass_mode = VSR_SPRING_MASS_REDUCED;
+  }
+  double getStepFrequency() const { return s_.step_frequency; }
+  vsr_settings& raw() { return s_; }
+  const vsr_settings& raw() const { return s_; }
+
+ private:
+  vsr_settings s_;
+};
+
+class Outcome {  // tasks/locomotion/Outcome.java (first + last Observation)
+ public:
+  explicit Outcome(const vsr_result& r) : r_(r) {}
+  double getDistance() const { return r_.last_center_x - r_.first_center_x; }          // :152-166
+  double getTime() const { return r_.t_last - r_.t_first; }                              // :194-196
+  double getVelocity() const { return getDistance() / getTime(); }                       // :198-200
+  double getAreaRatioEnergy() const { return r_.area_ratio_energy_last - r_.area_ratio_energy_first; }  // :42-58
+  double getControlEnergy() const { return r_.control_energy_last - r_.control_energy_first; }          // :126-142
+  double getControlPower() const { return getControlEnergy() / getTime(); }
+  double getAreaRatioPower() const { return getAreaRatioEnergy() / getTime(); }
+  double getCorrectedEfficiency() const { return getDistance() / (1.0 + getControlPower() * getTime()); }  // :148-150
+  const vsr_result& record() const { return r_; }
+
+ private:
+  vsr_result r_;
+};
+
+// ---------------------------------------------------------------- flattening
+struct BatchDesc {  // owns the flat arrays behind a vsr_batch_desc
+  vsr_batch_desc desc{};
+  std::vector<vsr_shape> shapes;
+  std::vector<std::vector<uint8_t>> masks;
+  std::vector<std::vector<int32_t>> sensorOffsets, hidden;
+  std::vector<std::vector<vsr_sensor>> sensors;
+  std::vector<int32_t> robotShape;
+  std::vector<double> params, xs, ys;
+  std::vector<size_t> paramOffsets;
+  std::vector<int> nVoxels;
+  int nTicks = 0;
+};
+
+inline bool sameSensor(const vsr_sensor& a, const vsr_sensor& b) {
+  return a.base == b.base && a.axes == b.axes && a.rotated == b.rotated && a.aggregator == b.aggregator &&
+         a.soft_norm == b.soft_norm && a.max_velocity_norm == b.max_velocity_norm && a.interval == b.interval;
+}
+
+class Locomotion {  // tasks/locomotion/Locomotion.java
+ public:
+  static constexpr double TERRAIN_BORDER_HEIGHT = 100, TERRAIN_BORDER_WIDTH = 10;
+  static constexpr int TERRAIN_LENGTH = 2000;
+  using Profile = std::pair<std::vector<double>, std::vector<double>>;
+
+  Locomotion(double finalT, Profile groundProfile, Settings settings)
+      : Locomotion(finalT, groundProfile, std::numeric_limits<double>::quiet_NaN(), settings) {}
+  Locomotion(double finalT, Profile groundProfile, double initialPlacement, Settings settings)
+      : finalT_(finalT), profile_(std::move(groundProfile)), settings_(settings) {
+    auto& xs = profile_.first;
+    if (xs.size() != profile_.second.size()) throw std::invalid_argument("xs[] and ys[] must have the same length");  // Ground.java:49-51
+    if (xs.size() < 2) throw std::invalid_argument("There must be at least 2 points");                                // :52-54
+    for (size_t i = 1; i < xs.size(); i++)
+      if (xs[i] < xs[i - 1]) throw std::invalid_argument("x coordinates must be sorted");                            // :55-58
+    initialPlacement_ = std::isnan(initialPlacement) ? xs[1] + 1.0 : initialPlacement;                               // Locomotion.java:50-52
+  }
+
+  static Profile createTerrain(const std::string& name) {  // :61-146
+    const double L = TERRAIN_LENGTH, BW = TERRAIN_BORDER_WIDTH, BH = TERRAIN_BORDER_HEIGHT;
+    const std::string num = R"([0-9]+(\.[0-9]+)?)";
+    std::smatch m;
+    if (name == "flat") return {{0, BW, L - BW, L}, {BH, 5, 5, BH}};
+    if (RobotUtils::match("flatWithStart-([0-9]+)", name, m)) {
+      JavaRandom rnd(std::stoll(m[1]));
+      int n = rnd.nextInt(10) + 10;
+      for (int i = 0; i < n; i++) rnd.nextDouble();
+      double angle = M_PI / 18.0 * (rnd.nextDouble() * 2.0 - 1.0);
+      double start = Voxel::SIDE_LENGTH * 8.0;
+      return {{0, BW, BW + start, L - BW, L}, {BH, 5 + start * std::sin(angle), 5, 5, BH}};
+    }
+    bool hilly = RobotUtils::match("hilly-(" + num + ")-(" + num + ")-([0-9]+)", name, m);
+    bool steppy = !hilly && RobotUtils::match("steppy-(" + num + ")-(" + num + ")-([0-9]+)", name, m);
+    if (hilly || steppy) {
+      double h = std::stod(m[1]), w = std::stod(m[3]);
+      JavaRandom rnd(std::stoll(m[5]));
+      std::vector<double> xs = {0, BW}, ys = {BH, 0};
+      while (xs.back() < L - BW) {
+        xs.push_back(xs.back() + std::max(1.0, (rnd.nextGaussian() * 0.25 + 1) * w));
+        if (steppy) {
+          xs.push_back(xs.back() + 0.5);
+          ys.push_back(ys.back());
+        }
+        ys.push_back(ys.back() + rnd.nextGaussian() * h);
+      }
+      xs.push_back(xs.back() + BW);
+      ys.push_back(BH);
+      return {xs, ys};
+    }
+    if (RobotUtils::match("downhill-(" + num + ")", name, m)) {
+      double dY = (L - 2 * BW) * std::sin(std::stod(m[1]) / 180 * M_PI);
+      return {{0, BW, L - BW, L}, {BH + dY, 5 + dY, 5, BH}};
+    }
+    if (RobotUtils::match("uphill-(" + num + ")", name, m)) {
+      double dY = (L - 2 * BW) * std::sin(std::stod(m[1]) / 180 * M_PI);
+      return {{0, BW, L - BW, L}, {BH, 5, 5 + dY, BH + dY}};
+    }
+    throw std::invalid_argument("Unknown terrain name: " + name);
+  }
+
+  // Flatten robots + this task into a vsr_batch_desc (what the Java side would hand over).
+  std::unique_ptr<BatchDesc> compile(const std::vector<Robot>& robots, uint32_t precision = VSR_PRECISION_F32,
+                                     size_t trajectoryRobots = 0) const {
+    if (robots.empty()) throw std::invalid_argument("empty batch");
+    auto b = std::make_unique<BatchDesc>();
+    vsr_batch_desc& d = b->desc;
+    d.abi_version = VSR_ABI_VERSION;
+    d.precision = precision;
+    d.n_robots = robots.size();
+    d.controller_kind = robots[0].getController().kind();
+    d.settings = settings_.raw();
+    d.final_t = finalT_;
+    b->xs = profile_.first;
+    b->ys = profile_.second;
+    d.initial_placement = initialPlacement_;
+    d.trajectory_robots = trajectoryRobots;
+    std::vector<double> ticks = tickTimes(finalT_, d.settings.step_frequency);
+    b->nTicks = int(ticks.size());
+    b->paramOffsets.push_back(0);
+    bool haveMaterial = false;
+    for (const Robot& r : robots) {
+      if (r.getController().kind() != d.controller_kind) throw std::invalid_argument("one controller kind per batch");
+      const Grid<Voxel>& vox = r.getVoxels();
+      std::vector<uint8_t> mask;
+      std::vector<int32_t> offs = {0}, hid;
+      std::vector<vsr_sensor> sens;
+      for (auto& v : vox.values()) {
+        mask.push_back(v ? 1 : 0);
+        if (!v) continue;
+        for (auto& s : v->getSensors()) sens.push_back(s->encode());
+        offs.push_back(int32_t(sens.size()));
+        if (!haveMaterial) {
+          d.material = v->material();
+          haveMaterial = true;
+        } else if (std::memcmp(&d.material, &v->material(), sizeof(vsr_material)) != 0) {
+          throw Unsupported("one voxel material per batch on the accelerated path");
+        }
+      }
+      if (d.controller_kind == VSR_CTRL_MLP) {
+        auto& f = static_cast<const CentralizedSensing&>(r.getController()).getFunction();
+        hid.assign(f.getNeurons().begin() + 1, f.getNeurons().end() - 1);
+        d.mlp_activation = int(f.getActivation());
+      }
+      // find or add the shape class
+      int cls = -1;
+      for (size_t k = 0; k < b->masks.size() && cls < 0; k++) {
+        if (b->shapes[k].w != vox.getW() || b->shapes[k].h != vox.getH() || b->masks[k] != mask || b->sensorOffsets[k] != offs ||
+            b->hidden[k] != hid || b->sensors[k].size() != sens.size())
+          continue;
+        bool same = true;
+        for (size_t q = 0; q < sens.size() && same; q++) same = sameSensor(sens[q], b->sensors[k][q]);
+        if (same) cls = int(k);
+      }
+      if (cls < 0) {
+        cls = int(b->masks.size());
+        vsr_shape sh{};
+        sh.w = vox.getW();
+        sh.h = vox.getH();
+        b->shapes.push_back(sh);
+        b->masks.push_back(mask);
+        b->sensorOffsets.push_back(offs);
+        b->sensors.push_back(sens);
+        b->hidden.push_back(hid);
+        b->nVoxels.push_back(int(offs.size()) - 1);
+      }
+      b->robotShape.push_back(cls);
+      std::vector<double> p = r.getController().params(vox, ticks);
+      b->params.insert(b->params.end(), p.begin(), p.end());
+      b->paramOffsets.push_back(b->params.size());
+    }
+    if (!haveMaterial) throw std::invalid_argument("robot without voxels");
+    for (size_t k = 0; k < b->shapes.size(); k++) {  // pointers only once the vectors stopped growing
+      b->shapes[k].mask = b->masks[k].data();
+      b->shapes[k].sensor_offsets = b->sensorOffsets[k].data();
+      b->shapes[k].sensors = b->sensors[k].data();
+      b->shapes[k].n_hidden = int32_t(b->hidden[k].size());
+      b->shapes[k].hidden = b->hidden[k].data();
+    }
+    d.shapes = b->shapes.data();
+    d.n_shapes = int32_t(b->shapes.size());
+    d.robot_shape = b->robotShape.data();
+    d.params = b->params.data();
+    d.param_offsets = b->paramOffsets.data();
+    d.terrain_xs = b->xs.data();
+    d.terrain_ys = b->ys.data();
+    d.terrain_n = int32_t(b->xs.size());
+    return b;
+  }
+
+  // The batch entry the reference lacks: List<Outcome> apply(List<Robot>).  One kernel launch.
+  std::vector<Outcome> apply(const std::vector<Robot>& robots, int device = 0) const {
+    auto bd = compile(robots);
+    vsr_batch* h = nullptr;
+    check(vsr_batch_create(&bd->desc, &h));
+    struct Guard {
+      vsr_batch* h;
+      ~Guard() { vsr_batch_destroy(h); }
+    } guard{h};
+    check(vsr_batch_upload(h, device, nullptr));
+    check(vsr_batch_run(h, nullptr));
+    std::vector<vsr_result> res(robots.size());
+    check(vsr_batch_results(h, res.data(), res.size()));
+    std::vector<Outcome> out;
+    for (auto& r : res) out.emplace_back(r);
+    return out;
+  }
+  Outcome apply(const Robot& robot, int device = 0) const { return apply(std::vector<Robot>{robot}, device)[0]; }  // :168-207
+
+ private:
+  static void check(int rc) {
+    if (rc == VSR_OK) return;
+    std::string msg = vsr_last_error();
+    if (rc == VSR_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    if (rc == VSR_ERR_UNSUPPORTED) throw Unsupported(msg);
+    throw std::runtime_error("vsr error " + std::to_string(rc) + ": " + msg);
+  }
+  double finalT_;
+  Profile profile_;
+  double initialPlacement_;
+  Settings settings_;
+};
+
+}  // namespace hmsrobots

@@ -1,0 +1,82 @@
+"""The C++ host mirror (2dhmsr_b200/host/hmsrobots.hpp) against the reference's vectors, the Python
+mirror (two independent implementations of RobotUtils / createTerrain / java.util.Random) and,
+on a GPU, against the Python path through the same C ABI."""
+import importlib
+import json
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+H = importlib.import_module("2dhmsr_b200")
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "2dhmsr_b200", "host", "host_check")
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def _run(mode):
+    out = subprocess.run([EXE, mode], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return json.loads(out.stdout)
+
+
+def test_cpp_host_mirror_selfcheck():
+    j = _run("selfcheck")
+    g = GOLD["survey_java_random"]
+    assert j["seed0_nextDouble"] == g["seed0_nextDouble"] and j["seed0_nextInt"] == g["seed0_nextInt"]
+    assert j["seed42_nextInt"] == g["seed42_nextInt"]
+    assert j["seed0_nextGaussian"] == pytest.approx(g["seed0_nextGaussian"], abs=1e-15)
+    # terrain DSL: identical to the Python mirror (independent implementation) and to the SURVEY points
+    for name, kx, ky in (("hilly-1-10-0", "hilly_xs", "hilly_ys"), ("steppy-2-8-3", "steppy_xs", "steppy_ys")):
+        t = H.Locomotion.create_terrain(name)
+        assert np.allclose(j[kx], t[0], rtol=0, atol=1e-12) and np.allclose(j[ky], t[1], rtol=0, atol=1e-12)
+    assert len(j["hilly_xs"]) == GOLD["survey_hilly_1_10_0"]["n_points"]
+    assert np.allclose(j["flatWithStart_ys"], H.Locomotion.create_terrain("flatWithStart-2")[1], atol=1e-12)
+    assert np.allclose(j["uphill_ys"], H.Locomotion.create_terrain("uphill-10")[1], atol=1e-12)
+    for name, m in j["shapes"].items():
+        ref = "".join("1" if v else "0" for v in H.RobotUtils.build_shape(name).values())
+        assert m == ref, name
+    # MultiLayerPerceptronTest.java:50-95
+    assert j["mlp_apply"] == GOLD["reference_mlp_apply"]["output"]
+    assert j["mlp_unflat_layer0_neuron1"] == GOLD["reference_mlp_flat"]["unflat"][0][1]
+    assert j["mlp_flat"] == GOLD["reference_mlp_flat"]["flat"] and j["count_weights"] == 1507
+    assert j["n_ticks"] == 1200 and j["last_tick"] == GOLD["survey_ticks"]["last"]
+    # descriptors equal the Python mirror's
+    bd = helpers.locomotion().compile([helpers.config1_robot()])
+    assert j["cfg1_kind"] == bd.desc.controller_kind and j["cfg1_n_params"] == 12000
+    sig = np.ctypeslib.as_array(bd.desc.params, shape=(12000,))
+    assert j["cfg1_param_5_1"] == sig[51] and j["cfg1_initial_placement"] == 11.0
+    enc = []
+    for i in range(bd.desc.shapes[0].sensor_offsets[10]):
+        s = bd.desc.shapes[0].sensors[i]
+        enc += [s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval]
+    assert j["cfg1_sensors"] == enc
+    assert j["phase_n_shapes"] == 1 and len(j["phase_params"]) == 3 * 12
+    assert j["phase_params"][:4] == [1.0, 1.0, 0.1, 0.1 + 0.7 * 3]  # voxel order (0,0), (3,0), ...
+    assert j["worm_inputs"] == 64
+    # error behaviour: IllegalArgumentException -> std::invalid_argument, same messages
+    assert j["err_terrain"] == "invalid_argument:Unknown terrain name: moon"
+    assert j["err_shape"] == "invalid_argument:Unknown body name: snake-3"
+    assert j["err_sensors"].startswith("invalid_argument:Unknown sensorizing function name")
+    assert j["err_lidar"].startswith("Unsupported:")
+    assert j["err_weights"] == "invalid_argument:Wrong number of weights: 11 expected, 5 found"
+    assert j["err_dims"].startswith("invalid_argument:Wrong dimension of input or output")
+    assert j["err_ground"] == "invalid_argument:x coordinates must be sorted"
+    assert j["err_range"].startswith("invalid_argument:Max has to be lower")
+
+
+@pytest.mark.gpu
+def test_cpp_locomotion_apply_equals_python_path():
+    j = _run("run")
+    o = helpers.locomotion().apply(helpers.config1_robot())
+    assert j["cfg1"]["distance"] == o.get_distance() and j["cfg1"]["velocity"] == o.get_velocity()
+    assert j["cfg1"]["time"] == pytest.approx(20 - 1 / 60, abs=1e-9)
+    body = helpers.body_of("biped-4x3")
+    robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(4, 3, lambda x, y, b=b: b + 0.7 * x + 0.3 * y)), body)
+              for b in (0.1, 0.2, 0.3)]
+    outs = helpers.locomotion().apply(robots)
+    assert j["phase_distance"] == [o.get_distance() for o in outs]
