@@ -457,64 +457,101 @@ __device__ __noinline__ BodyState<real> contact_init_mass(const CPar<real> P, Bo
 }
 
 // SequentialImpulses.solveVelocityConstraints (dyn4j) for the constraints of one mass.
+// Runs 10x per tick on a few lanes, i.e. latency bound: every field is loaded up front (the
+// loads are independent; interleaved with the stores to the same struct the compiler would
+// have to serialise them), then the arithmetic chain, then the two or four stores.
 template <typename real>
 __device__ __noinline__ BodyState<real> contact_solve_mass(const CPar<real> P, BodyState<real> B, CBody<real>& cb) {
   const real im = P.im, ii = P.ii;
-  for (int q = 0; q < cb.n; q++) {
+  const int ncon = cb.n;
+  for (int q = 0; q < ncon; q++) {
     CCon<real>& c = cb.c[q];
-    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-    for (int k = 0; k < c.n; k++) {
-      CPoint<real>& p = c.p[k];
-      real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+    // ---- loads
+    const int cn = c.n, blk = c.block;
+    const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+    const real r1x0 = c.p[0].r1x, r1y0 = c.p[0].r1y, mN0 = c.p[0].massN, mT0 = c.p[0].massT, vb0 = c.p[0].vb;
+    real jn0 = c.p[0].jn, jt0 = c.p[0].jt;
+    // the second point is read unconditionally (its slot exists; unused values are ignored)
+    const real r1x1 = c.p[1].r1x, r1y1 = c.p[1].r1y, mN1 = c.p[1].massN, mT1 = c.p[1].massT, vb1 = c.p[1].vb;
+    real jn1 = c.p[1].jn, jt1 = c.p[1].jt;
+    const real K00 = c.K00, K01 = c.K01, K11 = c.K11, iK00 = c.iK00, iK01 = c.iK01, iK11 = c.iK11;
+    const bool two = cn == 2;
+    // ---- friction of every point first
+    {
+      real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
       real tn = tx * rvx + ty * rvy;
-      real jt = p.massT * (-tn);
-      real maxJt = P.mu * p.jn;
-      real Jt0 = p.jt;
-      p.jt = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
-      jt = p.jt - Jt0;
+      real jt = mT0 * (-tn);
+      real maxJt = P.mu * jn0;
+      real Jt0 = jt0;
+      jt0 = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
+      jt = jt0 - Jt0;
       real Px = tx * jt, Py = ty * jt;
       B.vx -= im * Px;
       B.vy -= im * Py;
-      B.w -= ii * (p.r1x * Py - p.r1y * Px);
+      B.w -= ii * (r1x0 * Py - r1y0 * Px);
     }
-    if (c.n == 1 || !c.block) {
-      for (int k = 0; k < c.n; k++) {
-        CPoint<real>& p = c.p[k];
-        real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+    if (two) {
+      real rvx = -(B.vx - B.w * r1y1), rvy = -(B.vy + B.w * r1x1);
+      real tn = tx * rvx + ty * rvy;
+      real jt = mT1 * (-tn);
+      real maxJt = P.mu * jn1;
+      real Jt0 = jt1;
+      jt1 = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
+      jt = jt1 - Jt0;
+      real Px = tx * jt, Py = ty * jt;
+      B.vx -= im * Px;
+      B.vy -= im * Py;
+      B.w -= ii * (r1x1 * Py - r1y1 * Px);
+    }
+    // ---- then the normal constraint(s)
+    if (!two || !blk) {
+      {
+        real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
         real rvn = nx * rvx + ny * rvy;
-        real j = -p.massN * (rvn - p.vb);
-        real j0 = p.jn;
-        p.jn = r_max(j0 + j, real(0));
-        j = p.jn - j0;
+        real j = -mN0 * (rvn - vb0);
+        real j0 = jn0;
+        jn0 = r_max(j0 + j, real(0));
+        j = jn0 - j0;
         real Px = nx * j, Py = ny * j;
         B.vx -= im * Px;
         B.vy -= im * Py;
-        B.w -= ii * (p.r1x * Py - p.r1y * Px);
+        B.w -= ii * (r1x0 * Py - r1y0 * Px);
+      }
+      if (two) {
+        real rvx = -(B.vx - B.w * r1y1), rvy = -(B.vy + B.w * r1x1);
+        real rvn = nx * rvx + ny * rvy;
+        real j = -mN1 * (rvn - vb1);
+        real j0 = jn1;
+        jn1 = r_max(j0 + j, real(0));
+        j = jn1 - j0;
+        real Px = nx * j, Py = ny * j;
+        B.vx -= im * Px;
+        B.vy -= im * Py;
+        B.w -= ii * (r1x1 * Py - r1y1 * Px);
       }
     } else {
-      CPoint<real>& p1 = c.p[0];
-      CPoint<real>& p2 = c.p[1];
-      real ax = p1.jn, ay = p2.jn;
-      real rvx = -(B.vx - B.w * p1.r1y), rvy = -(B.vy + B.w * p1.r1x);
+      // 2-point block solver (the Box2D / dyn4j LCP enumeration)
+      real ax = jn0, ay = jn1;
+      real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
       real rvn1 = nx * rvx + ny * rvy;
-      rvx = -(B.vx - B.w * p2.r1y);
-      rvy = -(B.vy + B.w * p2.r1x);
+      rvx = -(B.vx - B.w * r1y1);
+      rvy = -(B.vy + B.w * r1x1);
       real rvn2 = nx * rvx + ny * rvy;
-      real bx = rvn1 - p1.vb, by = rvn2 - p2.vb;
-      bx -= c.K00 * ax + c.K01 * ay;
-      by -= c.K01 * ax + c.K11 * ay;
-      real x = -(c.iK00 * bx + c.iK01 * by), y = -(c.iK01 * bx + c.iK11 * by);
+      real bx = rvn1 - vb0, by = rvn2 - vb1;
+      bx -= K00 * ax + K01 * ay;
+      by -= K01 * ax + K11 * ay;
+      real x = -(iK00 * bx + iK01 * by), y = -(iK01 * bx + iK11 * by);
       bool ok = (x >= real(0) && y >= real(0));
       if (!ok) {
-        x = -p1.massN * bx;
+        x = -mN0 * bx;
         y = real(0);
-        real v2 = c.K01 * x + by;
+        real v2 = K01 * x + by;
         ok = (x >= real(0) && v2 >= real(0));
       }
       if (!ok) {
         x = real(0);
-        y = -p2.massN * by;
-        real v1 = c.K01 * y + bx;
+        y = -mN1 * by;
+        real v1 = K01 * y + bx;
         ok = (y >= real(0) && v1 >= real(0));
       }
       if (!ok) {
@@ -527,15 +564,22 @@ __device__ __noinline__ BodyState<real> contact_solve_mass(const CPar<real> P, B
         real Px = nx * dx, Py = ny * dx;
         B.vx -= im * Px;
         B.vy -= im * Py;
-        B.w -= ii * (p1.r1x * Py - p1.r1y * Px);
+        B.w -= ii * (r1x0 * Py - r1y0 * Px);
         Px = nx * dy;
         Py = ny * dy;
         B.vx -= im * Px;
         B.vy -= im * Py;
-        B.w -= ii * (p2.r1x * Py - p2.r1y * Px);
-        p1.jn = x;
-        p2.jn = y;
+        B.w -= ii * (r1x1 * Py - r1y1 * Px);
+        jn0 = x;
+        jn1 = y;
       }
+    }
+    // ---- stores
+    c.p[0].jn = jn0;
+    c.p[0].jt = jt0;
+    if (two) {
+      c.p[1].jn = jn1;
+      c.p[1].jt = jt1;
     }
   }
   return B;
