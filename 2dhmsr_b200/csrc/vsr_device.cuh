@@ -618,27 +618,30 @@ __device__ __noinline__ BodyState<real> contact_position_mass(const CPar<real> P
 }
 
 // ---------------------------------------------------------------- springs
-// The 18 DistanceJoints of a voxel in `allSpringJoints` order (Voxel.java:303-470):
-// X(index, body1, body2, anchor1 sign x,y, anchor2 sign x,y, range class)
-#define VSR_SPRINGS(X)               \
-  X(0, 0, 1, +1, -1, -1, -1, 0)      \
-  X(1, 1, 2, -1, -1, -1, +1, 0)      \
-  X(2, 2, 3, -1, +1, +1, +1, 0)      \
-  X(3, 3, 0, +1, +1, +1, -1, 0)      \
-  X(4, 0, 1, +1, +1, -1, +1, 0)      \
-  X(5, 1, 2, +1, -1, +1, +1, 0)      \
-  X(6, 2, 3, -1, -1, +1, -1, 0)      \
-  X(7, 3, 0, -1, +1, -1, -1, 0)      \
-  X(8, 0, 1, +1, +1, -1, -1, 1)      \
-  X(9, 0, 1, +1, -1, -1, +1, 1)      \
-  X(10, 1, 2, +1, -1, -1, +1, 1)     \
-  X(11, 1, 2, -1, -1, +1, +1, 1)     \
-  X(12, 2, 3, -1, +1, +1, -1, 1)     \
-  X(13, 2, 3, -1, -1, +1, +1, 1)     \
-  X(14, 3, 0, -1, +1, +1, -1, 1)     \
-  X(15, 3, 0, +1, +1, -1, -1, 1)     \
-  X(16, 0, 2, 0, 0, 0, 0, 2)         \
-  X(17, 1, 3, 0, 0, 0, 0, 2)
+// The 18 DistanceJoints of a voxel, indices as in `allSpringJoints` (Voxel.java:303-470).
+// Listed in the canonical SOLVE order: inside a voxel the sweep alternates the perfect matchings
+// of K4 ({01,23}, {12,30}, {02,13}) so that consecutive solves touch disjoint masses (two
+// independent dependency chains); `nxt` is the index of the spring solved next (prefetch).
+// X(index, nxt, body1, body2, anchor1 sign x,y, anchor2 sign x,y, range class)
+#define VSR_SPRINGS(X)                  \
+  X(0, 2, 0, 1, +1, -1, -1, -1, 0)      \
+  X(2, 1, 2, 3, -1, +1, +1, +1, 0)      \
+  X(1, 3, 1, 2, -1, -1, -1, +1, 0)      \
+  X(3, 4, 3, 0, +1, +1, +1, -1, 0)      \
+  X(4, 6, 0, 1, +1, +1, -1, +1, 0)      \
+  X(6, 5, 2, 3, -1, -1, +1, -1, 0)      \
+  X(5, 7, 1, 2, +1, -1, +1, +1, 0)      \
+  X(7, 8, 3, 0, -1, +1, -1, -1, 0)      \
+  X(8, 12, 0, 1, +1, +1, -1, -1, 1)     \
+  X(12, 9, 2, 3, -1, +1, +1, -1, 1)     \
+  X(9, 13, 0, 1, +1, -1, -1, +1, 1)     \
+  X(13, 10, 2, 3, -1, -1, +1, +1, 1)    \
+  X(10, 14, 1, 2, +1, -1, -1, +1, 1)    \
+  X(14, 11, 3, 0, -1, +1, +1, -1, 1)    \
+  X(11, 15, 1, 2, -1, -1, +1, +1, 1)    \
+  X(15, 16, 3, 0, +1, +1, -1, -1, 1)    \
+  X(16, 17, 0, 2, 0, 0, 0, 0, 2)        \
+  X(17, 0, 1, 3, 0, 0, 0, 0, 2)
 
 template <typename real>
 __device__ __forceinline__ real activation(int a, real x) {
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
       // (softMass, bias) as one 2-vector per spring and thread ([spring][thread]: a warp reads
       // consecutive 16- / 8-byte words, conflict-free).  That frees ~110 registers.
       const real sw = P.spring_w;
-#define VSR_SPRING_INIT(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                        \
+#define VSR_SPRING_INIT(s, nxt, b1, b2, a1x, a1y, a2x, a2y, cls)                                        \
   if (FULLSPR || (P.spring_mask & (1u << s))) {                                                    \
     real r1x = real(a1x) * ch[b1] - real(a1y) * sh[b1], r1y = real(a1x) * sh[b1] + real(a1y) * ch[b1]; \
     real r2x = real(a2x) * ch[b2] - real(a2y) * sh[b2], r2y = real(a2x) * sh[b2] + real(a2y) * ch[b2]; \
@@ -939,16 +942,16 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #pragma unroll 1
       for (int it = 0; it < P.vel_iters; it++) {
         if (sync_mode & 2) __syncthreads();
-#define VSR_SPRING_SOLVE(s, b1, b2, a1x, a1y, a2x, a2y, cls)                                          \
+#define VSR_SPRING_SOLVE(s, nxt, b1, b2, a1x, a1y, a2x, a2y, cls)                                          \
   /* software prefetch, one spring ahead (unconditional, so that an absent spring keeps the chain  \
      intact); the fences stop ptxas from hoisting all 36 loads to the top of the loop, which costs  \
      108 registers and spills them straight back to local memory */                                 \
   const R4 q##s = qn_;                                                                                \
   const R2 p##s = pn_;                                                                                \
   asm volatile("" ::: "memory");                                                                      \
-  if (s + 1 < 18) {                                                                                   \
-    qn_ = spr[(s + 1 < 18 ? s + 1 : 0) * SPR_STRIDE + tid];                                           \
-    pn_ = spr2[(s + 1 < 18 ? s + 1 : 0) * SPR_STRIDE + tid];                                          \
+  if (s != 17) {                                                                                      \
+    qn_ = spr[(nxt) * SPR_STRIDE + tid];                                                              \
+    pn_ = spr2[(nxt) * SPR_STRIDE + tid];                                                             \
   }                                                                                                   \
   asm volatile("" ::: "memory");                                                                      \
   if (FULLSPR || (P.spring_mask & (1u << s))) {                                                       \

@@ -136,6 +136,7 @@ typedef struct {
   double rest;               /* current rest distance (applyForce) */
   double imp;                /* accumulated impulse (warm start) */
   double nx, ny, cr1, cr2, gamma, bias, soft;
+  int full; /* index 0..17 in Voxel.allSpringJoints with all four scaffoldings */
 } OSpring;
 
 typedef struct {
@@ -169,6 +170,7 @@ typedef struct {
 
 typedef struct {
   int nv, nb, ns, nw;
+  int next_full;
   int* vox_gx;
   int* vox_gy;
   OBody* bodies;
@@ -249,6 +251,7 @@ static void add_spring(ORobot* r, int b1, int b2, double a1x, double a1y, double
   s->rrest = rrest;
   s->rmax = rmax;
   s->rest = rrest; /* Voxel.java:473 */
+  s->full = r->next_full++;
 }
 
 /* Robot.join, Robot.java:66-71: anchor = body1's centre (sic). */
@@ -321,18 +324,21 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
     }
     uint32_t sc = m->spring_scaffoldings;
     if (sc & VSR_SCAFFOLD_SIDE_INTERNAL) { /* :303-341 */
+      r->next_full = 0;
       add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, -h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 1, b0 + 2, -h, -h, -h, +h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, +h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 3, b0 + 0, +h, +h, +h, -h, sp_min, sp_rest, sp_max);
     }
     if (sc & VSR_SCAFFOLD_SIDE_EXTERNAL) { /* :342-380 */
+      r->next_full = 4;
       add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, +h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 1, b0 + 2, +h, -h, +h, +h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, -h, sp_min, sp_rest, sp_max);
       add_spring(r, b0 + 3, b0 + 0, -h, +h, -h, -h, sp_min, sp_rest, sp_max);
     }
     if (sc & VSR_SCAFFOLD_SIDE_CROSS) { /* :381-443 */
+      r->next_full = 8;
       add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
       add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
       add_spring(r, b0 + 1, b0 + 2, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
@@ -343,6 +349,7 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
       add_spring(r, b0 + 3, b0 + 0, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
     }
     if (sc & VSR_SCAFFOLD_CENTRAL_CROSS) { /* :444-470 */
+      r->next_full = 16;
       add_spring(r, b0 + 0, b0 + 2, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
       add_spring(r, b0 + 1, b0 + 3, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
     }
@@ -397,7 +404,20 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   r->nj = r->ns + r->nw;
   r->jorder = (int*)malloc(sizeof(int) * (size_t)(r->nj > 0 ? r->nj : 1));
   int c = 0;
-  for (int s = 0; s < r->ns; s++) r->jorder[c++] = s;
+  if (R->o.order == VSR_ORACLE_ORDER_CANONICAL) {
+    /* Inside a voxel the canonical sweep alternates the perfect matchings of K4 ({01,23}, {12,30},
+       {02,13}: SURVEY.md Appendix B), so that consecutive solves touch disjoint masses -- the order
+       the CUDA kernel's unrolled block uses (two independent dependency chains).  Springs of
+       different voxels share no mass, so the voxel order is immaterial. */
+    static const int PERM[18] = {0, 2, 1, 3, 4, 6, 5, 7, 8, 12, 9, 13, 10, 14, 11, 15, 16, 17};
+    int per = r->nv > 0 ? r->ns / r->nv : 0;
+    for (int v = 0; v < r->nv; v++)
+      for (int i = 0; i < 18; i++)
+        for (int k = 0; k < per; k++)
+          if (r->springs[v * per + k].full == PERM[i]) r->jorder[c++] = v * per + k;
+  } else {
+    for (int s = 0; s < r->ns; s++) r->jorder[c++] = s;
+  }
   if (R->o.order == VSR_ORACLE_ORDER_CANONICAL) {
     for (int w = 0; w < r->nw; w++)
       if (r->welds[w].horizontal) r->jorder[c++] = ~w;
