@@ -649,13 +649,15 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // Warps of a block walk the instruction stream together (see the barriers in the kernel), so
   // the more warps per block the better, up to the register-file limit of 12.  A batch that does
   // not fill the chip is spread as one block per SM with just enough warps each.
-  int wpb = 12;
+  const int WPB_MAX = VSR_MAX_THREADS / 32;
+  int wpb = WPB_MAX;
   {
     int sms_ = 148;
     cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, b->device);
-    if (groups_all <= (long long)sms_ * 12) wpb = (int)std::max<long long>(1, (groups_all + sms_ - 1) / sms_);
+    const long long slots = (long long)sms_ * VSR_MIN_BLOCKS;  // resident blocks on the chip
+    if (groups_all <= slots * WPB_MAX) wpb = (int)std::max<long long>(1, (groups_all + slots - 1) / slots);
   }
-  if (wpb_env > 0) wpb = std::min(12, wpb_env);
+  if (wpb_env > 0) wpb = std::min(WPB_MAX, wpb_env);
   const bool eff_mode = st.spring_mass_mode == VSR_SPRING_MASS_EFFECTIVE;
   if (sizeof(real) == 8) wpb = std::min(wpb, VSR_MAX_THREADS / 64);  // fp64: 32-byte vectors, half the stride
   if (blk) wpb = (nvox + 31) / 32;

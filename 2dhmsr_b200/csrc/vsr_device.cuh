@@ -676,6 +676,9 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #ifndef VSR_MAX_THREADS
 #define VSR_MAX_THREADS 384
 #endif
+#ifndef VSR_MIN_BLOCKS
+#define VSR_MIN_BLOCKS 1
+#endif
 // One warp per block: no block-level synchronisation exists, and 32-thread blocks give the
 // finest balance of robot groups over the 148 SMs.  FULLSPR = all four spring scaffoldings
 // present (the default voxel): the 18 solves then form one branch-free basic block.
@@ -684,7 +687,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // BLK = one robot per block (33..128 voxels): neighbour exchange through shared memory and
 // block-wide votes instead of warp shuffles / ballots.
 template <typename real, int CTRL, bool FAST, bool BLK>
-__global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const Params<real> P) {
+__global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
   constexpr bool FULLSPR = FAST;
@@ -921,22 +924,31 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
         wr2x[3][1] = -sn_[1] * P.weld_len; wr2y[3][1] = cs_[1] * P.weld_len;
         EXFLIP()
       }
-      // warm start: body1 += (imp) ; body2 -= (imp), r1 = 0
-#define VSR_WELD_WARM(side, k, own, is_b1)                                                     \
-  {                                                                                            \
-    /* impulses of absent welds stay exactly 0, so no branch is needed */                      \
-    if (is_b1) {                                                                               \
-      vx[own] += wix[side][k] * im; vy[own] += wiy[side][k] * im; w[own] += ii * wiz[side][k]; \
-    } else {                                                                                   \
-      vx[own] -= wix[side][k] * im; vy[own] -= wiy[side][k] * im;                              \
-      w[own] -= ii * (wr2x[side][k] * wiy[side][k] - wr2y[side][k] * wix[side][k] + wiz[side][k]); \
-    }                                                                                          \
+      // warm start: body1 += (imp), body2 -= (imp), r1 = 0.  Each weld is owned (accumulated and
+      // solved) by the lane of its body1 -- sides 0 (left) and 2 (down); the lane of body2 fetches the
+      // accumulated impulse: its masses 1, 2 belong to the RIGHT neighbour's side-0 welds and its
+      // masses 0, 1 to the UPPER neighbour's side-2 welds.  Impulses of absent welds stay exactly 0.
+      {
+        EXP(0, wix[0][0]) EXP(1, wiy[0][0]) EXP(2, wiz[0][0]) EXP(3, wix[0][1]) EXP(4, wiy[0][1]) EXP(5, wiz[0][1])
+        EXP(6, wix[2][0]) EXP(7, wiy[2][0]) EXP(8, wiz[2][0]) EXP(9, wix[2][1]) EXP(10, wiy[2][1]) EXP(11, wiz[2][1])
+        EXSYNC()
+#define VSR_WELD_WARM_B1(side, k, own) \
+  vx[own] += wix[side][k] * im; vy[own] += wiy[side][k] * im; w[own] += ii * wiz[side][k];
+#define VSR_WELD_WARM_B2(side, k, own, src, slot0)                                              \
+  {                                                                                              \
+    const real ix_ = hm[side] * EXG(slot0, wix[src][k], nl[side]), iy_ = hm[side] * EXG(slot0 + 1, wiy[src][k], nl[side]), \
+               iz_ = hm[side] * EXG(slot0 + 2, wiz[src][k], nl[side]);                          \
+    vx[own] -= ix_ * im; vy[own] -= iy_ * im;                                                    \
+    w[own] -= ii * (wr2x[side][k] * iy_ - wr2y[side][k] * ix_ + iz_);                            \
   }
-      VSR_WELD_WARM(0, 0, 0, true) VSR_WELD_WARM(0, 1, 3, true)
-      VSR_WELD_WARM(1, 0, 1, false) VSR_WELD_WARM(1, 1, 2, false)
-      VSR_WELD_WARM(2, 0, 3, true) VSR_WELD_WARM(2, 1, 2, true)
-      VSR_WELD_WARM(3, 0, 0, false) VSR_WELD_WARM(3, 1, 1, false)
-#undef VSR_WELD_WARM
+        VSR_WELD_WARM_B1(0, 0, 0) VSR_WELD_WARM_B1(0, 1, 3)
+        VSR_WELD_WARM_B1(2, 0, 3) VSR_WELD_WARM_B1(2, 1, 2)
+        VSR_WELD_WARM_B2(1, 0, 1, 0, 0) VSR_WELD_WARM_B2(1, 1, 2, 0, 3)
+        VSR_WELD_WARM_B2(3, 0, 0, 2, 6) VSR_WELD_WARM_B2(3, 1, 1, 2, 9)
+        EXFLIP()
+#undef VSR_WELD_WARM_B1
+#undef VSR_WELD_WARM_B2
+      }
 
       // ---- velocity iterations: all joints, then all contacts
 #pragma unroll 1
@@ -980,40 +992,48 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #define VSR_GATHER_V(tag, part, side)                                                         \
   const real tag##vx = EXG(part * 3 + 0, vx[part], nl[side]), tag##vy = EXG(part * 3 + 1, vy[part], nl[side]), \
              tag##w = EXG(part * 3 + 2, w[part], nl[side]);
-#define VSR_WELD_VEL(side, k, own, tag, is_b1)                                                  \
+// body1's lane solves the weld (own mass `own` is body1, the gathered `tag` mass is body2) ...
+#define VSR_WELD_VEL_B1(side, k, own, tag, L)                                                   \
+  real L##x, L##y, L##z;                                                                        \
   {                                                                                             \
-    real v1x = is_b1 ? vx[own] : tag##vx, v1y = is_b1 ? vy[own] : tag##vy, w1 = is_b1 ? w[own] : tag##w; \
-    real v2x = is_b1 ? tag##vx : vx[own], v2y = is_b1 ? tag##vy : vy[own], w2 = is_b1 ? tag##w : w[own]; \
     real r2x = wr2x[side][k], r2y = wr2y[side][k];                                              \
-    real lx, ly, lz;                                                                            \
-    weld_solve33<real>(v1x - (v2x - w2 * r2y), v1y - (v2y + w2 * r2x), w1 - w2, r2x, r2y, inertia, \
-                       weld_alpha, inv_two_im, lx, ly, lz);                                     \
+    weld_solve33<real>(vx[own] - (tag##vx - tag##w * r2y), vy[own] - (tag##vy + tag##w * r2x), w[own] - tag##w, r2x, r2y, \
+                       inertia, weld_alpha, inv_two_im, L##x, L##y, L##z);                      \
     /* branch-free: a voxel without a neighbour on this side scales the impulse by 0 */         \
-    lx *= hm[side]; ly *= hm[side]; lz *= hm[side];                                             \
-    wix[side][k] += lx; wiy[side][k] += ly; wiz[side][k] += lz;                                 \
-    if (is_b1) {                                                                                \
-      vx[own] += lx * im; vy[own] += ly * im; w[own] += ii * lz;                                \
-    } else {                                                                                    \
-      vx[own] -= lx * im; vy[own] -= ly * im; w[own] -= ii * (r2x * ly - r2y * lx + lz);        \
-    }                                                                                           \
+    L##x *= hm[side]; L##y *= hm[side]; L##z *= hm[side];                                       \
+    wix[side][k] += L##x; wiy[side][k] += L##y; wiz[side][k] += L##z;                           \
+    vx[own] += L##x * im; vy[own] += L##y * im; w[own] += ii * L##z;                            \
+  }
+// ... and body2's lane applies the impulse it receives from that lane
+#define VSR_WELD_VEL_B2(side, k, own, slot0, L)                                                 \
+  {                                                                                             \
+    const real bx_ = hm[side] * EXG(slot0, L##x, nl[side]), by_ = hm[side] * EXG(slot0 + 1, L##y, nl[side]), \
+               bz_ = hm[side] * EXG(slot0 + 2, L##z, nl[side]);                                 \
+    vx[own] -= bx_ * im; vy[own] -= by_ * im;                                                   \
+    w[own] -= ii * (wr2x[side][k] * by_ - wr2y[side][k] * bx_ + bz_);                           \
   }
         {  // horizontal welds (left/right sides): each mass has at most one
           VSR_PUBLISH_V()
-          VSR_GATHER_V(l1, 1, 0) VSR_GATHER_V(l2, 2, 0) VSR_GATHER_V(r0, 0, 1) VSR_GATHER_V(r3, 3, 1)
-          VSR_WELD_VEL(0, 0, 0, l1, true) VSR_WELD_VEL(0, 1, 3, l2, true)
-          VSR_WELD_VEL(1, 0, 1, r0, false) VSR_WELD_VEL(1, 1, 2, r3, false)
+          VSR_GATHER_V(l1, 1, 0) VSR_GATHER_V(l2, 2, 0)
+          VSR_WELD_VEL_B1(0, 0, 0, l1, la) VSR_WELD_VEL_B1(0, 1, 3, l2, lb)
+          EXFLIP()
+          EXP(0, lax) EXP(1, lay) EXP(2, laz) EXP(3, lbx) EXP(4, lby) EXP(5, lbz) EXSYNC()
+          VSR_WELD_VEL_B2(1, 0, 1, 0, la) VSR_WELD_VEL_B2(1, 1, 2, 3, lb)
           EXFLIP()
         }
         {  // vertical welds (down/up sides)
           VSR_PUBLISH_V()
-          VSR_GATHER_V(d0, 0, 2) VSR_GATHER_V(d1, 1, 2) VSR_GATHER_V(u3, 3, 3) VSR_GATHER_V(u2, 2, 3)
-          VSR_WELD_VEL(2, 0, 3, d0, true) VSR_WELD_VEL(2, 1, 2, d1, true)
-          VSR_WELD_VEL(3, 0, 0, u3, false) VSR_WELD_VEL(3, 1, 1, u2, false)
+          VSR_GATHER_V(d0, 0, 2) VSR_GATHER_V(d1, 1, 2)
+          VSR_WELD_VEL_B1(2, 0, 3, d0, da) VSR_WELD_VEL_B1(2, 1, 2, d1, db)
+          EXFLIP()
+          EXP(0, dax) EXP(1, day) EXP(2, daz) EXP(3, dbx) EXP(4, dby) EXP(5, dbz) EXSYNC()
+          VSR_WELD_VEL_B2(3, 0, 0, 0, da) VSR_WELD_VEL_B2(3, 1, 1, 3, db)
           EXFLIP()
         }
 #undef VSR_GATHER_V
 #undef VSR_PUBLISH_V
-#undef VSR_WELD_VEL
+#undef VSR_WELD_VEL_B1
+#undef VSR_WELD_VEL_B2
 
         if (sync_mode & 8) __syncthreads();
         if (n_items > 0 && xmode) {
@@ -1133,35 +1153,40 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
 #define VSR_GATHER_CS(tag, part, side) \
   const real tag##c = EXG(12 + part * 2, cs_[part], nl[side]), tag##s = EXG(13 + part * 2, sn_[part], nl[side]);
 #define VSR_OWN_CS(tag, own) const real tag##c = cs_[own], tag##s = sn_[own];
-#define VSR_WELD_POS(side, own, tag, is_b1, horiz)                                             \
-  {                                                                                            \
-    real x1 = is_b1 ? x[own] : tag##x, y1 = is_b1 ? y[own] : tag##y, t1 = is_b1 ? th[own] : tag##t; \
-    real x2 = is_b1 ? tag##x : x[own], y2 = is_b1 ? tag##y : y[own], t2 = is_b1 ? tag##t : th[own]; \
-    const real s2 = tag##s, c2 = tag##c; /* body2's rotation */                                \
-    real r2x = horiz ? c2 * P.weld_len : -s2 * P.weld_len;                                     \
-    real r2y = horiz ? s2 * P.weld_len : c2 * P.weld_len;                                      \
-    real Cx = x1 - (x2 + r2x), Cy = y1 - (y2 + r2y), Cz = t1 - t2;                             \
-    const real PI_ = real(3.14159265358979323846);                                             \
-    if (Cz < -PI_) Cz += real(2) * PI_;                                                        \
-    if (Cz > PI_) Cz -= real(2) * PI_;                                                         \
-    real linErr = r_sqrt(Cx * Cx + Cy * Cy), angErr = r_abs(Cz);                               \
-    real lx, ly, lz;                                                                           \
-    weld_solve33<real>(Cx, Cy, Cz, r2x, r2y, inertia, weld_alpha, inv_two_im, lx, ly, lz);          \
-    const real pm = done ? real(0) : hm[side];                                                 \
-    lx *= pm; ly *= pm; lz *= pm;                                                              \
-    if (is_b1) {                                                                               \
-      x[own] += lx * im; y[own] += ly * im; th[own] += ii * lz;                                \
-    } else {                                                                                   \
-      x[own] -= lx * im; y[own] -= ly * im; th[own] -= ii * (r2x * ly - r2y * lx + lz);        \
-    }                                                                                          \
-    solved = solved && (!has[side] || ((linErr <= P.lin_tol) && (angErr <= P.ang_tol)));       \
+#define VSR_WELD_POS_B1(side, own, tag, horiz, L)                                               \
+  real L##x, L##y, L##z;                                                                        \
+  {                                                                                             \
+    const real s2 = tag##s, c2 = tag##c; /* body2's rotation */                                 \
+    real r2x = horiz ? c2 * P.weld_len : -s2 * P.weld_len;                                      \
+    real r2y = horiz ? s2 * P.weld_len : c2 * P.weld_len;                                       \
+    real Cx = x[own] - (tag##x + r2x), Cy = y[own] - (tag##y + r2y), Cz = th[own] - tag##t;     \
+    const real PI_ = real(3.14159265358979323846);                                              \
+    if (Cz < -PI_) Cz += real(2) * PI_;                                                         \
+    if (Cz > PI_) Cz -= real(2) * PI_;                                                          \
+    real linErr = r_sqrt(Cx * Cx + Cy * Cy), angErr = r_abs(Cz);                                \
+    weld_solve33<real>(Cx, Cy, Cz, r2x, r2y, inertia, weld_alpha, inv_two_im, L##x, L##y, L##z); \
+    const real pm = done ? real(0) : hm[side];                                                  \
+    L##x *= pm; L##y *= pm; L##z *= pm;                                                         \
+    x[own] += L##x * im; y[own] += L##y * im; th[own] += ii * L##z;                             \
+    solved = solved && (!has[side] || ((linErr <= P.lin_tol) && (angErr <= P.ang_tol)));        \
+  }
+#define VSR_WELD_POS_B2(side, own, horiz, slot0, L)                                             \
+  {                                                                                             \
+    const real pm = done ? real(0) : hm[side];                                                  \
+    const real bx_ = pm * EXG(slot0, L##x, nl[side]), by_ = pm * EXG(slot0 + 1, L##y, nl[side]), \
+               bz_ = pm * EXG(slot0 + 2, L##z, nl[side]);                                       \
+    const real r2x = horiz ? cs_[own] * P.weld_len : -sn_[own] * P.weld_len;                    \
+    const real r2y = horiz ? sn_[own] * P.weld_len : cs_[own] * P.weld_len;                     \
+    x[own] -= bx_ * im; y[own] -= by_ * im; th[own] -= ii * (r2x * by_ - r2y * bx_ + bz_);      \
   }
           {
             VSR_PUBLISH_P()
-            VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0) VSR_GATHER_P(r0, 0, 1) VSR_GATHER_P(r3, 3, 1)
-            VSR_GATHER_CS(l1, 1, 0) VSR_GATHER_CS(l2, 2, 0) VSR_OWN_CS(r0, 1) VSR_OWN_CS(r3, 2)
-            VSR_WELD_POS(0, 0, l1, true, true) VSR_WELD_POS(0, 3, l2, true, true)
-            VSR_WELD_POS(1, 1, r0, false, true) VSR_WELD_POS(1, 2, r3, false, true)
+            VSR_GATHER_P(l1, 1, 0) VSR_GATHER_P(l2, 2, 0)
+            VSR_GATHER_CS(l1, 1, 0) VSR_GATHER_CS(l2, 2, 0)
+            VSR_WELD_POS_B1(0, 0, l1, true, la) VSR_WELD_POS_B1(0, 3, l2, true, lb)
+            EXFLIP()
+            EXP(0, lax) EXP(1, lay) EXP(2, laz) EXP(3, lbx) EXP(4, lby) EXP(5, lbz) EXSYNC()
+            VSR_WELD_POS_B2(1, 1, true, 0, la) VSR_WELD_POS_B2(1, 2, true, 3, lb)
             EXFLIP()
           }
           // masses 0, 1 are body2 of the vertical welds: their angles just changed
@@ -1169,17 +1194,20 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, 1) vsr_episode_kernel(const P
           r_sincos(th[1], &sn_[1], &cs_[1]);
           {
             VSR_PUBLISH_P()
-            VSR_GATHER_P(d0, 0, 2) VSR_GATHER_P(d1, 1, 2) VSR_GATHER_P(u3, 3, 3) VSR_GATHER_P(u2, 2, 3)
-            VSR_GATHER_CS(d0, 0, 2) VSR_GATHER_CS(d1, 1, 2) VSR_OWN_CS(u3, 0) VSR_OWN_CS(u2, 1)
-            VSR_WELD_POS(2, 3, d0, true, false) VSR_WELD_POS(2, 2, d1, true, false)
-            VSR_WELD_POS(3, 0, u3, false, false) VSR_WELD_POS(3, 1, u2, false, false)
+            VSR_GATHER_P(d0, 0, 2) VSR_GATHER_P(d1, 1, 2)
+            VSR_GATHER_CS(d0, 0, 2) VSR_GATHER_CS(d1, 1, 2)
+            VSR_WELD_POS_B1(2, 3, d0, false, da) VSR_WELD_POS_B1(2, 2, d1, false, db)
+            EXFLIP()
+            EXP(0, dax) EXP(1, day) EXP(2, daz) EXP(3, dbx) EXP(4, dby) EXP(5, dbz) EXSYNC()
+            VSR_WELD_POS_B2(3, 0, false, 0, da) VSR_WELD_POS_B2(3, 1, false, 3, db)
             EXFLIP()
           }
 #undef VSR_GATHER_P
 #undef VSR_PUBLISH_P
 #undef VSR_GATHER_CS
 #undef VSR_OWN_CS
-#undef VSR_WELD_POS
+#undef VSR_WELD_POS_B1
+#undef VSR_WELD_POS_B2
           // masses 1, 2 are body2 of the next iteration's horizontal welds
           r_sincos(th[1], &sn_[1], &cs_[1]);
           r_sincos(th[2], &sn_[2], &cs_[2]);
