@@ -67,7 +67,7 @@ class vsr_settings(C.Structure):
         ("ground_friction", C.c_double),
         ("ground_restitution", C.c_double),
         ("spring_mass_mode", C.c_int32),
-        ("reserved", C.c_int32),
+        ("self_collision", C.c_int32),
     ]
 
 
@@ -180,6 +180,7 @@ def default_settings() -> vsr_settings:
     s.ground_friction = 0.2
     s.ground_restitution = 0.0
     s.spring_mass_mode = VSR_SPRING_MASS_REDUCED
+    s.self_collision = 1
     return s
 
 

@@ -62,6 +62,7 @@ extern "C" void vsr_default_settings(vsr_settings* s) {
   s->ground_friction = 0.2;
   s->ground_restitution = 0.0;
   s->spring_mass_mode = VSR_SPRING_MASS_REDUCED;
+  s->self_collision = 1;
 }
 
 extern "C" void vsr_default_material(vsr_material* m) {
@@ -118,6 +119,8 @@ struct Bucket {
   void* d_traj = nullptr;
   void* d_cbuf = nullptr;
   size_t cbuf_bytes = 0;
+  void* d_sbuf = nullptr;  // intra-robot contact arena
+  size_t sbuf_bytes = 0;
 };
 
 }  // namespace
@@ -171,9 +174,10 @@ static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf);
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf);
     k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
+    k.d_sbuf = nullptr; k.sbuf_bytes = 0;
   }
   cudaFree(b->d_results);
   b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
@@ -629,6 +633,9 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.vel_iters = st.velocity_iterations;
   P.pos_iters = st.position_iterations;
   P.spring_mode = st.spring_mass_mode;
+  P.self_coll = st.self_collision ? 1 : 0;
+  P.mu_self = (real)std::sqrt(m.friction * m.friction);          // CoefficientMixer: sqrt(f1 f2)
+  P.rest_e_self = (real)std::max(m.restitution, m.restitution);  // max(e1, e2)
   P.spring_mask = b->spring_mask;
   P.mlp_act = d.mlp_activation;
   P.debug_robot = -1;
@@ -668,7 +675,8 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
   const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
-                      (size_t)wpb * (P.smem_per_warp + 288) * sizeof(real) + (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
+                      (size_t)wpb * (P.smem_per_warp + VSR_XB_STRIDE) * sizeof(real) +
+                      (blk ? (size_t)(2 * 20 * 128 + 19 * 128 + 8) * sizeof(real) : 0);
   P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
@@ -701,6 +709,14 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
       k.cbuf_bytes = need;
     }
     P.cbuf = k.d_cbuf;
+    size_t need_s = P.self_coll ? (size_t)grid * threads * 2 * sizeof(SList<real>) : 0;
+    if (need_s > k.sbuf_bytes) {
+      cudaFree(k.d_sbuf);
+      k.d_sbuf = nullptr;
+      CUDA_TRY(cudaMalloc(&k.d_sbuf, need_s));
+      k.sbuf_bytes = need_s;
+    }
+    P.sbuf = k.d_sbuf;
   }
   kern<<<(unsigned)grid, threads, smem, s>>>(P);
   CUDA_TRY(cudaGetLastError());

@@ -100,6 +100,9 @@ struct Params {
   int mlp_act;
   int smem_per_warp;     // reals of staging per warp
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
+  void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
+  int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
+  real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
   int sync_mode;         // bit0: barrier per tick, bit1: per velocity iteration (code locality only)
   long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
@@ -175,6 +178,27 @@ struct CBody {
   CCon<real> c[MAXC];
 };
 
+// intra-robot contacts (mass against mass, Voxel.java:178-185,474): owned by the thread of the
+// lower body index (ka = its mass), the partner is mass kb of thread tb
+#define SC_CAP 4
+template <typename real>
+struct SPoint {
+  real px, py, depth, jn, jt;
+  int id;
+  real r1x, r1y, r2x, r2y, l1x, l1y, l2x, l2y, massN, massT, vb;
+};
+template <typename real>
+struct SCon {
+  int ka, tb, kb, n, block, pad;
+  real nx, ny;  // manifold normal: from the owner's mass to the partner
+  SPoint<real> p[2];
+  real K00, K01, K11, iK00, iK01, iK11;
+};
+template <typename real>
+struct SList {
+  SCon<real> c[SC_CAP + 1];  // + one scratch entry (overflow probe)
+};
+
 template <typename real>
 struct Poly4 {
   real vx[4], vy[4], nx[4], ny[4];
@@ -245,10 +269,14 @@ __device__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx
 // collision.
 template <typename real>
 __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real bs, real half, real x0, real y0,
-                                                 real x1, real y1, real base_y, CCon<real>& c) {
+                                                 real x1, real y1, real base_y, int mm, CCon<real>& c) {
   // exact geometric ties (a mass lying flat on a flat segment) are decided by rule, with this
-  // margin, exactly as in the oracle: the mass' own face wins
+  // margin, exactly as in the oracle: the mass' own face wins.
+  // mm != 0: the second polygon is another mass, given as (x0, y0, x1, y1) = (centre, cos, sin);
+  // neighbouring masses touch corner to corner at rest, so there every comparison carries the
+  // margin and a contact needs a penetration above it (see the oracle's sat_penetration).
   const real tie_eps = sizeof(real) == 8 ? real(1e-12) : real(1e-6);
+  const real in_eps = mm ? tie_eps : real(0);
   Poly4<real> A, B;
   const real lx[4] = {-1, 1, 1, -1}, ly[4] = {-1, -1, 1, 1};
 #pragma unroll
@@ -261,17 +289,31 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   A.nx[1] = bc; A.ny[1] = bs;
   A.nx[2] = -bs; A.ny[2] = bc;
   A.nx[3] = -bc; A.ny[3] = -bs;
-  B.vx[0] = x0; B.vy[0] = y0;
-  B.vx[1] = x0; B.vy[1] = base_y;
-  B.vx[2] = x1; B.vy[2] = base_y;
-  B.vx[3] = x1; B.vy[3] = y1;
+  if (mm) {
+    const real c2 = x1, s2 = y1;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    int j = (i + 1) & 3;
-    real ex = B.vx[j] - B.vx[i], ey = B.vy[j] - B.vy[i];
-    real l = r_sqrt(ex * ex + ey * ey);
-    B.nx[i] = ey / l;
-    B.ny[i] = -ex / l;
+    for (int i = 0; i < 4; i++) {
+      real px = lx[i] * half, py = ly[i] * half;
+      B.vx[i] = x0 + c2 * px - s2 * py;
+      B.vy[i] = y0 + s2 * px + c2 * py;
+    }
+    B.nx[0] = s2; B.ny[0] = -c2;
+    B.nx[1] = c2; B.ny[1] = s2;
+    B.nx[2] = -s2; B.ny[2] = c2;
+    B.nx[3] = -c2; B.ny[3] = -s2;
+  } else {
+    B.vx[0] = x0; B.vy[0] = y0;
+    B.vx[1] = x0; B.vy[1] = base_y;
+    B.vx[2] = x1; B.vy[2] = base_y;
+    B.vx[3] = x1; B.vy[3] = y1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int j = (i + 1) & 3;
+      real ex = B.vx[j] - B.vx[i], ey = B.vy[j] - B.vy[i];
+      real l = r_sqrt(ex * ex + ey * ey);
+      B.nx[i] = ey / l;
+      B.ny[i] = -ex / l;
+    }
   }
   // SAT: least-negative separation over the face normals of both polygons
   real best = -1e30f, nx = 0, ny = 0;
@@ -283,7 +325,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
       real v = A.nx[i] * (B.vx[j] - A.vx[i]) + A.ny[i] * (B.vy[j] - A.vy[i]);
       s = v < s ? v : s;
     }
-    if (s > best) { best = s; nx = A.nx[i]; ny = A.ny[i]; }
+    if (s > best + (i > 0 ? in_eps : real(0))) { best = s; nx = A.nx[i]; ny = A.ny[i]; }
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -295,7 +337,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
     }
     if (s > best + tie_eps) { best = s; nx = -B.nx[j]; ny = -B.ny[j]; }
   }
-  if (!(best < real(0))) return 0;
+  if (!(best < -in_eps)) return 0;
   // ClippingManifoldSolver.getManifold (dyn4j)
   Edge<real> ref, inc;
   farthest_edge(A, nx, ny, ref);
@@ -366,7 +408,7 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     if (!(x1 > x0)) continue;
     if (ylo > r_max(y0, y1)) continue;
     CCon<real> c;
-    if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, c)) continue;
+    if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, 0, c)) continue;
     if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
     for (int i = 0; i < old_n; i++) {
@@ -394,6 +436,7 @@ struct BodyState {
 template <typename real>
 struct CPar {
   real im, ii, mu, rest_vel, rest_e, lin_tol, max_corr, baumgarte;
+  real mu_s, rest_e_s;  // mass against mass (CoefficientMixer: sqrt(f f), max(e, e))
 };
 
 // SequentialImpulses.initialize (dyn4j) for the constraints of one mass (the ground is
@@ -617,6 +660,267 @@ __device__ __noinline__ BodyState<real> contact_position_mass(const CPar<real> P
   return B;
 }
 
+// ---------------------------------------------------------------- intra-robot contacts
+// The mass table `mt` is the shared-memory exchange of one robot scope (a warp, or the block of a
+// big robot): mt[(k * 4 + c) * mts + t] = component c of mass k of thread t.  Components are
+// (x, y, cos, sin) during detection, (vx, vy, w) in the velocity phases, (x, y, theta) in the
+// position phase.
+#define VSR_MTI(k, c, t) (((k) * 4 + (c)) * mts + (t))
+
+// Narrowphase for one candidate pair + ContactConstraint.update (warm start by point id) + the
+// position-dependent half of SequentialImpulses.initialize (the bodies do not move between this
+// detection and the next step's initialisation).  Returns 1 when *out holds a constraint.
+template <typename real>
+__device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, real ay, real ac, real as, real bx,
+                                      real by, real bc, real bs, int ka, int tb, int kb, const SCon<real>* old,
+                                      int old_n, SCon<real>* out) {
+  CCon<real> m;
+  if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, m)) return 0;
+  SCon<real> c;
+  c.ka = ka; c.tb = tb; c.kb = kb; c.n = m.n; c.block = 0; c.pad = 0;
+  c.nx = m.nx; c.ny = m.ny;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    c.p[k].px = m.p[k].px; c.p[k].py = m.p[k].py; c.p[k].depth = m.p[k].depth;
+    c.p[k].id = m.p[k].id;
+    c.p[k].jn = real(0); c.p[k].jt = real(0); c.p[k].vb = real(0);
+  }
+  for (int i = 0; i < old_n; i++) {
+    const SCon<real>& o = old[i];
+    if (o.ka != ka || o.tb != tb || o.kb != kb) continue;
+    for (int k = 0; k < c.n; k++)
+      for (int l = 0; l < o.n; l++)
+        if (o.p[l].id == c.p[k].id) {
+          c.p[k].jn = o.p[l].jn;
+          c.p[k].jt = o.p[l].jt;
+        }
+    break;
+  }
+  const real im = P.im, ii = P.ii;
+  const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    SPoint<real>& p = c.p[k];
+    if (k >= c.n) { p.px = ax; p.py = ay; }  // unused slot: finite numbers
+    p.r1x = p.px - ax; p.r1y = p.py - ay;
+    p.r2x = p.px - bx; p.r2y = p.py - by;
+    p.l1x = ac * p.r1x + as * p.r1y; p.l1y = -as * p.r1x + ac * p.r1y;
+    p.l2x = bc * p.r2x + bs * p.r2y; p.l2y = -bs * p.r2x + bc * p.r2y;
+    real rn1 = p.r1x * ny - p.r1y * nx, rn2 = p.r2x * ny - p.r2y * nx;
+    p.massN = real(1) / (im + im + ii * rn1 * rn1 + ii * rn2 * rn2);
+    real rt1 = p.r1x * ty - p.r1y * tx, rt2 = p.r2x * ty - p.r2y * tx;
+    p.massT = real(1) / (im + im + ii * rt1 * rt1 + ii * rt2 * rt2);
+  }
+  c.K00 = c.K01 = c.K11 = c.iK00 = c.iK01 = c.iK11 = real(0);
+  if (c.n == 2) {
+    real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx, rn1B = c.p[0].r2x * ny - c.p[0].r2y * nx;
+    real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx, rn2B = c.p[1].r2x * ny - c.p[1].r2y * nx;
+    real mm = im + im;
+    c.K00 = mm + ii * rn1A * rn1A + ii * rn1B * rn1B;
+    c.K01 = mm + ii * rn1A * rn2A + ii * rn1B * rn2B;
+    c.K11 = mm + ii * rn2A * rn2A + ii * rn2B * rn2B;
+    real det = c.K00 * c.K11 - c.K01 * c.K01;
+    if (c.K00 * c.K00 < real(1000) * det) {
+      c.block = 1;
+      real id = real(1) / det;
+      c.iK00 = id * c.K11;
+      c.iK01 = -id * c.K01;
+      c.iK11 = id * c.K00;
+    } else {
+      c.n = 1;
+    }
+  }
+  *out = c;
+  return 1;
+}
+
+// the velocity-dependent half of SequentialImpulses.initialize: the restitution bias, from the
+// velocities before any warm start
+template <typename real>
+__device__ __noinline__ void self_bias(const CPar<real> P, SCon<real>& c, const real* mt, int mts, int ta) {
+  const int ka = c.ka, kb = c.kb, tb = c.tb;
+  const real v1x = mt[VSR_MTI(ka, 0, ta)], v1y = mt[VSR_MTI(ka, 1, ta)], w1 = mt[VSR_MTI(ka, 2, ta)];
+  const real v2x = mt[VSR_MTI(kb, 0, tb)], v2y = mt[VSR_MTI(kb, 1, tb)], w2 = mt[VSR_MTI(kb, 2, tb)];
+  const real nx = c.nx, ny = c.ny;
+  for (int k = 0; k < c.n; k++) {
+    SPoint<real>& p = c.p[k];
+    real rvx = (v2x - w2 * p.r2y) - (v1x - w1 * p.r1y);
+    real rvy = (v2y + w2 * p.r2x) - (v1y + w1 * p.r1x);
+    real rvn = nx * rvx + ny * rvy;
+    real vb = real(0);
+    if (rvn < -P.rest_vel) vb += -P.rest_e_s * rvn;
+    p.vb = vb;
+  }
+}
+
+template <typename real>
+struct Body2 {
+  real v1x, v1y, w1, v2x, v2y, w2;
+};
+template <typename real>
+__device__ __forceinline__ void body2_apply(const real im, const real ii, Body2<real>& B, real r1x, real r1y, real r2x,
+                                            real r2y, real Px, real Py) {
+  B.v1x -= im * Px; B.v1y -= im * Py; B.w1 -= ii * (r1x * Py - r1y * Px);
+  B.v2x += im * Px; B.v2y += im * Py; B.w2 += ii * (r2x * Py - r2y * Px);
+}
+#define VSR_B2_LOAD()                                                                              \
+  const int ka = c.ka, kb = c.kb, tb = c.tb;                                                       \
+  Body2<real> B = {mt[VSR_MTI(ka, 0, ta)], mt[VSR_MTI(ka, 1, ta)], mt[VSR_MTI(ka, 2, ta)],         \
+                   mt[VSR_MTI(kb, 0, tb)], mt[VSR_MTI(kb, 1, tb)], mt[VSR_MTI(kb, 2, tb)]};
+#define VSR_B2_STORE()                                                                             \
+  mt[VSR_MTI(ka, 0, ta)] = B.v1x; mt[VSR_MTI(ka, 1, ta)] = B.v1y; mt[VSR_MTI(ka, 2, ta)] = B.w1;   \
+  mt[VSR_MTI(kb, 0, tb)] = B.v2x; mt[VSR_MTI(kb, 1, tb)] = B.v2y; mt[VSR_MTI(kb, 2, tb)] = B.w2;
+
+// warm start of one mass-mass constraint
+template <typename real>
+__device__ __noinline__ void self_warm(const CPar<real> P, SCon<real>& c, real* mt, int mts, int ta) {
+  VSR_B2_LOAD()
+  const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+  for (int k = 0; k < c.n; k++) {
+    const SPoint<real>& p = c.p[k];
+    body2_apply(P.im, P.ii, B, p.r1x, p.r1y, p.r2x, p.r2y, nx * p.jn + tx * p.jt, ny * p.jn + ty * p.jt);
+  }
+  VSR_B2_STORE()
+}
+
+// SequentialImpulses.solveVelocityConstraints (dyn4j) for one mass-mass constraint
+template <typename real>
+__device__ __noinline__ void self_solve(const CPar<real> P, SCon<real>& c, real* mt, int mts, int ta) {
+  VSR_B2_LOAD()
+  const real im = P.im, ii = P.ii;
+  const int cn = c.n, blk = c.block;
+  const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+  const SPoint<real> p0 = c.p[0], p1 = c.p[1];
+  real jn0 = p0.jn, jt0 = p0.jt, jn1 = p1.jn, jt1 = p1.jt;
+  const bool two = cn == 2;
+#define VSR_RELV(p, rvx, rvy)                                   \
+  real rvx = (B.v2x - B.w2 * p.r2y) - (B.v1x - B.w1 * p.r1y);   \
+  real rvy = (B.v2y + B.w2 * p.r2x) - (B.v1y + B.w1 * p.r1x);
+  {
+    VSR_RELV(p0, rvx, rvy)
+    real tn = tx * rvx + ty * rvy;
+    real jt = p0.massT * (-tn);
+    real maxJt = P.mu_s * jn0;
+    real J0 = jt0;
+    jt0 = r_max(-maxJt, r_min(J0 + jt, maxJt));
+    jt = jt0 - J0;
+    body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, tx * jt, ty * jt);
+  }
+  if (two) {
+    VSR_RELV(p1, rvx, rvy)
+    real tn = tx * rvx + ty * rvy;
+    real jt = p1.massT * (-tn);
+    real maxJt = P.mu_s * jn1;
+    real J0 = jt1;
+    jt1 = r_max(-maxJt, r_min(J0 + jt, maxJt));
+    jt = jt1 - J0;
+    body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, tx * jt, ty * jt);
+  }
+  if (!two || !blk) {
+    {
+      VSR_RELV(p0, rvx, rvy)
+      real rvn = nx * rvx + ny * rvy;
+      real j = -p0.massN * (rvn - p0.vb);
+      real j0 = jn0;
+      jn0 = r_max(j0 + j, real(0));
+      j = jn0 - j0;
+      body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, nx * j, ny * j);
+    }
+    if (two) {
+      VSR_RELV(p1, rvx, rvy)
+      real rvn = nx * rvx + ny * rvy;
+      real j = -p1.massN * (rvn - p1.vb);
+      real j0 = jn1;
+      jn1 = r_max(j0 + j, real(0));
+      j = jn1 - j0;
+      body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, nx * j, ny * j);
+    }
+  } else {
+    real ax = jn0, ay = jn1;
+    real rvn1, rvn2;
+    {
+      VSR_RELV(p0, rvx, rvy)
+      rvn1 = nx * rvx + ny * rvy;
+    }
+    {
+      VSR_RELV(p1, rvx, rvy)
+      rvn2 = nx * rvx + ny * rvy;
+    }
+    real bx = rvn1 - p0.vb, by = rvn2 - p1.vb;
+    bx -= c.K00 * ax + c.K01 * ay;
+    by -= c.K01 * ax + c.K11 * ay;
+    real x = -(c.iK00 * bx + c.iK01 * by), y = -(c.iK01 * bx + c.iK11 * by);
+    bool ok = (x >= real(0) && y >= real(0));
+    if (!ok) {
+      x = -p0.massN * bx;
+      y = real(0);
+      real v2 = c.K01 * x + by;
+      ok = (x >= real(0) && v2 >= real(0));
+    }
+    if (!ok) {
+      x = real(0);
+      y = -p1.massN * by;
+      real v1 = c.K01 * y + bx;
+      ok = (y >= real(0) && v1 >= real(0));
+    }
+    if (!ok) {
+      x = real(0);
+      y = real(0);
+      ok = (bx >= real(0) && by >= real(0));
+    }
+    if (ok) {
+      real dx = x - ax, dy = y - ay;
+      body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, nx * dx, ny * dx);
+      body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, nx * dy, ny * dy);
+      jn0 = x;
+      jn1 = y;
+    }
+  }
+#undef VSR_RELV
+  c.p[0].jn = jn0;
+  c.p[0].jt = jt0;
+  if (two) {
+    c.p[1].jn = jn1;
+    c.p[1].jt = jt1;
+  }
+  VSR_B2_STORE()
+}
+
+// SequentialImpulses.solvePositionContraints (dyn4j) for one mass-mass constraint; the table holds
+// (x, y, theta).  Returns the minimum separation seen.
+template <typename real>
+__device__ __noinline__ real self_position(const CPar<real> P, const SCon<real>& c, real* mt, int mts, int ta) {
+  const int ka = c.ka, kb = c.kb, tb = c.tb;
+  real x1 = mt[VSR_MTI(ka, 0, ta)], y1 = mt[VSR_MTI(ka, 1, ta)], t1 = mt[VSR_MTI(ka, 2, ta)];
+  real x2 = mt[VSR_MTI(kb, 0, tb)], y2 = mt[VSR_MTI(kb, 1, tb)], t2 = mt[VSR_MTI(kb, 2, tb)];
+  const real im = P.im, ii = P.ii;
+  const real nx = c.nx, ny = c.ny;
+  real minSep = real(0);
+  for (int k = 0; k < c.n; k++) {
+    const SPoint<real>& p = c.p[k];
+    real s1, c1, s2, c2;
+    r_sincos(t1, &s1, &c1);
+    r_sincos(t2, &s2, &c2);
+    real r1x = c1 * p.l1x - s1 * p.l1y, r1y = s1 * p.l1x + c1 * p.l1y;
+    real r2x = c2 * p.l2x - s2 * p.l2y, r2y = s2 * p.l2x + c2 * p.l2y;
+    real p1x = x1 + r1x, p1y = y1 + r1y;
+    real p2x = x2 + r2x, p2y = y2 + r2y;
+    real sep = (p2x - p1x) * nx + (p2y - p1y) * ny - p.depth;
+    minSep = sep < minSep ? sep : minSep;
+    real cl = r_clamp<real>(sep + P.lin_tol, -P.max_corr, real(0));
+    real cp = P.baumgarte * cl;
+    real rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
+    real K = im + im + ii * rn1 * rn1 + ii * rn2 * rn2;
+    real jp = -cp / K;
+    real Jx = nx * jp, Jy = ny * jp;
+    x1 -= Jx * im; y1 -= Jy * im; t1 -= ii * (r1x * Jy - r1y * Jx);
+    x2 += Jx * im; y2 += Jy * im; t2 += ii * (r2x * Jy - r2y * Jx);
+  }
+  mt[VSR_MTI(ka, 0, ta)] = x1; mt[VSR_MTI(ka, 1, ta)] = y1; mt[VSR_MTI(ka, 2, ta)] = t1;
+  mt[VSR_MTI(kb, 0, tb)] = x2; mt[VSR_MTI(kb, 1, tb)] = y2; mt[VSR_MTI(kb, 2, tb)] = t2;
+  return minSep;
+}
+
 // ---------------------------------------------------------------- springs
 // The 18 DistanceJoints of a voxel, indices as in `allSpringJoints` (Voxel.java:303-470).
 // Listed in the canonical SOLVE order: inside a voxel the sweep alternates the perfect matchings
@@ -709,6 +1013,9 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // ---------------------------------------------------------------- the episode kernel
 #ifndef VSR_MAX_THREADS
 #define VSR_MAX_THREADS 384
+// reals of shared memory per warp for the contact exchange: 16 fields x 32 (mass table; the
+// ground-contact exchange uses the first 8) + the 32-entry work list
+#define VSR_XB_STRIDE 544
 #endif
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
@@ -740,11 +1047,20 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   real* stage = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)wib * P.smem_per_warp;
   // contact exchange: the contact masses of a warp are solved one per lane; their owners post the
   // mass state here ([field][item], conflict-free for the solving lanes) and read the result back
-  real* xb = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp + (size_t)wib * 288;
-  int* wl = reinterpret_cast<int*>(xb + 256);  // work list: (owner lane << 3) | (mass << 1) | buffer
+  real* xb = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp + (size_t)wib * VSR_XB_STRIDE;
+  int* wl = reinterpret_cast<int*>(xb + 512);  // work list: (owner lane << 3) | (mass << 1) | buffer
 #define XB(j, item) xb[(j) * 32 + (item)]
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
-  real* const ex = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * (P.smem_per_warp + 288);
+  real* const ex = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * (P.smem_per_warp + VSR_XB_STRIDE);
+  // mass table of the intra-robot contacts ([16 fields][scope threads], see VSR_MTI): the warp's
+  // exchange region (the ground-contact exchange is dead while it is in use), or block-wide for
+  // a big robot; + per-voxel bounding data (centre x, y, radius) for the pair pruning
+  constexpr int MTS = BLK ? 128 : 32;
+  real* const mt = BLK ? ex + 2 * 20 * 128 : xb;
+  real* const vxb = BLK ? mt + 16 * 128 : stage;
+  int* const bsc = reinterpret_cast<int*>(mt + 19 * 128);  // BLK: per-warp counts for the block-wide scan
+  const int mt_t = BLK ? tid : lane;
+#define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
   real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
   int exsel = 0;
 #define EXP(slot_, value_) if (BLK) ex[(exsel * 20 + (slot_)) * 128 + tid] = (value_);
@@ -781,7 +1097,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   const real ang_f = r_clamp<real>(real(1) - dt * P.ang_damp, real(0), real(1));
   const real max_trans2 = P.max_trans * P.max_trans;
   const TPar<real> tpar = {P.terr_x, P.terr_y, P.terr_n, P.half, P.base_y};
-  const CPar<real> cpar = {P.inv_m, P.inv_i, P.mu, P.rest_vel, P.rest_e, P.lin_tol, P.max_corr, P.baumgarte};
+  const CPar<real> cpar = {P.inv_m, P.inv_i, P.mu, P.rest_vel, P.rest_e, P.lin_tol, P.max_corr, P.baumgarte,
+                           P.mu_self, P.rest_e_self};
   // reduced-mass springs: k, d and gamma are constants (same expression as the per-spring one)
   const real gam_c = real(1) / (dt * (real(2) * P.red_mass * P.spring_zeta * P.spring_w + dt * (P.red_mass * P.spring_w * P.spring_w)));
   const int sync_mode = P.sync_mode;
@@ -834,6 +1151,34 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     int n_items = 0, item_base = 0;  // this warp's contact masses / this lane's first slot
     bool xmode = true;               // all of them fit one round of 32 lanes
     CBody<real>* cbp = nullptr;      // the contact mass this lane solves
+    // intra-robot contacts owned by this thread: two lists (this step's / the previous step's) and,
+    // packed in one word, count (bits 0-3), position in the robot's solve order (4-15), the longest
+    // list of any robot in the scope (16-27) and the current list (31)
+    SList<real>* const sbase = reinterpret_cast<SList<real>*>(P.sbuf) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    unsigned sst = 0;
+#define S_N ((int)(sst & 15u))
+#define S_START ((int)((sst >> 4) & 0xfffu))
+#define S_TOT ((int)((sst >> 16) & 0xfffu))
+#define S_CUR (sbase + (sst >> 31))
+// one constraint per robot and round, in the robot's order (Gauss-Seidel inside a robot)
+#define VSR_SELF_ROUNDS(GUARD, CALL)                                  \
+  for (int i_ = 0, tot_ = S_TOT; i_ < tot_; i_++) {                   \
+    const int li_ = i_ - S_START;                                     \
+    if ((GUARD) && li_ >= 0 && li_ < S_N) {                           \
+      SCon<real>& sc_ = S_CUR->c[li_];                                \
+      CALL;                                                           \
+    }                                                                 \
+    SSYNC()                                                           \
+  }
+#define VSR_MT_PUT(a0, a1, a2)                                                                     \
+  _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                  \
+    mt[VSR_MTK(k, 0)] = a0[k]; mt[VSR_MTK(k, 1)] = a1[k]; mt[VSR_MTK(k, 2)] = a2[k];               \
+  }
+#define VSR_MT_GET(a0, a1, a2)                                                                     \
+  _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                  \
+    a0[k] = mt[VSR_MTK(k, 0)]; a1[k] = mt[VSR_MTK(k, 1)]; a2[k] = mt[VSR_MTK(k, 2)];               \
+  }
+#define VSR_MTK(k, c) (((k) * 4 + (c)) * MTS + mt_t)
     int status = 0;
     real last_f = real(0), ar_energy = real(0), ctrl_energy = real(0);
     real readings[MAX_READ];
@@ -852,6 +1197,13 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         vx[k] *= lin_f;
         vy[k] *= lin_f;
         w[k] *= ang_f;
+      }
+      // ---- intra-robot contacts: restitution bias from the velocities before any warm start
+      if (S_TOT > 0) {
+        VSR_MT_PUT(vx, vy, w)
+        SSYNC()
+        for (int li = 0; li < S_N; li++) self_bias(cpar, S_CUR->c[li], mt, MTS, mt_t);
+        SSYNC()
       }
       // ---- contacts: initialise + warm start
 #define VSR_SLOT(k) (item_base + __popc(cmask & ((1u << (k)) - 1u)))
@@ -885,6 +1237,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
           }
         }
+      }
+      if (S_TOT > 0) {  // warm start of the intra-robot constraints, after the ground's
+        if (!BLK) __syncwarp();
+        VSR_MT_PUT(vx, vy, w)
+        SSYNC()
+        VSR_SELF_ROUNDS(true, self_warm(cpar, sc_, mt, MTS, mt_t))
+        VSR_MT_GET(vx, vy, w)
+        if (!BLK) __syncwarp();
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
       real ch[4], sh[4];
@@ -1095,6 +1455,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
           }
         }
+        if (S_TOT > 0) {  // then the intra-robot constraints, one per robot at a time
+          if (!BLK) __syncwarp();
+          VSR_MT_PUT(vx, vy, w)
+          SSYNC()
+          VSR_SELF_ROUNDS(true, self_solve(cpar, sc_, mt, MTS, mt_t))
+          VSR_MT_GET(vx, vy, w)
+          if (!BLK) __syncwarp();
+        }
       }
 
       if (sync_mode & 4) __syncthreads();
@@ -1170,6 +1538,23 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               }
             }
             solved = minSep >= real(-3) * P.lin_tol;
+          }
+          if (S_TOT > 0) {
+            if (!BLK) __syncwarp();
+            VSR_MT_PUT(x, y, th)
+            SSYNC()
+            real sms = real(0);
+            VSR_SELF_ROUNDS(!done, {
+              const real ms_ = self_position(cpar, sc_, mt, MTS, mt_t);
+              sms = ms_ < sms ? ms_ : sms;
+            })
+            if (!done) {
+              VSR_MT_GET(x, y, th)
+              r_sincos(th[1], &sn_[1], &cs_[1]);
+              r_sincos(th[2], &sn_[2], &cs_[2]);
+              solved = solved && (sms >= real(-3) * P.lin_tol);
+            }
+            if (!BLK) __syncwarp();
           }
           // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)
 #define VSR_PUBLISH_P()                                                                       \
@@ -1278,6 +1663,86 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
 #endif
         }
+      }
+
+      // ---- intra-robot pairs: every mass against every later mass of the robot that is not welded
+      //      to it.  Order inside a robot = (owner voxel, partner voxel, partner mass, own mass),
+      //      the oracle's canonical enumeration.
+      if (P.self_coll) {
+        if (!BLK) __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          mt[VSR_MTK(k, 0)] = x[k]; mt[VSR_MTK(k, 1)] = y[k]; mt[VSR_MTK(k, 2)] = cs_[k]; mt[VSR_MTK(k, 3)] = sn_[k];
+        }
+        const real vcx = real(0.25) * ((x[0] + x[1]) + (x[2] + x[3])), vcy = real(0.25) * ((y[0] + y[1]) + (y[2] + y[3]));
+        real vrad = real(0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) vrad = r_max(vrad, r_max(r_abs(x[k] - vcx), r_abs(y[k] - vcy)));
+        vxb[0 * MTS + mt_t] = vcx; vxb[1 * MTS + mt_t] = vcy; vxb[2 * MTS + mt_t] = vrad;
+        SSYNC()
+        int n_new = 0;
+        if (active) {
+          const int old_n = S_N;
+          const SCon<real>* const oldc = S_CUR->c;
+          SCon<real>* const newc = (sbase + ((sst >> 31) ^ 1u))->c;
+          const real rr = real(2.8284271247461903) * P.half;  // two half diagonals
+          const int j_right = has[1] ? nl[1] - lane0 : -1, j_up = has[3] ? nl[3] - lane0 : -1;
+          for (int j = v; j < nvox; j++) {
+            const int tj = lane0 + j;
+            if (j != v) {
+              const real lim = vrad + vxb[2 * MTS + tj] + rr;
+              if (r_abs(vxb[0 * MTS + tj] - vcx) > lim || r_abs(vxb[1 * MTS + tj] - vcy) > lim) continue;
+            }
+            // welded pairs, bit (own mass * 4 + partner mass): right neighbour 1-0, 2-3; upper 0-3, 1-2
+            const unsigned wm = j == j_right ? ((1u << 4) | (1u << 11)) : (j == j_up ? ((1u << 3) | (1u << 6)) : 0u);
+#pragma unroll 1
+            for (int kb = 0; kb < 4; kb++) {
+              const real bx = mt[((kb * 4 + 0) * MTS) + tj], by = mt[((kb * 4 + 1) * MTS) + tj];
+#pragma unroll
+              for (int ka = 0; ka < 4; ka++) {
+                if (j == v && kb <= ka) continue;
+                if ((wm >> (ka * 4 + kb)) & 1u) continue;
+                if (r_abs(x[ka] - bx) > rr || r_abs(y[ka] - by) > rr) continue;
+                const int got = self_pair(cpar, P.half, x[ka], y[ka], cs_[ka], sn_[ka], bx, by,
+                                          mt[((kb * 4 + 2) * MTS) + tj], mt[((kb * 4 + 3) * MTS) + tj], ka, tj, kb, oldc,
+                                          old_n, &newc[n_new]);
+                if (got) {
+                  if (n_new == SC_CAP) status |= STATUS_CONTACT_OVERFLOW;
+                  else n_new++;
+                }
+              }
+            }
+          }
+        }
+        // position of this thread's constraints in its robot's order, and the longest robot list
+        int incl = n_new;
+#pragma unroll
+        for (int d2 = 1; d2 < 32; d2 <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d2);
+          if (lane >= d2) incl += t;
+        }
+        int s_start, s_tot;
+        if (BLK) {
+          if (lane == 31) bsc[wib] = incl;
+          __syncthreads();
+          int before = 0, all = 0;
+          for (int q = 0; q < wpb; q++) {
+            const int c = bsc[q];
+            before += q < wib ? c : 0;
+            all += c;
+          }
+          s_start = before + incl - n_new;
+          s_tot = all;
+        } else {
+          const int first = lane_ok ? lane0 : lane, last = lane_ok ? lane0 + nvox - 1 : lane;
+          const int below = __shfl_sync(0xffffffffu, incl, first > 0 ? first - 1 : 0);
+          const int upto = __shfl_sync(0xffffffffu, incl, last);
+          const int base = first > 0 ? below : 0;
+          s_start = incl - n_new - base;
+          s_tot = (int)__reduce_max_sync(0xffffffffu, (unsigned)(lane_ok ? upto - base : 0));
+        }
+        sst = (unsigned)n_new | ((unsigned)s_start << 4) | ((unsigned)s_tot << 16) | ((sst ^ 0x80000000u) & 0x80000000u);
+        SSYNC()
       }
 
       // ---- work list of this warp's contact masses (one per lane from the next tick on)

@@ -59,7 +59,8 @@ typedef struct vsr_settings {
   double ground_friction;       /* 0.2  BodyFixture default (Ground.java:72 passes none) */
   double ground_restitution;    /* 0.0 */
   int32_t spring_mass_mode;     /* VSR_SPRING_MASS_* : which mass turns (f, zeta) into (k, d) */
-  int32_t reserved;
+  int32_t self_collision;       /* 1 (default): masses of one robot collide with each other unless welded
+                                   (Voxel.java:178-185,474; Robot.java:66-71); 0: ground contacts only */
 } vsr_settings;
 
 #define VSR_SPRING_MASS_REDUCED 0   /* m1*m2/(m1+m2)  (Box2D-2.4 lineage)            */

@@ -763,7 +763,11 @@ static void ground_poly(const vsr_batch_desc* d, double base_y, int seg, OPoly* 
 /* Narrowphase.  dyn4j runs GJK + EPA; for two convex polygons the EPA result is the
    minimum-translation vector, i.e. the face normal (of either polygon) with the
    smallest overlap = the SAT answer restated here.  Normal points from A to B. */
-static int sat_penetration(const OPoly* A, const OPoly* B, double* nx, double* ny, double* depth) {
+static int sat_penetration(const OPoly* A, const OPoly* B, int mm, double* nx, double* ny, double* depth) {
+  /* mm = mass against mass (intra-robot).  Masses of neighbouring voxels touch corner to corner at
+     rest, so every comparison there is decided by rule with a margin instead of by the last bit:
+     an earlier face wins ties, and a contact needs a penetration above the margin. */
+  const double in_eps = mm ? TIE_EPS : 0.0;
   double best = -INFINITY, bx = 0, by = 0;
   for (int i = 0; i < A->n; i++) {
     double s = INFINITY;
@@ -771,7 +775,7 @@ static int sat_penetration(const OPoly* A, const OPoly* B, double* nx, double* n
       double v = A->nx[i] * (B->vx[j] - A->vx[i]) + A->ny[i] * (B->vy[j] - A->vy[i]);
       if (v < s) s = v;
     }
-    if (s > best) {
+    if (s > best + (i > 0 ? in_eps : 0.0)) {
       best = s;
       bx = A->nx[i];
       by = A->ny[i];
@@ -789,7 +793,7 @@ static int sat_penetration(const OPoly* A, const OPoly* B, double* nx, double* n
       by = -B->ny[j];
     }
   }
-  if (!(best < 0.0)) return 0;
+  if (!(best < -in_eps)) return 0;
   *nx = bx;
   *ny = by;
   *depth = -best;
@@ -965,7 +969,7 @@ static void detect(ORun* R, ORobot* r) {
       OPoly G;
       ground_poly(d, R->base_y, seg, &G);
       double nx, ny, depth;
-      if (!sat_penetration(&A, &G, &nx, &ny, &depth)) continue;
+      if (!sat_penetration(&A, &G, 0, &nx, &ny, &depth)) continue;
       OContact c;
       memset(&c, 0, sizeof c);
       c.b1 = b;
@@ -979,12 +983,26 @@ static void detect(ORun* R, ORobot* r) {
       r->touch[b / 4] = 1; /* Touch.java:35-48: a body whose userData != this robot */
     }
   }
-  if (R->o.self_collision) {
-    /* masses of the same robot collide unless welded (Voxel.java:178-185,474) */
+  if (R->o.self_collision || d->settings.self_collision) {
+    /* masses of the same robot collide unless welded (Voxel.java:178-185,474: RobotFilter allows
+       every pair, the springs allow collisions, WeldJoint keeps dyn4j's default = not allowed) */
     double mu_s = sqrt(d->material.friction * d->material.friction);
     double e_s = d->material.restitution;
-    for (int a = 0; a < r->nb; a++) {
-      for (int b = a + 1; b < r->nb; b++) {
+    int canonical = R->o.order == VSR_ORACLE_ORDER_CANONICAL;
+    int npairs = canonical ? r->nv * r->nv * 16 : r->nb * r->nb;
+    for (int q = 0; q < npairs; q++) {
+      int a, b;
+      if (canonical) { /* the kernel's enumeration: owner voxel, partner voxel, partner mass, own mass */
+        int va = q / (r->nv * 16), rem = q % (r->nv * 16);
+        int vb = rem / 16, kb = (rem / 4) % 4, ka = rem % 4;
+        a = 4 * va + ka;
+        b = 4 * vb + kb;
+      } else {
+        a = q / r->nb;
+        b = q % r->nb;
+      }
+      if (!(a < b)) continue;
+      {
         OBody* A0 = &r->bodies[a];
         OBody* B0 = &r->bodies[b];
         double rr = 2.0 * R->half * 1.4142135623730951;
@@ -998,7 +1016,7 @@ static void detect(ORun* R, ORobot* r) {
         mass_poly(A0, R->half, &A);
         mass_poly(B0, R->half, &B);
         double nx, ny, depth;
-        if (!sat_penetration(&A, &B, &nx, &ny, &depth)) continue;
+        if (!sat_penetration(&A, &B, 1, &nx, &ny, &depth)) continue;
         OContact c;
         memset(&c, 0, sizeof c);
         c.b1 = a;
