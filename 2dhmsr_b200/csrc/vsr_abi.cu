@@ -121,6 +121,8 @@ struct Bucket {
   size_t cbuf_bytes = 0;
   void* d_sbuf = nullptr;  // intra-robot contact arena
   size_t sbuf_bytes = 0;
+  void* d_lbuf = nullptr;  // per-block contact lists
+  size_t lbuf_bytes = 0;
 };
 
 }  // namespace
@@ -174,10 +176,11 @@ static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf);
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
     k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
     k.d_sbuf = nullptr; k.sbuf_bytes = 0;
+    k.d_lbuf = nullptr; k.lbuf_bytes = 0;
   }
   cudaFree(b->d_results);
   b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
@@ -675,8 +678,8 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
   const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
-                      (size_t)wpb * (P.smem_per_warp + VSR_XB_STRIDE) * sizeof(real) +
-                      (blk ? (size_t)(2 * 20 * 128 + 19 * 128 + 8) * sizeof(real) : 0);
+                      ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + VSR_LHD_REALS) * sizeof(real) +
+                      (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
   P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
@@ -717,6 +720,14 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
       k.sbuf_bytes = need_s;
     }
     P.sbuf = k.d_sbuf;
+    size_t need_l = (size_t)grid * 8 * stride * sizeof(int);
+    if (need_l > k.lbuf_bytes) {
+      cudaFree(k.d_lbuf);
+      k.d_lbuf = nullptr;
+      CUDA_TRY(cudaMalloc(&k.d_lbuf, need_l));
+      k.lbuf_bytes = need_l;
+    }
+    P.lbuf = (int*)k.d_lbuf;
   }
   kern<<<(unsigned)grid, threads, smem, s>>>(P);
   CUDA_TRY(cudaGetLastError());

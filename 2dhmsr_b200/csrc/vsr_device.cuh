@@ -101,6 +101,7 @@ struct Params {
   int smem_per_warp;     // reals of staging per warp
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
+  int* lbuf;             // contact lists: [grid blocks][8 * max threads per block]
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
@@ -391,7 +392,8 @@ struct TPar {
 // points with the same id are carried over (ContactConstraint.update).
 template <typename real>
 __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, real bc, real bs, int& hint,
-                                        const CBody<real>& old, int had_contact, CBody<real>& cb, int& n_out) {
+                                        const CBody<real>& old, int had_contact, CBody<real>& cb, int& n_out,
+                                        real im, real ii) {
   real e = P.half * (r_abs(bc) + r_abs(bs));
   real xlo = bx - e, xhi = bx + e, ylo = by - e;
   int n = P.terr_n;
@@ -420,6 +422,42 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
             c.p[k].jt = old.c[i].p[l].jt;
           }
     }
+    // SequentialImpulses.initialize (dyn4j), the part that depends on positions only (the ground
+    // is static: invM2 = invI2 = 0): the mass does not move between this detection and the next
+    // step's initialisation
+    {
+      const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+      for (int k = 0; k < c.n; k++) {
+        CPoint<real>& p = c.p[k];
+        p.r1x = p.px - bx;
+        p.r1y = p.py - by;
+        p.l1x = bc * p.r1x + bs * p.r1y;
+        p.l1y = -bs * p.r1x + bc * p.r1y;
+        real rn1 = p.r1x * ny - p.r1y * nx;
+        p.massN = real(1) / (im + ii * rn1 * rn1);
+        real rt1 = p.r1x * ty - p.r1y * tx;
+        p.massT = real(1) / (im + ii * rt1 * rt1);
+        p.vb = real(0);
+      }
+      c.block = 0;
+      if (c.n == 2) {
+        real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx;
+        real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx;
+        c.K00 = im + ii * rn1A * rn1A;
+        c.K01 = im + ii * rn1A * rn2A;
+        c.K11 = im + ii * rn2A * rn2A;
+        real det = c.K00 * c.K11 - c.K01 * c.K01;
+        if (c.K00 * c.K00 < real(1000) * det) {
+          c.block = 1;
+          real id = real(1) / det;
+          c.iK00 = id * c.K11;
+          c.iK01 = -id * c.K01;
+          c.iK11 = id * c.K00;
+        } else {
+          c.n = 1;
+        }
+      }
+    }
     cb.c[cn++] = c;
   }
   if (cn > 0 || had_contact) cb.n = cn;
@@ -439,57 +477,32 @@ struct CPar {
   real mu_s, rest_e_s;  // mass against mass (CoefficientMixer: sqrt(f f), max(e, e))
 };
 
-// SequentialImpulses.initialize (dyn4j) for the constraints of one mass (the ground is
-// static: invM2 = invI2 = 0), followed by their warm start.
+// SequentialImpulses.initialize (dyn4j), the velocity-dependent half for the constraints of one
+// mass: the restitution bias, from the velocities before any warm start.
 template <typename real>
-__device__ __noinline__ BodyState<real> contact_init_mass(const CPar<real> P, BodyState<real> B, real bc, real bs,
-                                                          CBody<real>& cb) {
-  const real im = P.im, ii = P.ii;
+__device__ __noinline__ void contact_bias_mass(const CPar<real> P, real vx, real vy, real w, CBody<real>& cb) {
   for (int q = 0; q < cb.n; q++) {
     CCon<real>& c = cb.c[q];
-    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
+    const real nx = c.nx, ny = c.ny;
     for (int k = 0; k < c.n; k++) {
       CPoint<real>& p = c.p[k];
-      p.r1x = p.px - B.x;
-      p.r1y = p.py - B.y;
-      p.l1x = bc * p.r1x + bs * p.r1y;
-      p.l1y = -bs * p.r1x + bc * p.r1y;
-      real rn1 = p.r1x * ny - p.r1y * nx;
-      p.massN = real(1) / (im + ii * rn1 * rn1);
-      real rt1 = p.r1x * ty - p.r1y * tx;
-      p.massT = real(1) / (im + ii * rt1 * rt1);
-      real rvx = -(B.vx - B.w * p.r1y), rvy = -(B.vy + B.w * p.r1x);
+      real rvx = -(vx - w * p.r1y), rvy = -(vy + w * p.r1x);
       real rvn = nx * rvx + ny * rvy;
-      p.vb = real(0);
-      if (rvn < -P.rest_vel) p.vb += -P.rest_e * rvn;
-    }
-    c.block = 0;
-    if (c.n == 2) {
-      real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx;
-      real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx;
-      c.K00 = im + ii * rn1A * rn1A;
-      c.K01 = im + ii * rn1A * rn2A;
-      c.K11 = im + ii * rn2A * rn2A;
-      real det = c.K00 * c.K11 - c.K01 * c.K01;
-      if (c.K00 * c.K00 < real(1000) * det) {
-        c.block = 1;
-        real id = real(1) / det;
-        c.iK00 = id * c.K11;
-        c.iK01 = -id * c.K01;
-        c.iK11 = id * c.K00;
-      } else {
-        c.n = 1;
-      }
+      real vb = real(0);
+      if (rvn < -P.rest_vel) vb += -P.rest_e * rvn;
+      p.vb = vb;
     }
   }
-  // the oracle warm-starts after ALL constraints are initialised; for one mass against a
-  // static ground the initialisation of other masses does not read this mass' velocity,
-  // so doing it per mass is identical -- but all constraints of THIS mass first.
+}
+// ... and the warm start of those constraints
+template <typename real>
+__device__ __noinline__ BodyState<real> contact_warm_mass(const CPar<real> P, BodyState<real> B, const CBody<real>& cb) {
+  const real im = P.im, ii = P.ii;
   for (int q = 0; q < cb.n; q++) {
-    CCon<real>& c = cb.c[q];
+    const CCon<real>& c = cb.c[q];
     real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
     for (int k = 0; k < c.n; k++) {
-      CPoint<real>& p = c.p[k];
+      const CPoint<real>& p = c.p[k];
       real Px = nx * p.jn + tx * p.jt, Py = ny * p.jn + ty * p.jt;
       B.vx -= im * Px;
       B.vy -= im * Py;
@@ -921,6 +934,67 @@ __device__ __noinline__ real self_position(const CPar<real> P, const SCon<real>&
   return minSep;
 }
 
+// ---------------------------------------------------------------- the block's contact list
+// An item: (owner thread << 5) | kind-specific bits | kind.  Ground (kind 0): (mass * 2 + buffer)
+// << 1 -> the owner's CBody.  Intra-robot (kind 1): list << 4 | index << 1 -> the owner's SCon.
+#define VSR_ITEM_OWNER(code) ((code) >> 5)
+#define VSR_ITEM_GROUND(code) (!((code) & 1))
+#define VSR_ITEM_MASS(code) (((code) >> 2) & 3)
+template <typename real>
+__device__ __forceinline__ CBody<real>& item_cbody(CBody<real>* blk_cb, int code) {
+  return blk_cb[(size_t)VSR_ITEM_OWNER(code) * 8 + ((code >> 1) & 7)];
+}
+template <typename real>
+__device__ __forceinline__ SCon<real>& item_scon(SList<real>* blk_sl, int code) {
+  return blk_sl[(size_t)VSR_ITEM_OWNER(code) * 2 + ((code >> 4) & 1)].c[(code >> 1) & 7];
+}
+enum : int { ROUND_WARM = 0, ROUND_VELOCITY = 1, ROUND_POSITION = 2 };
+// One round per dependency level, every thread of the block takes items: the items of a level
+// touch disjoint masses, so solving them at once equals solving the whole list in its order
+// (ground constraints first, then every robot's intra-robot constraints in the robot's
+// enumeration).  `aux` (position rounds): [0][thread] robot already solved, [1][thread] a
+// constraint of this thread is still violated.
+template <int MODE, typename real>
+__device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, int mts, const int* lhd, const int* items,
+                                               int n_lv, int tid, int bdim, CBody<real>* blk_cb, SList<real>* blk_sl,
+                                               real* aux) {
+  for (int l = 0, lo = 0; l < n_lv; l++) {
+    const int hi = lhd[2 + l];
+    for (int i = lo + tid; i < hi; i += bdim) {
+      const int code = items[i];
+      const int ow = VSR_ITEM_OWNER(code);
+      if (MODE == ROUND_POSITION && aux[ow] != real(0)) continue;
+      if (VSR_ITEM_GROUND(code)) {
+        const int km = VSR_ITEM_MASS(code);
+        CBody<real>& cb = item_cbody(blk_cb, code);
+        const int i0 = VSR_MTI(km, 0, ow), i1 = VSR_MTI(km, 1, ow), i2 = VSR_MTI(km, 2, ow);
+        if (MODE == ROUND_POSITION) {
+          BodyState<real> B = {mt[i0], mt[i1], mt[i2], real(0), real(0), real(0)};
+          real ms;
+          B = contact_position_mass(cpar, B, cb, ms);
+          mt[i0] = B.x; mt[i1] = B.y; mt[i2] = B.th;
+          if (ms < real(-3) * cpar.lin_tol) aux[bdim + ow] = real(1);
+        } else {
+          BodyState<real> B = {real(0), real(0), real(0), mt[i0], mt[i1], mt[i2]};
+          if (MODE == ROUND_WARM) B = contact_warm_mass(cpar, B, cb);
+          else B = contact_solve_mass(cpar, B, cb);
+          mt[i0] = B.vx; mt[i1] = B.vy; mt[i2] = B.w;
+        }
+      } else {
+        SCon<real>& sc = item_scon(blk_sl, code);
+        if (MODE == ROUND_WARM) self_warm(cpar, sc, mt, mts, ow);
+        else if (MODE == ROUND_VELOCITY) self_solve(cpar, sc, mt, mts, ow);
+        else {
+          const real ms = self_position(cpar, sc, mt, mts, ow);
+          if (ms < real(-3) * cpar.lin_tol) aux[bdim + ow] = real(1);
+        }
+      }
+    }
+    lo = hi;
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- springs
 // The 18 DistanceJoints of a voxel, indices as in `allSpringJoints` (Voxel.java:303-470).
 // Listed in the canonical SOLVE order: inside a voxel the sweep alternates the perfect matchings
@@ -1013,9 +1087,9 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // ---------------------------------------------------------------- the episode kernel
 #ifndef VSR_MAX_THREADS
 #define VSR_MAX_THREADS 384
-// reals of shared memory per warp for the contact exchange: 16 fields x 32 (mass table; the
-// ground-contact exchange uses the first 8) + the 32-entry work list
-#define VSR_XB_STRIDE 544
+// reals of shared memory reserved for the header of the block's contact list
+#define VSR_LHD_REALS 48
+#define VSR_MAX_LEVELS 32
 #endif
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
@@ -1045,23 +1119,25 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
   real* sgam = reinterpret_cast<real*>(spr2 + 18 * SPR_STRIDE);               // [18][SPR_STRIDE], effective-mass mode only
   real* stage = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)wib * P.smem_per_warp;
-  // contact exchange: the contact masses of a warp are solved one per lane; their owners post the
-  // mass state here ([field][item], conflict-free for the solving lanes) and read the result back
-  real* xb = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp + (size_t)wib * VSR_XB_STRIDE;
-  int* wl = reinterpret_cast<int*>(xb + 512);  // work list: (owner lane << 3) | (mass << 1) | buffer
-#define XB(j, item) xb[(j) * 32 + (item)]
+  // Contact exchange, block-wide.  Contacts are sparse and irregular (a few masses of a robot touch
+  // the ground or each other), so the block pools them: every thread posts the state of its masses
+  // in the mass table mt[16 fields][MTS threads] (see VSR_MTI), the block's constraints -- listed
+  // once per tick in `items`, ordered by dependency level -- are solved one per thread, and the
+  // owners read their masses back.
+  constexpr int MTS = SPR_STRIDE;  // the largest block of this instantiation
+  constexpr int mts = MTS;
+  real* const mt = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp;
+  // list header: [0] ground items, [1] levels, [2..33] end offset of each level, [34..] scratch
+  int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS);
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
-  real* const ex = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * (P.smem_per_warp + VSR_XB_STRIDE);
-  // mass table of the intra-robot contacts ([16 fields][scope threads], see VSR_MTI): the warp's
-  // exchange region (the ground-contact exchange is dead while it is in use), or block-wide for
-  // a big robot; + per-voxel bounding data (centre x, y, radius) for the pair pruning
-  constexpr int MTS = BLK ? 128 : 32;
-  real* const mt = BLK ? ex + 2 * 20 * 128 : xb;
-  real* const vxb = BLK ? mt + 16 * 128 : stage;
-  int* const bsc = reinterpret_cast<int*>(mt + 19 * 128);  // BLK: per-warp counts for the block-wide scan
-  const int mt_t = BLK ? tid : lane;
-#define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
+  real* const ex = mt + 16 * MTS + VSR_LHD_REALS;
   real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
+  // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
+  real* const aux = stage_blk;
+  const int bdim = blockDim.x;
+  int* const items = P.lbuf + (size_t)blockIdx.x * 8 * MTS;
+  const int mt_t = tid;
+#define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
   int exsel = 0;
 #define EXP(slot_, value_) if (BLK) ex[(exsel * 20 + (slot_)) * 128 + tid] = (value_);
 #define EXSYNC() if (BLK) __syncthreads();
@@ -1148,28 +1224,13 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
     for (int k = 0; k < 4; k++) hint[k] = 0;
     unsigned cmask = 0;  // masses with ground constraints
-    int n_items = 0, item_base = 0;  // this warp's contact masses / this lane's first slot
-    bool xmode = true;               // all of them fit one round of 32 lanes
-    CBody<real>* cbp = nullptr;      // the contact mass this lane solves
     // intra-robot contacts owned by this thread: two lists (this step's / the previous step's) and,
-    // packed in one word, count (bits 0-3), position in the robot's solve order (4-15), the longest
-    // list of any robot in the scope (16-27) and the current list (31)
+    // packed in one word, count (bits 0-3) and the current list (31)
     SList<real>* const sbase = reinterpret_cast<SList<real>*>(P.sbuf) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     unsigned sst = 0;
 #define S_N ((int)(sst & 15u))
-#define S_START ((int)((sst >> 4) & 0xfffu))
-#define S_TOT ((int)((sst >> 16) & 0xfffu))
 #define S_CUR (sbase + (sst >> 31))
-// one constraint per robot and round, in the robot's order (Gauss-Seidel inside a robot)
-#define VSR_SELF_ROUNDS(GUARD, CALL)                                  \
-  for (int i_ = 0, tot_ = S_TOT; i_ < tot_; i_++) {                   \
-    const int li_ = i_ - S_START;                                     \
-    if ((GUARD) && li_ >= 0 && li_ < S_N) {                           \
-      SCon<real>& sc_ = S_CUR->c[li_];                                \
-      CALL;                                                           \
-    }                                                                 \
-    SSYNC()                                                           \
-  }
+#define VSR_MTK(k, c) (((k) * 4 + (c)) * MTS + mt_t)
 #define VSR_MT_PUT(a0, a1, a2)                                                                     \
   _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                  \
     mt[VSR_MTK(k, 0)] = a0[k]; mt[VSR_MTK(k, 1)] = a1[k]; mt[VSR_MTK(k, 2)] = a2[k];               \
@@ -1178,7 +1239,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                  \
     a0[k] = mt[VSR_MTK(k, 0)]; a1[k] = mt[VSR_MTK(k, 1)]; a2[k] = mt[VSR_MTK(k, 2)];               \
   }
-#define VSR_MTK(k, c) (((k) * 4 + (c)) * MTS + mt_t)
+    CBody<real>* const blk_cb = reinterpret_cast<CBody<real>*>(P.cbuf) + (size_t)blockIdx.x * blockDim.x * 8;
+    SList<real>* const blk_sl = reinterpret_cast<SList<real>*>(P.sbuf) + (size_t)blockIdx.x * blockDim.x * 2;
     int status = 0;
     real last_f = real(0), ar_energy = real(0), ctrl_energy = real(0);
     real readings[MAX_READ];
@@ -1186,6 +1248,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     for (int q = 0; q < MAX_READ; q++) readings[q] = real(0);
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
 
+    __syncthreads();
+    for (int q = tid; q < 34; q += bdim) lhd[q] = 0;  // no contacts yet
+    __syncthreads();
     for (int tick = 0; tick < P.n_ticks; tick++) {
       if (sync_mode & 1) __syncthreads();
       // =========================== World.step(1) ===========================
@@ -1198,53 +1263,26 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         vy[k] *= lin_f;
         w[k] *= ang_f;
       }
-      // ---- intra-robot contacts: restitution bias from the velocities before any warm start
-      if (S_TOT > 0) {
+      // ---- contacts: SequentialImpulses.initialize.  The position-dependent half was done at
+      //      detection; here the restitution bias of every constraint from the velocities before
+      //      any warm start, then the warm starts.
+      const int n_lv = lhd[1];  // levels of this block's contact list (0: no contacts); block-uniform
+      if (n_lv > 0) {
         VSR_MT_PUT(vx, vy, w)
-        SSYNC()
-        for (int li = 0; li < S_N; li++) self_bias(cpar, S_CUR->c[li], mt, MTS, mt_t);
-        SSYNC()
-      }
-      // ---- contacts: initialise + warm start
-#define VSR_SLOT(k) (item_base + __popc(cmask & ((1u << (k)) - 1u)))
-      if (n_items > 0 && xmode) {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (cmask & (1u << k)) {
-            const int sl = VSR_SLOT(k);
-            XB(0, sl) = x[k]; XB(1, sl) = y[k]; XB(2, sl) = cs_[k]; XB(3, sl) = sn_[k];
-            XB(4, sl) = vx[k]; XB(5, sl) = vy[k]; XB(6, sl) = w[k];
-          }
-        __syncwarp();
-        if (lane < n_items) {
-          BodyState<real> B = {XB(0, lane), XB(1, lane), real(0), XB(4, lane), XB(5, lane), XB(6, lane)};
-          B = contact_init_mass(cpar, B, XB(2, lane), XB(3, lane), *cbp);
-          XB(4, lane) = B.vx; XB(5, lane) = B.vy; XB(6, lane) = B.w;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (cmask & (1u << k)) {
-            const int sl = VSR_SLOT(k);
-            vx[k] = XB(4, sl); vy[k] = XB(5, sl); w[k] = XB(6, sl);
-          }
-      } else if (cmask) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (cmask & (1u << k)) {
-            BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-            B = contact_init_mass(cpar, B, cs_[k], sn_[k], CBODY(k));
-            vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
+        __syncthreads();
+        for (int i_ = tid, hi_ = lhd[2 + n_lv - 1]; i_ < hi_; i_ += bdim) {
+          const int code = items[i_];
+          const int ow = VSR_ITEM_OWNER(code);
+          if (VSR_ITEM_GROUND(code)) {
+            const int km = VSR_ITEM_MASS(code);
+            contact_bias_mass(cpar, mt[VSR_MTI(km, 0, ow)], mt[VSR_MTI(km, 1, ow)], mt[VSR_MTI(km, 2, ow)], item_cbody(blk_cb, code));
+          } else {
+            self_bias(cpar, item_scon(blk_sl, code), mt, MTS, ow);
           }
         }
-      }
-      if (S_TOT > 0) {  // warm start of the intra-robot constraints, after the ground's
-        if (!BLK) __syncwarp();
-        VSR_MT_PUT(vx, vy, w)
-        SSYNC()
-        VSR_SELF_ROUNDS(true, self_warm(cpar, sc_, mt, MTS, mt_t))
+        __syncthreads();
+        contact_rounds<ROUND_WARM>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
         VSR_MT_GET(vx, vy, w)
-        if (!BLK) __syncwarp();
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
       real ch[4], sh[4];
@@ -1425,43 +1463,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #undef VSR_WELD_VEL_B2
 
         if (sync_mode & 8) __syncthreads();
-        if (n_items > 0 && xmode) {
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (cmask & (1u << k)) {
-              const int sl = VSR_SLOT(k);
-              XB(4, sl) = vx[k]; XB(5, sl) = vy[k]; XB(6, sl) = w[k];
-            }
-          __syncwarp();
-          if (lane < n_items) {
-            BodyState<real> B = {real(0), real(0), real(0), XB(4, lane), XB(5, lane), XB(6, lane)};
-            B = contact_solve_mass(cpar, B, *cbp);
-            XB(4, lane) = B.vx; XB(5, lane) = B.vy; XB(6, lane) = B.w;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (cmask & (1u << k)) {
-              const int sl = VSR_SLOT(k);
-              vx[k] = XB(4, sl); vy[k] = XB(5, sl); w[k] = XB(6, sl);
-            }
-        } else if (cmask) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (cmask & (1u << k)) {
-              BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-              B = contact_solve_mass(cpar, B, CBODY(k));
-              vx[k] = B.vx; vy[k] = B.vy; w[k] = B.w;
-            }
-          }
-        }
-        if (S_TOT > 0) {  // then the intra-robot constraints, one per robot at a time
-          if (!BLK) __syncwarp();
+        // contacts (SequentialImpulses.solveVelocityConstraints), pooled over the block
+        if (n_lv > 0) {
           VSR_MT_PUT(vx, vy, w)
-          SSYNC()
-          VSR_SELF_ROUNDS(true, self_solve(cpar, sc_, mt, MTS, mt_t))
+          __syncthreads();
+          contact_rounds<ROUND_VELOCITY>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
           VSR_MT_GET(vx, vy, w)
-          if (!BLK) __syncwarp();
         }
       }
 
@@ -1490,72 +1497,25 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       {
         bool done = BLK ? !(rb < P.n_robots) : !active;  // BLK: idle threads follow their block
         for (int it = 0; it < P.pos_iters; it++) {
-          if (BLK ? done : (bool)__all_sync(0xffffffffu, done)) break;  // BLK: done is block-uniform
+          // with contacts in the block every warp stays for the block-wide rounds until the last
+          // robot of the block is done; without, a warp leaves as soon as its robots are
+          const bool wdone = BLK ? done : (bool)__all_sync(0xffffffffu, done);
+          if (n_lv > 0 ? (bool)__syncthreads_and(done) : wdone) break;
           bool solved = true;
-          if (n_items > 0 && xmode) {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              if (cmask & (1u << k)) {
-                const int sl = VSR_SLOT(k);
-                XB(0, sl) = x[k]; XB(1, sl) = y[k]; XB(2, sl) = th[k]; XB(7, sl) = done ? real(1) : real(0);
-              }
-            __syncwarp();
-            if (lane < n_items) {
-              real ms = real(0);
-              if (XB(7, lane) == real(0)) {
-                BodyState<real> B = {XB(0, lane), XB(1, lane), XB(2, lane), real(0), real(0), real(0)};
-                B = contact_position_mass(cpar, B, *cbp, ms);
-                XB(0, lane) = B.x; XB(1, lane) = B.y; XB(2, lane) = B.th;
-              }
-              XB(3, lane) = ms;
-            }
-            __syncwarp();
-            if (!done && cmask) {
-              real minSep = real(0);
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-                if (cmask & (1u << k)) {
-                  const int sl = VSR_SLOT(k);
-                  x[k] = XB(0, sl); y[k] = XB(1, sl); th[k] = XB(2, sl);
-                  const real ms = XB(3, sl);
-                  minSep = ms < minSep ? ms : minSep;
-                  if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
-                }
-              solved = minSep >= real(-3) * P.lin_tol;
-            }
-            __syncwarp();
-          } else if (!done && cmask) {
-            real minSep = real(0);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              if (cmask & (1u << k)) {
-                BodyState<real> B = {x[k], y[k], th[k], vx[k], vy[k], w[k]};
-                real ms;
-                B = contact_position_mass(cpar, B, CBODY(k), ms);
-                minSep = ms < minSep ? ms : minSep;
-                x[k] = B.x; y[k] = B.y; th[k] = B.th;
-                if (k == 1 || k == 2) r_sincos(th[k], &sn_[k], &cs_[k]);
-              }
-            }
-            solved = minSep >= real(-3) * P.lin_tol;
-          }
-          if (S_TOT > 0) {
-            if (!BLK) __syncwarp();
+          if (n_lv > 0) {
             VSR_MT_PUT(x, y, th)
-            SSYNC()
-            real sms = real(0);
-            VSR_SELF_ROUNDS(!done, {
-              const real ms_ = self_position(cpar, sc_, mt, MTS, mt_t);
-              sms = ms_ < sms ? ms_ : sms;
-            })
+            aux[0 * bdim + tid] = done ? real(1) : real(0);
+            aux[1 * bdim + tid] = real(0);
+            __syncthreads();
+            contact_rounds<ROUND_POSITION>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
             if (!done) {
               VSR_MT_GET(x, y, th)
               r_sincos(th[1], &sn_[1], &cs_[1]);
               r_sincos(th[2], &sn_[2], &cs_[2]);
-              solved = solved && (sms >= real(-3) * P.lin_tol);
+              solved = aux[1 * bdim + tid] == real(0);
             }
-            if (!BLK) __syncwarp();
           }
+          if (!wdone) {
           // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)
 #define VSR_PUBLISH_P()                                                                       \
   EXP(0, x[0]) EXP(1, y[0]) EXP(2, th[0]) EXP(3, x[1]) EXP(4, y[1]) EXP(5, th[1])                  \
@@ -1625,6 +1585,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           // masses 1, 2 are body2 of the next iteration's horizontal welds
           r_sincos(th[1], &sn_[1], &cs_[1]);
           r_sincos(th[2], &sn_[2], &cs_[2]);
+          }  // !wdone
           // robot-wide (island-wide) vote
           if (BLK) {
             if (__syncthreads_and(solved || done)) done = true;
@@ -1647,7 +1608,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           // cheap reject: far above the highest point of the terrain near this mass
           int cn = 0;
           int ov = detect_mass(tpar, x[k], y[k], cs_[k], sn_[k], hint[k], CBODY(k), (int)((old_cmask >> k) & 1u),
-                               cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn);
+                               cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn, im, ii);
           flip ^= 1u << k;
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
           if (cn > 0) cmask |= 1u << k;
@@ -1668,8 +1629,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       // ---- intra-robot pairs: every mass against every later mass of the robot that is not welded
       //      to it.  Order inside a robot = (owner voxel, partner voxel, partner mass, own mass),
       //      the oracle's canonical enumeration.
+      const int rbase = BLK ? 0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
+      int n_new = 0;
+      unsigned lvpack = 0;  // dependency level of each of this thread's constraints, 8 bits each
       if (P.self_coll) {
-        if (!BLK) __syncwarp();
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           mt[VSR_MTK(k, 0)] = x[k]; mt[VSR_MTK(k, 1)] = y[k]; mt[VSR_MTK(k, 2)] = cs_[k]; mt[VSR_MTK(k, 3)] = sn_[k];
@@ -1678,34 +1641,32 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         real vrad = real(0);
 #pragma unroll
         for (int k = 0; k < 4; k++) vrad = r_max(vrad, r_max(r_abs(x[k] - vcx), r_abs(y[k] - vcy)));
-        vxb[0 * MTS + mt_t] = vcx; vxb[1 * MTS + mt_t] = vcy; vxb[2 * MTS + mt_t] = vrad;
+        aux[0 * bdim + tid] = vcx; aux[1 * bdim + tid] = vcy; aux[2 * bdim + tid] = vrad;
         SSYNC()
-        int n_new = 0;
+        SCon<real>* const newc = (sbase + ((sst >> 31) ^ 1u))->c;
         if (active) {
           const int old_n = S_N;
           const SCon<real>* const oldc = S_CUR->c;
-          SCon<real>* const newc = (sbase + ((sst >> 31) ^ 1u))->c;
           const real rr = real(2.8284271247461903) * P.half;  // two half diagonals
           const int j_right = has[1] ? nl[1] - lane0 : -1, j_up = has[3] ? nl[3] - lane0 : -1;
           for (int j = v; j < nvox; j++) {
-            const int tj = lane0 + j;
+            const int tj = rbase + j;
             if (j != v) {
-              const real lim = vrad + vxb[2 * MTS + tj] + rr;
-              if (r_abs(vxb[0 * MTS + tj] - vcx) > lim || r_abs(vxb[1 * MTS + tj] - vcy) > lim) continue;
+              const real lim = vrad + aux[2 * bdim + tj] + rr;
+              if (r_abs(aux[0 * bdim + tj] - vcx) > lim || r_abs(aux[1 * bdim + tj] - vcy) > lim) continue;
             }
             // welded pairs, bit (own mass * 4 + partner mass): right neighbour 1-0, 2-3; upper 0-3, 1-2
             const unsigned wm = j == j_right ? ((1u << 4) | (1u << 11)) : (j == j_up ? ((1u << 3) | (1u << 6)) : 0u);
 #pragma unroll 1
             for (int kb = 0; kb < 4; kb++) {
-              const real bx = mt[((kb * 4 + 0) * MTS) + tj], by = mt[((kb * 4 + 1) * MTS) + tj];
+              const real bx = mt[VSR_MTI(kb, 0, tj)], by = mt[VSR_MTI(kb, 1, tj)];
 #pragma unroll
               for (int ka = 0; ka < 4; ka++) {
                 if (j == v && kb <= ka) continue;
                 if ((wm >> (ka * 4 + kb)) & 1u) continue;
                 if (r_abs(x[ka] - bx) > rr || r_abs(y[ka] - by) > rr) continue;
-                const int got = self_pair(cpar, P.half, x[ka], y[ka], cs_[ka], sn_[ka], bx, by,
-                                          mt[((kb * 4 + 2) * MTS) + tj], mt[((kb * 4 + 3) * MTS) + tj], ka, tj, kb, oldc,
-                                          old_n, &newc[n_new]);
+                const int got = self_pair(cpar, P.half, x[ka], y[ka], cs_[ka], sn_[ka], bx, by, mt[VSR_MTI(kb, 2, tj)],
+                                          mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_n, &newc[n_new]);
                 if (got) {
                   if (n_new == SC_CAP) status |= STATUS_CONTACT_OVERFLOW;
                   else n_new++;
@@ -1714,7 +1675,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
           }
         }
-        // position of this thread's constraints in its robot's order, and the longest robot list
+        // position of this thread's constraints in its robot's order
         int incl = n_new;
 #pragma unroll
         for (int d2 = 1; d2 < 32; d2 <<= 1) {
@@ -1723,11 +1684,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
         int s_start, s_tot;
         if (BLK) {
-          if (lane == 31) bsc[wib] = incl;
+          if (lane == 31) lhd[34 + wib] = incl;
           __syncthreads();
           int before = 0, all = 0;
           for (int q = 0; q < wpb; q++) {
-            const int c = bsc[q];
+            const int c = lhd[34 + q];
             before += q < wib ? c : 0;
             all += c;
           }
@@ -1741,33 +1702,70 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           s_start = incl - n_new - base;
           s_tot = (int)__reduce_max_sync(0xffffffffu, (unsigned)(lane_ok ? upto - base : 0));
         }
-        sst = (unsigned)n_new | ((unsigned)s_start << 4) | ((unsigned)s_tot << 16) | ((sst ^ 0x80000000u) & 0x80000000u);
+        // dependency levels: a constraint runs one round after the last earlier constraint that
+        // touches one of its two masses (ground constraints of a mass count as round 0).  Walk the
+        // robot's list in order, one constraint at a time; the counters replace the mass table.
         SSYNC()
+        real* const cnt = mt;  // small integers held as reals: each thread keeps to its own columns
+#pragma unroll
+        for (int k = 0; k < 4; k++) cnt[k * MTS + tid] = (real)((cmask >> k) & 1u);
+        SSYNC()
+        for (int i = 0; i < s_tot; i++) {
+          const int li = i - s_start;
+          if (li >= 0 && li < n_new) {
+            const int ia = newc[li].ka * MTS + tid, ib = newc[li].kb * MTS + newc[li].tb;
+            const int ca = (int)cnt[ia], cb2 = (int)cnt[ib];
+            int lv = ca > cb2 ? ca : cb2;
+            cnt[ia] = (real)(lv + 1);
+            cnt[ib] = (real)(lv + 1);
+            if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_CONTACT_OVERFLOW; }
+            lvpack |= (unsigned)lv << (8 * li);
+          }
+          SSYNC()
+        }
+        sst = (unsigned)n_new | ((sst ^ 0x80000000u) & 0x80000000u);
       }
 
-      // ---- work list of this warp's contact masses (one per lane from the next tick on)
+      // ---- the block's contact list for the next step: ground items, then the intra-robot
+      //      constraints by level
       {
-        const int cnt = __popc(cmask);
-        int incl = cnt;
+        __syncthreads();
+        for (int q = tid; q < 34; q += bdim) lhd[q] = 0;
+        __syncthreads();
+        const int gc = __popc(cmask);
+        int gpos = 0;
+        if (gc) gpos = atomicAdd(&lhd[0], gc);
+        int spos[SC_CAP];
 #pragma unroll
-        for (int d2 = 1; d2 < 32; d2 <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, d2);
-          if (lane >= d2) incl += t;
+        for (int li = 0; li < SC_CAP; li++) {
+          spos[li] = 0;
+          if (li < n_new) spos[li] = atomicAdd(&lhd[2 + ((lvpack >> (8 * li)) & 255u)], 1);
         }
-        item_base = incl - cnt;
-        n_items = __shfl_sync(0xffffffffu, incl, 31);
-        xmode = n_items <= 32;
-        if (n_items > 0 && xmode) {
-          __syncwarp();
+        __syncthreads();
+        if (tid == 0) {
+          int run = lhd[0], nl_ = run > 0 ? 1 : 0;
+          for (int l = 0; l < VSR_MAX_LEVELS; l++) {
+            const int c = lhd[2 + l];
+            run += c;
+            lhd[2 + l] = run;  // end offset of level l
+            if (c > 0) nl_ = l + 1;
+          }
+          lhd[1] = nl_;
+        }
+        __syncthreads();
+        if (gc) {
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            if (cmask & (1u << k)) wl[VSR_SLOT(k)] = (lane << 3) | (k << 1) | (int)((flip >> k) & 1u);
-          __syncwarp();
-          if (lane < n_items) {
-            const int code = wl[lane];
-            cbp = reinterpret_cast<CBody<real>*>(P.cbuf) + ((size_t)blockIdx.x * blockDim.x + (size_t)wib * 32 + (code >> 3)) * 8 + (code & 7);
-          }
+            if (cmask & (1u << k)) items[gpos++] = (tid << 5) | (k << 2) | (int)(((flip >> k) & 1u) << 1);
         }
+#pragma unroll
+        for (int li = 0; li < SC_CAP; li++)
+          if (li < n_new) {
+            const int lv = (int)((lvpack >> (8 * li)) & 255u);
+            const int start = lv == 0 ? lhd[0] : lhd[2 + lv - 1];
+            items[start + spos[li]] = (tid << 5) | (int)((sst >> 31) << 4) | (li << 1) | 1;
+          }
+        __syncthreads();
       }
 
       // =========================== Robot.act(t) ===========================

@@ -7,7 +7,7 @@ from oracle import oracle
 import helpers
 shape = sys.argv[1] if len(sys.argv) > 1 else "biped-4x3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-loco = helpers.locomotion(5.0)
+loco = helpers.locomotion(5.0, self_collision=int(os.environ.get("SELF", "1")))
 robots = helpers.phase_robots(n, shape=shape, seed=3)
 bd = loco.compile(robots, precision=1, trajectory_robots=n)
 res, tr = helpers.gpu_run(bd, trajectories=n)
@@ -24,7 +24,7 @@ for r in range(n):
             b = np.unravel_index(np.argmax(dd), dd.shape)
             print("   tick", k, "max %.3e at body %d comp %d" % (dd.max(), b[0], b[1]), "nc", pr["n_contacts"][r, k], "piters", pr["pos_iters"][r, k])
 r = 2
-for k in (45, 46, 47):
+for k in ():
     print("tick", k)
     for b in (2, 3, 10, 11):
         print("   body", b, "gpu", np.array2string(tr[r, k, b], precision=6), "\n           orc", np.array2string(otr[r, k, b], precision=6))
