@@ -677,9 +677,18 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
   // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
   const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
-  const size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
-                      ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + VSR_LHD_REALS) * sizeof(real) +
-                      (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
+  size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
+                ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + VSR_LHD_REALS) * sizeof(real) +
+                (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
+  {
+    // what is left of the SM's shared memory caches the block's contact constraints
+    const size_t limit = 227 * 1024;
+    long long cap = smem < limit ? (long long)((limit - smem) / (VSR_POOL_FIELDS * sizeof(real))) : 0;
+    cap = std::min<long long>(cap, (long long)12 * threads) / 32 * 32;
+    if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 32 * 32;
+    P.pool_cap = (int)cap;
+    smem += (size_t)cap * VSR_POOL_FIELDS * sizeof(real);
+  }
   P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
@@ -720,7 +729,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
       k.sbuf_bytes = need_s;
     }
     P.sbuf = k.d_sbuf;
-    size_t need_l = (size_t)grid * 8 * stride * sizeof(int);
+    size_t need_l = (size_t)grid * 12 * stride * sizeof(int);
     if (need_l > k.lbuf_bytes) {
       cudaFree(k.d_lbuf);
       k.d_lbuf = nullptr;

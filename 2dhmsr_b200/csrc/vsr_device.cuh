@@ -101,7 +101,8 @@ struct Params {
   int smem_per_warp;     // reals of staging per warp
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
-  int* lbuf;             // contact lists: [grid blocks][8 * max threads per block]
+  int* lbuf;             // contact lists: [grid blocks][12 * max threads per block]
+  int pool_cap;          // constraints of a block cached in shared memory (the rest stay in global)
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
@@ -159,44 +160,31 @@ template <typename real> struct Real2T;
 template <> struct Real2T<float> { typedef float2 type; };
 template <> struct Real2T<double> { typedef double2 type; };
 
-// ---------------------------------------------------------------- contacts (per mass)
-template <typename real>
-struct CPoint {
-  real px, py, depth, jn, jt;  // persistent (warm start by id)
-  int id;
-  real r1x, r1y, l1x, l1y, massN, massT, vb;  // per step
-};
-template <typename real>
-struct CCon {
-  int seg, n, block;
-  real nx, ny;  // manifold normal: from the mass to the ground
-  CPoint<real> p[2];
-  real K00, K01, K11, iK00, iK01, iK11;
-};
-template <typename real>
-struct CBody {
-  int n;
-  CCon<real> c[MAXC];
-};
-
-// intra-robot contacts (mass against mass, Voxel.java:178-185,474): owned by the thread of the
-// lower body index (ka = its mass), the partner is mass kb of thread tb
+// ---------------------------------------------------------------- contact constraints
+// One record type for both kinds: a mass against a ground segment (tb < 0; seg = the segment) and a
+// mass against another mass of the same robot (Voxel.java:178-185,474; owned by the thread of the
+// lower body index, ka = its mass; the partner is mass kb of block thread tb).
 #define SC_CAP 4
 template <typename real>
 struct SPoint {
-  real px, py, depth, jn, jt;
+  real px, py, depth, jn, jt;  // persistent (warm start by id)
   int id;
-  real r1x, r1y, r2x, r2y, l1x, l1y, l2x, l2y, massN, massT, vb;
+  real r1x, r1y, r2x, r2y, l1x, l1y, l2x, l2y, massN, massT, vb;  // per step
 };
 template <typename real>
 struct SCon {
-  int ka, tb, kb, n, block, pad;
-  real nx, ny;  // manifold normal: from the owner's mass to the partner
+  int ka, tb, kb, n, block, seg;
+  real nx, ny;  // manifold normal: from body 1 (the owner's mass) to body 2
   SPoint<real> p[2];
   real K00, K01, K11, iK00, iK01, iK11;
 };
 template <typename real>
-struct SList {
+struct CBody {  // ground constraints of one mass
+  int n;
+  SCon<real> c[MAXC];
+};
+template <typename real>
+struct SList {  // intra-robot constraints owned by one thread
   SCon<real> c[SC_CAP + 1];  // + one scratch entry (overflow probe)
 };
 
@@ -270,7 +258,7 @@ __device__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx
 // collision.
 template <typename real>
 __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real bs, real half, real x0, real y0,
-                                                 real x1, real y1, real base_y, int mm, CCon<real>& c) {
+                                                 real x1, real y1, real base_y, int mm, SCon<real>& c) {
   // exact geometric ties (a mass lying flat on a flat segment) are decided by rule, with this
   // margin, exactly as in the oracle: the mass' own face wins.
   // mm != 0: the second polygon is another mass, given as (x0, y0, x1, y1) = (centre, cos, sin);
@@ -368,7 +356,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   for (int i = 0; i < 2; i++) {
     real depth = fx * c2[i].x + fy * c2[i].y - fo;
     if (depth >= real(0)) {
-      CPoint<real>& p = c.p[c.n++];
+      SPoint<real>& p = c.p[c.n++];
       p.px = c2[i].x;
       p.py = c2[i].y;
       p.depth = depth;
@@ -393,7 +381,7 @@ struct TPar {
 template <typename real>
 __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, real bc, real bs, int& hint,
                                         const CBody<real>& old, int had_contact, CBody<real>& cb, int& n_out,
-                                        real im, real ii) {
+                                        real im, real ii, int k_mass) {
   real e = P.half * (r_abs(bc) + r_abs(bs));
   real xlo = bx - e, xhi = bx + e, ylo = by - e;
   int n = P.terr_n;
@@ -409,10 +397,11 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     if (x1 < xlo) continue;
     if (!(x1 > x0)) continue;
     if (ylo > r_max(y0, y1)) continue;
-    CCon<real> c;
+    SCon<real> c;
     if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, 0, c)) continue;
     if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
+    c.ka = k_mass; c.tb = -1; c.kb = 0;
     for (int i = 0; i < old_n; i++) {
       if (old.c[i].seg != seg) continue;
       for (int k = 0; k < c.n; k++)
@@ -428,11 +417,13 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     {
       const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
       for (int k = 0; k < c.n; k++) {
-        CPoint<real>& p = c.p[k];
+        SPoint<real>& p = c.p[k];
         p.r1x = p.px - bx;
         p.r1y = p.py - by;
         p.l1x = bc * p.r1x + bs * p.r1y;
         p.l1y = -bs * p.r1x + bc * p.r1y;
+        p.r2x = real(0); p.r2y = real(0);  // static body 2: never multiplied by anything but 0
+        p.l2x = p.px; p.l2y = p.py;        // ... at the origin, unrotated
         real rn1 = p.r1x * ny - p.r1y * nx;
         p.massN = real(1) / (im + ii * rn1 * rn1);
         real rt1 = p.r1x * ty - p.r1y * tx;
@@ -477,208 +468,302 @@ struct CPar {
   real mu_s, rest_e_s;  // mass against mass (CoefficientMixer: sqrt(f f), max(e, e))
 };
 
-// SequentialImpulses.initialize (dyn4j), the velocity-dependent half for the constraints of one
-// mass: the restitution bias, from the velocities before any warm start.
+// ---------------------------------------------------------------- constraints: the solver's view
+// One record type serves both kinds of contact constraint (SCon): a mass against a ground segment
+// (tb < 0: body 2 is static, invM2 = invI2 = 0 -- exactly how the oracle solves it, with its
+// STATIC_BODY) and a mass against another mass of the robot.  The mass table `mt` is the block's
+// shared-memory exchange: mt[(k * 4 + c) * mts + t] = component c of mass k of thread t;
+// components are (x, y, cos, sin) during detection, (vx, vy, w) in the velocity phases and
+// (x, y, theta) in the position phase.
+#define VSR_MTI(k, c, t) (((k) * 4 + (c)) * mts + (t))
+
+// what the velocity phases need of one constraint, in registers
 template <typename real>
-__device__ __noinline__ void contact_bias_mass(const CPar<real> P, real vx, real vy, real w, CBody<real>& cb) {
-  for (int q = 0; q < cb.n; q++) {
-    CCon<real>& c = cb.c[q];
-    const real nx = c.nx, ny = c.ny;
-    for (int k = 0; k < c.n; k++) {
-      CPoint<real>& p = c.p[k];
-      real rvx = -(vx - w * p.r1y), rvy = -(vy + w * p.r1x);
-      real rvn = nx * rvx + ny * rvy;
-      real vb = real(0);
-      if (rvn < -P.rest_vel) vb += -P.rest_e * rvn;
-      p.vb = vb;
-    }
+struct ConVel {
+  int n, block, ka, kb, tb;
+  real nx, ny;
+  real r1x[2], r1y[2], r2x[2], r2y[2], mN[2], mT[2], vb[2], jn[2], jt[2];
+  real K00, K01, K11, iK00, iK01, iK11;
+};
+// ... and the position phase
+template <typename real>
+struct ConPos {
+  int n, ka, kb, tb;
+  real nx, ny;
+  real l1x[2], l1y[2], l2x[2], l2y[2], depth[2];
+};
+#define VSR_POOL_FIELDS 27
+template <typename real>
+__device__ __forceinline__ int con_hdr(const SCon<real>& c) {
+  return c.n | (c.block << 2) | (c.ka << 4) | (c.kb << 6) | ((c.tb + 1) << 8);
+}
+#define VSR_HDR_UNPACK(d, h) \
+  d.n = (h) & 3; d.ka = ((h) >> 4) & 3; d.kb = ((h) >> 6) & 3; d.tb = ((h) >> 8) - 1;
+
+template <typename real>
+__device__ __forceinline__ ConVel<real> con_vel_from_record(const SCon<real>& c) {
+  ConVel<real> d;
+  d.n = c.n; d.block = c.block; d.ka = c.ka; d.kb = c.kb; d.tb = c.tb;
+  d.nx = c.nx; d.ny = c.ny;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    d.r1x[k] = c.p[k].r1x; d.r1y[k] = c.p[k].r1y; d.r2x[k] = c.p[k].r2x; d.r2y[k] = c.p[k].r2y;
+    d.mN[k] = c.p[k].massN; d.mT[k] = c.p[k].massT; d.vb[k] = c.p[k].vb;
+    d.jn[k] = c.p[k].jn; d.jt[k] = c.p[k].jt;
+  }
+  d.K00 = c.K00; d.K01 = c.K01; d.K11 = c.K11; d.iK00 = c.iK00; d.iK01 = c.iK01; d.iK11 = c.iK11;
+  return d;
+}
+// pool[field * cap + slot]: the block's constraints of this tick, cached in shared memory
+template <typename real>
+__device__ __forceinline__ void con_vel_to_pool(const ConVel<real>& d, real* pool, int cap, int s) {
+  reinterpret_cast<int*>(pool)[s * (int)(sizeof(real) / 4)] = d.n | (d.block << 2) | (d.ka << 4) | (d.kb << 6) | ((d.tb + 1) << 8);
+  pool[1 * cap + s] = d.nx; pool[2 * cap + s] = d.ny;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int f = 3 + 9 * k;
+    pool[(f + 0) * cap + s] = d.r1x[k]; pool[(f + 1) * cap + s] = d.r1y[k]; pool[(f + 2) * cap + s] = d.r2x[k];
+    pool[(f + 3) * cap + s] = d.r2y[k]; pool[(f + 4) * cap + s] = d.mN[k]; pool[(f + 5) * cap + s] = d.mT[k];
+    pool[(f + 6) * cap + s] = d.vb[k]; pool[(f + 7) * cap + s] = d.jn[k]; pool[(f + 8) * cap + s] = d.jt[k];
+  }
+  pool[21 * cap + s] = d.K00; pool[22 * cap + s] = d.K01; pool[23 * cap + s] = d.K11;
+  pool[24 * cap + s] = d.iK00; pool[25 * cap + s] = d.iK01; pool[26 * cap + s] = d.iK11;
+}
+template <typename real>
+__device__ __forceinline__ ConVel<real> con_vel_from_pool(const real* pool, int cap, int s) {
+  ConVel<real> d;
+  const int h = reinterpret_cast<const int*>(pool)[s * (int)(sizeof(real) / 4)];
+  VSR_HDR_UNPACK(d, h)
+  d.block = (h >> 2) & 1;
+  d.nx = pool[1 * cap + s]; d.ny = pool[2 * cap + s];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int f = 3 + 9 * k;
+    d.r1x[k] = pool[(f + 0) * cap + s]; d.r1y[k] = pool[(f + 1) * cap + s]; d.r2x[k] = pool[(f + 2) * cap + s];
+    d.r2y[k] = pool[(f + 3) * cap + s]; d.mN[k] = pool[(f + 4) * cap + s]; d.mT[k] = pool[(f + 5) * cap + s];
+    d.vb[k] = pool[(f + 6) * cap + s]; d.jn[k] = pool[(f + 7) * cap + s]; d.jt[k] = pool[(f + 8) * cap + s];
+  }
+  d.K00 = pool[21 * cap + s]; d.K01 = pool[22 * cap + s]; d.K11 = pool[23 * cap + s];
+  d.iK00 = pool[24 * cap + s]; d.iK01 = pool[25 * cap + s]; d.iK11 = pool[26 * cap + s];
+  return d;
+}
+template <typename real>
+__device__ __forceinline__ ConPos<real> con_pos_from_record(const SCon<real>& c) {
+  ConPos<real> d;
+  d.n = c.n; d.ka = c.ka; d.kb = c.kb; d.tb = c.tb;
+  d.nx = c.nx; d.ny = c.ny;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    d.l1x[k] = c.p[k].l1x; d.l1y[k] = c.p[k].l1y; d.l2x[k] = c.p[k].l2x; d.l2y[k] = c.p[k].l2y;
+    d.depth[k] = c.p[k].depth;
+  }
+  return d;
+}
+template <typename real>
+__device__ __forceinline__ void con_pos_to_pool(const ConPos<real>& d, real* pool, int cap, int s) {
+  reinterpret_cast<int*>(pool)[s * (int)(sizeof(real) / 4)] = d.n | (d.ka << 4) | (d.kb << 6) | ((d.tb + 1) << 8);
+  pool[1 * cap + s] = d.nx; pool[2 * cap + s] = d.ny;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int f = 3 + 5 * k;
+    pool[(f + 0) * cap + s] = d.l1x[k]; pool[(f + 1) * cap + s] = d.l1y[k]; pool[(f + 2) * cap + s] = d.l2x[k];
+    pool[(f + 3) * cap + s] = d.l2y[k]; pool[(f + 4) * cap + s] = d.depth[k];
   }
 }
-// ... and the warm start of those constraints
 template <typename real>
-__device__ __noinline__ BodyState<real> contact_warm_mass(const CPar<real> P, BodyState<real> B, const CBody<real>& cb) {
-  const real im = P.im, ii = P.ii;
-  for (int q = 0; q < cb.n; q++) {
-    const CCon<real>& c = cb.c[q];
-    real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-    for (int k = 0; k < c.n; k++) {
-      const CPoint<real>& p = c.p[k];
-      real Px = nx * p.jn + tx * p.jt, Py = ny * p.jn + ty * p.jt;
-      B.vx -= im * Px;
-      B.vy -= im * Py;
-      B.w -= ii * (p.r1x * Py - p.r1y * Px);
-    }
+__device__ __forceinline__ ConPos<real> con_pos_from_pool(const real* pool, int cap, int s) {
+  ConPos<real> d;
+  const int h = reinterpret_cast<const int*>(pool)[s * (int)(sizeof(real) / 4)];
+  VSR_HDR_UNPACK(d, h)
+  d.nx = pool[1 * cap + s]; d.ny = pool[2 * cap + s];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int f = 3 + 5 * k;
+    d.l1x[k] = pool[(f + 0) * cap + s]; d.l1y[k] = pool[(f + 1) * cap + s]; d.l2x[k] = pool[(f + 2) * cap + s];
+    d.l2y[k] = pool[(f + 3) * cap + s]; d.depth[k] = pool[(f + 4) * cap + s];
   }
-  return B;
+  return d;
 }
 
-// SequentialImpulses.solveVelocityConstraints (dyn4j) for the constraints of one mass.
-// Runs 10x per tick on a few lanes, i.e. latency bound: every field is loaded up front (the
-// loads are independent; interleaved with the stores to the same struct the compiler would
-// have to serialise them), then the arithmetic chain, then the two or four stores.
+// the two bodies of a constraint (body 2 of a ground constraint: zeros, never written back)
 template <typename real>
-__device__ __noinline__ BodyState<real> contact_solve_mass(const CPar<real> P, BodyState<real> B, CBody<real>& cb) {
-  const real im = P.im, ii = P.ii;
-  const int ncon = cb.n;
-  for (int q = 0; q < ncon; q++) {
-    CCon<real>& c = cb.c[q];
-    // ---- loads
-    const int cn = c.n, blk = c.block;
-    const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-    const real r1x0 = c.p[0].r1x, r1y0 = c.p[0].r1y, mN0 = c.p[0].massN, mT0 = c.p[0].massT, vb0 = c.p[0].vb;
-    real jn0 = c.p[0].jn, jt0 = c.p[0].jt;
-    // the second point is read unconditionally (its slot exists; unused values are ignored)
-    const real r1x1 = c.p[1].r1x, r1y1 = c.p[1].r1y, mN1 = c.p[1].massN, mT1 = c.p[1].massT, vb1 = c.p[1].vb;
-    real jn1 = c.p[1].jn, jt1 = c.p[1].jt;
-    const real K00 = c.K00, K01 = c.K01, K11 = c.K11, iK00 = c.iK00, iK01 = c.iK01, iK11 = c.iK11;
-    const bool two = cn == 2;
-    // ---- friction of every point first
+struct Body2 {
+  real v1x, v1y, w1, v2x, v2y, w2;
+};
+template <typename real>
+__device__ __forceinline__ Body2<real> body2_load(const real* mt, int mts, int ta, int ka, int tb, int kb) {
+  Body2<real> B;
+  B.v1x = mt[VSR_MTI(ka, 0, ta)]; B.v1y = mt[VSR_MTI(ka, 1, ta)]; B.w1 = mt[VSR_MTI(ka, 2, ta)];
+  const bool gnd = tb < 0;
+  const int t2 = gnd ? ta : tb;
+  B.v2x = gnd ? real(0) : mt[VSR_MTI(kb, 0, t2)];
+  B.v2y = gnd ? real(0) : mt[VSR_MTI(kb, 1, t2)];
+  B.w2 = gnd ? real(0) : mt[VSR_MTI(kb, 2, t2)];
+  return B;
+}
+template <typename real>
+__device__ __forceinline__ void body2_store(real* mt, int mts, int ta, int ka, int tb, int kb, const Body2<real>& B) {
+  mt[VSR_MTI(ka, 0, ta)] = B.v1x; mt[VSR_MTI(ka, 1, ta)] = B.v1y; mt[VSR_MTI(ka, 2, ta)] = B.w1;
+  if (tb >= 0) {
+    mt[VSR_MTI(kb, 0, tb)] = B.v2x; mt[VSR_MTI(kb, 1, tb)] = B.v2y; mt[VSR_MTI(kb, 2, tb)] = B.w2;
+  }
+}
+template <typename real>
+__device__ __forceinline__ void body2_apply(const real im, const real ii, const real im2, const real ii2, Body2<real>& B,
+                                            real r1x, real r1y, real r2x, real r2y, real Px, real Py) {
+  B.v1x -= im * Px; B.v1y -= im * Py; B.w1 -= ii * (r1x * Py - r1y * Px);
+  B.v2x += im2 * Px; B.v2y += im2 * Py; B.w2 += ii2 * (r2x * Py - r2y * Px);
+}
+
+// SequentialImpulses.initialize (dyn4j), the velocity-dependent half: the restitution bias, from
+// the velocities before any warm start (the position-dependent half is done at detection)
+template <typename real>
+__device__ __forceinline__ void con_bias(const CPar<real>& P, ConVel<real>& d, const Body2<real>& B) {
+  const real e = d.tb < 0 ? P.rest_e : P.rest_e_s;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    real rvx = (B.v2x - B.w2 * d.r2y[k]) - (B.v1x - B.w1 * d.r1y[k]);
+    real rvy = (B.v2y + B.w2 * d.r2x[k]) - (B.v1y + B.w1 * d.r1x[k]);
+    real rvn = d.nx * rvx + d.ny * rvy;
+    real vb = real(0);
+    if (rvn < -P.rest_vel) vb += -e * rvn;
+    d.vb[k] = vb;
+  }
+}
+// warm start
+template <typename real>
+__device__ __forceinline__ void con_warm(const CPar<real>& P, const ConVel<real>& d, Body2<real>& B) {
+  const real im2 = d.tb < 0 ? real(0) : P.im, ii2 = d.tb < 0 ? real(0) : P.ii;
+  const real nx = d.nx, ny = d.ny, tx = ny, ty = -nx;
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    if (k < d.n)
+      body2_apply(P.im, P.ii, im2, ii2, B, d.r1x[k], d.r1y[k], d.r2x[k], d.r2y[k], nx * d.jn[k] + tx * d.jt[k],
+                  ny * d.jn[k] + ty * d.jt[k]);
+}
+// SequentialImpulses.solveVelocityConstraints (dyn4j) for one constraint: friction of every point
+// first, then the normal constraint(s) (block solver for two points)
+template <typename real>
+__device__ __forceinline__ void con_solve(const CPar<real>& P, ConVel<real>& d, Body2<real>& B) {
+  const bool gnd = d.tb < 0;
+  const real im = P.im, ii = P.ii, im2 = gnd ? real(0) : im, ii2 = gnd ? real(0) : ii;
+  const real mu = gnd ? P.mu : P.mu_s;
+  const real nx = d.nx, ny = d.ny, tx = ny, ty = -nx;
+  const bool two = d.n == 2;
+#define VSR_RELV(k, rvx, rvy)                                        \
+  real rvx = (B.v2x - B.w2 * d.r2y[k]) - (B.v1x - B.w1 * d.r1y[k]);  \
+  real rvy = (B.v2y + B.w2 * d.r2x[k]) - (B.v1y + B.w1 * d.r1x[k]);
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k == 0 || two) {
+      VSR_RELV(k, rvx, rvy)
+      real tn = tx * rvx + ty * rvy;
+      real jt = d.mT[k] * (-tn);
+      real maxJt = mu * d.jn[k];
+      real J0 = d.jt[k];
+      d.jt[k] = r_max(-maxJt, r_min(J0 + jt, maxJt));
+      jt = d.jt[k] - J0;
+      body2_apply(im, ii, im2, ii2, B, d.r1x[k], d.r1y[k], d.r2x[k], d.r2y[k], tx * jt, ty * jt);
+    }
+  }
+  if (!two || !d.block) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (k == 0 || two) {
+        VSR_RELV(k, rvx, rvy)
+        real rvn = nx * rvx + ny * rvy;
+        real j = -d.mN[k] * (rvn - d.vb[k]);
+        real j0 = d.jn[k];
+        d.jn[k] = r_max(j0 + j, real(0));
+        j = d.jn[k] - j0;
+        body2_apply(im, ii, im2, ii2, B, d.r1x[k], d.r1y[k], d.r2x[k], d.r2y[k], nx * j, ny * j);
+      }
+    }
+  } else {
+    // 2-point block solver (the Box2D / dyn4j LCP enumeration)
+    real ax = d.jn[0], ay = d.jn[1];
+    real rvn1, rvn2;
     {
-      real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
-      real tn = tx * rvx + ty * rvy;
-      real jt = mT0 * (-tn);
-      real maxJt = P.mu * jn0;
-      real Jt0 = jt0;
-      jt0 = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
-      jt = jt0 - Jt0;
-      real Px = tx * jt, Py = ty * jt;
-      B.vx -= im * Px;
-      B.vy -= im * Py;
-      B.w -= ii * (r1x0 * Py - r1y0 * Px);
+      VSR_RELV(0, rvx, rvy)
+      rvn1 = nx * rvx + ny * rvy;
     }
-    if (two) {
-      real rvx = -(B.vx - B.w * r1y1), rvy = -(B.vy + B.w * r1x1);
-      real tn = tx * rvx + ty * rvy;
-      real jt = mT1 * (-tn);
-      real maxJt = P.mu * jn1;
-      real Jt0 = jt1;
-      jt1 = r_max(-maxJt, r_min(Jt0 + jt, maxJt));
-      jt = jt1 - Jt0;
-      real Px = tx * jt, Py = ty * jt;
-      B.vx -= im * Px;
-      B.vy -= im * Py;
-      B.w -= ii * (r1x1 * Py - r1y1 * Px);
+    {
+      VSR_RELV(1, rvx, rvy)
+      rvn2 = nx * rvx + ny * rvy;
     }
-    // ---- then the normal constraint(s)
-    if (!two || !blk) {
-      {
-        real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
-        real rvn = nx * rvx + ny * rvy;
-        real j = -mN0 * (rvn - vb0);
-        real j0 = jn0;
-        jn0 = r_max(j0 + j, real(0));
-        j = jn0 - j0;
-        real Px = nx * j, Py = ny * j;
-        B.vx -= im * Px;
-        B.vy -= im * Py;
-        B.w -= ii * (r1x0 * Py - r1y0 * Px);
-      }
-      if (two) {
-        real rvx = -(B.vx - B.w * r1y1), rvy = -(B.vy + B.w * r1x1);
-        real rvn = nx * rvx + ny * rvy;
-        real j = -mN1 * (rvn - vb1);
-        real j0 = jn1;
-        jn1 = r_max(j0 + j, real(0));
-        j = jn1 - j0;
-        real Px = nx * j, Py = ny * j;
-        B.vx -= im * Px;
-        B.vy -= im * Py;
-        B.w -= ii * (r1x1 * Py - r1y1 * Px);
-      }
-    } else {
-      // 2-point block solver (the Box2D / dyn4j LCP enumeration)
-      real ax = jn0, ay = jn1;
-      real rvx = -(B.vx - B.w * r1y0), rvy = -(B.vy + B.w * r1x0);
-      real rvn1 = nx * rvx + ny * rvy;
-      rvx = -(B.vx - B.w * r1y1);
-      rvy = -(B.vy + B.w * r1x1);
-      real rvn2 = nx * rvx + ny * rvy;
-      real bx = rvn1 - vb0, by = rvn2 - vb1;
-      bx -= K00 * ax + K01 * ay;
-      by -= K01 * ax + K11 * ay;
-      real x = -(iK00 * bx + iK01 * by), y = -(iK01 * bx + iK11 * by);
-      bool ok = (x >= real(0) && y >= real(0));
-      if (!ok) {
-        x = -mN0 * bx;
-        y = real(0);
-        real v2 = K01 * x + by;
-        ok = (x >= real(0) && v2 >= real(0));
-      }
-      if (!ok) {
-        x = real(0);
-        y = -mN1 * by;
-        real v1 = K01 * y + bx;
-        ok = (y >= real(0) && v1 >= real(0));
-      }
-      if (!ok) {
-        x = real(0);
-        y = real(0);
-        ok = (bx >= real(0) && by >= real(0));
-      }
-      if (ok) {
-        real dx = x - ax, dy = y - ay;
-        real Px = nx * dx, Py = ny * dx;
-        B.vx -= im * Px;
-        B.vy -= im * Py;
-        B.w -= ii * (r1x0 * Py - r1y0 * Px);
-        Px = nx * dy;
-        Py = ny * dy;
-        B.vx -= im * Px;
-        B.vy -= im * Py;
-        B.w -= ii * (r1x1 * Py - r1y1 * Px);
-        jn0 = x;
-        jn1 = y;
-      }
+    real bx = rvn1 - d.vb[0], by = rvn2 - d.vb[1];
+    bx -= d.K00 * ax + d.K01 * ay;
+    by -= d.K01 * ax + d.K11 * ay;
+    real x = -(d.iK00 * bx + d.iK01 * by), y = -(d.iK01 * bx + d.iK11 * by);
+    bool ok = (x >= real(0) && y >= real(0));
+    if (!ok) {
+      x = -d.mN[0] * bx;
+      y = real(0);
+      real v2 = d.K01 * x + by;
+      ok = (x >= real(0) && v2 >= real(0));
     }
-    // ---- stores
-    c.p[0].jn = jn0;
-    c.p[0].jt = jt0;
-    if (two) {
-      c.p[1].jn = jn1;
-      c.p[1].jt = jt1;
+    if (!ok) {
+      x = real(0);
+      y = -d.mN[1] * by;
+      real v1 = d.K01 * y + bx;
+      ok = (y >= real(0) && v1 >= real(0));
+    }
+    if (!ok) {
+      x = real(0);
+      y = real(0);
+      ok = (bx >= real(0) && by >= real(0));
+    }
+    if (ok) {
+      real dx = x - ax, dy = y - ay;
+      body2_apply(im, ii, im2, ii2, B, d.r1x[0], d.r1y[0], d.r2x[0], d.r2y[0], nx * dx, ny * dx);
+      body2_apply(im, ii, im2, ii2, B, d.r1x[1], d.r1y[1], d.r2x[1], d.r2y[1], nx * dy, ny * dy);
+      d.jn[0] = x;
+      d.jn[1] = y;
     }
   }
-  return B;
+#undef VSR_RELV
 }
 
-// SequentialImpulses.solvePositionContraints (dyn4j) for one mass; returns min separation.
+// SequentialImpulses.solvePositionContraints (dyn4j) for one constraint; the table holds
+// (x, y, theta).  Returns the minimum separation seen.
 template <typename real>
-__device__ __noinline__ BodyState<real> contact_position_mass(const CPar<real> P, BodyState<real> B, CBody<real>& cb,
-                                                              real& minSepOut) {
-  const real im = P.im, ii = P.ii;
+__device__ __forceinline__ real con_position(const CPar<real>& P, const ConPos<real>& d, real* mt, int mts, int ta) {
+  const bool gnd = d.tb < 0;
+  const int ka = d.ka, kb = d.kb, tb = gnd ? ta : d.tb;
+  real x1 = mt[VSR_MTI(ka, 0, ta)], y1 = mt[VSR_MTI(ka, 1, ta)], t1 = mt[VSR_MTI(ka, 2, ta)];
+  real x2 = gnd ? real(0) : mt[VSR_MTI(kb, 0, tb)], y2 = gnd ? real(0) : mt[VSR_MTI(kb, 1, tb)],
+       t2 = gnd ? real(0) : mt[VSR_MTI(kb, 2, tb)];
+  const real im = P.im, ii = P.ii, im2 = gnd ? real(0) : im, ii2 = gnd ? real(0) : ii;
+  const real nx = d.nx, ny = d.ny;
   real minSep = real(0);
-  for (int q = 0; q < cb.n; q++) {
-    CCon<real>& c = cb.c[q];
-    real nx = c.nx, ny = c.ny;
-    for (int k = 0; k < c.n; k++) {
-      CPoint<real>& p = c.p[k];
-      real bs, bc;
-      r_sincos(B.th, &bs, &bc);
-      real r1x = bc * p.l1x - bs * p.l1y, r1y = bs * p.l1x + bc * p.l1y;
-      real p1x = B.x + r1x, p1y = B.y + r1y;
-      real sep = (p.px - p1x) * nx + (p.py - p1y) * ny - p.depth;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k < d.n) {
+      real s1, c1, s2 = real(0), c2 = real(1);
+      r_sincos(t1, &s1, &c1);
+      if (!gnd) r_sincos(t2, &s2, &c2);
+      real r1x = c1 * d.l1x[k] - s1 * d.l1y[k], r1y = s1 * d.l1x[k] + c1 * d.l1y[k];
+      real r2x = c2 * d.l2x[k] - s2 * d.l2y[k], r2y = s2 * d.l2x[k] + c2 * d.l2y[k];
+      real p1x = x1 + r1x, p1y = y1 + r1y;
+      real p2x = x2 + r2x, p2y = y2 + r2y;
+      real sep = (p2x - p1x) * nx + (p2y - p1y) * ny - d.depth[k];
       minSep = sep < minSep ? sep : minSep;
       real cl = r_clamp<real>(sep + P.lin_tol, -P.max_corr, real(0));
       real cp = P.baumgarte * cl;
-      real rn1 = r1x * ny - r1y * nx;
-      real K = im + ii * rn1 * rn1;
+      real rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
+      real K = im + im2 + ii * rn1 * rn1 + ii2 * rn2 * rn2;
       real jp = -cp / K;
       real Jx = nx * jp, Jy = ny * jp;
-      B.x -= Jx * im;
-      B.y -= Jy * im;
-      B.th -= ii * (r1x * Jy - r1y * Jx);
+      x1 -= Jx * im; y1 -= Jy * im; t1 -= ii * (r1x * Jy - r1y * Jx);
+      x2 += Jx * im2; y2 += Jy * im2; t2 += ii2 * (r2x * Jy - r2y * Jx);
     }
   }
-  minSepOut = minSep;
-  return B;
+  mt[VSR_MTI(ka, 0, ta)] = x1; mt[VSR_MTI(ka, 1, ta)] = y1; mt[VSR_MTI(ka, 2, ta)] = t1;
+  if (!gnd) {
+    mt[VSR_MTI(kb, 0, tb)] = x2; mt[VSR_MTI(kb, 1, tb)] = y2; mt[VSR_MTI(kb, 2, tb)] = t2;
+  }
+  return minSep;
 }
-
-// ---------------------------------------------------------------- intra-robot contacts
-// The mass table `mt` is the shared-memory exchange of one robot scope (a warp, or the block of a
-// big robot): mt[(k * 4 + c) * mts + t] = component c of mass k of thread t.  Components are
-// (x, y, cos, sin) during detection, (vx, vy, w) in the velocity phases, (x, y, theta) in the
-// position phase.
-#define VSR_MTI(k, c, t) (((k) * 4 + (c)) * mts + (t))
 
 // Narrowphase for one candidate pair + ContactConstraint.update (warm start by point id) + the
 // position-dependent half of SequentialImpulses.initialize (the bodies do not move between this
@@ -687,10 +772,10 @@ template <typename real>
 __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, real ay, real ac, real as, real bx,
                                       real by, real bc, real bs, int ka, int tb, int kb, const SCon<real>* old,
                                       int old_n, SCon<real>* out) {
-  CCon<real> m;
+  SCon<real> m;
   if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, m)) return 0;
   SCon<real> c;
-  c.ka = ka; c.tb = tb; c.kb = kb; c.n = m.n; c.block = 0; c.pad = 0;
+  c.ka = ka; c.tb = tb; c.kb = kb; c.n = m.n; c.block = 0; c.seg = -1;
   c.nx = m.nx; c.ny = m.ny;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
@@ -747,247 +832,57 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
   return 1;
 }
 
-// the velocity-dependent half of SequentialImpulses.initialize: the restitution bias, from the
-// velocities before any warm start
+// ---------------------------------------------------------------- the block's constraint list
+// An item: (owner thread << 7) | kind-specific bits | kind.  Ground (kind 0): (mass * 2 + buffer)
+// << 4 | index << 1 -> the owner's CBody.  Intra-robot (kind 1): list << 4 | index << 1 -> the
+// owner's SList.
+#define VSR_ITEM_OWNER(code) ((code) >> 7)
 template <typename real>
-__device__ __noinline__ void self_bias(const CPar<real> P, SCon<real>& c, const real* mt, int mts, int ta) {
-  const int ka = c.ka, kb = c.kb, tb = c.tb;
-  const real v1x = mt[VSR_MTI(ka, 0, ta)], v1y = mt[VSR_MTI(ka, 1, ta)], w1 = mt[VSR_MTI(ka, 2, ta)];
-  const real v2x = mt[VSR_MTI(kb, 0, tb)], v2y = mt[VSR_MTI(kb, 1, tb)], w2 = mt[VSR_MTI(kb, 2, tb)];
-  const real nx = c.nx, ny = c.ny;
-  for (int k = 0; k < c.n; k++) {
-    SPoint<real>& p = c.p[k];
-    real rvx = (v2x - w2 * p.r2y) - (v1x - w1 * p.r1y);
-    real rvy = (v2y + w2 * p.r2x) - (v1y + w1 * p.r1x);
-    real rvn = nx * rvx + ny * rvy;
-    real vb = real(0);
-    if (rvn < -P.rest_vel) vb += -P.rest_e_s * rvn;
-    p.vb = vb;
-  }
-}
-
-template <typename real>
-struct Body2 {
-  real v1x, v1y, w1, v2x, v2y, w2;
-};
-template <typename real>
-__device__ __forceinline__ void body2_apply(const real im, const real ii, Body2<real>& B, real r1x, real r1y, real r2x,
-                                            real r2y, real Px, real Py) {
-  B.v1x -= im * Px; B.v1y -= im * Py; B.w1 -= ii * (r1x * Py - r1y * Px);
-  B.v2x += im * Px; B.v2y += im * Py; B.w2 += ii * (r2x * Py - r2y * Px);
-}
-#define VSR_B2_LOAD()                                                                              \
-  const int ka = c.ka, kb = c.kb, tb = c.tb;                                                       \
-  Body2<real> B = {mt[VSR_MTI(ka, 0, ta)], mt[VSR_MTI(ka, 1, ta)], mt[VSR_MTI(ka, 2, ta)],         \
-                   mt[VSR_MTI(kb, 0, tb)], mt[VSR_MTI(kb, 1, tb)], mt[VSR_MTI(kb, 2, tb)]};
-#define VSR_B2_STORE()                                                                             \
-  mt[VSR_MTI(ka, 0, ta)] = B.v1x; mt[VSR_MTI(ka, 1, ta)] = B.v1y; mt[VSR_MTI(ka, 2, ta)] = B.w1;   \
-  mt[VSR_MTI(kb, 0, tb)] = B.v2x; mt[VSR_MTI(kb, 1, tb)] = B.v2y; mt[VSR_MTI(kb, 2, tb)] = B.w2;
-
-// warm start of one mass-mass constraint
-template <typename real>
-__device__ __noinline__ void self_warm(const CPar<real> P, SCon<real>& c, real* mt, int mts, int ta) {
-  VSR_B2_LOAD()
-  const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-  for (int k = 0; k < c.n; k++) {
-    const SPoint<real>& p = c.p[k];
-    body2_apply(P.im, P.ii, B, p.r1x, p.r1y, p.r2x, p.r2y, nx * p.jn + tx * p.jt, ny * p.jn + ty * p.jt);
-  }
-  VSR_B2_STORE()
-}
-
-// SequentialImpulses.solveVelocityConstraints (dyn4j) for one mass-mass constraint
-template <typename real>
-__device__ __noinline__ void self_solve(const CPar<real> P, SCon<real>& c, real* mt, int mts, int ta) {
-  VSR_B2_LOAD()
-  const real im = P.im, ii = P.ii;
-  const int cn = c.n, blk = c.block;
-  const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-  const SPoint<real> p0 = c.p[0], p1 = c.p[1];
-  real jn0 = p0.jn, jt0 = p0.jt, jn1 = p1.jn, jt1 = p1.jt;
-  const bool two = cn == 2;
-#define VSR_RELV(p, rvx, rvy)                                   \
-  real rvx = (B.v2x - B.w2 * p.r2y) - (B.v1x - B.w1 * p.r1y);   \
-  real rvy = (B.v2y + B.w2 * p.r2x) - (B.v1y + B.w1 * p.r1x);
-  {
-    VSR_RELV(p0, rvx, rvy)
-    real tn = tx * rvx + ty * rvy;
-    real jt = p0.massT * (-tn);
-    real maxJt = P.mu_s * jn0;
-    real J0 = jt0;
-    jt0 = r_max(-maxJt, r_min(J0 + jt, maxJt));
-    jt = jt0 - J0;
-    body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, tx * jt, ty * jt);
-  }
-  if (two) {
-    VSR_RELV(p1, rvx, rvy)
-    real tn = tx * rvx + ty * rvy;
-    real jt = p1.massT * (-tn);
-    real maxJt = P.mu_s * jn1;
-    real J0 = jt1;
-    jt1 = r_max(-maxJt, r_min(J0 + jt, maxJt));
-    jt = jt1 - J0;
-    body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, tx * jt, ty * jt);
-  }
-  if (!two || !blk) {
-    {
-      VSR_RELV(p0, rvx, rvy)
-      real rvn = nx * rvx + ny * rvy;
-      real j = -p0.massN * (rvn - p0.vb);
-      real j0 = jn0;
-      jn0 = r_max(j0 + j, real(0));
-      j = jn0 - j0;
-      body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, nx * j, ny * j);
-    }
-    if (two) {
-      VSR_RELV(p1, rvx, rvy)
-      real rvn = nx * rvx + ny * rvy;
-      real j = -p1.massN * (rvn - p1.vb);
-      real j0 = jn1;
-      jn1 = r_max(j0 + j, real(0));
-      j = jn1 - j0;
-      body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, nx * j, ny * j);
-    }
-  } else {
-    real ax = jn0, ay = jn1;
-    real rvn1, rvn2;
-    {
-      VSR_RELV(p0, rvx, rvy)
-      rvn1 = nx * rvx + ny * rvy;
-    }
-    {
-      VSR_RELV(p1, rvx, rvy)
-      rvn2 = nx * rvx + ny * rvy;
-    }
-    real bx = rvn1 - p0.vb, by = rvn2 - p1.vb;
-    bx -= c.K00 * ax + c.K01 * ay;
-    by -= c.K01 * ax + c.K11 * ay;
-    real x = -(c.iK00 * bx + c.iK01 * by), y = -(c.iK01 * bx + c.iK11 * by);
-    bool ok = (x >= real(0) && y >= real(0));
-    if (!ok) {
-      x = -p0.massN * bx;
-      y = real(0);
-      real v2 = c.K01 * x + by;
-      ok = (x >= real(0) && v2 >= real(0));
-    }
-    if (!ok) {
-      x = real(0);
-      y = -p1.massN * by;
-      real v1 = c.K01 * y + bx;
-      ok = (y >= real(0) && v1 >= real(0));
-    }
-    if (!ok) {
-      x = real(0);
-      y = real(0);
-      ok = (bx >= real(0) && by >= real(0));
-    }
-    if (ok) {
-      real dx = x - ax, dy = y - ay;
-      body2_apply(im, ii, B, p0.r1x, p0.r1y, p0.r2x, p0.r2y, nx * dx, ny * dx);
-      body2_apply(im, ii, B, p1.r1x, p1.r1y, p1.r2x, p1.r2y, nx * dy, ny * dy);
-      jn0 = x;
-      jn1 = y;
-    }
-  }
-#undef VSR_RELV
-  c.p[0].jn = jn0;
-  c.p[0].jt = jt0;
-  if (two) {
-    c.p[1].jn = jn1;
-    c.p[1].jt = jt1;
-  }
-  VSR_B2_STORE()
-}
-
-// SequentialImpulses.solvePositionContraints (dyn4j) for one mass-mass constraint; the table holds
-// (x, y, theta).  Returns the minimum separation seen.
-template <typename real>
-__device__ __noinline__ real self_position(const CPar<real> P, const SCon<real>& c, real* mt, int mts, int ta) {
-  const int ka = c.ka, kb = c.kb, tb = c.tb;
-  real x1 = mt[VSR_MTI(ka, 0, ta)], y1 = mt[VSR_MTI(ka, 1, ta)], t1 = mt[VSR_MTI(ka, 2, ta)];
-  real x2 = mt[VSR_MTI(kb, 0, tb)], y2 = mt[VSR_MTI(kb, 1, tb)], t2 = mt[VSR_MTI(kb, 2, tb)];
-  const real im = P.im, ii = P.ii;
-  const real nx = c.nx, ny = c.ny;
-  real minSep = real(0);
-  for (int k = 0; k < c.n; k++) {
-    const SPoint<real>& p = c.p[k];
-    real s1, c1, s2, c2;
-    r_sincos(t1, &s1, &c1);
-    r_sincos(t2, &s2, &c2);
-    real r1x = c1 * p.l1x - s1 * p.l1y, r1y = s1 * p.l1x + c1 * p.l1y;
-    real r2x = c2 * p.l2x - s2 * p.l2y, r2y = s2 * p.l2x + c2 * p.l2y;
-    real p1x = x1 + r1x, p1y = y1 + r1y;
-    real p2x = x2 + r2x, p2y = y2 + r2y;
-    real sep = (p2x - p1x) * nx + (p2y - p1y) * ny - p.depth;
-    minSep = sep < minSep ? sep : minSep;
-    real cl = r_clamp<real>(sep + P.lin_tol, -P.max_corr, real(0));
-    real cp = P.baumgarte * cl;
-    real rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
-    real K = im + im + ii * rn1 * rn1 + ii * rn2 * rn2;
-    real jp = -cp / K;
-    real Jx = nx * jp, Jy = ny * jp;
-    x1 -= Jx * im; y1 -= Jy * im; t1 -= ii * (r1x * Jy - r1y * Jx);
-    x2 += Jx * im; y2 += Jy * im; t2 += ii * (r2x * Jy - r2y * Jx);
-  }
-  mt[VSR_MTI(ka, 0, ta)] = x1; mt[VSR_MTI(ka, 1, ta)] = y1; mt[VSR_MTI(ka, 2, ta)] = t1;
-  mt[VSR_MTI(kb, 0, tb)] = x2; mt[VSR_MTI(kb, 1, tb)] = y2; mt[VSR_MTI(kb, 2, tb)] = t2;
-  return minSep;
-}
-
-// ---------------------------------------------------------------- the block's contact list
-// An item: (owner thread << 5) | kind-specific bits | kind.  Ground (kind 0): (mass * 2 + buffer)
-// << 1 -> the owner's CBody.  Intra-robot (kind 1): list << 4 | index << 1 -> the owner's SCon.
-#define VSR_ITEM_OWNER(code) ((code) >> 5)
-#define VSR_ITEM_GROUND(code) (!((code) & 1))
-#define VSR_ITEM_MASS(code) (((code) >> 2) & 3)
-template <typename real>
-__device__ __forceinline__ CBody<real>& item_cbody(CBody<real>* blk_cb, int code) {
-  return blk_cb[(size_t)VSR_ITEM_OWNER(code) * 8 + ((code >> 1) & 7)];
-}
-template <typename real>
-__device__ __forceinline__ SCon<real>& item_scon(SList<real>* blk_sl, int code) {
-  return blk_sl[(size_t)VSR_ITEM_OWNER(code) * 2 + ((code >> 4) & 1)].c[(code >> 1) & 7];
+__device__ __forceinline__ SCon<real>& item_record(CBody<real>* blk_cb, SList<real>* blk_sl, int code) {
+  const int ow = VSR_ITEM_OWNER(code), sub = (code >> 4) & 7, idx = (code >> 1) & 7;
+  SCon<real>* g = blk_cb[(size_t)ow * 8 + sub].c + idx;
+  SCon<real>* s = blk_sl[(size_t)ow * 2 + (sub & 1)].c + idx;
+  return *((code & 1) ? s : g);
 }
 enum : int { ROUND_WARM = 0, ROUND_VELOCITY = 1, ROUND_POSITION = 2 };
 // One round per dependency level, every thread of the block takes items: the items of a level
-// touch disjoint masses, so solving them at once equals solving the whole list in its order
-// (ground constraints first, then every robot's intra-robot constraints in the robot's
-// enumeration).  `aux` (position rounds): [0][thread] robot already solved, [1][thread] a
-// constraint of this thread is still violated.
+// touch disjoint masses, so solving them at once equals solving the whole list in its order (per
+// robot: the ground constraints mass by mass, then the intra-robot constraints in the robot's
+// enumeration).  Items below `cap` live in the shared-memory pool, the rest in their records.
+// `aux` (position rounds): [0][thread] robot already solved, [1][thread] a constraint of this
+// thread is still violated.
 template <int MODE, typename real>
 __device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, int mts, const int* lhd, const int* items,
                                                int n_lv, int tid, int bdim, CBody<real>* blk_cb, SList<real>* blk_sl,
-                                               real* aux) {
+                                               real* aux, real* pool, int cap) {
   for (int l = 0, lo = 0; l < n_lv; l++) {
     const int hi = lhd[2 + l];
     for (int i = lo + tid; i < hi; i += bdim) {
       const int code = items[i];
       const int ow = VSR_ITEM_OWNER(code);
-      if (MODE == ROUND_POSITION && aux[ow] != real(0)) continue;
-      if (VSR_ITEM_GROUND(code)) {
-        const int km = VSR_ITEM_MASS(code);
-        CBody<real>& cb = item_cbody(blk_cb, code);
-        const int i0 = VSR_MTI(km, 0, ow), i1 = VSR_MTI(km, 1, ow), i2 = VSR_MTI(km, 2, ow);
-        if (MODE == ROUND_POSITION) {
-          BodyState<real> B = {mt[i0], mt[i1], mt[i2], real(0), real(0), real(0)};
-          real ms;
-          B = contact_position_mass(cpar, B, cb, ms);
-          mt[i0] = B.x; mt[i1] = B.y; mt[i2] = B.th;
-          if (ms < real(-3) * cpar.lin_tol) aux[bdim + ow] = real(1);
-        } else {
-          BodyState<real> B = {real(0), real(0), real(0), mt[i0], mt[i1], mt[i2]};
-          if (MODE == ROUND_WARM) B = contact_warm_mass(cpar, B, cb);
-          else B = contact_solve_mass(cpar, B, cb);
-          mt[i0] = B.vx; mt[i1] = B.vy; mt[i2] = B.w;
-        }
+      const bool pooled = i < cap;
+      if (MODE == ROUND_POSITION) {
+        if (aux[ow] != real(0)) continue;
+        const ConPos<real> d = pooled ? con_pos_from_pool(pool, cap, i) : con_pos_from_record(item_record(blk_cb, blk_sl, code));
+        const real ms = con_position(cpar, d, mt, mts, ow);
+        if (ms < real(-3) * cpar.lin_tol) aux[bdim + ow] = real(1);
       } else {
-        SCon<real>& sc = item_scon(blk_sl, code);
-        if (MODE == ROUND_WARM) self_warm(cpar, sc, mt, mts, ow);
-        else if (MODE == ROUND_VELOCITY) self_solve(cpar, sc, mt, mts, ow);
-        else {
-          const real ms = self_position(cpar, sc, mt, mts, ow);
-          if (ms < real(-3) * cpar.lin_tol) aux[bdim + ow] = real(1);
+        ConVel<real> d = pooled ? con_vel_from_pool(pool, cap, i) : con_vel_from_record(item_record(blk_cb, blk_sl, code));
+        Body2<real> B = body2_load(mt, mts, ow, d.ka, d.tb, d.kb);
+        if (MODE == ROUND_WARM) {
+          con_warm(cpar, d, B);
+        } else {
+          con_solve(cpar, d, B);
+          if (pooled) {
+            pool[10 * cap + i] = d.jn[0]; pool[11 * cap + i] = d.jt[0];
+            pool[19 * cap + i] = d.jn[1]; pool[20 * cap + i] = d.jt[1];
+          } else {
+            SCon<real>& c = item_record(blk_cb, blk_sl, code);
+            c.p[0].jn = d.jn[0]; c.p[0].jt = d.jt[0];
+            c.p[1].jn = d.jn[1]; c.p[1].jt = d.jt[1];
+          }
         }
+        body2_store(mt, mts, ow, d.ka, d.tb, d.kb, B);
       }
     }
     lo = hi;
@@ -1088,7 +983,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #ifndef VSR_MAX_THREADS
 #define VSR_MAX_THREADS 384
 // reals of shared memory reserved for the header of the block's contact list
-#define VSR_LHD_REALS 48
+#define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
 #endif
 #ifndef VSR_MIN_BLOCKS
@@ -1131,11 +1026,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS);
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
   real* const ex = mt + 16 * MTS + VSR_LHD_REALS;
+  // the tick's constraints as the solver rounds read them: [VSR_POOL_FIELDS][pool_cap]
+  real* const pool = ex + (BLK ? 2 * 20 * 128 : 0);
+  const int cap = P.pool_cap;
   real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
-  int* const items = P.lbuf + (size_t)blockIdx.x * 8 * MTS;
+  int* const items = P.lbuf + (size_t)blockIdx.x * 12 * MTS;
   const int mt_t = tid;
 #define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
   int exsel = 0;
@@ -1249,7 +1147,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
 
     __syncthreads();
-    for (int q = tid; q < 34; q += bdim) lhd[q] = 0;  // no contacts yet
+    for (int q = tid; q < 66; q += bdim) lhd[q] = 0;  // no contacts yet
     __syncthreads();
     for (int tick = 0; tick < P.n_ticks; tick++) {
       if (sync_mode & 1) __syncthreads();
@@ -1273,15 +1171,19 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         for (int i_ = tid, hi_ = lhd[2 + n_lv - 1]; i_ < hi_; i_ += bdim) {
           const int code = items[i_];
           const int ow = VSR_ITEM_OWNER(code);
-          if (VSR_ITEM_GROUND(code)) {
-            const int km = VSR_ITEM_MASS(code);
-            contact_bias_mass(cpar, mt[VSR_MTI(km, 0, ow)], mt[VSR_MTI(km, 1, ow)], mt[VSR_MTI(km, 2, ow)], item_cbody(blk_cb, code));
+          SCon<real>& c = item_record(blk_cb, blk_sl, code);
+          ConVel<real> d = con_vel_from_record(c);
+          const Body2<real> B = body2_load(mt, mts, ow, d.ka, d.tb, d.kb);
+          con_bias(cpar, d, B);
+          if (i_ < cap) {
+            con_vel_to_pool(d, pool, cap, i_);
           } else {
-            self_bias(cpar, item_scon(blk_sl, code), mt, MTS, ow);
+            c.p[0].vb = d.vb[0];
+            c.p[1].vb = d.vb[1];
           }
         }
         __syncthreads();
-        contact_rounds<ROUND_WARM>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
+        contact_rounds<ROUND_WARM>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
         VSR_MT_GET(vx, vy, w)
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
@@ -1467,11 +1369,23 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         if (n_lv > 0) {
           VSR_MT_PUT(vx, vy, w)
           __syncthreads();
-          contact_rounds<ROUND_VELOCITY>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
+          contact_rounds<ROUND_VELOCITY>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
           VSR_MT_GET(vx, vy, w)
         }
       }
 
+      if (n_lv > 0) {
+        // pooled constraints: the accumulated impulses go back to their records (the next step's
+        // warm start), the pool now caches what the position rounds read
+        const int n_it = lhd[2 + n_lv - 1];
+        for (int i_ = tid; i_ < n_it && i_ < cap; i_ += bdim) {
+          SCon<real>& c = item_record(blk_cb, blk_sl, items[i_]);
+          c.p[0].jn = pool[10 * cap + i_]; c.p[0].jt = pool[11 * cap + i_];
+          c.p[1].jn = pool[19 * cap + i_]; c.p[1].jt = pool[20 * cap + i_];
+          con_pos_to_pool(con_pos_from_record(c), pool, cap, i_);
+        }
+        __syncthreads();
+      }
       if (sync_mode & 4) __syncthreads();
       // ---- integrate positions (integratePosition, dyn4j; translation/rotation caps)
 #pragma unroll
@@ -1507,7 +1421,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             aux[0 * bdim + tid] = done ? real(1) : real(0);
             aux[1 * bdim + tid] = real(0);
             __syncthreads();
-            contact_rounds<ROUND_POSITION>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux);
+            contact_rounds<ROUND_POSITION>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
             if (!done) {
               VSR_MT_GET(x, y, th)
               r_sincos(th[1], &sn_[1], &cs_[1]);
@@ -1602,20 +1516,22 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       // ---- World.detect: new manifolds for Touch and for the next step
       const unsigned old_cmask = cmask;
       cmask = 0;
+      unsigned gcn = 0;  // ground constraints per mass, 4 bits each
       if (active) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           // cheap reject: far above the highest point of the terrain near this mass
           int cn = 0;
           int ov = detect_mass(tpar, x[k], y[k], cs_[k], sn_[k], hint[k], CBODY(k), (int)((old_cmask >> k) & 1u),
-                               cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn, im, ii);
+                               cbase[2 * k + (((flip >> k) & 1u) ^ 1u)], cn, im, ii, k);
           flip ^= 1u << k;
           if (ov) status |= STATUS_CONTACT_OVERFLOW;
           if (cn > 0) cmask |= 1u << k;
+          gcn |= (unsigned)cn << (4 * k);
 #ifdef VSR_DEBUG_DUMP
           if (rb == P.debug_robot && tick >= P.debug_tick && tick <= P.debug_tick_end)
             for (int q = 0; q < cn; q++) {
-              const CCon<real>& c = CBODY(k).c[q];
+              const SCon<real>& c = CBODY(k).c[q];
               printf("[kernel] tick %d body %d seg %d n %d normal (%.9g, %.9g) pose (%.9g %.9g %.9g)\n", tick, v * 4 + k,
                      c.seg, c.n, (double)c.nx, (double)c.ny, (double)x[k] + P.origin_x, (double)y[k], (double)th[k]);
               for (int z = 0; z < c.n; z++)
@@ -1684,11 +1600,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
         int s_start, s_tot;
         if (BLK) {
-          if (lane == 31) lhd[34 + wib] = incl;
+          if (lane == 31) lhd[66 + wib] = incl;
           __syncthreads();
           int before = 0, all = 0;
           for (int q = 0; q < wpb; q++) {
-            const int c = lhd[34 + q];
+            const int c = lhd[66 + q];
             before += q < wib ? c : 0;
             all += c;
           }
@@ -1708,7 +1624,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         SSYNC()
         real* const cnt = mt;  // small integers held as reals: each thread keeps to its own columns
 #pragma unroll
-        for (int k = 0; k < 4; k++) cnt[k * MTS + tid] = (real)((cmask >> k) & 1u);
+        for (int k = 0; k < 4; k++) cnt[k * MTS + tid] = (real)((gcn >> (4 * k)) & 15u);
         SSYNC()
         for (int i = 0; i < s_tot; i++) {
           const int li = i - s_start;
@@ -1726,45 +1642,43 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         sst = (unsigned)n_new | ((sst ^ 0x80000000u) & 0x80000000u);
       }
 
-      // ---- the block's contact list for the next step: ground items, then the intra-robot
-      //      constraints by level
+      // ---- the block's constraint list for the next step, by dependency level: the q-th ground
+      //      constraint of a mass has level q, the intra-robot ones follow (levels above)
       {
         __syncthreads();
-        for (int q = tid; q < 34; q += bdim) lhd[q] = 0;
+        for (int q = tid; q < 66; q += bdim) lhd[q] = 0;
         __syncthreads();
-        const int gc = __popc(cmask);
-        int gpos = 0;
-        if (gc) gpos = atomicAdd(&lhd[0], gc);
-        int spos[SC_CAP];
 #pragma unroll
-        for (int li = 0; li < SC_CAP; li++) {
-          spos[li] = 0;
-          if (li < n_new) spos[li] = atomicAdd(&lhd[2 + ((lvpack >> (8 * li)) & 255u)], 1);
+        for (int k = 0; k < 4; k++) {
+          const int cn = (int)((gcn >> (4 * k)) & 15u);
+          for (int q = 0; q < cn; q++) atomicAdd(&lhd[2 + q], 1);
         }
+#pragma unroll
+        for (int li = 0; li < SC_CAP; li++)
+          if (li < n_new) atomicAdd(&lhd[2 + ((lvpack >> (8 * li)) & 255u)], 1);
         __syncthreads();
         if (tid == 0) {
-          int run = lhd[0], nl_ = run > 0 ? 1 : 0;
+          int run = 0, nl_ = 0;
           for (int l = 0; l < VSR_MAX_LEVELS; l++) {
             const int c = lhd[2 + l];
+            lhd[34 + l] = run;  // cursor: start of level l
             run += c;
-            lhd[2 + l] = run;  // end offset of level l
+            lhd[2 + l] = run;   // end offset of level l
             if (c > 0) nl_ = l + 1;
           }
           lhd[1] = nl_;
         }
         __syncthreads();
-        if (gc) {
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (cmask & (1u << k)) items[gpos++] = (tid << 5) | (k << 2) | (int)(((flip >> k) & 1u) << 1);
+        for (int k = 0; k < 4; k++) {
+          const int cn = (int)((gcn >> (4 * k)) & 15u);
+          for (int q = 0; q < cn; q++)
+            items[atomicAdd(&lhd[34 + q], 1)] = (tid << 7) | ((k * 2 + (int)((flip >> k) & 1u)) << 4) | (q << 1);
         }
 #pragma unroll
         for (int li = 0; li < SC_CAP; li++)
-          if (li < n_new) {
-            const int lv = (int)((lvpack >> (8 * li)) & 255u);
-            const int start = lv == 0 ? lhd[0] : lhd[2 + lv - 1];
-            items[start + spos[li]] = (tid << 5) | (int)((sst >> 31) << 4) | (li << 1) | 1;
-          }
+          if (li < n_new)
+            items[atomicAdd(&lhd[34 + ((lvpack >> (8 * li)) & 255u)], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
         __syncthreads();
       }
 
