@@ -678,16 +678,18 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
   const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
-                ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + VSR_LHD_REALS) * sizeof(real) +
+                ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + (size_t)(blk ? 1 : wpb) * VSR_LHD_REALS) * sizeof(real) +
                 (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
   {
     // what is left of the SM's shared memory caches the block's contact constraints
     const size_t limit = 227 * 1024;
     long long cap = smem < limit ? (long long)((limit - smem) / (VSR_POOL_FIELDS * sizeof(real))) : 0;
-    cap = std::min<long long>(cap, (long long)12 * threads) / 32 * 32;
-    if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 32 * 32;
+    // one pool per scope: the warp (its robots' constraints), or the block of a big robot
+    const int scopes = blk ? 1 : wpb;
+    cap = std::min<long long>(cap / scopes, blk ? (long long)12 * threads : 12 * 32) / 4 * 4;
+    if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
     P.pool_cap = (int)cap;
-    smem += (size_t)cap * VSR_POOL_FIELDS * sizeof(real);
+    smem += (size_t)cap * scopes * VSR_POOL_FIELDS * sizeof(real);
   }
   P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
   void (*kern)(const Params<real>) = nullptr;

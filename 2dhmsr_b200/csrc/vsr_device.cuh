@@ -316,6 +316,9 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
     }
     if (s > best + (i > 0 ? in_eps : real(0))) { best = s; nx = A.nx[i]; ny = A.ny[i]; }
   }
+  // `best` never decreases: separated along one of the first mass' axes is final (the common case
+  // for the corner-to-corner neighbours)
+  if (mm && !(best < -in_eps)) return 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     real s = 1e30f;
@@ -501,7 +504,7 @@ __device__ __forceinline__ int con_hdr(const SCon<real>& c) {
   d.n = (h) & 3; d.ka = ((h) >> 4) & 3; d.kb = ((h) >> 6) & 3; d.tb = ((h) >> 8) - 1;
 
 template <typename real>
-__device__ __forceinline__ ConVel<real> con_vel_from_record(const SCon<real>& c) {
+__device__ __noinline__ ConVel<real> con_vel_from_record(const SCon<real>& c) {
   ConVel<real> d;
   d.n = c.n; d.block = c.block; d.ka = c.ka; d.kb = c.kb; d.tb = c.tb;
   d.nx = c.nx; d.ny = c.ny;
@@ -548,7 +551,7 @@ __device__ __forceinline__ ConVel<real> con_vel_from_pool(const real* pool, int 
   return d;
 }
 template <typename real>
-__device__ __forceinline__ ConPos<real> con_pos_from_record(const SCon<real>& c) {
+__device__ __noinline__ ConPos<real> con_pos_from_record(const SCon<real>& c) {
   ConPos<real> d;
   d.n = c.n; d.ka = c.ka; d.kb = c.kb; d.tb = c.tb;
   d.nx = c.nx; d.ny = c.ny;
@@ -666,19 +669,16 @@ __device__ __forceinline__ void con_solve(const CPar<real>& P, ConVel<real>& d, 
       body2_apply(im, ii, im2, ii2, B, d.r1x[k], d.r1y[k], d.r2x[k], d.r2y[k], tx * jt, ty * jt);
     }
   }
-  if (!two || !d.block) {
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      if (k == 0 || two) {
-        VSR_RELV(k, rvx, rvy)
-        real rvn = nx * rvx + ny * rvy;
-        real j = -d.mN[k] * (rvn - d.vb[k]);
-        real j0 = d.jn[k];
-        d.jn[k] = r_max(j0 + j, real(0));
-        j = d.jn[k] - j0;
-        body2_apply(im, ii, im2, ii2, B, d.r1x[k], d.r1y[k], d.r2x[k], d.r2y[k], nx * j, ny * j);
-      }
-    }
+  if (!two) {
+    // (a two-point constraint always carries its block matrix: an ill-conditioned one was cut to
+    // one point at initialisation)
+    VSR_RELV(0, rvx, rvy)
+    real rvn = nx * rvx + ny * rvy;
+    real j = -d.mN[0] * (rvn - d.vb[0]);
+    real j0 = d.jn[0];
+    d.jn[0] = r_max(j0 + j, real(0));
+    j = d.jn[0] - j0;
+    body2_apply(im, ii, im2, ii2, B, d.r1x[0], d.r1y[0], d.r2x[0], d.r2y[0], nx * j, ny * j);
   } else {
     // 2-point block solver (the Box2D / dyn4j LCP enumeration)
     real ax = d.jn[0], ay = d.jn[1];
@@ -845,19 +845,20 @@ __device__ __forceinline__ SCon<real>& item_record(CBody<real>* blk_cb, SList<re
   return *((code & 1) ? s : g);
 }
 enum : int { ROUND_WARM = 0, ROUND_VELOCITY = 1, ROUND_POSITION = 2 };
-// One round per dependency level, every thread of the block takes items: the items of a level
+// One round per dependency level, every thread of the scope (the warp; the block of a big robot)
+// takes items: the items of a level
 // touch disjoint masses, so solving them at once equals solving the whole list in its order (per
 // robot: the ground constraints mass by mass, then the intra-robot constraints in the robot's
 // enumeration).  Items below `cap` live in the shared-memory pool, the rest in their records.
 // `aux` (position rounds): [0][thread] robot already solved, [1][thread] a constraint of this
 // thread is still violated.
-template <int MODE, typename real>
+template <int MODE, bool BLK, typename real>
 __device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, int mts, const int* lhd, const int* items,
-                                               int n_lv, int tid, int bdim, CBody<real>* blk_cb, SList<real>* blk_sl,
-                                               real* aux, real* pool, int cap) {
+                                               int n_lv, int st, int sdim, int bdim, CBody<real>* blk_cb,
+                                               SList<real>* blk_sl, real* aux, real* pool, int cap) {
   for (int l = 0, lo = 0; l < n_lv; l++) {
     const int hi = lhd[2 + l];
-    for (int i = lo + tid; i < hi; i += bdim) {
+    for (int i = lo + st; i < hi; i += sdim) {
       const int code = items[i];
       const int ow = VSR_ITEM_OWNER(code);
       const bool pooled = i < cap;
@@ -886,7 +887,7 @@ __device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, 
       }
     }
     lo = hi;
-    __syncthreads();
+    if (BLK) __syncthreads(); else __syncwarp();
   }
 }
 
@@ -985,6 +986,8 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
+// candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
+#define VSR_MAX_CAND 6
 #endif
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
@@ -1023,17 +1026,18 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   constexpr int mts = MTS;
   real* const mt = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp;
   // list header: [0] ground items, [1] levels, [2..33] end offset of each level, [34..] scratch
-  int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS);
+  int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS) + (BLK ? 0 : wib * VSR_LHD_REALS);
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
-  real* const ex = mt + 16 * MTS + VSR_LHD_REALS;
+  real* const ex = mt + 16 * MTS + (size_t)(BLK ? 1 : (blockDim.x >> 5)) * VSR_LHD_REALS;
   // the tick's constraints as the solver rounds read them: [VSR_POOL_FIELDS][pool_cap]
-  real* const pool = ex + (BLK ? 2 * 20 * 128 : 0);
-  const int cap = P.pool_cap;
+  const int cap = P.pool_cap;  // per scope
+  real* const pool = ex + (BLK ? 2 * 20 * 128 : wib * VSR_POOL_FIELDS * cap);
+  const int st = BLK ? tid : lane, sdim = BLK ? blockDim.x : 32;  // thread index / size of the scope
   real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
-  int* const items = P.lbuf + (size_t)blockIdx.x * 12 * MTS;
+  int* const items = P.lbuf + (size_t)blockIdx.x * 12 * MTS + (BLK ? 0 : wib * 12 * 32);
   const int mt_t = tid;
 #define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
   int exsel = 0;
@@ -1146,9 +1150,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     for (int q = 0; q < MAX_READ; q++) readings[q] = real(0);
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
 
-    __syncthreads();
-    for (int q = tid; q < 66; q += bdim) lhd[q] = 0;  // no contacts yet
-    __syncthreads();
+    SSYNC()
+    for (int q = st; q < 66; q += sdim) lhd[q] = 0;  // no contacts yet
+    SSYNC()
     for (int tick = 0; tick < P.n_ticks; tick++) {
       if (sync_mode & 1) __syncthreads();
       // =========================== World.step(1) ===========================
@@ -1164,11 +1168,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       // ---- contacts: SequentialImpulses.initialize.  The position-dependent half was done at
       //      detection; here the restitution bias of every constraint from the velocities before
       //      any warm start, then the warm starts.
-      const int n_lv = lhd[1];  // levels of this block's contact list (0: no contacts); block-uniform
+      const int n_lv = lhd[1];  // levels of this scope's constraint list (0: no contacts); uniform
       if (n_lv > 0) {
         VSR_MT_PUT(vx, vy, w)
-        __syncthreads();
-        for (int i_ = tid, hi_ = lhd[2 + n_lv - 1]; i_ < hi_; i_ += bdim) {
+        SSYNC()
+        for (int i_ = st, hi_ = lhd[2 + n_lv - 1]; i_ < hi_; i_ += sdim) {
           const int code = items[i_];
           const int ow = VSR_ITEM_OWNER(code);
           SCon<real>& c = item_record(blk_cb, blk_sl, code);
@@ -1182,8 +1186,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             c.p[1].vb = d.vb[1];
           }
         }
-        __syncthreads();
-        contact_rounds<ROUND_WARM>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
+        SSYNC()
+        contact_rounds<ROUND_WARM, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
         VSR_MT_GET(vx, vy, w)
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
@@ -1368,8 +1372,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         // contacts (SequentialImpulses.solveVelocityConstraints), pooled over the block
         if (n_lv > 0) {
           VSR_MT_PUT(vx, vy, w)
-          __syncthreads();
-          contact_rounds<ROUND_VELOCITY>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
+          SSYNC()
+          contact_rounds<ROUND_VELOCITY, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
           VSR_MT_GET(vx, vy, w)
         }
       }
@@ -1378,13 +1382,13 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         // pooled constraints: the accumulated impulses go back to their records (the next step's
         // warm start), the pool now caches what the position rounds read
         const int n_it = lhd[2 + n_lv - 1];
-        for (int i_ = tid; i_ < n_it && i_ < cap; i_ += bdim) {
+        for (int i_ = st; i_ < n_it && i_ < cap; i_ += sdim) {
           SCon<real>& c = item_record(blk_cb, blk_sl, items[i_]);
           c.p[0].jn = pool[10 * cap + i_]; c.p[0].jt = pool[11 * cap + i_];
           c.p[1].jn = pool[19 * cap + i_]; c.p[1].jt = pool[20 * cap + i_];
           con_pos_to_pool(con_pos_from_record(c), pool, cap, i_);
         }
-        __syncthreads();
+        SSYNC()
       }
       if (sync_mode & 4) __syncthreads();
       // ---- integrate positions (integratePosition, dyn4j; translation/rotation caps)
@@ -1411,17 +1415,15 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       {
         bool done = BLK ? !(rb < P.n_robots) : !active;  // BLK: idle threads follow their block
         for (int it = 0; it < P.pos_iters; it++) {
-          // with contacts in the block every warp stays for the block-wide rounds until the last
-          // robot of the block is done; without, a warp leaves as soon as its robots are
-          const bool wdone = BLK ? done : (bool)__all_sync(0xffffffffu, done);
-          if (n_lv > 0 ? (bool)__syncthreads_and(done) : wdone) break;
+          const bool wdone = BLK ? done : (bool)__all_sync(0xffffffffu, done);  // BLK: done is block-uniform
+          if (wdone) break;
           bool solved = true;
           if (n_lv > 0) {
             VSR_MT_PUT(x, y, th)
             aux[0 * bdim + tid] = done ? real(1) : real(0);
             aux[1 * bdim + tid] = real(0);
-            __syncthreads();
-            contact_rounds<ROUND_POSITION>(cpar, mt, MTS, lhd, items, n_lv, tid, bdim, blk_cb, blk_sl, aux, pool, cap);
+            SSYNC()
+            contact_rounds<ROUND_POSITION, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
             if (!done) {
               VSR_MT_GET(x, y, th)
               r_sincos(th[1], &sn_[1], &cs_[1]);
@@ -1560,10 +1562,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         aux[0 * bdim + tid] = vcx; aux[1 * bdim + tid] = vcy; aux[2 * bdim + tid] = vrad;
         SSYNC()
         SCon<real>* const newc = (sbase + ((sst >> 31) ^ 1u))->c;
+        int cand[VSR_MAX_CAND], n_cand = 0;  // (partner thread << 4) | partner mass << 2 | own mass
         if (active) {
-          const int old_n = S_N;
-          const SCon<real>* const oldc = S_CUR->c;
           const real rr = real(2.8284271247461903) * P.half;  // two half diagonals
+          real ae[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) ae[k] = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
           const int j_right = has[1] ? nl[1] - lane0 : -1, j_up = has[3] ? nl[3] - lane0 : -1;
           for (int j = v; j < nvox; j++) {
             const int tj = rbase + j;
@@ -1576,13 +1580,43 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll 1
             for (int kb = 0; kb < 4; kb++) {
               const real bx = mt[VSR_MTI(kb, 0, tj)], by = mt[VSR_MTI(kb, 1, tj)];
+              // half extent of the partner's bounding box
+              const real be = P.half * (r_abs(mt[VSR_MTI(kb, 2, tj)]) + r_abs(mt[VSR_MTI(kb, 3, tj)]));
 #pragma unroll
               for (int ka = 0; ka < 4; ka++) {
                 if (j == v && kb <= ka) continue;
                 if ((wm >> (ka * 4 + kb)) & 1u) continue;
-                if (r_abs(x[ka] - bx) > rr || r_abs(y[ka] - by) > rr) continue;
-                const int got = self_pair(cpar, P.half, x[ka], y[ka], cs_[ka], sn_[ka], bx, by, mt[VSR_MTI(kb, 2, tj)],
-                                          mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_n, &newc[n_new]);
+                // disjoint bounding boxes: separated (exact, unlike the narrowphase margin: safe side)
+                const real lim = be + ae[ka];
+                if (r_abs(x[ka] - bx) > lim || r_abs(y[ka] - by) > lim) continue;
+                const int code = (tj << 4) | (kb << 2) | ka;
+#pragma unroll
+                for (int q = 0; q < VSR_MAX_CAND; q++)
+                  if (q == n_cand) cand[q] = code;
+                if (n_cand == VSR_MAX_CAND) status |= STATUS_CONTACT_OVERFLOW;
+                else n_cand++;
+              }
+            }
+          }
+        }
+        // narrowphase: the q-th candidates of all threads together (one converged call per round)
+        {
+          const int max_cand = BLK ? VSR_MAX_CAND : (int)__reduce_max_sync(0xffffffffu, (unsigned)n_cand);
+          const SCon<real>* const oldc = S_CUR->c;
+          const int old_n = S_N;
+#pragma unroll
+          for (int q = 0; q < VSR_MAX_CAND; q++) {
+            if (q < max_cand) {
+              if (q < n_cand) {
+                const int code = cand[q];
+                const int tj = code >> 4, kb = (code >> 2) & 3, ka = code & 3;
+                real ax = x[0], ay = y[0], ac = cs_[0], as = sn_[0];
+#pragma unroll
+                for (int k = 1; k < 4; k++)
+                  if (ka == k) { ax = x[k]; ay = y[k]; ac = cs_[k]; as = sn_[k]; }
+                const int got = self_pair(cpar, P.half, ax, ay, ac, as, mt[VSR_MTI(kb, 0, tj)], mt[VSR_MTI(kb, 1, tj)],
+                                          mt[VSR_MTI(kb, 2, tj)], mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_n,
+                                          &newc[n_new]);
                 if (got) {
                   if (n_new == SC_CAP) status |= STATUS_CONTACT_OVERFLOW;
                   else n_new++;
@@ -1642,12 +1676,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         sst = (unsigned)n_new | ((sst ^ 0x80000000u) & 0x80000000u);
       }
 
-      // ---- the block's constraint list for the next step, by dependency level: the q-th ground
+      // ---- the scope's constraint list for the next step, by dependency level: the q-th ground
       //      constraint of a mass has level q, the intra-robot ones follow (levels above)
       {
-        __syncthreads();
-        for (int q = tid; q < 66; q += bdim) lhd[q] = 0;
-        __syncthreads();
+        SSYNC()
+        for (int q = st; q < 66; q += sdim) lhd[q] = 0;
+        SSYNC()
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const int cn = (int)((gcn >> (4 * k)) & 15u);
@@ -1656,8 +1690,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
         for (int li = 0; li < SC_CAP; li++)
           if (li < n_new) atomicAdd(&lhd[2 + ((lvpack >> (8 * li)) & 255u)], 1);
-        __syncthreads();
-        if (tid == 0) {
+        SSYNC()
+        if (st == 0) {
           int run = 0, nl_ = 0;
           for (int l = 0; l < VSR_MAX_LEVELS; l++) {
             const int c = lhd[2 + l];
@@ -1668,7 +1702,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           }
           lhd[1] = nl_;
         }
-        __syncthreads();
+        SSYNC()
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const int cn = (int)((gcn >> (4 * k)) & 15u);
@@ -1679,7 +1713,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         for (int li = 0; li < SC_CAP; li++)
           if (li < n_new)
             items[atomicAdd(&lhd[34 + ((lvpack >> (8 * li)) & 255u)], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
-        __syncthreads();
+        SSYNC()
       }
 
       // =========================== Robot.act(t) ===========================

@@ -1,3 +1,4 @@
+import os
 """Ad-hoc GPU check: kernel (fp64 / fp32) vs the oracle on small batches + a timing."""
 import importlib, math, os, sys, time
 import numpy as np
@@ -13,7 +14,8 @@ def phase_batch(n, shape="biped-4x3", sensors="uniform-ax+t-0", seed=0, terrain=
     for i in range(n):
         ph = rng.uniform(0, 2 * math.pi, size=(body.w, body.h))
         robots.append(H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(body.w, body.h, lambda x, y: float(ph[x, y]))), body))
-    return H.Locomotion(final_t, H.Locomotion.create_terrain(terrain), H.Settings()), robots
+    st = H.Settings().set(self_collision=int(os.environ.get("SELF", "1")))
+    return H.Locomotion(final_t, H.Locomotion.create_terrain(terrain), st), robots
 
 def main():
     loco, robots = phase_batch(6)

@@ -141,3 +141,22 @@ def test_reference_frames_png_centres():
     g = np.asarray(GOLD["reference_frames_png"]["centres"])
     got = np.asarray([[cx[k], cy[k]] for k in FRAME_TICKS])
     assert np.abs(got - g).max() <= 0.1
+
+
+def test_intra_robot_contacts_follow_the_setting():
+    # Voxel.java:178-185,474: every pair of masses of a robot may collide unless welded.  At rest the
+    # corner neighbours only touch (no constraint: a contact needs a penetration above the tie margin);
+    # once the voxels deform they overlap.  self_collision=0 keeps the ground contacts only.
+    robots = helpers.phase_robots(4, seed=5)
+    on, pon = oracle.run(helpers.locomotion(1.0, self_collision=1).compile(robots), stats=True)
+    off, poff = oracle.run(helpers.locomotion(1.0, self_collision=0).compile(robots), stats=True)
+    assert pon["n_contacts"][:, 0].max() == 0
+    assert poff["n_contacts"][:, :15].max() == 0          # free fall: nothing touches the ground yet
+    assert pon["n_contacts"][:, 1:15].max() > 0           # ... but corner neighbours already overlap
+    assert np.all(on["status"] == 0) and np.all(off["status"] == 0)
+    assert np.abs(on["last_center_y"] - off["last_center_y"]).max() > 1e-9
+    # a single voxel has no non-welded neighbours close enough: identical results
+    one = helpers.phase_robots(2, shape="box-1x1", seed=5)
+    a, _ = oracle.run(helpers.locomotion(2.0, self_collision=1).compile(one))
+    b, _ = oracle.run(helpers.locomotion(2.0, self_collision=0).compile(one))
+    assert a.tobytes() == b.tobytes()

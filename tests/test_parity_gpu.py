@@ -132,6 +132,17 @@ def test_fp64_centralized_mlp_with_sensors(hidden, sensors, act):
     assert np.all(res["control_energy_last"] > 0)
 
 
+def test_fp64_ground_contacts_only():
+    """vsr_settings.self_collision = 0: masses of a robot pass through each other, as in a
+    ground-only model; same parity bar."""
+    loco = helpers.locomotion(4.0, self_collision=0)
+    bd, res, tr, ores, otr = _both(loco, helpers.phase_robots(5, seed=9), F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    on, _ = helpers.gpu_run(helpers.locomotion(4.0).compile(helpers.phase_robots(5, seed=9), precision=F64))
+    assert np.abs(on["last_center_x"] - res["last_center_x"]).max() > 1e-6   # the setting matters
+
+
 def test_fp32_short_horizon_tolerances():
     loco = helpers.locomotion(2.0)
     robots = helpers.phase_robots(16, seed=21)
@@ -139,15 +150,20 @@ def test_fp32_short_horizon_tolerances():
     res, tr = helpers.gpu_run(bd, trajectories=16)
     ores, pr = oracle.run(bd, trajectory=True, stats=True, n_threads=8)
     otr = pr["trajectory"]
-    first_contact = int(np.argmax(pr["n_contacts"].max(axis=0) > 0))
-    assert first_contact >= 5
-    # fp32 vs fp64 agree to rounding (~1e-6) until a DISCRETE decision flips (a weld position error
-    # next to the 0.005 tolerance changes the number of position iterations; a contact starts one
-    # tick earlier/later): the typical robot stays below 2e-5 before the first contact, and a flipped
-    # decision costs at most a few 1e-4.
+    # first tick at which any mass of any robot reaches the ground (y = 5): intra-robot contacts
+    # (corner neighbours) exist from tick 1 on and are part of what is compared
+    th = otr[:, :, :40, 2]
+    low = otr[:, :, :40, 1] - 0.525 * (np.abs(np.cos(th)) + np.abs(np.sin(th)))
+    first_contact = int(np.argmax(low.min(axis=(0, 2)) < 5.0))
+    assert first_contact >= 5 and pr["n_contacts"][:, :first_contact].max() > 0
+    # fp32 vs fp64 agree to rounding (~2e-6) until a DISCRETE decision flips: a weld position error
+    # next to the 0.005 tolerance changes the number of position iterations, or -- the common case --
+    # two corner neighbours that only just overlap are a contact in one precision and not yet in the
+    # other (the narrowphase margin is 1e-12 in fp64 and 1e-6 in fp32).  Robots without a flip stay at
+    # rounding level; a flip costs up to a few 1e-3 before the first ground contact.
     pre = np.abs(tr[:, :first_contact, :, :2] - otr[:, :first_contact, :40, :2]).max(axis=(1, 2, 3))
-    assert np.median(pre) < 2e-5, pre
-    assert pre.max() < 2e-3, pre
+    assert np.percentile(pre, 25) < 2e-5, pre
+    assert pre.max() < 2e-2, pre
     full = np.abs(tr[..., :2] - otr[:, :, :40, :2]).max()
     assert full < 0.25, full                     # stated fp32 tolerance over 2 s (121 ticks)
     assert np.abs(res["first_center_x"] - ores["first_center_x"]).max() < 1e-5
