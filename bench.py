@@ -37,7 +37,7 @@ N_ROBOTS = 4096
 SHAPE, SENSORS, TERRAIN, FINAL_T = "biped-4x3", "uniform-ax+t-0", "flat", 20.0
 CONFIG = {
     "workload": "configs[1]: 4096 x biped-4x3, PhaseSin f=1 A=1 phases~U[0,2pi) (numpy PCG64 seed 0), "
-                "uniform-ax+t-0 sensors, flat terrain, 20 s = 1200 ticks, default Settings; per GPU",
+                "uniform-ax+t-0 sensors, flat terrain, 20 s = 1200 ticks, default Settings (ground and intra-robot contacts); per GPU",
     "robots_per_gpu": N_ROBOTS, "voxels_per_robot": 10, "ticks": 1200, "precision": "fp32",
     "l2": "flushed between timed steps (256 MiB write)", "parallelism": "robots sharded, no per-step communication",
 }
