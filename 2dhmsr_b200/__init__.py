@@ -8,7 +8,10 @@ fallback.
 from . import _abi as abi  # noqa: F401
 from .hmsrobots import (  # noqa: F401
     AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DoubleRange, Grid,
-    JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotUtils,
-    Sensor, Settings, SoftNormalization, TimeFunctions, Touch, Trend, Velocity, Voxel, VsrError,
+    JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotShape, RobotUtils,
+    Sensor, Settings, Snapshot, SoftNormalization, TimeFunctions, Touch, Trend, Velocity, Voxel, VsrError,
     compile_batch, tick_times,
+)
+from .behavior import (  # noqa: F401
+    BehaviorUtils, BoundingBox, Footprint, Gait, Observation, VoxelPoly, build_observations, ground_y_at,
 )

@@ -117,6 +117,7 @@ struct Bucket {
   void* d_params = nullptr;
   void* d_ring = nullptr;
   void* d_traj = nullptr;
+  void* d_vtrace = nullptr;
   void* d_cbuf = nullptr;
   size_t cbuf_bytes = 0;
   void* d_sbuf = nullptr;  // intra-robot contact arena
@@ -176,8 +177,8 @@ static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr;
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
     k.d_sbuf = nullptr; k.sbuf_bytes = 0;
     k.d_lbuf = nullptr; k.lbuf_bytes = 0;
@@ -564,6 +565,7 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
       if (k.traj_robots > 0) {
         size_t tb = (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz;
         CUDA_TRY(cudaMalloc(&k.d_traj, tb));
+        CUDA_TRY(cudaMalloc(&k.d_vtrace, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 2 * esz));
       }
     }
   }
@@ -576,7 +578,10 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
   CUDA_TRY(cudaMemsetAsync(b->d_results, 0, b->n_robots * sizeof(vsr_result), s));
   for (auto& k : b->buckets)
     if (k.traj_robots > 0)
+    {
       CUDA_TRY(cudaMemsetAsync(k.d_traj, 0, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz, s));
+      CUDA_TRY(cudaMemsetAsync(k.d_vtrace, 0, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 2 * esz, s));
+    }
   CUDA_TRY(cudaStreamSynchronize(s));
   b->uploaded = true;
   b->ran = false;
@@ -598,6 +603,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.ring = (real*)k.d_ring;
   P.trajectory = (real*)k.d_traj;
   P.traj_robots = k.traj_robots;
+  P.vtrace = (real*)k.d_vtrace;
   P.n_ticks = (int)b->ticks.size();
   P.tick_t = b->d_ticks;
   P.win_first = b->d_win;
@@ -809,6 +815,35 @@ extern "C" long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* ou
   }
   // world frame
   for (size_t i = 0; i < n; i += 6) out[i] += b->origin_x;
+  return (long long)n;
+}
+
+extern "C" long long vsr_batch_voxel_trace(vsr_batch* b, size_t robot, double* out, size_t capacity) {
+  if (!b || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->ran) return fail(VSR_ERR_STATE, "vsr_batch_voxel_trace before vsr_batch_run");
+  if (robot >= b->n_robots || robot >= b->desc.trajectory_robots)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "robot has no recorded trajectory");
+  Bucket* kb = nullptr;
+  int pos = -1;
+  for (auto& k : b->buckets)
+    for (size_t i = 0; i < k.robot_ids.size() && (long long)i < k.traj_robots; i++)
+      if ((size_t)k.robot_ids[i] == robot) {
+        kb = &k;
+        pos = (int)i;
+      }
+  if (!kb) return fail(VSR_ERR_STATE, "trajectory bucket not found");
+  const int nt = (int)b->ticks.size();
+  const size_t n = (size_t)nt * kb->shape.nvox * 2;
+  if (capacity < n) return fail(VSR_ERR_INVALID_ARGUMENT, "voxel trace buffer too small");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->run_stream));
+  if (b->precision == VSR_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(out, (double*)kb->d_vtrace + (size_t)pos * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), (float*)kb->d_vtrace + (size_t)pos * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+  }
   return (long long)n;
 }
 

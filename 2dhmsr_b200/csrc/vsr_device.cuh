@@ -76,6 +76,7 @@ struct Params {
   real* ring;                 // [ring_depth][n_channels][n_robots * nvox]
   real* trajectory;           // [traj_robots][n_ticks][nvox*4][6], bucket order, or null
   long long traj_robots;
+  real* vtrace;               // [traj_robots][n_ticks][nvox][2]: touching the ground, applied force
   // time
   int n_ticks;
   const double* tick_t;       // [n_ticks] accumulated t
@@ -1862,6 +1863,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           o[6 * k + 0] = x[k]; o[6 * k + 1] = y[k]; o[6 * k + 2] = th[k];
           o[6 * k + 3] = vx[k]; o[6 * k + 4] = vy[k]; o[6 * k + 5] = w[k];
         }
+        // what VoxelPoly carries besides the geometry (Voxel.java:605-616): Touch.isTouchingGround and
+        // getLastAppliedForce (the energies are running sums of these and of the area ratio)
+        real* q = P.vtrace + (((size_t)rb * P.n_ticks + tick) * (size_t)nvox + (size_t)v) * 2;
+        q[0] = cmask ? real(1) : real(0);
+        q[1] = last_f;
       }
 
       // ---- Observation: first and last tick only (Outcome.java:152-166)

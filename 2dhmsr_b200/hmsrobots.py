@@ -509,26 +509,86 @@ class Settings:
         return self._s
 
 
-class Outcome:
-    """tasks/locomotion/Outcome.java: only what the first and the last Observation give."""
+class Snapshot:
+    """core/snapshots/Snapshot.java: content + the class that produced it + children."""
 
-    def __init__(self, rec):
+    def __init__(self, content, snapshottable_class: str, children=None):
+        self.content, self.snapshottable_class = content, snapshottable_class
+        self.children = list(children) if children else []
+
+    def get_content(self):
+        return self.content
+
+    def get_children(self):
+        return self.children
+
+    @staticmethod
+    def world(snapshots) -> "Snapshot":  # Snapshot.world(List<Snapshot>)
+        return Snapshot(None, "World", snapshots)
+
+
+class RobotShape:
+    """core/snapshots/RobotShape.java: Grid<VoxelPoly> + bounding box."""
+
+    def __init__(self, polies: "Grid", bounding_box):
+        self.polies, self.box = polies, bounding_box
+
+    def get_polies(self) -> "Grid":
+        return self.polies
+
+    def bounding_box(self):
+        return self.box
+
+
+class Outcome:
+    """tasks/locomotion/Outcome.java.
+
+    Built either from the ``vsr_result`` record (what the first and the last Observation give: distance,
+    time, velocity, energies -- the fitness path, nothing per tick leaves the device) or from the full
+    ``observations`` map (``Locomotion.apply(..., observations=True)`` or with a listener), which adds
+    the spectra, postures, footprints and gaits."""
+
+    def __init__(self, rec=None, observations=None):
+        if isinstance(rec, dict) and observations is None:  # new Outcome(Map<Double, Observation>)
+            rec, observations = None, rec
         self.rec = rec
+        self.observations = dict(sorted(observations.items())) if observations is not None else None
+
+    # ---- first / last observation
+    def _ends(self):
+        ks = list(self.observations)
+        return self.observations[ks[0]], self.observations[ks[-1]], ks[0], ks[-1]
+
+    def _polies(self, o):
+        return [v for v in o.voxel_polies.values() if v is not None]
 
     def get_distance(self) -> float:  # :152-166
-        return float(self.rec["last_center_x"] - self.rec["first_center_x"])
+        if self.observations is None:
+            return float(self.rec["last_center_x"] - self.rec["first_center_x"])
+        f, l, _, _ = self._ends()
+        from .behavior import BehaviorUtils
+        return BehaviorUtils.center(self._polies(l))[0] - BehaviorUtils.center(self._polies(f))[0]
 
     def get_time(self) -> float:  # :194-196
-        return float(self.rec["t_last"] - self.rec["t_first"])
+        if self.observations is None:
+            return float(self.rec["t_last"] - self.rec["t_first"])
+        _, _, t0, t1 = self._ends()
+        return t1 - t0
 
     def get_velocity(self) -> float:  # :198-200
         return self.get_distance() / self.get_time()
 
     def get_area_ratio_energy(self) -> float:  # :42-58
-        return float(self.rec["area_ratio_energy_last"] - self.rec["area_ratio_energy_first"])
+        if self.observations is None:
+            return float(self.rec["area_ratio_energy_last"] - self.rec["area_ratio_energy_first"])
+        f, l, _, _ = self._ends()
+        return sum(v.get_area_ratio_energy() for v in self._polies(l)) - sum(v.get_area_ratio_energy() for v in self._polies(f))
 
     def get_control_energy(self) -> float:  # :126-142
-        return float(self.rec["control_energy_last"] - self.rec["control_energy_first"])
+        if self.observations is None:
+            return float(self.rec["control_energy_last"] - self.rec["control_energy_first"])
+        f, l, _, _ = self._ends()
+        return sum(v.get_control_energy() for v in self._polies(l)) - sum(v.get_control_energy() for v in self._polies(f))
 
     def get_control_power(self) -> float:
         return self.get_control_energy() / self.get_time()
@@ -538,6 +598,63 @@ class Outcome:
 
     def get_corrected_efficiency(self) -> float:  # :148-150
         return self.get_distance() / (1.0 + self.get_control_power() * self.get_time())
+
+    # ---- the per-tick part
+    def _need(self):
+        if self.observations is None:
+            raise NotImplementedError("this Outcome holds the first/last observation only: "
+                                      "run Locomotion.apply(..., observations=True)")
+        return self.observations
+
+    def get_observations(self):  # :190-192
+        return self._need()
+
+    def get_computation_time(self) -> float:  # :121-124
+        f, l, _, _ = (self._need(), *self._ends())[1:]
+        return l.computation_time - f.computation_time
+
+    def sub_outcome(self, start_t: float, end_t: float) -> "Outcome":  # :202-204: subMap(startT, endT)
+        return Outcome(observations={t: o for t, o in self._need().items() if start_t <= t < end_t})
+
+    def get_average_posture(self, n: int):  # :64-69
+        from .behavior import BehaviorUtils
+        return BehaviorUtils.compute_average_posture(
+            [BehaviorUtils.compute_posture(self._polies(o), n) for o in self._need().values()])
+
+    def _center_signal(self, fn):
+        from .behavior import BehaviorUtils
+        return {t: fn(BehaviorUtils.get_central_element(o.voxel_polies)) for t, o in self._need().items()}
+
+    def _spectrum(self, fn, min_f, max_f, n_bins):
+        from .behavior import BehaviorUtils
+        return BehaviorUtils.compute_quantized_spectrum(self._center_signal(fn), min_f, max_f, n_bins)
+
+    def get_center_angle_spectrum(self, min_f, max_f, n_bins):  # :71-79
+        return self._spectrum(lambda v: v.get_angle(), min_f, max_f, n_bins)
+
+    def get_center_x_position_spectrum(self, min_f, max_f, n_bins):  # :81-89
+        return self._spectrum(lambda v: v.center()[0], min_f, max_f, n_bins)
+
+    def get_center_x_velocity_spectrum(self, min_f, max_f, n_bins):  # :91-99
+        return self._spectrum(lambda v: v.get_linear_velocity()[0], min_f, max_f, n_bins)
+
+    def get_center_y_position_spectrum(self, min_f, max_f, n_bins):  # :101-109
+        return self._spectrum(lambda v: v.center()[1], min_f, max_f, n_bins)
+
+    def get_center_y_velocity_spectrum(self, min_f, max_f, n_bins):  # :111-119
+        return self._spectrum(lambda v: v.get_linear_velocity()[1], min_f, max_f, n_bins)
+
+    def get_footprints_spectra(self, n: int, min_f, max_f, n_bins):  # :168-188
+        from .behavior import BehaviorUtils
+        fps = {t: BehaviorUtils.compute_footprint(self._polies(o), n) for t, o in self._need().items()}
+        return [BehaviorUtils.compute_quantized_spectrum({t: (1.0 if f.mask[i] else 0.0) for t, f in fps.items()},
+                                                         min_f, max_f, n_bins) for i in range(n)]
+
+    def get_main_gait(self, interval: float, longest_interval: float, n: int):
+        """BehaviorUtils.computeMainGait over the observations' voxel polies."""
+        from .behavior import BehaviorUtils
+        return BehaviorUtils.compute_main_gait(interval, longest_interval,
+                                               {t: self._polies(o) for t, o in self._need().items()}, n)
 
     def __repr__(self):
         return f"Outcome{{distance={self.get_distance():.6f}, time={self.get_time():.3f}, velocity={self.get_velocity():.6f}}}"
@@ -758,6 +875,16 @@ class DeviceBatch:
             _check(self.lib, int(got))
         return out
 
+    def voxel_trace(self, robot: int) -> np.ndarray:
+        """[tick][voxel][2] = touching the ground (0/1), applied force (vsr_batch_voxel_trace)."""
+        nv = self.lib.vsr_batch_n_bodies(self.h, robot) // 4
+        nt = self.lib.vsr_batch_n_ticks(self.h)
+        out = np.zeros((nt, nv, 2), dtype=np.float64)
+        got = self.lib.vsr_batch_voxel_trace(self.h, robot, _np_ptr(out, C.c_double), out.size)
+        if got < 0:
+            _check(self.lib, int(got))
+        return out
+
     def voxel_steps(self) -> int:
         return int(self.lib.vsr_batch_voxel_steps(self.h))
 
@@ -860,12 +987,44 @@ class Locomotion:
         return compile_batch(robots, self.final_t, self.ground_profile, self.initial_placement, self.settings,
                              precision, trajectory_robots)
 
-    def apply(self, robots, device: int = 0, precision: int = A.VSR_PRECISION_F32):
+    def apply(self, robots, listener=None, device: int = 0, precision: int = A.VSR_PRECISION_F32,
+              observations: bool = False):
+        """``Outcome apply(Robot[, SnapshotListener])`` (Locomotion.java:168-207) and its batched form
+        ``List<Outcome> apply(List<Robot>)``: one kernel launch for all robots.
+
+        Without a listener and with ``observations=False`` only the ``vsr_result`` records come back
+        (the fitness path).  ``observations=True`` also records every tick on the device and returns
+        Outcomes holding the reference's ``observations`` map; a ``listener`` (an object with
+        ``listen(t, snapshot)`` or a callable) is fed ``Snapshot.world([ground, robot])`` per tick and
+        robot, after the episode (the device runs all ticks in one launch)."""
+        import time as _time
         single = isinstance(robots, Robot)
         rs = [robots] if single else list(robots)
-        bd = self.compile(rs, precision)
+        full = observations or listener is not None
+        bd = self.compile(rs, precision, trajectory_robots=len(rs) if full else 0)
+        t0 = _time.time()
         with DeviceBatch(bd) as db:
             db.upload(device).run()
             res = db.results()
-        outs = [Outcome(res[i]) for i in range(len(rs))]
+            dumps = [(db.trajectory(i), db.voxel_trace(i)) for i in range(len(rs))] if full else None
+        wall = _time.time() - t0
+        if not full:
+            outs = [Outcome(res[i]) for i in range(len(rs))]
+            return outs[0] if single else outs
+        from .behavior import build_observations
+        tt = tick_times(self.final_t, self.settings.get_step_frequency())
+        outs = []
+        for i, r in enumerate(rs):
+            mat = next(v for v in r.get_voxels().values() if v is not None).material
+            obs = build_observations(r.get_voxels(), dumps[i][0], dumps[i][1], tt, (self.ground_profile[0], self.ground_profile[1]),
+                                     mat.side_length, mat.mass_side_length_ratio * mat.side_length, wall)
+            outs.append(Outcome(res[i], obs))
+            if listener is not None:
+                ground = Snapshot((list(self.ground_profile[0]), list(self.ground_profile[1])), "Ground")
+                for t, o in obs.items():
+                    polies = [v for v in o.voxel_polies.values() if v is not None]
+                    from .behavior import BoundingBox
+                    shape = RobotShape(o.voxel_polies, BoundingBox.largest(p.bounding_box() for p in polies))
+                    snap = Snapshot.world([ground, Snapshot(shape, "Robot", [Snapshot(p, "Voxel") for p in polies])])
+                    (listener.listen if hasattr(listener, "listen") else listener)(t, snap)
         return outs[0] if single else outs

@@ -229,6 +229,13 @@ int vsr_batch_results_device(vsr_batch* b, void** dptr, size_t* bytes);
    of doubles written, or <0.                                                   */
 long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* out, size_t capacity);
 
+/* What a VoxelPoly carries besides its geometry (Voxel.java:605-616), per tick, for robot r
+   (< trajectory_robots): out[tick][voxel][2] = Touch.isTouchingGround (0/1),
+   Voxel.getLastAppliedForce, voxels in Grid.values() order.  With vsr_batch_trajectory this is
+   all an Outcome.Observation holds (Locomotion.java:198-202).  Returns the number of doubles
+   written, or <0.                                                                          */
+long long vsr_batch_voxel_trace(vsr_batch* b, size_t robot, double* out, size_t capacity);
+
 /* Facts about the compiled batch. */
 size_t vsr_batch_voxel_steps(const vsr_batch* b); /* sum over robots of voxels*ticks */
 int vsr_batch_n_ticks(const vsr_batch* b);

@@ -32,6 +32,7 @@ class vsr_oracle_probe(C.Structure):
         ("signals", C.POINTER(C.c_double)), ("voxel_stride", C.c_size_t),
         ("readings", C.POINTER(C.c_double)), ("reading_stride", C.c_size_t),
         ("n_contacts", C.POINTER(C.c_int32)), ("pos_iters", C.POINTER(C.c_int32)),
+        ("touch", C.POINTER(C.c_double)),
     ]
 
 
@@ -91,7 +92,9 @@ def run(bd, order=ORDER_CANONICAL, seed=0, n_threads=1, max_ticks=0, robot_begin
         p.trajectory, p.body_stride = _dp(probes["trajectory"]), 4 * maxv
     if signals:
         probes["signals"] = np.zeros((rows, nt, maxv))
+        probes["touch"] = np.zeros((rows, nt, maxv))
         p.signals, p.voxel_stride = _dp(probes["signals"]), maxv
+        p.touch = _dp(probes["touch"])
     if readings:
         mr = max(1, max(bd.n_readings))
         probes["readings"] = np.zeros((rows, nt, mr))

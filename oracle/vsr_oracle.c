@@ -1497,6 +1497,10 @@ static void run_robot(ORun* R, size_t ridx) {
         double* o = pb->readings + ((size_t)row * R->nticks + k) * pb->reading_stride;
         for (int q = 0; q < r->n_readings && (size_t)q < pb->reading_stride; q++) o[q] = r->readings[q];
       }
+      if (pb->touch) {
+        double* o = pb->touch + ((size_t)row * R->nticks + k) * pb->voxel_stride;
+        for (int v = 0; v < r->nv && (size_t)v < pb->voxel_stride; v++) o[v] = r->touch[v] ? 1.0 : 0.0;
+      }
       if (pb->n_contacts) pb->n_contacts[(size_t)row * R->nticks + k] = r->ncontacts;
       if (pb->pos_iters) pb->pos_iters[(size_t)row * R->nticks + k] = iters;
     }

@@ -51,8 +51,9 @@ typedef struct vsr_oracle_probe {
   size_t voxel_stride;
   double* readings;     /* [robots][ticks][reading_stride] sensor readings, voxel order */
   size_t reading_stride;
-  int32_t* n_contacts;  /* [robots][ticks] number of ground contact constraints      */
+  int32_t* n_contacts;  /* [robots][ticks] number of contact constraints (all kinds)   */
   int32_t* pos_iters;   /* [robots][ticks] position iterations actually run          */
+  double* touch;        /* [robots][ticks][voxel_stride] Touch.isTouchingGround (0/1) */
 } vsr_oracle_probe;
 
 void vsr_oracle_default_opts(vsr_oracle_opts* o);

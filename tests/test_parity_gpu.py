@@ -239,3 +239,37 @@ def test_locomotion_apply_entry_point():
     assert one.get_distance() == outs[1].get_distance()
     assert all(np.isfinite(o.get_velocity()) for o in outs)
     assert outs[0].get_time() == pytest.approx(3.0 - 1 / 60, abs=1e-9) or outs[0].get_time() == pytest.approx(3.0, abs=1e-9)
+
+
+def test_observations_and_listener_through_the_api():
+    """``Locomotion.apply(robot, listener)`` with the per-tick Observation map.
+    The device dumps (bodies + touch / applied force per voxel) against the oracle's probes, and the
+    per-tick Outcome API on top of them."""
+    loco = helpers.locomotion(2.0)
+    robots = helpers.phase_robots(3, seed=4)   # (one controller kind per batch)
+    seen = []
+    outs = loco.apply(robots, listener=lambda t, snap: seen.append((t, snap)), precision=F64)
+    bd = loco.compile(robots, precision=F64)
+    ores, pr = oracle.run(bd, trajectory=True, signals=True)
+    assert len(seen) == 3 * 121 and seen[0][1].get_children()[1].snapshottable_class == "Robot"
+    tt = H.tick_times(2.0, 1 / 60)
+    for i, out in enumerate(outs):
+        obs = out.get_observations()
+        assert list(obs) == pytest.approx(list(tt))
+        assert out.get_distance() == pytest.approx(float(ores[i]["last_center_x"] - ores[i]["first_center_x"]), abs=1e-7)
+        assert out.get_control_energy() == pytest.approx(
+            float(ores[i]["control_energy_last"] - ores[i]["control_energy_first"]), rel=1e-7)
+        assert out.get_area_ratio_energy() == pytest.approx(
+            float(ores[i]["area_ratio_energy_last"] - ores[i]["area_ratio_energy_first"]), rel=1e-7)
+        for k in (0, 40, 120):
+            polies = [v for v in obs[tt[k]].voxel_polies.values() if v is not None]
+            touch = [v.is_touching_ground() for v in polies]
+            force = [v.get_last_applied_force() for v in polies]
+            assert touch == [bool(b) for b in pr["touch"][i, k, :len(polies)]]
+            assert force == pytest.approx(list(pr["signals"][i, k, :len(polies)]), abs=1e-9)
+        assert any(v.is_touching_ground() for o in obs.values() for v in o.voxel_polies.values() if v is not None)
+        assert len(out.get_center_x_velocity_spectrum(0.0, 10.0, 8)) == 8
+        assert out.get_average_posture(6).count(lambda b: b) > 6
+    # the record-only path (no per-tick dump) gives the same summary
+    fast = loco.apply(robots, precision=F64)
+    assert [o.get_distance() for o in fast] == pytest.approx([o.get_distance() for o in outs], abs=1e-9)
