@@ -7,7 +7,8 @@ fallback.
 """
 from . import _abi as abi  # noqa: F401
 from .hmsrobots import (  # noqa: F401
-    AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DoubleRange, Grid,
+    AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DistributedSensing, DistributedSensingNonDirectional,
+    DoubleRange, Grid,
     JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotShape, RobotUtils,
     Sensor, Settings, Snapshot, SoftNormalization, TimeFunctions, Touch, Trend, Velocity, Voxel, VsrError,
     compile_batch, tick_times,

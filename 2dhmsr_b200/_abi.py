@@ -43,6 +43,8 @@ VSR_AXIS_Y = 2
 VSR_CTRL_PHASE_SIN = 0
 VSR_CTRL_TABULATED = 1
 VSR_CTRL_MLP = 2
+VSR_CTRL_DISTRIBUTED = 3
+VSR_CTRL_DISTRIBUTED_ND = 4
 
 VSR_ACT = {"RELU": 0, "SIGMOID": 1, "SIN": 2, "TANH": 3, "SIGN": 4, "IDENTITY": 5}
 
@@ -128,7 +130,7 @@ class vsr_batch_desc(C.Structure):
         ("robot_shape", C.POINTER(C.c_int32)),
         ("material", vsr_material),
         ("mlp_activation", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("distributed_signals", C.c_int32),
         ("params", C.POINTER(C.c_double)),
         ("param_offsets", C.POINTER(C.c_size_t)),
         ("final_t", C.c_double),

@@ -208,7 +208,9 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     if (d->terrain_xs[i] < d->terrain_xs[i - 1])
       return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted");  // Ground.java:55-58
   if (!d->params || !d->param_offsets) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
-  if (d->controller_kind < VSR_CTRL_PHASE_SIN || d->controller_kind > VSR_CTRL_MLP)
+  if (d->controller_kind >= VSR_CTRL_DISTRIBUTED && (d->distributed_signals < 0 || d->distributed_signals > 4))
+    return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: 0..4 signals per side are supported");
+  if (d->controller_kind < VSR_CTRL_PHASE_SIN || d->controller_kind > VSR_CTRL_DISTRIBUTED_ND)
     return fail(VSR_ERR_INVALID_ARGUMENT, "unknown controller kind");
   const vsr_material& m = d->material;
   {
@@ -422,7 +424,36 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     // controller layout
     if (d->controller_kind == VSR_CTRL_PHASE_SIN) S.n_params = 2 + nv;
     else if (d->controller_kind == VSR_CTRL_TABULATED) S.n_params = nt * nv;
-    else {
+    else if (d->controller_kind >= VSR_CTRL_DISTRIBUTED) {
+      // one MultiLayerPerceptron per voxel: nOfInputs = readings + 4 * signals, nOfOutputs = 1 + 4 * signals
+      // (DistributedSensing.java:141-147); hidden sizes shared; weights stay in flat order per voxel
+      if (sh.n_hidden < 0 || sh.n_hidden + 2 > MAX_LAYERS) {
+        delete b;
+        return fail(VSR_ERR_UNSUPPORTED, "too many MLP layers");
+      }
+      const int sg = d->distributed_signals;
+      S.n_layers = sh.n_hidden + 2;
+      for (int i = 0; i < sh.n_hidden; i++) {
+        S.neurons[1 + i] = sh.hidden[i];
+        if (sh.hidden[i] <= 0 || sh.hidden[i] > VSR_DIST_WIDTH) {
+          delete b;
+          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: hidden layers of 1..24 neurons are supported");
+        }
+      }
+      S.neurons[0] = 0;  // per voxel
+      S.neurons[S.n_layers - 1] = d->controller_kind == VSR_CTRL_DISTRIBUTED_ND ? 1 + sg : 1 + 4 * sg;
+      int off = 0;
+      for (int v = 0; v < nv; v++) {
+        const int nin = (v + 1 < nv ? S.read_off[v + 1] : S.n_readings) - S.read_off[v] + 4 * sg;
+        S.dist_off[v] = off;
+        int prev = nin;
+        for (int i = 1; i < S.n_layers; i++) {
+          off += S.neurons[i] * (prev + 1);
+          prev = S.neurons[i];
+        }
+      }
+      S.n_params = off;
+    } else {
       if (sh.n_hidden < 0 || sh.n_hidden + 2 > MAX_LAYERS) {
         delete b;
         return fail(VSR_ERR_UNSUPPORTED, "too many MLP layers");
@@ -461,7 +492,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     if (np != (size_t)S.n_params) {
       delete b;
       char msg[256];
-      if (d->controller_kind == VSR_CTRL_MLP)  // MultiLayerPerceptron.java:56-62
+      if (d->controller_kind >= VSR_CTRL_MLP)  // MultiLayerPerceptron.java:56-62
         snprintf(msg, sizeof msg, "Wrong number of weights: %d expected, %zu found", S.n_params, np);
       else
         snprintf(msg, sizeof msg, "robot %zu: %d controller parameters expected, %zu found", r, S.n_params, np);
@@ -647,6 +678,8 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.rest_e_self = (real)std::max(m.restitution, m.restitution);  // max(e1, e2)
   P.spring_mask = b->spring_mask;
   P.mlp_act = d.mlp_activation;
+  P.dist_signals = d.controller_kind >= VSR_CTRL_DISTRIBUTED ? d.distributed_signals : -1;
+  P.dist_nd = d.controller_kind == VSR_CTRL_DISTRIBUTED_ND ? 1 : 0;
   P.debug_robot = -1;
   P.debug_tick = -1;
   if (const char* dbg = getenv("VSR_DEBUG")) {  // "robot:tick" (bucket index)

@@ -35,6 +35,7 @@ constexpr int MAX_SENS = 4;    // sensors per voxel
 constexpr int MAX_READ = 6;    // readings per voxel
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
+#define VSR_DIST_WIDTH 24      // DistributedSensing: widest layer of a voxel's MLP (6 readings + 4 x 4 signals = 22 inputs)
 constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
@@ -63,6 +64,7 @@ struct ShapeDev {
   int neurons[MAX_LAYERS];
   int layer_off[MAX_LAYERS];  // offset of layer i's (transposed) weights
   int n_params;               // controller parameters per robot (device layout)
+  int dist_off[MAX_VOX];      // DistributedSensing: offset of each voxel's weights in the robot's parameters
 };
 
 template <typename real>
@@ -99,6 +101,8 @@ struct Params {
   int spring_mode;       // 0 reduced mass, 1 effective mass
   unsigned spring_mask;  // bit s = spring s present (scaffoldings)
   int mlp_act;
+  int dist_signals;      // DistributedSensing: signals per side; < 0 for the other controllers
+  int dist_nd;           // DistributedSensingNonDirectional: one set of signals for all neighbours
   int smem_per_warp;     // reals of staging per warp
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
@@ -1150,6 +1154,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
     for (int q = 0; q < MAX_READ; q++) readings[q] = real(0);
     double first_cx = 0, first_cy = 0, first_are = 0, first_ce = 0;
+    // DistributedSensing: the signals this voxel emitted at the previous tick, [towards N, E, S, W][4]
+    real lsig[CTRL == CTRL_MLP ? 16 : 1];
+#pragma unroll
+    for (int q = 0; q < (CTRL == CTRL_MLP ? 16 : 1); q++) lsig[q] = real(0);
 
     SSYNC()
     for (int q = st; q < 66; q += sdim) lhd[q] = 0;  // no contacts yet
@@ -1816,6 +1824,72 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         f = (real)(sin(2.0 * 3.14159265358979323846 * fr * P.tick_t[tick] + ph) * am);
       } else if (CTRL == CTRL_TABULATED) {
         f = par[(size_t)tick * nvox + (active ? v : 0)];
+      } else if (P.dist_signals >= 0) {
+        // DistributedSensing.computeControlSignals (:150-186): every voxel runs its own
+        // MultiLayerPerceptron on (own readings, what its N, E, S, W neighbours emitted towards it at
+        // the previous tick); output 0 is the control signal, the rest is what it emits now.
+        // Dir: N = (0, -1) = the voxel below, E = right, S = above, W = left; a neighbour's signals
+        // towards this voxel sit at the opposite direction's index (Dir.adjacent).
+        const int sg = P.dist_signals;
+        real a[VSR_DIST_WIDTH], b2[VSR_DIST_WIDTH];
+        int nin = 0;
+        {
+          const int base = S.read_off[active ? v : 0];
+          const int nr = active ? ((v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base) : 0;
+#pragma unroll
+          for (int q = 0; q < MAX_READ; q++)
+            if (q < nr) a[q] = readings[q];
+          nin = nr;
+          // gather: side (kernel numbering 0 left, 1 right, 2 down, 3 up) of Dir d, and the slot the
+          // neighbour wrote for the opposite direction
+          EXP(0, lsig[0]) EXP(1, lsig[1]) EXP(2, lsig[2]) EXP(3, lsig[3]) EXP(4, lsig[4]) EXP(5, lsig[5])
+          EXP(6, lsig[6]) EXP(7, lsig[7]) EXP(8, lsig[8]) EXP(9, lsig[9]) EXP(10, lsig[10]) EXP(11, lsig[11])
+          EXP(12, lsig[12]) EXP(13, lsig[13]) EXP(14, lsig[14]) EXP(15, lsig[15])
+          EXSYNC()
+#pragma unroll
+          for (int dir = 0; dir < 4; dir++) {
+            const int side = dir == 0 ? 2 : (dir == 1 ? 1 : (dir == 2 ? 3 : 0));
+            const int opp = (dir + 2) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              // (non-directional: everybody reads what the neighbour keeps in slot 0)
+              const real gd = EXG(opp * 4 + q, lsig[opp * 4 + q], nl[side]);
+              const real gn = EXG(q, lsig[q], nl[side]);
+              const real g = P.dist_nd ? gn : gd;
+              if (q < sg) a[nin + dir * sg + q] = has[side] ? g : real(0);
+            }
+          }
+          nin += 4 * sg;
+          EXFLIP()
+        }
+        const real* W = par + (active ? S.dist_off[v] : 0);
+        int np = nin;
+#pragma unroll 1
+        for (int q = 0; q < np; q++) a[q] = activation<real>(P.mlp_act, a[q]);
+        real* pa = a;
+        real* pb = b2;
+#pragma unroll 1
+        for (int li = 1; li < S.n_layers; li++) {
+          const int nn = S.neurons[li];
+          if (active) {
+#pragma unroll 1
+            for (int j = 0; j < nn; j++) {
+              real sum = W[0];
+#pragma unroll 1
+              for (int k = 1; k < np + 1; k++) sum = sum + pa[k - 1] * W[k];
+              pb[j] = activation<real>(P.mlp_act, sum);
+              W += np + 1;
+            }
+          }
+          np = nn;
+          real* t = pa; pa = pb; pb = t;
+        }
+        f = active ? pa[0] : real(0);
+#pragma unroll
+        for (int dir = 0; dir < 4; dir++)
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (q < sg && !(P.dist_nd && dir > 0)) lsig[dir * 4 + q] = active ? pa[1 + dir * sg + q] : real(0);
       } else {
         // CentralizedSensing + MultiLayerPerceptron.apply: inputs = readings of all voxels
         // in voxel order; lane j of the robot evaluates neurons j, j+nvox, ...

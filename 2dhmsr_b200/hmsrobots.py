@@ -353,6 +353,29 @@ class MultiLayerPerceptron:
     def get_params(self):
         return self.weights
 
+    _ACT = {
+        "RELU": lambda x: 0.0 if x < 0 else x, "SIGMOID": lambda x: 1.0 / (1.0 + math.exp(-x)),
+        "SIN": math.sin, "TANH": math.tanh, "SIGN": lambda x: (x > 0) - (x < 0) + 0.0, "IDENTITY": lambda x: x,
+    }
+
+    def apply(self, x: Sequence[float]):
+        """MultiLayerPerceptron.apply (:168-189) on the host, in double (reference of the device's
+        arithmetic in tests; the product path evaluates controllers in the kernel)."""
+        if len(x) != self.neurons[0]:
+            raise ValueError(f"Expected input length is {self.neurons[0]}: found {len(x)}")
+        f = self._ACT[self.activation]
+        w = self.unflat(self.weights, self.neurons)
+        a = [f(float(v)) for v in x]
+        for i in range(1, len(self.neurons)):
+            b = []
+            for j in range(self.neurons[i]):
+                s = w[i - 1][j][0]
+                for k in range(1, self.neurons[i - 1] + 1):
+                    s = s + a[k - 1] * w[i - 1][j][k]
+                b.append(f(s))
+            a = b
+        return a
+
     def get_input_dimension(self):
         return self.neurons[0]
 
@@ -388,6 +411,113 @@ class CentralizedSensing(Controller):
 
     def params(self, voxels, tick_times):
         return np.asarray(self.function.weights, dtype=np.float64)
+
+
+class DistributedSensing(Controller):
+    """controllers/DistributedSensing.java: one function per voxel, fed with the voxel's sensor readings
+    and with ``signals`` values from each of its N, E, S, W neighbours' previous outputs; output 0 is the
+    control signal, the other ``4 * signals`` are emitted towards the neighbours (:141-207).  The
+    accelerated path takes one MultiLayerPerceptron per voxel (Starter.java:176-190), all with the same
+    activation and hidden layer sizes."""
+    KIND = A.VSR_CTRL_DISTRIBUTED
+    DIRS = ((0, -1, 0), (1, 0, 1), (0, 1, 2), (-1, 0, 3))  # N, E, S, W: dx, dy, index (:83-101)
+    ADJACENT = (2, 3, 0, 1)                                  # Dir.adjacent: N<->S, E<->W
+
+    def __init__(self, voxels: Grid, signals: int):
+        self.signals = int(signals)
+        self.n_of_input_grid = Grid.create(voxels.w, voxels.h, lambda x, y: 0 if voxels.get(x, y) is None
+                                           else self.n_of_inputs_of(voxels.get(x, y), self.signals))
+        self.n_of_output_grid = Grid.create(voxels.w, voxels.h, lambda x, y: 0 if voxels.get(x, y) is None
+                                            else self.n_of_outputs_of(voxels.get(x, y), self.signals))
+        self.functions = Grid.create(voxels.w, voxels.h, None)
+        self.reset()
+
+    @staticmethod
+    def n_of_inputs_of(voxel: "Voxel", signals: int) -> int:  # :141-143
+        return signals * 4 + sum(len(s.domains()) for s in voxel.get_sensors())
+
+    @staticmethod
+    def n_of_outputs_of(voxel: "Voxel", signals: int) -> int:  # :145-147
+        return 1 + signals * 4
+
+    def n_of_inputs(self, x: int, y: int) -> int:
+        return self.n_of_input_grid.get(x, y)
+
+    def n_of_outputs(self, x: int, y: int) -> int:
+        return self.n_of_output_grid.get(x, y)
+
+    def get_functions(self) -> Grid:
+        return self.functions
+
+    def reset(self) -> None:  # :209-222
+        w, h = self.n_of_input_grid.w, self.n_of_input_grid.h
+        self.last_signals = Grid.create(w, h, lambda x, y: [0.0] * (4 * self.signals)
+                                        if self.n_of_output_grid.get(x, y) else None)
+
+    def _last_signals(self, x: int, y: int):  # getLastSignals :188-207
+        vals = [0.0] * (4 * self.signals)
+        c = 0
+        for dx, dy, _ in self.DIRS:
+            ax, ay = x + dx, y + dy
+            adj = self.last_signals.get(ax, ay) if 0 <= ax < self.last_signals.w and 0 <= ay < self.last_signals.h else None
+            if adj is not None:
+                i = self.ADJACENT[self.DIRS.index((dx, dy, _))]
+                vals[c:c + self.signals] = adj[i * self.signals:(i + 1) * self.signals]
+            c += self.signals
+        return vals
+
+    def compute_control_signals(self, t: float, readings: Grid) -> Grid:
+        """computeControlSignals (:150-186) on a grid of per-voxel sensor readings (host-side reference
+        of the device's arithmetic; the functions are evaluated with ``MultiLayerPerceptron.apply``)."""
+        out = Grid.create(readings.w, readings.h, None)
+        cur = Grid.create(readings.w, readings.h, None)
+        for (x, y), r in readings:
+            if r is None:
+                continue
+            inputs = list(r) + self._last_signals(x, y)
+            f = self.functions.get(x, y)
+            o = f.apply(inputs) if f is not None else [0.0] * self.n_of_outputs(x, y)
+            out.set(x, y, float(o[0]))
+            cur.set(x, y, [float(v) for v in o[1:]])
+        for (x, y), c in cur:
+            if c is not None:
+                self.last_signals.set(x, y, c)
+        return out
+
+    def params(self, voxels, tick_times):
+        ws = []
+        for (x, y), v in voxels:
+            if v is None:
+                continue
+            f = self.functions.get(x, y)
+            if not isinstance(f, MultiLayerPerceptron):
+                raise NotImplementedError("DistributedSensing: the accelerated path needs a MultiLayerPerceptron "
+                                          f"for every voxel (none at {x},{y})")
+            if f.get_input_dimension() != self.n_of_inputs(x, y) or f.get_output_dimension() != self.n_of_outputs(x, y):
+                raise ValueError(f"Wrong dimension of input or output in the function of voxel ({x},{y})")
+            ws.append(np.asarray(f.weights, dtype=np.float64))
+        return np.concatenate(ws)
+
+
+class DistributedSensingNonDirectional(DistributedSensing):
+    """controllers/DistributedSensingNonDirectional.java: ``1 + signals`` outputs; every neighbour reads the
+    same ``signals`` values (:57-78)."""
+    KIND = A.VSR_CTRL_DISTRIBUTED_ND
+
+    @staticmethod
+    def n_of_outputs_of(voxel: "Voxel", signals: int) -> int:  # :57-59
+        return 1 + signals
+
+    def _last_signals(self, x: int, y: int):  # :61-78
+        vals = [0.0] * (4 * self.signals)
+        c = 0
+        for dx, dy, _ in self.DIRS:
+            ax, ay = x + dx, y + dy
+            adj = self.last_signals.get(ax, ay) if 0 <= ax < self.last_signals.w and 0 <= ay < self.last_signals.h else None
+            if adj is not None:
+                vals[c:c + self.signals] = adj[0:self.signals]
+            c += self.signals
+        return vals
 
 
 class Robot:
@@ -748,6 +878,7 @@ def compile_batch(
     robot_shape = np.zeros(len(robots), dtype=np.int32)
     material = None
     activation = None
+    dist_signals = None
     plist = []
     for i, r in enumerate(robots):
         vox = r.voxels
@@ -766,6 +897,23 @@ def compile_batch(
                 activation = act
             elif activation != act:
                 raise ValueError("one MLP activation per batch")
+        elif kind in (A.VSR_CTRL_DISTRIBUTED, A.VSR_CTRL_DISTRIBUTED_ND):
+            fs = [r.controller.functions.get(x, y) for (x, y), v in vox if v is not None]
+            if any(not isinstance(f, MultiLayerPerceptron) for f in fs):
+                raise NotImplementedError("DistributedSensing: the accelerated path needs a MultiLayerPerceptron for every voxel")
+            hs = {tuple(f.neurons[1:-1]) for f in fs}
+            acts = {A.VSR_ACT[f.activation] for f in fs}
+            if len(hs) != 1 or len(acts) != 1:
+                raise NotImplementedError("DistributedSensing: one activation and one set of hidden layer sizes per robot")
+            hidden, act = hs.pop(), acts.pop()
+            if activation is None:
+                activation = act
+            elif activation != act:
+                raise ValueError("one MLP activation per batch")
+            if dist_signals is None:
+                dist_signals = r.controller.signals
+            elif dist_signals != r.controller.signals:
+                raise ValueError("one DistributedSensing signal count per batch")
         for v in vox.values():
             if v is None:
                 continue
@@ -784,6 +932,7 @@ def compile_batch(
         raise ValueError("robot without voxels")
     d.material = A.vsr_material.from_buffer_copy(material)
     d.mlp_activation = activation if activation is not None else 0
+    d.distributed_signals = dist_signals if dist_signals is not None else 0
 
     arr = (A.vsr_shape * len(shapes_c))()
     for k, (w, h, mask, sens, hidden) in enumerate(shapes_c):

@@ -140,6 +140,17 @@ typedef struct vsr_shape {
                                 .java:168-189. params = flat weights in
                                 MultiLayerPerceptron.flat order (:139-151), bias first     */
 
+#define VSR_CTRL_DISTRIBUTED 3 /* DistributedSensing.java:150-207 with one MultiLayerPerceptron per
+                                  voxel (Starter.java:176-190): inputs = the voxel's sensor readings
+                                  then `distributed_signals` values from each of the N, E, S, W
+                                  neighbours' previous outputs; outputs = control + 4 * signals.
+                                  All voxels share the hidden layer sizes (vsr_shape.hidden).
+                                  params = the voxels' flat weights (MultiLayerPerceptron.flat
+                                  order), concatenated in Grid.values() order                  */
+
+#define VSR_CTRL_DISTRIBUTED_ND 4 /* DistributedSensingNonDirectional.java:57-78: outputs = control +
+                                     `distributed_signals` values, the same for all four neighbours   */
+
 #define VSR_ACT_RELU 0 /* MultiLayerPerceptron.java:89-95, enum order */
 #define VSR_ACT_SIGMOID 1
 #define VSR_ACT_SIN 2
@@ -165,7 +176,7 @@ typedef struct vsr_batch_desc {
   vsr_material material;      /* one material per batch (default Voxel) */
   /* controller parameters, ragged per robot */
   int32_t mlp_activation;      /* VSR_ACT_* */
-  int32_t reserved0;
+  int32_t distributed_signals; /* VSR_CTRL_DISTRIBUTED: signals per side (DistributedSensing.java:50) */
   const double* params;        /* concatenated per-robot parameter vectors */
   const size_t* param_offsets; /* [n_robots+1] */
   /* Locomotion task: Locomotion.java:50-59 */

@@ -200,6 +200,12 @@ typedef struct {
   /* MLP */
   int n_layers;
   int32_t* neurons;
+  /* DistributedSensing */
+  int* vox_read_off; /* [nv + 1] first reading of each voxel */
+  int* vox_at;       /* [w * h] voxel index at grid cell, or -1 */
+  int grid_w, grid_h;
+  double* last_sig;  /* [nv][4 * signals] lastSignalsGrid */
+  double* cur_sig;   /* [nv][4 * signals] currentSignalsGrid */
 } ORobot;
 
 typedef struct {
@@ -467,6 +473,31 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   r->n_readings = off_r;
   r->readings = (double*)calloc((size_t)(off_r + 1), sizeof(double));
 
+  /* --- DistributedSensing: per-voxel reading ranges, grid lookup, signal grids (reset() = zeros) --- */
+  r->vox_read_off = (int*)calloc((size_t)nv + 1, sizeof(int));
+  {
+    int acc = 0, si2 = 0;
+    for (int v = 0; v < nv; v++) {
+      r->vox_read_off[v] = acc;
+      if (sh->sensor_offsets)
+        for (int k = sh->sensor_offsets[v]; k < sh->sensor_offsets[v + 1]; k++, si2++) acc += sensor_dim(&sh->sensors[k]);
+    }
+    r->vox_read_off[nv] = acc;
+  }
+  r->grid_w = sh->w;
+  r->grid_h = sh->h;
+  r->vox_at = (int*)malloc(sizeof(int) * (size_t)(sh->w * sh->h));
+  for (int i = 0; i < sh->w * sh->h; i++) r->vox_at[i] = -1;
+  for (int v = 0; v < nv; v++) r->vox_at[r->vox_gy[v] * sh->w + r->vox_gx[v]] = v;
+  r->last_sig = r->cur_sig = NULL;
+  if (d->controller_kind >= VSR_CTRL_DISTRIBUTED) {
+    size_t ns4 = (size_t)nv * 4 * (size_t)(d->distributed_signals > 0 ? d->distributed_signals : 1);
+    r->last_sig = (double*)calloc(ns4, sizeof(double));
+    r->cur_sig = (double*)calloc(ns4, sizeof(double));
+    r->n_layers = 2 + sh->n_hidden;
+    r->neurons = (int32_t*)malloc(sizeof(int32_t) * (size_t)r->n_layers);
+    for (int i = 0; i < sh->n_hidden; i++) r->neurons[1 + i] = sh->hidden[i];
+  }
   /* --- MLP topology: CentralizedSensing.nOfInputs/nOfOutputs, :68-83 --- */
   if (d->controller_kind == VSR_CTRL_MLP) {
     r->n_layers = 2 + sh->n_hidden;
@@ -479,6 +510,10 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
 }
 
 static void robot_free(ORobot* r) {
+  free(r->vox_read_off);
+  free(r->vox_at);
+  free(r->last_sig);
+  free(r->cur_sig);
   free(r->vox_gx);
   free(r->vox_gy);
   free(r->bodies);
@@ -1405,6 +1440,33 @@ static void robot_control(ORun* R, ORobot* r, size_t ridx, int tick, double* sig
     for (int v = 0; v < r->nv; v++) out[v] = sin(2.0 * PI * P[0] * t + P[2 + v]) * P[1]; /* PhaseSin.java:61 */
   } else if (d->controller_kind == VSR_CTRL_TABULATED) {
     for (int v = 0; v < r->nv; v++) out[v] = P[(size_t)tick * (size_t)r->nv + v];
+  } else if (d->controller_kind >= VSR_CTRL_DISTRIBUTED) {
+    /* DistributedSensing.computeControlSignals (:150-186) with one MultiLayerPerceptron per voxel
+       (Starter.java:176-190).  Dir order N(0,-1) E(1,0) S(0,1) W(-1,0) (:83-101); a neighbour's
+       signals towards this voxel sit at Dir.adjacent(dir).index (:188-207). */
+    static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}, ADJ[4] = {2, 3, 0, 1};
+    const int sg = d->distributed_signals;
+    const int nd = d->controller_kind == VSR_CTRL_DISTRIBUTED_ND; /* DistributedSensingNonDirectional.java:57-78 */
+    const double* W = P;
+    double in[64], outv[64];
+    for (int v = 0; v < r->nv; v++) {
+      int nr = r->vox_read_off[v + 1] - r->vox_read_off[v];
+      for (int q = 0; q < nr; q++) in[q] = r->readings[r->vox_read_off[v] + q]; /* getSensorReadings first */
+      int c = nr;
+      for (int dir = 0; dir < 4; dir++) {
+        int ax = r->vox_gx[v] + DX[dir], ay = r->vox_gy[v] + DY[dir];
+        int a = (ax >= 0 && ax < r->grid_w && ay >= 0 && ay < r->grid_h) ? r->vox_at[ay * r->grid_w + ax] : -1;
+        for (int q = 0; q < sg; q++) in[c + q] = a >= 0 ? r->last_sig[(size_t)a * 4 * sg + (nd ? 0 : ADJ[dir] * sg) + q] : 0.0;
+        c += sg;
+      }
+      r->neurons[0] = c;
+      r->neurons[r->n_layers - 1] = nd ? 1 + sg : 1 + 4 * sg;
+      vsr_oracle_mlp_apply(d->mlp_activation, r->neurons, r->n_layers, W, in, outv);
+      for (int i = 1; i < r->n_layers; i++) W += (size_t)r->neurons[i] * (size_t)(r->neurons[i - 1] + 1);
+      out[v] = outv[0];
+      for (int q = 0; q < (nd ? sg : 4 * sg); q++) r->cur_sig[(size_t)v * 4 * sg + q] = outv[1 + q];
+    }
+    for (int q = 0; q < r->nv * 4 * sg; q++) r->last_sig[q] = r->cur_sig[q];
   } else {
     vsr_oracle_mlp_apply(d->mlp_activation, r->neurons, r->n_layers, P, r->readings, out);
   }

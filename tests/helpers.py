@@ -43,6 +43,24 @@ def mlp_robots(n, shape="worm-8x2", sensors="uniform-ax+t-0", hidden=(), seed=1,
     return out
 
 
+def distributed_robots(n, shape="biped-4x3", sensors="uniform-ax+t-0", signals=1, hidden=(2,), seed=1, activation="TANH",
+                       directional=True):
+    """Starter.java:176-190: DistributedSensing with one MLP per voxel, weights ~ U(-1, 1)."""
+    rng = np.random.default_rng(seed)
+    body = body_of(shape, sensors)
+    out = []
+    for _ in range(n):
+        ds = (H.DistributedSensing if directional else H.DistributedSensingNonDirectional)(body, signals)
+        for (x, y), v in body:
+            if v is None:
+                continue
+            nin, nout = ds.n_of_inputs(x, y), ds.n_of_outputs(x, y)
+            nw = H.MultiLayerPerceptron.count_weights([nin, *hidden, nout])
+            ds.get_functions().set(x, y, H.MultiLayerPerceptron(activation, nin, list(hidden), nout, rng.uniform(-1, 1, size=nw)))
+        out.append(H.Robot(ds, body))
+    return out
+
+
 def locomotion(final_t=20.0, terrain="flat", **settings):
     return H.Locomotion(final_t, H.Locomotion.create_terrain(terrain), H.Settings().set(**settings))
 

@@ -160,3 +160,32 @@ def test_intra_robot_contacts_follow_the_setting():
     a, _ = oracle.run(helpers.locomotion(2.0, self_collision=1).compile(one))
     b, _ = oracle.run(helpers.locomotion(2.0, self_collision=0).compile(one))
     assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("directional", [True, False])
+def test_distributed_sensing_matches_the_host_restatement(directional):
+    # SURVEY 8(f) rank 2.  The oracle's per-tick readings fed through the Python DistributedSensing
+    # (a line-by-line restatement of DistributedSensing.java:150-207 over MultiLayerPerceptron.apply)
+    # must give the forces the oracle applied.
+    robots = helpers.distributed_robots(2, signals=2, hidden=(3,), seed=9, directional=directional)
+    bd = helpers.locomotion(1.0).compile(robots)
+    res, pr = oracle.run(bd, signals=True, readings=True)
+    assert np.all(res["status"] == 0)
+    body = robots[0].get_voxels()
+    cells = [(x, y) for (x, y), v in body if v is not None]
+    for i, r in enumerate(robots):
+        ctrl = r.get_controller()
+        ctrl.reset()
+        for k in range(0, 60):
+            rd = H.Grid.create(body.w, body.h, None)
+            for j, (x, y) in enumerate(cells):
+                rd.set(x, y, list(pr["readings"][i, k, 2 * j:2 * j + 2]))   # uniform-ax+t-0: 2 readings per voxel
+            out = ctrl.compute_control_signals(0.0, rd)
+            want = [max(-1.0, min(1.0, out.get(x, y))) for (x, y) in cells]   # Voxel.applyForce clamps
+            assert pr["signals"][i, k, :len(cells)] == pytest.approx(want, abs=1e-12), k
+    # signals matter: the same weights with the neighbours' messages cut (signals = 0 is another network)
+    assert np.abs(pr["signals"][0, 30] - pr["signals"][0, 1]).max() > 1e-6
+    with pytest.raises(NotImplementedError):
+        broken = helpers.distributed_robots(1)[0]
+        broken.get_controller().get_functions().set(0, 0, None)
+        helpers.locomotion(1.0).compile([broken])

@@ -273,3 +273,19 @@ def test_observations_and_listener_through_the_api():
     # the record-only path (no per-tick dump) gives the same summary
     fast = loco.apply(robots, precision=F64)
     assert [o.get_distance() for o in fast] == pytest.approx([o.get_distance() for o in outs], abs=1e-9)
+
+
+@pytest.mark.parametrize("shape,signals,hidden,directional", [
+    ("biped-4x3", 1, (2,), True), ("worm-8x2", 2, (3,), True), ("box-6x6", 1, (), True), ("biped-4x3", 2, (2,), False)])
+def test_fp64_distributed_sensing(shape, signals, hidden, directional):
+    """SURVEY 8(f) rank 2: DistributedSensing (one MLP per voxel, messages between N/E/S/W neighbours;
+    box-6x6 runs the one-block-per-robot variant with the shared-memory neighbour exchange)."""
+    robots = helpers.distributed_robots(3, shape=shape, signals=signals, hidden=hidden, seed=12, directional=directional)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0), robots, F64)
+    nb = 4 * bd.n_voxels[0]
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :nb, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+    assert np.all(res["control_energy_last"] > 0)
+    r32, _ = helpers.gpu_run(helpers.locomotion(3.0).compile(robots))
+    assert np.all(r32["status"] == 0) and np.abs(r32["last_center_x"] - ores["last_center_x"]).max() < 1.5
