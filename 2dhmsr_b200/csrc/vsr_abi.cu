@@ -378,7 +378,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       int s0 = sh.sensor_offsets ? sh.sensor_offsets[v] : 0, s1 = sh.sensor_offsets ? sh.sensor_offsets[v + 1] : 0;
       if (s1 - s0 > MAX_SENS) {
         delete b;
-        return fail(VSR_ERR_UNSUPPORTED, "more than 4 sensors per voxel");
+        return fail(VSR_ERR_UNSUPPORTED, "more than 5 sensors per voxel");
       }
       S.n_sens[v] = (int8_t)(s1 - s0);
       S.read_off[v] = (int16_t)ro;
@@ -386,15 +386,16 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       for (int k = s0; k < s1; k++) {
         const vsr_sensor& q = sh.sensors[k];
         SensorDev& D = S.sens[v][k - s0];
-        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_VELOCITY || q.aggregator < VSR_AGG_NONE ||
+        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_TIME_SIN || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
+            q.aggregator < VSR_AGG_NONE ||
             q.aggregator > VSR_AGG_TREND) {
           delete b;
           return fail(VSR_ERR_INVALID_ARGUMENT, "unknown sensor");
         }
         int dim = sensor_dim(q);
         D.base = (int8_t)q.base; D.axes = (int8_t)q.axes; D.rotated = (int8_t)(q.rotated != 0);
-        D.agg = (int8_t)q.aggregator; D.soft = (int8_t)(q.soft_norm != 0); D.dim = (int8_t)dim;
-        D.max_norm = (float)q.max_velocity_norm; D.interval = (float)q.interval;
+        D.agg = (int8_t)q.aggregator; D.soft = (int8_t)q.soft_norm; D.dim = (int8_t)dim;
+        D.max_norm = q.max_velocity_norm; D.interval = (float)q.interval;
         D.win = 0; D.ch = 0;
         if (q.aggregator != VSR_AGG_NONE) {
           if (!(q.interval > 0)) {

@@ -31,7 +31,7 @@
 namespace vsr {
 
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
-constexpr int MAX_SENS = 4;    // sensors per voxel
+constexpr int MAX_SENS = 5;    // sensors per voxel
 constexpr int MAX_READ = 6;    // readings per voxel
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
@@ -39,14 +39,15 @@ constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
 constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
-enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2 };
+enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2, SENSOR_ANGLE = 3, SENSOR_CONSTANT = 4,
+             SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7 };
 enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
 enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2 };
 
 struct SensorDev {
   int8_t base, axes, rotated, agg, soft, win, ch, dim;
-  float max_norm;
   float interval;
+  double max_norm;  // Velocity: domain bound; Constant / TimeFunction: the value / the frequency
 };
 
 // One shape class (Grid<Boolean> + sensor layout), compiled on the host.
@@ -1763,6 +1764,22 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             raw[0] = area_ratio;
             dmin = real(0.5);
             dmax = real(1.5);
+          } else if (sd.base == SENSOR_ANGLE) {
+            raw[0] = ang;
+            dmin = real(-3.14159265358979323846);
+            dmax = real(3.14159265358979323846);
+          } else if (sd.base == SENSOR_CONSTANT) {
+            raw[0] = (real)sd.max_norm;
+            dmin = r_min(real(0), raw[0]);
+            dmax = r_max(real(1), raw[0]);
+          } else if (sd.base == SENSOR_APPLIED_FORCE) {
+            raw[0] = last_f;  // the force of the previous control step (sensors act before the controller)
+            dmin = real(-1);
+          } else if (sd.base == SENSOR_MALFUNCTION) {
+            raw[0] = real(0);
+          } else if (sd.base == SENSOR_TIME_SIN) {
+            raw[0] = (real)sin(2.0 * 3.14159265358979323846 * (double)sd.max_norm * P.tick_t[tick]);
+            dmin = real(-1);
           } else {
             int c = 0;
             real sa, ca;
@@ -1772,8 +1789,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               // unit(angle + pi/2) = (-sin, cos) (Velocity.java:75 builds it numerically: same to 1 ulp)
               raw[c++] = sd.rotated ? -mvx * sa + mvy * ca : mvy;
             }
-            dmin = -sd.max_norm;
-            dmax = sd.max_norm;
+            dmin = -(real)sd.max_norm;
+            dmax = (real)sd.max_norm;
           }
           real val[2] = {raw[0], raw[1]};
           if (sd.agg != AGG_NONE) {
@@ -1802,10 +1819,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           }
           for (int d = 0; d < sd.dim; d++) {
             real o = val[d];
-            if (sd.soft) {
+            if (sd.soft == 1) {
               real cl = r_min(r_max(o, dmin), dmax);
               real nv = (cl - dmin) / (dmax - dmin);
               o = r_tanh(((nv * real(2)) - real(1)) * real(2)) / real(2) + real(0.5);
+            } else if (sd.soft == 2) {  // Normalization: DoubleRange.normalize
+              o = (r_min(r_max(o, dmin), dmax) - dmin) / (dmax - dmin);
             }
             // static indexing of the register array
 #pragma unroll

@@ -192,6 +192,76 @@ class Velocity(Sensor):  # sensors/Velocity.java:29-80
         return s
 
 
+class Angle(Sensor):  # sensors/Angle.java
+    def domains(self):
+        return [DoubleRange(-math.pi, math.pi)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_ANGLE
+        return s
+
+
+class Constant(Sensor):  # sensors/Constant.java (one value per sensor on the accelerated path)
+    def __init__(self, *values: float):
+        if len(values) != 1:
+            raise NotImplementedError("Constant: one value per sensor on the accelerated path")
+        self.values = [float(v) for v in values]
+
+    def domains(self):
+        lo, hi = min(0.0, min(self.values)), max(1.0, max(self.values))
+        return [DoubleRange(lo, hi) for _ in self.values]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_CONSTANT
+        s.max_velocity_norm = self.values[0]
+        return s
+
+
+class AppliedForce(Sensor):  # sensors/AppliedForce.java
+    def domains(self):
+        return [DoubleRange(-1.0, 1.0)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_APPLIED_FORCE
+        return s
+
+
+class Malfunction(Sensor):  # sensors/Malfunction.java (a non-breakable voxel is never broken)
+    def domains(self):
+        return [DoubleRange(0.0, 1.0)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_MALFUNCTION
+        return s
+
+
+class TimeFunction(Sensor):
+    """sensors/TimeFunction.java.  The accelerated path evaluates ``t -> sin(2 pi f t)`` on [-1, 1] (the
+    "cpg" sensor of RobotUtils.java:57); build it with ``TimeFunction.sin(f)``."""
+
+    def __init__(self, function, min_: float, max_: float, _freq: Optional[float] = None):
+        self.function, self.min, self.max, self._freq = function, min_, max_, _freq
+
+    @staticmethod
+    def sin(frequency: float) -> "TimeFunction":
+        return TimeFunction(lambda t: math.sin(2 * math.pi * frequency * t), -1.0, 1.0, frequency)
+
+    def domains(self):
+        return [DoubleRange(self.min, self.max)]
+
+    def encode(self):
+        if self._freq is None or (self.min, self.max) != (-1.0, 1.0):
+            raise NotImplementedError("TimeFunction: only TimeFunction.sin(f) on [-1, 1] runs on the device")
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_TIME_SIN
+        s.max_velocity_norm = self._freq
+        return s
+
+
 class _Aggregator(Sensor):  # sensors/AggregatorSensor.java:31-66
     KIND = A.VSR_AGG_NONE
 
@@ -233,6 +303,21 @@ class SoftNormalization(Sensor):  # sensors/SoftNormalization.java
     def encode(self):
         s = self.sensor.encode()
         s.soft_norm = 1
+        return s
+
+
+class Normalization(Sensor):  # sensors/Normalization.java
+    def __init__(self, sensor: Sensor):
+        if isinstance(sensor, (SoftNormalization, Normalization)):
+            raise NotImplementedError("nested normalizations are outside the hot path")
+        self.sensor = sensor
+
+    def domains(self):
+        return [DoubleRange(0.0, 1.0) for _ in self.sensor.domains()]
+
+    def encode(self):
+        s = self.sensor.encode()
+        s.soft_norm = A.VSR_NORM_LINEAR
         return s
 
 
@@ -543,8 +628,13 @@ def _params(pattern: str, string: str):
 class RobotUtils:
     """util/RobotUtils.java: body-shape and sensor-layout mini DSLs."""
 
-    PREDEFINED_SENSORS = {  # :38-60 (hot-path subset; TreeMap => sorted keys)
+    PREDEFINED_SENSORS = {  # :38-60 (TreeMap => sorted keys); the lidars "l1", "l5" are not on the device
         "a": lambda x, y: SoftNormalization(AreaRatio()),
+        "cpg": lambda x, y: Normalization(TimeFunction.sin(-1.0)),
+        "m": lambda x, y: Malfunction(),
+        "px": lambda x, y: Constant(x),
+        "py": lambda x, y: Constant(y),
+        "r": lambda x, y: SoftNormalization(Angle()),
         "ax": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.X), 0.5)),
         "axy": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.X, Velocity.Y), 0.5)),
         "ay": lambda x, y: SoftNormalization(Trend(Velocity(True, 4.0, Velocity.Y), 0.5)),
@@ -553,7 +643,7 @@ class RobotUtils:
         "vxy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.X, Velocity.Y), 0.5)),
         "vy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.Y), 0.5)),
     }
-    _OUT_OF_PATH = {"r", "px", "py", "m", "cpg", "l5", "l1"}
+    _OUT_OF_PATH = {"l5", "l1"}
 
     @staticmethod
     def build_shape(name: str) -> Grid:  # :198-242
@@ -611,7 +701,18 @@ class RobotUtils:
             )
         if _params("empty", name) is not None:
             return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else Voxel([]))
-        for out in (r"spinedTouch-.*", r"spinedTouchSighted-.*", r"uniformAll-.*"):
+        p = _params(r"spinedTouch-(?<cpg>[tf])-(?<malfunction>[tf])-(?<noiseSigma>\d+(\.\d+)?)", name)
+        if p is not None:  # :134-149
+            if float(p["noiseSigma"]) != 0:
+                raise NotImplementedError("Noisy sensors are outside the accelerated hot path")
+
+            def spined(body, x, y, p=p):
+                pick = [("a", True), ("m", p["malfunction"] == "t"), ("t", y == 0), ("vxy", y == body.h - 1),
+                        ("cpg", x == body.w - 1 and y == body.h - 1 and p["cpg"] == "t")]
+                return Voxel([RobotUtils.sensor(n, x, y, body) for n, cond in pick if cond])
+
+            return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else spined(body, x, y))
+        for out in (r"spinedTouchSighted-.*", r"uniformAll-.*"):
             if _params(out, name) is not None:
                 raise NotImplementedError(f"sensorizing function '{name}' is outside the accelerated hot path")
         raise ValueError(f"Unknown sensorizing function name: {name}")

@@ -91,12 +91,23 @@ typedef struct vsr_material {
 #define VSR_SCAFFOLD_CENTRAL_CROSS 8u
 #define VSR_SCAFFOLD_ALL 15u
 
-/* ---- Sensors: every entry of RobotUtils.PREDEFINED_SENSORS on the hot path is
- *      [SoftNormalization](  [Average|Trend]( Touch | AreaRatio | Velocity ) )
- *      (RobotUtils.java:38-53).  One vsr_sensor encodes one such composition.     ---- */
+/* ---- Sensors: every entry of RobotUtils.PREDEFINED_SENSORS but the lidars is
+ *      [SoftNormalization|Normalization](  [Average|Trend]( base sensor ) )
+ *      (RobotUtils.java:38-57).  One vsr_sensor encodes one such composition.     ---- */
 #define VSR_SENSOR_TOUCH 0      /* sensors/Touch.java:35-65, 1 reading, domain [0,1]   */
 #define VSR_SENSOR_AREA_RATIO 1 /* sensors/AreaRatio.java:21-37, domain [0.5,1.5]      */
 #define VSR_SENSOR_VELOCITY 2   /* sensors/Velocity.java:57-80, 1-2 readings           */
+#define VSR_SENSOR_ANGLE 3      /* sensors/Angle.java: Voxel.getAngle, domain [-pi,pi]   */
+#define VSR_SENSOR_CONSTANT 4   /* sensors/Constant.java (one value = `param`; "px", "py"),
+                                   domain [min(0, v), max(1, v)]                        */
+#define VSR_SENSOR_APPLIED_FORCE 5 /* sensors/AppliedForce.java, domain [-1,1]          */
+#define VSR_SENSOR_MALFUNCTION 6   /* sensors/Malfunction.java on a non-breakable voxel: 0 */
+#define VSR_SENSOR_TIME_SIN 7   /* sensors/TimeFunction.java with t -> sin(2 pi f t), f = `param`,
+                                   domain [-1,1] (RobotUtils "cpg": f = -1)             */
+
+#define VSR_NORM_NONE 0
+#define VSR_NORM_SOFT 1   /* sensors/SoftNormalization.java:38-48 */
+#define VSR_NORM_LINEAR 2 /* sensors/Normalization.java: DoubleRange.normalize of the inner domain */
 
 #define VSR_AGG_NONE 0
 #define VSR_AGG_AVERAGE 1 /* sensors/Average.java:33-45 */
@@ -110,9 +121,9 @@ typedef struct vsr_sensor {
   int32_t axes;             /* VELOCITY: VSR_AXIS_X | VSR_AXIS_Y              */
   int32_t rotated;          /* VELOCITY: project on the voxel's own axes      */
   int32_t aggregator;       /* VSR_AGG_*                                      */
-  int32_t soft_norm;        /* wrap in SoftNormalization.java:38-48           */
+  int32_t soft_norm;        /* VSR_NORM_*: the outermost wrapper              */
   int32_t reserved;
-  double max_velocity_norm; /* VELOCITY domain [-m, m]                        */
+  double max_velocity_norm; /* VELOCITY domain [-m, m]; CONSTANT / TIME_SIN: `param` */
   double interval;          /* aggregator window, seconds (0.25 / 0.5)        */
 } vsr_sensor;
 

@@ -1375,6 +1375,22 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
       raw[0] = voxel_area_ratio(R, r, v);
       dmin = 0.5;
       dmax = 1.5;
+    } else if (S->base == VSR_SENSOR_ANGLE) { /* Angle.java */
+      raw[0] = voxel_angle(r, v);
+      dmin = -PI;
+      dmax = PI;
+    } else if (S->base == VSR_SENSOR_CONSTANT) { /* Constant.java: domain [min(0, v), max(1, v)] */
+      raw[0] = S->max_velocity_norm;
+      dmin = fmin(0.0, raw[0]);
+      dmax = fmax(1.0, raw[0]);
+    } else if (S->base == VSR_SENSOR_APPLIED_FORCE) { /* AppliedForce.java */
+      raw[0] = r->last_force[v];
+      dmin = -1.0;
+    } else if (S->base == VSR_SENSOR_MALFUNCTION) { /* Malfunction.java, non-breakable voxel */
+      raw[0] = 0.0;
+    } else if (S->base == VSR_SENSOR_TIME_SIN) { /* TimeFunction.java with t -> sin(2 pi f t) */
+      raw[0] = sin(2.0 * PI * S->max_velocity_norm * T[tick]);
+      dmin = -1.0;
     } else { /* Velocity.sense, Velocity.java:57-80 */
       const OBody* b = &r->bodies[4 * v];
       double vx = 0, vy = 0;
@@ -1414,7 +1430,10 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
       }
     }
     for (int k = 0; k < dim; k++)
-      r->readings[r->sens_off[si] + k] = S->soft_norm ? soft_norm(val[k], dmin, dmax) : val[k];
+      r->readings[r->sens_off[si] + k] =
+          S->soft_norm == VSR_NORM_SOFT ? soft_norm(val[k], dmin, dmax)
+          : S->soft_norm == VSR_NORM_LINEAR ? (fmin(fmax(val[k], dmin), dmax) - dmin) / (dmax - dmin) /* Normalization.java */
+                                            : val[k];
   }
 }
 

@@ -189,3 +189,37 @@ def test_distributed_sensing_matches_the_host_restatement(directional):
         broken = helpers.distributed_robots(1)[0]
         broken.get_controller().get_functions().set(0, 0, None)
         helpers.locomotion(1.0).compile([broken])
+
+
+def test_cheap_sensors_read_what_the_reference_defines():
+    # Angle, Constant (px, py), Malfunction, TimeFunction ("cpg") and the linear
+    # Normalization wrapper (RobotUtils.java:41,54-57)
+    body = helpers.body_of("worm-4x2", "uniform-r+px+py+cpg+m-0")
+    robots = [H.Robot(H.PhaseSin(1.0, 0.5, H.Grid.create(4, 2, lambda x, y: 0.3 * x)), body)]
+    loco = helpers.locomotion(1.0)
+    bd = loco.compile(robots)
+    res, pr = oracle.run(bd, readings=True, trajectory=True)
+    rd = pr["readings"][0].reshape(60, 8, 5)          # [tick][voxel][r, px, py, cpg, m]
+    t = H.tick_times(1.0, 1 / 60)
+    cells = [(x, y) for (x, y), v in body if v is not None]
+    for j, (x, y) in enumerate(cells):
+        assert np.all(rd[:, j, 1] == x / 3.0) and np.all(rd[:, j, 2] == y / 1.0)    # Constant(x/(w-1)), Constant(y/(h-1))
+        assert np.all(rd[:, j, 4] == 0.0)                                            # never broken
+        assert rd[:, j, 3] == pytest.approx((np.sin(2 * np.pi * -1 * t) + 1) / 2, abs=1e-12)   # Normalization of [-1, 1]
+    # "r" = SoftNormalization(Angle): angle 0 -> 0.5 at the first tick, then the actuation tilts the voxels a little
+    assert rd[0, :, 0] == pytest.approx(0.5, abs=1e-9) and rd[:10, :, 0] == pytest.approx(0.5, abs=5e-3)
+    tr = pr["trajectory"][0][:, :32].reshape(60, 8, 4, 6)
+    ang = (np.arctan2(tr[:, :, 1, 1] - tr[:, :, 0, 1], tr[:, :, 1, 0] - tr[:, :, 0, 0]) +
+           np.arctan2(tr[:, :, 2, 1] - tr[:, :, 3, 1], tr[:, :, 2, 0] - tr[:, :, 3, 0])) / 2
+    want = np.tanh(((np.clip(ang, -np.pi, np.pi) + np.pi) / (2 * np.pi) * 2 - 1) * 2) / 2 + 0.5
+    assert rd[:, :, 0] == pytest.approx(want, abs=1e-12)
+    # AppliedForce reads the force of the previous control step
+    body2 = H.Grid.create(2, 1, lambda x, y: H.Voxel([H.AppliedForce()]))
+    r2 = [H.Robot(H.PhaseSin(1.0, 0.7, H.Grid.create(2, 1, 0.0)), body2)]
+    _, p2 = oracle.run(loco.compile(r2), readings=True, signals=True)
+    assert p2["readings"][0, 0, :2] == pytest.approx(0.0) and \
+        p2["readings"][0, 1:, :2] == pytest.approx(p2["signals"][0, :-1, :2], abs=1e-15)
+    assert [len(v.get_sensors()) for v in helpers.body_of("biped-4x3", "spinedTouch-t-t-0").values() if v] == \
+        [3, 3, 2, 2, 2, 2, 3, 3, 3, 4]
+    with pytest.raises(NotImplementedError):
+        helpers.body_of("biped-4x3", "uniform-l5-0")

@@ -289,3 +289,15 @@ def test_fp64_distributed_sensing(shape, signals, hidden, directional):
     assert np.all(res["control_energy_last"] > 0)
     r32, _ = helpers.gpu_run(helpers.locomotion(3.0).compile(robots))
     assert np.all(r32["status"] == 0) and np.abs(r32["last_center_x"] - ores["last_center_x"]).max() < 1.5
+
+
+@pytest.mark.parametrize("sensors", ["uniform-r+px+py+cpg+m-0", "spinedTouch-t-t-0"])
+def test_fp64_mlp_with_the_cheap_sensors(sensors):
+    """Angle, Constant, Malfunction, TimeFunction("cpg"), Normalization and the
+    spinedTouch layout, read by a CentralizedSensing MLP."""
+    robots = helpers.mlp_robots(3, shape="biped-4x3", sensors=sensors, hidden=(5,), seed=17)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+    assert np.all(res["control_energy_last"] > 0)
