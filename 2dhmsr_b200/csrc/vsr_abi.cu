@@ -14,6 +14,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "vsr_device.cuh"
@@ -148,6 +149,11 @@ struct vsr_batch {
   int device = -1;
   bool uploaded = false, ran = false;
   cudaStream_t run_stream = nullptr;
+  // shape buckets are independent launches: with several of them they run on side streams, forked
+  // from and joined back into the caller's stream
+  std::vector<cudaStream_t> side_streams;
+  std::vector<cudaEvent_t> side_done;
+  cudaEvent_t fork_event = nullptr;
   double* d_ticks = nullptr;
   int16_t* d_win = nullptr;
   void* d_terr_x = nullptr;
@@ -175,6 +181,10 @@ static double ground_y_at(const vsr_batch_desc* d, double x) {
 static void free_xfers(vsr_batch* b);
 static void free_device(vsr_batch* b) {
   if (b->device >= 0) cudaSetDevice(b->device);
+  for (auto st : b->side_streams) cudaStreamDestroy(st);
+  for (auto ev : b->side_done) cudaEventDestroy(ev);
+  if (b->fork_event) cudaEventDestroy(b->fork_event);
+  b->side_streams.clear(); b->side_done.clear(); b->fork_event = nullptr;
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
     cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
@@ -727,6 +737,8 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     // one pool per scope: the warp (its robots' constraints), or the block of a big robot
     const int scopes = blk ? 1 : wpb;
     cap = std::min<long long>(cap / scopes, blk ? (long long)12 * threads : 12 * 32) / 4 * 4;
+    // a big robot's block is small (2..4 warps): a modest pool leaves room for a second block on the SM
+    if (blk) cap = std::min<long long>(cap, getenv("VSR_BLK_POOL") ? atoll(getenv("VSR_BLK_POOL")) : 96);
     if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
     P.pool_cap = (int)cap;
     smem += (size_t)cap * scopes * VSR_POOL_FIELDS * sizeof(real);
@@ -793,9 +805,42 @@ extern "C" int vsr_batch_run(vsr_batch* b, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   b->run_stream = s;
   b->last_launches = 0;
-  for (auto& k : b->buckets) {
-    int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, s) : launch_bucket<float>(b, k, s);
-    if (rc) return rc;
+  const size_t nb = b->buckets.size();
+  if (nb <= 1) {
+    for (auto& k : b->buckets) {
+      int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, s) : launch_bucket<float>(b, k, s);
+      if (rc) return rc;
+    }
+  } else {
+    const size_t ns = std::min<size_t>(nb, 16);
+    if (b->side_streams.empty()) {
+      b->side_streams.resize(ns);
+      b->side_done.resize(ns);
+      for (size_t i = 0; i < ns; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->side_streams[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&b->side_done[i], cudaEventDisableTiming));
+      }
+      CUDA_TRY(cudaEventCreateWithFlags(&b->fork_event, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(b->fork_event, s));
+    for (size_t i = 0; i < ns; i++) CUDA_TRY(cudaStreamWaitEvent(b->side_streams[i], b->fork_event, 0));
+    // the heaviest buckets first
+    std::vector<size_t> order(nb);
+    for (size_t i = 0; i < nb; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+      return b->buckets[x].robot_ids.size() * (size_t)b->buckets[x].shape.nvox >
+             b->buckets[y].robot_ids.size() * (size_t)b->buckets[y].shape.nvox;
+    });
+    for (size_t q = 0; q < nb; q++) {
+      Bucket& k = b->buckets[order[q]];
+      cudaStream_t ss = b->side_streams[q % ns];
+      int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, ss) : launch_bucket<float>(b, k, ss);
+      if (rc) return rc;
+    }
+    for (size_t i = 0; i < ns; i++) {
+      CUDA_TRY(cudaEventRecord(b->side_done[i], b->side_streams[i]));
+      CUDA_TRY(cudaStreamWaitEvent(s, b->side_done[i], 0));
+    }
   }
   b->ran = true;
   return VSR_OK;

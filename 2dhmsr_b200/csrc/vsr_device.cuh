@@ -170,7 +170,7 @@ template <> struct Real2T<double> { typedef double2 type; };
 // One record type for both kinds: a mass against a ground segment (tb < 0; seg = the segment) and a
 // mass against another mass of the same robot (Voxel.java:178-185,474; owned by the thread of the
 // lower body index, ka = its mass; the partner is mass kb of block thread tb).
-#define SC_CAP 4
+#define SC_CAP 6
 template <typename real>
 struct SPoint {
   real px, py, depth, jn, jt;  // persistent (warm start by id)
@@ -993,7 +993,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
 // candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
-#define VSR_MAX_CAND 6
+#define VSR_MAX_CAND 8
 #endif
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
@@ -1559,7 +1559,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       //      the oracle's canonical enumeration.
       const int rbase = BLK ? 0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
       int n_new = 0;
-      unsigned lvpack = 0;  // dependency level of each of this thread's constraints, 8 bits each
+      unsigned long long lvpack = 0;  // dependency level of each of this thread's constraints, 8 bits each
       if (P.self_coll) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1679,7 +1679,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             cnt[ia] = (real)(lv + 1);
             cnt[ib] = (real)(lv + 1);
             if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_CONTACT_OVERFLOW; }
-            lvpack |= (unsigned)lv << (8 * li);
+            lvpack |= (unsigned long long)lv << (8 * li);
           }
           SSYNC()
         }
@@ -1699,7 +1699,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
 #pragma unroll
         for (int li = 0; li < SC_CAP; li++)
-          if (li < n_new) atomicAdd(&lhd[2 + ((lvpack >> (8 * li)) & 255u)], 1);
+          if (li < n_new) atomicAdd(&lhd[2 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1);
         SSYNC()
         if (st == 0) {
           int run = 0, nl_ = 0;
@@ -1722,7 +1722,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
         for (int li = 0; li < SC_CAP; li++)
           if (li < n_new)
-            items[atomicAdd(&lhd[34 + ((lvpack >> (8 * li)) & 255u)], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
+            items[atomicAdd(&lhd[34 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
         SSYNC()
       }
 
