@@ -210,6 +210,68 @@ struct SoftNormalization : Sensor {  // sensors/SoftNormalization.java
   }
 };
 
+struct Normalization : Sensor {  // sensors/Normalization.java
+  SensorPtr sensor;
+  explicit Normalization(SensorPtr s) : sensor(std::move(s)) {
+    if (sensor->isSoftNorm()) throw Unsupported("nested normalizations are outside the hot path");
+  }
+  bool isSoftNorm() const override { return true; }
+  std::vector<DoubleRange> getDomains() const override {
+    return std::vector<DoubleRange>(sensor->getDomains().size(), DoubleRange(0, 1));
+  }
+  vsr_sensor encode() const override {
+    vsr_sensor s = sensor->encode();
+    s.soft_norm = VSR_NORM_LINEAR;
+    return s;
+  }
+};
+struct Angle : Sensor {  // sensors/Angle.java
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(-M_PI, M_PI)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_ANGLE;
+    return s;
+  }
+};
+struct Constant : Sensor {  // sensors/Constant.java (one value per sensor on the accelerated path)
+  double value;
+  explicit Constant(double v) : value(v) {}
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(std::min(0.0, value), std::max(1.0, value))}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_CONSTANT;
+    s.max_velocity_norm = value;
+    return s;
+  }
+};
+struct AppliedForce : Sensor {  // sensors/AppliedForce.java
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(-1, 1)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_APPLIED_FORCE;
+    return s;
+  }
+};
+struct Malfunction : Sensor {  // sensors/Malfunction.java (a non-breakable voxel is never broken)
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(0, 1)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_MALFUNCTION;
+    return s;
+  }
+};
+struct TimeFunctionSin : Sensor {  // sensors/TimeFunction.java with t -> sin(2 pi f t) on [-1, 1] ("cpg": f = -1)
+  double frequency;
+  explicit TimeFunctionSin(double f) : frequency(f) {}
+  std::vector<DoubleRange> getDomains() const override { return {DoubleRange(-1, 1)}; }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_TIME_SIN;
+    s.max_velocity_norm = frequency;
+    return s;
+  }
+};
+
 // ---------------------------------------------------------------- Voxel
 class Voxel {  // core/objects/Voxel.java:103-160
  public:
@@ -405,6 +467,58 @@ class CentralizedSensing : public Controller {  // controllers/CentralizedSensin
   MultiLayerPerceptron function_;
 };
 
+// controllers/DistributedSensing.java (and ...NonDirectional): one MultiLayerPerceptron per voxel
+// (Starter.java:176-190), fed with the voxel's readings and `signals` values from each of the N, E, S, W
+// neighbours' previous outputs; output 0 is the control signal.
+class DistributedSensing : public Controller {
+ public:
+  DistributedSensing(const Grid<Voxel>& voxels, int signals, bool directional = true)
+      : signals_(signals), directional_(directional), w_(voxels.getW()), h_(voxels.getH()),
+        functions_(size_t(voxels.getW()) * voxels.getH()) {
+    for (int y = 0; y < h_; y++)
+      for (int x = 0; x < w_; x++) {
+        auto v = voxels.get(x, y);
+        nIn_.push_back(v ? nOfInputs(*v, signals) : 0);
+        nOut_.push_back(v ? nOfOutputs(signals, directional) : 0);
+      }
+  }
+  static int nOfInputs(const Voxel& v, int signals) {  // :141-143
+    int n = signals * 4;
+    for (auto& s : v.getSensors()) n += int(s->getDomains().size());
+    return n;
+  }
+  static int nOfOutputs(int signals, bool directional = true) { return directional ? 1 + signals * 4 : 1 + signals; }  // :145-147
+  int nOfInputs(int x, int y) const { return nIn_[size_t(y) * w_ + x]; }
+  int nOfOutputs(int x, int y) const { return nOut_[size_t(y) * w_ + x]; }
+  void setFunction(int x, int y, MultiLayerPerceptron f) {
+    if (f.getInputDimension() != nOfInputs(x, y) || f.getOutputDimension() != nOfOutputs(x, y))
+      throw std::invalid_argument("Wrong dimension of input or output in the function of voxel (" + std::to_string(x) + "," +
+                                  std::to_string(y) + ")");
+    functions_[size_t(y) * w_ + x] = std::move(f);
+  }
+  int getSignals() const { return signals_; }
+  int kind() const override { return directional_ ? VSR_CTRL_DISTRIBUTED : VSR_CTRL_DISTRIBUTED_ND; }
+  const std::optional<MultiLayerPerceptron>& getFunction(int x, int y) const { return functions_[size_t(y) * w_ + x]; }
+  std::vector<double> params(const Grid<Voxel>& voxels, const std::vector<double>&) const override {
+    std::vector<double> out;
+    for (int y = 0; y < h_; y++)
+      for (int x = 0; x < w_; x++) {
+        if (!voxels.get(x, y)) continue;
+        auto& f = functions_[size_t(y) * w_ + x];
+        if (!f) throw Unsupported("DistributedSensing: the accelerated path needs a MultiLayerPerceptron for every voxel");
+        out.insert(out.end(), f->getParams().begin(), f->getParams().end());
+      }
+    return out;
+  }
+
+ private:
+  int signals_;
+  bool directional_;
+  int w_, h_;
+  std::vector<int> nIn_, nOut_;
+  std::vector<std::optional<MultiLayerPerceptron>> functions_;
+};
+
 class Robot {  // core/objects/Robot.java:57-64
  public:
   Robot(ControllerPtr controller, Grid<Voxel> voxels) : controller_(std::move(controller)), voxels_(std::move(voxels)) {}
@@ -453,7 +567,7 @@ inline Grid<bool> buildShape(const std::string& name) {  // util/RobotUtils.java
   }
   throw std::invalid_argument("Unknown body name: " + name);
 }
-inline SensorPtr sensor(const std::string& n) {  // PREDEFINED_SENSORS, :38-53 (hot-path subset)
+inline SensorPtr sensor(const std::string& n, double x = 0, double y = 0) {  // PREDEFINED_SENSORS, :38-57 (all but the lidars)
   auto vel = [](double m, int axes) { return std::make_shared<Velocity>(true, m, axes); };
   if (n == "t") return std::make_shared<Average>(std::make_shared<Touch>(), 0.25);
   if (n == "a") return std::make_shared<SoftNormalization>(std::make_shared<AreaRatio>());
@@ -463,7 +577,12 @@ inline SensorPtr sensor(const std::string& n) {  // PREDEFINED_SENSORS, :38-53 (
   if (n == "ax") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::X), 0.5));
   if (n == "ay") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::Y), 0.5));
   if (n == "axy") return std::make_shared<SoftNormalization>(std::make_shared<Trend>(vel(4, Velocity::X | Velocity::Y), 0.5));
-  for (const char* o : {"r", "px", "py", "m", "cpg", "l5", "l1"})
+  if (n == "r") return std::make_shared<SoftNormalization>(std::make_shared<Angle>());
+  if (n == "px") return std::make_shared<Constant>(x);
+  if (n == "py") return std::make_shared<Constant>(y);
+  if (n == "m") return std::make_shared<Malfunction>();
+  if (n == "cpg") return std::make_shared<Normalization>(std::make_shared<TimeFunctionSin>(-1.0));
+  for (const char* o : {"l5", "l1"})
     if (n == o) throw Unsupported("sensor '" + n + "' is outside the accelerated hot path");
   throw std::invalid_argument("Unknown sensor name: " + n);
 }
@@ -484,7 +603,9 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
       return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
         if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
         std::vector<SensorPtr> ss;
-        for (auto& n : names) ss.push_back(sensor(n));
+        // RobotUtils.sensor (:249-263): x / (w - 1), y / (h - 1)
+        const double nx = double(x) / (double(body.getW()) - 1.0), ny = double(y) / (double(body.getH()) - 1.0);
+        for (auto& n : names) ss.push_back(sensor(n, nx, ny));
         return Voxel(ss);
       });
     };
@@ -496,7 +617,23 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
         return Voxel({});
       });
     };
-  for (const char* o : {"spinedTouch-", "spinedTouchSighted-", "uniformAll-"})
+  if (match(R"(spinedTouch-([tf])-([tf])-(\d+(\.\d+)?))", name, m)) {  // :134-149
+    if (std::stod(m[3]) != 0) throw Unsupported("Noisy sensors are outside the accelerated hot path");
+    const bool cpg = m[1] == "t", malfunction = m[2] == "t";
+    return [cpg, malfunction](const Grid<bool>& body) {
+      return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
+        if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
+        std::vector<SensorPtr> ss;
+        ss.push_back(sensor("a"));
+        if (malfunction) ss.push_back(sensor("m"));
+        if (y == 0) ss.push_back(sensor("t"));
+        if (y == body.getH() - 1) ss.push_back(sensor("vxy"));
+        if (x == body.getW() - 1 && y == body.getH() - 1 && cpg) ss.push_back(sensor("cpg"));
+        return Voxel(ss);
+      });
+    };
+  }
+  for (const char* o : {"spinedTouchSighted-", "uniformAll-"})
     if (name.rfind(o, 0) == 0) throw Unsupported("sensorizing function '" + name + "' is outside the accelerated hot path");
   throw std::invalid_argument("Unknown sensorizing function name: " + name);
 }
@@ -660,6 +797,22 @@ class Locomotion {  // tasks/locomotion/Locomotion.java
         auto& f = static_cast<const CentralizedSensing&>(r.getController()).getFunction();
         hid.assign(f.getNeurons().begin() + 1, f.getNeurons().end() - 1);
         d.mlp_activation = int(f.getActivation());
+      } else if (d.controller_kind >= VSR_CTRL_DISTRIBUTED) {
+        auto& ds = static_cast<const DistributedSensing&>(r.getController());
+        bool first = true;
+        for (int y = 0; y < vox.getH(); y++)
+          for (int x = 0; x < vox.getW(); x++) {
+            if (!vox.get(x, y)) continue;
+            auto& f = ds.getFunction(x, y);
+            if (!f) throw Unsupported("DistributedSensing: the accelerated path needs a MultiLayerPerceptron for every voxel");
+            std::vector<int32_t> h2(f->getNeurons().begin() + 1, f->getNeurons().end() - 1);
+            if (first) hid = h2;
+            else if (hid != h2 || d.mlp_activation != int(f->getActivation()))
+              throw Unsupported("DistributedSensing: one activation and one set of hidden layer sizes per robot");
+            d.mlp_activation = int(f->getActivation());
+            first = false;
+          }
+        d.distributed_signals = ds.getSignals();
       }
       // find or add the shape class
       int cls = -1;

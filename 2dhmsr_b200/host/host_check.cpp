@@ -40,6 +40,22 @@ static Robot phaseRobot(double base) {
   return Robot(std::make_shared<PhaseSin>(1.0, 1.0, ph), body);
 }
 
+// Starter.java:176-190: DistributedSensing, one MLP(TANH, [2]) per voxel, weights from java.util.Random(seed)
+static Robot distributedRobot(long seed, bool directional) {
+  Grid<Voxel> body = RobotUtils::buildSensorizingFunction("uniform-ax+t-0")(RobotUtils::buildShape("biped-4x3"));
+  auto ds = std::make_shared<DistributedSensing>(body, 1, directional);
+  JavaRandom rnd(seed);
+  for (int y = 0; y < body.getH(); y++)
+    for (int x = 0; x < body.getW(); x++) {
+      if (!body.get(x, y)) continue;
+      const int nin = ds->nOfInputs(x, y), nout = ds->nOfOutputs(x, y);
+      std::vector<double> ws(MultiLayerPerceptron::countWeights({nin, 2, nout}));
+      for (auto& w : ws) w = rnd.nextDouble() * 2.0 - 1.0;
+      ds->setFunction(x, y, MultiLayerPerceptron(MultiLayerPerceptron::TANH, nin, {2}, nout, ws));
+    }
+  return Robot(ds, body);
+}
+
 template <class F>
 static std::string throwsWhat(F f) {
   try {
@@ -94,6 +110,24 @@ int main(int argc, char** argv) {
     std::cout << " \"phase_params\": " << jarr(bd2->params) << ",\n \"phase_n_shapes\": " << bd2->desc.n_shapes << ",\n";
     Grid<Voxel> worm = RobotUtils::buildSensorizingFunction("uniform-t+vxy+a-0")(RobotUtils::buildShape("worm-8x2"));
     std::cout << " \"worm_inputs\": " << CentralizedSensing::nOfInputs(worm) << ",\n";
+    // DistributedSensing + the sensors beyond the first round
+    auto bd3 = loco.compile({distributedRobot(7, true)});
+    auto bd4 = loco.compile({distributedRobot(7, false)});
+    std::cout << " \"dist_kind\": " << bd3->desc.controller_kind << ",\n \"dist_signals\": " << bd3->desc.distributed_signals
+              << ",\n \"dist_n_params\": " << bd3->params.size() << ",\n \"dist_param_0\": " << bd3->params[0]
+              << ",\n \"dist_nd_kind\": " << bd4->desc.controller_kind << ",\n \"dist_nd_n_params\": " << bd4->params.size() << ",\n";
+    Grid<Voxel> spined = RobotUtils::buildSensorizingFunction("spinedTouch-t-t-0")(RobotUtils::buildShape("biped-4x3"));
+    std::vector<double> nsens;
+    for (auto& v : spined.values())
+      if (v) nsens.push_back(double(v->getSensors().size()));
+    std::cout << " \"spined_sensor_counts\": " << jarr(nsens) << ",\n";
+    Grid<Voxel> rich = RobotUtils::buildSensorizingFunction("uniform-r+px+py+cpg+m-0")(RobotUtils::buildShape("worm-4x2"));
+    std::vector<double> enc2;
+    for (auto& sp : rich.get(3, 1)->getSensors()) {
+      vsr_sensor q = sp->encode();
+      for (double z : {double(q.base), double(q.soft_norm), q.max_velocity_norm}) enc2.push_back(z);
+    }
+    std::cout << " \"rich_sensors_3_1\": " << jarr(enc2) << ",\n";
     // error behaviour
     std::cout << " \"err_terrain\": \"" << throwsWhat([] { Locomotion::createTerrain("moon"); }) << "\",\n";
     std::cout << " \"err_shape\": \"" << throwsWhat([] { RobotUtils::buildShape("snake-3"); }) << "\",\n";
@@ -112,7 +146,11 @@ int main(int argc, char** argv) {
     std::cout << "{ \"cfg1\": {\"distance\": " << o1.getDistance() << ", \"time\": " << o1.getTime() << ", \"velocity\": " << o1.getVelocity()
               << ", \"control_energy\": " << o1.getControlEnergy() << "},\n  \"phase_distance\": [";
     for (size_t i = 0; i < outs.size(); i++) std::cout << (i ? ", " : "") << outs[i].getDistance();
-    std::cout << "] }\n";
+    Locomotion loco5(5, Locomotion::createTerrain("flat"), Settings());
+    auto d1 = loco5.apply({distributedRobot(7, true), distributedRobot(8, true)});
+    auto d2 = loco5.apply(std::vector<Robot>{distributedRobot(7, false)});
+    std::cout << "],\n  \"distributed_distance\": [" << d1[0].getDistance() << ", " << d1[1].getDistance() << ", " << d2[0].getDistance()
+              << "] }\n";
     return 0;
   }
   std::fprintf(stderr, "usage: host_check selfcheck|run\n");

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 H = importlib.import_module("2dhmsr_b200")
+A = H.abi
 import helpers
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -58,6 +59,14 @@ def test_cpp_host_mirror_selfcheck():
     assert j["phase_n_shapes"] == 1 and len(j["phase_params"]) == 3 * 12
     assert j["phase_params"][:4] == [1.0, 1.0, 0.1, 0.1 + 0.7 * 3]  # voxel order (0,0), (3,0), ...
     assert j["worm_inputs"] == 64
+    # DistributedSensing: biped-4x3 x (2 readings + 4 signals -> [2] -> 1 + 4): 10 * (2*7 + 5*3) weights
+    assert j["dist_kind"] == A.VSR_CTRL_DISTRIBUTED and j["dist_signals"] == 1 and j["dist_n_params"] == 290
+    assert j["dist_param_0"] == H.JavaRandom(7).next_double() * 2.0 - 1.0
+    assert j["dist_nd_kind"] == A.VSR_CTRL_DISTRIBUTED_ND and j["dist_nd_n_params"] == 10 * (2 * 7 + 2 * 3)
+    assert j["spined_sensor_counts"] == [3, 3, 2, 2, 2, 2, 3, 3, 3, 4]
+    # uniform-r+px+py+cpg+m at (3, 1) of a 4x2 worm: (base, normalisation, parameter) per sensor
+    assert j["rich_sensors_3_1"] == [A.VSR_SENSOR_ANGLE, 1, 0, A.VSR_SENSOR_CONSTANT, 0, 1.0, A.VSR_SENSOR_CONSTANT, 0, 1.0,
+                                     A.VSR_SENSOR_TIME_SIN, 2, -1.0, A.VSR_SENSOR_MALFUNCTION, 0, 0]
     # error behaviour: IllegalArgumentException -> std::invalid_argument, same messages
     assert j["err_terrain"] == "invalid_argument:Unknown terrain name: moon"
     assert j["err_shape"] == "invalid_argument:Unknown body name: snake-3"
@@ -80,3 +89,20 @@ def test_cpp_locomotion_apply_equals_python_path():
               for b in (0.1, 0.2, 0.3)]
     outs = helpers.locomotion().apply(robots)
     assert j["phase_distance"] == [o.get_distance() for o in outs]
+
+    def dist_robot(seed, directional):
+        body = helpers.body_of("biped-4x3")
+        ds = (H.DistributedSensing if directional else H.DistributedSensingNonDirectional)(body, 1)
+        rnd = H.JavaRandom(seed)
+        for (x, y), v in body:
+            if v is None:
+                continue
+            nin, nout = ds.n_of_inputs(x, y), ds.n_of_outputs(x, y)
+            nw = H.MultiLayerPerceptron.count_weights([nin, 2, nout])
+            ds.get_functions().set(x, y, H.MultiLayerPerceptron("TANH", nin, [2], nout, [rnd.next_double() * 2.0 - 1.0 for _ in range(nw)]))
+        return H.Robot(ds, body)
+
+    l5 = helpers.locomotion(5.0)
+    want = [o.get_distance() for o in l5.apply([dist_robot(7, True), dist_robot(8, True)])] + \
+           [l5.apply(dist_robot(7, False)).get_distance()]
+    assert j["distributed_distance"] == want
