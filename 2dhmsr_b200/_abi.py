@@ -105,6 +105,8 @@ class vsr_sensor(C.Structure):
         ("reserved", C.c_int32),
         ("max_velocity_norm", C.c_double),
         ("interval", C.c_double),
+        ("noise_sigma", C.c_double),
+        ("noise_seed", C.c_int64),
     ]
 
 

@@ -136,6 +136,10 @@ struct vsr_batch {
   std::vector<Bucket> buckets;
   std::vector<int> robot_bucket, robot_pos, robot_nvox;
   std::vector<double> ticks;
+  std::vector<double> noise;  // Noisy sensors: the first 2 * n_ticks gaussians of java.util.Random(seed)
+  bool noisy = false;
+  long long noise_seed = 0;
+  double* d_noise = nullptr;
   std::vector<int16_t> win_first;  // [MAX_WINDOWS][n_ticks]
   int ring_depth = 1;
   std::vector<double> terr_x, terr_y;  // local frame
@@ -406,6 +410,15 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         D.base = (int8_t)q.base; D.axes = (int8_t)q.axes; D.rotated = (int8_t)(q.rotated != 0);
         D.agg = (int8_t)q.aggregator; D.soft = (int8_t)q.soft_norm; D.dim = (int8_t)dim;
         D.max_norm = q.max_velocity_norm; D.interval = (float)q.interval;
+        D.noise = q.noise_sigma > 0 ? q.noise_sigma : 0.0;
+        if (q.noise_sigma > 0) {
+          if (b->noisy && b->noise_seed != (long long)q.noise_seed) {
+            delete b;
+            return fail(VSR_ERR_UNSUPPORTED, "Noisy sensors: one seed per batch");
+          }
+          b->noisy = true;
+          b->noise_seed = (long long)q.noise_seed;
+        }
         D.win = 0; D.ch = 0;
         if (q.aggregator != VSR_AGG_NONE) {
           if (!(q.interval > 0)) {
@@ -588,6 +601,36 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
     int rc;
     if ((rc = add_xfer(xs, b->ticks.data(), nt * sizeof(double), (void**)&b->d_ticks))) return rc;
     if ((rc = add_xfer(xs, b->win_first.data(), b->win_first.size() * sizeof(int16_t), (void**)&b->d_win))) return rc;
+    if (b->noisy) {
+      // java.util.Random: 48-bit LCG, nextGaussian by the polar method (StrictMath.log/sqrt; libm agrees to 1 ulp)
+      unsigned long long seed = ((unsigned long long)b->noise_seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+      auto next = [&](int bits) {
+        seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (long long)(seed >> (48 - bits));
+      };
+      auto next_double = [&]() { return (double)((next(26) << 27) + next(27)) * (1.0 / (double)(1LL << 53)); };
+      b->noise.resize((size_t)2 * nt);
+      bool have = false;
+      double spare = 0;
+      for (auto& g : b->noise) {
+        if (have) {
+          g = spare;
+          have = false;
+          continue;
+        }
+        double v1, v2, sq;
+        do {
+          v1 = 2 * next_double() - 1;
+          v2 = 2 * next_double() - 1;
+          sq = v1 * v1 + v2 * v2;
+        } while (sq >= 1 || sq == 0);
+        double mul = std::sqrt(-2 * std::log(sq) / sq);
+        spare = v2 * mul;
+        have = true;
+        g = v1 * mul;
+      }
+      if ((rc = add_xfer(xs, b->noise.data(), b->noise.size() * sizeof(double), (void**)&b->d_noise))) return rc;
+    }
     if (f64) {
       if ((rc = add_xfer_real<double>(xs, b->terr_x, &b->d_terr_x))) return rc;
       if ((rc = add_xfer_real<double>(xs, b->terr_y, &b->d_terr_y))) return rc;
@@ -648,6 +691,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.vtrace = (real*)k.d_vtrace;
   P.n_ticks = (int)b->ticks.size();
   P.tick_t = b->d_ticks;
+  P.noise_tab = b->d_noise;
   P.win_first = b->d_win;
   P.terr_x = (const real*)b->d_terr_x;
   P.terr_y = (const real*)b->d_terr_y;

@@ -48,6 +48,7 @@ struct SensorDev {
   int8_t base, axes, rotated, agg, soft, win, ch, dim;
   float interval;
   double max_norm;  // Velocity: domain bound; Constant / TimeFunction: the value / the frequency
+  double noise;     // Noisy: sigma (0 = not noisy)
 };
 
 // One shape class (Grid<Boolean> + sensor layout), compiled on the host.
@@ -84,6 +85,7 @@ struct Params {
   int n_ticks;
   const double* tick_t;       // [n_ticks] accumulated t
   const int16_t* win_first;   // [MAX_WINDOWS][n_ticks] oldest kept tick
+  const double* noise_tab;    // [2 * n_ticks] java.util.Random(seed).nextGaussian() stream (Noisy sensors)
   // terrain (local frame: x - origin_x)
   const real* terr_x;
   const real* terr_y;
@@ -1825,6 +1827,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               o = r_tanh(((nv * real(2)) - real(1)) * real(2)) / real(2) + real(0.5);
             } else if (sd.soft == 2) {  // Normalization: DoubleRange.normalize
               o = (r_min(r_max(o, dmin), dmax) - dmin) / (dmax - dmin);
+            }
+            if (sd.noise > 0.0) {
+              // Noisy.sense (Noisy.java:57-62): every instance owns a Random(seed), so a sensor of
+              // dimension dim draws gaussians number tick * dim + d of the same stream (host table)
+              const real ext = sd.soft ? real(1) : dmax - dmin;
+              o = o + (real)(P.noise_tab[(size_t)tick * sd.dim + d] * sd.noise) * ext;
             }
             // static indexing of the register array
 #pragma unroll

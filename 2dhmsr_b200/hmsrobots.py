@@ -321,6 +321,25 @@ class Normalization(Sensor):  # sensors/Normalization.java
         return s
 
 
+class Noisy(Sensor):
+    """sensors/Noisy.java: the wrapped sensor's readings + ``Random(seed).nextGaussian() * sigma * extent`` of the
+    reading's domain (:49-62).  The generator belongs to the sensor instance; a robot is evaluated from a
+    freshly constructed state (the stream starts at the seed for every episode)."""
+
+    def __init__(self, sensor: Sensor, sigma: float, seed: int):
+        if isinstance(sensor, Noisy):
+            raise NotImplementedError("nested Noisy sensors are outside the hot path")
+        self.sensor, self.sigma, self.seed = sensor, float(sigma), int(seed)
+
+    def domains(self):
+        return self.sensor.domains()
+
+    def encode(self):
+        s = self.sensor.encode()
+        s.noise_sigma, s.noise_seed = self.sigma, self.seed
+        return s
+
+
 # --------------------------------------------------------------------------- Voxel / Robot
 class Voxel:
     """core/objects/Voxel.java: the 13-argument constructor (:103-142) and the
@@ -692,24 +711,24 @@ class RobotUtils:
         keys = "|".join(sorted(set(RobotUtils.PREDEFINED_SENSORS) | RobotUtils._OUT_OF_PATH))
         p = _params(rf"uniform-(?<sensors>({keys})(\+({keys}))*)-(?<noiseSigma>\d+(\.\d+)?)", name)
         if p is not None:
-            if float(p["noiseSigma"]) != 0:
-                raise NotImplementedError("Noisy sensors are outside the accelerated hot path")
+            sigma = float(p["noiseSigma"])
             names = p["sensors"].split("+")
+            noisy = (lambda s: s) if sigma == 0 else (lambda s: Noisy(s, sigma, 0))  # :172-175
             return lambda body: Grid.create(
                 body.w, body.h,
-                lambda x, y: None if not body.get(x, y) else Voxel([RobotUtils.sensor(n, x, y, body) for n in names]),
+                lambda x, y: None if not body.get(x, y) else Voxel([noisy(RobotUtils.sensor(n, x, y, body)) for n in names]),
             )
         if _params("empty", name) is not None:
             return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else Voxel([]))
         p = _params(r"spinedTouch-(?<cpg>[tf])-(?<malfunction>[tf])-(?<noiseSigma>\d+(\.\d+)?)", name)
         if p is not None:  # :134-149
-            if float(p["noiseSigma"]) != 0:
-                raise NotImplementedError("Noisy sensors are outside the accelerated hot path")
+            sg = float(p["noiseSigma"])
 
-            def spined(body, x, y, p=p):
+            def spined(body, x, y, p=p, sg=sg):
                 pick = [("a", True), ("m", p["malfunction"] == "t"), ("t", y == 0), ("vxy", y == body.h - 1),
                         ("cpg", x == body.w - 1 and y == body.h - 1 and p["cpg"] == "t")]
-                return Voxel([RobotUtils.sensor(n, x, y, body) for n, cond in pick if cond])
+                ss = [RobotUtils.sensor(n, x, y, body) for n, cond in pick if cond]
+                return Voxel(ss if sg == 0 else [Noisy(s, sg, 0) for s in ss])
 
             return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else spined(body, x, y))
         for out in (r"spinedTouchSighted-.*", r"uniformAll-.*"):
@@ -985,7 +1004,7 @@ def compile_batch(
         vox = r.voxels
         mask = bytes(1 if v is not None else 0 for v in vox.values())
         sens = tuple(
-            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval)
+            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed)
                   for s in (ss.encode() for ss in v.get_sensors()))
             for v in vox.values() if v is not None
         )
@@ -1048,7 +1067,7 @@ def compile_batch(
         nread = 0
         for j, t in enumerate(flat):
             s = sarr[j]
-            s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval = t
+            s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed = t
             nread += (bin(s.axes & 3).count("1") if s.base == A.VSR_SENSOR_VELOCITY else 1)
         b.keep(sarr)
         hid = b.keep(np.asarray(hidden if hidden else [0], dtype=np.int32))

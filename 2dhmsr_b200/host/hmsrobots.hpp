@@ -225,6 +225,21 @@ struct Normalization : Sensor {  // sensors/Normalization.java
     return s;
   }
 };
+struct Noisy : Sensor {  // sensors/Noisy.java: + Random(seed).nextGaussian() * sigma * extent of the reading's domain
+  SensorPtr sensor;
+  double sigma;
+  long seed;
+  Noisy(SensorPtr s, double sigma_, long seed_) : sensor(std::move(s)), sigma(sigma_), seed(seed_) {}
+  bool isAggregator() const override { return sensor->isAggregator(); }
+  bool isSoftNorm() const override { return sensor->isSoftNorm(); }
+  std::vector<DoubleRange> getDomains() const override { return sensor->getDomains(); }
+  vsr_sensor encode() const override {
+    vsr_sensor s = sensor->encode();
+    s.noise_sigma = sigma;
+    s.noise_seed = seed;
+    return s;
+  }
+};
 struct Angle : Sensor {  // sensors/Angle.java
   std::vector<DoubleRange> getDomains() const override { return {DoubleRange(-M_PI, M_PI)}; }
   vsr_sensor encode() const override {
@@ -590,7 +605,7 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
   std::smatch m;
   const std::string keys = "a|ax|axy|ay|cpg|l1|l5|m|px|py|r|t|vx|vxy|vy";
   if (match("uniform-((" + keys + ")(\\+(" + keys + "))*)-(\\d+(\\.\\d+)?)", name, m)) {
-    if (std::stod(m[5]) != 0) throw Unsupported("Noisy sensors are outside the accelerated hot path");
+    const double sigma = std::stod(m[5]);
     std::vector<std::string> names;
     std::string list = m[1], cur;
     for (char c : list + "+") {
@@ -599,13 +614,16 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
         cur.clear();
       } else cur += c;
     }
-    return [names](const Grid<bool>& body) {
+    return [names, sigma](const Grid<bool>& body) {
       return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
         if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
         std::vector<SensorPtr> ss;
         // RobotUtils.sensor (:249-263): x / (w - 1), y / (h - 1)
         const double nx = double(x) / (double(body.getW()) - 1.0), ny = double(y) / (double(body.getH()) - 1.0);
-        for (auto& n : names) ss.push_back(sensor(n, nx, ny));
+        for (auto& n : names) {
+          SensorPtr sp = sensor(n, nx, ny);
+          ss.push_back(sigma == 0 ? sp : std::make_shared<Noisy>(sp, sigma, 0));  // :172-175
+        }
         return Voxel(ss);
       });
     };
@@ -618,9 +636,9 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
       });
     };
   if (match(R"(spinedTouch-([tf])-([tf])-(\d+(\.\d+)?))", name, m)) {  // :134-149
-    if (std::stod(m[3]) != 0) throw Unsupported("Noisy sensors are outside the accelerated hot path");
+    const double sigma = std::stod(m[3]);
     const bool cpg = m[1] == "t", malfunction = m[2] == "t";
-    return [cpg, malfunction](const Grid<bool>& body) {
+    return [cpg, malfunction, sigma](const Grid<bool>& body) {
       return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
         if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
         std::vector<SensorPtr> ss;
@@ -629,6 +647,8 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
         if (y == 0) ss.push_back(sensor("t"));
         if (y == body.getH() - 1) ss.push_back(sensor("vxy"));
         if (x == body.getW() - 1 && y == body.getH() - 1 && cpg) ss.push_back(sensor("cpg"));
+        if (sigma != 0)
+          for (auto& sp : ss) sp = std::make_shared<Noisy>(sp, sigma, 0);
         return Voxel(ss);
       });
     };
@@ -692,7 +712,8 @@ struct BatchDesc {  // owns the flat arrays behind a vsr_batch_desc
 
 inline bool sameSensor(const vsr_sensor& a, const vsr_sensor& b) {
   return a.base == b.base && a.axes == b.axes && a.rotated == b.rotated && a.aggregator == b.aggregator &&
-         a.soft_norm == b.soft_norm && a.max_velocity_norm == b.max_velocity_norm && a.interval == b.interval;
+         a.soft_norm == b.soft_norm && a.max_velocity_norm == b.max_velocity_norm && a.interval == b.interval &&
+         a.noise_sigma == b.noise_sigma && a.noise_seed == b.noise_seed;
 }
 
 class Locomotion {  // tasks/locomotion/Locomotion.java

@@ -125,6 +125,9 @@ typedef struct vsr_sensor {
   int32_t reserved;
   double max_velocity_norm; /* VELOCITY domain [-m, m]; CONSTANT / TIME_SIN: `param` */
   double interval;          /* aggregator window, seconds (0.25 / 0.5)        */
+  double noise_sigma;       /* > 0: wrapped in sensors/Noisy.java (outermost): every reading gets
+                               java.util.Random(noise_seed).nextGaussian() * sigma * domain extent */
+  int64_t noise_seed;       /* one seed per batch (RobotUtils.java:148 passes 0)                  */
 } vsr_sensor;
 
 /* ---- Shape class: a Grid<Boolean> body + its per-voxel sensor lists.

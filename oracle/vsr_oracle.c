@@ -197,6 +197,10 @@ typedef struct {
   int* sens_off;    /* offset in readings */
   double** hist;    /* [n_sens] -> [ticks][dim] */
   int* hist_first;  /* index of the oldest kept tick */
+  /* Noisy: one java.util.Random per sensor instance (Noisy.java:49) */
+  unsigned long long* rng_seed; /* [n_sens] */
+  double* rng_spare;            /* [n_sens] nextNextGaussian */
+  unsigned char* rng_have;      /* [n_sens] haveNextNextGaussian */
   /* MLP */
   int n_layers;
   int32_t* neurons;
@@ -472,6 +476,11 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   }
   r->n_readings = off_r;
   r->readings = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+  r->rng_seed = (unsigned long long*)calloc((size_t)ns + 1, sizeof(unsigned long long));
+  r->rng_spare = (double*)calloc((size_t)ns + 1, sizeof(double));
+  r->rng_have = (unsigned char*)calloc((size_t)ns + 1, 1);
+  for (int q = 0; q < r->n_sens; q++)
+    r->rng_seed[q] = ((unsigned long long)r->sens[q]->noise_seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
 
   /* --- DistributedSensing: per-voxel reading ranges, grid lookup, signal grids (reset() = zeros) --- */
   r->vox_read_off = (int*)calloc((size_t)nv + 1, sizeof(int));
@@ -510,6 +519,9 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
 }
 
 static void robot_free(ORobot* r) {
+  free(r->rng_seed);
+  free(r->rng_spare);
+  free(r->rng_have);
   free(r->vox_read_off);
   free(r->vox_at);
   free(r->last_sig);
@@ -1357,6 +1369,32 @@ static double soft_norm(double x, double mn, double mx) {
 }
 
 /* Voxel.act (:197-203) for all voxels, then sensors (CompositeSensor.act: inner first). */
+/* java.util.Random: next(bits), nextDouble, nextGaussian (polar method) for one sensor's generator */
+static long long jr_next(unsigned long long* seed, int bits) {
+  *seed = (*seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+  return (long long)(*seed >> (48 - bits));
+}
+static double jr_next_double(unsigned long long* seed) {
+  long long a = jr_next(seed, 26), b = jr_next(seed, 27);
+  return (double)((a << 27) + b) * (1.0 / (double)(1LL << 53));
+}
+static double jr_next_gaussian(ORobot* r, int si) {
+  if (r->rng_have[si]) {
+    r->rng_have[si] = 0;
+    return r->rng_spare[si];
+  }
+  double v1, v2, s;
+  do {
+    v1 = 2 * jr_next_double(&r->rng_seed[si]) - 1;
+    v2 = 2 * jr_next_double(&r->rng_seed[si]) - 1;
+    s = v1 * v1 + v2 * v2;
+  } while (s >= 1 || s == 0);
+  double mul = sqrt(-2 * log(s) / s);
+  r->rng_spare[si] = v2 * mul;
+  r->rng_have[si] = 1;
+  return v1 * mul;
+}
+
 static void robot_sense(ORun* R, ORobot* r, int tick) {
   const double* T = R->ticks;
   for (int v = 0; v < r->nv; v++) {
@@ -1429,11 +1467,16 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
         dmax = ext / S->interval;
       }
     }
-    for (int k = 0; k < dim; k++)
-      r->readings[r->sens_off[si] + k] =
-          S->soft_norm == VSR_NORM_SOFT ? soft_norm(val[k], dmin, dmax)
-          : S->soft_norm == VSR_NORM_LINEAR ? (fmin(fmax(val[k], dmin), dmax) - dmin) / (dmax - dmin) /* Normalization.java */
-                                            : val[k];
+    for (int k = 0; k < dim; k++) {
+      double o = S->soft_norm == VSR_NORM_SOFT ? soft_norm(val[k], dmin, dmax)
+                 : S->soft_norm == VSR_NORM_LINEAR ? (fmin(fmax(val[k], dmin), dmax) - dmin) / (dmax - dmin) /* Normalization.java */
+                                                   : val[k];
+      if (S->noise_sigma > 0) { /* Noisy.sense, Noisy.java:57-62: sigma * extent of the wrapped sensor's domain */
+        double ext = S->soft_norm != VSR_NORM_NONE ? 1.0 : dmax - dmin;
+        o = o + jr_next_gaussian(r, si) * (ext * S->noise_sigma);
+      }
+      r->readings[r->sens_off[si] + k] = o;
+    }
   }
 }
 

@@ -223,3 +223,27 @@ def test_cheap_sensors_read_what_the_reference_defines():
         [3, 3, 2, 2, 2, 2, 3, 3, 3, 4]
     with pytest.raises(NotImplementedError):
         helpers.body_of("biped-4x3", "uniform-l5-0")
+
+
+def test_noisy_sensors_draw_from_java_util_random():
+    # Noisy.java:49-62: every sensor instance owns a Random(0); reading i of a sensor of dimension d gets
+    # gaussian number tick * d + i of that stream, scaled by sigma * extent of the (outer) domain.
+    sigma = 0.05
+    clean = helpers.body_of("worm-3x1", "uniform-t+vxy+px-0")
+    noisy = helpers.body_of("worm-3x1", f"uniform-t+vxy+px-{sigma}")
+    ctrl = lambda b: H.PhaseSin(1.0, 0.0, H.Grid.create(b.w, b.h, 0.0))     # amplitude 0: the body ignores the readings
+    loco = helpers.locomotion(0.5)
+    _, pc = oracle.run(loco.compile([H.Robot(ctrl(clean), clean)]), readings=True)
+    _, pn = oracle.run(loco.compile([H.Robot(ctrl(noisy), noisy)]), readings=True)
+    nt = pc["readings"].shape[1]                            # 31 ticks: t += 1/60 overshoots 0.5 by rounding
+    rc, rn = pc["readings"][0].reshape(nt, 3, 4), pn["readings"][0].reshape(nt, 3, 4)   # [t, vx, vy, px]
+    g1, g2 = H.JavaRandom(0), H.JavaRandom(0)
+    s1 = [g1.next_gaussian() for _ in range(nt)]            # dimension-1 sensors
+    s2 = [g2.next_gaussian() for _ in range(2 * nt)]        # the dimension-2 velocity sensor
+    for k in range(nt):
+        for v in range(3):
+            assert rn[k, v, 0] - rc[k, v, 0] == pytest.approx(s1[k] * sigma * 1.0, abs=1e-12)          # Average(Touch): [0, 1]
+            assert rn[k, v, 1] - rc[k, v, 1] == pytest.approx(s2[2 * k] * sigma * 1.0, abs=1e-12)      # SoftNormalization: [0, 1]
+            assert rn[k, v, 2] - rc[k, v, 2] == pytest.approx(s2[2 * k + 1] * sigma * 1.0, abs=1e-12)
+            assert rn[k, v, 3] - rc[k, v, 3] == pytest.approx(s1[k] * sigma * 1.0, abs=1e-12)          # Constant in [0, 1]
+    assert s1[0] == pytest.approx(0.8025330637390305, abs=1e-15)   # Random(0).nextGaussian()

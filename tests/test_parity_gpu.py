@@ -301,3 +301,15 @@ def test_fp64_mlp_with_the_cheap_sensors(sensors):
     assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
     assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
     assert np.all(res["control_energy_last"] > 0)
+
+
+def test_fp64_noisy_sensors():
+    """Noisy sensors (uniform-...-0.02): the device reads the Random(0) gaussian stream from a host table,
+    the oracle runs one generator per sensor instance as the reference does."""
+    robots = helpers.mlp_robots(3, shape="biped-4x3", sensors="uniform-t+vxy+a-0.02", hidden=(4,), seed=23)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    clean, _ = helpers.gpu_run(helpers.locomotion(3.0).compile(
+        helpers.mlp_robots(3, shape="biped-4x3", sensors="uniform-t+vxy+a-0", hidden=(4,), seed=23), precision=F64))
+    assert np.abs(clean["last_center_x"] - res["last_center_x"]).max() > 1e-6      # the noise reaches the controller
