@@ -400,7 +400,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       for (int k = s0; k < s1; k++) {
         const vsr_sensor& q = sh.sensors[k];
         SensorDev& D = S.sens[v][k - s0];
-        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_TIME_SIN || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
+        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_CONTROL_POWER || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
             q.aggregator < VSR_AGG_NONE ||
             q.aggregator > VSR_AGG_TREND) {
           delete b;

@@ -6,20 +6,23 @@
 // inside Locomotion.apply's loop (tasks/locomotion/Locomotion.java:196-203).
 //
 // Mapping:
-//   * one LANE per voxel, floor(32 / n_voxels) robots per warp, a warp runs the whole
-//     episode (all ticks) of its robots; no block-level synchronisation at all;
+//   * one LANE per voxel, floor(32 / n_voxels) robots per warp (one block per robot above 32
+//     voxels), a warp runs the whole episode (all ticks) of its robots; the warps of a block walk
+//     the (large, unrolled) instruction stream together behind data-free barriers;
 //   * the 4 masses of a voxel (pose + velocity) and its 18 spring-dampers
 //     (Voxel.java:239-479) live in that lane's registers: the 18 soft DistanceJoint
 //     solves of a velocity iteration are pure register arithmetic, fully unrolled;
-//   * the rigid WeldJoints between neighbouring voxels (Robot.java:91-114) are solved
-//     redundantly by both lanes after exchanging the partner mass' state with warp
-//     shuffles: first all left/right welds, then all up/down welds (each mass has at
-//     most one of each => a 2-colouring);
-//   * ground contact (Ground.java:64-70 polygons) is per mass: SAT + clipping manifold,
-//     sequential impulses with the 2-point block solver, Baumgarte position pass;
-//   * sensors (Touch/AreaRatio/Velocity with Average/Trend windows and
-//     SoftNormalization) and controllers (PhaseSin, tabulated TimeFunctions, per-robot
-//     MLP) run in the same kernel right after the step.
+//   * the rigid WeldJoints between neighbouring voxels (Robot.java:91-114) are solved once, by
+//     the lane of body 1, after gathering the partner mass' state with warp shuffles; the impulse
+//     is handed to the lane of body 2: first all left/right welds, then all up/down welds (each
+//     mass has at most one of each => a 2-colouring);
+//   * contacts -- a mass against a ground polygon (Ground.java:64-70) or against another mass of
+//     the robot (Voxel.java:178-185,474) -- are one record type: SAT + clipping manifold,
+//     sequential impulses with the 2-point block solver, Baumgarte position pass; the constraints
+//     of a robot scope are listed per tick by dependency level and solved one per lane;
+//   * sensors (Touch/AreaRatio/Velocity/Angle/... with Average/Trend windows, the normalisations
+//     and Noisy) and controllers (PhaseSin, tabulated TimeFunctions, centralized or distributed
+//     per-robot MLPs) run in the same kernel right after the step.
 // The resulting Gauss-Seidel order (springs -> horizontal welds -> vertical welds ->
 // contacts) is the oracle's VSR_ORACLE_ORDER_CANONICAL.
 #pragma once
@@ -40,7 +43,8 @@ constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
 enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2, SENSOR_ANGLE = 3, SENSOR_CONSTANT = 4,
-             SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7 };
+             SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7, SENSOR_CRUMPLING = 8,
+             SENSOR_CONTROL_POWER = 9 };
 enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
 enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2 };
 
@@ -467,10 +471,6 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
   return overflow;
 }
 
-template <typename real>
-struct BodyState {
-  real x, y, th, vx, vy, w;
-};
 // the scalars the contact routines need, passed by value (registers): taking the kernel's
 // Params by reference would force a local-memory copy of the whole struct
 template <typename real>
@@ -1000,9 +1000,6 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
 #endif
-// One warp per block: no block-level synchronisation exists, and 32-thread blocks give the
-// finest balance of robot groups over the 148 SMs.  FULLSPR = all four spring scaffoldings
-// present (the default voxel): the 18 solves then form one branch-free basic block.
 // FAST = the default voxel (all four scaffoldings, reduced-mass springs): no per-spring branch,
 // constant gamma.  Everything else takes the generic instantiation.
 // BLK = one robot per block (33..128 voxels): neighbour exchange through shared memory and
@@ -1782,6 +1779,21 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           } else if (sd.base == SENSOR_TIME_SIN) {
             raw[0] = (real)sin(2.0 * 3.14159265358979323846 * (double)sd.max_norm * P.tick_t[tick]);
             dmin = real(-1);
+          } else if (sd.base == SENSOR_CRUMPLING) {
+            real cnt = real(0);
+            const real thr = P.side * real(0.2);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = i + 1; j < 4; j++) {
+                const real ddx = x[i] - x[j], ddy = y[i] - y[j];
+                if (r_sqrt(ddx * ddx + ddy * ddy) < thr) cnt = cnt + real(1);
+              }
+            raw[0] = real(2) * cnt / real(12);
+          } else if (sd.base == SENSOR_CONTROL_POWER) {
+            const double tprev = tick > 0 ? P.tick_t[tick - 1] : 0.0;
+            raw[0] = ctrl_energy / (real)(P.tick_t[tick] - tprev);
+            dmax = (real)(1.0 / sd.max_norm);
           } else {
             int c = 0;
             real sa, ca;

@@ -239,6 +239,30 @@ class Malfunction(Sensor):  # sensors/Malfunction.java (a non-breakable voxel is
         return s
 
 
+class Crumpling(Sensor):  # sensors/Crumpling.java
+    def domains(self):
+        return [DoubleRange(0.0, 1.0)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_CRUMPLING
+        return s
+
+
+class ControlPower(Sensor):  # sensors/ControlPower.java
+    def __init__(self, control_interval: float):
+        self.control_interval = float(control_interval)
+
+    def domains(self):
+        return [DoubleRange(0.0, 1.0 / self.control_interval)]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_CONTROL_POWER
+        s.max_velocity_norm = self.control_interval
+        return s
+
+
 class TimeFunction(Sensor):
     """sensors/TimeFunction.java.  The accelerated path evaluates ``t -> sin(2 pi f t)`` on [-1, 1] (the
     "cpg" sensor of RobotUtils.java:57); build it with ``TimeFunction.sin(f)``."""

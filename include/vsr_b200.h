@@ -105,6 +105,10 @@ typedef struct vsr_material {
 #define VSR_SENSOR_TIME_SIN 7   /* sensors/TimeFunction.java with t -> sin(2 pi f t), f = `param`,
                                    domain [-1,1] (RobotUtils "cpg": f = -1)             */
 
+#define VSR_SENSOR_CRUMPLING 8  /* sensors/Crumpling.java: share of the 6 mass pairs closer than 0.2 side lengths */
+#define VSR_SENSOR_CONTROL_POWER 9 /* sensors/ControlPower.java: Voxel.getControlEnergy / (t - previous t),
+                                      domain [0, 1 / `param`] (param = controlInterval)                  */
+
 #define VSR_NORM_NONE 0
 #define VSR_NORM_SOFT 1   /* sensors/SoftNormalization.java:38-48 */
 #define VSR_NORM_LINEAR 2 /* sensors/Normalization.java: DoubleRange.normalize of the inner domain */

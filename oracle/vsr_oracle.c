@@ -1429,6 +1429,18 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
     } else if (S->base == VSR_SENSOR_TIME_SIN) { /* TimeFunction.java with t -> sin(2 pi f t) */
       raw[0] = sin(2.0 * PI * S->max_velocity_norm * T[tick]);
       dmin = -1.0;
+    } else if (S->base == VSR_SENSOR_CRUMPLING) { /* Crumpling.java */
+      const OBody* b = &r->bodies[4 * v];
+      double c = 0.0;
+      for (int i = 0; i < 4; i++)
+        for (int j = i + 1; j < 4; j++) {
+          double dx = b[i].x - b[j].x, dy = b[i].y - b[j].y;
+          if (sqrt(dx * dx + dy * dy) < R->d->material.side_length * 0.2) c = c + 1.0;
+        }
+      raw[0] = 2.0 * c / 12.0;
+    } else if (S->base == VSR_SENSOR_CONTROL_POWER) { /* ControlPower.java: lastT = the previous sense time */
+      raw[0] = r->ctrl_energy[v] / (T[tick] - (tick > 0 ? T[tick - 1] : 0.0));
+      dmax = 1.0 / S->max_velocity_norm;
     } else { /* Velocity.sense, Velocity.java:57-80 */
       const OBody* b = &r->bodies[4 * v];
       double vx = 0, vy = 0;

@@ -247,3 +247,17 @@ def test_noisy_sensors_draw_from_java_util_random():
             assert rn[k, v, 2] - rc[k, v, 2] == pytest.approx(s2[2 * k + 1] * sigma * 1.0, abs=1e-12)
             assert rn[k, v, 3] - rc[k, v, 3] == pytest.approx(s1[k] * sigma * 1.0, abs=1e-12)          # Constant in [0, 1]
     assert s1[0] == pytest.approx(0.8025330637390305, abs=1e-15)   # Random(0).nextGaussian()
+
+
+def test_crumpling_and_control_power():
+    body = H.Grid.create(2, 1, lambda x, y: H.Voxel([H.Crumpling(), H.ControlPower(1 / 60), H.AppliedForce()]))
+    r = [H.Robot(H.PhaseSin(1.0, 0.8, H.Grid.create(2, 1, 0.0)), body)]
+    res, pr = oracle.run(helpers.locomotion(1.0).compile(r), readings=True, signals=True)
+    rd = pr["readings"][0].reshape(-1, 2, 3)
+    t = H.tick_times(1.0, 1 / 60)
+    assert np.all(rd[:, :, 0] == 0.0)                       # Crumpling.java: no two masses within 0.6
+    f = pr["signals"][0][:, :2]
+    energy = np.cumsum(np.vstack([np.zeros((1, 2)), f[:-1] ** 2]), axis=0)   # Voxel.act adds the previous force squared
+    dt = np.diff(np.concatenate([[0.0], t]))
+    assert rd[:, :, 1] == pytest.approx(energy / dt[:, None], rel=1e-12, abs=1e-12)   # ControlPower.java
+    assert res[0]["control_energy_last"] == pytest.approx(energy[-1].sum(), rel=1e-12)

@@ -313,3 +313,24 @@ def test_fp64_noisy_sensors():
     clean, _ = helpers.gpu_run(helpers.locomotion(3.0).compile(
         helpers.mlp_robots(3, shape="biped-4x3", sensors="uniform-t+vxy+a-0", hidden=(4,), seed=23), precision=F64))
     assert np.abs(clean["last_center_x"] - res["last_center_x"]).max() > 1e-6      # the noise reaches the controller
+
+
+def test_fp64_custom_sensor_sets():
+    """Crumpling, ControlPower, AppliedForce, a soft-normalised Angle and a noisy constant on every voxel,
+    read by a DistributedSensing controller."""
+    mk = lambda x, y: H.Voxel([H.Crumpling(), H.ControlPower(1 / 60), H.AppliedForce(),
+                               H.SoftNormalization(H.Angle()), H.Noisy(H.Constant(0.25 * x), 0.1, 3)])
+    body = H.Grid.create(3, 2, mk)
+    rng = np.random.default_rng(5)
+    robots = []
+    for _ in range(3):
+        ds = H.DistributedSensing(body, 1)
+        for (x, y), v in body:
+            nin, nout = ds.n_of_inputs(x, y), ds.n_of_outputs(x, y)
+            nw = H.MultiLayerPerceptron.count_weights([nin, 3, nout])
+            ds.get_functions().set(x, y, H.MultiLayerPerceptron("TANH", nin, [3], nout, rng.uniform(-1, 1, size=nw)))
+        robots.append(H.Robot(ds, body))
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :24, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
