@@ -445,6 +445,12 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     }
     S.n_readings = ro;
     S.n_channels = maxch;
+    // PhaseSin / TimeFunctions never read a sensor and no reading is observable through the boundary
+    // (Outcome, Observation): the sensor programs of such a batch are validated above and then dropped
+    if (d->controller_kind == VSR_CTRL_PHASE_SIN || d->controller_kind == VSR_CTRL_TABULATED) {
+      for (int v = 0; v < nv; v++) S.n_sens[v] = 0;
+      S.n_channels = 0;
+    }
     // controller layout
     if (d->controller_kind == VSR_CTRL_PHASE_SIN) S.n_params = 2 + nv;
     else if (d->controller_kind == VSR_CTRL_TABULATED) S.n_params = nt * nv;
