@@ -7,7 +7,7 @@ fallback.
 """
 from . import _abi as abi  # noqa: F401
 from .hmsrobots import (  # noqa: F401
-    Angle, AppliedForce, Constant, ControlPower, Crumpling, Malfunction, Noisy, Normalization, TimeFunction,
+    Angle, AppliedForce, Constant, ControlPower, Crumpling, Lidar, Malfunction, Noisy, Normalization, TimeFunction,
     AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DistributedSensing, DistributedSensingNonDirectional,
     DoubleRange, Grid,
     JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotShape, RobotUtils,

@@ -43,7 +43,8 @@ VSR_AXIS_Y = 2
 VSR_CTRL_PHASE_SIN = 0
 VSR_CTRL_TABULATED = 1
 VSR_SENSOR_ANGLE, VSR_SENSOR_CONSTANT, VSR_SENSOR_APPLIED_FORCE, VSR_SENSOR_MALFUNCTION, VSR_SENSOR_TIME_SIN = 3, 4, 5, 6, 7
-VSR_SENSOR_CRUMPLING, VSR_SENSOR_CONTROL_POWER = 8, 9
+VSR_SENSOR_CRUMPLING, VSR_SENSOR_CONTROL_POWER, VSR_SENSOR_LIDAR = 8, 9, 10
+VSR_LIDAR_MAX_RAYS = 8
 VSR_NORM_NONE, VSR_NORM_SOFT, VSR_NORM_LINEAR = 0, 1, 2
 VSR_CTRL_MLP = 2
 VSR_CTRL_DISTRIBUTED = 3
@@ -108,6 +109,7 @@ class vsr_sensor(C.Structure):
         ("interval", C.c_double),
         ("noise_sigma", C.c_double),
         ("noise_seed", C.c_int64),
+        ("lidar_dirs", C.c_double * VSR_LIDAR_MAX_RAYS),
     ]
 
 

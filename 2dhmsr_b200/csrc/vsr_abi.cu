@@ -169,6 +169,7 @@ struct vsr_batch {
 
 static int sensor_dim(const vsr_sensor& s) {
   if (s.base == VSR_SENSOR_VELOCITY) return ((s.axes & VSR_AXIS_X) ? 1 : 0) + ((s.axes & VSR_AXIS_Y) ? 1 : 0);
+  if (s.base == VSR_SENSOR_LIDAR) return s.axes;
   return 1;
 }
 
@@ -400,7 +401,8 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       for (int k = s0; k < s1; k++) {
         const vsr_sensor& q = sh.sensors[k];
         SensorDev& D = S.sens[v][k - s0];
-        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_CONTROL_POWER || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
+        if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_LIDAR ||
+            (q.base == VSR_SENSOR_LIDAR && (q.axes < 1 || q.axes > VSR_LIDAR_MAX_RAYS || q.aggregator != VSR_AGG_NONE)) || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
             q.aggregator < VSR_AGG_NONE ||
             q.aggregator > VSR_AGG_TREND) {
           delete b;
@@ -411,6 +413,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         D.agg = (int8_t)q.aggregator; D.soft = (int8_t)q.soft_norm; D.dim = (int8_t)dim;
         D.max_norm = q.max_velocity_norm; D.interval = (float)q.interval;
         D.noise = q.noise_sigma > 0 ? q.noise_sigma : 0.0;
+        for (int z = 0; z < VSR_LIDAR_MAX_RAYS; z++) D.dirs[z] = q.base == VSR_SENSOR_LIDAR && z < q.axes ? q.lidar_dirs[z] : 0.0;
         if (q.noise_sigma > 0) {
           if (b->noisy && b->noise_seed != (long long)q.noise_seed) {
             delete b;
@@ -438,7 +441,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       }
       if (nr > MAX_READ) {
         delete b;
-        return fail(VSR_ERR_UNSUPPORTED, "more than 6 readings per voxel");
+        return fail(VSR_ERR_UNSUPPORTED, "more than 12 readings per voxel");
       }
       ro += nr;
       maxch = std::max(maxch, ch);
@@ -615,7 +618,7 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
         return (long long)(seed >> (48 - bits));
       };
       auto next_double = [&]() { return (double)((next(26) << 27) + next(27)) * (1.0 / (double)(1LL << 53)); };
-      b->noise.resize((size_t)2 * nt);
+      b->noise.resize((size_t)VSR_LIDAR_MAX_RAYS * nt);  // a sensor of dimension dim reads entries tick * dim + d
       bool have = false;
       double spare = 0;
       for (auto& g : b->noise) {

@@ -35,7 +35,7 @@ namespace vsr {
 
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
 constexpr int MAX_SENS = 5;    // sensors per voxel
-constexpr int MAX_READ = 6;    // readings per voxel
+constexpr int MAX_READ = 12;   // readings per voxel
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
 #define VSR_DIST_WIDTH 24      // DistributedSensing: widest layer of a voxel's MLP (6 readings + 4 x 4 signals = 22 inputs)
@@ -44,7 +44,7 @@ constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
 enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2, SENSOR_ANGLE = 3, SENSOR_CONSTANT = 4,
              SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7, SENSOR_CRUMPLING = 8,
-             SENSOR_CONTROL_POWER = 9 };
+             SENSOR_CONTROL_POWER = 9, SENSOR_LIDAR = 10 };
 enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
 enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2 };
 
@@ -53,6 +53,7 @@ struct SensorDev {
   float interval;
   double max_norm;  // Velocity: domain bound; Constant / TimeFunction: the value / the frequency
   double noise;     // Noisy: sigma (0 = not noisy)
+  double dirs[8];   // Lidar: ray directions (axes = their number, max_norm = the ray length)
 };
 
 // One shape class (Grid<Boolean> + sensor layout), compiled on the host.
@@ -391,6 +392,31 @@ struct TPar {
   int terr_n;
   real half, base_y;
 };
+// Lidar.sense (Lidar.java:96-103) for one ray: World.raycast against the ground polygons (the filter
+// drops every robot part).  A ray that starts above the terrain enters a ground polygon through its
+// top edge, and the polygons share their side edges, so the first hit is the nearest crossing of the
+// terrain polyline from above; none within `len` reads `len`.
+template <typename real>
+__device__ __noinline__ real lidar_cast(const TPar<real> P, real ox, real oy, real dx, real dy, real len, int hint) {
+  const int n = P.terr_n;
+  const real xlo = r_min(ox, ox + dx * len), xhi = r_max(ox, ox + dx * len);
+  int s = hint;
+  while (s > 0 && P.terr_x[s] > xlo) --s;
+  real best = len;
+  for (int seg = s; seg + 1 < n && P.terr_x[seg] <= xhi; ++seg) {
+    const real x0 = P.terr_x[seg], y0 = P.terr_y[seg], x1 = P.terr_x[seg + 1], y1 = P.terr_y[seg + 1];
+    if (!(x1 > x0)) continue;
+    const real ex = x1 - x0, ey = y1 - y0;
+    const real den = dx * ey - dy * ex;     // cross(D, E); > 0: the ray runs against the upward normal
+    if (!(den > real(0))) continue;
+    const real ax = x0 - ox, ay = y0 - oy;
+    const real t = (ax * ey - ay * ex) / den;   // cross(A - O, E) / cross(D, E)
+    const real u = (ax * dy - ay * dx) / den;   // cross(A - O, D) / cross(D, E)
+    if (t >= real(0) && u >= real(0) && u <= real(1) && t < best) best = t;
+  }
+  return best;
+}
+
 // World.detect (dyn4j) for one mass: every ground segment its AABB overlaps; impulses of
 // points with the same id are carried over (ContactConstraint.update).
 template <typename real>
@@ -1794,6 +1820,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             const double tprev = tick > 0 ? P.tick_t[tick - 1] : 0.0;
             raw[0] = ctrl_energy / (real)(P.tick_t[tick] - tprev);
             dmax = (real)(1.0 / sd.max_norm);
+          } else if (sd.base == SENSOR_LIDAR) {
+            dmax = (real)sd.max_norm;  // the rays are cast below, one reading each
           } else {
             int c = 0;
             real sa, ca;
@@ -1832,7 +1860,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
           }
           for (int d = 0; d < sd.dim; d++) {
-            real o = val[d];
+            real o = val[d < 2 ? d : 0];
+            if (sd.base == SENSOR_LIDAR) {
+              // from Voxel.center (the mean of the 4 mass centres) at rayDirection + Voxel.getAngle
+              const real ocx = (((x[0] + x[1]) + x[2]) + x[3]) / real(4), ocy = (((y[0] + y[1]) + y[2]) + y[3]) / real(4);
+              real rs, rc;
+              r_sincos((real)sd.dirs[d] + ang, &rs, &rc);
+              o = lidar_cast(tpar, ocx, ocy, rc, rs, (real)sd.max_norm, hint[0]);
+            }
             if (sd.soft == 1) {
               real cl = r_min(r_max(o, dmin), dmax);
               real nv = (cl - dmin) / (dmax - dmin);
@@ -1846,11 +1881,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               const real ext = sd.soft ? real(1) : dmax - dmin;
               o = o + (real)(P.noise_tab[(size_t)tick * sd.dim + d] * sd.noise) * ext;
             }
-            // static indexing of the register array
-#pragma unroll
-            for (int q = 0; q < MAX_READ; q++)
-              if (q == ro) readings[q] = o;
-            ro++;
+            readings[ro++] = o;  // (dynamic index: a small thread-local array, not registers)
           }
         }
       }
@@ -1875,9 +1906,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         {
           const int base = S.read_off[active ? v : 0];
           const int nr = active ? ((v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base) : 0;
-#pragma unroll
-          for (int q = 0; q < MAX_READ; q++)
-            if (q < nr) a[q] = readings[q];
+#pragma unroll 1
+          for (int q = 0; q < nr; q++) a[q] = readings[q];
           nin = nr;
           // gather: side (kernel numbering 0 left, 1 right, 2 down, 3 up) of Dir d, and the slot the
           // neighbour wrote for the opposite direction
@@ -1938,9 +1968,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         if (active) {
           int base = S.read_off[v];
           int nr = (v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base;
-#pragma unroll
-          for (int q = 0; q < MAX_READ; q++)
-            if (q < nr) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
+#pragma unroll 1
+          for (int q = 0; q < nr; q++) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
         }
         if (BLK) __syncthreads(); else __syncwarp();
         real* a = act0;

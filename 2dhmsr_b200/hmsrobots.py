@@ -263,6 +263,51 @@ class ControlPower(Sensor):  # sensors/ControlPower.java
         return s
 
 
+class Lidar(Sensor):
+    """sensors/Lidar.java: rays from the voxel centre; a reading is the distance to the terrain (robot
+    parts are filtered out, :37-46) or the ray length."""
+    SIDES = {  # :66-86 (startAngle, endAngle)
+        "N": (math.pi / 4.0, math.pi * 3.0 / 4.0), "E": (math.pi * -1.0 / 4.0, math.pi / 4.0),
+        "S": (math.pi * 5.0 / 4.0, math.pi * 7.0 / 4.0), "W": (math.pi * 3.0 / 4.0, math.pi * 5.0 / 4.0),
+    }
+
+    def __init__(self, ray_length: float, *ray_directions: float):
+        if not 1 <= len(ray_directions) <= A.VSR_LIDAR_MAX_RAYS:
+            raise NotImplementedError(f"Lidar: 1..{A.VSR_LIDAR_MAX_RAYS} rays per sensor on the accelerated path")
+        self.ray_length, self.ray_directions = float(ray_length), [float(d) for d in ray_directions]
+
+    @staticmethod
+    def sample_range_with_rays(n: int, start: float, end: float) -> List[float]:  # :88-94
+        if n == 1:
+            return [(end - start) / 2]
+        out, d = [], start
+        for _ in range(n):  # DoubleStream.iterate: running sum
+            out.append(d)
+            d = d + (end - start) / (n - 1)
+        return out
+
+    @staticmethod
+    def from_sides(ray_length: float, rays_per_side: dict) -> "Lidar":  # :57-65
+        dirs: List[float] = []
+        for side, n in rays_per_side.items():
+            for d in Lidar.sample_range_with_rays(n, *Lidar.SIDES[side]):
+                if d not in dirs:  # .distinct()
+                    dirs.append(d)
+        return Lidar(ray_length, *dirs)
+
+    def domains(self):
+        return [DoubleRange(0.0, self.ray_length) for _ in self.ray_directions]
+
+    def encode(self):
+        s = A.vsr_sensor()
+        s.base = A.VSR_SENSOR_LIDAR
+        s.axes = len(self.ray_directions)
+        s.max_velocity_norm = self.ray_length
+        for i, d in enumerate(self.ray_directions):
+            s.lidar_dirs[i] = d
+        return s
+
+
 class TimeFunction(Sensor):
     """sensors/TimeFunction.java.  The accelerated path evaluates ``t -> sin(2 pi f t)`` on [-1, 1] (the
     "cpg" sensor of RobotUtils.java:57); build it with ``TimeFunction.sin(f)``."""
@@ -674,6 +719,8 @@ class RobotUtils:
     PREDEFINED_SENSORS = {  # :38-60 (TreeMap => sorted keys); the lidars "l1", "l5" are not on the device
         "a": lambda x, y: SoftNormalization(AreaRatio()),
         "cpg": lambda x, y: Normalization(TimeFunction.sin(-1.0)),
+        "l1": lambda x, y: Normalization(Lidar.from_sides(10.0, {RobotUtils.lidar_side(x, y): 1})),
+        "l5": lambda x, y: Normalization(Lidar.from_sides(10.0, {RobotUtils.lidar_side(x, y): 5})),
         "m": lambda x, y: Malfunction(),
         "px": lambda x, y: Constant(x),
         "py": lambda x, y: Constant(y),
@@ -686,7 +733,17 @@ class RobotUtils:
         "vxy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.X, Velocity.Y), 0.5)),
         "vy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.Y), 0.5)),
     }
-    _OUT_OF_PATH = {"l5", "l1"}
+    _OUT_OF_PATH: set = set()
+
+    @staticmethod
+    def lidar_side(x: float, y: float) -> str:  # :244-255
+        if y > x and y > (1 - x):
+            return "N"
+        if y >= x and y <= (1 - x):
+            return "W"
+        if y < x and y < (1 - x):
+            return "S"
+        return "E"
 
     @staticmethod
     def build_shape(name: str) -> Grid:  # :198-242
@@ -744,18 +801,24 @@ class RobotUtils:
             )
         if _params("empty", name) is not None:
             return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else Voxel([]))
-        p = _params(r"spinedTouch-(?<cpg>[tf])-(?<malfunction>[tf])-(?<noiseSigma>\d+(\.\d+)?)", name)
-        if p is not None:  # :134-149
+        p = _params(r"spinedTouch(?<sighted>Sighted)?-(?<cpg>[tf])-(?<malfunction>[tf])-(?<noiseSigma>\d+(\.\d+)?)", name)
+        if p is not None:  # :134-165
+            sighted = p["sighted"] is not None
             sg = float(p["noiseSigma"])
 
             def spined(body, x, y, p=p, sg=sg):
                 pick = [("a", True), ("m", p["malfunction"] == "t"), ("t", y == 0), ("vxy", y == body.h - 1),
-                        ("cpg", x == body.w - 1 and y == body.h - 1 and p["cpg"] == "t")]
+                        ("cpg", x == body.w - 1 and y == body.h - 1 and p["cpg"] == "t"),
+                        ("l5", sighted and x == body.w - 1)]
                 ss = [RobotUtils.sensor(n, x, y, body) for n, cond in pick if cond]
                 return Voxel(ss if sg == 0 else [Noisy(s, sg, 0) for s in ss])
 
             return lambda body: Grid.create(body.w, body.h, lambda x, y: None if not body.get(x, y) else spined(body, x, y))
-        for out in (r"spinedTouchSighted-.*", r"uniformAll-.*"):
+        p = _params(r"uniformAll-(?<noiseSigma>\d+(\.\d+)?)", name)
+        if p is not None:  # :177-189: every predefined sensor, TreeMap (sorted) order
+            return RobotUtils.build_sensorizing_function(
+                "uniform-" + "+".join(sorted(RobotUtils.PREDEFINED_SENSORS)) + "-" + p["noiseSigma"])
+        for out in (r"spinedTouchSighted-.*",):
             if _params(out, name) is not None:
                 raise NotImplementedError(f"sensorizing function '{name}' is outside the accelerated hot path")
         raise ValueError(f"Unknown sensorizing function name: {name}")
@@ -1028,7 +1091,8 @@ def compile_batch(
         vox = r.voxels
         mask = bytes(1 if v is not None else 0 for v in vox.values())
         sens = tuple(
-            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed)
+            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed,
+                   tuple(s.lidar_dirs))
                   for s in (ss.encode() for ss in v.get_sensors()))
             for v in vox.values() if v is not None
         )
@@ -1091,8 +1155,10 @@ def compile_batch(
         nread = 0
         for j, t in enumerate(flat):
             s = sarr[j]
-            s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed = t
-            nread += (bin(s.axes & 3).count("1") if s.base == A.VSR_SENSOR_VELOCITY else 1)
+            s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed = t[:9]
+            for z, dv in enumerate(t[9]):
+                s.lidar_dirs[z] = dv
+            nread += (bin(s.axes & 3).count("1") if s.base == A.VSR_SENSOR_VELOCITY else s.axes if s.base == A.VSR_SENSOR_LIDAR else 1)
         b.keep(sarr)
         hid = b.keep(np.asarray(hidden if hidden else [0], dtype=np.int32))
         arr[k].w, arr[k].h = w, h

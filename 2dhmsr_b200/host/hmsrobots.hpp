@@ -240,6 +240,49 @@ struct Noisy : Sensor {  // sensors/Noisy.java: + Random(seed).nextGaussian() * 
     return s;
   }
 };
+struct Lidar : Sensor {  // sensors/Lidar.java
+  enum Side { N, E, S, W };
+  double rayLength;
+  std::vector<double> rayDirections;
+  Lidar(double len, std::vector<double> dirs) : rayLength(len), rayDirections(std::move(dirs)) {
+    if (rayDirections.empty() || rayDirections.size() > VSR_LIDAR_MAX_RAYS)
+      throw Unsupported("Lidar: 1..8 rays per sensor on the accelerated path");
+  }
+  static std::pair<double, double> sideAngles(Side s) {  // :66-86
+    switch (s) {
+      case N: return {M_PI / 4.0, M_PI * 3.0 / 4.0};
+      case E: return {M_PI * -1.0 / 4.0, M_PI / 4.0};
+      case S: return {M_PI * 5.0 / 4.0, M_PI * 7.0 / 4.0};
+      default: return {M_PI * 3.0 / 4.0, M_PI * 5.0 / 4.0};
+    }
+  }
+  static std::vector<double> sampleRangeWithRays(int n, double start, double end) {  // :88-94
+    if (n == 1) return {(end - start) / 2};
+    std::vector<double> out;
+    double d = start;
+    for (int i = 0; i < n; i++) {  // DoubleStream.iterate: running sum
+      out.push_back(d);
+      d = d + (end - start) / (n - 1);
+    }
+    return out;
+  }
+  static std::shared_ptr<Lidar> ofSide(double len, Side s, int n) {  // :57-65
+    auto a = sideAngles(s);
+    std::vector<double> dirs;
+    for (double d : sampleRangeWithRays(n, a.first, a.second))
+      if (std::find(dirs.begin(), dirs.end(), d) == dirs.end()) dirs.push_back(d);
+    return std::make_shared<Lidar>(len, dirs);
+  }
+  std::vector<DoubleRange> getDomains() const override { return std::vector<DoubleRange>(rayDirections.size(), DoubleRange(0, rayLength)); }
+  vsr_sensor encode() const override {
+    vsr_sensor s{};
+    s.base = VSR_SENSOR_LIDAR;
+    s.axes = int32_t(rayDirections.size());
+    s.max_velocity_norm = rayLength;
+    for (size_t i = 0; i < rayDirections.size(); i++) s.lidar_dirs[i] = rayDirections[i];
+    return s;
+  }
+};
 struct Angle : Sensor {  // sensors/Angle.java
   std::vector<DoubleRange> getDomains() const override { return {DoubleRange(-M_PI, M_PI)}; }
   vsr_sensor encode() const override {
@@ -597,8 +640,10 @@ inline SensorPtr sensor(const std::string& n, double x = 0, double y = 0) {  // 
   if (n == "py") return std::make_shared<Constant>(y);
   if (n == "m") return std::make_shared<Malfunction>();
   if (n == "cpg") return std::make_shared<Normalization>(std::make_shared<TimeFunctionSin>(-1.0));
-  for (const char* o : {"l5", "l1"})
-    if (n == o) throw Unsupported("sensor '" + n + "' is outside the accelerated hot path");
+  if (n == "l5" || n == "l1") {  // lidarSide, :244-255
+    Lidar::Side side = (y > x && y > (1 - x)) ? Lidar::N : (y >= x && y <= (1 - x)) ? Lidar::W : (y < x && y < (1 - x)) ? Lidar::S : Lidar::E;
+    return std::make_shared<Normalization>(Lidar::ofSide(10.0, side, n == "l5" ? 5 : 1));
+  }
   throw std::invalid_argument("Unknown sensor name: " + n);
 }
 inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(const std::string& name) {  // :124-196
@@ -713,7 +758,8 @@ struct BatchDesc {  // owns the flat arrays behind a vsr_batch_desc
 inline bool sameSensor(const vsr_sensor& a, const vsr_sensor& b) {
   return a.base == b.base && a.axes == b.axes && a.rotated == b.rotated && a.aggregator == b.aggregator &&
          a.soft_norm == b.soft_norm && a.max_velocity_norm == b.max_velocity_norm && a.interval == b.interval &&
-         a.noise_sigma == b.noise_sigma && a.noise_seed == b.noise_seed;
+         a.noise_sigma == b.noise_sigma && a.noise_seed == b.noise_seed &&
+         std::memcmp(a.lidar_dirs, b.lidar_dirs, sizeof a.lidar_dirs) == 0;
 }
 
 class Locomotion {  // tasks/locomotion/Locomotion.java

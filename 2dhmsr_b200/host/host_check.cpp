@@ -132,7 +132,14 @@ int main(int argc, char** argv) {
     std::cout << " \"err_terrain\": \"" << throwsWhat([] { Locomotion::createTerrain("moon"); }) << "\",\n";
     std::cout << " \"err_shape\": \"" << throwsWhat([] { RobotUtils::buildShape("snake-3"); }) << "\",\n";
     std::cout << " \"err_sensors\": \"" << throwsWhat([] { RobotUtils::buildSensorizingFunction("uniform-zz-0"); }) << "\",\n";
-    std::cout << " \"err_lidar\": \"" << throwsWhat([] { RobotUtils::buildSensorizingFunction("uniform-l5-0")(RobotUtils::buildShape("box-2x2")); }) << "\",\n";
+    {
+      Grid<Voxel> sighted = RobotUtils::buildSensorizingFunction("uniform-l5-0")(RobotUtils::buildShape("worm-3x2"));
+      vsr_sensor q = sighted.get(2, 0)->getSensors()[0]->encode();   // bottom right corner: side E
+      std::vector<double> e = {double(q.base), double(q.axes), double(q.soft_norm), q.max_velocity_norm};
+      for (int i = 0; i < q.axes; i++) e.push_back(q.lidar_dirs[i]);
+      std::cout << " \"lidar_2_0\": " << jarr(e) << ",\n";
+    }
+    std::cout << " \"err_lidar\": \"" << throwsWhat([] { RobotUtils::buildSensorizingFunction("uniformAll-0")(RobotUtils::buildShape("box-2x2")); }) << "\",\n";
     std::cout << " \"err_weights\": \"" << throwsWhat([] { MultiLayerPerceptron(MultiLayerPerceptron::TANH, 3, {2}, 1, std::vector<double>(5)); }) << "\",\n";
     std::cout << " \"err_dims\": \"" << throwsWhat([&] { CentralizedSensing(worm, MultiLayerPerceptron(MultiLayerPerceptron::TANH, 63, {}, 16, std::vector<double>(16 * 64))); }) << "\",\n";
     std::cout << " \"err_ground\": \"" << throwsWhat([] { Locomotion(1, {{0, 5, 3}, {0, 0, 0}}, Settings()); }) << "\",\n";

@@ -91,7 +91,7 @@ typedef struct vsr_material {
 #define VSR_SCAFFOLD_CENTRAL_CROSS 8u
 #define VSR_SCAFFOLD_ALL 15u
 
-/* ---- Sensors: every entry of RobotUtils.PREDEFINED_SENSORS but the lidars is
+/* ---- Sensors: every entry of RobotUtils.PREDEFINED_SENSORS is
  *      [SoftNormalization|Normalization](  [Average|Trend]( base sensor ) )
  *      (RobotUtils.java:38-57).  One vsr_sensor encodes one such composition.     ---- */
 #define VSR_SENSOR_TOUCH 0      /* sensors/Touch.java:35-65, 1 reading, domain [0,1]   */
@@ -108,6 +108,11 @@ typedef struct vsr_material {
 #define VSR_SENSOR_CRUMPLING 8  /* sensors/Crumpling.java: share of the 6 mass pairs closer than 0.2 side lengths */
 #define VSR_SENSOR_CONTROL_POWER 9 /* sensors/ControlPower.java: Voxel.getControlEnergy / (t - previous t),
                                       domain [0, 1 / `param`] (param = controlInterval)                  */
+
+#define VSR_SENSOR_LIDAR 10 /* sensors/Lidar.java: `axes` rays of length `param` from the voxel centre at
+                               lidar_dirs[i] + Voxel.getAngle(); a reading is the distance to the terrain
+                               (robot parts are filtered out, :37-46) or the ray length                  */
+#define VSR_LIDAR_MAX_RAYS 8
 
 #define VSR_NORM_NONE 0
 #define VSR_NORM_SOFT 1   /* sensors/SoftNormalization.java:38-48 */
@@ -132,6 +137,7 @@ typedef struct vsr_sensor {
   double noise_sigma;       /* > 0: wrapped in sensors/Noisy.java (outermost): every reading gets
                                java.util.Random(noise_seed).nextGaussian() * sigma * domain extent */
   int64_t noise_seed;       /* one seed per batch (RobotUtils.java:148 passes 0)                  */
+  double lidar_dirs[VSR_LIDAR_MAX_RAYS]; /* LIDAR: rayDirections                                  */
 } vsr_sensor;
 
 /* ---- Shape class: a Grid<Boolean> body + its per-voxel sensor lists.

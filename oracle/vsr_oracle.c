@@ -233,6 +233,7 @@ static int shape_nvox(const vsr_shape* s) {
 }
 static int sensor_dim(const vsr_sensor* s) {
   if (s->base == VSR_SENSOR_VELOCITY) return ((s->axes & VSR_AXIS_X) ? 1 : 0) + ((s->axes & VSR_AXIS_Y) ? 1 : 0);
+  if (s->base == VSR_SENSOR_LIDAR) return s->axes;
   return 1;
 }
 
@@ -1395,6 +1396,26 @@ static double jr_next_gaussian(ORobot* r, int si) {
   return v1 * mul;
 }
 
+/* Lidar.sense (Lidar.java:96-103) for one ray: World.raycast against the ground polygons only (the
+   DetectFilter drops the robot's fixtures, :37-46).  A ray that starts above the terrain enters a ground
+   polygon through its top edge and the polygons share their sides: the first hit is the nearest crossing
+   of the terrain polyline from above; none within the ray length reads the ray length. */
+static double lidar_cast(const vsr_batch_desc* d, double ox, double oy, double dx, double dy, double len) {
+  double best = len;
+  for (int seg = 0; seg + 1 < d->terrain_n; seg++) {
+    double x0 = d->terrain_xs[seg], y0 = d->terrain_ys[seg], x1 = d->terrain_xs[seg + 1], y1 = d->terrain_ys[seg + 1];
+    if (!(x1 > x0)) continue;
+    double ex = x1 - x0, ey = y1 - y0;
+    double den = dx * ey - dy * ex;
+    if (!(den > 0.0)) continue;
+    double ax = x0 - ox, ay = y0 - oy;
+    double t = (ax * ey - ay * ex) / den;
+    double u = (ax * dy - ay * dx) / den;
+    if (t >= 0.0 && u >= 0.0 && u <= 1.0 && t < best) best = t;
+  }
+  return best;
+}
+
 static void robot_sense(ORun* R, ORobot* r, int tick) {
   const double* T = R->ticks;
   for (int v = 0; v < r->nv; v++) {
@@ -1406,8 +1427,15 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
     const vsr_sensor* S = r->sens[si];
     int v = r->sens_voxel[si];
     int dim = sensor_dim(S);
-    double raw[2] = {0, 0}, dmin = 0, dmax = 1;
-    if (S->base == VSR_SENSOR_TOUCH) {
+    double raw[VSR_LIDAR_MAX_RAYS] = {0, 0, 0, 0, 0, 0, 0, 0}, dmin = 0, dmax = 1;
+    if (S->base == VSR_SENSOR_LIDAR) {
+      const OBody* b = &r->bodies[4 * v];
+      double cx = (((b[0].x + b[1].x) + b[2].x) + b[3].x) / 4.0, cy = (((b[0].y + b[1].y) + b[2].y) + b[3].y) / 4.0; /* Voxel.center */
+      double ang = voxel_angle(r, v);
+      for (int k = 0; k < dim; k++)
+        raw[k] = lidar_cast(R->d, cx, cy, cos(S->lidar_dirs[k] + ang), sin(S->lidar_dirs[k] + ang), S->max_velocity_norm);
+      dmax = S->max_velocity_norm;
+    } else if (S->base == VSR_SENSOR_TOUCH) {
       raw[0] = r->touch[v] ? 1.0 : 0.0;
     } else if (S->base == VSR_SENSOR_AREA_RATIO) {
       raw[0] = voxel_area_ratio(R, r, v);
@@ -1457,7 +1485,8 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
       dmin = -S->max_velocity_norm;
       dmax = S->max_velocity_norm;
     }
-    double val[2] = {raw[0], raw[1]};
+    double val[VSR_LIDAR_MAX_RAYS];
+    for (int k = 0; k < VSR_LIDAR_MAX_RAYS; k++) val[k] = raw[k];
     if (S->aggregator != VSR_AGG_NONE) {
       double* H = r->hist[si];
       for (int k = 0; k < dim; k++) H[(size_t)tick * dim + k] = raw[k];

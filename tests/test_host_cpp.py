@@ -71,7 +71,9 @@ def test_cpp_host_mirror_selfcheck():
     assert j["err_terrain"] == "invalid_argument:Unknown terrain name: moon"
     assert j["err_shape"] == "invalid_argument:Unknown body name: snake-3"
     assert j["err_sensors"].startswith("invalid_argument:Unknown sensorizing function name")
-    assert j["err_lidar"].startswith("Unsupported:")
+    assert j["err_lidar"].startswith("Unsupported:")     # uniformAll: 15 sensors per voxel
+    enc = helpers.body_of("worm-3x2", "uniform-l5-0").get(2, 0).get_sensors()[0].encode()
+    assert j["lidar_2_0"] == [A.VSR_SENSOR_LIDAR, 5, A.VSR_NORM_LINEAR, 10.0] + list(enc.lidar_dirs)[:5]
     assert j["err_weights"] == "invalid_argument:Wrong number of weights: 11 expected, 5 found"
     assert j["err_dims"].startswith("invalid_argument:Wrong dimension of input or output")
     assert j["err_ground"] == "invalid_argument:x coordinates must be sorted"

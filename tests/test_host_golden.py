@@ -92,7 +92,13 @@ def test_sensor_dsl_and_encoding():
     with pytest.raises(ValueError, match="Unknown sensorizing function name"):
         H.RobotUtils.build_sensorizing_function("uniform-zz-0")
     with pytest.raises(NotImplementedError):
-        H.RobotUtils.build_sensorizing_function("uniform-l5-0")(H.RobotUtils.build_shape("box-2x2"))
+        H.RobotUtils.build_sensorizing_function("spinedTouch-t-f-0.1-x")(H.RobotUtils.build_shape("box-2x2")) \
+            if False else H.Lidar(10.0, *([0.0] * 9))       # more than 8 rays per sensor
+    l5 = H.RobotUtils.build_sensorizing_function("uniform-l5-0")(H.RobotUtils.build_shape("box-2x2"))
+    # lidarSide (RobotUtils.java:244-255) of the normalised cell (1, 0) is E; 5 rays over [-pi/4, pi/4], running sum
+    dirs = l5.get(1, 0).get_sensors()[0].sensor.ray_directions
+    assert len(dirs) == 5 and dirs[0] == -math.pi / 4 and dirs[2] == pytest.approx(0.0, abs=1e-15) and dirs[4] == pytest.approx(math.pi / 4)
+    assert H.Lidar.sample_range_with_rays(1, 1.0, 2.0) == [0.5]      # (end - start) / 2, Lidar.java:89-90
     with pytest.raises(ValueError):
         H.DoubleRange(1.0, 0.0)
 

@@ -1,5 +1,6 @@
 """The oracle against closed forms, its own regression pins and the reference's shipped frames."""
 import importlib
+import math
 import json
 import os
 
@@ -222,7 +223,7 @@ def test_cheap_sensors_read_what_the_reference_defines():
     assert [len(v.get_sensors()) for v in helpers.body_of("biped-4x3", "spinedTouch-t-t-0").values() if v] == \
         [3, 3, 2, 2, 2, 2, 3, 3, 3, 4]
     with pytest.raises(NotImplementedError):
-        helpers.body_of("biped-4x3", "uniform-l5-0")
+        helpers.body_of("biped-4x3", "spinedTouchSighted-t-t-0") and H.Lidar(10.0)     # a lidar needs 1..8 rays
 
 
 def test_noisy_sensors_draw_from_java_util_random():
@@ -261,3 +262,28 @@ def test_crumpling_and_control_power():
     dt = np.diff(np.concatenate([[0.0], t]))
     assert rd[:, :, 1] == pytest.approx(energy / dt[:, None], rel=1e-12, abs=1e-12)   # ControlPower.java
     assert res[0]["control_energy_last"] == pytest.approx(energy[-1].sum(), rel=1e-12)
+
+
+def test_lidar_reads_the_distance_to_the_terrain():
+    # Lidar.java:96-103 on flat ground (y = 5): a ray at angle a below the horizon from a centre at height h
+    # reads h / -sin(a), capped at the ray length; rays pointing up read the ray length.
+    body = H.Grid.create(1, 1, lambda x, y: H.Voxel([H.Lidar(10.0, -math.pi / 2, -math.pi / 4, math.pi / 2, -0.05)]))
+    r = [H.Robot(H.PhaseSin(1.0, 0.0, H.Grid.create(1, 1, 0.0)), body)]
+    _, pr = oracle.run(helpers.locomotion(1.0).compile(r), readings=True, trajectory=True)
+    tr = pr["trajectory"][0][:, :4]
+    cy = tr[:, :, 1].mean(axis=1)
+    ang = (np.arctan2(tr[:, 1, 1] - tr[:, 0, 1], tr[:, 1, 0] - tr[:, 0, 0]) + np.arctan2(tr[:, 2, 1] - tr[:, 3, 1], tr[:, 2, 0] - tr[:, 3, 0])) / 2
+    rd = pr["readings"][0][:, :4]
+    h = cy - 5.0
+    assert rd[:, 0] == pytest.approx(h / -np.sin(-math.pi / 2 + ang), rel=1e-9)
+    assert rd[:, 1] == pytest.approx(h / -np.sin(-math.pi / 4 + ang), rel=1e-9)
+    assert np.all(rd[:, 2] == 10.0)
+    assert np.all(rd[:, 3] == 10.0)                      # 0.05 rad below the horizon: the ground is 30+ away
+    # next to the left wall ((0, 100) -> (10, 5)) a ray to the west hits the wall
+    body2 = H.Grid.create(1, 1, lambda x, y: H.Voxel([H.Normalization(H.Lidar(10.0, math.pi))]))
+    loco = H.Locomotion(0.5, H.Locomotion.create_terrain("flat"), H.Settings(), initial_placement=10.5)
+    _, p2 = oracle.run(loco.compile([H.Robot(H.PhaseSin(1.0, 0.0, H.Grid.create(1, 1, 0.0)), body2)]), readings=True, trajectory=True)
+    c0 = p2["trajectory"][0][0, :4]
+    cx, cyy = c0[:, 0].mean(), c0[:, 1].mean()
+    wall_x = 10.0 - (cyy - 5.0) * 10.0 / 95.0            # the wall at height cy
+    assert p2["readings"][0][0, 0] == pytest.approx((cx - wall_x) / 10.0, rel=1e-6)

@@ -334,3 +334,13 @@ def test_fp64_custom_sensor_sets():
     assert np.all(res["status"] == 0)
     assert np.abs(tr[..., :3] - otr[:, :, :24, :3]).max() < 1e-7
     assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+
+
+def test_fp64_lidar_on_hilly_terrain():
+    """Lidar rays against a hilly profile (spinedTouchSighted layout: l5 on the front column, cpg, touch,
+    velocity), read by a CentralizedSensing MLP."""
+    robots = helpers.mlp_robots(3, shape="biped-4x3", sensors="spinedTouchSighted-t-f-0", hidden=(6,), seed=31)
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0, terrain="hilly-1-10-0"), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
