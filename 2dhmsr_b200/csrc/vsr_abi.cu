@@ -470,7 +470,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         S.neurons[1 + i] = sh.hidden[i];
         if (sh.hidden[i] <= 0 || sh.hidden[i] > VSR_DIST_WIDTH) {
           delete b;
-          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: hidden layers of 1..24 neurons are supported");
+          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: hidden layers of 1..32 neurons are supported");
         }
       }
       S.neurons[0] = 0;  // per voxel
@@ -479,6 +479,10 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       for (int v = 0; v < nv; v++) {
         const int nin = (v + 1 < nv ? S.read_off[v + 1] : S.n_readings) - S.read_off[v] + 4 * sg;
         S.dist_off[v] = off;
+        if (nin > VSR_DIST_WIDTH || S.neurons[S.n_layers - 1] > VSR_DIST_WIDTH) {
+          delete b;
+          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: at most 32 inputs / outputs per voxel");
+        }
         int prev = nin;
         for (int i = 1; i < S.n_layers; i++) {
           off += S.neurons[i] * (prev + 1);
@@ -789,7 +793,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     long long cap = smem < limit ? (long long)((limit - smem) / (VSR_POOL_FIELDS * sizeof(real))) : 0;
     // one pool per scope: the warp (its robots' constraints), or the block of a big robot
     const int scopes = blk ? 1 : wpb;
-    cap = std::min<long long>(cap / scopes, blk ? (long long)12 * threads : 12 * 32) / 4 * 4;
+    cap = std::min<long long>(cap / scopes, blk ? (long long)VSR_ITEMS_PER_THREAD * threads : VSR_ITEMS_PER_THREAD * 32) / 4 * 4;
     // a big robot's block is small (2..4 warps): a modest pool leaves room for a second block on the SM
     if (blk) cap = std::min<long long>(cap, getenv("VSR_BLK_POOL") ? atoll(getenv("VSR_BLK_POOL")) : 96);
     if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
@@ -836,7 +840,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
       k.sbuf_bytes = need_s;
     }
     P.sbuf = k.d_sbuf;
-    size_t need_l = (size_t)grid * 12 * stride * sizeof(int);
+    size_t need_l = (size_t)grid * VSR_ITEMS_PER_THREAD * stride * sizeof(int);
     if (need_l > k.lbuf_bytes) {
       cudaFree(k.d_lbuf);
       k.d_lbuf = nullptr;

@@ -38,7 +38,7 @@ constexpr int MAX_SENS = 5;    // sensors per voxel
 constexpr int MAX_READ = 12;   // readings per voxel
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
-#define VSR_DIST_WIDTH 24      // DistributedSensing: widest layer of a voxel's MLP (6 readings + 4 x 4 signals = 22 inputs)
+#define VSR_DIST_WIDTH 32      // DistributedSensing: widest layer of a voxel's MLP (12 readings + 4 x 4 signals = 28 inputs)
 constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
@@ -114,7 +114,7 @@ struct Params {
   int smem_per_warp;     // reals of staging per warp
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
-  int* lbuf;             // contact lists: [grid blocks][12 * max threads per block]
+  int* lbuf;             // contact lists: [grid blocks][VSR_ITEMS_PER_THREAD * max threads per block]
   int pool_cap;          // constraints of a block cached in shared memory (the rest stay in global)
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
@@ -1020,6 +1020,8 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
+#define VSR_ITEMS_PER_THREAD 16
+static_assert(4 * MAXC + SC_CAP <= VSR_ITEMS_PER_THREAD, "contact list capacity");
 // candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
 #define VSR_MAX_CAND 8
 #endif
@@ -1068,7 +1070,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
-  int* const items = P.lbuf + (size_t)blockIdx.x * 12 * MTS + (BLK ? 0 : wib * 12 * 32);
+  // (a thread lists at most 4 * MAXC ground + SC_CAP intra-robot constraints)
+  int* const items = P.lbuf + (size_t)blockIdx.x * VSR_ITEMS_PER_THREAD * MTS + (BLK ? 0 : wib * VSR_ITEMS_PER_THREAD * 32);
   const int mt_t = tid;
 #define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
   int exsel = 0;
