@@ -17,3 +17,6 @@ from .hmsrobots import (  # noqa: F401
 from .behavior import (  # noqa: F401
     BehaviorUtils, BoundingBox, Footprint, Gait, Observation, VoxelPoly, build_observations, ground_y_at,
 )
+from .devolocomotion import (  # noqa: F401
+    DevoLocomotion, DevoOutcome, DevoStageOutcome, DistanceBasedDevoLocomotion, TimeBasedDevoLocomotion,
+)

@@ -148,6 +148,8 @@ class vsr_batch_desc(C.Structure):
         ("initial_placement", C.c_double),
         ("settings", vsr_settings),
         ("trajectory_robots", C.c_size_t),
+        ("t_start", C.c_double),
+        ("robot_placement", C.POINTER(C.c_double)),
     ]
 
 
@@ -224,6 +226,8 @@ def _declare(lib) -> None:
     lib.vsr_default_material.restype = None
     lib.vsr_tick_count.argtypes = [C.c_double, C.c_double]
     lib.vsr_tick_count.restype = C.c_int
+    lib.vsr_tick_count_from.argtypes = [C.c_double, C.c_double, C.c_double]
+    lib.vsr_tick_count_from.restype = C.c_int
     lib.vsr_batch_create.argtypes = [C.POINTER(vsr_batch_desc), C.POINTER(vp)]
     lib.vsr_batch_create.restype = C.c_int
     lib.vsr_batch_upload.argtypes = [vp, C.c_int, vp]
@@ -236,6 +240,8 @@ def _declare(lib) -> None:
     lib.vsr_batch_results_device.restype = C.c_int
     lib.vsr_batch_trajectory.argtypes = [vp, sz, C.POINTER(C.c_double), sz]
     lib.vsr_batch_trajectory.restype = C.c_longlong
+    lib.vsr_batch_final_bbox.argtypes = [vp, C.POINTER(C.c_double), sz]
+    lib.vsr_batch_final_bbox.restype = C.c_int
     lib.vsr_batch_voxel_trace.argtypes = [vp, sz, C.POINTER(C.c_double), sz]
     lib.vsr_batch_voxel_trace.restype = C.c_longlong
     lib.vsr_batch_voxel_steps.argtypes = [vp]
@@ -259,9 +265,9 @@ def _declare(lib) -> None:
 
 
 EXPORTED_SYMBOLS = [
-    "vsr_default_settings", "vsr_default_material", "vsr_tick_count", "vsr_batch_create",
+    "vsr_default_settings", "vsr_default_material", "vsr_tick_count", "vsr_tick_count_from", "vsr_batch_create",
     "vsr_batch_upload", "vsr_batch_run", "vsr_batch_results", "vsr_batch_results_device",
-    "vsr_batch_trajectory", "vsr_batch_voxel_trace", "vsr_batch_voxel_steps", "vsr_batch_n_ticks", "vsr_batch_n_bodies",
+    "vsr_batch_trajectory", "vsr_batch_final_bbox", "vsr_batch_voxel_trace", "vsr_batch_voxel_steps", "vsr_batch_n_ticks", "vsr_batch_n_bodies",
     "vsr_batch_last_launches", "vsr_batch_upload_bytes", "vsr_batch_destroy", "vsr_last_error", "vsr_abi_version",
     "vsr_device_count",
 ]

@@ -85,9 +85,9 @@ extern "C" void vsr_default_material(vsr_material* m) {
 }
 
 // Locomotion.java:195-203 + AbstractTask.java:48: t = 0; while (t < finalT) t = t + dT;
-static std::vector<double> tick_times(double final_t, double dt) {
+static std::vector<double> tick_times(double final_t, double dt, double t_start = 0.0) {
   std::vector<double> t;
-  double tt = 0.0;
+  double tt = t_start;
   while (tt < final_t) {
     tt = tt + dt;
     t.push_back(tt);
@@ -97,6 +97,10 @@ static std::vector<double> tick_times(double final_t, double dt) {
 extern "C" int vsr_tick_count(double final_t, double dt) {
   if (!(dt > 0)) return 0;
   return (int)tick_times(final_t, dt).size();
+}
+extern "C" int vsr_tick_count_from(double t_start, double final_t, double dt) {
+  if (!(dt > 0)) return 0;
+  return (int)tick_times(final_t, dt, t_start).size();
 }
 
 namespace {
@@ -118,6 +122,11 @@ struct Bucket {
   void* d_params = nullptr;
   void* d_ring = nullptr;
   void* d_traj = nullptr;
+  // per-robot initial placement (vsr_batch_desc.robot_placement): offsets from the shape's default one
+  std::vector<double> place_off;  // [robots][2]
+  void* d_place = nullptr;
+  std::vector<double> unplaced_x, unplaced_y;  // the shape's masses with bbox.min.x = 0, y as assembled
+  double default_dx = 0, default_dy = 0;
   void* d_vtrace = nullptr;
   void* d_cbuf = nullptr;
   size_t cbuf_bytes = 0;
@@ -163,6 +172,7 @@ struct vsr_batch {
   void* d_terr_x = nullptr;
   void* d_terr_y = nullptr;
   double* d_results = nullptr;
+  double* d_bbox = nullptr;  // Robot.boundingBox at the last tick, [n_robots][4]
   int last_launches = 0;
   std::vector<Xfer> xfers;  // not shared: one handle per host thread
 };
@@ -193,12 +203,14 @@ static void free_device(vsr_batch* b) {
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
     cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr;
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_place = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
     k.d_sbuf = nullptr; k.sbuf_bytes = 0;
     k.d_lbuf = nullptr; k.lbuf_bytes = 0;
   }
   cudaFree(b->d_results);
+  cudaFree(b->d_bbox);
+  b->d_bbox = nullptr;
   b->d_ticks = nullptr; b->d_win = nullptr; b->d_terr_x = b->d_terr_y = nullptr; b->d_results = nullptr;
   b->uploaded = b->ran = false;
 }
@@ -249,7 +261,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
   b->desc = *d;
   b->precision = (int)d->precision;
   b->n_robots = d->n_robots;
-  b->ticks = tick_times(d->final_t, st.step_frequency);
+  b->ticks = tick_times(d->final_t, st.step_frequency, d->t_start);
   const int nt = (int)b->ticks.size();
   if (nt == 0) {
     delete b;
@@ -386,6 +398,14 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     for (int i = 0; i < nv * 4; i++) {
       S.init_x[i] = X[i] - b->origin_x;
       S.init_y[i] = Y[i] + dy;
+    }
+    {
+      Bucket& kb = buckets[si];
+      kb.unplaced_x.resize((size_t)nv * 4);
+      kb.unplaced_y = Y;
+      for (int i = 0; i < nv * 4; i++) kb.unplaced_x[i] = X[i] - d->initial_placement;  // bbox.min.x at 0
+      kb.default_dx = d->initial_placement;
+      kb.default_dy = dy;
     }
     // sensors
     int ro = 0, maxch = 0;
@@ -541,6 +561,27 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     b->robot_nvox[r] = S.nvox;
     k.robot_ids.push_back((int)r);
     if ((size_t)r < d->trajectory_robots) k.traj_robots++;
+    if (d->robot_placement) {
+      // Locomotion.java:180-187 for this robot's own placement: x to the placement, y one unit above the ground
+      const double px = d->robot_placement[r];
+      double min_gap = INFINITY;
+      const double hh = m.side_length * m.mass_side_length_ratio / 2.0;
+      for (int v = 0; v < S.nvox; v++) {
+        double cx = 0, mny = INFINITY;
+        for (int q = 0; q < 4; q++) {
+          cx += k.unplaced_x[v * 4 + q] + px;
+          mny = std::min(mny, k.unplaced_y[v * 4 + q] - hh);
+        }
+        cx /= 4.0;
+        min_gap = std::min(min_gap, mny - ground_y_at(d, cx));
+      }
+      if (!std::isfinite(px) || !std::isfinite(min_gap)) {
+        delete b;
+        return fail(VSR_ERR_INVALID_ARGUMENT, "initial placement outside the ground profile");
+      }
+      k.place_off.push_back(px - k.default_dx);
+      k.place_off.push_back((1.0 - min_gap) - k.default_dy);
+    }
     size_t base = k.params.size();
     k.params.resize(base + np);
     if (d->controller_kind == VSR_CTRL_MLP) {
@@ -652,12 +693,17 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
       if ((rc = add_xfer_real<float>(xs, b->terr_y, &b->d_terr_y))) return rc;
     }
     CUDA_TRY(cudaMalloc((void**)&b->d_results, b->n_robots * sizeof(vsr_result)));
+    CUDA_TRY(cudaMalloc((void**)&b->d_bbox, b->n_robots * 4 * sizeof(double)));
     for (auto& k : b->buckets) {
       const size_t nr = k.robot_ids.size();
       if ((rc = add_xfer(xs, &k.shape, sizeof(ShapeDev), (void**)&k.d_shape))) return rc;
       if ((rc = add_xfer(xs, k.robot_ids.data(), nr * sizeof(int), (void**)&k.d_ids))) return rc;
       rc = f64 ? add_xfer_real<double>(xs, k.params, &k.d_params) : add_xfer_real<float>(xs, k.params, &k.d_params);
       if (rc) return rc;
+      if (!k.place_off.empty()) {
+        rc = f64 ? add_xfer_real<double>(xs, k.place_off, &k.d_place) : add_xfer_real<float>(xs, k.place_off, &k.d_place);
+        if (rc) return rc;
+      }
       size_t ring = (size_t)k.shape.ring_depth * (size_t)std::max(1, k.shape.n_channels) * nr * (size_t)k.shape.nvox;
       CUDA_TRY(cudaMalloc(&k.d_ring, ring * esz));
       if (k.traj_robots > 0) {
@@ -697,6 +743,8 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.n_robots = (long long)k.robot_ids.size();
   P.robot_ids = k.d_ids;
   P.params = (const real*)k.d_params;
+  P.final_bbox = b->d_bbox;
+  P.place_off = (const real*)k.d_place;
   P.results = b->d_results;
   P.ring = (real*)k.d_ring;
   P.trajectory = (real*)k.d_traj;
@@ -800,7 +848,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     P.pool_cap = (int)cap;
     smem += (size_t)cap * scopes * VSR_POOL_FIELDS * sizeof(real);
   }
-  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : 7;
+  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : (1 | 2 | 16 | 32 | 64 | 128);
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
 #define VSR_PICK(C)                                                                                  \
@@ -952,6 +1000,16 @@ extern "C" long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* ou
   // world frame
   for (size_t i = 0; i < n; i += 6) out[i] += b->origin_x;
   return (long long)n;
+}
+
+extern "C" int vsr_batch_final_bbox(vsr_batch* b, double* out, size_t n) {
+  if (!b || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->ran) return fail(VSR_ERR_STATE, "vsr_batch_final_bbox before vsr_batch_run");
+  if (n != b->n_robots) return fail(VSR_ERR_INVALID_ARGUMENT, "bounding box count differs from n_robots");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaMemcpyAsync(out, b->d_bbox, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, b->run_stream));
+  CUDA_TRY(cudaStreamSynchronize(b->run_stream));
+  return VSR_OK;
 }
 
 extern "C" long long vsr_batch_voxel_trace(vsr_batch* b, size_t robot, double* out, size_t capacity) {

@@ -81,7 +81,9 @@ struct Params {
   long long n_robots;
   const int* robot_ids;       // bucket index -> batch index
   const real* params;         // [n_robots][n_params] (bucket order)
+  const real* place_off;      // [n_robots][2] offset of the robot's placement from the shape's default, or null
   double* results;            // vsr_result records, batch order (11 doubles each)
+  double* final_bbox;         // [n_robots][4] Robot.boundingBox at the last tick (min x, min y, max x, max y), batch order
   real* ring;                 // [ring_depth][n_channels][n_robots * nvox]
   real* trajectory;           // [traj_robots][n_ticks][nvox*4][6], bucket order, or null
   long long traj_robots;
@@ -119,7 +121,8 @@ struct Params {
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
-  int sync_mode;         // bit0: barrier per tick, bit1: per velocity iteration (code locality only)
+  int sync_mode;         // lockstep barriers (code locality only): 1 per tick, 2 per velocity iteration, 8 inside it,
+                         // 16 after the spring init, 32 after the velocity loop, 64 after the position loop, 128 after detection
   long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
   int debug_tick, debug_tick_end;
 };
@@ -1134,8 +1137,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     real x[4], y[4], th[4], vx[4], vy[4], w[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      x[k] = active ? (real)S.init_x[v * 4 + k] : real(0);
-      y[k] = active ? (real)S.init_y[v * 4 + k] : real(k);
+      x[k] = active ? (real)S.init_x[v * 4 + k] + (P.place_off ? P.place_off[2 * rb] : real(0)) : real(0);
+      y[k] = active ? (real)S.init_y[v * 4 + k] + (P.place_off ? P.place_off[2 * rb + 1] : real(0)) : real(k);
       th[k] = vx[k] = vy[k] = w[k] = real(0);
     }
     // cos/sin of the 4 rotation angles, kept current across the tick (recomputed only where an
@@ -1191,8 +1194,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     SSYNC()
     for (int q = st; q < 66; q += sdim) lhd[q] = 0;  // no contacts yet
     SSYNC()
-    for (int tick = 0; tick < P.n_ticks; tick++) {
+    // tick -1 is detection only: a dyn4j World starts with updateRequired = true, i.e. the first step()
+    // begins with detect() -- contacts that exist at the placement (a robot developed next to a wall,
+    // DevoLocomotion.java) are solved from the first step on
+    for (int tick = -1; tick < P.n_ticks; tick++) {
       if (sync_mode & 1) __syncthreads();
+      if (tick >= 0) {
       // =========================== World.step(1) ===========================
       // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
 #pragma unroll
@@ -1270,7 +1277,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       VSR_SPRINGS(VSR_SPRING_INIT)
 #undef VSR_SPRING_INIT
 
-      if (sync_mode & 4) __syncthreads();
+      if (sync_mode & 16) __syncthreads();
       // ---- welds: WeldJoint.initializeConstraints + warm start.
       // Side s of this voxel: 0 left (own masses 0,3 are body1; partner masses 1,2 body2),
       // 1 right (own 1,2 are body2; partner 0,3 body1), 2 down (own 3,2 body1; partner 0,1
@@ -1428,7 +1435,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
         SSYNC()
       }
-      if (sync_mode & 4) __syncthreads();
+      if (sync_mode & 32) __syncthreads();
       // ---- integrate positions (integratePosition, dyn4j; translation/rotation caps)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -1552,7 +1559,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 
       r_sincos(th[0], &sn_[0], &cs_[0]);
       r_sincos(th[3], &sn_[3], &cs_[3]);
-      if (sync_mode & 4) __syncthreads();
+      }  // tick >= 0
+      if (sync_mode & 64) __syncthreads();
       // ---- World.detect: new manifolds for Touch and for the next step
       const unsigned old_cmask = cmask;
       cmask = 0;
@@ -1755,7 +1763,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       }
 
       // =========================== Robot.act(t) ===========================
-      if (sync_mode & 4) __syncthreads();
+      if (sync_mode & 128) __syncthreads();
+      if (tick < 0) continue;
       // ---- Voxel.act: energies; geometry shared by the sensors
       const real* s4 = sn_;
       const real* c4 = cs_;
@@ -2055,6 +2064,27 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           }
         }
         if (BLK) __syncthreads(); else __syncwarp();
+        if (tick == P.n_ticks - 1) {
+          // Robot.boundingBox (Robot.java:116-120) = the largest box of the voxels' outer corners
+          // (Voxel.java:481-495): what a later stage of a task is placed by (DevoLocomotion.java)
+          if (lane_ok) {
+            st[sidx * 4 + 0] = r_min(r_min(ox[0], ox[1]), r_min(ox[2], ox[3]));
+            st[sidx * 4 + 1] = r_min(r_min(oy[0], oy[1]), r_min(oy[2], oy[3]));
+            st[sidx * 4 + 2] = r_max(r_max(ox[0], ox[1]), r_max(ox[2], ox[3]));
+            st[sidx * 4 + 3] = r_max(r_max(oy[0], oy[1]), r_max(oy[2], oy[3]));
+          }
+          if (BLK) __syncthreads(); else __syncwarp();
+          if (active && v == 0) {
+            real bx0 = st[lane0 * 4 + 0], by0 = st[lane0 * 4 + 1], bx1 = st[lane0 * 4 + 2], by1 = st[lane0 * 4 + 3];
+            for (int q = 1; q < nvox; q++) {
+              bx0 = r_min(bx0, st[(lane0 + q) * 4 + 0]); by0 = r_min(by0, st[(lane0 + q) * 4 + 1]);
+              bx1 = r_max(bx1, st[(lane0 + q) * 4 + 2]); by1 = r_max(by1, st[(lane0 + q) * 4 + 3]);
+            }
+            double* B = P.final_bbox + (size_t)P.robot_ids[rb] * 4;
+            B[0] = (double)bx0 + P.origin_x; B[1] = (double)by0; B[2] = (double)bx1 + P.origin_x; B[3] = (double)by1;
+          }
+          if (BLK) __syncthreads(); else __syncwarp();
+        }
       }
     }
     // robot-wide OR of the per-voxel status bits into the record

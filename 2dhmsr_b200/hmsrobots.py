@@ -1007,10 +1007,11 @@ RESULT_DTYPE = np.dtype([
 assert RESULT_DTYPE.itemsize == C.sizeof(A.vsr_result)
 
 
-def tick_times(final_t: float, dt: float) -> np.ndarray:
+def tick_times(final_t: float, dt: float, t_start: float = 0.0) -> np.ndarray:
     """``t = 0; while (t < finalT) t = t + dT`` in double (Locomotion.java:195-203,
-    AbstractTask.java:48).  1200 ticks for finalT = 20, dt = 1/60."""
-    out, t = [], 0.0
+    AbstractTask.java:48).  1200 ticks for finalT = 20, dt = 1/60.  ``t_start``: the clock of a later
+    stage of a longer task (DevoLocomotion) keeps running."""
+    out, t = [], float(t_start)
     while t < final_t:
         t = t + dt
         out.append(t)
@@ -1053,6 +1054,8 @@ def compile_batch(
     settings: Settings,
     precision: int = A.VSR_PRECISION_F32,
     trajectory_robots: int = 0,
+    t_start: float = 0.0,
+    placements: Optional[Sequence[float]] = None,
 ) -> BatchDesc:
     """Flatten a list of Robots + one Locomotion task into a ``vsr_batch_desc``."""
     if len(robots) == 0:
@@ -1076,7 +1079,13 @@ def compile_batch(
     d.terrain_xs, d.terrain_ys, d.terrain_n = _np_ptr(xs, C.c_double), _np_ptr(ys, C.c_double), xs.size
     d.initial_placement = float(xs[1] + 1.0) if initial_placement is None else float(initial_placement)
     d.trajectory_robots = trajectory_robots
-    ticks = tick_times(final_t, d.settings.step_frequency)
+    d.t_start = float(t_start)
+    if placements is not None:
+        if len(placements) != len(robots):
+            raise ValueError("one placement per robot")
+        pl = b.keep(np.ascontiguousarray(placements, dtype=np.float64))
+        d.robot_placement = _np_ptr(pl, C.c_double)
+    ticks = tick_times(final_t, d.settings.step_frequency, t_start)
     b.n_ticks = len(ticks)
 
     # shape classes: (mask, per-voxel sensor encodings, hidden layers)
@@ -1234,6 +1243,13 @@ class DeviceBatch:
             _check(self.lib, int(got))
         return out
 
+    def final_bbox(self) -> np.ndarray:
+        """[robot][4] = Robot.boundingBox at the last tick: min x, min y, max x, max y (vsr_batch_final_bbox)."""
+        n = int(self.bd.desc.n_robots)
+        out = np.zeros((n, 4), dtype=np.float64)
+        _check(self.lib, self.lib.vsr_batch_final_bbox(self.h, _np_ptr(out, C.c_double), n))
+        return out
+
     def voxel_trace(self, robot: int) -> np.ndarray:
         """[tick][voxel][2] = touching the ground (0/1), applied force (vsr_batch_voxel_trace)."""
         nv = self.lib.vsr_batch_n_bodies(self.h, robot) // 4
@@ -1342,9 +1358,9 @@ class Locomotion:
         raise ValueError(f"Unknown terrain name: {name}")
 
     def compile(self, robots: Sequence[Robot], precision: int = A.VSR_PRECISION_F32,
-                trajectory_robots: int = 0) -> BatchDesc:
+                trajectory_robots: int = 0, t_start: float = 0.0, placements=None) -> BatchDesc:
         return compile_batch(robots, self.final_t, self.ground_profile, self.initial_placement, self.settings,
-                             precision, trajectory_robots)
+                             precision, trajectory_robots, t_start, placements)
 
     def apply(self, robots, listener=None, device: int = 0, precision: int = A.VSR_PRECISION_F32,
               observations: bool = False):

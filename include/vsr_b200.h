@@ -214,6 +214,11 @@ typedef struct vsr_batch_desc {
   /* optional per-tick body dump for the first `trajectory_robots` robots
      (SnapshotListener / Observation path, Locomotion.java:198-202) */
   size_t trajectory_robots;
+  /* stages of a longer task (DevoLocomotion.java): the episode's clock starts at t_start (ticks
+     t_start + dT, ... while t < final_t; 0 for a plain Locomotion) and every robot may have its
+     own initial placement (NULL: initial_placement for all)                                     */
+  double t_start;
+  const double* robot_placement; /* [n_robots] or NULL */
 } vsr_batch_desc;
 
 /* ---- Per-robot result: what Outcome needs from the first and the last
@@ -237,6 +242,7 @@ void vsr_default_material(vsr_material* out);
 /* Number of ticks `while (t < finalT) t += dt` runs (Java double accumulation,
    Locomotion.java:195-203) and the tick times themselves. */
 int vsr_tick_count(double final_t, double dt);
+int vsr_tick_count_from(double t_start, double final_t, double dt);
 
 /* Validate + compile the descriptor (host only; copies everything it needs).
    Replaces: robot.reset() + world assembly, Locomotion.java:172-191.          */
@@ -263,6 +269,11 @@ int vsr_batch_results_device(vsr_batch* b, void** dptr, size_t* bytes);
    world-insertion order (voxel order, then NW, NE, SE, SW).  Returns the number
    of doubles written, or <0.                                                   */
 long long vsr_batch_trajectory(vsr_batch* b, size_t robot, double* out, size_t capacity);
+
+/* Robot.boundingBox() (Robot.java:116-120) of every robot at the last tick: out[robot][4] = min x, min y,
+   max x, max y (world frame).  The next stage of a DevoLocomotion task places the developed robot at
+   this min x (DevoLocomotion.java: rebuildWorld).                                                   */
+int vsr_batch_final_bbox(vsr_batch* b, double* out, size_t n);
 
 /* What a VoxelPoly carries besides its geometry (Voxel.java:605-616), per tick, for robot r
    (< trajectory_robots): out[tick][voxel][2] = Touch.isTouchingGround (0/1),

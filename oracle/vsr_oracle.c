@@ -58,6 +58,16 @@ void vsr_oracle_default_opts(vsr_oracle_opts* o) {
 
 /* ------------------------------------------------------------------ ticks */
 /* Locomotion.java:195-203 + AbstractTask.java:48: t = 0; while (t < finalT) t = t + dT. */
+static int tick_times_from(double t_start, double final_t, double dt, double* t, int n) {
+  double tt = t_start;
+  int k = 0;
+  while (tt < final_t) {
+    tt = tt + dt;
+    if (t && k < n) t[k] = tt;
+    k++;
+  }
+  return k;
+}
 int vsr_oracle_tick_times(double final_t, double dt, double* t, int n) {
   double tt = 0.0;
   int k = 0;
@@ -393,7 +403,7 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
     if (x0 < minx) minx = x0;
     if (x3 < minx) minx = x3;
   }
-  double dx = d->initial_placement - minx;
+  double dx = (d->robot_placement ? d->robot_placement[ridx] : d->initial_placement) - minx;
   for (int b = 0; b < r->nb; b++) r->bodies[b].x += dx;
   double min_gap = INFINITY;
   for (v = 0; v < nv; v++) {
@@ -1715,9 +1725,9 @@ int vsr_oracle_run(const vsr_batch_desc* d, const vsr_oracle_opts* opts, vsr_res
   R.probe = probe;
   R.out = out;
   double dt = d->settings.step_frequency;
-  R.nticks = vsr_oracle_tick_times(d->final_t, dt, NULL, 0);
+  R.nticks = tick_times_from(d->t_start, d->final_t, dt, NULL, 0); /* a stage of a longer task starts its clock at t_start */
   R.ticks = (double*)malloc(sizeof(double) * (size_t)(R.nticks + 1));
-  vsr_oracle_tick_times(d->final_t, dt, R.ticks, R.nticks);
+  tick_times_from(d->t_start, d->final_t, dt, R.ticks, R.nticks);
   double miny = INFINITY;
   for (int i = 0; i < d->terrain_n; i++)
     if (d->terrain_ys[i] < miny) miny = d->terrain_ys[i];

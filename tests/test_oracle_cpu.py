@@ -287,3 +287,29 @@ def test_lidar_reads_the_distance_to_the_terrain():
     cx, cyy = c0[:, 0].mean(), c0[:, 1].mean()
     wall_x = 10.0 - (cyy - 5.0) * 10.0 / 95.0            # the wall at height cy
     assert p2["readings"][0][0, 0] == pytest.approx((cx - wall_x) / 10.0, rel=1e-6)
+
+
+def test_stage_clock_and_per_robot_placement():
+    # a stage of a longer task (DevoLocomotion.java): the clock starts at t_start, every robot has its own placement
+    robots = helpers.phase_robots(3, seed=8)
+    flat = helpers.locomotion(1.0)
+    a, pa = oracle.run(flat.compile(robots), trajectory=True)
+    b, pb = oracle.run(flat.compile(robots, placements=[11.0, 40.0, 300.5]), trajectory=True)
+    # on flat ground a robot placed elsewhere does the same thing there
+    assert np.allclose(pb["trajectory"][1][:, :, 0] - 29.0, pa["trajectory"][1][:, :, 0], atol=1e-9)
+    assert np.allclose(pb["trajectory"][2][:, :, 1:], pa["trajectory"][2][:, :, 1:], atol=1e-9)
+    assert b["first_center_x"] - a["first_center_x"] == pytest.approx([0.0, 29.0, 289.5], abs=1e-9)
+    # the clock: 1 Hz PhaseSin controllers repeat after a whole second
+    c, _ = oracle.run(helpers.locomotion(3.0).compile(robots, t_start=2.0))
+    assert c["n_ticks"].tolist() == [60] * 3 or c["n_ticks"].tolist() == [61] * 3
+    assert c["t_first"] == pytest.approx(2.0 + 1 / 60)
+    n = int(c["n_ticks"][0])
+    a2, _ = oracle.run(helpers.locomotion(n / 60 - 1e-9).compile(robots))
+    assert np.allclose(c["last_center_x"], a2["last_center_x"], atol=1e-6)
+    # on hills the placement decides the height
+    hilly = helpers.locomotion(0.2, terrain="hilly-1-10-0")
+    h, ph = oracle.run(hilly.compile(robots, placements=[30.0, 100.0, 555.0]), trajectory=True)
+    ys = [ph["trajectory"][i][0, :, 1].min() for i in range(3)]
+    assert len({round(y, 6) for y in ys}) == 3
+    with pytest.raises(ValueError):
+        flat.compile(robots, placements=[1.0])

@@ -344,3 +344,67 @@ def test_fp64_lidar_on_hilly_terrain():
     assert np.all(res["status"] == 0)
     assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
     assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+
+
+def test_fp64_stage_with_placements_and_clock():
+    """A stage of a longer task: t_start and per-robot placements (hilly terrain), and the final bounding box
+    the next stage is placed by."""
+    robots = helpers.phase_robots(4, seed=14)
+    loco = helpers.locomotion(4.5, terrain="hilly-1-10-0")
+    bd = loco.compile(robots, precision=F64, trajectory_robots=4, t_start=3.0, placements=[11.0, 57.3, 250.0, 1200.25])
+    with H.DeviceBatch(bd) as db:
+        db.upload(0).run()
+        res, box = db.results(), db.final_bbox()
+        tr = np.stack([db.trajectory(i) for i in range(4)])
+    ores, pr = oracle.run(bd, trajectory=True)
+    otr = pr["trajectory"]
+    assert np.all(res["status"] == 0) and np.all(res["n_ticks"] == ores["n_ticks"])
+    assert res["t_first"] == pytest.approx(3.0 + 1 / 60)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    last = otr[:, -1, :40]
+    c, s = np.cos(last[:, :, 2]), np.sin(last[:, :, 2])
+    k = np.arange(40) % 4
+    lx, ly = np.array([-1, 1, 1, -1])[k] * 0.525, np.array([1, 1, -1, -1])[k] * 0.525
+    cx, cy = last[:, :, 0] + c * lx - s * ly, last[:, :, 1] + s * lx + c * ly
+    assert box == pytest.approx(np.stack([cx.min(1), cy.min(1), cx.max(1), cy.max(1)], axis=1), abs=1e-7)
+
+
+def test_time_based_devo_locomotion_chains_stages():
+    """TimeBasedDevoLocomotion.java: the robot is re-developed at the scheduled times, placed where the old one
+    stood, the clock keeps running.  Against the oracle chained by hand."""
+    bodies = [helpers.body_of("biped-4x3"), helpers.body_of("worm-5x2"), helpers.body_of("biped-5x3")]
+
+    def solution(seed):
+        rng = np.random.default_rng(seed)
+
+        def develop(prev):
+            b = bodies[0] if prev is None else bodies[(bodies.index(prev.get_voxels()) + 1) % 3]
+            ph = rng.uniform(0, 2 * np.pi, size=(b.w, b.h))
+            return H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(b.w, b.h, lambda x, y: float(ph[x, y]))), b)
+        return develop
+
+    terrain = H.Locomotion.create_terrain("hilly-1-10-0")
+    task = H.TimeBasedDevoLocomotion.uniformly_distributed(3, 4.5, terrain, H.Settings())
+    outs = task.apply([solution(1), solution(2)], precision=F64)
+    assert [len(o.get_devo_outcomes()) for o in outs] == [3, 3]
+    assert [r.get_voxels().w for r in outs[0].get_robots()] == [4, 5, 5]
+    # the same chain through the oracle
+    for si, seed in enumerate((1, 2)):
+        dev, robot, place, t = solution(seed), None, 11.0, 0.0
+        for stage, t_end in enumerate(task.development_schedule[:2] + [4.5]):
+            robot = dev(robot)
+            bd = H.compile_batch([robot], t_end, terrain, None, H.Settings(), F64, 1, t, [place])
+            ores, pr = oracle.run(bd, trajectory=True)
+            got = outs[si].get_devo_outcomes()[stage]
+            assert got.distance == pytest.approx(float(ores[0]["last_center_x"] - ores[0]["first_center_x"]), abs=1e-6)
+            assert got.time == pytest.approx(float(ores[0]["t_last"] - ores[0]["t_first"]), abs=1e-12)
+            last = pr["trajectory"][0][-1, :4 * bd.n_voxels[0]]
+            kk = np.arange(last.shape[0]) % 4
+            cxs = last[:, 0] + np.cos(last[:, 2]) * (np.array([-1, 1, 1, -1])[kk] * 0.525) - np.sin(last[:, 2]) * (np.array([1, 1, -1, -1])[kk] * 0.525)
+            place, t = float(cxs.min()), float(ores[0]["t_last"])
+    # distance-based development: stages end when the robot has advanced enough
+    dtask = H.DistanceBasedDevoLocomotion(1.0, 3.0, 6.0, H.Locomotion.create_terrain("flat"), H.Settings())
+    dout = dtask.apply(solution(5), precision=F64)
+    stages = dout.get_devo_outcomes()
+    assert len(stages) >= 1 and sum(dout.get_times()) <= 6.0 + 1e-9
+    assert all(s.outcome.get_observations() for s in stages)
