@@ -38,7 +38,8 @@ def test_device_present_and_native_library_loaded():
     assert "libvsr_b200.so" in maps  # the in-tree CUDA library, not a fallback
 
 
-@pytest.mark.parametrize("shape,n", [("biped-4x3", 6), ("worm-8x2", 4), ("box-1x1", 3), ("box-3x3", 3), ("biped-6x4", 2)])
+@pytest.mark.parametrize("shape,n", [("biped-4x3", 6), ("worm-8x2", 4), ("box-1x1", 3), ("box-3x3", 3), ("biped-6x4", 2),
+                                     ("box-8x4", 2)])   # 32 voxels: exactly one warp
 def test_fp64_kernel_matches_oracle_bodies(shape, n):
     bd, res, tr, ores, otr = _both(helpers.locomotion(5.0), helpers.phase_robots(n, shape=shape, seed=3), F64)
     nb = 4 * bd.n_voxels[0]
@@ -52,15 +53,15 @@ def test_fp64_kernel_matches_oracle_bodies(shape, n):
 
 
 @pytest.mark.parametrize("shape,terrain,sensors", [("box-10x10", "flat", "uniform-ax+t-0"), ("biped-9x5", "hilly-1-10-0", "uniform-t+vxy+a-0"),
-                                                   ("worm-11x3", "flat", "uniform-a-0"), ("box-6x6", "steppy-1-6-2", "uniform-t-0")])
+                                                   ("worm-11x3", "flat", "uniform-a-0"), ("box-6x6", "steppy-1-6-2", "uniform-t-0"),
+                                                   ("box-16x8", "flat", "uniform-a-0")])   # 128 voxels: the largest
 def test_fp64_big_robots_one_block_per_robot(shape, terrain, sensors):
     """33..128 voxels (BASELINE config 4 goes up to 10x10): the one-block-per-robot variant."""
     robots = helpers.phase_robots(3, shape=shape, sensors=sensors, seed=17)
     bd, res, tr, ores, otr = _both(helpers.locomotion(3.0, terrain=terrain), robots, F64)
     nb = 4 * bd.n_voxels[0]
-    assert nb > 128 and np.all((res["status"] & 1) == 0)
+    assert nb > 128 and np.all(res["status"] == 0)
     ok = res["status"] == 0
-    assert ok.sum() >= 2
     assert np.abs(tr[ok][:, :, :nb, :3] - otr[ok][:, :, :nb, :3]).max() < 1e-7
     assert np.allclose(res["last_center_x"][ok], ores["last_center_x"][ok], atol=1e-6)
     assert np.allclose(res["area_ratio_energy_last"][ok], ores["area_ratio_energy_last"][ok], rtol=1e-9)
