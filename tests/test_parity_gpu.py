@@ -409,3 +409,20 @@ def test_time_based_devo_locomotion_chains_stages():
     stages = dout.get_devo_outcomes()
     assert len(stages) >= 1 and sum(dout.get_times()) <= 6.0 + 1e-9
     assert all(s.outcome.get_observations() for s in stages)
+
+
+def test_fp32_closed_loop_controllers_short_horizon():
+    """The product precision with sensing in the loop (DistributedSensing on a noisy spinedTouchSighted layout,
+    hills): rounding-level agreement with the fp64 oracle before the first ground contact, and a bounded
+    difference over 1 s (contact on/off and the corner-neighbour contacts are discrete events)."""
+    robots = helpers.distributed_robots(6, sensors="spinedTouchSighted-t-t-0.01", signals=1, hidden=(3,), seed=41)
+    loco = helpers.locomotion(1.0, terrain="hilly-1-10-0")
+    bd = loco.compile(robots, trajectory_robots=6)
+    res, tr = helpers.gpu_run(bd, trajectories=6)
+    ores, pr = oracle.run(bd, trajectory=True, n_threads=8)
+    otr = pr["trajectory"][:, :, :40]
+    assert np.all(res["status"] == 0)
+    early = np.abs(tr[:, :10, :, :2] - otr[:, :10, :, :2]).max(axis=(1, 2, 3))
+    assert np.percentile(early, 25) < 2e-5 and early.max() < 2e-2, early
+    assert np.abs(tr[..., :2] - otr[..., :2]).max() < 0.3
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=0.2)
