@@ -280,7 +280,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   // mm != 0: the second polygon is another mass, given as (x0, y0, x1, y1) = (centre, cos, sin);
   // neighbouring masses touch corner to corner at rest, so there every comparison carries the
   // margin and a contact needs a penetration above it (see the oracle's sat_penetration).
-  const real tie_eps = sizeof(real) == 8 ? real(1e-12) : real(1e-6);
+  const real tie_eps = sizeof(real) == 8 ? real(1e-12) : real(VSR_TIE_EPS_F32);
   const real in_eps = mm ? tie_eps : real(0);
   Poly4<real> A, B;
   const real lx[4] = {-1, 1, 1, -1}, ly[4] = {-1, -1, 1, 1};
@@ -1022,6 +1022,9 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #define VSR_MAX_THREADS 384
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
+#ifndef VSR_TIE_EPS_F32
+#define VSR_TIE_EPS_F32 1e-6f
+#endif
 #define VSR_MAX_LEVELS 32
 #define VSR_ITEMS_PER_THREAD 16
 static_assert(4 * MAXC + SC_CAP <= VSR_ITEMS_PER_THREAD, "contact list capacity");
