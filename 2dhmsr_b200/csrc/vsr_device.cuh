@@ -31,6 +31,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// margin of the geometric tie rules in the fp32 build (1e-12 in fp64), see collide_mass_segment
+#ifndef VSR_TIE_EPS_F32
+#define VSR_TIE_EPS_F32 1e-6f
+#endif
+
 namespace vsr {
 
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
@@ -1022,9 +1027,6 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #define VSR_MAX_THREADS 384
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
-#ifndef VSR_TIE_EPS_F32
-#define VSR_TIE_EPS_F32 1e-6f
-#endif
 #define VSR_MAX_LEVELS 32
 #define VSR_ITEMS_PER_THREAD 16
 static_assert(4 * MAXC + SC_CAP <= VSR_ITEMS_PER_THREAD, "contact list capacity");
