@@ -8,17 +8,22 @@
  *   Voxel.assemble/act/applyForce/getters  core/objects/Voxel.java:197-203,224-237,239-479,508-556
  *   Robot.assemble/act          core/objects/Robot.java:66-114
  *   Ground / yAt                core/objects/Ground.java:43-82,104-111
- *   sensors                     core/sensors/{Touch,AreaRatio,Velocity,AggregatorSensor,Average,
- *                                             Trend,SoftNormalization}.java
+ *   sensors                     core/sensors/{Touch,AreaRatio,Velocity,Angle,Constant,AppliedForce,
+ *                                             Malfunction,Crumpling,ControlPower,TimeFunction,Lidar,
+ *                                             AggregatorSensor,Average,Trend,SoftNormalization,
+ *                                             Normalization,Noisy}.java
  *   controllers                 core/controllers/{PhaseSin,TimeFunctions,CentralizedSensing,
+ *                                                 DistributedSensing[NonDirectional],
  *                                                 MultiLayerPerceptron}.java
  *   Outcome                     tasks/locomotion/Outcome.java:42-58,126-142,152-200
  *
  * and, for World.step(1), the published algorithm of org.dyn4j:dyn4j:4.2.1
  * (pom.xml:31-35; Box2D lineage; NOT in /root/reference, NOT runnable here):
  * semi-implicit Euler, soft DistanceJoint, rigid WeldJoint, SAT/clipping manifolds,
- * sequential impulses with a 2-point block solver, Baumgarte position pass.
- * PARITY UNPINNED for that part (no golden vector exists anywhere in the reference).
+ * sequential impulses with a 2-point block solver, Baumgarte position pass; contacts of a mass with
+ * the ground and with the other masses of its robot (Voxel.java:178-185,474).
+ * PARITY UNPINNED for that part: the one physics vector the reference ships (assets/frames.png, the
+ * robot centre at 5 ticks of Example.main) is not reproduced (tests/test_oracle_cpu.py, xfail).
  *
  * Each numbered dyn4j item of SURVEY.md Appendix C sits behind one function so it
  * can be corrected if a dyn4j 4.2.1 run ever becomes available.
