@@ -170,6 +170,9 @@ struct vsr_batch {
   double* d_ticks = nullptr;
   int16_t* d_win = nullptr;
   void* d_terr_x = nullptr;
+  std::vector<double> hgrid;  // coarse height map of the terrain (see Params::hgrid)
+  void* d_hgrid = nullptr;
+  double hgrid_x0 = 0, hgrid_cw = 4.0;
   void* d_terr_y = nullptr;
   double* d_results = nullptr;
   double* d_bbox = nullptr;  // Robot.boundingBox at the last tick, [n_robots][4]
@@ -685,6 +688,21 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
       }
       if ((rc = add_xfer(xs, b->noise.data(), b->noise.size() * sizeof(double), (void**)&b->d_noise))) return rc;
     }
+    {
+      // the highest point of the profile over each cell (closed ranges: a shared end point counts on both sides)
+      const size_t tn = b->terr_x.size();
+      b->hgrid_x0 = b->terr_x.front();
+      const int nc = std::max(1, (int)std::ceil((b->terr_x.back() - b->hgrid_x0) / b->hgrid_cw));
+      b->hgrid.assign((size_t)nc, -INFINITY);
+      for (size_t i = 0; i + 1 < tn; i++) {
+        const double x0 = b->terr_x[i], x1 = b->terr_x[i + 1], y0 = b->terr_y[i], y1 = b->terr_y[i + 1];
+        const int c0 = std::max(0, std::min(nc - 1, (int)std::floor((x0 - b->hgrid_x0) / b->hgrid_cw)));
+        const int c1 = std::max(0, std::min(nc - 1, (int)std::floor((x1 - b->hgrid_x0) / b->hgrid_cw)));
+        for (int c = c0; c <= c1; c++) b->hgrid[(size_t)c] = std::max(b->hgrid[(size_t)c], std::max(y0, y1));
+      }
+      rc = f64 ? add_xfer_real<double>(xs, b->hgrid, &b->d_hgrid) : add_xfer_real<float>(xs, b->hgrid, &b->d_hgrid);
+      if (rc) return rc;
+    }
     if (f64) {
       if ((rc = add_xfer_real<double>(xs, b->terr_x, &b->d_terr_x))) return rc;
       if ((rc = add_xfer_real<double>(xs, b->terr_y, &b->d_terr_y))) return rc;
@@ -757,6 +775,10 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.terr_x = (const real*)b->d_terr_x;
   P.terr_y = (const real*)b->d_terr_y;
   P.terr_n = (int)b->terr_x.size();
+  P.hgrid = (const real*)b->d_hgrid;
+  P.hgrid_n = (int)b->hgrid.size();
+  P.hgrid_x0 = (real)b->hgrid_x0;
+  P.hgrid_inv = (real)(1.0 / b->hgrid_cw);
   P.base_y = (real)b->base_y;
   P.origin_x = b->origin_x;
   P.dt = (real)st.step_frequency;

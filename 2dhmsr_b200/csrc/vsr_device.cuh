@@ -102,6 +102,11 @@ struct Params {
   const real* terr_x;
   const real* terr_y;
   int terr_n;
+  // coarse height map of the terrain: the highest point of the profile over each cell of width 1 / hgrid_inv
+  // (local frame, from hgrid_x0): a mass wholly above it cannot touch the ground
+  const real* hgrid;
+  int hgrid_n;
+  real hgrid_x0, hgrid_inv;
   real base_y;
   double origin_x;
   // settings / material
@@ -1570,7 +1575,72 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       const unsigned old_cmask = cmask;
       cmask = 0;
       unsigned gcn = 0;  // ground constraints per mass, 4 bits each
-      if (active) {
+      if (!BLK && cap >= 16) {
+        // Only a few masses of a warp are near the ground.  Those (by the coarse height map; a mass that
+        // had contacts always) are listed for the whole warp and detected one per lane, writing straight
+        // into their owners' records; the pool -- idle during detection -- is the scratch space.
+        int* const scr = reinterpret_cast<int*>(pool);  // [32][5] hints + flags, [128] list, [32][4] results
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          mt[VSR_MTK(k, 0)] = x[k]; mt[VSR_MTK(k, 1)] = y[k]; mt[VSR_MTK(k, 2)] = cs_[k]; mt[VSR_MTK(k, 3)] = sn_[k];
+          scr[lane * 5 + k] = hint[k];
+        }
+        scr[lane * 5 + 4] = (int)((flip & 15u) | (old_cmask << 4));
+        unsigned cand = 0;
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const real e = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
+            int c0 = (int)floorf((float)((x[k] - e - P.hgrid_x0) * P.hgrid_inv)), c1 = (int)floorf((float)((x[k] + e - P.hgrid_x0) * P.hgrid_inv));
+            c0 = max(0, min(c0, P.hgrid_n - 1));
+            c1 = max(0, min(c1, P.hgrid_n - 1));
+            real hm = P.hgrid[c0];
+            for (int c = c0 + 1; c <= c1; c++) hm = r_max(hm, P.hgrid[c]);
+            if (((old_cmask >> k) & 1u) || !(y[k] - e > hm)) cand |= 1u << k;
+          }
+        }
+        const int ncand = __popc(cand);
+        int incl = ncand;
+#pragma unroll
+        for (int d2 = 1; d2 < 32; d2 <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d2);
+          if (lane >= d2) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        {
+          int pos = incl - ncand;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (cand & (1u << k)) scr[160 + pos++] = (lane << 2) | k;
+        }
+        __syncwarp();
+        for (int i = lane; i < total; i += 32) {
+          const int code = scr[160 + i];
+          const int ol = code >> 2, k = code & 3;
+          const int fl = scr[ol * 5 + 4];
+          int h = scr[ol * 5 + k];
+          const int fb = (fl >> k) & 1, had = (fl >> (4 + k)) & 1;
+          const int tl = (wib << 5) + ol;
+          CBody<real>* const ob = blk_cb + (size_t)tl * 8;
+          int cn = 0;
+          const int ov = detect_mass(tpar, mt[VSR_MTI(k, 0, tl)], mt[VSR_MTI(k, 1, tl)], mt[VSR_MTI(k, 2, tl)], mt[VSR_MTI(k, 3, tl)],
+                                     h, ob[2 * k + fb], had, ob[2 * k + (fb ^ 1)], cn, im, ii, k);
+          scr[288 + ol * 4 + k] = cn | (ov << 4) | (h << 8);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (cand & (1u << k)) {
+            const int r = scr[288 + lane * 4 + k];
+            hint[k] = r >> 8;
+            flip ^= 1u << k;
+            if (r & 16) status |= STATUS_CONTACT_OVERFLOW;
+            const int cn = r & 15;
+            if (cn > 0) cmask |= 1u << k;
+            gcn |= (unsigned)cn << (4 * k);
+          }
+        __syncwarp();
+      } else if (active) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           // cheap reject: far above the highest point of the terrain near this mass
