@@ -8,6 +8,8 @@
 // Locomotion::apply flattens the robots into a vsr_batch_desc and calls libvsr_b200.so.
 #pragma once
 
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -724,9 +726,106 @@ class Settings {  // org.dyn4j.dynamics.Settings as a value holder (Locomotion.j
   vsr_settings s_;
 };
 
-class Outcome {  // tasks/locomotion/Outcome.java (first + last Observation)
+// ---------------------------------------------------------------- per-tick view (Observation path)
+struct Point2 {
+  double x, y;
+};
+struct BoundingBox {  // util/BoundingBox.java
+  Point2 min, max;
+};
+class VoxelPoly {  // core/snapshots/VoxelPoly.java: the 4 outer vertexes of a voxel and its scalar state
+ public:
+  VoxelPoly(std::array<Point2, 4> v, double angle, Point2 vel, bool touching, double areaRatio, double areaRatioEnergy,
+            double lastAppliedForce, double controlEnergy)
+      : v_(v), angle_(angle), vel_(vel), touching_(touching), areaRatio_(areaRatio), areaRatioEnergy_(areaRatioEnergy),
+        lastAppliedForce_(lastAppliedForce), controlEnergy_(controlEnergy) {}
+  const std::array<Point2, 4>& vertexes() const { return v_; }
+  BoundingBox boundingBox() const {  // Poly.java:51-64
+    BoundingBox b{{v_[0].x, v_[0].y}, {v_[0].x, v_[0].y}};
+    for (auto& p : v_) {
+      b.min.x = std::min(b.min.x, p.x); b.min.y = std::min(b.min.y, p.y);
+      b.max.x = std::max(b.max.x, p.x); b.max.y = std::max(b.max.y, p.y);
+    }
+    return b;
+  }
+  double area() const {  // Poly.java:40-49
+    double a = 0;
+    for (int i = 0; i < 4; i++) a = a + v_[i].x * (v_[(4 + i + 1) % 4].y - v_[(4 + i - 1) % 4].y);
+    return 0.5 * std::fabs(a);
+  }
+  Point2 center() const { return {(v_[0].x + v_[1].x + v_[2].x + v_[3].x) / 4.0, (v_[0].y + v_[1].y + v_[2].y + v_[3].y) / 4.0}; }
+  double getAngle() const { return angle_; }
+  Point2 getLinearVelocity() const { return vel_; }
+  bool isTouchingGround() const { return touching_; }
+  double getAreaRatio() const { return areaRatio_; }
+  double getAreaRatioEnergy() const { return areaRatioEnergy_; }
+  double getLastAppliedForce() const { return lastAppliedForce_; }
+  double getControlEnergy() const { return controlEnergy_; }
+
+ private:
+  std::array<Point2, 4> v_;
+  double angle_;
+  Point2 vel_;
+  bool touching_;
+  double areaRatio_, areaRatioEnergy_, lastAppliedForce_, controlEnergy_;
+};
+struct Observation {  // Outcome.java:38-39
+  Grid<VoxelPoly> voxelPolies;
+  double terrainHeight, computationTime;
+};
+namespace BehaviorUtils {  // behavior/BehaviorUtils.java (the geometric part)
+inline Point2 center(const std::vector<VoxelPoly>& shapes) {  // :47-56
+  double x = 0, y = 0;
+  for (auto& s : shapes) {
+    Point2 c = s.center();
+    x = x + c.x;
+    y = y + c.y;
+  }
+  return {x / double(shapes.size()), y / double(shapes.size())};
+}
+inline std::vector<bool> computeFootprint(const std::vector<VoxelPoly>& polies, int n) {  // :68-91
+  if (polies.empty()) throw std::invalid_argument("Empty robot");
+  double mn = INFINITY, mx = -INFINITY;
+  for (auto& p : polies) {
+    mn = std::min(mn, p.boundingBox().min.x);
+    mx = std::max(mx, p.boundingBox().max.x);
+  }
+  std::vector<bool> mask(size_t(n), false);
+  for (auto& p : polies) {
+    if (!p.isTouchingGround()) continue;
+    int lo = int(std::floor((p.boundingBox().min.x - mn) / (mx - mn) * double(n - 1) + 0.5));
+    int hi = int(std::floor((p.boundingBox().max.x - mn) / (mx - mn) * double(n - 1) + 0.5));
+    for (int x = lo; x <= std::min(hi, n - 1); x++) mask[size_t(x)] = true;
+  }
+  return mask;
+}
+}  // namespace BehaviorUtils
+
+class Outcome {  // tasks/locomotion/Outcome.java: the record of the first + last Observation, optionally all of them
  public:
   explicit Outcome(const vsr_result& r) : r_(r) {}
+  Outcome(const vsr_result& r, std::map<double, Observation> obs) : r_(r), observations_(std::move(obs)) {}
+  // the per-tick part (needs Locomotion::apply(robots, true))
+  const std::map<double, Observation>& getObservations() const {  // :190-192
+    if (observations_.empty()) throw Unsupported("this Outcome holds the first/last observation only");
+    return observations_;
+  }
+  static std::vector<VoxelPoly> polies(const Observation& o) {
+    std::vector<VoxelPoly> out;
+    for (auto& v : o.voxelPolies.values())
+      if (v) out.push_back(*v);
+    return out;
+  }
+  double getDistanceFromObservations() const {  // :152-166 on the map
+    auto& m = getObservations();
+    return BehaviorUtils::center(polies(m.rbegin()->second)).x - BehaviorUtils::center(polies(m.begin()->second)).x;
+  }
+  Outcome subOutcome(double startT, double endT) const {  // :202-204: subMap(startT, endT)
+    std::map<double, Observation> sub;
+    for (auto& kv : getObservations())
+      if (kv.first >= startT && kv.first < endT) sub.emplace(kv.first, kv.second);
+    return Outcome(r_, std::move(sub));
+  }
   double getDistance() const { return r_.last_center_x - r_.first_center_x; }          // :152-166
   double getTime() const { return r_.t_last - r_.t_first; }                              // :194-196
   double getVelocity() const { return getDistance() / getTime(); }                       // :198-200
@@ -739,6 +838,7 @@ class Outcome {  // tasks/locomotion/Outcome.java (first + last Observation)
 
  private:
   vsr_result r_;
+  std::map<double, Observation> observations_;
 };
 
 // ---------------------------------------------------------------- flattening
@@ -945,6 +1045,80 @@ class Locomotion {  // tasks/locomotion/Locomotion.java
     return out;
   }
   Outcome apply(const Robot& robot, int device = 0) const { return apply(std::vector<Robot>{robot}, device)[0]; }  // :168-207
+
+  // ... with the observations map of Locomotion.java:193-203 built from the device's per-tick dumps
+  // (vsr_batch_trajectory + vsr_batch_voxel_trace); the scalar getters follow Voxel.java:508-556
+  std::vector<Outcome> applyWithObservations(const std::vector<Robot>& robots, int device = 0) const {
+    auto bd = compile(robots, VSR_PRECISION_F32, robots.size());
+    vsr_batch* h = nullptr;
+    check(vsr_batch_create(&bd->desc, &h));
+    struct Guard {
+      vsr_batch* h;
+      ~Guard() { vsr_batch_destroy(h); }
+    } guard{h};
+    check(vsr_batch_upload(h, device, nullptr));
+    check(vsr_batch_run(h, nullptr));
+    std::vector<vsr_result> res(robots.size());
+    check(vsr_batch_results(h, res.data(), res.size()));
+    const std::vector<double> tt = tickTimes(finalT_, settings_.getStepFrequency());
+    const size_t nt = tt.size();
+    std::vector<Outcome> out;
+    for (size_t r = 0; r < robots.size(); r++) {
+      const Grid<Voxel>& vox = robots[r].getVoxels();
+      const size_t nv = vox.count();
+      std::vector<double> traj(nt * nv * 4 * 6), trace(nt * nv * 2);
+      if (vsr_batch_trajectory(h, r, traj.data(), traj.size()) < 0 || vsr_batch_voxel_trace(h, r, trace.data(), trace.size()) < 0)
+        throw std::runtime_error(vsr_last_error());
+      const vsr_material& m = vox.values()[size_t(std::find_if(vox.values().begin(), vox.values().end(), [](auto& v) { return bool(v); }) - vox.values().begin())]->material();
+      const double hh = m.side_length * m.mass_side_length_ratio / 2.0;
+      static const double lx[4] = {-1, 1, 1, -1}, ly[4] = {1, 1, -1, -1};
+      std::vector<double> are(nv, 0.0), ce(nv, 0.0), prevF(nv, 0.0);
+      std::map<double, Observation> obs;
+      for (size_t k = 0; k < nt; k++) {
+        double cxs = 0;
+        size_t j = 0;
+        Grid<VoxelPoly> polies = Grid<VoxelPoly>::create(vox.getW(), vox.getH(), [&](int x, int y) -> std::optional<VoxelPoly> {
+          (void)x; (void)y;
+          return std::nullopt;
+        });
+        for (int y = 0; y < vox.getH(); y++)
+          for (int x = 0; x < vox.getW(); x++) {
+            if (!vox.get(x, y)) continue;
+            const double* b = &traj[((k * nv + j) * 4) * 6];
+            std::array<Point2, 4> vs;
+            double mvx = 0, mvy = 0, bcx = 0;
+            for (int q = 0; q < 4; q++) {
+              const double c = std::cos(b[6 * q + 2]), s2 = std::sin(b[6 * q + 2]);
+              vs[size_t(q)] = {b[6 * q] + c * lx[q] * hh - s2 * ly[q] * hh, b[6 * q + 1] + s2 * lx[q] * hh + c * ly[q] * hh};
+              mvx = mvx + b[6 * q + 3];
+              mvy = mvy + b[6 * q + 4];
+              bcx += b[6 * q];
+            }
+            cxs += bcx / 4.0;
+            double area = 0;
+            for (int i = 0; i < 4; i++) area = area + vs[size_t(i)].x * (vs[size_t((i + 1) % 4)].y - vs[size_t((i + 3) % 4)].y);
+            const double ratio = 0.5 * std::fabs(area) / m.side_length / m.side_length;
+            const double ang = (std::atan2(b[6 + 1] - b[1], b[6] - b[0]) + std::atan2(b[12 + 1] - b[18 + 1], b[12] - b[18])) / 2.0;
+            are[j] += ratio * ratio;               // Voxel.act (Voxel.java:197-203) runs before the controller:
+            ce[j] += prevF[j] * prevF[j];          // the energy of tick k holds the force applied at tick k - 1
+            const double f = trace[(k * nv + j) * 2 + 1];
+            polies.set(x, y, VoxelPoly(vs, ang, {mvx / 4.0, mvy / 4.0}, trace[(k * nv + j) * 2] != 0.0, ratio, are[j], f, ce[j]));
+            prevF[j] = f;
+            j++;
+          }
+        obs.emplace(tt[k], Observation{polies, groundYAt(cxs / double(nv)), 0.0});
+      }
+      out.emplace_back(res[r], std::move(obs));
+    }
+    return out;
+  }
+  double groundYAt(double x) const {  // Ground.yAt (Ground.java:104-111)
+    for (size_t i = 1; i < profile_.first.size(); i++)
+      if (profile_.first[i - 1] <= x && x <= profile_.first[i])
+        return (x - profile_.first[i - 1]) * (profile_.second[i] - profile_.second[i - 1]) / (profile_.first[i] - profile_.first[i - 1]) +
+               profile_.second[i - 1];
+    return std::nan("");
+  }
 
  private:
   static void check(int rc) {

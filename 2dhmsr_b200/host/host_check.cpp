@@ -156,7 +156,20 @@ int main(int argc, char** argv) {
     Locomotion loco5(5, Locomotion::createTerrain("flat"), Settings());
     auto d1 = loco5.apply({distributedRobot(7, true), distributedRobot(8, true)});
     auto d2 = loco5.apply(std::vector<Robot>{distributedRobot(7, false)});
-    std::cout << "],\n  \"distributed_distance\": [" << d1[0].getDistance() << ", " << d1[1].getDistance() << ", " << d2[0].getDistance()
+    // the per-tick Observation map of a 2 s episode
+    Locomotion loco2(2, Locomotion::createTerrain("flat"), Settings());
+    auto ob = loco2.applyWithObservations({phaseRobot(0.1)})[0];
+    int touches = 0;
+    for (auto& kv : ob.getObservations())
+      for (auto& p : Outcome::polies(kv.second)) touches += p.isTouchingGround() ? 1 : 0;
+    auto& lastObs = ob.getObservations().rbegin()->second;
+    auto fp = BehaviorUtils::computeFootprint(Outcome::polies(lastObs), 4);
+    std::cout << "],\n  \"obs\": {\"n\": " << ob.getObservations().size() << ", \"distance\": " << ob.getDistanceFromObservations()
+              << ", \"record_distance\": " << ob.getDistance() << ", \"touches\": " << touches
+              << ", \"last_control_energy\": " << Outcome::polies(lastObs)[0].getControlEnergy()
+              << ", \"terrain_height\": " << lastObs.terrainHeight << ", \"footprint\": \"" << (fp[0] ? '_' : '.') << (fp[1] ? '_' : '.')
+              << (fp[2] ? '_' : '.') << (fp[3] ? '_' : '.') << "\", \"sub\": " << ob.subOutcome(0.5, 1.0).getObservations().size() << "}";
+    std::cout << ",\n  \"distributed_distance\": [" << d1[0].getDistance() << ", " << d1[1].getDistance() << ", " << d2[0].getDistance()
               << "] }\n";
     return 0;
   }

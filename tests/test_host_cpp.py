@@ -108,3 +108,16 @@ def test_cpp_locomotion_apply_equals_python_path():
     want = [o.get_distance() for o in l5.apply([dist_robot(7, True), dist_robot(8, True)])] + \
            [l5.apply(dist_robot(7, False)).get_distance()]
     assert j["distributed_distance"] == want
+    # the per-tick Observation map through the C++ mirror against the Python one
+    o = helpers.locomotion(2.0).apply(robots[0], observations=True)
+    obs = o.get_observations()
+    polies = lambda ob: [v for v in ob.voxel_polies.values() if v is not None]
+    last = list(obs.values())[-1]
+    assert j["obs"]["n"] == len(obs) == 121
+    assert j["obs"]["distance"] == pytest.approx(o.get_distance(), abs=1e-9)
+    assert j["obs"]["record_distance"] == pytest.approx(j["obs"]["distance"], abs=1e-4)   # fp32 record vs double host sum
+    assert j["obs"]["touches"] == sum(p.is_touching_ground() for ob in obs.values() for p in polies(ob))
+    assert j["obs"]["last_control_energy"] == pytest.approx(polies(last)[0].get_control_energy(), rel=1e-12)
+    assert j["obs"]["terrain_height"] == last.terrain_height == 5.0
+    assert j["obs"]["footprint"] == repr(H.BehaviorUtils.compute_footprint(polies(last), 4))
+    assert j["obs"]["sub"] == len(o.sub_outcome(0.5, 1.0).get_observations())
