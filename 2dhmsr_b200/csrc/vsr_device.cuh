@@ -451,7 +451,10 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     if (x1 < xlo) continue;
     if (!(x1 > x0)) continue;
     if (ylo > r_max(y0, y1)) continue;
-    SCon<real> c;
+    // the record is built in place (the arena), not in thread-local memory; a scratch copy only takes the
+    // manifold that would not fit
+    SCon<real> scratch;
+    SCon<real>& c = cn < MAXC ? cb.c[cn] : scratch;
     if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, 0, c)) continue;
     if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
@@ -503,7 +506,7 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
         }
       }
     }
-    cb.c[cn++] = c;
+    cn++;
   }
   if (cn > 0 || had_contact) cb.n = cn;
   n_out = cn;
@@ -819,16 +822,14 @@ template <typename real>
 __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, real ay, real ac, real as, real bx,
                                       real by, real bc, real bs, int ka, int tb, int kb, const SCon<real>* old,
                                       int old_n, SCon<real>* out) {
-  SCon<real> m;
-  if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, m)) return 0;
-  SCon<real> c;
-  c.ka = ka; c.tb = tb; c.kb = kb; c.n = m.n; c.block = 0; c.seg = -1;
-  c.nx = m.nx; c.ny = m.ny;
+  // the record is built in place (the owner's list in the arena)
+  SCon<real>& c = *out;
+  if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, c)) return 0;
+  c.ka = ka; c.tb = tb; c.kb = kb; c.block = 0; c.seg = -1;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    c.p[k].px = m.p[k].px; c.p[k].py = m.p[k].py; c.p[k].depth = m.p[k].depth;
-    c.p[k].id = m.p[k].id;
-    c.p[k].jn = real(0); c.p[k].jt = real(0); c.p[k].vb = real(0);
+    if (k >= c.n) { c.p[k].jn = real(0); c.p[k].jt = real(0); }
+    c.p[k].vb = real(0);
   }
   for (int i = 0; i < old_n; i++) {
     const SCon<real>& o = old[i];
@@ -875,7 +876,6 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
       c.n = 1;
     }
   }
-  *out = c;
   return 1;
 }
 
