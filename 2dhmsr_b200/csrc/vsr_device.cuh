@@ -1799,7 +1799,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 
       // ---- the scope's constraint list for the next step, by dependency level: the q-th ground
       //      constraint of a mass has level q, the intra-robot ones follow (levels above)
-      {
+      if (!BLK && !__any_sync(0xffffffffu, gcn != 0u || n_new != 0)) {
+        if (lane == 0) lhd[1] = 0;  // nothing touches anything in this warp
+        __syncwarp();
+      } else {
         SSYNC()
         for (int q = st; q < 66; q += sdim) lhd[q] = 0;
         SSYNC()
@@ -1812,7 +1815,20 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         for (int li = 0; li < SC_CAP; li++)
           if (li < n_new) atomicAdd(&lhd[2 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1);
         SSYNC()
-        if (st == 0) {
+        if (!BLK) {
+          // one level per lane (VSR_MAX_LEVELS = 32): prefix sum of the counts by shuffles
+          const int c = lhd[2 + lane];
+          int incl = c;
+#pragma unroll
+          for (int d2 = 1; d2 < 32; d2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d2);
+            if (lane >= d2) incl += t;
+          }
+          const unsigned used = __ballot_sync(0xffffffffu, c > 0);
+          lhd[34 + lane] = incl - c;  // cursor: start of level `lane`
+          lhd[2 + lane] = incl;       // end offset of level `lane`
+          if (lane == 0) lhd[1] = used ? 32 - __clz(used) : 0;
+        } else if (st == 0) {
           int run = 0, nl_ = 0;
           for (int l = 0; l < VSR_MAX_LEVELS; l++) {
             const int c = lhd[2 + l];
