@@ -1689,6 +1689,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           real ae[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) ae[k] = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
+          const real vreach = vrad + r_max(r_max(ae[0], ae[1]), r_max(ae[2], ae[3]));  // mass centres + their extents
           const int j_right = has[1] ? nl[1] - lane0 : -1, j_up = has[3] ? nl[3] - lane0 : -1;
           for (int j = v; j < nvox; j++) {
             const int tj = rbase + j;
@@ -1703,6 +1704,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               const real bx = mt[VSR_MTI(kb, 0, tj)], by = mt[VSR_MTI(kb, 1, tj)];
               // half extent of the partner's bounding box
               const real be = P.half * (r_abs(mt[VSR_MTI(kb, 2, tj)]) + r_abs(mt[VSR_MTI(kb, 3, tj)]));
+              // the partner mass against this voxel's box first: most masses of a neighbour are out of reach
+              if (r_abs(bx - vcx) > vreach + be || r_abs(by - vcy) > vreach + be) continue;
 #pragma unroll
               for (int ka = 0; ka < 4; ka++) {
                 if (j == v && kb <= ka) continue;
