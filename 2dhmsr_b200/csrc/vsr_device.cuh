@@ -1575,11 +1575,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       const unsigned old_cmask = cmask;
       cmask = 0;
       unsigned gcn = 0;  // ground constraints per mass, 4 bits each
-      if (!BLK && cap >= 16) {
+      if (cap * VSR_POOL_FIELDS >= 416 * (BLK ? wpb : 1)) {
         // Only a few masses of a warp are near the ground.  Those (by the coarse height map; a mass that
         // had contacts always) are listed for the whole warp and detected one per lane, writing straight
         // into their owners' records; the pool -- idle during detection -- is the scratch space.
-        int* const scr = reinterpret_cast<int*>(pool);  // [32][5] hints + flags, [128] list, [32][4] results
+        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 416 : 0);  // [32][5] hints + flags, [128] list, [32][4] results
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           mt[VSR_MTK(k, 0)] = x[k]; mt[VSR_MTK(k, 1)] = y[k]; mt[VSR_MTK(k, 2)] = cs_[k]; mt[VSR_MTK(k, 3)] = sn_[k];
