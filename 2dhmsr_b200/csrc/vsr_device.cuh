@@ -1590,7 +1590,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         if (active) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const real e = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
+            const real e = P.half * (r_abs(cs_[k]) + r_abs(sn_[k])) + real(0.01);  // (+ a margin: the cell index is rounded)
             int c0 = (int)floorf((float)((x[k] - e - P.hgrid_x0) * P.hgrid_inv)), c1 = (int)floorf((float)((x[k] + e - P.hgrid_x0) * P.hgrid_inv));
             c0 = max(0, min(c0, P.hgrid_n - 1));
             c1 = max(0, min(c1, P.hgrid_n - 1));
