@@ -1096,15 +1096,21 @@ def compile_batch(
     activation = None
     dist_signals = None
     plist = []
+    body_cache: dict = {}  # robots of a population usually share one body Grid: describe it once
     for i, r in enumerate(robots):
         vox = r.voxels
-        mask = bytes(1 if v is not None else 0 for v in vox.values())
-        sens = tuple(
-            tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma, s.noise_seed,
-                   tuple(s.lidar_dirs))
-                  for s in (ss.encode() for ss in v.get_sensors()))
-            for v in vox.values() if v is not None
-        )
+        cached = body_cache.get(id(vox))
+        if cached is None:
+            mask = bytes(1 if v is not None else 0 for v in vox.values())
+            sens = tuple(
+                tuple((s.base, s.axes, s.rotated, s.aggregator, s.soft_norm, s.max_velocity_norm, s.interval, s.noise_sigma,
+                       s.noise_seed, tuple(s.lidar_dirs))
+                      for s in (ss.encode() for ss in v.get_sensors()))
+                for v in vox.values() if v is not None
+            )
+            mats = {bytes(v.material) for v in vox.values() if v is not None}
+            cached = body_cache[id(vox)] = (vox, mask, sens, mats)
+        _, mask, sens, mats = cached
         hidden: Tuple[int, ...] = ()
         if kind == A.VSR_CTRL_MLP:
             f = r.controller.function
@@ -1131,10 +1137,7 @@ def compile_batch(
                 dist_signals = r.controller.signals
             elif dist_signals != r.controller.signals:
                 raise ValueError("one DistributedSensing signal count per batch")
-        for v in vox.values():
-            if v is None:
-                continue
-            mb = bytes(v.material)
+        for mb in mats:
             if material is None:
                 material = mb
             elif material != mb:
