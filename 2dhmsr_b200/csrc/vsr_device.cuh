@@ -36,6 +36,9 @@
 #define VSR_TIE_EPS_F32 1e-6f
 #endif
 
+// candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
+#define VSR_MAX_CAND 8
+
 namespace vsr {
 
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
@@ -190,7 +193,6 @@ template <> struct Real2T<double> { typedef double2 type; };
 // One record type for both kinds: a mass against a ground segment (tb < 0; seg = the segment) and a
 // mass against another mass of the same robot (Voxel.java:178-185,474; owned by the thread of the
 // lower body index, ka = its mass; the partner is mass kb of block thread tb).
-#define SC_CAP 6
 template <typename real>
 struct SPoint {
   real px, py, depth, jn, jt;  // persistent (warm start by id)
@@ -211,7 +213,7 @@ struct CBody {  // ground constraints of one mass
 };
 template <typename real>
 struct SList {  // intra-robot constraints owned by one thread
-  SCon<real> c[SC_CAP + 1];  // + one scratch entry (overflow probe)
+  SCon<real> c[VSR_MAX_CAND];  // slot q = the thread's q-th candidate pair of the tick (a bit mask says which hold)
 };
 
 template <typename real>
@@ -821,7 +823,7 @@ __device__ __forceinline__ real con_position(const CPar<real>& P, const ConPos<r
 template <typename real>
 __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, real ay, real ac, real as, real bx,
                                       real by, real bc, real bs, int ka, int tb, int kb, const SCon<real>* old,
-                                      int old_n, SCon<real>* out) {
+                                      unsigned old_mask, SCon<real>* out) {
   // the record is built in place (the owner's list in the arena)
   SCon<real>& c = *out;
   if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, c)) return 0;
@@ -831,7 +833,8 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
     if (k >= c.n) { c.p[k].jn = real(0); c.p[k].jt = real(0); }
     c.p[k].vb = real(0);
   }
-  for (int i = 0; i < old_n; i++) {
+  for (int i = 0; i < VSR_MAX_CAND; i++) {
+    if (!((old_mask >> i) & 1u)) continue;
     const SCon<real>& o = old[i];
     if (o.ka != ka || o.tb != tb || o.kb != kb) continue;
     for (int k = 0; k < c.n; k++)
@@ -1034,9 +1037,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
 #define VSR_ITEMS_PER_THREAD 16
-static_assert(4 * MAXC + SC_CAP <= VSR_ITEMS_PER_THREAD, "contact list capacity");
-// candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
-#define VSR_MAX_CAND 8
+static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list capacity");
 #endif
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
@@ -1083,7 +1084,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
-  // (a thread lists at most 4 * MAXC ground + SC_CAP intra-robot constraints)
+  // (a thread lists at most 4 * MAXC ground + VSR_MAX_CAND intra-robot constraints)
   int* const items = P.lbuf + (size_t)blockIdx.x * VSR_ITEMS_PER_THREAD * MTS + (BLK ? 0 : wib * VSR_ITEMS_PER_THREAD * 32);
   const int mt_t = tid;
 #define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
@@ -1174,10 +1175,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     for (int k = 0; k < 4; k++) hint[k] = 0;
     unsigned cmask = 0;  // masses with ground constraints
     // intra-robot contacts owned by this thread: two lists (this step's / the previous step's) and,
-    // packed in one word, count (bits 0-3) and the current list (31)
+    // packed in one word, the mask of the slots that hold a constraint (bits 0-7) and the current list (31)
     SList<real>* const sbase = reinterpret_cast<SList<real>*>(P.sbuf) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     unsigned sst = 0;
-#define S_N ((int)(sst & 15u))
+#define S_MASK (sst & 0xffu)
 #define S_CUR (sbase + (sst >> 31))
 #define VSR_MTK(k, c) (((k) * 4 + (c)) * MTS + mt_t)
 #define VSR_MT_PUT(a0, a1, a2)                                                                     \
@@ -1669,7 +1670,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       //      to it.  Order inside a robot = (owner voxel, partner voxel, partner mass, own mass),
       //      the oracle's canonical enumeration.
       const int rbase = BLK ? 0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
-      int n_new = 0;
+      unsigned smask = 0;  // slots of the new list that hold a constraint
       unsigned long long lvpack = 0;  // dependency level of each of this thread's constraints, 8 bits each
       if (P.self_coll) {
 #pragma unroll
@@ -1723,11 +1724,43 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
           }
         }
-        // narrowphase: the q-th candidates of all threads together (one converged call per round)
-        {
+        // narrowphase.  Candidate q of a thread goes to slot q of its list; with the pool as scratch space
+        // the warp's candidates are spread over its lanes (one round), else every thread does its own.
+        if (cap * VSR_POOL_FIELDS >= 576 * (BLK ? wpb : 1)) {
+          int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 576 : 0);  // [32][8] candidates, [32] meta, [256] list, [32] results
+#pragma unroll
+          for (int q = 0; q < VSR_MAX_CAND; q++) scr[lane * 8 + q] = cand[q];
+          scr[256 + lane] = (int)S_MASK;
+          int incl = n_cand;
+#pragma unroll
+          for (int d2 = 1; d2 < 32; d2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d2);
+            if (lane >= d2) incl += t;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          for (int q = 0, pos = incl - n_cand; q < n_cand; q++) scr[288 + pos + q] = (lane << 3) | q;
+          scr[544 + lane] = 0;
+          __syncwarp();
+          const unsigned cur = sst >> 31;
+          for (int i = lane; i < total; i += 32) {
+            const int it = scr[288 + i];
+            const int ol = it >> 3, q = it & 7;
+            const int code = scr[ol * 8 + q];
+            const int tj = code >> 4, kb = (code >> 2) & 3, ka = code & 3;
+            const int tl = (BLK ? 0 : 0) + (wib << 5) + ol;
+            SList<real>* const own = blk_sl + (size_t)tl * 2;
+            const int got = self_pair(cpar, P.half, mt[VSR_MTI(ka, 0, tl)], mt[VSR_MTI(ka, 1, tl)], mt[VSR_MTI(ka, 2, tl)],
+                                      mt[VSR_MTI(ka, 3, tl)], mt[VSR_MTI(kb, 0, tj)], mt[VSR_MTI(kb, 1, tj)], mt[VSR_MTI(kb, 2, tj)],
+                                      mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, own[cur].c, (unsigned)scr[256 + ol], &own[cur ^ 1u].c[q]);
+            if (got) atomicOr(&scr[544 + ol], 1 << q);
+          }
+          __syncwarp();
+          smask = (unsigned)scr[544 + lane];
+          __syncwarp();
+        } else {
           const int max_cand = BLK ? VSR_MAX_CAND : (int)__reduce_max_sync(0xffffffffu, (unsigned)n_cand);
           const SCon<real>* const oldc = S_CUR->c;
-          const int old_n = S_N;
+          const unsigned old_mask = S_MASK;
 #pragma unroll
           for (int q = 0; q < VSR_MAX_CAND; q++) {
             if (q < max_cand) {
@@ -1738,17 +1771,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
                 for (int k = 1; k < 4; k++)
                   if (ka == k) { ax = x[k]; ay = y[k]; ac = cs_[k]; as = sn_[k]; }
-                const int got = self_pair(cpar, P.half, ax, ay, ac, as, mt[VSR_MTI(kb, 0, tj)], mt[VSR_MTI(kb, 1, tj)],
-                                          mt[VSR_MTI(kb, 2, tj)], mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_n,
-                                          &newc[n_new]);
-                if (got) {
-                  if (n_new == SC_CAP) status |= STATUS_CONTACT_OVERFLOW;
-                  else n_new++;
-                }
+                if (self_pair(cpar, P.half, ax, ay, ac, as, mt[VSR_MTI(kb, 0, tj)], mt[VSR_MTI(kb, 1, tj)], mt[VSR_MTI(kb, 2, tj)],
+                              mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_mask, &newc[q]))
+                  smask |= 1u << q;
               }
             }
           }
         }
+        const int n_new = __popc(smask);
         // position of this thread's constraints in its robot's order
         int incl = n_new;
 #pragma unroll
@@ -1787,22 +1817,23 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         for (int i = 0; i < s_tot; i++) {
           const int li = i - s_start;
           if (li >= 0 && li < n_new) {
-            const int ia = newc[li].ka * MTS + tid, ib = newc[li].kb * MTS + newc[li].tb;
+            const int sl = (int)__fns(smask, 0, li + 1);  // the li-th slot in use
+            const int ia = newc[sl].ka * MTS + tid, ib = newc[sl].kb * MTS + newc[sl].tb;
             const int ca = (int)cnt[ia], cb2 = (int)cnt[ib];
             int lv = ca > cb2 ? ca : cb2;
             cnt[ia] = (real)(lv + 1);
             cnt[ib] = (real)(lv + 1);
             if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_CONTACT_OVERFLOW; }
-            lvpack |= (unsigned long long)lv << (8 * li);
+            lvpack |= (unsigned long long)lv << (8 * sl);
           }
           SSYNC()
         }
-        sst = (unsigned)n_new | ((sst ^ 0x80000000u) & 0x80000000u);
+        sst = smask | ((sst ^ 0x80000000u) & 0x80000000u);
       }
 
       // ---- the scope's constraint list for the next step, by dependency level: the q-th ground
       //      constraint of a mass has level q, the intra-robot ones follow (levels above)
-      if (!BLK && !__any_sync(0xffffffffu, gcn != 0u || n_new != 0)) {
+      if (!BLK && !__any_sync(0xffffffffu, gcn != 0u || smask != 0u)) {
         if (lane == 0) lhd[1] = 0;  // nothing touches anything in this warp
         __syncwarp();
       } else {
@@ -1815,8 +1846,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           for (int q = 0; q < cn; q++) atomicAdd(&lhd[2 + q], 1);
         }
 #pragma unroll
-        for (int li = 0; li < SC_CAP; li++)
-          if (li < n_new) atomicAdd(&lhd[2 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1);
+        for (int li = 0; li < VSR_MAX_CAND; li++)
+          if ((smask >> li) & 1u) atomicAdd(&lhd[2 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1);
         SSYNC()
         if (!BLK) {
           // one level per lane (VSR_MAX_LEVELS = 32): prefix sum of the counts by shuffles
@@ -1850,8 +1881,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             items[atomicAdd(&lhd[34 + q], 1)] = (tid << 7) | ((k * 2 + (int)((flip >> k) & 1u)) << 4) | (q << 1);
         }
 #pragma unroll
-        for (int li = 0; li < SC_CAP; li++)
-          if (li < n_new)
+        for (int li = 0; li < VSR_MAX_CAND; li++)
+          if ((smask >> li) & 1u)
             items[atomicAdd(&lhd[34 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
         SSYNC()
       }
