@@ -416,7 +416,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       int s0 = sh.sensor_offsets ? sh.sensor_offsets[v] : 0, s1 = sh.sensor_offsets ? sh.sensor_offsets[v + 1] : 0;
       if (s1 - s0 > MAX_SENS) {
         delete b;
-        return fail(VSR_ERR_UNSUPPORTED, "more than 5 sensors per voxel");
+        return fail(VSR_ERR_UNSUPPORTED, "more than 16 sensors per voxel");
       }
       S.n_sens[v] = (int8_t)(s1 - s0);
       S.read_off[v] = (int16_t)ro;
@@ -464,7 +464,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       }
       if (nr > MAX_READ) {
         delete b;
-        return fail(VSR_ERR_UNSUPPORTED, "more than 12 readings per voxel");
+        return fail(VSR_ERR_UNSUPPORTED, "more than 24 readings per voxel");
       }
       ro += nr;
       maxch = std::max(maxch, ch);
@@ -493,7 +493,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         S.neurons[1 + i] = sh.hidden[i];
         if (sh.hidden[i] <= 0 || sh.hidden[i] > VSR_DIST_WIDTH) {
           delete b;
-          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: hidden layers of 1..32 neurons are supported");
+          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: hidden layers of 1..40 neurons are supported");
         }
       }
       S.neurons[0] = 0;  // per voxel
@@ -504,7 +504,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         S.dist_off[v] = off;
         if (nin > VSR_DIST_WIDTH || S.neurons[S.n_layers - 1] > VSR_DIST_WIDTH) {
           delete b;
-          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: at most 32 inputs / outputs per voxel");
+          return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: at most 40 inputs / outputs per voxel");
         }
         int prev = nin;
         for (int i = 1; i < S.n_layers; i++) {

@@ -42,11 +42,11 @@
 namespace vsr {
 
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
-constexpr int MAX_SENS = 5;    // sensors per voxel
-constexpr int MAX_READ = 12;   // readings per voxel
+constexpr int MAX_SENS = 16;   // sensors per voxel (uniformAll-*: all 15 predefined ones)
+constexpr int MAX_READ = 24;   // readings per voxel (uniformAll-*: 21)
 constexpr int MAXC = 2;        // simultaneous ground constraints per mass
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
-#define VSR_DIST_WIDTH 32      // DistributedSensing: widest layer of a voxel's MLP (12 readings + 4 x 4 signals = 28 inputs)
+#define VSR_DIST_WIDTH 40      // DistributedSensing: widest layer of a voxel's MLP (24 readings + 4 x 4 signals = 40 inputs)
 constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
 
 enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };

@@ -818,7 +818,7 @@ class RobotUtils:
         if p is not None:  # :177-189: every predefined sensor, TreeMap (sorted) order
             return RobotUtils.build_sensorizing_function(
                 "uniform-" + "+".join(sorted(RobotUtils.PREDEFINED_SENSORS)) + "-" + p["noiseSigma"])
-        for out in (r"spinedTouchSighted-.*",):
+        for out in ():
             if _params(out, name) is not None:
                 raise NotImplementedError(f"sensorizing function '{name}' is outside the accelerated hot path")
         raise ValueError(f"Unknown sensorizing function name: {name}")

@@ -682,10 +682,10 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
         return Voxel({});
       });
     };
-  if (match(R"(spinedTouch-([tf])-([tf])-(\d+(\.\d+)?))", name, m)) {  // :134-149
-    const double sigma = std::stod(m[3]);
-    const bool cpg = m[1] == "t", malfunction = m[2] == "t";
-    return [cpg, malfunction, sigma](const Grid<bool>& body) {
+  if (match(R"(spinedTouch(Sighted)?-([tf])-([tf])-(\d+(\.\d+)?))", name, m)) {  // :134-165
+    const double sigma = std::stod(m[4]);
+    const bool sighted = m[1].matched, cpg = m[2] == "t", malfunction = m[3] == "t";
+    return [sighted, cpg, malfunction, sigma](const Grid<bool>& body) {
       return Grid<Voxel>::create(body.getW(), body.getH(), [&](int x, int y) -> std::optional<Voxel> {
         if (!body.get(x, y) || !*body.get(x, y)) return std::nullopt;
         std::vector<SensorPtr> ss;
@@ -694,14 +694,19 @@ inline std::function<Grid<Voxel>(const Grid<bool>&)> buildSensorizingFunction(co
         if (y == 0) ss.push_back(sensor("t"));
         if (y == body.getH() - 1) ss.push_back(sensor("vxy"));
         if (x == body.getW() - 1 && y == body.getH() - 1 && cpg) ss.push_back(sensor("cpg"));
+        if (sighted && x == body.getW() - 1)  // :163; RobotUtils.sensor normalises the position (:257-263)
+          ss.push_back(sensor("l5", double(x) / (double(body.getW()) - 1.0), double(y) / (double(body.getH()) - 1.0)));
         if (sigma != 0)
           for (auto& sp : ss) sp = std::make_shared<Noisy>(sp, sigma, 0);
         return Voxel(ss);
       });
     };
   }
-  for (const char* o : {"spinedTouchSighted-", "uniformAll-"})
-    if (name.rfind(o, 0) == 0) throw Unsupported("sensorizing function '" + name + "' is outside the accelerated hot path");
+  if (match(R"(uniformAll-(\d+(\.\d+)?))", name, m)) {  // :177-189: every predefined sensor in TreeMap (sorted) order
+    std::string all = keys;
+    std::replace(all.begin(), all.end(), '|', '+');
+    return buildSensorizingFunction("uniform-" + all + "-" + std::string(m[1]));
+  }
   throw std::invalid_argument("Unknown sensorizing function name: " + name);
 }
 }  // namespace RobotUtils

@@ -139,7 +139,22 @@ int main(int argc, char** argv) {
       for (int i = 0; i < q.axes; i++) e.push_back(q.lidar_dirs[i]);
       std::cout << " \"lidar_2_0\": " << jarr(e) << ",\n";
     }
-    std::cout << " \"err_lidar\": \"" << throwsWhat([] { RobotUtils::buildSensorizingFunction("uniformAll-0")(RobotUtils::buildShape("box-2x2")); }) << "\",\n";
+    {
+      // uniformAll (RobotUtils.java:177-189): the 15 predefined sensors in sorted order = 21 readings per voxel;
+      // spinedTouchSighted (:150-165): the last column also carries the 5-ray lidar
+      Grid<Voxel> all = RobotUtils::buildSensorizingFunction("uniformAll-0")(RobotUtils::buildShape("box-2x2"));
+      std::vector<double> bases;
+      int readings = 0;
+      for (auto& sp : all.get(1, 1)->getSensors()) {
+        bases.push_back(double(sp->encode().base));
+        readings += int(sp->getDomains().size());
+      }
+      std::cout << " \"all_bases_1_1\": " << jarr(bases) << ", \"all_readings\": " << readings << ",\n";
+      Grid<Voxel> ss = RobotUtils::buildSensorizingFunction("spinedTouchSighted-t-f-0")(RobotUtils::buildShape("biped-4x3"));
+      std::vector<double> cnt;
+      for (auto& e : ss.values()) if (e) cnt.push_back(double(e->getSensors().size()));
+      std::cout << " \"sighted_sensor_counts\": " << jarr(cnt) << ",\n";
+    }
     std::cout << " \"err_weights\": \"" << throwsWhat([] { MultiLayerPerceptron(MultiLayerPerceptron::TANH, 3, {2}, 1, std::vector<double>(5)); }) << "\",\n";
     std::cout << " \"err_dims\": \"" << throwsWhat([&] { CentralizedSensing(worm, MultiLayerPerceptron(MultiLayerPerceptron::TANH, 63, {}, 16, std::vector<double>(16 * 64))); }) << "\",\n";
     std::cout << " \"err_ground\": \"" << throwsWhat([] { Locomotion(1, {{0, 5, 3}, {0, 0, 0}}, Settings()); }) << "\",\n";

@@ -71,7 +71,13 @@ def test_cpp_host_mirror_selfcheck():
     assert j["err_terrain"] == "invalid_argument:Unknown terrain name: moon"
     assert j["err_shape"] == "invalid_argument:Unknown body name: snake-3"
     assert j["err_sensors"].startswith("invalid_argument:Unknown sensorizing function name")
-    assert j["err_lidar"].startswith("Unsupported:")     # uniformAll: 15 sensors per voxel
+    # uniformAll (RobotUtils.java:177-189): 15 sensors in TreeMap order, 21 readings per voxel
+    allv = helpers.body_of("box-2x2", "uniformAll-0").get(1, 1)
+    assert j["all_bases_1_1"] == [s.encode().base for s in allv.get_sensors()] and len(j["all_bases_1_1"]) == 15
+    assert j["all_readings"] == sum(len(s.domains()) for s in allv.get_sensors()) == 21
+    # spinedTouchSighted (:150-165): spinedTouch + a 5-ray lidar on the last column
+    sighted = helpers.body_of("biped-4x3", "spinedTouchSighted-t-f-0")
+    assert j["sighted_sensor_counts"] == [len(v.get_sensors()) for v in sighted.values() if v is not None]
     enc = helpers.body_of("worm-3x2", "uniform-l5-0").get(2, 0).get_sensors()[0].encode()
     assert j["lidar_2_0"] == [A.VSR_SENSOR_LIDAR, 5, A.VSR_NORM_LINEAR, 10.0] + list(enc.lidar_dirs)[:5]
     assert j["err_weights"] == "invalid_argument:Wrong number of weights: 11 expected, 5 found"

@@ -337,6 +337,22 @@ def test_fp64_custom_sensor_sets():
     assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
 
 
+@pytest.mark.parametrize("controller", ["centralized", "distributed"])
+def test_fp64_uniform_all_sensors(controller):
+    """uniformAll-* (RobotUtils.java:177-189): the 15 predefined sensors on every voxel (21 readings: two
+    lidars, windowed averages, trends, constants, cpg ...), read by a CentralizedSensing MLP (210 inputs on a
+    biped-4x3) and by a DistributedSensing controller (21 readings + 4 x 2 signals per voxel)."""
+    if controller == "centralized":
+        robots = helpers.mlp_robots(3, shape="biped-4x3", sensors="uniformAll-0", hidden=(8,), seed=41)
+    else:
+        robots = helpers.distributed_robots(3, shape="biped-4x3", signals=2, hidden=(4,), seed=43, sensors="uniformAll-0.01")
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0, terrain="hilly-1-10-0"), robots, F64)
+    assert np.all(res["status"] == 0)
+    assert np.abs(tr[..., :3] - otr[:, :, :40, :3]).max() < 1e-7
+    assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=1e-8)
+    assert np.all(res["control_energy_last"] > 0)
+
+
 def test_fp64_lidar_on_hilly_terrain():
     """Lidar rays against a hilly profile (spinedTouchSighted layout: l5 on the front column, cpg, touch,
     velocity), read by a CentralizedSensing MLP."""
