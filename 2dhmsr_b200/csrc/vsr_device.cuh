@@ -226,10 +226,18 @@ struct Edge {
   int i1, i2, index;
 };
 
+// a[i] for i in 0..3 as register selects: a dynamically indexed local array would live in local memory,
+// and with the shared-memory carve-out of this kernel the L1 is too small to hold the stack frames
+template <typename real>
+__device__ __forceinline__ real sel4(const real* a, int i) {
+  const real lo = (i & 1) ? a[1] : a[0], hi = (i & 1) ? a[3] : a[2];
+  return (i & 2) ? hi : lo;
+}
+
 // Polygon.getFarthestFeature (dyn4j): farthest vertex along n, then the adjacent edge
 // that is most perpendicular to n, CCW winding kept.
 template <typename real>
-__device__ void farthest_edge(const Poly4<real>& P, real nx, real ny, Edge<real>& e) {
+__device__ __forceinline__ void farthest_edge(const Poly4<real>& P, real nx, real ny, Edge<real>& e) {
   int idx = 0;
   real best = P.vx[0] * nx + P.vy[0] * ny;
 #pragma unroll
@@ -240,18 +248,19 @@ __device__ void farthest_edge(const Poly4<real>& P, real nx, real ny, Edge<real>
       idx = i;
     }
   }
-  int prev = (idx + 3) & 3, next = (idx + 1) & 3;
-  real ln = P.nx[prev] * nx + P.ny[prev] * ny;
-  real rn = P.nx[idx] * nx + P.ny[idx] * ny;
-  e.mx = P.vx[idx];
-  e.my = P.vy[idx];
+  const int prev = (idx + 3) & 3, next = (idx + 1) & 3;
+  const real ln = sel4(P.nx, prev) * nx + sel4(P.ny, prev) * ny;
+  const real rn = sel4(P.nx, idx) * nx + sel4(P.ny, idx) * ny;
+  const real ix = sel4(P.vx, idx), iy = sel4(P.vy, idx);
+  e.mx = ix;
+  e.my = iy;
   if (ln < rn) {
-    e.x1 = P.vx[idx]; e.y1 = P.vy[idx]; e.i1 = idx;
-    e.x2 = P.vx[next]; e.y2 = P.vy[next]; e.i2 = next;
+    e.x1 = ix; e.y1 = iy; e.i1 = idx;
+    e.x2 = sel4(P.vx, next); e.y2 = sel4(P.vy, next); e.i2 = next;
     e.index = next == 0 ? 4 : next;
   } else {
-    e.x1 = P.vx[prev]; e.y1 = P.vy[prev]; e.i1 = prev;
-    e.x2 = P.vx[idx]; e.y2 = P.vy[idx]; e.i2 = idx;
+    e.x1 = sel4(P.vx, prev); e.y1 = sel4(P.vy, prev); e.i1 = prev;
+    e.x2 = ix; e.y2 = iy; e.i2 = idx;
     e.index = idx == 0 ? 4 : idx;  // one label per edge (see the oracle's farthest_edge)
   }
 }
@@ -262,23 +271,22 @@ struct ClipPt {
   int idx;
 };
 
-// ClippingManifoldSolver.clip (dyn4j)
+// ClippingManifoldSolver.clip (dyn4j): the points of (v1, v2) behind the plane, then the crossing point if
+// the two lie on different sides -- at most two; returns how many of (o0, o1) hold.
 template <typename real>
-__device__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx, real ny, real offset,
-                         ClipPt<real>* out) {
-  int n = 0;
-  real d1 = nx * v1.x + ny * v1.y - offset, d2 = nx * v2.x + ny * v2.y - offset;
-  if (d1 <= real(0)) out[n++] = v1;
-  if (d2 <= real(0)) out[n++] = v2;
-  if (d1 * d2 < real(0)) {
-    real u = d1 / (d1 - d2);
-    ClipPt<real> p;
-    p.x = v1.x + (v2.x - v1.x) * u;
-    p.y = v1.y + (v2.y - v1.y) * u;
-    p.idx = d1 > real(0) ? v1.idx : v2.idx;
-    if (n < 2) out[n++] = p;
-  }
-  return n;
+__device__ __forceinline__ int clip_edge(const ClipPt<real>& v1, const ClipPt<real>& v2, real nx, real ny, real offset,
+                                         ClipPt<real>& o0, ClipPt<real>& o1) {
+  const real d1 = nx * v1.x + ny * v1.y - offset, d2 = nx * v2.x + ny * v2.y - offset;
+  const bool k1 = d1 <= real(0), k2 = d2 <= real(0), cross = d1 * d2 < real(0);
+  const real u = d1 / (d1 - d2);
+  ClipPt<real> p;
+  p.x = v1.x + (v2.x - v1.x) * u;
+  p.y = v1.y + (v2.y - v1.y) * u;
+  p.idx = d1 > real(0) ? v1.idx : v2.idx;
+  // k1 && k2 excludes a crossing; neither excludes it too (both in front)
+  o0 = k1 ? v1 : (k2 ? v2 : p);
+  o1 = (k1 && k2) ? v2 : p;
+  return (k1 ? 1 : 0) + (k2 ? 1 : 0) + (cross ? 1 : 0);
 }
 
 // Narrowphase (SAT == the EPA answer for two convex polygons) + clipping manifold for
@@ -373,11 +381,11 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
   real rl = r_sqrt(rx * rx + ry * ry);
   rx /= rl;
   ry /= rl;
-  ClipPt<real> a = {inc.x1, inc.y1, inc.i1}, b = {inc.x2, inc.y2, inc.i2}, c1[3], c2[3];
+  ClipPt<real> a = {inc.x1, inc.y1, inc.i1}, b = {inc.x2, inc.y2, inc.i2}, c1[2], c2[2];
   real o1 = -(rx * ref.x1 + ry * ref.y1);
-  if (clip_edge(a, b, -rx, -ry, o1, c1) < 2) return 0;
+  if (clip_edge(a, b, -rx, -ry, o1, c1[0], c1[1]) < 2) return 0;
   real o2 = rx * ref.x2 + ry * ref.y2;
-  if (clip_edge(c1[0], c1[1], rx, ry, o2, c2) < 2) return 0;
+  if (clip_edge(c1[0], c1[1], rx, ry, o2, c2[0], c2[1]) < 2) return 0;
   real fx = -ry, fy = rx;
   real fo = fx * ref.mx + fy * ref.my;
   c.nx = flipped ? fx : -fx;
