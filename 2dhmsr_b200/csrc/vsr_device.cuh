@@ -28,6 +28,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -62,6 +63,15 @@ struct SensorDev {
   double max_norm;  // Velocity: domain bound; Constant / TimeFunction: the value / the frequency
   double noise;     // Noisy: sigma (0 = not noisy)
   double dirs[8];   // Lidar: ray directions (axes = their number, max_norm = the ray length)
+};
+
+static_assert(offsetof(SensorDev, interval) == 8 && offsetof(SensorDev, max_norm) == 16 && sizeof(SensorDev) % 8 == 0,
+              "the kernel reads the head of a SensorDev as two 8-byte words");
+// the scalars of a SensorDev, unpacked in registers
+struct SensorHdr {
+  int base, axes, rotated, agg, soft, win, ch, dim;
+  float interval;
+  double max_norm, noise;
 };
 
 // One shape class (Grid<Boolean> + sensor layout), compiled on the host.
@@ -1926,7 +1936,21 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         int ro = 0;
         const int ns = S.n_sens[v];
         for (int si = 0; si < ns; si++) {
-          const SensorDev sd = S.sens[v][si];
+          // the record's scalars by four independent 8-byte loads (one latency); a struct copy would put the
+          // whole record, ray directions included, on the stack because `dirs` is indexed dynamically
+          const SensorDev* const sp = &S.sens[v][si];
+          SensorHdr sd;
+          {
+            const int2 hw = __ldg(reinterpret_cast<const int2*>(sp));
+            const int2 iw = __ldg(reinterpret_cast<const int2*>(sp) + 1);
+            sd.max_norm = __ldg(&sp->max_norm);
+            sd.noise = __ldg(&sp->noise);
+            sd.base = (int)(int8_t)(hw.x & 255); sd.axes = (int)(int8_t)((hw.x >> 8) & 255);
+            sd.rotated = (int)(int8_t)((hw.x >> 16) & 255); sd.agg = (int)(int8_t)((hw.x >> 24) & 255);
+            sd.soft = (int)(int8_t)(hw.y & 255); sd.win = (int)(int8_t)((hw.y >> 8) & 255);
+            sd.ch = (int)(int8_t)((hw.y >> 16) & 255); sd.dim = (int)(int8_t)((hw.y >> 24) & 255);
+            sd.interval = __int_as_float(iw.x);
+          }
           real raw[2] = {0, 0}, dmin = real(0), dmax = real(1);
           if (sd.base == SENSOR_TOUCH) {
             raw[0] = cmask ? real(1) : real(0);
@@ -1968,13 +1992,13 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           } else if (sd.base == SENSOR_LIDAR) {
             dmax = (real)sd.max_norm;  // the rays are cast below, one reading each
           } else {
-            int c = 0;
             real sa, ca;
             r_sincos(ang, &sa, &ca);
-            if (sd.axes & 1) raw[c++] = sd.rotated ? mvx * ca + mvy * sa : mvx;
+            if (sd.axes & 1) raw[0] = sd.rotated ? mvx * ca + mvy * sa : mvx;
             if (sd.axes & 2) {
               // unit(angle + pi/2) = (-sin, cos) (Velocity.java:75 builds it numerically: same to 1 ulp)
-              raw[c++] = sd.rotated ? -mvx * sa + mvy * ca : mvy;
+              const real vy_ = sd.rotated ? -mvx * sa + mvy * ca : mvy;
+              if (sd.axes & 1) raw[1] = vy_; else raw[0] = vy_;  // (static indices: raw stays in registers)
             }
             dmin = -(real)sd.max_norm;
             dmax = (real)sd.max_norm;
@@ -1983,7 +2007,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           if (sd.agg != AGG_NONE) {
             const int depth = S.ring_depth;
             const int f = P.win_first[sd.win * P.n_ticks + tick];
-            for (int d = 0; d < sd.dim; d++) {
+#pragma unroll
+            for (int d = 0; d < 2; d++) {  // aggregated sensors have one or two readings
+              if (d >= sd.dim) break;
               real* ring = P.ring + ((size_t)(sd.ch + d)) * n_gl + gl;
               const size_t stride = (size_t)S.n_channels * n_gl;
               ring[(size_t)(tick % depth) * stride] = raw[d];
@@ -2005,12 +2031,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
           }
           for (int d = 0; d < sd.dim; d++) {
-            real o = val[d < 2 ? d : 0];
+            real o = d == 1 ? val[1] : val[0];
             if (sd.base == SENSOR_LIDAR) {
               // from Voxel.center (the mean of the 4 mass centres) at rayDirection + Voxel.getAngle
               const real ocx = (((x[0] + x[1]) + x[2]) + x[3]) / real(4), ocy = (((y[0] + y[1]) + y[2]) + y[3]) / real(4);
               real rs, rc;
-              r_sincos((real)sd.dirs[d] + ang, &rs, &rc);
+              r_sincos((real)__ldg(&sp->dirs[d]) + ang, &rs, &rc);
               o = lidar_cast(tpar, ocx, ocy, rc, rs, (real)sd.max_norm, hint[0]);
             }
             if (sd.soft == 1) {
