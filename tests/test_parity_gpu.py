@@ -217,6 +217,53 @@ def test_full_size_properties_config2():
     assert 0.5 < d[:256].std() / od.std() < 2.0
 
 
+def test_properties_config3_mlp_worms():
+    """BASELINE config 3 at reduced size (4096 of the 65 536 worm-8x2 robots, CentralizedSensing MLP [21, 21] on
+    ax+t, full 20 s): size-independent properties -- determinism, independence of the batch composition, replicas
+    agree, finite and bounded outcomes, a controller that actually acts."""
+    robots = helpers.mlp_robots(4096, hidden=(21, 21), seed=1)
+    loco = helpers.locomotion(20.0)
+    bd = loco.compile(robots)
+    r1, _ = helpers.gpu_run(bd)
+    r2, _ = helpers.gpu_run(bd)
+    assert r1.tobytes() == r2.tobytes()
+    assert np.all(r1["status"] == 0) and np.all(r1["n_ticks"] == 1200)
+    d = r1["last_center_x"] - r1["first_center_x"]
+    assert np.all(np.isfinite(d)) and np.abs(d).max() < 400
+    assert np.all(r1["control_energy_last"] > 0) and np.all(r1["control_energy_last"] <= 16 * 1200 + 1e-3)  # |f| <= 1
+    pick = [0, 9, 2048, 4095]
+    rs, _ = helpers.gpu_run(loco.compile([robots[i] for i in pick]))
+    assert rs.tobytes() == r1[pick].tobytes()
+    rr, _ = helpers.gpu_run(loco.compile([robots[7]] * 5))
+    assert all(rr[i].tobytes() == r1[7].tobytes() for i in range(5))
+
+
+def test_properties_config4_mixed_shapes_on_hills():
+    """BASELINE config 4 at reduced size (1024 robots of random biped / worm / box shapes up to 10 x 10 on
+    hilly-1-10-0 with t+vxy+a sensors, 5 s): one launch per shape bucket on side streams; the result of a robot
+    does not depend on what else is in the batch, overflow is flagged, never silent."""
+    rng = np.random.default_rng(2)
+    bodies, robots = {}, []
+    for _ in range(1024):
+        kind = ("biped", "worm", "box")[rng.integers(3)]
+        w = int(rng.integers(4 if kind == "biped" else 2, 11)); h = int(rng.integers(2 if kind == "biped" else 1, 11))
+        key = f"{kind}-{w}x{h}"
+        b = bodies.setdefault(key, helpers.body_of(key, "uniform-t+vxy+a-0"))
+        ph = rng.uniform(0, 2 * np.pi, size=(b.w, b.h))
+        robots.append(H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(b.w, b.h, lambda x, y, ph=ph: float(ph[x, y]))), b))
+    loco = helpers.locomotion(5.0, terrain="hilly-1-10-0")
+    bd = loco.compile(robots)
+    r1, _ = helpers.gpu_run(bd)
+    r2, _ = helpers.gpu_run(loco.compile(robots))
+    assert r1.tobytes() == r2.tobytes()
+    assert np.all((r1["status"] & 1) == 0) and (r1["status"] != 0).mean() < 0.01   # nothing non-finite; overflow is rare
+    # (301 ticks, not 300: Java's `t += dT` accumulates to 4.99999... after 300 steps, AbstractTask.java:48)
+    assert np.all(np.isfinite(r1["last_center_x"])) and np.all(r1["n_ticks"] == bd.n_ticks) and bd.n_ticks == 301
+    pick = list(range(0, 1024, 97))
+    rs, _ = helpers.gpu_run(loco.compile([robots[i] for i in pick]))
+    assert rs.tobytes() == r1[pick].tobytes()
+
+
 def test_call_order_errors():
     bd = helpers.locomotion(1.0).compile(helpers.phase_robots(2))
     with H.DeviceBatch(bd) as db:
