@@ -300,8 +300,8 @@ __device__ __forceinline__ int clip_edge(const ClipPt<real>& v1, const ClipPt<re
 }
 
 // Narrowphase (SAT == the EPA answer for two convex polygons) + clipping manifold for
-// one mass against one ground segment.  Returns 1 and fills c (n, normal, points) on
-// collision.
+// one mass against one ground segment.  Returns the number of manifold points (0 = no collision) and fills c
+// (n, normal, points).
 template <typename real>
 __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real bs, real half, real x0, real y0,
                                                  real x1, real y1, real base_y, int mm, SCon<real>& c) {
@@ -414,7 +414,7 @@ __device__ __noinline__ int collide_mass_segment(real bx, real by, real bc, real
       p.id = (ref.index & 7) | ((inc.index & 7) << 3) | ((c2[i].idx & 7) << 6) | (flipped << 9);
     }
   }
-  return c.n > 0;
+  return c.n;  // (the callers keep the count in a register: c lives in global memory)
 }
 
 // terrain description passed by value (registers) to detect_mass
@@ -475,13 +475,15 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     // manifold that would not fit
     SCon<real> scratch;
     SCon<real>& c = cn < MAXC ? cb.c[cn] : scratch;
-    if (!collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, 0, c)) continue;
+    // (the point count in a register: reading c.n back from the arena is an L2 round trip before every loop)
+    const int n_c = collide_mass_segment(bx, by, bc, bs, P.half, x0, y0, x1, y1, P.base_y, 0, c);
+    if (!n_c) continue;
     if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
     c.ka = k_mass; c.tb = -1; c.kb = 0;
     for (int i = 0; i < old_n; i++) {
       if (old.c[i].seg != seg) continue;
-      for (int k = 0; k < c.n; k++)
+      for (int k = 0; k < n_c; k++)
         for (int l = 0; l < old.c[i].n; l++)
           if (old.c[i].p[l].id == c.p[k].id) {
             c.p[k].jn = old.c[i].p[l].jn;
@@ -493,7 +495,9 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     // step's initialisation
     {
       const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
-      for (int k = 0; k < c.n; k++) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (k >= n_c) break;
         SPoint<real>& p = c.p[k];
         p.r1x = p.px - bx;
         p.r1y = p.py - by;
@@ -508,7 +512,7 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
         p.vb = real(0);
       }
       c.block = 0;
-      if (c.n == 2) {
+      if (n_c == 2) {
         real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx;
         real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx;
         c.K00 = im + ii * rn1A * rn1A;
@@ -844,18 +848,19 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
                                       unsigned old_mask, SCon<real>* out) {
   // the record is built in place (the owner's list in the arena)
   SCon<real>& c = *out;
-  if (!collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, c)) return 0;
+  const int n_c = collide_mass_segment(ax, ay, ac, as, half, bx, by, bc, bs, real(0), 1, c);
+  if (!n_c) return 0;
   c.ka = ka; c.tb = tb; c.kb = kb; c.block = 0; c.seg = -1;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    if (k >= c.n) { c.p[k].jn = real(0); c.p[k].jt = real(0); }
+    if (k >= n_c) { c.p[k].jn = real(0); c.p[k].jt = real(0); }
     c.p[k].vb = real(0);
   }
   for (int i = 0; i < VSR_MAX_CAND; i++) {
     if (!((old_mask >> i) & 1u)) continue;
     const SCon<real>& o = old[i];
     if (o.ka != ka || o.tb != tb || o.kb != kb) continue;
-    for (int k = 0; k < c.n; k++)
+    for (int k = 0; k < n_c; k++)
       for (int l = 0; l < o.n; l++)
         if (o.p[l].id == c.p[k].id) {
           c.p[k].jn = o.p[l].jn;
@@ -868,7 +873,7 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     SPoint<real>& p = c.p[k];
-    if (k >= c.n) { p.px = ax; p.py = ay; }  // unused slot: finite numbers
+    if (k >= n_c) { p.px = ax; p.py = ay; }  // unused slot: finite numbers
     p.r1x = p.px - ax; p.r1y = p.py - ay;
     p.r2x = p.px - bx; p.r2y = p.py - by;
     p.l1x = ac * p.r1x + as * p.r1y; p.l1y = -as * p.r1x + ac * p.r1y;
@@ -879,7 +884,7 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
     p.massT = real(1) / (im + im + ii * rt1 * rt1 + ii * rt2 * rt2);
   }
   c.K00 = c.K01 = c.K11 = c.iK00 = c.iK01 = c.iK11 = real(0);
-  if (c.n == 2) {
+  if (n_c == 2) {
     real rn1A = c.p[0].r1x * ny - c.p[0].r1y * nx, rn1B = c.p[0].r2x * ny - c.p[0].r2y * nx;
     real rn2A = c.p[1].r1x * ny - c.p[1].r1y * nx, rn2B = c.p[1].r2x * ny - c.p[1].r2y * nx;
     real mm = im + im;
