@@ -481,14 +481,29 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
     if (cn == MAXC) { overflow = 1; break; }
     c.seg = seg;
     c.ka = k_mass; c.tb = -1; c.kb = 0;
-    for (int i = 0; i < old_n; i++) {
-      if (old.c[i].seg != seg) continue;
-      for (int k = 0; k < n_c; k++)
-        for (int l = 0; l < old.c[i].n; l++)
-          if (old.c[i].p[l].id == c.p[k].id) {
-            c.p[k].jn = old.c[i].p[l].jn;
-            c.p[k].jt = old.c[i].p[l].jt;
-          }
+    // ContactConstraint.update: impulses of the points with the same id are carried over.  Everything the match
+    // needs is loaded in one batch (independent loads = one L2 round trip; walking seg -> n -> id -> impulse
+    // were four) and compared in registers, in the order of the loops it replaces (later matches win).
+    if (old_n > 0) {
+      const int idn[2] = {c.p[0].id, c.p[1].id};
+      real jn[2], jt[2];
+      bool hit[2] = {false, false};
+#pragma unroll
+      for (int i = 0; i < MAXC; i++) {
+        const SCon<real>& o = old.c[i];
+        const int oseg = o.seg, on = o.n, oid[2] = {o.p[0].id, o.p[1].id};
+        const real ojn[2] = {o.p[0].jn, o.p[1].jn}, ojt[2] = {o.p[0].jt, o.p[1].jt};
+        if (i < old_n && oseg == seg) {
+#pragma unroll
+          for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int l = 0; l < 2; l++)
+              if (k < n_c && l < on && oid[l] == idn[k]) { jn[k] = ojn[l]; jt[k] = ojt[l]; hit[k] = true; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+        if (hit[k]) { c.p[k].jn = jn[k]; c.p[k].jt = jt[k]; }
     }
     // SequentialImpulses.initialize (dyn4j), the part that depends on positions only (the ground
     // is static: invM2 = invI2 = 0): the mass does not move between this detection and the next
