@@ -871,17 +871,31 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
     if (k >= n_c) { c.p[k].jn = real(0); c.p[k].jt = real(0); }
     c.p[k].vb = real(0);
   }
-  for (int i = 0; i < VSR_MAX_CAND; i++) {
-    if (!((old_mask >> i) & 1u)) continue;
-    const SCon<real>& o = old[i];
-    if (o.ka != ka || o.tb != tb || o.kb != kb) continue;
-    for (int k = 0; k < n_c; k++)
-      for (int l = 0; l < o.n; l++)
-        if (o.p[l].id == c.p[k].id) {
-          c.p[k].jn = o.p[l].jn;
-          c.p[k].jt = o.p[l].jt;
-        }
-    break;
+  // ContactConstraint.update: the first slot of the previous list that held this pair; its points' impulses are
+  // carried over by id.  The keys of the slots in use are loaded together (independent, predicated loads), then
+  // the matching record in one batch: two L2 round trips instead of one or more per slot.
+  {
+    int mi = -1;
+#pragma unroll
+    for (int i = VSR_MAX_CAND - 1; i >= 0; i--) {
+      int oka = -1, otb = -2, okb = -1;
+      if ((old_mask >> i) & 1u) { oka = old[i].ka; otb = old[i].tb; okb = old[i].kb; }
+      if (oka == ka && otb == tb && okb == kb) mi = i;  // descending: the first match wins
+    }
+    if (mi >= 0) {
+      const SCon<real>& o = old[mi];
+      const int on = o.n, oid[2] = {o.p[0].id, o.p[1].id}, idn[2] = {c.p[0].id, c.p[1].id};
+      const real ojn[2] = {o.p[0].jn, o.p[1].jn}, ojt[2] = {o.p[0].jt, o.p[1].jt};
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        real jn = real(0), jt = real(0);
+        bool hit = false;
+#pragma unroll
+        for (int l = 0; l < 2; l++)
+          if (k < n_c && l < on && oid[l] == idn[k]) { jn = ojn[l]; jt = ojt[l]; hit = true; }
+        if (hit) { c.p[k].jn = jn; c.p[k].jt = jt; }
+      }
+    }
   }
   const real im = P.im, ii = P.ii;
   const real nx = c.nx, ny = c.ny, tx = ny, ty = -nx;
