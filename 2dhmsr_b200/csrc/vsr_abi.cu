@@ -134,6 +134,11 @@ struct Bucket {
   size_t sbuf_bytes = 0;
   void* d_lbuf = nullptr;  // per-block contact lists
   size_t lbuf_bytes = 0;
+  // launch plan, fixed at upload (nothing in it depends on the stream): vsr_batch_run is one <<<>>> per bucket
+  std::vector<unsigned char> pblob;  // Params<real> by value
+  const void* kern = nullptr;
+  unsigned grid = 0, threads = 0;
+  size_t smem = 0;
 };
 
 }  // namespace
@@ -237,6 +242,26 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
   for (int i = 1; i < d->terrain_n; i++)
     if (d->terrain_xs[i] < d->terrain_xs[i - 1])
       return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted");  // Ground.java:55-58
+  {
+    // Capacity check instead of a run-time flag: a mass (a square of side mass_side_length, any rotation: an
+    // interval of at most its diagonal on the x axis) can overlap at most `most` ground polygons at once
+    // (Ground.java:61-79: one polygon per segment).  The device keeps MAXC constraints per mass, which covers
+    // every terrain Locomotion.createTerrain can generate (segments >= 1 wide; steppy risers 0.5 wide between
+    // treads >= 1 wide: at most 3); a profile that could need more is refused here, never truncated at run time.
+    const double diag = d->material.side_length * d->material.mass_side_length_ratio * std::sqrt(2.0) + 1e-9;
+    std::vector<double> lo, hi;  // non-degenerate segments
+    for (int i = 0; i + 1 < d->terrain_n; i++)
+      if (d->terrain_xs[i + 1] > d->terrain_xs[i]) { lo.push_back(d->terrain_xs[i]); hi.push_back(d->terrain_xs[i + 1]); }
+    int most = 0;
+    for (size_t i = 0; i < lo.size(); i++) {
+      size_t k = i;
+      while (k + 1 < lo.size() && lo[k + 1] <= hi[i] + diag) k++;
+      most = std::max(most, (int)(k - i + 1));
+    }
+    if (most > vsr::MAXC)
+      return fail(VSR_ERR_UNSUPPORTED, "ground profile too fine: a mass could touch " + std::to_string(most) +
+                                           " ground polygons at once, the device keeps " + std::to_string(vsr::MAXC));
+  }
   if (!d->params || !d->param_offsets) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
   if (d->controller_kind >= VSR_CTRL_DISTRIBUTED && (d->distributed_signals < 0 || d->distributed_signals > 4))
     return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: 0..4 signals per side are supported");
@@ -638,8 +663,20 @@ static void free_xfers(vsr_batch* b) {
   b->xfers.clear();
 }
 
+template <typename real>
+static int prepare_bucket(vsr_batch* b, Bucket& k);
+static int upload_impl(vsr_batch* b, int device, void* stream);
+
 extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
   if (!b) return fail(VSR_ERR_INVALID_ARGUMENT, "null batch");
+  const bool first = !b->uploaded;
+  const int rc = upload_impl(b, device, stream);
+  // a first upload that failed part-way leaves nothing behind: no leak, and a retry starts from scratch
+  if (rc != VSR_OK && first) free_device(b);
+  return rc;
+}
+
+static int upload_impl(vsr_batch* b, int device, void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -730,6 +767,9 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
         CUDA_TRY(cudaMalloc(&k.d_vtrace, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 2 * esz));
       }
     }
+    // kernel arguments, launch geometry, shared-memory carve-out and the contact arenas of every bucket
+    for (auto& k : b->buckets)
+      if ((rc = f64 ? prepare_bucket<double>(b, k) : prepare_bucket<float>(b, k))) return rc;
   }
   // the copies proper: every input of the episode, from pinned memory
   b->upload_bytes = 0;
@@ -750,8 +790,20 @@ extern "C" int vsr_batch_upload(vsr_batch* b, int device, void* stream) {
   return VSR_OK;
 }
 
+// Development knobs (block size, pool size, optional barriers): compiled in with -DVSR_TUNING only; the release
+// library reads no environment variable.
+static const char* tuning_env(const char* name) {
+#ifdef VSR_TUNING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
+// Everything of a launch that does not depend on the stream, done once at upload.
 template <typename real>
-static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
+static int prepare_bucket(vsr_batch* b, Bucket& k) {
   const vsr_batch_desc& d = b->desc;
   const vsr_settings& st = d.settings;
   const vsr_material& m = d.material;
@@ -820,7 +872,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   P.dist_nd = d.controller_kind == VSR_CTRL_DISTRIBUTED_ND ? 1 : 0;
   P.debug_robot = -1;
   P.debug_tick = -1;
-  if (const char* dbg = getenv("VSR_DEBUG")) {  // "robot:tick" (bucket index)
+  if (const char* dbg = tuning_env("VSR_DEBUG")) {  // "robot:tick" (bucket index)
     long dr = -1, dk = -1, de = -1;
     int got = sscanf(dbg, "%ld:%ld:%ld", &dr, &dk, &de);
     if (got >= 2) { P.debug_robot = dr; P.debug_tick = (int)dk; P.debug_tick_end = (int)(got == 3 ? de : dk); }
@@ -831,7 +883,7 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   int maxn = 1;
   for (int i = 0; i < k.shape.n_layers; i++) maxn = std::max(maxn, k.shape.neurons[i]);
   int per_robot = 2 * ((maxn + 3) & ~3);
-  int wpb_env = getenv("VSR_WPB") ? atoi(getenv("VSR_WPB")) : 0;
+  int wpb_env = tuning_env("VSR_WPB") ? atoi(tuning_env("VSR_WPB")) : 0;
   const long long groups_all = ((long long)k.robot_ids.size() + G - 1) / G;
   // Warps of a block walk the instruction stream together (see the barriers in the kernel), so
   // the more warps per block the better, up to the register-file limit of 12.  A batch that does
@@ -865,12 +917,12 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     const int scopes = blk ? 1 : wpb;
     cap = std::min<long long>(cap / scopes, blk ? (long long)VSR_ITEMS_PER_THREAD * threads : VSR_ITEMS_PER_THREAD * 32) / 4 * 4;
     // a big robot's block is small (2..4 warps): a modest pool leaves room for a second block on the SM
-    if (blk) cap = std::min<long long>(cap, getenv("VSR_BLK_POOL") ? atoll(getenv("VSR_BLK_POOL")) : 96);
-    if (const char* e = getenv("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
+    if (blk) cap = std::min<long long>(cap, tuning_env("VSR_BLK_POOL") ? atoll(tuning_env("VSR_BLK_POOL")) : 96);
+    if (const char* e = tuning_env("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
     P.pool_cap = (int)cap;
     smem += (size_t)cap * scopes * VSR_POOL_FIELDS * sizeof(real);
   }
-  P.sync_mode = getenv("VSR_SYNC") ? atoi(getenv("VSR_SYNC")) : (1 | 2 | 16 | 32 | 64 | 128);
+  P.sync_mode = tuning_env("VSR_SYNC") ? atoi(tuning_env("VSR_SYNC")) : (2 | 16 | 32 | 64);
   void (*kern)(const Params<real>) = nullptr;
   const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
 #define VSR_PICK(C)                                                                                  \
@@ -883,7 +935,9 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
   }
 #undef VSR_PICK
   P.ctrl = d.controller_kind;
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the attribute belongs to the kernel, not to the launch: buckets that share an instantiation ask for different
+  // sizes, so it is raised to the SM's limit once and for all (the carve-out follows each launch's actual size)
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int occ = 0, sms = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
@@ -919,8 +973,17 @@ static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
     }
     P.lbuf = (int*)k.d_lbuf;
   }
-  kern<<<(unsigned)grid, threads, smem, s>>>(P);
-  CUDA_TRY(cudaGetLastError());
+  k.pblob.assign(reinterpret_cast<const unsigned char*>(&P), reinterpret_cast<const unsigned char*>(&P) + sizeof P);
+  k.kern = reinterpret_cast<const void*>(kern);
+  k.grid = (unsigned)grid;
+  k.threads = (unsigned)threads;
+  k.smem = smem;
+  return VSR_OK;
+}
+
+static int launch_bucket(vsr_batch* b, Bucket& k, cudaStream_t s) {
+  void* args[1] = {k.pblob.data()};
+  CUDA_TRY(cudaLaunchKernel(k.kern, dim3(k.grid), dim3(k.threads), args, k.smem, s));
   b->last_launches++;
   return VSR_OK;
 }
@@ -935,7 +998,7 @@ extern "C" int vsr_batch_run(vsr_batch* b, void* stream) {
   const size_t nb = b->buckets.size();
   if (nb <= 1) {
     for (auto& k : b->buckets) {
-      int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, s) : launch_bucket<float>(b, k, s);
+      int rc = launch_bucket(b, k, s);
       if (rc) return rc;
     }
   } else {
@@ -961,7 +1024,7 @@ extern "C" int vsr_batch_run(vsr_batch* b, void* stream) {
     for (size_t q = 0; q < nb; q++) {
       Bucket& k = b->buckets[order[q]];
       cudaStream_t ss = b->side_streams[q % ns];
-      int rc = b->precision == VSR_PRECISION_F64 ? launch_bucket<double>(b, k, ss) : launch_bucket<float>(b, k, ss);
+      int rc = launch_bucket(b, k, ss);
       if (rc) return rc;
     }
     for (size_t i = 0; i < ns; i++) {

@@ -45,7 +45,7 @@ namespace vsr {
 constexpr int MAX_VOX = 128;   // voxels per robot (<= 32: robots share a warp; else one block per robot)
 constexpr int MAX_SENS = 16;   // sensors per voxel (uniformAll-*: all 15 predefined ones)
 constexpr int MAX_READ = 24;   // readings per voxel (uniformAll-*: 21)
-constexpr int MAXC = 2;        // simultaneous ground constraints per mass
+constexpr int MAXC = 3;        // simultaneous ground constraints per mass (vsr_batch_create rejects terrains that could need more)
 constexpr int MAX_LAYERS = 6;  // MLP layers (input + hidden + output)
 #define VSR_DIST_WIDTH 40      // DistributedSensing: widest layer of a voxel's MLP (24 readings + 4 x 4 signals = 40 inputs)
 constexpr int MAX_WINDOWS = 2; // distinct aggregator intervals per shape
@@ -55,7 +55,9 @@ enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2, SENSOR_ANGL
              SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7, SENSOR_CRUMPLING = 8,
              SENSOR_CONTROL_POWER = 9, SENSOR_LIDAR = 10 };
 enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
-enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2 };
+// vsr_result.status bits (include/vsr_b200.h): the three capacity bits mean that constraints were DROPPED for
+// this robot (its result is not the reference's physics)
+enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2, STATUS_PAIR_OVERFLOW = 4, STATUS_LEVEL_OVERFLOW = 8 };
 
 struct SensorDev {
   int8_t base, axes, rotated, agg, soft, win, ch, dim;
@@ -144,8 +146,10 @@ struct Params {
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
-  int sync_mode;         // lockstep barriers (code locality only): 1 per tick, 2 per velocity iteration, 8 inside it,
-                         // 16 after the spring init, 32 after the velocity loop, 64 after the position loop, 128 after detection
+  int sync_mode;         // optional lockstep barriers (code locality only): 2 per velocity iteration, 8 inside it,
+                         // 16 after the spring init, 32 after the velocity loop, 64 after the position loop.
+                         // The barriers at the top of a tick and before Robot.act are unconditional: they also
+                         // separate the phases that share the block-wide scratch `aux`.
   long long debug_robot; // bucket index of a robot whose manifolds are printed (-1 = off)
   int debug_tick, debug_tick_end;
 };
@@ -1088,7 +1092,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
-#define VSR_ITEMS_PER_THREAD 16
+#define VSR_ITEMS_PER_THREAD 20
 static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list capacity");
 #endif
 #ifndef VSR_MIN_BLOCKS
@@ -1261,7 +1265,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     // begins with detect() -- contacts that exist at the placement (a robot developed next to a wall,
     // DevoLocomotion.java) are solved from the first step on
     for (int tick = -1; tick < P.n_ticks; tick++) {
-      if (sync_mode & 1) __syncthreads();
+      // REQUIRED barrier (not only code locality): `aux` aliases the controller staging of the whole block
+      // (stage_blk), so the position-pass / broadphase scratch of one warp lands in regions other warps use
+      // for their MLP activations and first/last-tick sums; this barrier and the one before Robot.act
+      // separate those phases block-wide.
+      __syncthreads();
       if (tick >= 0) {
       // =========================== World.step(1) ===========================
       // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
@@ -1770,7 +1778,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
                 for (int q = 0; q < VSR_MAX_CAND; q++)
                   if (q == n_cand) cand[q] = code;
-                if (n_cand == VSR_MAX_CAND) status |= STATUS_CONTACT_OVERFLOW;
+                if (n_cand == VSR_MAX_CAND) status |= STATUS_PAIR_OVERFLOW;
                 else n_cand++;
               }
             }
@@ -1875,7 +1883,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             int lv = ca > cb2 ? ca : cb2;
             cnt[ia] = (real)(lv + 1);
             cnt[ib] = (real)(lv + 1);
-            if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_CONTACT_OVERFLOW; }
+            if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_LEVEL_OVERFLOW; }
             lvpack |= (unsigned long long)lv << (8 * sl);
           }
           SSYNC()
@@ -1940,7 +1948,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       }
 
       // =========================== Robot.act(t) ===========================
-      if (sync_mode & 128) __syncthreads();
+      __syncthreads();  // REQUIRED: detection's use of `aux` ends here, the controllers' staging begins (see the tick's top)
       if (tick < 0) continue;
       // ---- Voxel.act: energies; geometry shared by the sensors
       const real* s4 = sn_;

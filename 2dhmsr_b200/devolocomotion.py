@@ -72,7 +72,12 @@ class DevoLocomotion:
             db.upload(device).run()
             res, box = db.results(), db.final_bbox()
             traj = [db.trajectory(i) for i in range(len(robots))] if trajectories else None
-        return res, box, traj
+            trace = [db.voxel_trace(i) for i in range(len(robots))] if trajectories else None
+        bad = np.flatnonzero(res["status"] != 0)
+        if bad.size:  # truncated physics or a non-finite state must not become a silent Outcome
+            raise RuntimeError(f"stage at t={t_start}: status {res['status'][bad[0]]} for robot {int(bad[0])} "
+                               "(1 = non-finite state, 2 = contact capacity exceeded; see include/vsr_b200.h)")
+        return res, box, traj, trace
 
 
 class TimeBasedDevoLocomotion(DevoLocomotion):
@@ -114,7 +119,7 @@ class TimeBasedDevoLocomotion(DevoLocomotion):
             ticks = tick_times(t_end, dt, t)
             if len(ticks) == 0:
                 continue
-            res, box, _ = self._stage(robots, places, t, t_end, device, precision)
+            res, box, _, _ = self._stage(robots, places, t, t_end, device, precision)
             t = float(ticks[-1])
             for i in range(len(sols)):
                 outs[i].add_devo_stage_outcome(DevoStageOutcome(robots[i], Outcome(res[i])))
@@ -141,15 +146,15 @@ class DistanceBasedDevoLocomotion(DevoLocomotion):
         place = self.initial_placement
         out = DevoOutcome()
         t = 0.0
+        stage_x = place                       # :109 robot.boundingBox().min().x() of the first robot
         while t < self.max_t:
-            stage_t, stage_x = t, place
+            stage_t = t
             # run until the stage's time limit (one update past it ends the task) or maxT
             t_end = min(self.max_t, stage_t + self.stage_max_t + dt)
             ticks = tick_times(t_end, dt, t)
-            res, box, traj = self._stage([robot], [place], t, t_end, device, precision, trajectories=True)
+            res, box, traj, trace = self._stage([robot], [place], t, t_end, device, precision, trajectories=True)
             mat = next(v for v in robot.get_voxels().values() if v is not None).material
-            trace = np.zeros((len(ticks), traj[0].shape[1] // 4, 2))
-            obs = build_observations(robot.get_voxels(), traj[0], trace, ticks, self.ground_profile, mat.side_length,
+            obs = build_observations(robot.get_voxels(), traj[0], trace[0], ticks, self.ground_profile, mat.side_length,
                                      mat.mass_side_length_ratio * mat.side_length)
             keys = list(obs)
             minx = [min(p.bounding_box().min[0] for p in o.voxel_polies.values() if p is not None) for o in obs.values()]
@@ -167,6 +172,11 @@ class DistanceBasedDevoLocomotion(DevoLocomotion):
                 out.add_devo_stage_outcome(DevoStageOutcome(robot, Outcome(observations=stage_obs)))
                 place = minx[cut - 1]
                 robot = solution(robot)
+                # :145 stageX = robot.center().x() of the developed robot, placed with its bounding box's min x at
+                # `place`: Robot.center = the mean of the voxel centres (Robot.java:123-125)
+                cells = [x for (x, _), v in robot.get_voxels() if v is not None]
+                side = next(v for v in robot.get_voxels().values() if v is not None).material.side_length
+                stage_x = place + side * (float(np.mean(cells)) + 0.5 - min(cells))
                 continue
             if stage_obs:   # :147-153: what is left when the loop ends
                 out.add_devo_stage_outcome(DevoStageOutcome(robot, Outcome(observations=stage_obs)))

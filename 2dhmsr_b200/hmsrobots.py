@@ -733,7 +733,6 @@ class RobotUtils:
         "vxy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.X, Velocity.Y), 0.5)),
         "vy": lambda x, y: SoftNormalization(Average(Velocity(True, 8.0, Velocity.Y), 0.5)),
     }
-    _OUT_OF_PATH: set = set()
 
     @staticmethod
     def lidar_side(x: float, y: float) -> str:  # :244-255
@@ -780,8 +779,6 @@ class RobotUtils:
 
     @staticmethod
     def sensor(name: str, x: int, y: int, body: Grid) -> Sensor:  # :249-263
-        if name in RobotUtils._OUT_OF_PATH:
-            raise NotImplementedError(f"sensor '{name}' is outside the accelerated hot path")
         w1, h1 = body.w - 1.0, body.h - 1.0
         nx = x / w1 if w1 != 0 else math.nan
         ny = y / h1 if h1 != 0 else math.nan
@@ -789,7 +786,7 @@ class RobotUtils:
 
     @staticmethod
     def build_sensorizing_function(name: str) -> Callable[[Grid], Grid]:  # :124-196
-        keys = "|".join(sorted(set(RobotUtils.PREDEFINED_SENSORS) | RobotUtils._OUT_OF_PATH))
+        keys = "|".join(sorted(RobotUtils.PREDEFINED_SENSORS))
         p = _params(rf"uniform-(?<sensors>({keys})(\+({keys}))*)-(?<noiseSigma>\d+(\.\d+)?)", name)
         if p is not None:
             sigma = float(p["noiseSigma"])
@@ -818,9 +815,6 @@ class RobotUtils:
         if p is not None:  # :177-189: every predefined sensor, TreeMap (sorted) order
             return RobotUtils.build_sensorizing_function(
                 "uniform-" + "+".join(sorted(RobotUtils.PREDEFINED_SENSORS)) + "-" + p["noiseSigma"])
-        for out in ():
-            if _params(out, name) is not None:
-                raise NotImplementedError(f"sensorizing function '{name}' is outside the accelerated hot path")
         raise ValueError(f"Unknown sensorizing function name: {name}")
 
 
@@ -890,6 +884,12 @@ class Outcome:
             rec, observations = None, rec
         self.rec = rec
         self.observations = dict(sorted(observations.items())) if observations is not None else None
+
+    def get_status(self) -> int:
+        """``vsr_result.status`` (include/vsr_b200.h, VSR_STATUS_*): 0 = a valid episode.  Not in the reference
+        (dyn4j has no contact capacity and lets NaN through); ``Locomotion.apply`` raises on a non-zero
+        status unless told otherwise."""
+        return 0 if self.rec is None else int(self.rec["status"])
 
     # ---- first / last observation
     def _ends(self):
@@ -1366,7 +1366,7 @@ class Locomotion:
                              precision, trajectory_robots, t_start, placements)
 
     def apply(self, robots, listener=None, device: int = 0, precision: int = A.VSR_PRECISION_F32,
-              observations: bool = False):
+              observations: bool = False, check_status: bool = True):
         """``Outcome apply(Robot[, SnapshotListener])`` (Locomotion.java:168-207) and its batched form
         ``List<Outcome> apply(List<Robot>)``: one kernel launch for all robots.
 
@@ -1386,6 +1386,12 @@ class Locomotion:
             res = db.results()
             dumps = [(db.trajectory(i), db.voxel_trace(i)) for i in range(len(rs))] if full else None
         wall = _time.time() - t0
+        bad = np.flatnonzero(res["status"] != 0)
+        if check_status and bad.size:
+            # truncated physics (contact capacity) or a non-finite state must not come back as a silent Outcome
+            raise RuntimeError(f"{bad.size} robot(s) ended with a non-zero status (first: robot {int(bad[0])}, status "
+                               f"{int(res['status'][bad[0]])}; bits: 1 non-finite, 2/4/8 contact capacity, see "
+                               "include/vsr_b200.h); pass check_status=False to get the flagged Outcomes")
         if not full:
             outs = [Outcome(res[i]) for i in range(len(rs))]
             return outs[0] if single else outs

@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+"""bench.py -- BASELINE.json's metric on BASELINE.json's configs.
 
 metric : voxel-steps/s (sum over robots of voxels x ticks, per second)
-config : configs[1] = 4096 x biped-4x3, random-phase PhaseSin, uniform-ax+t-0 sensors, flat
-         terrain, 20 s episode (1200 ticks), default Settings -- per GPU (weak scaling).
-step   : one pass of the hot path over the batch = the whole batched episode (one kernel launch).
+value  : configs[1] = 4096 x biped-4x3, random-phase PhaseSin, uniform-ax+t-0 sensors, flat terrain, 20 s
+         episode (1200 ticks), default Settings -- per GPU (weak scaling), fp32 (the reference computes in
+         double: the `fp64` sub-record is the same workload on the fp64 build of the same kernel).
+step   : one pass of the hot path over the batch = the whole batched episode (one kernel launch per shape class).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--extra all|none]
     torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, NCCL)
 
 `value`  : device-resident throughput (CUDA events on the launch stream, L2 flushed between steps).
 `e2e`    : the same metric through the C ABI with HOST buffers: upload (H2D) + run + results (D2H)
            per step, plus the final NCCL gather of the result records when N > 1.
+`extra_configs`: configs[2] (65 536 MLP worms, hidden [] and [21, 21]), configs[3] (65 536 mixed shapes on hilly
+           terrain) and the per-GPU share of configs[4] (131 072 bipeds per GPU: `--gpus 8` is the 1 M-robot sweep
+           with the NCCL gather), each with its own value / e2e / roofline fraction on its own algorithmic bytes;
+           1 warm-up + 2 timed steps each, whatever --steps says.
 `--impl reference`: the CPU restatement of the dyn4j path (oracle/, "port": the Java reference
            cannot run in this image), all host threads, bounded sample of the same workload.
 """
@@ -20,7 +25,6 @@ from __future__ import annotations
 import argparse
 import importlib
 import json
-import math
 import os
 import subprocess
 import sys
@@ -32,26 +36,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_VOXEL_STEP = 405.6  # 192 bodies + 144 spring impulses + 57.6 welds + 4 control + 8 sensors
 N_ROBOTS = 4096
-SHAPE, SENSORS, TERRAIN, FINAL_T = "biped-4x3", "uniform-ax+t-0", "flat", 20.0
 CONFIG = {
     "workload": "configs[1]: 4096 x biped-4x3, PhaseSin f=1 A=1 phases~U[0,2pi) (numpy PCG64 seed 0), "
-                "uniform-ax+t-0 sensors, flat terrain, 20 s = 1200 ticks, default Settings (ground and intra-robot contacts); per GPU",
+                "uniform-ax+t-0 sensors, flat terrain, 20 s = 1200 ticks, default Settings (ground and intra-robot "
+                "contacts); per GPU; fp32 (the reference's arithmetic is IEEE double: see the fp64 sub-record)",
     "robots_per_gpu": N_ROBOTS, "voxels_per_robot": 10, "ticks": 1200, "precision": "fp32",
     "l2": "flushed between timed steps (256 MiB write)", "parallelism": "robots sharded, no per-step communication",
 }
-
-
-def build_batch(H, n, seed):
-    rng = np.random.default_rng(seed)
-    body = H.RobotUtils.build_sensorizing_function(SENSORS)(H.RobotUtils.build_shape(SHAPE))
-    robots = []
-    for _ in range(n):
-        ph = rng.uniform(0, 2 * math.pi, size=(body.w, body.h))
-        robots.append(H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(body.w, body.h, lambda x, y: float(ph[x, y]))), body))
-    loco = H.Locomotion(FINAL_T, H.Locomotion.create_terrain(TERRAIN), H.Settings())
-    return loco, robots
+EXTRA_STEPS = 2
 
 
 class ClockSampler:
@@ -87,10 +80,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_run(H, n_robots, seed, threads):
-    """Time the oracle (C restatement of the dyn4j path) on `n_robots` of the same workload."""
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(n_robots, seed, threads):
+    """Time the oracle (C restatement of the dyn4j path) on `n_robots` of configs[1]."""
+    import workloads
     from oracle import oracle
-    loco, robots = build_batch(H, n_robots, seed)
+    loco, robots = workloads.config2(n_robots, seed)
     bd = loco.compile(robots)
     t0 = time.perf_counter()
     oracle.run(bd, n_threads=threads)
@@ -98,47 +93,140 @@ def cpu_port_run(H, n_robots, seed, threads):
     return bd.voxel_steps() / dt, dt
 
 
-def cpu_baseline(H, budget_s=12.0):
+def cpu_baseline(budget_s=12.0):
     threads = os.cpu_count() or 1
-    _, pilot = cpu_port_run(H, threads, 123, threads)           # one robot per thread
-    n = int(max(threads, min(4096, threads * max(1, round(budget_s / max(pilot, 1e-3))))))
-    v, dt = cpu_port_run(H, n, 0, threads)
-    return {"value": v, "unit": "voxel-steps/s", "cores": threads, "kind": "port",
+    _, pilot = cpu_port_run(threads, 123, threads)           # one robot per thread
+    n = int(max(threads, min(N_ROBOTS, threads * max(1, round(budget_s / max(pilot, 1e-3))))))
+    v, dt = cpu_port_run(n, 0, threads)
+    return {"value": v, "unit": "voxel-steps/s", "cores": threads, "value_per_core": v / threads, "kind": "port",
             "sample": f"{n} robots of the same workload (full 1200-tick episodes), one robot per thread, "
                       f"{threads} threads, {dt:.1f} s; fp64 C restatement of the dyn4j path -- not the JVM"}
 
 
 def reference_arm(args):
-    """--impl reference: the CPU port on all host threads, bounded sample per step."""
+    """--impl reference: the CPU port on all host threads; a step = the whole 4096-robot batch when the host gets
+    through it in <= 15 s, else a bounded sample of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    H = importlib.import_module("2dhmsr_b200")
+    import workloads
+    from oracle import oracle
     threads = os.cpu_count() or 1
-    _, pilot = cpu_port_run(H, threads, 123, threads)
-    per_step = int(max(threads, min(N_ROBOTS, threads * max(1, round(8.0 / max(pilot, 1e-3))))))
-    for _ in range(args.warmup):
-        cpu_port_run(H, threads, 5, threads)
+    _, pilot = cpu_port_run(threads, 123, threads)
+    rate = threads / max(pilot, 1e-3)                       # robots per second
+    total_budget = 150.0                                    # the whole --steps K run, seconds
+    per_step = int(min(N_ROBOTS, max(threads, rate * min(15.0, total_budget / max(1, args.steps)))))
+    per_step = max(threads, per_step // threads * threads)
+    for _ in range(min(args.warmup, 2)):
+        cpu_port_run(threads, 5, threads)
     t, vs = 0.0, 0
     for k in range(args.steps):
-        loco, robots = build_batch(H, per_step, k)
+        loco, robots = workloads.config2(per_step, k)
         bd = loco.compile(robots)
-        from oracle import oracle
         t0 = time.perf_counter()
         oracle.run(bd, n_threads=threads)
         t += time.perf_counter() - t0
         vs += bd.voxel_steps()
     value = vs / t
-    sample = (f"{per_step} robots x 1200 ticks per step (bounded sample of the 4096-robot batch), one robot per "
-              f"thread, {threads} threads; fp64 C restatement of the dyn4j path -- not the JVM")
+    what = "the whole 4096-robot batch" if per_step == N_ROBOTS else f"bounded sample of the {N_ROBOTS}-robot batch"
+    sample = (f"{per_step} robots x 1200 ticks per step ({what}), one robot per thread, {threads} threads; "
+              "fp64 C restatement of the dyn4j path -- not the JVM")
     print(json.dumps({
         "impl": "reference", "metric": "voxel-steps/s", "value": value, "unit": "voxel-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
-        "cpu_baseline": {"value": value, "unit": "voxel-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxel-steps/s", "cores": threads, "value_per_core": value / threads,
+                         "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class Runner:
+    """One workload on this rank's GPU: device-resident and end-to-end timings of whole-episode steps."""
+
+    def __init__(self, H, sharding, torch, dist, dev, local, world, flush):
+        self.H, self.sharding, self.torch, self.dist = H, sharding, torch, dist
+        self.dev, self.local, self.world, self.flush = dev, local, world, flush
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def _run_timed(self, db):
+        torch, stream = self.torch, self.stream
+        with torch.cuda.stream(stream):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            db.run(stream.cuda_stream)
+            ev1.record(stream)
+        return ev0, ev1
+
+    def _finish(self, db, n_total):
+        """Read the step's result back: D2H of the Outcome records (N = 1) or the NCCL gather of every rank's
+        records straight from the device result buffers (N > 1)."""
+        if self.world > 1:
+            self.torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+            return self.sharding.gather_results(self.sharding.device_records(db, self.dev), n_total)
+        return db.results()
+
+    def measure(self, bd, n_total, steps, warmup, separate=True):
+        """Returns dict(ms=[...] device-resident per step, e2e_s=[...] per step, launches, h2d, res).
+        separate=True: K device-resident steps, then K end-to-end steps (the headline config).
+        separate=False: every timed step is an end-to-end step whose kernel is also bracketed by CUDA events."""
+        H, torch, sp = self.H, self.torch, self.stream.cuda_stream
+        db = H.DeviceBatch(bd)
+        try:
+            db.upload(self.local, sp)
+            for _ in range(warmup):
+                db.run(sp)
+                db.results()
+            ms, e2e_s, launches = [], [], 0
+            if separate:
+                self.barrier()
+                for _ in range(steps):
+                    self.flush.fill_(1)                       # evict L2 between timed steps
+                    torch.cuda.synchronize(self.dev)
+                    ev0, ev1 = self._run_timed(db)
+                    ev1.synchronize()
+                    ms.append(ev0.elapsed_time(ev1))
+                    launches += db.last_launches()
+                self.barrier()
+                db.upload(self.local, sp)                    # untimed: NCCL communicator / pinned buffers
+                db.run(sp)
+                self._finish(db, n_total)
+            for _ in range(steps):
+                self.flush.fill_(1)
+                self.barrier()
+                t0 = time.perf_counter()
+                db.upload(self.local, sp)                    # H2D of every input of the episode (pinned staging)
+                ev0, ev1 = self._run_timed(db)
+                res = self._finish(db, n_total)
+                torch.cuda.synchronize(self.dev)
+                e2e_s.append(time.perf_counter() - t0)
+                if not separate:
+                    ms.append(ev0.elapsed_time(ev1))
+                launches += db.last_launches()
+            self.barrier()
+            h2d = int(db.lib.vsr_batch_upload_bytes(db.h))
+        finally:
+            db.close()
+        return {"ms": ms, "e2e_s": e2e_s, "launches": launches, "h2d": h2d, "res": res}
+
+    def reduce(self, m):
+        """Max over ranks of the summed times (the contract), plus the per-rank lists."""
+        torch, dist = self.torch, self.dist
+        t = torch.tensor([sum(m["ms"]), sum(m["e2e_s"])], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            allr = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(allr, t)
+            per = torch.stack(allr).cpu().numpy()
+        else:
+            per = t.cpu().numpy()[None]
+        return float(per[:, 0].max()), float(per[:, 1].max()), per
 
 
 def main():
@@ -148,6 +236,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--robots", type=int, default=N_ROBOTS, help="robots per GPU (default: the BASELINE config)")
+    ap.add_argument("--extra", default="all", choices=["all", "none"], help="also run configs[2..4] (extra_configs)")
+    ap.add_argument("--extra-scale", type=float, default=1.0, help="scale the extra configs' robot counts (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -156,6 +246,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import workloads
     H = importlib.import_module("2dhmsr_b200")
     sharding = importlib.import_module("2dhmsr_b200.sharding")
     rank = int(os.environ.get("RANK", "0"))
@@ -165,111 +256,129 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
-    n_total = args.robots * world                       # weak scaling: fixed work per GPU
-    b, e = sharding.shard_range(n_total, rank, world)
-    loco, robots = build_batch(H, e - b, seed=rank)     # every rank its own slice of the population
-    t0 = time.perf_counter()
-    bd = loco.compile(robots)
-    db = H.DeviceBatch(bd)
-    t_compile = time.perf_counter() - t0
-    voxel_steps_local = bd.voxel_steps()
-    stream = torch.cuda.Stream(device=dev)
-    sp = stream.cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    R = Runner(H, sharding, torch, dist, dev, local, world, flush)
+    warmup = max(args.warmup, 3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    db.upload(local, sp)
-    for _ in range(max(args.warmup, 3)):
-        db.run(sp)
-        db.results()
-
+    # ---- the headline: configs[1], every rank its own 4096-robot slice of the population (weak scaling)
+    n_total = args.robots * world
+    b, e = sharding.shard_range(n_total, rank, world)
+    t0 = time.perf_counter()
+    loco, robots = workloads.config2(e - b, seed=rank)
+    bd = loco.compile(robots)
+    t_compile = time.perf_counter() - t0
+    vs_local = bd.voxel_steps()
+    bytes_vs = workloads.algorithmic_bytes_per_voxel_step(robots[:1])
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- device-resident: inputs already in HBM, K launches timed with CUDA events on the stream
-    barrier()
-    launches, ms = 0, 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)                                   # evict L2 between timed steps
-        torch.cuda.synchronize(dev)
-        with torch.cuda.stream(stream):
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(stream)
-            db.run(sp)
-            ev1.record(stream)
-        ev1.synchronize()
-        ms += ev0.elapsed_time(ev1)
-        launches += db.last_launches()
-    barrier()
-    # ---- end to end through the C ABI: host buffers -> H2D -> run -> D2H (+ final gather)
-    def e2e_step():
-        db.upload(local, sp)                      # H2D of every input of the episode (pinned staging)
-        db.run(sp)
-        if world > 1:                             # NCCL all_gather straight from the result buffer
-            torch.cuda.current_stream(dev).wait_stream(stream)
-            return sharding.gather_results(sharding.device_records(db, dev), n_total)
-        return db.results()                       # D2H of the Outcome records
-
-    e2e_step()                                    # untimed: NCCL communicator / pinned buffers
-    h2d = None
-    t_e2e = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        barrier()
-        t0 = time.perf_counter()
-        res = e2e_step()
-        torch.cuda.synchronize(dev)
-        t_e2e += time.perf_counter() - t0
-        launches += db.last_launches()
-        h2d = int(db.lib.vsr_batch_upload_bytes(db.h))
-    barrier()
+    m = R.measure(bd, n_total, args.steps, warmup, separate=True)
     clocks = sampler.stop()
+    res = m["res"]
     assert res.shape[0] == n_total and np.all(res["status"] == 0)
-
-    t = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
-    ms_max, e2e_max = float(t[0]), float(t[1])
-    total_vs = voxel_steps_local * world
+    ms_max, e2e_max, per = R.reduce(m)
+    total_vs = vs_local * world
     value = total_vs * args.steps / (ms_max / 1e3)
     e2e_value = total_vs * args.steps / e2e_max
+    out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         launch_s = (ms_max / 1e3) / args.steps
-        achieved = BYTES_PER_VOXEL_STEP * voxel_steps_local / launch_s / 1e9
-        traffic = None
+        achieved = bytes_vs * vs_local / launch_s / 1e9
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: " + tj.get("source", "profiles/traffic.json") + " (an ncu --set full capture; not measured in this run)"
         except Exception:
             pass
         out = {
             "metric": "voxel-steps/s", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(CONFIG, robots_per_gpu=args.robots, compile_s=round(t_compile, 3)),
-            "e2e": {"value": e2e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": h2d,
+            "config": dict(CONFIG, robots_per_gpu=args.robots),
+            "e2e": {"value": e2e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": m["h2d"],
                     "d2h_bytes_per_step": int((e - b) * 88)},
-            "gpu_launches": launches,
+            "gpu_launches": m["launches"],
             "clocks": clocks,
+            "compile_s": round(t_compile, 3),
+            "per_rank": {"ms_per_step": [float(x) / args.steps for x in per[:, 0]],
+                         "e2e_ms_per_step": [1e3 * float(x) / args.steps for x in per[:, 1]]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vsr_episode_kernel<float, PHASE_SIN, full>",
-                         "algorithmic_bytes_per_voxel_step": BYTES_PER_VOXEL_STEP, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "vsr_episode_kernel<float, PHASE_SIN, full>",
+                         "algorithmic_bytes_per_voxel_step": bytes_vs, "peak_source": peak_src,
                          "note": "per GPU; the path is FP32-issue/latency bound, not HBM bound (DESIGN.md)"},
         }
+
+    # ---- the same workload on the fp64 build of the kernel (the reference's arithmetic; the build the 1e-8 parity
+    #      tests run): 1 warm-up + 2 timed steps
+    bd64 = loco.compile(robots, precision=H.abi.VSR_PRECISION_F64)
+    m64 = R.measure(bd64, n_total, EXTRA_STEPS, 1, separate=False)
+    ms64, e64, _ = R.reduce(m64)
+    if rank == 0:
+        out["fp64"] = {"value": total_vs * EXTRA_STEPS / (ms64 / 1e3), "e2e": total_vs * EXTRA_STEPS / e64,
+                       "ms_per_step": ms64 / EXTRA_STEPS, "unit": "voxel-steps/s", "steps": EXTRA_STEPS,
+                       "status_nonzero": int((m64["res"]["status"] != 0).sum()),
+                       "note": "same workload and kernel source, real = double (the parity build)"}
+    del bd64
+
+    # ---- extra_configs
+    if args.extra == "all":
+        sc = args.extra_scale
+        n3, n4, n5 = int(65536 * sc), int(65536 * sc), int(131072 * sc)
+        specs = [
+            ("configs[2] hidden=[]", f"{n3} x worm-8x2 per GPU, CentralizedSensing MLP TANH 32->16 (528 weights), "
+             "uniform-ax+t-0, flat, 1200 ticks", lambda: workloads.config3(n3, (), seed=1 + 100 * rank), n3),
+            ("configs[2] hidden=[21,21]", f"{n3} x worm-8x2 per GPU, CentralizedSensing MLP TANH 32->21->21->16 "
+             "(1507 weights), uniform-ax+t-0, flat, 1200 ticks", lambda: workloads.config3(n3, (21, 21), seed=1 + 100 * rank), n3),
+            ("configs[3]", f"{n4} mixed biped/worm/box shapes up to 10x10 per GPU (full size is 262 144), PhaseSin, "
+             "uniform-t+vxy+a-0, hilly-1-10-0, 1200 ticks; one launch per shape class on 16 side streams",
+             lambda: workloads.config4(n4, seed=2 + 100 * rank), n4),
+            ("configs[4] per-GPU share", f"{n5} x biped-4x3 per GPU as configs[1] (8 GPUs = the 1 048 576-robot sweep), "
+             "NCCL all_gather of the vsr_result records inside e2e", lambda: workloads.config5_share(n5, rank), n5),
+        ]
+        extras = []
+        for name, desc, build, n_local in specs:
+            t0 = time.perf_counter()
+            lo, rb = build()
+            bdx = lo.compile(rb)
+            tc = time.perf_counter() - t0
+            bvs = workloads.algorithmic_bytes_per_voxel_step(rb)
+            vsx = bdx.voxel_steps()
+            del rb
+            mx = R.measure(bdx, n_local * world, EXTRA_STEPS, 1, separate=False)
+            msx, ex, perx = R.reduce(mx)
+            tv = torch.tensor([float(vsx)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv)
+            if rank == 0:
+                tot = float(tv[0])
+                ach = bvs * vsx / ((msx / 1e3) / EXTRA_STEPS) / 1e9
+                extras.append({
+                    "name": name, "workload": desc, "robots_per_gpu": n_local, "voxel_steps_per_step": tot,
+                    "value": tot * EXTRA_STEPS / (msx / 1e3), "ms_per_step": msx / EXTRA_STEPS, "steps": EXTRA_STEPS,
+                    "e2e": {"value": tot * EXTRA_STEPS / ex, "unit": "voxel-steps/s", "h2d_bytes_per_step": mx["h2d"],
+                            "d2h_bytes_per_step": int(n_local * 88)},
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_voxel_step": bvs},
+                    "status_nonzero": int((mx["res"]["status"] != 0).sum()), "gpu_launches": mx["launches"],
+                    "host_compile_s": round(tc, 2),
+                    "per_rank_ms_per_step": [float(x) / EXTRA_STEPS for x in perx[:, 0]],
+                })
+            del bdx
+        if rank == 0:
+            out["extra_configs"] = extras
+
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(H)
+            out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
-    db.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -230,8 +230,16 @@ typedef struct vsr_result {
   double area_ratio_energy_first, area_ratio_energy_last; /* sum over voxels  */
   double control_energy_first, control_energy_last;
   int32_t n_ticks;
-  int32_t status; /* 0 ok, 1 = non-finite state encountered */
+  int32_t status; /* 0 = ok; else a bit set (VSR_STATUS_*): the record is NOT a valid Outcome */
 } vsr_result;
+
+/* vsr_result.status bits.  The reference (dyn4j) has no contact capacity; the device keeps fixed-size
+   per-mass / per-voxel constraint lists, and a robot that ever needs more is FLAGGED, never silently
+   truncated: callers must treat a non-zero status as a failed episode (the host mirror raises).        */
+#define VSR_STATUS_NONFINITE 1        /* a non-finite centre was observed                                 */
+#define VSR_STATUS_CONTACT_OVERFLOW 2 /* a mass touched more ground polygons at once than the device keeps */
+#define VSR_STATUS_PAIR_OVERFLOW 4    /* a voxel had more mass-pair candidates in one tick than it keeps   */
+#define VSR_STATUS_LEVEL_OVERFLOW 8   /* a chain of dependent contact constraints exceeded 32 levels       */
 
 typedef struct vsr_batch vsr_batch;
 

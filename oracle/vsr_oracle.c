@@ -193,6 +193,12 @@ typedef struct {
   OWeld* welds;
   int* jorder; /* joint order: >=0 spring index, <0 -> weld index ~j */
   int nj;
+  /* VSR_ORACLE_ORDER_DFS: per-body joint lists in world insertion order (ConstraintGraphNode.joints) and the
+     island's contact order of the step */
+  int* adj_start; /* [nb + 1] */
+  int* adj;       /* joints of each body, encoded like jorder */
+  int* corder;    /* contact order of this step (indices into contacts), or NULL = detection order */
+  int cap_corder;
   OContact* contacts;
   int ncontacts, cap_contacts;
   OContact* old;
@@ -463,6 +469,30 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
     }
   }
 
+  /* per-body joint lists, in the order world.addJoint saw the joints (Voxel.java:216-221: a voxel's 18 springs;
+     Robot.java:81-88: then all welds): ConstraintGraphNode.joints of dyn4j */
+  r->adj_start = (int*)calloc((size_t)r->nb + 1, sizeof(int));
+  r->adj = (int*)malloc(sizeof(int) * (size_t)(2 * r->nj > 0 ? 2 * r->nj : 1));
+  r->corder = NULL;
+  r->cap_corder = 0;
+  {
+    for (int si = 0; si < r->ns; si++) { r->adj_start[r->springs[si].b1 + 1]++; r->adj_start[r->springs[si].b2 + 1]++; }
+    for (int w = 0; w < r->nw; w++) { r->adj_start[r->welds[w].b1 + 1]++; r->adj_start[r->welds[w].b2 + 1]++; }
+    for (int b = 0; b < r->nb; b++) r->adj_start[b + 1] += r->adj_start[b];
+    int* fill = (int*)calloc((size_t)r->nb + 1, sizeof(int));
+    for (int si = 0; si < r->ns; si++) {
+      int b1 = r->springs[si].b1, b2 = r->springs[si].b2;
+      r->adj[r->adj_start[b1] + fill[b1]++] = si;
+      r->adj[r->adj_start[b2] + fill[b2]++] = si;
+    }
+    for (int w = 0; w < r->nw; w++) {
+      int b1 = r->welds[w].b1, b2 = r->welds[w].b2;
+      r->adj[r->adj_start[b1] + fill[b1]++] = ~w;
+      r->adj[r->adj_start[b2] + fill[b2]++] = ~w;
+    }
+    free(fill);
+  }
+
   /* --- per voxel state: Voxel.reset, Voxel.java:640-651 --- */
   r->last_force = (double*)calloc((size_t)nv, sizeof(double));
   r->ar_energy = (double*)calloc((size_t)nv, sizeof(double));
@@ -548,6 +578,9 @@ static void robot_free(ORobot* r) {
   free(r->springs);
   free(r->welds);
   free(r->jorder);
+  free(r->adj_start);
+  free(r->adj);
+  free(r->corder);
   free(r->contacts);
   free(r->old);
   free(r->last_force);
@@ -1288,14 +1321,198 @@ static double contact_position(const vsr_settings* s, ORobot* r, OContact* c) {
 }
 
 /* ------------------------------------------------------------------ World.step(1) */
+
+/* ------------------------------------------------------------------ dyn4j C.7: continuous collision detection
+   World.solveTOI (dyn4j 4.2.1, recalled) with ContinuousDetectionMode.ALL: after the islands are solved every
+   dynamic body that is not a bullet is tested against the STATIC bodies it is not already in contact with
+   (body1.isInContact(body2): a contact constraint from the previous detect()); ConservativeAdvancement finds the
+   first time in [0, 1] of the step at which the two shapes come within distanceEpsilon (cbrt(ulp) ~ 6.06e-6) when
+   the body moves from its pose before the step by (v dt, w dt); the body is put back at that pose
+   (transform0.lerp) and TimeOfImpactSolver pushes it linearTolerance INTO the other shape so that the next
+   discrete detect() finds the pair.  Velocities are not touched. */
+typedef struct { double x, y, th; } OPose;
+
+/* distance between two disjoint convex polygons (closest points p1 on A, p2 on B); returns 0 when they overlap */
+static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p1x, double* p1y, double* p2x, double* p2y) {
+  double nx, ny, depth;
+  if (sat_penetration(A, B, 0, &nx, &ny, &depth)) return 0;
+  double best = INFINITY;
+  for (int pass = 0; pass < 2; pass++) {
+    const OPoly* P = pass ? B : A; /* vertices of P against the edges of Q */
+    const OPoly* Q = pass ? A : B;
+    for (int i = 0; i < P->n; i++)
+      for (int j = 0; j < Q->n; j++) {
+        int k = (j + 1) % Q->n;
+        double ex = Q->vx[k] - Q->vx[j], ey = Q->vy[k] - Q->vy[j];
+        double t = ((P->vx[i] - Q->vx[j]) * ex + (P->vy[i] - Q->vy[j]) * ey) / (ex * ex + ey * ey);
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        double qx = Q->vx[j] + t * ex, qy = Q->vy[j] + t * ey;
+        double dx = P->vx[i] - qx, dy = P->vy[i] - qy, dd = sqrt(dx * dx + dy * dy);
+        if (dd < best) {
+          best = dd;
+          if (pass) { *p1x = qx; *p1y = qy; *p2x = P->vx[i]; *p2y = P->vy[i]; }
+          else { *p1x = P->vx[i]; *p1y = P->vy[i]; *p2x = qx; *p2y = qy; }
+        }
+      }
+  }
+  *dist = best;
+  return 1;
+}
+
+static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
+  const vsr_batch_desc* d = R->d;
+  const double dist_eps = cbrt(EPS_E);
+  const double rmax = R->half * 1.4142135623730951; /* Rectangle.getRadius */
+  for (int b = 0; b < r->nb; b++) {
+    OBody* B = &r->bodies[b];
+    const double dpx = B->vx * dt, dpy = B->vy * dt, da = B->w * dt;
+    /* swept AABB of the mass */
+    OBody b0 = *B;
+    b0.x = pose0[b].x; b0.y = pose0[b].y; b0.th = pose0[b].th;
+    OPoly P0, P1;
+    mass_poly(&b0, R->half, &P0);
+    mass_poly(B, R->half, &P1);
+    double minx = INFINITY, maxx = -INFINITY, miny = INFINITY;
+    for (int i = 0; i < 4; i++) {
+      minx = fmin(minx, fmin(P0.vx[i], P1.vx[i]));
+      maxx = fmax(maxx, fmax(P0.vx[i], P1.vx[i]));
+      miny = fmin(miny, fmin(P0.vy[i], P1.vy[i]));
+    }
+    double t2 = 1.0, best_d = 0, bp1x = 0, bp1y = 0, bp2x = 0, bp2y = 0;
+    int found = 0;
+    for (int seg = 0; seg + 1 < d->terrain_n; seg++) {
+      if (d->terrain_xs[seg + 1] < minx || d->terrain_xs[seg] > maxx) continue;
+      if (!(d->terrain_xs[seg + 1] > d->terrain_xs[seg])) continue;
+      if (miny > fmax(d->terrain_ys[seg], d->terrain_ys[seg + 1])) continue;
+      int in_contact = 0; /* body1.isInContact(body2): constraints of the last detect() */
+      for (int i = 0; i < r->ncontacts && !in_contact; i++)
+        if (r->contacts[i].b1 == b && r->contacts[i].b2 < 0 && r->contacts[i].seg == seg) in_contact = 1;
+      if (in_contact) continue;
+      OPoly G;
+      ground_poly(d, R->base_y, seg, &G);
+      /* ConservativeAdvancement.getTimeOfImpact on [0, t2] */
+      OBody lb = b0;
+      OPoly A;
+      mass_poly(&lb, R->half, &A);
+      double dist, p1x, p1y, p2x, p2y;
+      if (!poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y)) continue; /* not separated at t = 0 */
+      double l = 0.0, l0 = 0.0;
+      int ok = 1, iter = 0;
+      if (dist >= dist_eps) {
+        const double amax = rmax * fabs(da);
+        if (sqrt(dpx * dpx + dpy * dpy) + amax == 0.0) continue;
+        while (dist > dist_eps && iter < 30) {
+          double nx = (p2x - p1x) / dist, ny = (p2y - p1y) / dist;
+          double drel = dpx * nx + dpy * ny + amax;
+          if (drel <= EPS_E) { ok = 0; break; }
+          double adv = dist / drel;
+          l += adv;
+          if (l < 0.0 || l > t2) { ok = 0; break; }
+          if (l <= l0) break;
+          l0 = l;
+          iter++;
+          lb.x = b0.x + dpx * l; lb.y = b0.y + dpy * l; lb.th = b0.th + da * l;
+          mass_poly(&lb, R->half, &A);
+          if (!poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y)) { /* overshoot: back up */
+            l -= adv;
+            lb.x = b0.x + dpx * l; lb.y = b0.y + dpy * l; lb.th = b0.th + da * l;
+            mass_poly(&lb, R->half, &A);
+            poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y);
+            break;
+          }
+        }
+      }
+      if (!ok) continue;
+      if (l < t2) { t2 = l; found = 1; best_d = dist; bp1x = p1x; bp1y = p1y; bp2x = p2x; bp2y = p2y; }
+    }
+    if (!found) continue;
+    /* body1.transform0.lerp(transform, t): the pose at the time of impact */
+    B->x = pose0[b].x + (B->x - pose0[b].x) * t2;
+    B->y = pose0[b].y + (B->y - pose0[b].y) * t2;
+    B->th = pose0[b].th + (B->th - pose0[b].th) * t2;
+    /* TimeOfImpactSolver.solve: push the pair linearTolerance into each other (static body 2) */
+    {
+      double nx = bp2x - bp1x, ny = bp2y - bp1y, nl = sqrt(nx * nx + ny * ny);
+      if (nl > 0) { nx /= nl; ny /= nl; }
+      double C = best_d - d->settings.linear_tolerance;
+      C = C < -d->settings.max_linear_correction ? -d->settings.max_linear_correction : (C > 0 ? 0 : C);
+      double r1x = bp1x - B->x, r1y = bp1y - B->y;
+      double rn1 = r1x * ny - r1y * nx;
+      double K = B->invM + B->invI * rn1 * rn1;
+      double imp = K > EPS_E ? -C / K : 0.0;
+      double Jx = nx * imp, Jy = ny * imp;
+      B->x += Jx * B->invM;
+      B->y += Jy * B->invM;
+      B->th += B->invI * (r1x * Jy - r1y * Jx);
+    }
+  }
+}
+
+/* ConstraintGraph.solve (dyn4j 4.2.1, recalled; Box2D's b2World::Solve): islands are built by a depth-first search
+   from the first dynamic body in world order that is not on an island yet.  A body popped from the (LIFO) stack is
+   added; its contact constraints are visited first, then its joints, each in the node's list order; a constraint not
+   yet on the island is appended to the island's list and its other body, if not seen, is pushed (static bodies are
+   added but not expanded).  The island then solves joints and contacts IN THAT DISCOVERY ORDER -- not in world
+   insertion order.  All masses of a robot hang together through springs and welds: one island per robot.
+   Contact lists per body are taken in detection order (dyn4j: the order the pairs first touched -- a broadphase
+   artefact that cannot be restated). */
+static void island_order(ORobot* r) {
+  int nb = r->nb, nc = r->ncontacts;
+  if (r->cap_corder < nc + 1) {
+    r->cap_corder = 2 * nc + 16;
+    r->corder = (int*)realloc(r->corder, sizeof(int) * (size_t)r->cap_corder);
+  }
+  unsigned char* on_body = (unsigned char*)calloc((size_t)nb + 1, 1);
+  unsigned char* on_joint = (unsigned char*)calloc((size_t)r->nj + 1, 1); /* springs [0, ns), welds ns + w */
+  unsigned char* on_con = (unsigned char*)calloc((size_t)nc + 1, 1);
+  int* stack = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+  int nj_out = 0, nc_out = 0;
+  for (int seed = 0; seed < nb; seed++) {
+    if (on_body[seed]) continue;
+    int sp = 0;
+    stack[sp++] = seed;
+    on_body[seed] = 1;
+    while (sp > 0) {
+      int b = stack[--sp];
+      for (int i = 0; i < nc; i++) { /* node.contactConstraints */
+        OContact* c = &r->contacts[i];
+        if (on_con[i] || (c->b1 != b && c->b2 != b)) continue;
+        on_con[i] = 1;
+        r->corder[nc_out++] = i;
+        int other = c->b1 == b ? c->b2 : c->b1;
+        if (other >= 0 && !on_body[other]) { stack[sp++] = other; on_body[other] = 1; }
+      }
+      for (int q = r->adj_start[b]; q < r->adj_start[b + 1]; q++) { /* node.joints */
+        int j = r->adj[q];
+        int slot = j >= 0 ? j : r->ns + (~j);
+        if (on_joint[slot]) continue;
+        on_joint[slot] = 1;
+        r->jorder[nj_out++] = j;
+        int b1 = j >= 0 ? r->springs[j].b1 : r->welds[~j].b1, b2 = j >= 0 ? r->springs[j].b2 : r->welds[~j].b2;
+        int other = b1 == b ? b2 : b1;
+        if (!on_body[other]) { stack[sp++] = other; on_body[other] = 1; }
+      }
+    }
+  }
+  free(on_body); free(on_joint); free(on_con); free(stack);
+}
+
 static int world_step(ORun* R, ORobot* r, double dt) {
   const vsr_batch_desc* d = R->d;
   const vsr_settings* s = &d->settings;
+  const int dfs = R->o.order == VSR_ORACLE_ORDER_DFS;
+  if (dfs) island_order(r);
+  OPose* pose0 = NULL;
+  if (R->o.ccd) { /* body.transform0 = body.transform, before the islands are solved */
+    pose0 = (OPose*)malloc(sizeof(OPose) * (size_t)r->nb);
+    for (int b = 0; b < r->nb; b++) { pose0[b].x = r->bodies[b].x; pose0[b].y = r->bodies[b].y; pose0[b].th = r->bodies[b].th; }
+  }
+#define CON(i) (&r->contacts[dfs ? r->corder[i] : (i)])
   /* Island.solve (dyn4j): integrate velocities */
   for (int b = 0; b < r->nb; b++) integrate_velocity(d, &r->bodies[b], dt);
   /* solver.initialize(contacts): all masses/biases first, then all warm starts */
-  for (int i = 0; i < r->ncontacts; i++) contact_init(s, r, &r->contacts[i]);
-  for (int i = 0; i < r->ncontacts; i++) contact_warm(r, &r->contacts[i]);
+  for (int i = 0; i < r->ncontacts; i++) contact_init(s, r, CON(i));
+  for (int i = 0; i < r->ncontacts; i++) contact_warm(r, CON(i));
   /* joints: initializeConstraints (+ warm start) */
   for (int i = 0; i < r->nj; i++) {
     int j = r->jorder[i];
@@ -1309,7 +1526,7 @@ static int world_step(ORun* R, ORobot* r, double dt) {
       if (j >= 0) spring_solve(r, &r->springs[j]);
       else weld_solve(r, &r->welds[~j]);
     }
-    for (int i = 0; i < r->ncontacts; i++) contact_solve(r, &r->contacts[i]);
+    for (int i = 0; i < r->ncontacts; i++) contact_solve(r, CON(i));
   }
   for (int b = 0; b < r->nb; b++) integrate_position(s, &r->bodies[b], dt);
   /* position iterations: contacts, then joints; stop when both report solved */
@@ -1318,7 +1535,7 @@ static int world_step(ORun* R, ORobot* r, double dt) {
     iters++;
     double minSep = 0.0;
     for (int i = 0; i < r->ncontacts; i++) {
-      double ms = contact_position(s, r, &r->contacts[i]);
+      double ms = contact_position(s, r, CON(i));
       if (ms < minSep) minSep = ms;
     }
     int contactsSolved = minSep >= -3.0 * s->linear_tolerance;
@@ -1330,6 +1547,11 @@ static int world_step(ORun* R, ORobot* r, double dt) {
       jointsSolved = jointsSolved && ok;
     }
     if (contactsSolved && jointsSolved) break;
+  }
+#undef CON
+  if (pose0) {
+    ccd_pass(R, r, pose0, dt);
+    free(pose0);
   }
   /* new contacts for Touch and for the next step */
   detect(R, r);

@@ -31,6 +31,10 @@ extern "C" {
 #define VSR_ORACLE_ORDER_SHUFFLED 2  /* seeded random permutation of the joints (measures
                                         how much the Gauss-Seidel order matters)             */
 
+#define VSR_ORACLE_ORDER_DFS 3       /* dyn4j's own: island discovery order of ConstraintGraph.solve (depth-first
+                                        from the first body, contacts before joints at every node, LIFO stack),
+                                        recomputed every step because mass-mass contacts change the walk     */
+
 typedef struct vsr_oracle_opts {
   int32_t order;        /* VSR_ORACLE_ORDER_* */
   uint32_t seed;        /* SHUFFLED */
@@ -39,7 +43,7 @@ typedef struct vsr_oracle_opts {
   size_t robot_begin;   /* run robots [robot_begin, robot_end) ; end==0 -> n_robots */
   size_t robot_end;
   int32_t self_collision; /* 1: also solve mass-mass contacts inside a robot (Voxel.java:178-185,474) */
-  int32_t reserved;
+  int32_t ccd;          /* 1: dyn4j's time-of-impact pass for masses about to touch the ground (C.7) */
 } vsr_oracle_opts;
 
 /* Optional per-tick probes; any pointer may be NULL.  Row r is robot
