@@ -37,8 +37,9 @@
 #define VSR_TIE_EPS_F32 1e-6f
 #endif
 
-// candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts
-#define VSR_MAX_CAND 8
+// candidate mass pairs per thread and tick that pass the broadphase of the intra-robot contacts (8 overflowed for
+// 7 of 131 072 robots of BASELINE config 4: tall bipeds that fold up; 16 has not been seen to)
+#define VSR_MAX_CAND 16
 
 namespace vsr {
 
@@ -939,13 +940,13 @@ __device__ __noinline__ int self_pair(const CPar<real> P, real half, real ax, re
 }
 
 // ---------------------------------------------------------------- the block's constraint list
-// An item: (owner thread << 7) | kind-specific bits | kind.  Ground (kind 0): (mass * 2 + buffer)
-// << 4 | index << 1 -> the owner's CBody.  Intra-robot (kind 1): list << 4 | index << 1 -> the
+// An item: (owner thread << 8) | kind-specific bits | kind.  Ground (kind 0): (mass * 2 + buffer)
+// << 5 | index << 1 -> the owner's CBody.  Intra-robot (kind 1): list << 5 | index << 1 -> the
 // owner's SList.
-#define VSR_ITEM_OWNER(code) ((code) >> 7)
+#define VSR_ITEM_OWNER(code) ((code) >> 8)
 template <typename real>
 __device__ __forceinline__ SCon<real>& item_record(CBody<real>* blk_cb, SList<real>* blk_sl, int code) {
-  const int ow = VSR_ITEM_OWNER(code), sub = (code >> 4) & 7, idx = (code >> 1) & 7;
+  const int ow = VSR_ITEM_OWNER(code), sub = (code >> 5) & 7, idx = (code >> 1) & 15;
   SCon<real>* g = blk_cb[(size_t)ow * 8 + sub].c + idx;
   SCon<real>* s = blk_sl[(size_t)ow * 2 + (sub & 1)].c + idx;
   return *((code & 1) ? s : g);
@@ -1092,7 +1093,7 @@ __device__ __forceinline__ void weld_solve33(real cx, real cy, real cz, real r2x
 // reals of shared memory reserved for the header of the block's contact list
 #define VSR_LHD_REALS 80
 #define VSR_MAX_LEVELS 32
-#define VSR_ITEMS_PER_THREAD 20
+#define VSR_ITEMS_PER_THREAD 28
 static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list capacity");
 #endif
 #ifndef VSR_MIN_BLOCKS
@@ -1231,10 +1232,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     for (int k = 0; k < 4; k++) hint[k] = 0;
     unsigned cmask = 0;  // masses with ground constraints
     // intra-robot contacts owned by this thread: two lists (this step's / the previous step's) and,
-    // packed in one word, the mask of the slots that hold a constraint (bits 0-7) and the current list (31)
+    // packed in one word, the mask of the slots that hold a constraint (bits 0-15) and the current list (31)
     SList<real>* const sbase = reinterpret_cast<SList<real>*>(P.sbuf) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     unsigned sst = 0;
-#define S_MASK (sst & 0xffu)
+#define S_MASK (sst & 0xffffu)
 #define S_CUR (sbase + (sst >> 31))
 #define VSR_MTK(k, c) (((k) * 4 + (c)) * MTS + mt_t)
 #define VSR_MT_PUT(a0, a1, a2)                                                                     \
@@ -1731,7 +1732,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       //      the oracle's canonical enumeration.
       const int rbase = BLK ? 0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
       unsigned smask = 0;  // slots of the new list that hold a constraint
-      unsigned long long lvpack = 0;  // dependency level of each of this thread's constraints, 8 bits each
+      unsigned long long lvpack[2] = {0ull, 0ull};  // dependency level of each of this thread's constraints, 8 bits each
       if (P.self_coll) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1744,7 +1745,16 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         aux[0 * bdim + tid] = vcx; aux[1 * bdim + tid] = vcy; aux[2 * bdim + tid] = vrad;
         SSYNC()
         SCon<real>* const newc = (sbase + ((sst >> 31) ^ 1u))->c;
-        int cand[VSR_MAX_CAND], n_cand = 0;  // (partner thread << 4) | partner mass << 2 | own mass
+        // Candidate q of a thread = (partner thread << 4) | partner mass << 2 | own mass, bound for slot q of the thread's
+        // list.  With the pool as scratch space the candidates are written there as they are found and the warp's
+        // candidates are spread over its lanes afterwards (one narrowphase round); without it every thread runs the
+        // narrowphase of a candidate on the spot.
+        const bool pooled_np = cap * VSR_POOL_FIELDS >= 576 * (BLK ? wpb : 1);
+        // scratch: [32][16] candidates and the [512] list as 16-bit words, [32] meta and [32] results as words
+        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 576 : 0);
+        unsigned short* const scand = reinterpret_cast<unsigned short*>(scr);        // words [0, 256)
+        unsigned short* const slist = reinterpret_cast<unsigned short*>(scr + 288);  // words [288, 544)
+        int n_cand = 0;
         if (active) {
           const real rr = real(2.8284271247461903) * P.half;  // two half diagonals
           real ae[4];
@@ -1774,22 +1784,19 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
                 // disjoint bounding boxes: separated (exact, unlike the narrowphase margin: safe side)
                 const real lim = be + ae[ka];
                 if (r_abs(x[ka] - bx) > lim || r_abs(y[ka] - by) > lim) continue;
-                const int code = (tj << 4) | (kb << 2) | ka;
-#pragma unroll
-                for (int q = 0; q < VSR_MAX_CAND; q++)
-                  if (q == n_cand) cand[q] = code;
-                if (n_cand == VSR_MAX_CAND) status |= STATUS_PAIR_OVERFLOW;
-                else n_cand++;
+                if (n_cand == VSR_MAX_CAND) { status |= STATUS_PAIR_OVERFLOW; continue; }
+                if (pooled_np) {
+                  scand[lane * VSR_MAX_CAND + n_cand] = (unsigned short)((tj << 4) | (kb << 2) | ka);
+                } else if (self_pair(cpar, P.half, x[ka], y[ka], cs_[ka], sn_[ka], bx, by, mt[VSR_MTI(kb, 2, tj)],
+                                     mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, S_CUR->c, S_MASK, &newc[n_cand])) {
+                  smask |= 1u << n_cand;
+                }
+                n_cand++;
               }
             }
           }
         }
-        // narrowphase.  Candidate q of a thread goes to slot q of its list; with the pool as scratch space
-        // the warp's candidates are spread over its lanes (one round), else every thread does its own.
-        if (cap * VSR_POOL_FIELDS >= 576 * (BLK ? wpb : 1)) {
-          int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 576 : 0);  // [32][8] candidates, [32] meta, [256] list, [32] results
-#pragma unroll
-          for (int q = 0; q < VSR_MAX_CAND; q++) scr[lane * 8 + q] = cand[q];
+        if (pooled_np) {
           scr[256 + lane] = (int)S_MASK;
           int incl = n_cand;
 #pragma unroll
@@ -1798,14 +1805,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             if (lane >= d2) incl += t;
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
-          for (int q = 0, pos = incl - n_cand; q < n_cand; q++) scr[288 + pos + q] = (lane << 3) | q;
+          for (int q = 0, pos = incl - n_cand; q < n_cand; q++) slist[pos + q] = (unsigned short)((lane << 4) | q);
           scr[544 + lane] = 0;
           __syncwarp();
           const unsigned cur = sst >> 31;
           for (int i = lane; i < total; i += 32) {
-            const int it = scr[288 + i];
-            const int ol = it >> 3, q = it & 7;
-            const int code = scr[ol * 8 + q];
+            const int it = slist[i];
+            const int ol = it >> 4, q = it & 15;
+            const int code = scand[ol * VSR_MAX_CAND + q];
             const int tj = code >> 4, kb = (code >> 2) & 3, ka = code & 3;
             const int tl = (BLK ? 0 : 0) + (wib << 5) + ol;
             SList<real>* const own = blk_sl + (size_t)tl * 2;
@@ -1817,26 +1824,6 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           __syncwarp();
           smask = (unsigned)scr[544 + lane];
           __syncwarp();
-        } else {
-          const int max_cand = BLK ? VSR_MAX_CAND : (int)__reduce_max_sync(0xffffffffu, (unsigned)n_cand);
-          const SCon<real>* const oldc = S_CUR->c;
-          const unsigned old_mask = S_MASK;
-#pragma unroll
-          for (int q = 0; q < VSR_MAX_CAND; q++) {
-            if (q < max_cand) {
-              if (q < n_cand) {
-                const int code = cand[q];
-                const int tj = code >> 4, kb = (code >> 2) & 3, ka = code & 3;
-                real ax = x[0], ay = y[0], ac = cs_[0], as = sn_[0];
-#pragma unroll
-                for (int k = 1; k < 4; k++)
-                  if (ka == k) { ax = x[k]; ay = y[k]; ac = cs_[k]; as = sn_[k]; }
-                if (self_pair(cpar, P.half, ax, ay, ac, as, mt[VSR_MTI(kb, 0, tj)], mt[VSR_MTI(kb, 1, tj)], mt[VSR_MTI(kb, 2, tj)],
-                              mt[VSR_MTI(kb, 3, tj)], ka, tj, kb, oldc, old_mask, &newc[q]))
-                  smask |= 1u << q;
-              }
-            }
-          }
         }
         const int n_new = __popc(smask);
         // position of this thread's constraints in its robot's order
@@ -1884,7 +1871,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             cnt[ia] = (real)(lv + 1);
             cnt[ib] = (real)(lv + 1);
             if (lv >= VSR_MAX_LEVELS) { lv = VSR_MAX_LEVELS - 1; status |= STATUS_LEVEL_OVERFLOW; }
-            lvpack |= (unsigned long long)lv << (8 * sl);
+            lvpack[sl >> 3] |= (unsigned long long)lv << (8 * (sl & 7));
           }
           SSYNC()
         }
@@ -1905,9 +1892,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           const int cn = (int)((gcn >> (4 * k)) & 15u);
           for (int q = 0; q < cn; q++) atomicAdd(&lhd[2 + q], 1);
         }
-#pragma unroll
-        for (int li = 0; li < VSR_MAX_CAND; li++)
-          if ((smask >> li) & 1u) atomicAdd(&lhd[2 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1);
+        for (unsigned m_ = smask; m_; m_ &= m_ - 1u) {
+          const int li = __ffs((int)m_) - 1;
+          atomicAdd(&lhd[2 + ((unsigned)((lvpack[li >> 3] >> (8 * (li & 7))) & 255ull))], 1);
+        }
         SSYNC()
         if (!BLK) {
           // one level per lane (VSR_MAX_LEVELS = 32): prefix sum of the counts by shuffles
@@ -1938,12 +1926,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         for (int k = 0; k < 4; k++) {
           const int cn = (int)((gcn >> (4 * k)) & 15u);
           for (int q = 0; q < cn; q++)
-            items[atomicAdd(&lhd[34 + q], 1)] = (tid << 7) | ((k * 2 + (int)((flip >> k) & 1u)) << 4) | (q << 1);
+            items[atomicAdd(&lhd[34 + q], 1)] = (tid << 8) | ((k * 2 + (int)((flip >> k) & 1u)) << 5) | (q << 1);
         }
-#pragma unroll
-        for (int li = 0; li < VSR_MAX_CAND; li++)
-          if ((smask >> li) & 1u)
-            items[atomicAdd(&lhd[34 + ((unsigned)((lvpack >> (8 * li)) & 255ull))], 1)] = (tid << 7) | (int)((sst >> 31) << 4) | (li << 1) | 1;
+        for (unsigned m_ = smask; m_; m_ &= m_ - 1u) {
+          const int li = __ffs((int)m_) - 1;
+          items[atomicAdd(&lhd[34 + ((unsigned)((lvpack[li >> 3] >> (8 * (li & 7))) & 255ull))], 1)] = (tid << 8) | (int)((sst >> 31) << 5) | (li << 1) | 1;
+        }
         SSYNC()
       }
 

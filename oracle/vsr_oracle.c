@@ -1553,6 +1553,18 @@ static int world_step(ORun* R, ORobot* r, double dt) {
     ccd_pass(R, r, pose0, dt);
     free(pose0);
   }
+  if (R->o.state_fp32) {
+    const double ox = d->initial_placement;
+    for (int b = 0; b < r->nb; b++) {
+      OBody* B = &r->bodies[b];
+      B->x = ox + (double)(float)(B->x - ox);
+      B->y = (double)(float)B->y;
+      B->th = (double)(float)B->th;
+      B->vx = (double)(float)B->vx;
+      B->vy = (double)(float)B->vy;
+      B->w = (double)(float)B->w;
+    }
+  }
   /* new contacts for Touch and for the next step */
   detect(R, r);
   return iters;

@@ -123,3 +123,17 @@ def test_product_path_never_touches_the_oracle():
                 for pat in (r"libvsr_oracle", r"vsr_oracle_\w+\s*\(", r"^\s*(from|import)\s+oracle", r"oracle/",
                             r"#include.*oracle", r"oracle\.(run|lib|build)"):
                     assert not re.search(pat, src, flags=re.M), (pat, os.path.join(dp, f))
+
+
+def test_create_rejects_a_ground_profile_finer_than_the_contact_capacity():
+    """The device keeps 3 ground constraints per mass (enough for every terrain Locomotion.createTerrain builds:
+    segments >= 1 wide, steppy risers 0.5 wide between treads >= 1 wide).  A profile on which a mass could touch
+    more polygons at once is refused at create -- never truncated at run time."""
+    import helpers
+    robots = helpers.phase_robots(1)
+    for name in ("flat", "hilly-1-10-0", "hilly-0.5-1-3", "steppy-1-6-2", "steppy-2-1-9", "uphill-10", "flatWithStart-4"):
+        H.DeviceBatch(helpers.locomotion(1.0, terrain=name).compile(robots)).close()   # vsr_batch_create (host only) accepts it
+    xs = [0.0, 10.0] + [10.0 + 0.3 * i for i in range(1, 200)] + [100.0]
+    ys = [100.0, 5.0] + [5.0 + 0.05 * (i % 2) for i in range(1, 200)] + [100.0]
+    with pytest.raises(NotImplementedError, match="ground profile too fine"):
+        H.DeviceBatch(H.Locomotion(1.0, [xs, ys], H.Settings()).compile(robots))

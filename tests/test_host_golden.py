@@ -171,3 +171,21 @@ def test_compile_batch_layout():
         H.Locomotion(1.0, [[0, 5, 3], [0, 0, 0]], H.Settings())
     with pytest.raises(ValueError, match="at least 2 points"):
         H.Locomotion(1.0, [[0], [0]], H.Settings())
+
+
+def test_fp32_protocol_fixture_matches_the_live_oracle():
+    """tests/golden/fp32_protocol.npz (the oracle half of the fp32 parity protocol, tests/test_fp32_protocol_gpu.py)
+    cannot go stale: a slice of it is recomputed here -- canonical order and one shuffled order."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_fp32_protocol as proto
+    from oracle import oracle
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "fp32_protocol.npz"))
+    meta = json.loads(str(fix["meta"]))
+    assert meta["n"] == proto.N >= 1024 and meta["k"] == proto.K >= 8
+    for name, (loco, robots) in proto.configs(8).items():   # the generators are prefix-stable: robot i does not depend on n
+        bd = loco.compile(robots[:3])
+        r, _ = oracle.run(bd, n_threads=3)
+        assert np.allclose(r["last_center_x"] - r["first_center_x"], fix[name + "_canon"][:3], rtol=0, atol=1e-9), name
+        s, _ = oracle.run(bd, order=oracle.ORDER_SHUFFLED, seed=meta["shuffle_seed0"] + 2, n_threads=3)
+        assert np.allclose(s["last_center_x"] - s["first_center_x"], fix[name + "_shuf"][2][:3], rtol=0, atol=1e-9), name
