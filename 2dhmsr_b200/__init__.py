@@ -9,7 +9,7 @@ from . import _abi as abi  # noqa: F401
 from .hmsrobots import (  # noqa: F401
     Angle, AppliedForce, Constant, ControlPower, Crumpling, Lidar, Malfunction, Noisy, Normalization, TimeFunction,
     AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DistributedSensing, DistributedSensingNonDirectional,
-    DoubleRange, Grid,
+    DoubleRange, DynamicNormalization, Grid,
     JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotShape, RobotUtils,
     Sensor, Settings, Snapshot, SoftNormalization, TimeFunctions, Touch, Trend, Velocity, Voxel, VsrError,
     compile_batch, tick_times,

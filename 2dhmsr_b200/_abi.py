@@ -37,6 +37,7 @@ VSR_SENSOR_VELOCITY = 2
 VSR_AGG_NONE = 0
 VSR_AGG_AVERAGE = 1
 VSR_AGG_TREND = 2
+VSR_AGG_DYNAMIC_NORM = 3
 VSR_AXIS_X = 1
 VSR_AXIS_Y = 2
 
@@ -244,6 +245,8 @@ def _declare(lib) -> None:
     lib.vsr_batch_final_bbox.restype = C.c_int
     lib.vsr_batch_voxel_trace.argtypes = [vp, sz, C.POINTER(C.c_double), sz]
     lib.vsr_batch_voxel_trace.restype = C.c_longlong
+    lib.vsr_batch_sensor_readings.argtypes = [vp, sz, C.POINTER(C.c_double), sz]
+    lib.vsr_batch_sensor_readings.restype = C.c_longlong
     lib.vsr_batch_voxel_steps.argtypes = [vp]
     lib.vsr_batch_voxel_steps.restype = sz
     lib.vsr_batch_n_ticks.argtypes = [vp]
@@ -267,7 +270,7 @@ def _declare(lib) -> None:
 EXPORTED_SYMBOLS = [
     "vsr_default_settings", "vsr_default_material", "vsr_tick_count", "vsr_tick_count_from", "vsr_batch_create",
     "vsr_batch_upload", "vsr_batch_run", "vsr_batch_results", "vsr_batch_results_device",
-    "vsr_batch_trajectory", "vsr_batch_final_bbox", "vsr_batch_voxel_trace", "vsr_batch_voxel_steps", "vsr_batch_n_ticks", "vsr_batch_n_bodies",
+    "vsr_batch_trajectory", "vsr_batch_final_bbox", "vsr_batch_voxel_trace", "vsr_batch_sensor_readings", "vsr_batch_voxel_steps", "vsr_batch_n_ticks", "vsr_batch_n_bodies",
     "vsr_batch_last_launches", "vsr_batch_upload_bytes", "vsr_batch_destroy", "vsr_last_error", "vsr_abi_version",
     "vsr_device_count",
 ]

@@ -128,6 +128,7 @@ struct Bucket {
   std::vector<double> unplaced_x, unplaced_y;  // the shape's masses with bbox.min.x = 0, y as assembled
   double default_dx = 0, default_dy = 0;
   void* d_vtrace = nullptr;
+  void* d_rtrace = nullptr;  // [traj_robots][n_ticks][n_readings]
   void* d_cbuf = nullptr;
   size_t cbuf_bytes = 0;
   void* d_sbuf = nullptr;  // intra-robot contact arena
@@ -210,8 +211,8 @@ static void free_device(vsr_batch* b) {
   b->side_streams.clear(); b->side_done.clear(); b->fork_event = nullptr;
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_place = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr;
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_rtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_place = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr; k.d_rtrace = nullptr;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
     k.d_sbuf = nullptr; k.sbuf_bytes = 0;
     k.d_lbuf = nullptr; k.lbuf_bytes = 0;
@@ -452,7 +453,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         if (q.base < VSR_SENSOR_TOUCH || q.base > VSR_SENSOR_LIDAR ||
             (q.base == VSR_SENSOR_LIDAR && (q.axes < 1 || q.axes > VSR_LIDAR_MAX_RAYS || q.aggregator != VSR_AGG_NONE)) || q.soft_norm < 0 || q.soft_norm > VSR_NORM_LINEAR ||
             q.aggregator < VSR_AGG_NONE ||
-            q.aggregator > VSR_AGG_TREND) {
+            q.aggregator > VSR_AGG_DYNAMIC_NORM) {
           delete b;
           return fail(VSR_ERR_INVALID_ARGUMENT, "unknown sensor");
         }
@@ -496,9 +497,10 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     }
     S.n_readings = ro;
     S.n_channels = maxch;
-    // PhaseSin / TimeFunctions never read a sensor and no reading is observable through the boundary
-    // (Outcome, Observation): the sensor programs of such a batch are validated above and then dropped
-    if (d->controller_kind == VSR_CTRL_PHASE_SIN || d->controller_kind == VSR_CTRL_TABULATED) {
+    // PhaseSin / TimeFunctions never read a sensor: unless the per-tick dumps (vsr_batch_sensor_readings) were asked
+    // for, no reading is observable through the boundary and the sensor programs of such a batch are validated
+    // above and then dropped
+    if ((d->controller_kind == VSR_CTRL_PHASE_SIN || d->controller_kind == VSR_CTRL_TABULATED) && d->trajectory_robots == 0) {
       for (int v = 0; v < nv; v++) S.n_sens[v] = 0;
       S.n_channels = 0;
     }
@@ -765,6 +767,7 @@ static int upload_impl(vsr_batch* b, int device, void* stream) {
         size_t tb = (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz;
         CUDA_TRY(cudaMalloc(&k.d_traj, tb));
         CUDA_TRY(cudaMalloc(&k.d_vtrace, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 2 * esz));
+        CUDA_TRY(cudaMalloc(&k.d_rtrace, std::max<size_t>(1, (size_t)k.traj_robots * nt * (size_t)k.shape.n_readings) * esz));
       }
     }
     // kernel arguments, launch geometry, shared-memory carve-out and the contact arenas of every bucket
@@ -783,6 +786,7 @@ static int upload_impl(vsr_batch* b, int device, void* stream) {
     {
       CUDA_TRY(cudaMemsetAsync(k.d_traj, 0, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 4 * 6 * esz, s));
       CUDA_TRY(cudaMemsetAsync(k.d_vtrace, 0, (size_t)k.traj_robots * nt * (size_t)k.shape.nvox * 2 * esz, s));
+      CUDA_TRY(cudaMemsetAsync(k.d_rtrace, 0, std::max<size_t>(1, (size_t)k.traj_robots * nt * (size_t)k.shape.n_readings) * esz, s));
     }
   CUDA_TRY(cudaStreamSynchronize(s));
   b->uploaded = true;
@@ -820,6 +824,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   P.trajectory = (real*)k.d_traj;
   P.traj_robots = k.traj_robots;
   P.vtrace = (real*)k.d_vtrace;
+  P.rtrace = (real*)k.d_rtrace;
   P.n_ticks = (int)b->ticks.size();
   P.tick_t = b->d_ticks;
   P.noise_tab = b->d_noise;
@@ -1121,6 +1126,36 @@ extern "C" long long vsr_batch_voxel_trace(vsr_batch* b, size_t robot, double* o
   } else {
     std::vector<float> tmp(n);
     CUDA_TRY(cudaMemcpy(tmp.data(), (float*)kb->d_vtrace + (size_t)pos * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+  }
+  return (long long)n;
+}
+
+extern "C" long long vsr_batch_sensor_readings(vsr_batch* b, size_t robot, double* out, size_t capacity) {
+  if (!b || !out) return fail(VSR_ERR_INVALID_ARGUMENT, "null argument");
+  if (!b->ran) return fail(VSR_ERR_STATE, "vsr_batch_sensor_readings before vsr_batch_run");
+  if (robot >= b->n_robots || robot >= b->desc.trajectory_robots)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "robot has no recorded trajectory");
+  Bucket* kb = nullptr;
+  int pos = -1;
+  for (auto& k : b->buckets)
+    for (size_t i = 0; i < k.robot_ids.size() && (long long)i < k.traj_robots; i++)
+      if ((size_t)k.robot_ids[i] == robot) {
+        kb = &k;
+        pos = (int)i;
+      }
+  if (!kb) return fail(VSR_ERR_STATE, "trajectory bucket not found");
+  const int nt = (int)b->ticks.size();
+  const size_t n = (size_t)nt * (size_t)kb->shape.n_readings;
+  if (capacity < n) return fail(VSR_ERR_INVALID_ARGUMENT, "sensor readings buffer too small");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->run_stream));
+  if (b->precision == VSR_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(out, (double*)kb->d_rtrace + (size_t)pos * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), (float*)kb->d_rtrace + (size_t)pos * n, n * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; i++) out[i] = tmp[i];
   }
   return (long long)n;

@@ -55,7 +55,7 @@ enum : int { CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2 };
 enum : int { SENSOR_TOUCH = 0, SENSOR_AREA = 1, SENSOR_VELOCITY = 2, SENSOR_ANGLE = 3, SENSOR_CONSTANT = 4,
              SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7, SENSOR_CRUMPLING = 8,
              SENSOR_CONTROL_POWER = 9, SENSOR_LIDAR = 10 };
-enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2 };
+enum : int { AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2, AGG_DYNAMIC_NORM = 3 };
 // vsr_result.status bits (include/vsr_b200.h): the three capacity bits mean that constraints were DROPPED for
 // this robot (its result is not the reference's physics)
 enum : int { STATUS_NONFINITE = 1, STATUS_CONTACT_OVERFLOW = 2, STATUS_PAIR_OVERFLOW = 4, STATUS_LEVEL_OVERFLOW = 8 };
@@ -109,6 +109,7 @@ struct Params {
   real* trajectory;           // [traj_robots][n_ticks][nvox*4][6], bucket order, or null
   long long traj_robots;
   real* vtrace;               // [traj_robots][n_ticks][nvox][2]: touching the ground, applied force
+  real* rtrace;               // [traj_robots][n_ticks][n_readings]: Voxel.getSensorReadings, voxels in order
   // time
   int n_ticks;
   const double* tick_t;       // [n_ticks] accumulated t
@@ -2048,6 +2049,17 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
                 for (int q = f; q < tick; q++) sum = sum + ring[(size_t)(q % depth) * stride];
                 sum = sum + raw[d];
                 val[d] = sum / (real)(tick - f + 1);
+              } else if (sd.agg == AGG_DYNAMIC_NORM) {
+                // DynamicNormalization.aggregate (:40-58): min / max over the kept window (the current reading
+                // included); (r - min) / (max - min) is 0/0 = NaN while they coincide, and Java's Math.min / max
+                // pass the NaN on (fminf / fmaxf would drop it)
+                real mn = raw[d], mx = raw[d];
+                for (int q = f; q < tick; q++) {
+                  const real pv = ring[(size_t)(q % depth) * stride];
+                  mn = r_min(mn, pv);
+                  mx = r_max(mx, pv);
+                }
+                val[d] = mx > mn ? r_min(r_max((raw[d] - mn) / (mx - mn), real(0)), real(1)) : (real)NAN;
               } else {
                 real li = (real)(P.tick_t[tick] - P.tick_t[f]);
                 real first = (f == tick) ? raw[d] : ring[(size_t)(f % depth) * stride];
@@ -2058,6 +2070,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               real ext = dmax - dmin;
               dmin = -ext / sd.interval;
               dmax = ext / sd.interval;
+            } else if (sd.agg == AGG_DYNAMIC_NORM) {
+              dmin = real(0);
+              dmax = real(1);
             }
           }
           for (int d = 0; d < sd.dim; d++) {
@@ -2069,6 +2084,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               r_sincos((real)__ldg(&sp->dirs[d]) + ang, &rs, &rc);
               o = lidar_cast(tpar, ocx, ocy, rc, rs, (real)sd.max_norm, hint[0]);
             }
+            const real o_in = o;
             if (sd.soft == 1) {
               real cl = r_min(r_max(o, dmin), dmax);
               real nv = (cl - dmin) / (dmax - dmin);
@@ -2076,6 +2092,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             } else if (sd.soft == 2) {  // Normalization: DoubleRange.normalize
               o = (r_min(r_max(o, dmin), dmax) - dmin) / (dmax - dmin);
             }
+            // (Java's Math.min / Math.max return NaN for a NaN argument; only DynamicNormalization produces one)
+            if (sd.agg == AGG_DYNAMIC_NORM && o_in != o_in) o = o_in;
             if (sd.noise > 0.0) {
               // Noisy.sense (Noisy.java:57-62): every instance owns a Random(seed), so a sensor of
               // dimension dim draws gaussians number tick * dim + d of the same stream (host table)
@@ -2196,7 +2214,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
       for (int c = 0; c < 3; c++)
         rest[c] = (f >= real(0)) ? P.rng_rest[c] - (P.rng_rest[c] - P.rng_min[c]) * f
-                                 : P.rng_rest[c] + (P.rng_max[c] - P.rng_rest[c]) * -f;
+                  : ((f < real(0)) ? P.rng_rest[c] + (P.rng_max[c] - P.rng_rest[c]) * -f
+                                   : rest[c]);  // NaN: neither branch of Voxel.applyForce (:230-235), the rest distance stays
 
       // ---- optional per-tick dump (SnapshotListener / Observation path)
       if (P.trajectory && active && rb < P.traj_robots) {
@@ -2211,6 +2230,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         real* q = P.vtrace + (((size_t)rb * P.n_ticks + tick) * (size_t)nvox + (size_t)v) * 2;
         q[0] = cmask ? real(1) : real(0);
         q[1] = last_f;
+        const int rbase_ = S.read_off[v];
+        const int rn_ = (v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - rbase_;
+        real* rt = P.rtrace + ((size_t)rb * P.n_ticks + tick) * (size_t)S.n_readings + rbase_;
+        if (S.n_sens[v] > 0)
+          for (int z = 0; z < rn_; z++) rt[z] = readings[z];
       }
 
       // ---- Observation: first and last tick only (Outcome.java:152-166)

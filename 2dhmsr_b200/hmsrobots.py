@@ -360,6 +360,16 @@ class Trend(_Aggregator):  # sensors/Trend.java:28-35
         return [DoubleRange(-d.extent() / self.interval, d.extent() / self.interval) for d in self.sensor.domains()]
 
 
+class DynamicNormalization(_Aggregator):
+    """sensors/DynamicNormalization.java:26-61: every reading rescaled by the minimum and maximum of the readings kept in
+    the window, clamped to [0, 1].  While the window holds a single distinct value (always at the first tick) the
+    reference divides 0 by 0: the reading is NaN there, and it is NaN here."""
+    KIND = A.VSR_AGG_DYNAMIC_NORM
+
+    def domains(self):
+        return [DoubleRange(0.0, 1.0) for _ in self.sensor.domains()]
+
+
 class SoftNormalization(Sensor):  # sensors/SoftNormalization.java
     def __init__(self, sensor: Sensor):
         if isinstance(sensor, SoftNormalization):
@@ -1262,6 +1272,17 @@ class DeviceBatch:
         if got < 0:
             _check(self.lib, int(got))
         return out
+
+    def sensor_readings(self, robot: int) -> np.ndarray:
+        """[tick][n_readings]: Voxel.getSensorReadings of the robot's voxels, concatenated in Grid.values() order
+        (vsr_batch_sensor_readings)."""
+        nt = self.lib.vsr_batch_n_ticks(self.h)
+        cap = nt * 24 * (self.lib.vsr_batch_n_bodies(self.h, robot) // 4)
+        out = np.zeros(cap, dtype=np.float64)
+        got = self.lib.vsr_batch_sensor_readings(self.h, robot, _np_ptr(out, C.c_double), out.size)
+        if got < 0:
+            _check(self.lib, int(got))
+        return out[:got].reshape(nt, got // nt if nt else 0)
 
     def voxel_steps(self) -> int:
         return int(self.lib.vsr_batch_voxel_steps(self.h))

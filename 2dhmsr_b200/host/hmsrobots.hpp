@@ -196,6 +196,12 @@ struct Trend : AggregatorSensor {  // sensors/Trend.java:28-35
     return d;
   }
 };
+struct DynamicNormalization : AggregatorSensor {  // sensors/DynamicNormalization.java:26-61 (0/0 = NaN at the first tick, as there)
+  DynamicNormalization(SensorPtr s, double i) : AggregatorSensor(std::move(s), i, VSR_AGG_DYNAMIC_NORM) {}
+  std::vector<DoubleRange> getDomains() const override {
+    return std::vector<DoubleRange>(sensor->getDomains().size(), DoubleRange(0.0, 1.0));
+  }
+};
 struct SoftNormalization : Sensor {  // sensors/SoftNormalization.java
   SensorPtr sensor;
   explicit SoftNormalization(SensorPtr s) : sensor(std::move(s)) {

@@ -121,6 +121,9 @@ typedef struct vsr_material {
 #define VSR_AGG_NONE 0
 #define VSR_AGG_AVERAGE 1 /* sensors/Average.java:33-45 */
 #define VSR_AGG_TREND 2   /* sensors/Trend.java:28-50   */
+#define VSR_AGG_DYNAMIC_NORM 3 /* sensors/DynamicNormalization.java:26-61: (reading - min) / (max - min) over the kept
+                                  window, clamped to [0, 1]; 0/0 = NaN while the window holds one distinct value
+                                  (always at the first tick), exactly as the reference computes it; domain [0, 1] */
 
 #define VSR_AXIS_X 1
 #define VSR_AXIS_Y 2
@@ -289,6 +292,11 @@ int vsr_batch_final_bbox(vsr_batch* b, double* out, size_t n);
    all an Outcome.Observation holds (Locomotion.java:198-202).  Returns the number of doubles
    written, or <0.                                                                          */
 long long vsr_batch_voxel_trace(vsr_batch* b, size_t robot, double* out, size_t capacity);
+
+/* Voxel.getSensorReadings (Voxel.java:530-536) of every voxel, per tick, for robot r (< trajectory_robots):
+   out[tick][n_readings], the voxels' readings concatenated in Grid.values() order -- the input vector of
+   CentralizedSensing (CentralizedSensing.java:98-104).  Returns the number of doubles written, or <0.   */
+long long vsr_batch_sensor_readings(vsr_batch* b, size_t robot, double* out, size_t capacity);
 
 /* Facts about the compiled batch. */
 size_t vsr_batch_voxel_steps(const vsr_batch* b); /* sum over robots of voxels*ticks */

@@ -81,8 +81,8 @@ final class DescWriter {
       s = s.get("sensor");
       cls = s.get("@class").asText();
     }
-    if (cls.equals(S + "Average") || cls.equals(S + "Trend")) {   // AggregatorSensor.java:29 interval
-      agg = cls.endsWith("Average") ? VsrLayouts.AGG_AVERAGE : VsrLayouts.AGG_TREND;
+    if (cls.equals(S + "Average") || cls.equals(S + "Trend") || cls.equals(S + "DynamicNormalization")) {   // AggregatorSensor.java:29 interval
+      agg = cls.endsWith("Average") ? VsrLayouts.AGG_AVERAGE : (cls.endsWith("Trend") ? VsrLayouts.AGG_TREND : VsrLayouts.AGG_DYNAMIC_NORM);
       interval = s.get("interval").asDouble();
       s = s.get("sensor");
       cls = s.get("@class").asText();

@@ -40,6 +40,7 @@ public final class VsrB200 {
   static final MethodHandle RESULTS = h("vsr_batch_results", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
   static final MethodHandle TRAJECTORY = h("vsr_batch_trajectory", FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG));
   static final MethodHandle VOXEL_TRACE = h("vsr_batch_voxel_trace", FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG));
+  static final MethodHandle SENSOR_READINGS = h("vsr_batch_sensor_readings", FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG));
   static final MethodHandle FINAL_BBOX = h("vsr_batch_final_bbox", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
   static final MethodHandle DESTROY = h("vsr_batch_destroy", FunctionDescriptor.ofVoid(ADDRESS));
   static final MethodHandle LAST_ERROR = h("vsr_last_error", FunctionDescriptor.of(ADDRESS));

@@ -136,7 +136,7 @@ public final class VsrLayouts {
       SENSOR_CONSTANT = 4, SENSOR_APPLIED_FORCE = 5, SENSOR_MALFUNCTION = 6, SENSOR_TIME_SIN = 7,
       SENSOR_CRUMPLING = 8, SENSOR_CONTROL_POWER = 9, SENSOR_LIDAR = 10;
   public static final int NORM_NONE = 0, NORM_SOFT = 1, NORM_LINEAR = 2;
-  public static final int AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2;
+  public static final int AGG_NONE = 0, AGG_AVERAGE = 1, AGG_TREND = 2, AGG_DYNAMIC_NORM = 3;
   public static final int AXIS_X = 1, AXIS_Y = 2;
   public static final int CTRL_PHASE_SIN = 0, CTRL_TABULATED = 1, CTRL_MLP = 2, CTRL_DISTRIBUTED = 3,
       CTRL_DISTRIBUTED_ND = 4;

@@ -1748,6 +1748,18 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
           for (int q = f; q <= tick; q++) sum = sum + H[(size_t)q * dim + k];
           val[k] = sum / (double)(tick - f + 1);
         }
+      } else if (S->aggregator == VSR_AGG_DYNAMIC_NORM) { /* DynamicNormalization.aggregate, :40-58 */
+        for (int k = 0; k < dim; k++) {
+          double mn = INFINITY, mx = -INFINITY;
+          for (int q = f; q <= tick; q++) {
+            mn = fmin(mn, H[(size_t)q * dim + k]);
+            mx = fmax(mx, H[(size_t)q * dim + k]);
+          }
+          double v = (raw[k] - mn) / (mx - mn); /* 0/0 = NaN while the window holds one distinct value */
+          val[k] = v != v ? v : fmin(fmax(v, 0.0), 1.0); /* Math.min / Math.max keep a NaN */
+        }
+        dmin = 0.0;
+        dmax = 1.0;
       } else { /* Trend.aggregate, Trend.java:37-50 */
         double li = T[tick] - T[f];
         for (int k = 0; k < dim; k++)
@@ -1761,6 +1773,7 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
       double o = S->soft_norm == VSR_NORM_SOFT ? soft_norm(val[k], dmin, dmax)
                  : S->soft_norm == VSR_NORM_LINEAR ? (fmin(fmax(val[k], dmin), dmax) - dmin) / (dmax - dmin) /* Normalization.java */
                                                    : val[k];
+      if (val[k] != val[k]) o = val[k]; /* Java's Math.min / Math.max return NaN for a NaN argument (DynamicNormalization) */
       if (S->noise_sigma > 0) { /* Noisy.sense, Noisy.java:57-62: sigma * extent of the wrapped sensor's domain */
         double ext = S->soft_norm != VSR_NORM_NONE ? 1.0 : dmax - dmin;
         o = o + jr_next_gaussian(r, si) * (ext * S->noise_sigma);

@@ -509,3 +509,57 @@ def test_fp32_closed_loop_controllers_short_horizon():
     assert np.percentile(early, 25) < 2e-5 and early.max() < 2e-2, early
     assert np.abs(tr[..., :2] - otr[..., :2]).max() < 0.3
     assert np.allclose(res["control_energy_last"], ores["control_energy_last"], rtol=0.2)
+
+
+def _readings_both(loco, robots, precision=F64):
+    bd = loco.compile(robots, precision=precision, trajectory_robots=len(robots))
+    with H.DeviceBatch(bd) as db:
+        db.upload(0).run()
+        res = db.results()
+        rd = [db.sensor_readings(i) for i in range(len(robots))]
+    ores, pr = oracle.run(bd, readings=True, n_threads=8)
+    return res, rd, ores, pr["readings"]
+
+
+@pytest.mark.parametrize("sensors,terrain", [("uniform-ax+t-0", "flat"), ("uniformAll-0", "hilly-1-10-0"),
+                                             ("spinedTouchSighted-t-f-0", "hilly-1-10-0"), ("uniform-t+vxy+a-0.01", "flat")])
+def test_fp64_sensor_readings_equal_the_oracle(sensors, terrain):
+    """Voxel.getSensorReadings, per tick, read straight from the device (vsr_batch_sensor_readings): every
+    predefined sensor against the oracle's readings -- open-loop robots, so a wrong reading cannot hide behind the
+    controller that consumes it."""
+    robots = helpers.phase_robots(3, shape="biped-4x3", sensors=sensors, seed=12)
+    res, rd, ores, ord_ = _readings_both(helpers.locomotion(3.0, terrain=terrain), robots)
+    assert np.all(res["status"] == 0)
+    for i in range(len(robots)):
+        assert rd[i].shape == ord_[i].shape and rd[i].shape[1] > 0
+        assert np.abs(rd[i] - ord_[i]).max() < 1e-7, (i, np.abs(rd[i] - ord_[i]).max())
+
+
+def test_fp64_dynamic_normalization():
+    """DynamicNormalization (plain and under SoftNormalization), NaN at the first tick as in the
+    reference (DynamicNormalization.java:52-55 with a one-sample window), equal to the oracle from then on."""
+    mk = lambda x, y: H.Voxel([H.DynamicNormalization(H.AreaRatio(), 0.25), H.Average(H.Touch(), 0.25),
+                               H.SoftNormalization(H.DynamicNormalization(H.Velocity(True, 8.0, H.Velocity.X, H.Velocity.Y), 0.5))])
+    body = H.Grid.create(4, 2, mk)
+    rng = np.random.default_rng(8)
+    robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(4, 2, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(4)]
+    res, rd, ores, ord_ = _readings_both(helpers.locomotion(3.0), robots)
+    assert np.all(res["status"] == 0)                       # the NaN stays inside the sensor: PhaseSin does not read it
+    for i in range(len(robots)):
+        assert np.array_equal(np.isnan(rd[i]), np.isnan(ord_[i]))
+        per = rd[i][0].reshape(8, 4)
+        assert np.all(np.isnan(per[:, [0, 2, 3]])) and np.all(per[:, 1] == 0.0)   # tick 0: 0/0, touch average 0
+        ok = ~np.isnan(ord_[i])
+        assert np.abs(rd[i][ok] - ord_[i][ok]).max() < 1e-7
+        assert ok[1:].mean() > 0.99
+    # closed loop: applyForce(NaN) at the first tick leaves the rest distances alone (Voxel.java:230-235), the control
+    # energy is NaN from then on, the bodies stay finite and follow the oracle
+    # (a reading that changes at every tick: a window of equal values up to rounding makes (r - min) / (max - min) a
+    # quotient of rounding errors, in the reference too -- e.g. the area ratio of an unactuated voxel in free fall)
+    body1 = H.Grid.create(2, 1, lambda x, y: H.Voxel([H.DynamicNormalization(H.Velocity(False, 8.0, H.Velocity.Y), 0.25)]))
+    nin, nout = H.CentralizedSensing.n_of_inputs(body1), H.CentralizedSensing.n_of_outputs(body1)
+    mlp = H.MultiLayerPerceptron("TANH", nin, [], nout, np.full(H.MultiLayerPerceptron.count_weights([nin, nout]), 0.1))
+    bd, res, tr, ores, otr = _both(helpers.locomotion(2.0), [H.Robot(H.CentralizedSensing(body1, mlp), body1)], F64)
+    assert res[0]["status"] == 0 and ores[0]["status"] == 0
+    assert np.abs(tr[..., :3] - otr[:, :, :8, :3]).max() < 1e-7
+    assert np.isnan(res[0]["control_energy_last"]) and np.isnan(ores[0]["control_energy_last"])
