@@ -164,6 +164,7 @@ struct vsr_batch {
   unsigned spring_mask = 0;
   size_t voxel_steps = 0;
   size_t upload_bytes = 0;
+  long long plan_warps = 0;  // warps of all buckets together (the launch plan fills the chip once, not once per bucket)
   // device
   int device = -1;
   bool uploaded = false, ran = false;
@@ -770,7 +771,15 @@ static int upload_impl(vsr_batch* b, int device, void* stream) {
         CUDA_TRY(cudaMalloc(&k.d_rtrace, std::max<size_t>(1, (size_t)k.traj_robots * nt * (size_t)k.shape.n_readings) * esz));
       }
     }
-    // kernel arguments, launch geometry, shared-memory carve-out and the contact arenas of every bucket
+    // kernel arguments, launch geometry, shared-memory carve-out and the contact arenas of every bucket.  The
+    // buckets run concurrently (side streams) and every block takes a whole SM's shared memory, so the block size
+    // follows the load of the WHOLE batch: small buckets of a big batch get full blocks, not one warp per SM.
+    b->plan_warps = 0;
+    for (auto& k : b->buckets) {
+      const int nv = k.shape.nvox;
+      b->plan_warps += nv > 32 ? (long long)k.robot_ids.size() * ((nv + 31) / 32)
+                               : ((long long)k.robot_ids.size() + 32 / nv - 1) / (32 / nv);
+    }
     for (auto& k : b->buckets)
       if ((rc = f64 ? prepare_bucket<double>(b, k) : prepare_bucket<float>(b, k))) return rc;
   }
@@ -899,30 +908,51 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
     int sms_ = 148;
     cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, b->device);
     const long long slots = (long long)sms_ * VSR_MIN_BLOCKS;  // resident blocks on the chip
-    if (groups_all <= slots * WPB_MAX) wpb = (int)std::max<long long>(1, (groups_all + slots - 1) / slots);
+    const long long load = std::max(groups_all, b->plan_warps);
+    if (load <= slots * WPB_MAX) wpb = (int)std::max<long long>(1, (load + slots - 1) / slots);
+    wpb = (int)std::max<long long>(1, std::min<long long>(wpb, groups_all));
   }
+  const int wpb_fill = wpb;  // warps per block that fill the chip once with this batch
   if (wpb_env > 0) wpb = std::min(WPB_MAX, wpb_env);
   const bool eff_mode = st.spring_mass_mode == VSR_SPRING_MASS_EFFECTIVE;
   if (sizeof(real) == 8) wpb = std::min(wpb, VSR_MAX_THREADS / 64);  // fp64: 32-byte vectors, half the stride
-  if (blk) wpb = (nvox + 31) / 32;
-  const int threads = 32 * wpb;
-  if (blk) P.smem_per_warp = std::max(128, (per_robot + wpb - 1) / wpb);  // block-wide staging = wpb * this
+  // Big robots: a robot takes wpr whole warps and a block holds rpb robots that walk the instruction stream
+  // together (one 2..4-warp block per robot ran at its own PC: instruction fetch was 30 % of the stall samples);
+  // the block's tables have `stride` thread columns (fp32 256, fp64 128).
+  const int stride = blk ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  const int wpr = blk ? (nvox + 31) / 32 : 1;
+  int rpb = blk ? std::max(1, std::min(stride / 32, std::max(wpb_fill, wpr)) / wpr) : 1;
+  if (blk) {
+    if (const char* e = tuning_env("VSR_RPB")) rpb = std::max(1, std::min(rpb, atoi(e)));
+    rpb = (int)std::max<long long>(1, std::min<long long>(rpb, (long long)k.robot_ids.size()));
+    wpb = wpr * rpb;
+  }
+  if (blk) P.smem_per_warp = std::max(128, (per_robot + wpr - 1) / wpr);  // a robot's staging = wpr * this
   else P.smem_per_warp = std::max(128, per_robot * G);
+  const size_t limit = 227 * 1024;
   // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
-  // contact exchange (+ the neighbour exchange of the one-block-per-robot variant)
-  const int stride = blk ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
-  size_t smem = (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
-                ((size_t)wpb * P.smem_per_warp + (size_t)16 * stride + (size_t)(blk ? 1 : wpb) * VSR_LHD_REALS) * sizeof(real) +
-                (blk ? (size_t)2 * 20 * 128 * sizeof(real) : 0);
+  // contact exchange (+ the neighbour exchange of the big-robot variant)
+  auto fixed_smem = [&](int wpb_, int rpb_) {
+    return (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
+           ((size_t)wpb_ * P.smem_per_warp + (size_t)16 * stride + (size_t)(blk ? rpb_ : wpb_) * VSR_LHD_REALS) * sizeof(real) +
+           (blk ? (size_t)2 * 20 * stride * sizeof(real) : 0);
+  };
+  // (a big robot's pool must at least hold the pooled detection scratch of its warps: 576 words each)
+  const size_t min_pool = blk ? (size_t)((576 * wpr + VSR_POOL_FIELDS - 1) / VSR_POOL_FIELDS + 3) / 4 * 4 * VSR_POOL_FIELDS * sizeof(real) : 0;
+  while (blk && rpb > 1 && fixed_smem(wpr * rpb, rpb) + rpb * min_pool > limit) rpb--;
+  if (blk) wpb = wpr * rpb;
+  P.wpr = wpr;
+  P.rpb = rpb;
+  const int threads = 32 * wpb;
+  size_t smem = fixed_smem(wpb, rpb);
   {
     // what is left of the SM's shared memory caches the block's contact constraints
-    const size_t limit = 227 * 1024;
     long long cap = smem < limit ? (long long)((limit - smem) / (VSR_POOL_FIELDS * sizeof(real))) : 0;
     // one pool per scope: the warp (its robots' constraints), or the block of a big robot
-    const int scopes = blk ? 1 : wpb;
-    cap = std::min<long long>(cap / scopes, blk ? (long long)VSR_ITEMS_PER_THREAD * threads : VSR_ITEMS_PER_THREAD * 32) / 4 * 4;
-    // a big robot's block is small (2..4 warps): a modest pool leaves room for a second block on the SM
-    if (blk) cap = std::min<long long>(cap, tuning_env("VSR_BLK_POOL") ? atoll(tuning_env("VSR_BLK_POOL")) : 96);
+    const int scopes = blk ? rpb : wpb;
+    cap = std::min<long long>(cap / scopes, blk ? (long long)VSR_ITEMS_PER_THREAD * 32 * wpr : VSR_ITEMS_PER_THREAD * 32) / 4 * 4;
+    // a big robot: enough for the pooled detection scratch of its warps (576 words each), no more than 160 constraints
+    if (blk) cap = std::min<long long>(cap, tuning_env("VSR_BLK_POOL") ? atoll(tuning_env("VSR_BLK_POOL")) : 160);
     if (const char* e = tuning_env("VSR_POOL")) cap = std::min<long long>(cap, atoll(e)) / 4 * 4;
     P.pool_cap = (int)cap;
     smem += (size_t)cap * scopes * VSR_POOL_FIELDS * sizeof(real);
@@ -948,7 +978,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
   if (occ < 1) return fail(VSR_ERR_CUDA, "episode kernel does not fit on an SM");
   const long long groups = (P.n_robots + G - 1) / G;
-  const long long want = blk ? groups : (groups + wpb - 1) / wpb;
+  const long long want = blk ? (groups + rpb - 1) / rpb : (groups + wpb - 1) / wpb;
   // persistent grid: one wave of resident blocks (a multiple of the SM count), each warp
   // (or block, for big robots) strides over robot groups
   const long long grid = std::max<long long>(1, std::min<long long>(want, (long long)occ * sms));

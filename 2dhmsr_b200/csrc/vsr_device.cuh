@@ -141,6 +141,7 @@ struct Params {
   int dist_signals;      // DistributedSensing: signals per side; < 0 for the other controllers
   int dist_nd;           // DistributedSensingNonDirectional: one set of signals for all neighbours
   int smem_per_warp;     // reals of staging per warp
+  int wpr, rpb;          // one-block-per-robot variant: warps per robot, robots per block (they walk the code together)
   void* cbuf;            // contact arena: [grid threads][4 masses][2 buffers] CBody<real>
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
   int* lbuf;             // contact lists: [grid blocks][VSR_ITEMS_PER_THREAD * max threads per block]
@@ -196,6 +197,19 @@ __device__ __forceinline__ real r_clamp(real x, real lo, real hi) { return r_min
 
 template <typename real>
 __device__ __forceinline__ real shfl(real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Named barriers (ids 1..15; 0 is __syncthreads): the threads of ONE robot of a block that holds several big
+// robots.  `n` = the robot's thread count (a multiple of 32); every one of them arrives.
+__device__ __forceinline__ void robot_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ bool robot_sync_and(int id, int n, bool p) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred q, r;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.and.pred r, %1, %2, q;\n\tselp.b32 %0, 1, 0, r;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(n), "r"((int)p)
+      : "memory");
+  return r != 0;
+}
 
 // 4-wide value for one 128-bit (fp32) shared-memory access per spring
 template <typename real> struct Real4T;
@@ -963,7 +977,7 @@ enum : int { ROUND_WARM = 0, ROUND_VELOCITY = 1, ROUND_POSITION = 2 };
 template <int MODE, bool BLK, typename real>
 __device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, int mts, const int* lhd, const int* items,
                                                int n_lv, int st, int sdim, int bdim, CBody<real>* blk_cb,
-                                               SList<real>* blk_sl, real* aux, real* pool, int cap) {
+                                               SList<real>* blk_sl, real* aux, real* pool, int cap, int bar_id) {
   for (int l = 0, lo = 0; l < n_lv; l++) {
     const int hi = lhd[2 + l];
     for (int i = lo + st; i < hi; i += sdim) {
@@ -995,7 +1009,7 @@ __device__ __forceinline__ void contact_rounds(const CPar<real> cpar, real* mt, 
       }
     }
     lo = hi;
-    if (BLK) __syncthreads(); else __syncwarp();
+    if (BLK) robot_sync(bar_id, sdim); else __syncwarp();
   }
 }
 
@@ -1102,7 +1116,9 @@ static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list cap
 #endif
 // FAST = the default voxel (all four scaffoldings, reduced-mass springs): no per-spring branch,
 // constant gamma.  Everything else takes the generic instantiation.
-// BLK = one robot per block (33..128 voxels): neighbour exchange through shared memory and
+// BLK = big robots (33..128 voxels): a robot takes P.wpr whole warps, a block holds P.rpb of them; the robots of a
+// block meet at the block-wide phase barriers only (instruction-fetch locality), everything inside a phase is
+// synchronised per robot with a named barrier; neighbour exchange through shared memory and
 // block-wide votes instead of warp shuffles / ballots.
 template <typename real, int CTRL, bool FAST, bool BLK>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_kernel(const Params<real> P) {
@@ -1116,7 +1132,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   typedef typename Real4T<real>::type R4;
   typedef typename Real2T<real>::type R2;
   // compile-time stride (= the largest block) so that every access has an immediate offset
-  constexpr int SPR_STRIDE = BLK ? 128 : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  constexpr int SPR_STRIDE = BLK ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  // the robot of this thread inside its block (BLK): its index, its thread count, this thread's / warp's index in it
+  const int wpr = BLK ? P.wpr : 1, rpb = BLK ? P.rpb : 1;
+  const int rthreads = wpr << 5;
+  const int rib = BLK ? (int)(threadIdx.x >> 5) / wpr : 0;
+  const int rt = BLK ? (int)threadIdx.x - rib * rthreads : 0;
+  const int wir = BLK ? (int)(threadIdx.x >> 5) - rib * wpr : 0;
+  const int bar_id = rib + 1;
   const int tid = threadIdx.x;
   R4* spr = reinterpret_cast<R4*>(smem_raw);                                  // [18][SPR_STRIDE]
   R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
@@ -1131,34 +1154,34 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   constexpr int mts = MTS;
   real* const mt = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp;
   // list header: [0] ground items, [1] levels, [2..33] end offset of each level, [34..] scratch
-  int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS) + (BLK ? 0 : wib * VSR_LHD_REALS);
+  int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS) + (BLK ? rib : wib) * VSR_LHD_REALS;
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
-  real* const ex = mt + 16 * MTS + (size_t)(BLK ? 1 : (blockDim.x >> 5)) * VSR_LHD_REALS;
+  real* const ex = mt + 16 * MTS + (size_t)(BLK ? rpb : (blockDim.x >> 5)) * VSR_LHD_REALS;
   // the tick's constraints as the solver rounds read them: [VSR_POOL_FIELDS][pool_cap]
   const int cap = P.pool_cap;  // per scope
-  real* const pool = ex + (BLK ? 2 * 20 * 128 : wib * VSR_POOL_FIELDS * cap);
-  const int st = BLK ? tid : lane, sdim = BLK ? blockDim.x : 32;  // thread index / size of the scope
+  real* const pool = ex + (BLK ? 2 * 20 * SPR_STRIDE + rib * VSR_POOL_FIELDS * cap : wib * VSR_POOL_FIELDS * cap);
+  const int st = BLK ? rt : lane, sdim = BLK ? rthreads : 32;  // thread index / size of the scope
   real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
   // (a thread lists at most 4 * MAXC ground + VSR_MAX_CAND intra-robot constraints)
-  int* const items = P.lbuf + (size_t)blockIdx.x * VSR_ITEMS_PER_THREAD * MTS + (BLK ? 0 : wib * VSR_ITEMS_PER_THREAD * 32);
+  int* const items = P.lbuf + (size_t)blockIdx.x * VSR_ITEMS_PER_THREAD * MTS + (BLK ? rib * VSR_ITEMS_PER_THREAD * rthreads : wib * VSR_ITEMS_PER_THREAD * 32);
   const int mt_t = tid;
-#define SSYNC() { if (BLK) __syncthreads(); else __syncwarp(); }
+#define SSYNC() { if (BLK) robot_sync(bar_id, rthreads); else __syncwarp(); }
   int exsel = 0;
-#define EXP(slot_, value_) if (BLK) ex[(exsel * 20 + (slot_)) * 128 + tid] = (value_);
-#define EXSYNC() if (BLK) __syncthreads();
-#define EXG(slot_, value_, src_) (BLK ? ex[(exsel * 20 + (slot_)) * 128 + (src_)] : shfl(value_, src_))
+#define EXP(slot_, value_) if (BLK) ex[(exsel * 20 + (slot_)) * SPR_STRIDE + tid] = (value_);
+#define EXSYNC() if (BLK) robot_sync(bar_id, rthreads);
+#define EXG(slot_, value_, src_) (BLK ? ex[(exsel * 20 + (slot_)) * SPR_STRIDE + (src_)] : shfl(value_, src_))
 #define EXFLIP() if (BLK) exsel ^= 1;
   const int nvox = S.nvox;
   const int G = BLK ? 1 : 32 / nvox;
   const int slot = BLK ? 0 : lane / nvox;
-  const int v = BLK ? tid : lane - slot * nvox;
-  const bool lane_ok = BLK ? (tid < nvox) : (slot < G);
-  const int lane0 = BLK ? 0 : slot * nvox;  // first lane (thread) of this lane's robot
+  const int v = BLK ? rt : lane - slot * nvox;
+  const bool lane_ok = BLK ? (rt < nvox) : (slot < G);
+  const int lane0 = BLK ? rib * rthreads : slot * nvox;  // first lane (block thread, BLK) of this lane's robot
   // lanes of this robot, for robot-wide votes
-  const unsigned robot_mask = lane_ok ? (((nvox == 32) ? 0xffffffffu : ((1u << nvox) - 1u)) << lane0) : 0u;
+  const unsigned robot_mask = (!BLK && lane_ok) ? (((nvox == 32) ? 0xffffffffu : ((1u << nvox) - 1u)) << lane0) : 0u;
   // neighbour lanes (own lane when absent: the shuffled value is then ignored)
   int nl[4];
   bool has[4];
@@ -1192,10 +1215,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   // the block-wide barriers below are legal.  The barriers carry no data: they keep the warps of
   // an SM inside the same stretch of the (large, fully unrolled) instruction stream, which turns
   // instruction-cache misses of one warp into hits for the others.
-  const long long warps_total = BLK ? (long long)gridDim.x : (long long)gridDim.x * wpb;
+  const long long warps_total = BLK ? (long long)gridDim.x * rpb : (long long)gridDim.x * wpb;
   const long long n_pass = (n_groups + warps_total - 1) / warps_total;
   for (long long pass = 0; pass < n_pass; pass++) {
-    const long long group = pass * warps_total + (BLK ? (long long)blockIdx.x : (long long)blockIdx.x * wpb + wib);
+    const long long group = pass * warps_total + (BLK ? (long long)blockIdx.x * rpb + rib : (long long)blockIdx.x * wpb + wib);
     const long long rb = group * G + slot;  // bucket index of this lane's robot
     const bool active = lane_ok && rb < P.n_robots;
     const long long gl = rb * nvox + v;     // global voxel lane (ring addressing)
@@ -1305,7 +1328,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           }
         }
         SSYNC()
-        contact_rounds<ROUND_WARM, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
+        contact_rounds<ROUND_WARM, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap, bar_id);
         VSR_MT_GET(vx, vy, w)
       }
       // ---- springs: DistanceJoint.initializeConstraints + warm start
@@ -1491,7 +1514,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         if (n_lv > 0) {
           VSR_MT_PUT(vx, vy, w)
           SSYNC()
-          contact_rounds<ROUND_VELOCITY, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
+          contact_rounds<ROUND_VELOCITY, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap, bar_id);
           VSR_MT_GET(vx, vy, w)
         }
       }
@@ -1533,7 +1556,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       {
         bool done = BLK ? !(rb < P.n_robots) : !active;  // BLK: idle threads follow their block
         for (int it = 0; it < P.pos_iters; it++) {
-          const bool wdone = BLK ? done : (bool)__all_sync(0xffffffffu, done);  // BLK: done is block-uniform
+          const bool wdone = BLK ? done : (bool)__all_sync(0xffffffffu, done);  // BLK: done is robot-uniform
           if (wdone) break;
           bool solved = true;
           if (n_lv > 0) {
@@ -1541,7 +1564,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             aux[0 * bdim + tid] = done ? real(1) : real(0);
             aux[1 * bdim + tid] = real(0);
             SSYNC()
-            contact_rounds<ROUND_POSITION, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap);
+            contact_rounds<ROUND_POSITION, BLK>(cpar, mt, MTS, lhd, items, n_lv, st, sdim, bdim, blk_cb, blk_sl, aux, pool, cap, bar_id);
             if (!done) {
               VSR_MT_GET(x, y, th)
               r_sincos(th[1], &sn_[1], &cs_[1]);
@@ -1622,7 +1645,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           }  // !wdone
           // robot-wide (island-wide) vote
           if (BLK) {
-            if (__syncthreads_and(solved || done)) done = true;
+            if (robot_sync_and(bar_id, rthreads, solved || done)) done = true;
           } else {
             unsigned bal = __ballot_sync(0xffffffffu, solved || done);
             if ((bal & robot_mask) == robot_mask) done = true;
@@ -1638,11 +1661,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       const unsigned old_cmask = cmask;
       cmask = 0;
       unsigned gcn = 0;  // ground constraints per mass, 4 bits each
-      if (cap * VSR_POOL_FIELDS >= 416 * (BLK ? wpb : 1)) {
+      if (cap * VSR_POOL_FIELDS >= 416 * wpr) {
         // Only a few masses of a warp are near the ground.  Those (by the coarse height map; a mass that
         // had contacts always) are listed for the whole warp and detected one per lane, writing straight
         // into their owners' records; the pool -- idle during detection -- is the scratch space.
-        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 416 : 0);  // [32][5] hints + flags, [128] list, [32][4] results
+        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wir * 416 : 0);  // [32][5] hints + flags, [128] list, [32][4] results
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           mt[VSR_MTK(k, 0)] = x[k]; mt[VSR_MTK(k, 1)] = y[k]; mt[VSR_MTK(k, 2)] = cs_[k]; mt[VSR_MTK(k, 3)] = sn_[k];
@@ -1731,7 +1754,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       // ---- intra-robot pairs: every mass against every later mass of the robot that is not welded
       //      to it.  Order inside a robot = (owner voxel, partner voxel, partner mass, own mass),
       //      the oracle's canonical enumeration.
-      const int rbase = BLK ? 0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
+      const int rbase = BLK ? lane0 : (wib << 5) + lane0;  // block thread of this robot's first voxel
       unsigned smask = 0;  // slots of the new list that hold a constraint
       unsigned long long lvpack[2] = {0ull, 0ull};  // dependency level of each of this thread's constraints, 8 bits each
       if (P.self_coll) {
@@ -1750,9 +1773,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         // list.  With the pool as scratch space the candidates are written there as they are found and the warp's
         // candidates are spread over its lanes afterwards (one narrowphase round); without it every thread runs the
         // narrowphase of a candidate on the spot.
-        const bool pooled_np = cap * VSR_POOL_FIELDS >= 576 * (BLK ? wpb : 1);
+        const bool pooled_np = cap * VSR_POOL_FIELDS >= 576 * wpr;
         // scratch: [32][16] candidates and the [512] list as 16-bit words, [32] meta and [32] results as words
-        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wib * 576 : 0);
+        int* const scr = reinterpret_cast<int*>(pool) + (BLK ? wir * 576 : 0);
         unsigned short* const scand = reinterpret_cast<unsigned short*>(scr);        // words [0, 256)
         unsigned short* const slist = reinterpret_cast<unsigned short*>(scr + 288);  // words [288, 544)
         int n_cand = 0;
@@ -1836,12 +1859,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
         int s_start, s_tot;
         if (BLK) {
-          if (lane == 31) lhd[66 + wib] = incl;
-          __syncthreads();
+          if (lane == 31) lhd[66 + wir] = incl;
+          SSYNC()
           int before = 0, all = 0;
-          for (int q = 0; q < wpb; q++) {
+          for (int q = 0; q < wpr; q++) {
             const int c = lhd[66 + q];
-            before += q < wib ? c : 0;
+            before += q < wir ? c : 0;
             all += c;
           }
           s_start = before + incl - n_new;
@@ -2181,8 +2204,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       } else {
         // CentralizedSensing + MultiLayerPerceptron.apply: inputs = readings of all voxels
         // in voxel order; lane j of the robot evaluates neurons j, j+nvox, ...
-        const int per_robot = BLK ? (blockDim.x >> 5) * P.smem_per_warp : P.smem_per_warp / (G > 0 ? G : 1);
-        real* act0 = BLK ? stage_blk : stage + (size_t)(lane_ok ? slot : 0) * per_robot;
+        const int per_robot = BLK ? wpr * P.smem_per_warp : P.smem_per_warp / (G > 0 ? G : 1);
+        real* act0 = BLK ? stage_blk + (size_t)rib * per_robot : stage + (size_t)(lane_ok ? slot : 0) * per_robot;
         real* act1 = act0 + per_robot / 2;
         if (active) {
           int base = S.read_off[v];
@@ -2190,7 +2213,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll 1
           for (int q = 0; q < nr; q++) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
         }
-        if (BLK) __syncthreads(); else __syncwarp();
+        SSYNC()
         real* a = act0;
         real* b = act1;
         for (int li = 1; li < S.n_layers; li++) {
@@ -2203,11 +2226,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               b[j] = activation<real>(P.mlp_act, sum);
             }
           }
-          if (BLK) __syncthreads(); else __syncwarp();
+          SSYNC()
           real* t = a; a = b; b = t;
         }
         f = active ? a[v] : real(0);
-        if (BLK) __syncthreads(); else __syncwarp();
+        SSYNC()
       }
       if (r_abs(f) > real(1)) f = f > real(0) ? real(1) : real(-1);
       last_f = f;
@@ -2241,23 +2264,25 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       if (tick == 0 || tick == P.n_ticks - 1) {
         // BehaviorUtils.center: mean over voxels of the mean of the 4 outer corners,
         // summed by the robot's first lane in voxel order (the oracle's order)
-        real* st = BLK ? stage_blk : stage;
-        const int sidx = BLK ? tid : lane;
-        if (BLK) __syncthreads(); else __syncwarp();
+        // (BLK: the robot's own slice of the staging area -- the robots of a block pass this point at different times)
+        real* st = BLK ? stage_blk + (size_t)rib * wpr * P.smem_per_warp : stage;
+        const int sidx = BLK ? rt : lane;
+        const int sl0 = BLK ? 0 : lane0;
+        SSYNC()
         if (lane_ok) {
           st[sidx * 4 + 0] = (((ox[0] + ox[1]) + ox[2]) + ox[3]) / real(4);
           st[sidx * 4 + 1] = (((oy[0] + oy[1]) + oy[2]) + oy[3]) / real(4);
           st[sidx * 4 + 2] = ar_energy;
           st[sidx * 4 + 3] = ctrl_energy;
         }
-        if (BLK) __syncthreads(); else __syncwarp();
+        SSYNC()
         if (active && v == 0) {
           double sx = 0, sy = 0, sa = 0, sc = 0;
           for (int q = 0; q < nvox; q++) {
-            sx = sx + (double)st[(lane0 + q) * 4 + 0];
-            sy = sy + (double)st[(lane0 + q) * 4 + 1];
-            sa += (double)st[(lane0 + q) * 4 + 2];
-            sc += (double)st[(lane0 + q) * 4 + 3];
+            sx = sx + (double)st[(sl0 + q) * 4 + 0];
+            sy = sy + (double)st[(sl0 + q) * 4 + 1];
+            sa += (double)st[(sl0 + q) * 4 + 2];
+            sc += (double)st[(sl0 + q) * 4 + 3];
           }
           double cx = sx / (double)nvox + P.origin_x, cy = sy / (double)nvox;
           if (tick == 0) {
@@ -2276,7 +2301,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             *reinterpret_cast<int2*>(&R[10]) = tail;
           }
         }
-        if (BLK) __syncthreads(); else __syncwarp();
+        SSYNC()
         if (tick == P.n_ticks - 1) {
           // Robot.boundingBox (Robot.java:116-120) = the largest box of the voxels' outer corners
           // (Voxel.java:481-495): what a later stage of a task is placed by (DevoLocomotion.java)
@@ -2286,17 +2311,17 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             st[sidx * 4 + 2] = r_max(r_max(ox[0], ox[1]), r_max(ox[2], ox[3]));
             st[sidx * 4 + 3] = r_max(r_max(oy[0], oy[1]), r_max(oy[2], oy[3]));
           }
-          if (BLK) __syncthreads(); else __syncwarp();
+          SSYNC()
           if (active && v == 0) {
-            real bx0 = st[lane0 * 4 + 0], by0 = st[lane0 * 4 + 1], bx1 = st[lane0 * 4 + 2], by1 = st[lane0 * 4 + 3];
+            real bx0 = st[sl0 * 4 + 0], by0 = st[sl0 * 4 + 1], bx1 = st[sl0 * 4 + 2], by1 = st[sl0 * 4 + 3];
             for (int q = 1; q < nvox; q++) {
-              bx0 = r_min(bx0, st[(lane0 + q) * 4 + 0]); by0 = r_min(by0, st[(lane0 + q) * 4 + 1]);
-              bx1 = r_max(bx1, st[(lane0 + q) * 4 + 2]); by1 = r_max(by1, st[(lane0 + q) * 4 + 3]);
+              bx0 = r_min(bx0, st[(sl0 + q) * 4 + 0]); by0 = r_min(by0, st[(sl0 + q) * 4 + 1]);
+              bx1 = r_max(bx1, st[(sl0 + q) * 4 + 2]); by1 = r_max(by1, st[(sl0 + q) * 4 + 3]);
             }
             double* B = P.final_bbox + (size_t)P.robot_ids[rb] * 4;
             B[0] = (double)bx0 + P.origin_x; B[1] = (double)by0; B[2] = (double)bx1 + P.origin_x; B[3] = (double)by1;
           }
-          if (BLK) __syncthreads(); else __syncwarp();
+          SSYNC()
         }
       }
     }
