@@ -160,6 +160,9 @@ struct vsr_batch {
   std::vector<double> terr_x, terr_y;  // local frame
   double base_y = 0, origin_x = 0;
   double rng_min[3], rng_rest[3], rng_max[3];
+  // passive-range limits of the springs (Voxel.java:262-285,331-338): lower / upper per range class, when finite
+  bool lim_lo_on = false, lim_hi_on = false;
+  double lim_lo[3] = {0, 0, 0}, lim_hi[3] = {0, 0, 0};
   double inv_m = 0, inv_i = 0, half = 0, red_mass = 0;
   unsigned spring_mask = 0;
   size_t voxel_steps = 0;
@@ -276,8 +279,6 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       return fail(VSR_ERR_INVALID_ARGUMENT, "Min of areaRatioPassiveRange cannot be lower than the value imposed by massSideLengthRatio");
     if (m.area_ratio_passive_max < m.area_ratio_passive_min || m.area_ratio_active_max < m.area_ratio_active_min)
       return fail(VSR_ERR_INVALID_ARGUMENT, "Max has to be lower or equal than min");  // DoubleRange.java:29-35
-    if (std::isfinite(m.area_ratio_passive_min) || std::isfinite(m.area_ratio_passive_max))
-      return fail(VSR_ERR_UNSUPPORTED, "finite areaRatioPassiveRange (DistanceJoint rope limits) is not on the accelerated path");
     if (!(m.side_length > 0) || !(m.mass > 0) || !(m.mass_side_length_ratio > 0) || !(m.spring_f > 0))
       return fail(VSR_ERR_INVALID_ARGUMENT, "non-positive voxel material parameter");
   }
@@ -325,6 +326,21 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
         delete b;
         return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
       }
+    // the passive SpringRanges: finite bounds become the DistanceJoints' lower / upper limits
+    b->lim_lo_on = std::isfinite(m.area_ratio_passive_min);
+    b->lim_hi_on = std::isfinite(m.area_ratio_passive_max);
+    {
+      const double pmin = b->lim_lo_on ? sqrt(L * L * m.area_ratio_passive_min) : 0.0;
+      const double pmax = b->lim_hi_on ? sqrt(L * L * m.area_ratio_passive_max) : 0.0;
+      b->lim_lo[0] = pmin - 2.0 * ms; b->lim_hi[0] = pmax - 2.0 * ms;
+      b->lim_lo[1] = sqrt(ms * ms + b->lim_lo[0] * b->lim_lo[0]); b->lim_hi[1] = sqrt(ms * ms + b->lim_hi[0] * b->lim_hi[0]);
+      b->lim_lo[2] = (pmin - ms) * sqrt(2.0); b->lim_hi[2] = (pmax - ms) * sqrt(2.0);
+      for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193 (a NaN bound of an infinite range passes there too)
+        if ((b->lim_lo_on && (b->lim_lo[c] > b->rng_rest[c] || b->lim_lo[c] < 0)) || (b->lim_hi_on && b->lim_hi[c] < b->rng_rest[c])) {
+          delete b;
+          return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
+        }
+    }
     unsigned mask = 0;
     if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_INTERNAL) mask |= 0x000Fu;
     if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_EXTERNAL) mask |= 0x00F0u;
@@ -872,7 +888,12 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
     P.rng_min[c] = (real)b->rng_min[c];
     P.rng_rest[c] = (real)b->rng_rest[c];
     P.rng_max[c] = (real)b->rng_max[c];
+    P.lim_lo[c] = (real)b->lim_lo[c];
+    P.lim_hi[c] = (real)b->lim_hi[c];
   }
+  P.lim_lo_on = b->lim_lo_on ? 1 : 0;
+  P.lim_hi_on = b->lim_hi_on ? 1 : 0;
+  const bool lim = b->lim_lo_on || b->lim_hi_on;
   P.weld_len = (real)(2.0 * b->half);
   P.vel_iters = st.velocity_iterations;
   P.pos_iters = st.position_iterations;
@@ -919,7 +940,8 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   // Big robots: a robot takes wpr whole warps and a block holds rpb robots that walk the instruction stream
   // together (one 2..4-warp block per robot ran at its own PC: instruction fetch was 30 % of the stall samples);
   // the block's tables have `stride` thread columns (fp32 256, fp64 128).
-  const int stride = blk ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  const int stride = (blk || lim) ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  if (!blk) wpb = std::min(wpb, stride / 32);
   const int wpr = blk ? (nvox + 31) / 32 : 1;
   int rpb = blk ? std::max(1, std::min(stride / 32, std::max(wpb_fill, wpr)) / wpr) : 1;
   if (blk) {
@@ -933,7 +955,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
   // contact exchange (+ the neighbour exchange of the big-robot variant)
   auto fixed_smem = [&](int wpb_, int rpb_) {
-    return (size_t)18 * stride * (6 + (eff_mode ? 1 : 0)) * sizeof(real) +
+    return (size_t)18 * stride * (6 + (eff_mode ? 1 : 0) + (lim ? 2 : 0)) * sizeof(real) +
            ((size_t)wpb_ * P.smem_per_warp + (size_t)16 * stride + (size_t)(blk ? rpb_ : wpb_) * VSR_LHD_REALS) * sizeof(real) +
            (blk ? (size_t)2 * 20 * stride * sizeof(real) : 0);
   };
@@ -959,10 +981,10 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   }
   P.sync_mode = tuning_env("VSR_SYNC") ? atoi(tuning_env("VSR_SYNC")) : (2 | 16 | 32 | 64);
   void (*kern)(const Params<real>) = nullptr;
-  const bool fast = (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
+  const bool fast = !lim && (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
 #define VSR_PICK(C)                                                                                  \
-  kern = blk ? (fast ? vsr_episode_kernel<real, C, true, true> : vsr_episode_kernel<real, C, false, true>) \
-             : (fast ? vsr_episode_kernel<real, C, true, false> : vsr_episode_kernel<real, C, false, false>)
+  kern = blk ? (fast ? vsr_episode_kernel<real, C, 1, true> : (lim ? vsr_episode_kernel<real, C, 2, true> : vsr_episode_kernel<real, C, 0, true>)) \
+             : (fast ? vsr_episode_kernel<real, C, 1, false> : (lim ? vsr_episode_kernel<real, C, 2, false> : vsr_episode_kernel<real, C, 0, false>))
   switch (d.controller_kind) {
     case VSR_CTRL_PHASE_SIN: VSR_PICK(CTRL_PHASE_SIN); break;
     case VSR_CTRL_TABULATED: VSR_PICK(CTRL_TABULATED); break;

@@ -137,6 +137,9 @@ struct Params {
   int vel_iters, pos_iters;
   int spring_mode;       // 0 reduced mass, 1 effective mass
   unsigned spring_mask;  // bit s = spring s present (scaffoldings)
+  // passive-range ("rope") limits of the springs, per range class; only the LIM instantiation reads them
+  int lim_lo_on, lim_hi_on;
+  real lim_lo[3], lim_hi[3];
   int mlp_act;
   int dist_signals;      // DistributedSensing: signals per side; < 0 for the other controllers
   int dist_nd;           // DistributedSensingNonDirectional: one set of signals for all neighbours
@@ -1114,16 +1117,20 @@ static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list cap
 #ifndef VSR_MIN_BLOCKS
 #define VSR_MIN_BLOCKS 1
 #endif
-// FAST = the default voxel (all four scaffoldings, reduced-mass springs): no per-spring branch,
-// constant gamma.  Everything else takes the generic instantiation.
+// MODE 1 (FAST) = the default voxel (all four scaffoldings, reduced-mass springs, no limits): no per-spring
+// branch, constant gamma.  MODE 0 = generic (partial scaffoldings, effective-mass springs).  MODE 2 (LIM) = generic
+// + the DistanceJoint limits of a finite areaRatioPassiveRange (Voxel.java:331-338): two more accumulated impulses
+// per spring, a one-sided rigid row per limit after each spring row and a position correction of the violated
+// limit (256 / 128 thread columns per block: the per-tick constants take 36 bytes more per spring).
 // BLK = big robots (33..128 voxels): a robot takes P.wpr whole warps, a block holds P.rpb of them; the robots of a
 // block meet at the block-wide phase barriers only (instruction-fetch locality), everything inside a phase is
 // synchronised per robot with a named barrier; neighbour exchange through shared memory and
 // block-wide votes instead of warp shuffles / ballots.
-template <typename real, int CTRL, bool FAST, bool BLK>
+template <typename real, int CTRL, int MODE, bool BLK>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
+  constexpr bool FAST = MODE == 1, LIM = MODE == 2;
   constexpr bool FULLSPR = FAST;
   const bool EFFMASS = FAST ? false : (P.spring_mode != 0);
   const int lane = threadIdx.x & 31;
@@ -1132,7 +1139,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   typedef typename Real4T<real>::type R4;
   typedef typename Real2T<real>::type R2;
   // compile-time stride (= the largest block) so that every access has an immediate offset
-  constexpr int SPR_STRIDE = BLK ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  constexpr int SPR_STRIDE = (BLK || LIM) ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   // the robot of this thread inside its block (BLK): its index, its thread count, this thread's / warp's index in it
   const int wpr = BLK ? P.wpr : 1, rpb = BLK ? P.rpb : 1;
   const int rthreads = wpr << 5;
@@ -1144,7 +1151,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   R4* spr = reinterpret_cast<R4*>(smem_raw);                                  // [18][SPR_STRIDE]
   R2* spr2 = reinterpret_cast<R2*>(spr + 18 * SPR_STRIDE);                     // [18][SPR_STRIDE]
   real* sgam = reinterpret_cast<real*>(spr2 + 18 * SPR_STRIDE);               // [18][SPR_STRIDE], effective-mass mode only
-  real* stage = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)wib * P.smem_per_warp;
+  R2* const slim = reinterpret_cast<R2*>(sgam + (EFFMASS ? 18 * SPR_STRIDE : 0));  // [18][SPR_STRIDE] (rigid mass, length), LIM only
+  real* const sfree = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (LIM ? 2 * 18 * SPR_STRIDE : 0);  // end of the spring tables
+  real* stage = sfree + (size_t)wib * P.smem_per_warp;
   // Contact exchange, block-wide.  Contacts are sparse and irregular (a few masses of a robot touch
   // the ground or each other), so the block pools them: every thread posts the state of its masses
   // in the mass table mt[16 fields][MTS threads] (see VSR_MTI), the block's constraints -- listed
@@ -1152,7 +1161,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   // owners read their masses back.
   constexpr int MTS = SPR_STRIDE;  // the largest block of this instantiation
   constexpr int mts = MTS;
-  real* const mt = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0) + (size_t)(blockDim.x >> 5) * P.smem_per_warp;
+  real* const mt = sfree + (size_t)(blockDim.x >> 5) * P.smem_per_warp;
   // list header: [0] ground items, [1] levels, [2..33] end offset of each level, [34..] scratch
   int* const lhd = reinterpret_cast<int*>(mt + 16 * MTS) + (BLK ? rib : wib) * VSR_LHD_REALS;
   // neighbour exchange of the one-block-per-robot variant: [2 buffers][20 fields][128 threads]
@@ -1161,7 +1170,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   const int cap = P.pool_cap;  // per scope
   real* const pool = ex + (BLK ? 2 * 20 * SPR_STRIDE + rib * VSR_POOL_FIELDS * cap : wib * VSR_POOL_FIELDS * cap);
   const int st = BLK ? rt : lane, sdim = BLK ? rthreads : 32;  // thread index / size of the scope
-  real* const stage_blk = sgam + (EFFMASS ? 18 * SPR_STRIDE : 0);
+  real* const stage_blk = sfree;
   // 4 reals per thread of block-wide scratch (the controller staging is idle outside control)
   real* const aux = stage_blk;
   const int bdim = blockDim.x;
@@ -1240,6 +1249,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
     for (int s = 0; s < 18; s++) simp[s] = real(0);
     real rest[3] = {P.rng_rest[0], P.rng_rest[1], P.rng_rest[2]};  // Voxel.reset: applyForce(0)
+    // accumulated impulses of the lower / upper limit rows (LIM)
+    real slo[LIM ? 18 : 1], shi[LIM ? 18 : 1];
+#pragma unroll
+    for (int s = 0; s < (LIM ? 18 : 1); s++) slo[s] = shi[s] = real(0);
+    const real inv_dt = real(1) / dt;
     // weld impulses: [side L,R,D,U][pair][x,y,z]
     real wix[4][2], wiy[4][2], wiz[4][2];
 #pragma unroll
@@ -1365,10 +1379,16 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       R2 p_; p_.x = soft; p_.y = bias;                                                             \
       spr2[s * SPR_STRIDE + tid] = p_;                                                             \
       if (EFFMASS) sgam[s * SPR_STRIDE + tid] = gamma;                                             \
+      if (LIM) {                                                                                   \
+        R2 l_; l_.x = real(1) / invMass; l_.y = len; /* the rigid row's effective mass, currentDistance */ \
+        slim[s * SPR_STRIDE + tid] = l_;                                                           \
+      }                                                                                            \
     }                                                                                              \
-    real jx = nx * simp[s], jy = ny * simp[s];                                                     \
-    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * cr1 * simp[s];                             \
-    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * cr2 * simp[s];                             \
+    /* warm start: spring + lower - upper along n (DistanceJoint.initializeConstraints) */         \
+    const real wi_ = LIM ? simp[s] + slo[LIM ? s : 0] - shi[LIM ? s : 0] : simp[s];                \
+    real jx = nx * wi_, jy = ny * wi_;                                                             \
+    vx[b1] += jx * im; vy[b1] += jy * im; w[b1] += ii * cr1 * wi_;                                 \
+    vx[b2] -= jx * im; vy[b2] -= jy * im; w[b2] -= ii * cr2 * wi_;                                 \
   }
       VSR_SPRINGS(VSR_SPRING_INIT)
 #undef VSR_SPRING_INIT
@@ -1450,6 +1470,36 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     const R2 p_ = p##s;                                                                               \
     const real g_ = EFFMASS ? sgam[s * SPR_STRIDE + tid] : gam_c;                                     \
     spring_solve(vx[b1], vy[b1], w[b1], vx[b2], vy[b2], w[b2], simp[s], q_, p_, g_, im, ii);          \
+    if (LIM) {                                                                                        \
+      /* the limit rows of DistanceJoint.solveVelocityConstraints (dyn4j 4.2 = Box2D 2.4's joint; the     \
+         oracle's spring_limits_solve): one-sided, accumulated impulse >= 0, bias = max(0, C) / dt */  \
+      const R2 l_ = slim[s * SPR_STRIDE + tid];                                                       \
+      if (P.lim_lo_on) {                                                                              \
+        const real C_ = l_.y - P.lim_lo[cls];                                                         \
+        const real bias_ = r_max(C_, real(0)) * inv_dt;                                               \
+        const real Jv_ = q_.x * (vx[b1] - vx[b2]) + q_.y * (vy[b1] - vy[b2]) + q_.z * w[b1] - q_.w * w[b2]; \
+        real j_ = -l_.x * (Jv_ + bias_);                                                              \
+        const real nw_ = r_max(slo[LIM ? s : 0] + j_, real(0));                                       \
+        j_ = nw_ - slo[LIM ? s : 0];                                                                  \
+        slo[LIM ? s : 0] = nw_;                                                                       \
+        const real jx_ = q_.x * j_, jy_ = q_.y * j_;                                                  \
+        vx[b1] += jx_ * im; vy[b1] += jy_ * im; w[b1] += ii * q_.z * j_;                              \
+        vx[b2] -= jx_ * im; vy[b2] -= jy_ * im; w[b2] -= ii * q_.w * j_;                              \
+      }                                                                                               \
+      if (P.lim_hi_on) {                                                                              \
+        const real C_ = P.lim_hi[cls] - l_.y;                                                         \
+        const real bias_ = r_max(C_, real(0)) * inv_dt;                                               \
+        const real Jv_ = -(q_.x * (vx[b1] - vx[b2]) + q_.y * (vy[b1] - vy[b2]) + q_.z * w[b1] - q_.w * w[b2]); \
+        real j_ = -l_.x * (Jv_ + bias_);                                                              \
+        const real nw_ = r_max(shi[LIM ? s : 0] + j_, real(0));                                       \
+        j_ = nw_ - shi[LIM ? s : 0];                                                                  \
+        shi[LIM ? s : 0] = nw_;                                                                       \
+        j_ = -j_;                                                                                     \
+        const real jx_ = q_.x * j_, jy_ = q_.y * j_;                                                  \
+        vx[b1] += jx_ * im; vy[b1] += jy_ * im; w[b1] += ii * q_.z * j_;                              \
+        vx[b2] -= jx_ * im; vy[b2] -= jy_ * im; w[b2] -= ii * q_.w * j_;                              \
+      }                                                                                               \
+    }                                                                                                 \
   }
         R4 qn_ = spr[tid];
         R2 pn_ = spr2[tid];
@@ -1571,6 +1621,38 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               r_sincos(th[2], &sn_[2], &cs_[2]);
               solved = aux[1 * bdim + tid] == real(0);
             }
+          }
+          if (LIM && !wdone) {
+            // DistanceJoint.solvePositionConstraints with limits (the oracle's spring_limits_position): the violated
+            // limit is corrected rigidly with the effective mass of this step's initialisation; the joints come in
+            // the island's order, the springs of a voxel before the welds
+            r_sincos(th[0], &sn_[0], &cs_[0]);
+            r_sincos(th[3], &sn_[3], &cs_[3]);
+            const real pm_ = done ? real(0) : real(1);
+#define VSR_SPRING_POS(s, nxt, b1, b2, a1x, a1y, a2x, a2y, cls)                                            \
+  if (P.spring_mask & (1u << s)) {                                                                    \
+    const real h_ = P.half;                                                                           \
+    const real r1x = (real(a1x) * cs_[b1] - real(a1y) * sn_[b1]) * h_, r1y = (real(a1x) * sn_[b1] + real(a1y) * cs_[b1]) * h_; \
+    const real r2x = (real(a2x) * cs_[b2] - real(a2y) * sn_[b2]) * h_, r2y = (real(a2x) * sn_[b2] + real(a2y) * cs_[b2]) * h_; \
+    real nx = r1x + x[b1] - (r2x + x[b2]), ny = r1y + y[b1] - (r2y + y[b2]);                          \
+    const real len = r_sqrt(nx * nx + ny * ny);                                                       \
+    const real inv = len > real(0) ? real(1) / len : real(0);                                         \
+    nx *= inv; ny *= inv;                                                                             \
+    const bool lo_ = P.lim_lo_on && len < P.lim_lo[cls], hi_ = !lo_ && P.lim_hi_on && len > P.lim_hi[cls]; \
+    if (lo_ || hi_) {                                                                                 \
+      real C_ = lo_ ? len - P.lim_lo[cls] : len - P.lim_hi[cls];                                      \
+      C_ = r_clamp<real>(C_, -P.max_corr, P.max_corr);                                                \
+      const real imp_ = -slim[s * SPR_STRIDE + tid].x * C_ * pm_;                                     \
+      const real Jx = nx * imp_, Jy = ny * imp_;                                                      \
+      x[b1] += Jx * im; y[b1] += Jy * im; th[b1] += ii * (r1x * Jy - r1y * Jx);                       \
+      x[b2] -= Jx * im; y[b2] -= Jy * im; th[b2] -= ii * (r2x * Jy - r2y * Jx);                       \
+      r_sincos(th[b1], &sn_[b1], &cs_[b1]);                                                           \
+      r_sincos(th[b2], &sn_[b2], &cs_[b2]);                                                           \
+      solved = solved && (r_abs(C_) < P.lin_tol);                                                     \
+    }                                                                                                 \
+  }
+            VSR_SPRINGS(VSR_SPRING_POS)
+#undef VSR_SPRING_POS
           }
           if (!wdone) {
           // WeldJoint.solvePositionConstraints: C = (p1 - p2, theta1 - theta2 - ref)

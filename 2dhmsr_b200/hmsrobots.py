@@ -444,6 +444,18 @@ class Voxel:
                 f"Min of areaRatioPassiveRange={m.area_ratio_passive_min} cannot be lower than the value "
                 f"({lim}) imposed by massSideLengthRatio={m.mass_side_length_ratio}"
             )
+        # Voxel.assemble builds the passive and active SpringRanges (Voxel.java:262-301); SpringRange (:189-193)
+        # rejects min > rest, max < rest, min < 0 (comparisons with the NaN of an infinite passive bound are false)
+        L, ms = m.side_length, m.side_length * m.mass_side_length_ratio
+        for a_min, a_max in ((m.area_ratio_passive_min, m.area_ratio_passive_max), (m.area_ratio_active_min, m.area_ratio_active_max)):
+            s_min = math.sqrt(L * L * a_min) if a_min >= 0 else math.nan
+            s_max = math.sqrt(L * L * a_max) if a_max >= 0 else math.nan
+            pp = (s_min - 2 * ms, L - 2 * ms, s_max - 2 * ms)
+            for lo_, rest_, hi_ in (pp,
+                                    tuple(math.sqrt(ms * ms + q * q) for q in pp),
+                                    ((s_min - ms) * math.sqrt(2.0), (L - ms) * math.sqrt(2.0), (s_max - ms) * math.sqrt(2.0))):
+                if lo_ > rest_ or hi_ < rest_ or lo_ < 0:
+                    raise ValueError(f"Wrong spring range [{lo_}, {rest_}, {hi_}]")
 
     def get_sensors(self) -> List[Sensor]:
         return self.sensors

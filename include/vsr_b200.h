@@ -77,8 +77,8 @@ typedef struct vsr_material {
   double friction;                /* 10.0  :63 */
   double restitution;             /* 0.1   :64 */
   double mass;                    /* 1.0   :65 */
-  double area_ratio_passive_min;  /* -inf  :66 (finite => rope limits: VSR_ERR_UNSUPPORTED) */
-  double area_ratio_passive_max;  /* +inf */
+  double area_ratio_passive_min;  /* -inf  :66; a finite bound becomes the lower / upper limit of every spring's   */
+  double area_ratio_passive_max;  /* +inf      DistanceJoint (the "rope" of Voxel.java:262-285,331-338)              */
   double area_ratio_active_min;   /* 0.8   :67 */
   double area_ratio_active_max;   /* 1.2 */
   uint32_t spring_scaffoldings;   /* bitmask of VSR_SCAFFOLD_*; :68 = all four */

@@ -28,9 +28,10 @@
  * Each numbered dyn4j item of SURVEY.md Appendix C sits behind one function so it
  * can be corrected if a dyn4j 4.2.1 run ever becomes available.
  *
- * Documented omissions: CCD/time-of-impact pass, at-rest sleeping
- * (actuated robots are woken every tick by setRestDistance), DistanceJoint limits
- * (disabled by the default passive range, Voxel.java:66,264-267,331-338).
+ * Documented omissions: at-rest sleeping (actuated robots are woken every tick by
+ * setRestDistance); the CCD / time-of-impact pass is behind vsr_oracle_opts.ccd (off by default, as in the kernel).
+ * DistanceJoint limits (a finite passive range, Voxel.java:66,264-267,331-338) are restated from the published
+ * Box2D 2.4 joint that dyn4j 4.2 ported.
  */
 #include "vsr_oracle.h"
 
@@ -152,6 +153,11 @@ typedef struct {
   double imp;                /* accumulated impulse (warm start) */
   double nx, ny, cr1, cr2, gamma, bias, soft;
   int full; /* index 0..17 in Voxel.allSpringJoints with all four scaffoldings */
+  /* passive-range limits ("rope", Voxel.java:331-338,370-377,433-440,460-467): DistanceJoint lower / upper limit */
+  int lo_on, hi_on;
+  double lo, hi;
+  double lo_imp, hi_imp; /* accumulated limit impulses (warm start) */
+  double mass, len;      /* rigid effective mass 1/K and the current length, from initializeConstraints */
 } OSpring;
 
 typedef struct {
@@ -270,9 +276,14 @@ static double ground_y_at(const vsr_batch_desc* d, double x) {
 }
 
 static void add_spring(ORobot* r, int b1, int b2, double a1x, double a1y, double a2x, double a2y,
-                       double rmin, double rrest, double rmax) {
+                       double rmin, double rrest, double rmax, double pmin, double pmax) {
   OSpring* s = &r->springs[r->ns++];
   memset(s, 0, sizeof *s);
+  /* joint.setLowerLimit / setUpperLimit only for a finite passive bound (Voxel.java:331-338) */
+  s->lo_on = pmin > -INFINITY;
+  s->hi_on = pmax < INFINITY;
+  s->lo = pmin;
+  s->hi = pmax;
   s->b1 = b1;
   s->b2 = b2;
   s->a1x = a1x;
@@ -337,8 +348,13 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   double h = ms / 2.0;
   static const double sx[4] = {-1, +1, +1, -1}; /* NW NE SE SW */
   static const double sy[4] = {+1, +1, -1, -1};
-  /* ranges :268-301 (passive range only gates the limits, which are disabled) */
+  /* ranges :262-301: the active ranges move the rest distances, the passive ones are the joints' limits */
   double amin = sqrt(L * L * m->area_ratio_active_min), amax = sqrt(L * L * m->area_ratio_active_max);
+  double pmin = sqrt(L * L * m->area_ratio_passive_min), pmax = sqrt(L * L * m->area_ratio_passive_max); /* NaN / inf when infinite */
+  int plo = isfinite(m->area_ratio_passive_min), phi = isfinite(m->area_ratio_passive_max);
+  double pp_min = plo ? pmin - 2.0 * ms : -INFINITY, pp_max = phi ? pmax - 2.0 * ms : INFINITY;
+  double pc_min = plo ? sqrt(ms * ms + pp_min * pp_min) : -INFINITY, pc_max = phi ? sqrt(ms * ms + pp_max * pp_max) : INFINITY;
+  double pd_min = plo ? (pmin - ms) * sqrt(2.0) : -INFINITY, pd_max = phi ? (pmax - ms) * sqrt(2.0) : INFINITY;
   double sp_min = amin - 2.0 * ms, sp_rest = L - 2.0 * ms, sp_max = amax - 2.0 * ms;
   double sc_min = sqrt(ms * ms + sp_min * sp_min), sc_rest = sqrt(ms * ms + sp_rest * sp_rest),
          sc_max = sqrt(ms * ms + sp_max * sp_max);
@@ -357,33 +373,33 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
     uint32_t sc = m->spring_scaffoldings;
     if (sc & VSR_SCAFFOLD_SIDE_INTERNAL) { /* :303-341 */
       r->next_full = 0;
-      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, -h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 1, b0 + 2, -h, -h, -h, +h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, +h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 3, b0 + 0, +h, +h, +h, -h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, -h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 1, b0 + 2, -h, -h, -h, +h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, +h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 3, b0 + 0, +h, +h, +h, -h, sp_min, sp_rest, sp_max, pp_min, pp_max);
     }
     if (sc & VSR_SCAFFOLD_SIDE_EXTERNAL) { /* :342-380 */
       r->next_full = 4;
-      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, +h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 1, b0 + 2, +h, -h, +h, +h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, -h, sp_min, sp_rest, sp_max);
-      add_spring(r, b0 + 3, b0 + 0, -h, +h, -h, -h, sp_min, sp_rest, sp_max);
+      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, +h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 1, b0 + 2, +h, -h, +h, +h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, -h, sp_min, sp_rest, sp_max, pp_min, pp_max);
+      add_spring(r, b0 + 3, b0 + 0, -h, +h, -h, -h, sp_min, sp_rest, sp_max, pp_min, pp_max);
     }
     if (sc & VSR_SCAFFOLD_SIDE_CROSS) { /* :381-443 */
       r->next_full = 8;
-      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 1, b0 + 2, +h, -h, -h, +h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 1, b0 + 2, -h, -h, +h, +h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, -h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, +h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 3, b0 + 0, -h, +h, +h, -h, sc_min, sc_rest, sc_max);
-      add_spring(r, b0 + 3, b0 + 0, +h, +h, -h, -h, sc_min, sc_rest, sc_max);
+      add_spring(r, b0 + 0, b0 + 1, +h, +h, -h, -h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 0, b0 + 1, +h, -h, -h, +h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 1, b0 + 2, +h, -h, -h, +h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 1, b0 + 2, -h, -h, +h, +h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, +h, +h, -h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 2, b0 + 3, -h, -h, +h, +h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 3, b0 + 0, -h, +h, +h, -h, sc_min, sc_rest, sc_max, pc_min, pc_max);
+      add_spring(r, b0 + 3, b0 + 0, +h, +h, -h, -h, sc_min, sc_rest, sc_max, pc_min, pc_max);
     }
     if (sc & VSR_SCAFFOLD_CENTRAL_CROSS) { /* :444-470 */
       r->next_full = 16;
-      add_spring(r, b0 + 0, b0 + 2, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
-      add_spring(r, b0 + 1, b0 + 3, 0, 0, 0, 0, cc_min, cc_rest, cc_max);
+      add_spring(r, b0 + 0, b0 + 2, 0, 0, 0, 0, cc_min, cc_rest, cc_max, pd_min, pd_max);
+      add_spring(r, b0 + 1, b0 + 3, 0, 0, 0, 0, cc_min, cc_rest, cc_max, pd_min, pd_max);
     }
   }
   /* --- Robot.assemble, Robot.java:91-114: gx outer, gy inner; left pair then lower pair --- */
@@ -645,7 +661,7 @@ static double spring_mass(const vsr_settings* s, const OBody* B1, const OBody* B
   return m1 > 0.0 ? m1 : m2;
 }
 
-/* DistanceJoint.initializeConstraints (dyn4j), soft (frequency > 0), limits off. */
+/* DistanceJoint.initializeConstraints (dyn4j 4.2: the Box2D 2.4 joint), soft (frequency > 0), optional limits. */
 static void spring_init(const vsr_batch_desc* d, ORobot* r, OSpring* s, double dt) {
   OBody* B1 = &r->bodies[s->b1];
   OBody* B2 = &r->bodies[s->b2];
@@ -681,14 +697,17 @@ static void spring_init(const vsr_batch_desc* d, ORobot* r, OSpring* s, double d
   s->ny = ny;
   s->cr1 = cr1;
   s->cr2 = cr2;
-  /* warm start (dtRatio = 1) */
-  double jx = nx * s->imp, jy = ny * s->imp;
+  s->mass = mass;
+  s->len = len;
+  /* warm start (dtRatio = 1): spring + lower - upper along n */
+  double wi = s->imp + s->lo_imp - s->hi_imp;
+  double jx = nx * wi, jy = ny * wi;
   B1->vx += jx * B1->invM;
   B1->vy += jy * B1->invM;
-  B1->w += B1->invI * cr1 * s->imp;
+  B1->w += B1->invI * cr1 * wi;
   B2->vx -= jx * B2->invM;
   B2->vy -= jy * B2->invM;
-  B2->w -= B2->invI * cr2 * s->imp;
+  B2->w -= B2->invI * cr2 * wi;
 }
 
 /* DistanceJoint.solveVelocityConstraints (dyn4j): Jv = n.(v1 + w1 x r1 - v2 - w2 x r2),
@@ -706,6 +725,81 @@ static void spring_solve(ORobot* r, OSpring* s) {
   B2->vx -= jx * B2->invM;
   B2->vy -= jy * B2->invM;
   B2->w -= B2->invI * s->cr2 * j;
+}
+
+/* The limits of DistanceJoint.solveVelocityConstraints (dyn4j 4.2 = b2DistanceJoint of Box2D 2.4, restated: the jar is
+   not in the reference tree): after the spring row, a one-sided rigid row per enabled limit,
+     lower: C = len - lo, bias = max(0, C) / dt, Cdot = n.(v1 - v2), impulse = -mass (Cdot + bias), accumulated >= 0;
+     upper: C = hi - len, bias = max(0, C) / dt, Cdot = n.(v2 - v1), impulse = -mass (Cdot + bias), accumulated >= 0,
+            applied along -n.
+   (n points from body 2 to body 1, so "len grows" = Cdot > 0.) */
+static void spring_limits_solve(ORobot* r, OSpring* s, double inv_dt) {
+  OBody* B1 = &r->bodies[s->b1];
+  OBody* B2 = &r->bodies[s->b2];
+  if (s->lo_on) {
+    double C = s->len - s->lo;
+    double bias = (C > 0.0 ? C : 0.0) * inv_dt;
+    double Jv = s->nx * (B1->vx - B2->vx) + s->ny * (B1->vy - B2->vy) + s->cr1 * B1->w - s->cr2 * B2->w;
+    double j = -s->mass * (Jv + bias);
+    double nw = s->lo_imp + j;
+    if (nw < 0.0) nw = 0.0;
+    j = nw - s->lo_imp;
+    s->lo_imp = nw;
+    double jx = s->nx * j, jy = s->ny * j;
+    B1->vx += jx * B1->invM;
+    B1->vy += jy * B1->invM;
+    B1->w += B1->invI * s->cr1 * j;
+    B2->vx -= jx * B2->invM;
+    B2->vy -= jy * B2->invM;
+    B2->w -= B2->invI * s->cr2 * j;
+  }
+  if (s->hi_on) {
+    double C = s->hi - s->len;
+    double bias = (C > 0.0 ? C : 0.0) * inv_dt;
+    double Jv = -(s->nx * (B1->vx - B2->vx) + s->ny * (B1->vy - B2->vy) + s->cr1 * B1->w - s->cr2 * B2->w);
+    double j = -s->mass * (Jv + bias);
+    double nw = s->hi_imp + j;
+    if (nw < 0.0) nw = 0.0;
+    j = nw - s->hi_imp;
+    s->hi_imp = nw;
+    j = -j;
+    double jx = s->nx * j, jy = s->ny * j;
+    B1->vx += jx * B1->invM;
+    B1->vy += jy * B1->invM;
+    B1->w += B1->invI * s->cr1 * j;
+    B2->vx -= jx * B2->invM;
+    B2->vy -= jy * B2->invM;
+    B2->w -= B2->invI * s->cr2 * j;
+  }
+}
+
+/* DistanceJoint.solvePositionConstraints with limits: a spring-damper without limits reports "solved"; with limits
+   the violated one is corrected rigidly (C clamped to +-maxLinearCorrection, the effective mass of
+   initializeConstraints), solved when |C| < linearTolerance. */
+static int spring_limits_position(const vsr_settings* S, ORobot* r, OSpring* s) {
+  OBody* B1 = &r->bodies[s->b1];
+  OBody* B2 = &r->bodies[s->b2];
+  double c1 = cos(B1->th), s1 = sin(B1->th), c2 = cos(B2->th), s2 = sin(B2->th);
+  double r1x = c1 * s->a1x - s1 * s->a1y, r1y = s1 * s->a1x + c1 * s->a1y;
+  double r2x = c2 * s->a2x - s2 * s->a2y, r2y = s2 * s->a2x + c2 * s->a2y;
+  double nx = r1x + B1->x - (r2x + B2->x), ny = r1y + B1->y - (r2y + B2->y);
+  double len = sqrt(nx * nx + ny * ny);
+  if (len > 0.0) { nx /= len; ny /= len; }
+  double C;
+  if (s->lo_on && len < s->lo) C = len - s->lo;
+  else if (s->hi_on && len > s->hi) C = len - s->hi;
+  else return 1;
+  if (C > S->max_linear_correction) C = S->max_linear_correction;
+  if (C < -S->max_linear_correction) C = -S->max_linear_correction;
+  double imp = -s->mass * C;
+  double Jx = nx * imp, Jy = ny * imp;
+  B1->x += Jx * B1->invM;
+  B1->y += Jy * B1->invM;
+  B1->th += B1->invI * (r1x * Jy - r1y * Jx);
+  B2->x -= Jx * B2->invM;
+  B2->y -= Jy * B2->invM;
+  B2->th -= B2->invI * (r2x * Jy - r2y * Jx);
+  return fabs(C) < S->linear_tolerance;
 }
 
 /* ------------------------------------------------------------------ dyn4j C.4 */
@@ -1523,8 +1617,10 @@ static int world_step(ORun* R, ORobot* r, double dt) {
   for (int it = 0; it < s->velocity_iterations; it++) {
     for (int i = 0; i < r->nj; i++) {
       int j = r->jorder[i];
-      if (j >= 0) spring_solve(r, &r->springs[j]);
-      else weld_solve(r, &r->welds[~j]);
+      if (j >= 0) {
+        spring_solve(r, &r->springs[j]);
+        if (r->springs[j].lo_on || r->springs[j].hi_on) spring_limits_solve(r, &r->springs[j], 1.0 / dt);
+      } else weld_solve(r, &r->welds[~j]);
     }
     for (int i = 0; i < r->ncontacts; i++) contact_solve(r, CON(i));
   }
@@ -1542,7 +1638,10 @@ static int world_step(ORun* R, ORobot* r, double dt) {
     int jointsSolved = 1;
     for (int i = 0; i < r->nj; i++) {
       int j = r->jorder[i];
-      if (j >= 0) continue; /* DistanceJoint with frequency > 0: nothing to do, "solved" */
+      if (j >= 0) { /* DistanceJoint with frequency > 0: "solved" unless a limit is enabled */
+        if (r->springs[j].lo_on || r->springs[j].hi_on) jointsSolved = spring_limits_position(s, r, &r->springs[j]) && jointsSolved;
+        continue;
+      }
       int ok = weld_position(s, r, &r->welds[~j]);
       jointsSolved = jointsSolved && ok;
     }
@@ -1957,8 +2056,6 @@ static int validate(const vsr_batch_desc* d) {
   for (int i = 1; i < d->terrain_n; i++)
     if (d->terrain_xs[i] < d->terrain_xs[i - 1])
       return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted"); /* Ground.java:55-58 */
-  if (isfinite(d->material.area_ratio_passive_min) || isfinite(d->material.area_ratio_passive_max))
-    return fail(VSR_ERR_UNSUPPORTED, "finite areaRatioPassiveRange (DistanceJoint limits) not restated");
   if (!d->param_offsets || !d->params) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
   return 0;
 }

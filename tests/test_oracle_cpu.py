@@ -122,12 +122,6 @@ def test_spring_mass_modes_and_validation():
     a, _ = oracle.run(helpers.locomotion(3.0, spring_mass_mode=0).compile(r))
     b, _ = oracle.run(helpers.locomotion(3.0, spring_mass_mode=1).compile(r))
     assert a[0]["last_center_y"] != b[0]["last_center_y"]  # the switch is live
-    m = H.abi.default_material()
-    m.area_ratio_passive_min, m.area_ratio_passive_max = 0.7, 1.3
-    body = H.Grid.create(1, 1, lambda x, y: H.Voxel([], m))
-    rob = H.Robot(H.PhaseSin(1, 1, H.Grid.create(1, 1, 0.0)), body)
-    with pytest.raises(NotImplementedError, match="limits"):
-        oracle.run(helpers.locomotion(1.0).compile([rob]))
     m2 = H.abi.default_material()
     m2.area_ratio_passive_min = 0.2
     with pytest.raises(ValueError, match="areaRatioPassiveRange"):
@@ -416,3 +410,55 @@ def test_dynamic_normalization_follows_the_reference_window():
     assert res[0]["status"] == 0 and np.isfinite(pr["trajectory"]).all()
     assert np.isnan(pr["signals"][0, 0, :2]).all() and np.isfinite(pr["signals"][0, 5:, :2]).all()
     assert np.isnan(res[0]["control_energy_last"])
+
+
+def _rope_material(lo=0.9, hi=1.1):
+    m = H.abi.default_material()
+    m.area_ratio_passive_min, m.area_ratio_passive_max = lo, hi
+    return m
+
+
+def _spring_lengths(tr, half=0.525):
+    """[tick][voxel][4]: lengths of the side-parallel internal springs 0..3 (Voxel.java:305-330) from a trajectory."""
+    h = half
+    a1 = np.array([[+h, -h], [-h, -h], [-h, +h], [+h, +h]])
+    a2 = np.array([[-h, -h], [-h, +h], [+h, +h], [+h, -h]])
+    nt, nb = tr.shape[:2]
+    b = tr.reshape(nt, nb // 4, 4, 6)
+    out = np.zeros((nt, nb // 4, 4))
+    for s in range(4):
+        p, q = b[:, :, s], b[:, :, (s + 1) % 4]
+        def world(m, a):
+            c, sn = np.cos(m[..., 2]), np.sin(m[..., 2])
+            return m[..., 0] + c * a[0] - sn * a[1], m[..., 1] + sn * a[0] + c * a[1]
+        x1, y1 = world(p, a1[s])
+        x2, y2 = world(q, a2[s])
+        out[:, :, s] = np.hypot(x1 - x2, y1 - y2)
+    return out
+
+
+def test_rope_limits_hold_the_passive_range():
+    # north_star "rope forces", SURVEY 8(f) rank 4: a finite areaRatioPassiveRange turns into lower / upper limits of
+    # every DistanceJoint (Voxel.java:262-285,331-338).  With the passive range (0.9, 1.1) inside the active one
+    # (0.8, 1.2) a full-amplitude controller drives the springs into their limits: they hold (one-sided rigid rows +
+    # position correction), where the unlimited voxel goes well beyond.
+    L, ms = 3.0, 1.05
+    lo, hi = np.sqrt(L * L * 0.9) - 2 * ms, np.sqrt(L * L * 1.1) - 2 * ms
+    ctrl = lambda: H.PhaseSin(1.0, 1.0, H.Grid.create(2, 1, 0.0))
+    runs = {}
+    for name, mat in (("free", None), ("rope", _rope_material())):
+        body = H.Grid.create(2, 1, lambda x, y: H.Voxel([], mat))
+        _, pr = oracle.run(helpers.locomotion(3.0).compile([H.Robot(ctrl(), body)]), trajectory=True)
+        runs[name] = _spring_lengths(pr["trajectory"][0])
+    assert runs["free"][0] == pytest.approx(L - 2 * ms, abs=1e-12)
+    assert runs["free"].min() < lo - 0.03 and runs["free"].max() > hi + 0.03       # the actuation asks for more
+    assert runs["rope"].min() > lo - 0.011 and runs["rope"].max() < hi + 0.011     # ... the limits hold (2 x linearTolerance)
+    assert runs["rope"].min() < lo + 0.01 and runs["rope"].max() > hi - 0.01       # ... and are reached
+    # one-sided: only the upper limit
+    body = H.Grid.create(2, 1, lambda x, y: H.Voxel([], _rope_material(-np.inf, 1.1)))
+    _, pr = oracle.run(helpers.locomotion(3.0).compile([H.Robot(ctrl(), body)]), trajectory=True)
+    up = _spring_lengths(pr["trajectory"][0])
+    assert up.max() < hi + 0.011 and up.min() < lo - 0.03
+    # SpringRange validation (Voxel.java:189-193): a passive range that excludes the rest length
+    with pytest.raises(ValueError, match="Wrong spring range"):
+        H.Voxel([], _rope_material(1.05, 1.3))

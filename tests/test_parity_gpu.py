@@ -563,3 +563,44 @@ def test_fp64_dynamic_normalization():
     assert res[0]["status"] == 0 and ores[0]["status"] == 0
     assert np.abs(tr[..., :3] - otr[:, :, :8, :3]).max() < 1e-7
     assert np.isnan(res[0]["control_energy_last"]) and np.isnan(ores[0]["control_energy_last"])
+
+
+@pytest.mark.parametrize("shape,lo,hi", [("biped-4x3", 0.9, 1.1), ("worm-5x2", -np.inf, 1.05), ("box-6x6", 0.92, np.inf)])
+def test_fp64_rope_limits(shape, lo, hi):
+    """A finite areaRatioPassiveRange (north_star's "rope forces", Voxel.java:262-285,331-338): lower / upper limits of
+    the DistanceJoints -- two more accumulated impulses per spring, a one-sided rigid row per limit after every spring
+    row, the position correction of the violated limit -- on a warp-shared and on a big robot, both limits and each
+    alone, against the oracle."""
+    m = H.abi.default_material()
+    m.area_ratio_passive_min, m.area_ratio_passive_max = lo, hi
+    g = H.RobotUtils.build_shape(shape)
+    body = H.Grid.create(g.w, g.h, lambda x, y: H.Voxel([H.AreaRatio()], m) if g.get(x, y) else None)
+    rng = np.random.default_rng(4)
+    robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(g.w, g.h, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(3)]
+    bd, res, tr, ores, otr = _both(helpers.locomotion(3.0, terrain="hilly-1-10-0"), robots, F64)
+    nb = 4 * bd.n_voxels[0]
+    assert np.all(res["status"] == 0) and np.all(ores["status"] == 0)
+    assert np.abs(tr[:, :, :nb, :3] - otr[:, :, :nb, :3]).max() < 1e-7
+    # ... and the limits are live: the same robots without them end up elsewhere
+    body0 = H.Grid.create(g.w, g.h, lambda x, y: H.Voxel([H.AreaRatio()]) if g.get(x, y) else None)
+    free = [H.Robot(r.get_controller(), body0) for r in robots]
+    res0, _ = helpers.gpu_run(helpers.locomotion(3.0, terrain="hilly-1-10-0").compile(free, precision=F64))
+    assert np.abs(res0["last_center_x"] - res["last_center_x"]).max() > 1e-3
+
+
+def test_fp32_rope_limits_run_on_the_product_path():
+    m = H.abi.default_material()
+    m.area_ratio_passive_min, m.area_ratio_passive_max = 0.9, 1.1
+    g = H.RobotUtils.build_shape("biped-4x3")
+    body = H.Grid.create(g.w, g.h, lambda x, y: H.Voxel([H.AreaRatio()], m) if g.get(x, y) else None)
+    rng = np.random.default_rng(6)
+    robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(g.w, g.h, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(64)]
+    loco = helpers.locomotion(2.0)
+    bd = loco.compile(robots, precision=A.VSR_PRECISION_F32, trajectory_robots=8)
+    res, tr = helpers.gpu_run(bd, trajectories=8)
+    ores, pr = oracle.run(bd, trajectory=True, n_threads=8, robot_end=8)
+    assert np.all(res["status"] == 0)
+    # before the first ground contact (tick ~20) the limit rows are already active (rigid rows: stiffer than the
+    # springs, so rounding is amplified more: 7e-4 measured)
+    assert np.abs(tr[:, :15, :, :2] - pr["trajectory"][:, :15, :40, :2]).max() < 3e-3
+    assert np.abs(tr[..., :2] - pr["trajectory"][:, :, :40, :2]).max() < 0.5
