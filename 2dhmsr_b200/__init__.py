@@ -8,7 +8,7 @@ fallback.
 from . import _abi as abi  # noqa: F401
 from .hmsrobots import (  # noqa: F401
     Angle, AppliedForce, Constant, ControlPower, Crumpling, Lidar, Malfunction, Noisy, Normalization, TimeFunction,
-    AreaRatio, Average, BatchDesc, CentralizedSensing, Controller, DeviceBatch, DistributedSensing, DistributedSensingNonDirectional,
+    AreaRatio, Average, BatchDesc, BreakableVoxel, CentralizedSensing, Controller, DeviceBatch, DistributedSensing, DistributedSensingNonDirectional,
     DoubleRange, DynamicNormalization, Grid,
     JavaRandom, Locomotion, MultiLayerPerceptron, Outcome, PhaseSin, RESULT_DTYPE, Robot, RobotShape, RobotUtils,
     Sensor, Settings, Snapshot, SoftNormalization, TimeFunctions, Touch, Trend, Velocity, Voxel, VsrError,

@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvsr_b200.so")
 
-VSR_ABI_VERSION = 1
+VSR_ABI_VERSION = 2
 
 VSR_OK = 0
 VSR_ERR_INVALID_ARGUMENT = -1
@@ -114,6 +114,21 @@ class vsr_sensor(C.Structure):
     ]
 
 
+VSR_MALFUNCTION_NONE, VSR_MALFUNCTION_ZERO, VSR_MALFUNCTION_FROZEN, VSR_MALFUNCTION_RANDOM = 0, 1, 2, 3
+VSR_COMPONENT_ACTUATOR, VSR_COMPONENT_SENSORS, VSR_COMPONENT_STRUCTURE = 0, 1, 2
+VSR_TRIGGER_CONTROL, VSR_TRIGGER_AREA, VSR_TRIGGER_TIME = 0, 1, 2
+
+
+class vsr_breakable(C.Structure):
+    _fields_ = [
+        ("enabled", C.c_int32),
+        ("malfunctions", C.c_uint32 * 3),
+        ("thresholds", C.c_double * 3),
+        ("restore_time", C.c_double),
+        ("random_seed", C.c_int64),
+    ]
+
+
 class vsr_shape(C.Structure):
     _fields_ = [
         ("w", C.c_int32),
@@ -124,6 +139,7 @@ class vsr_shape(C.Structure):
         ("n_hidden", C.c_int32),
         ("reserved", C.c_int32),
         ("hidden", C.POINTER(C.c_int32)),
+        ("breakable", C.POINTER(vsr_breakable)),
     ]
 
 

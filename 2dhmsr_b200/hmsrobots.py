@@ -461,6 +461,37 @@ class Voxel:
         return self.sensors
 
 
+class BreakableVoxel(Voxel):
+    """core/objects/BreakableVoxel.java: a voxel whose ACTUATOR, SENSORS or STRUCTURE may malfunction (ZERO, FROZEN,
+    RANDOM; STRUCTURE: FROZEN only, the others throw in the reference at the first break) when a CONTROL, AREA or TIME
+    counter trips its threshold, restored ``restore_time`` after the last break.  ``malfunctions`` maps a component name
+    to the set of its malfunction types, ``trigger_thresholds`` a trigger name to its threshold (both iterated in enum
+    order on the device, see include/vsr_b200.h)."""
+
+    COMPONENTS = ("ACTUATOR", "SENSORS", "STRUCTURE")
+    TRIGGERS = ("CONTROL", "AREA", "TIME")
+    TYPES = ("NONE", "ZERO", "FROZEN", "RANDOM")
+
+    def __init__(self, sensors: Sequence[Sensor], random_seed: int, malfunctions: dict, trigger_thresholds: dict,
+                 restore_time: float, material: Optional[A.vsr_material] = None):
+        super().__init__(sensors, material)
+        for c, ts in malfunctions.items():
+            if c not in self.COMPONENTS or any(t not in self.TYPES for t in ts) or not ts:
+                raise ValueError(f"unknown malfunction {c}: {ts}")
+        if any(t not in ("NONE", "FROZEN") for t in malfunctions.get("STRUCTURE", ())):
+            raise ValueError("Unsupported structure malfunction type.")   # BreakableVoxel.java:258
+        if any(t not in self.TRIGGERS for t in trigger_thresholds):
+            raise ValueError(f"unknown malfunction trigger in {trigger_thresholds}")
+        self.random_seed, self.malfunctions = int(random_seed), {c: frozenset(ts) for c, ts in malfunctions.items()}
+        self.trigger_thresholds, self.restore_time = dict(trigger_thresholds), float(restore_time)
+
+    def encode_breakable(self) -> tuple:
+        """(malfunction bit masks per component, thresholds per trigger (NaN = absent), restore time, seed)"""
+        mal = tuple(sum(1 << self.TYPES.index(t) for t in self.malfunctions.get(c, ())) for c in self.COMPONENTS)
+        thr = tuple(float(self.trigger_thresholds.get(t, math.nan)) for t in self.TRIGGERS)
+        return mal, thr, self.restore_time, self.random_seed
+
+
 class Controller:
     """core/controllers/Controller.java:29 (description only)."""
     KIND = -1
@@ -737,6 +768,54 @@ def _params(pattern: str, string: str):
 
 class RobotUtils:
     """util/RobotUtils.java: body-shape and sensor-layout mini DSLs."""
+
+    @staticmethod
+    def build_robot_transformation(name: str, external_random: Optional["JavaRandom"] = None):
+        """RobotUtils.buildRobotTransformation (:65-123): ``identity``, ``breakable-<time|area>-<thr mean>/<thr sd>-
+        <restore mean>/<restore sd>-<seed|rnd>`` (every voxel becomes a BreakableVoxel whose actuator freezes) and
+        ``broken-<ratio>-<seed|rnd>`` (a share of the voxels is broken from the first tick on, for good).  The draws
+        follow the reference's order: per voxel in Grid order nextInt, nextGaussian (threshold), nextGaussian (restore
+        time) / nextDouble, nextInt."""
+        breakable = (r"breakable-(?<triggerType>time|area)-(?<thresholdMean>\d+(\.\d+)?)/(?<thresholdStDev>\d+(\.\d+)?)-"
+                     r"(?<restTimeMean>\d+(\.\d+)?)/(?<restTimeStDev>\d+(\.\d+)?)-(?<seed>\d+|rnd)")
+        broken = r"broken-(?<ratio>\d+(\.\d+)?)-(?<seed>\d+|rnd)"
+        if _params("identity", name) is not None:
+            return lambda robot: robot
+
+        def rnd_of(p):
+            if p["seed"] != "rnd":
+                return JavaRandom(int(p["seed"]))
+            if external_random is None:
+                raise ValueError("seed 'rnd' needs an external random generator")
+            return external_random
+
+        p = _params(breakable, name)
+        if p is not None:
+            rnd = rnd_of(p)
+            tm, ts = float(p["thresholdMean"]), float(p["thresholdStDev"])
+            rm, rs = float(p["restTimeMean"]), float(p["restTimeStDev"])
+            trig = p["triggerType"].upper()
+
+            def mk(v):
+                if v is None:
+                    return None
+                seed = rnd.next_int()
+                thr = rnd.next_gaussian() * ts + tm
+                return BreakableVoxel(v.get_sensors(), seed, {"ACTUATOR": {"FROZEN"}}, {trig: thr}, rnd.next_gaussian() * rs + rm)
+            return lambda robot: Robot(robot.get_controller(), Grid.create_from(robot.get_voxels(), mk))
+        p = _params(broken, name)
+        if p is not None:
+            rnd = rnd_of(p)
+            ratio = float(p["ratio"])
+
+            def mk(v):
+                if v is None:
+                    return None
+                if rnd.next_double() > ratio:
+                    return v
+                return BreakableVoxel(v.get_sensors(), rnd.next_int(), {"ACTUATOR": {"FROZEN"}}, {"TIME": 0.0}, math.inf)
+            return lambda robot: Robot(robot.get_controller(), Grid.create_from(robot.get_voxels(), mk))
+        raise ValueError(f"Unknown transformation name: {name}")
 
     PREDEFINED_SENSORS = {  # :38-60 (TreeMap => sorted keys); the lidars "l1", "l5" are not on the device
         "a": lambda x, y: SoftNormalization(AreaRatio()),
@@ -1112,6 +1191,7 @@ def compile_batch(
 
     # shape classes: (mask, per-voxel sensor encodings, hidden layers)
     shape_keys: dict = {}
+    shape_brk: dict = {}
     shapes_c: list = []
     robot_shape = np.zeros(len(robots), dtype=np.int32)
     material = None
@@ -1131,8 +1211,11 @@ def compile_batch(
                 for v in vox.values() if v is not None
             )
             mats = {bytes(v.material) for v in vox.values() if v is not None}
-            cached = body_cache[id(vox)] = (vox, mask, sens, mats)
-        _, mask, sens, mats = cached
+            brk = tuple(v.encode_breakable() if isinstance(v, BreakableVoxel) else None for v in vox.values() if v is not None)
+            if all(q is None for q in brk):
+                brk = None
+            cached = body_cache[id(vox)] = (vox, mask, sens, mats, brk)
+        _, mask, sens, mats, brk = cached
         hidden: Tuple[int, ...] = ()
         if kind == A.VSR_CTRL_MLP:
             f = r.controller.function
@@ -1164,8 +1247,9 @@ def compile_batch(
                 material = mb
             elif material != mb:
                 raise NotImplementedError("one voxel material per batch on the accelerated path")
-        key = (vox.w, vox.h, mask, sens, hidden)
+        key = (vox.w, vox.h, mask, sens, hidden, repr(brk))
         if key not in shape_keys:
+            shape_brk[key] = brk
             shape_keys[key] = len(shapes_c)
             shapes_c.append(key)
         robot_shape[i] = shape_keys[key]
@@ -1177,8 +1261,22 @@ def compile_batch(
     d.distributed_signals = dist_signals if dist_signals is not None else 0
 
     arr = (A.vsr_shape * len(shapes_c))()
-    for k, (w, h, mask, sens, hidden) in enumerate(shapes_c):
+    for k, key_k in enumerate(shapes_c):
+        w, h, mask, sens, hidden = key_k[:5]
         m = b.keep(np.frombuffer(mask, dtype=np.uint8).copy())
+        brk = shape_brk.get(key_k)
+        if brk is not None:
+            barr = (A.vsr_breakable * len(brk))()
+            for j, q in enumerate(brk):
+                if q is None:
+                    continue
+                barr[j].enabled = 1
+                for z in range(3):
+                    barr[j].malfunctions[z] = q[0][z]
+                    barr[j].thresholds[z] = q[1][z]
+                barr[j].restore_time, barr[j].random_seed = q[2], q[3]
+            b.keep(barr)
+            arr[k].breakable = C.cast(barr, C.POINTER(A.vsr_breakable))
         offs = np.zeros(len(sens) + 1, dtype=np.int32)
         flat = []
         for j, vs in enumerate(sens):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VSR_ABI_VERSION 1
+#define VSR_ABI_VERSION 2
 
 /* ---- error codes (reference convention: unchecked IllegalArgumentException at
  *      validation time, e.g. Voxel.java:132-140, Ground.java:46-56,
@@ -143,6 +143,37 @@ typedef struct vsr_sensor {
   double lidar_dirs[VSR_LIDAR_MAX_RAYS]; /* LIDAR: rayDirections                                  */
 } vsr_sensor;
 
+/* ---- BreakableVoxel (core/objects/BreakableVoxel.java): a voxel whose actuator, sensors or structure may
+ *      malfunction.  After Voxel.act the voxel accumulates its trigger counters (time, control energy, area-ratio
+ *      energy since the last break); for every entry of triggerThresholds it draws random.nextDouble() and breaks when
+ *      the draw is < 1 - tanh(threshold / counter) (:142-158): a component and one of its malfunction types are drawn
+ *      with random.nextInt; everything is restored restoreTime after the last break (:163-167).  ACTUATOR: ZERO ->
+ *      applyForce(0), FROZEN -> the last applied force again, RANDOM -> U(-1, 1) (:170-180).  SENSORS: ZERO -> zeros,
+ *      FROZEN -> the readings of the tick it broke, RANDOM -> uniform in each reading's domain, drawn when a
+ *      controller asks for the readings (:183-193).  STRUCTURE: FROZEN -> the voxel's springs become rigid distance
+ *      joints (setFrequency(0), :249-257; re-applied only when the voxel breaks again, as there); other structure
+ *      types throw in the reference and are rejected here.  The reference iterates its Maps and Sets; this interface
+ *      fixes the enum order (CONTROL, AREA, TIME; ACTUATOR, SENSORS, STRUCTURE; NONE, ZERO, FROZEN, RANDOM), which is
+ *      what an EnumMap / EnumSet gives (a Map.of with several entries has no defined order in the reference either). */
+#define VSR_MALFUNCTION_NONE 0
+#define VSR_MALFUNCTION_ZERO 1
+#define VSR_MALFUNCTION_FROZEN 2
+#define VSR_MALFUNCTION_RANDOM 3
+#define VSR_COMPONENT_ACTUATOR 0
+#define VSR_COMPONENT_SENSORS 1
+#define VSR_COMPONENT_STRUCTURE 2
+#define VSR_TRIGGER_CONTROL 0
+#define VSR_TRIGGER_AREA 1
+#define VSR_TRIGGER_TIME 2
+typedef struct vsr_breakable {
+  int32_t enabled;           /* 0: a plain Voxel (the other fields are ignored)                                  */
+  uint32_t malfunctions[3];  /* per VSR_COMPONENT_*: bit t set = VSR_MALFUNCTION_t is in the component's set;
+                                0 = the component is not a key of the `malfunctions` map                        */
+  double thresholds[3];      /* per VSR_TRIGGER_*; NaN = the trigger is not a key of `triggerThresholds`         */
+  double restore_time;       /* may be +inf                                                                     */
+  int64_t random_seed;
+} vsr_breakable;
+
 /* ---- Shape class: a Grid<Boolean> body + its per-voxel sensor lists.
  *      Voxels are enumerated in Grid.values() order, i.e. row-major y*w+x with
  *      nulls skipped (Grid.java:180-188,268-270).                              ---- */
@@ -155,6 +186,7 @@ typedef struct vsr_shape {
   int32_t n_hidden;
   int32_t reserved;
   const int32_t* hidden;          /* [n_hidden]                                         */
+  const vsr_breakable* breakable; /* [n_voxels] in voxel order, or NULL: no BreakableVoxel in this shape class */
 } vsr_shape;
 
 /* ---- Controllers (one kind per batch; parameters per robot) ---- */

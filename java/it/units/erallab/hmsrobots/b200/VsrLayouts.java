@@ -20,7 +20,7 @@ public final class VsrLayouts {
   private VsrLayouts() {
   }
 
-  public static final int VSR_ABI_VERSION = 1;
+  public static final int VSR_ABI_VERSION = 2;
   public static final int VSR_LIDAR_MAX_RAYS = 8;
 
   /* dyn4j Settings + World gravity (vsr_settings) */
@@ -78,6 +78,15 @@ public final class VsrLayouts {
   ).withName("vsr_sensor");
 
   /* a Grid<Boolean> body + its per-voxel sensor lists (vsr_shape) */
+  /* one BreakableVoxel's parameters (vsr_breakable) */
+  public static final StructLayout VSR_BREAKABLE = MemoryLayout.structLayout(
+      JAVA_INT.withName("enabled"),
+      MemoryLayout.sequenceLayout(3, JAVA_INT).withName("malfunctions"),
+      MemoryLayout.sequenceLayout(3, JAVA_DOUBLE).withName("thresholds"),
+      JAVA_DOUBLE.withName("restore_time"),
+      JAVA_LONG.withName("random_seed")
+  ).withName("vsr_breakable");
+
   public static final StructLayout VSR_SHAPE = MemoryLayout.structLayout(
       JAVA_INT.withName("w"),
       JAVA_INT.withName("h"),
@@ -86,7 +95,8 @@ public final class VsrLayouts {
       ADDRESS.withName("sensors"),
       JAVA_INT.withName("n_hidden"),
       JAVA_INT.withName("reserved"),
-      ADDRESS.withName("hidden")
+      ADDRESS.withName("hidden"),
+      ADDRESS.withName("breakable")
   ).withName("vsr_shape");
 
   /* N robots, one terrain, one Settings (vsr_batch_desc) */

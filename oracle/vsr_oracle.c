@@ -158,6 +158,7 @@ typedef struct {
   double lo, hi;
   double lo_imp, hi_imp; /* accumulated limit impulses (warm start) */
   double mass, len;      /* rigid effective mass 1/K and the current length, from initializeConstraints */
+  int rigid;             /* frequency 0 (BreakableVoxel.updateStructureMalfunctionType): a rigid distance joint */
 } OSpring;
 
 typedef struct {
@@ -189,9 +190,28 @@ typedef struct {
   double K00, K01, K11, iK00, iK01, iK11;
 } OContact;
 
+/* BreakableVoxel.java: the parameters (vsr_breakable) and the transient state of one voxel */
+typedef struct {
+  int enabled;
+  unsigned mal[3];
+  double thr[3];
+  double restore;
+  unsigned long long seed; /* java.util.Random state (Random(randomSeed), :213) */
+  int state[3];            /* VSR_MALFUNCTION_* per VSR_COMPONENT_* */
+  int struct_frozen;       /* what updateStructureMalfunctionType (:244-258) last applied to the springs */
+  double cnt[3];           /* triggerCounters per VSR_TRIGGER_* */
+  double lastT, lastBreakT, lastCE, lastARE;
+  int have_snapshot;       /* sensorReadings != null */
+} OBreak;
+
 typedef struct {
   int nv, nb, ns, nw;
   int next_full;
+  OBreak* brk;     /* [nv] or NULL: no BreakableVoxel in this robot */
+  double* snap;    /* [n_readings] BreakableVoxel.sensorReadings of every voxel */
+  double* eff;     /* [n_readings] what Voxel.getSensorReadings returns at this control step */
+  double* rd_min;  /* [n_readings] final domain of every reading (Sensor.getDomains) */
+  double* rd_max;
   int* vox_gx;
   int* vox_gy;
   OBody* bodies;
@@ -538,6 +558,27 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   }
   r->n_readings = off_r;
   r->readings = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+  r->brk = NULL;
+  r->snap = r->eff = r->rd_min = r->rd_max = NULL;
+  if (sh->breakable) {
+    /* BreakableVoxel constructor + reset() (:97-104,216-229): counters 0, every component NONE, springs soft */
+    r->brk = (OBreak*)calloc((size_t)nv + 1, sizeof(OBreak));
+    r->snap = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+    r->eff = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+    r->rd_min = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+    r->rd_max = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+    for (int vv = 0; vv < nv; vv++) {
+      const vsr_breakable* q = &sh->breakable[vv];
+      OBreak* B = &r->brk[vv];
+      B->enabled = q->enabled != 0;
+      for (int z = 0; z < 3; z++) {
+        B->mal[z] = q->malfunctions[z];
+        B->thr[z] = q->thresholds[z];
+      }
+      B->restore = q->restore_time;
+      B->seed = ((unsigned long long)q->random_seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+    }
+  }
   r->rng_seed = (unsigned long long*)calloc((size_t)ns + 1, sizeof(unsigned long long));
   r->rng_spare = (double*)calloc((size_t)ns + 1, sizeof(double));
   r->rng_have = (unsigned char*)calloc((size_t)ns + 1, 1);
@@ -604,6 +645,11 @@ static void robot_free(ORobot* r) {
   free(r->ctrl_energy);
   free(r->touch);
   free(r->readings);
+  free(r->brk);
+  free(r->snap);
+  free(r->eff);
+  free(r->rd_min);
+  free(r->rd_max);
   for (int i = 0; i < r->n_sens; i++) free(r->hist[i]);
   free(r->hist);
   free(r->hist_first);
@@ -689,6 +735,10 @@ static void spring_init(const vsr_batch_desc* d, ORobot* r, OSpring* s, double d
   double gamma = dt * (dc + dt * k);
   gamma = gamma <= EPS_E ? 0.0 : 1.0 / gamma;
   double bias = x * dt * k * gamma;
+  if (s->rigid) { /* BreakableVoxel STRUCTURE FROZEN: setFrequency(0) -> a rigid DistanceJoint (gamma = bias = 0) */
+    gamma = 0.0;
+    bias = 0.0;
+  }
   invMass += gamma;
   s->soft = invMass <= EPS_E ? 0.0 : 1.0 / invMass;
   s->gamma = gamma;
@@ -786,7 +836,8 @@ static int spring_limits_position(const vsr_settings* S, ORobot* r, OSpring* s) 
   double len = sqrt(nx * nx + ny * ny);
   if (len > 0.0) { nx /= len; ny /= len; }
   double C;
-  if (s->lo_on && len < s->lo) C = len - s->lo;
+  if (s->rigid) C = len - s->rest; /* a rigid joint is corrected to its rest distance on both sides */
+  else if (s->lo_on && len < s->lo) C = len - s->lo;
   else if (s->hi_on && len > s->hi) C = len - s->hi;
   else return 1;
   if (C > S->max_linear_correction) C = S->max_linear_correction;
@@ -1639,7 +1690,8 @@ static int world_step(ORun* R, ORobot* r, double dt) {
     for (int i = 0; i < r->nj; i++) {
       int j = r->jorder[i];
       if (j >= 0) { /* DistanceJoint with frequency > 0: "solved" unless a limit is enabled */
-        if (r->springs[j].lo_on || r->springs[j].hi_on) jointsSolved = spring_limits_position(s, r, &r->springs[j]) && jointsSolved;
+        if (r->springs[j].lo_on || r->springs[j].hi_on || r->springs[j].rigid)
+          jointsSolved = spring_limits_position(s, r, &r->springs[j]) && jointsSolved;
         continue;
       }
       int ok = weld_position(s, r, &r->welds[~j]);
@@ -1764,6 +1816,87 @@ static double lidar_cast(const vsr_batch_desc* d, double ox, double oy, double d
   return best;
 }
 
+/* java.util.Random.nextInt(bound) */
+static int jr_next_int(unsigned long long* seed, int bound) {
+  if ((bound & -bound) == bound) return (int)(((long long)bound * jr_next(seed, 31)) >> 31);
+  for (;;) {
+    long long bits = jr_next(seed, 31);
+    long long val = bits % bound;
+    if (bits - val + (bound - 1) < (1LL << 31)) return (int)val;
+  }
+}
+static int nth_set_bit(unsigned m, int n) {
+  for (int b = 0; b < 32; b++)
+    if ((m >> b) & 1u) {
+      if (n == 0) return b;
+      n--;
+    }
+  return 0;
+}
+
+/* BreakableVoxel.act after super.act (:127-168): snapshot of the readings, trigger counters, one draw per trigger
+   threshold (enum order), the break itself (component, malfunction type: two nextInt), the restore.
+   updateStructureMalfunctionType (:244-258) runs at a break only -- a restore leaves the springs as they are. */
+static void breakable_act(ORun* R, ORobot* r, int tick) {
+  const double t = R->ticks[tick];
+  for (int v = 0; v < r->nv; v++) {
+    OBreak* B = &r->brk[v];
+    if (!B->enabled) continue;
+    if (B->state[VSR_COMPONENT_SENSORS] == VSR_MALFUNCTION_NONE || !B->have_snapshot) {
+      for (int q = r->vox_read_off[v]; q < r->vox_read_off[v + 1]; q++) r->snap[q] = r->readings[q];
+      B->have_snapshot = 1;
+    }
+    B->cnt[VSR_TRIGGER_TIME] = B->cnt[VSR_TRIGGER_TIME] + t - B->lastT;
+    B->cnt[VSR_TRIGGER_CONTROL] = B->cnt[VSR_TRIGGER_CONTROL] + (r->ctrl_energy[v] - B->lastCE);
+    B->cnt[VSR_TRIGGER_AREA] = B->cnt[VSR_TRIGGER_AREA] + (r->ar_energy[v] - B->lastARE);
+    B->lastT = t;
+    B->lastCE = r->ctrl_energy[v];
+    B->lastARE = r->ar_energy[v];
+    int breaking = 0;
+    for (int g = 0; g < 3; g++) {
+      if (B->thr[g] != B->thr[g]) continue; /* not a key of triggerThresholds */
+      double u = jr_next_double(&B->seed);
+      if (u < 1.0 - tanh(B->thr[g] / B->cnt[g])) {
+        B->cnt[0] = B->cnt[1] = B->cnt[2] = 0.0;
+        int ncomp = (B->mal[0] != 0) + (B->mal[1] != 0) + (B->mal[2] != 0);
+        if (ncomp > 0) {
+          breaking = 1;
+          int ci = jr_next_int(&B->seed, ncomp), c = 0;
+          for (c = 0; c < 3; c++)
+            if (B->mal[c] != 0 && ci-- == 0) break;
+          int nt = __builtin_popcount(B->mal[c]);
+          int ty = nth_set_bit(B->mal[c], jr_next_int(&B->seed, nt));
+          B->state[c] = ty;
+          int frozen = B->state[VSR_COMPONENT_STRUCTURE] == VSR_MALFUNCTION_FROZEN;
+          if (frozen != B->struct_frozen) {
+            B->struct_frozen = frozen;
+            int per = r->ns / (r->nv > 0 ? r->nv : 1);
+            for (int k = 0; k < per; k++) r->springs[v * per + k].rigid = frozen;
+          }
+        }
+      }
+    }
+    if (breaking) B->lastBreakT = t;
+    if (t - B->lastBreakT > B->restore) B->state[0] = B->state[1] = B->state[2] = VSR_MALFUNCTION_NONE;
+  }
+}
+
+/* BreakableVoxel.getSensorReadings (:183-193) for every voxel, into r->eff: what a controller reads */
+static const double* effective_readings(ORobot* r) {
+  if (!r->brk) return r->readings;
+  for (int v = 0; v < r->nv; v++) {
+    OBreak* B = &r->brk[v];
+    for (int q = r->vox_read_off[v]; q < r->vox_read_off[v + 1]; q++) {
+      if (!B->enabled) r->eff[q] = r->readings[q];
+      else if (B->state[VSR_COMPONENT_SENSORS] == VSR_MALFUNCTION_ZERO) r->eff[q] = 0.0;
+      else if (B->state[VSR_COMPONENT_SENSORS] == VSR_MALFUNCTION_RANDOM)
+        r->eff[q] = jr_next_double(&B->seed) * (r->rd_max[q] - r->rd_min[q]) + r->rd_min[q];
+      else r->eff[q] = r->snap[q]; /* NONE (the fresh snapshot) and FROZEN (the one of the break) */
+    }
+  }
+  return r->eff;
+}
+
 static void robot_sense(ORun* R, ORobot* r, int tick) {
   const double* T = R->ticks;
   for (int v = 0; v < r->nv; v++) {
@@ -1800,8 +1933,9 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
     } else if (S->base == VSR_SENSOR_APPLIED_FORCE) { /* AppliedForce.java */
       raw[0] = r->last_force[v];
       dmin = -1.0;
-    } else if (S->base == VSR_SENSOR_MALFUNCTION) { /* Malfunction.java, non-breakable voxel */
-      raw[0] = 0.0;
+    } else if (S->base == VSR_SENSOR_MALFUNCTION) { /* Malfunction.java: BreakableVoxel.isBroken (:234-237), else 0 */
+      const OBreak* B = r->brk ? &r->brk[v] : NULL;
+      raw[0] = (B && B->enabled && (B->state[0] || B->state[1] || B->state[2])) ? 1.0 : 0.0;
     } else if (S->base == VSR_SENSOR_TIME_SIN) { /* TimeFunction.java with t -> sin(2 pi f t) */
       raw[0] = sin(2.0 * PI * S->max_velocity_norm * T[tick]);
       dmin = -1.0;
@@ -1878,8 +2012,13 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
         o = o + jr_next_gaussian(r, si) * (ext * S->noise_sigma);
       }
       r->readings[r->sens_off[si] + k] = o;
+      if (r->rd_min) { /* Sensor.getDomains of the outermost wrapper (Noisy keeps its sensor's) */
+        r->rd_min[r->sens_off[si] + k] = S->soft_norm != VSR_NORM_NONE ? 0.0 : dmin;
+        r->rd_max[r->sens_off[si] + k] = S->soft_norm != VSR_NORM_NONE ? 1.0 : dmax;
+      }
     }
   }
+  if (r->brk) breakable_act(R, r, tick);
 }
 
 /* Voxel.applyForce, :224-237 */
@@ -1898,6 +2037,8 @@ static void robot_control(ORun* R, ORobot* r, size_t ridx, int tick, double* sig
   const vsr_batch_desc* d = R->d;
   const double* P = d->params + d->param_offsets[ridx];
   double t = R->ticks[tick];
+  const double* readings = (d->controller_kind == VSR_CTRL_PHASE_SIN || d->controller_kind == VSR_CTRL_TABULATED)
+                               ? r->readings : effective_readings(r); /* (open-loop controllers never ask for them) */
   double out_stack[64];
   double* out = r->nv <= 64 ? out_stack : (double*)malloc(sizeof(double) * (size_t)r->nv);
   if (d->controller_kind == VSR_CTRL_PHASE_SIN) {
@@ -1915,7 +2056,7 @@ static void robot_control(ORun* R, ORobot* r, size_t ridx, int tick, double* sig
     double in[64], outv[64];
     for (int v = 0; v < r->nv; v++) {
       int nr = r->vox_read_off[v + 1] - r->vox_read_off[v];
-      for (int q = 0; q < nr; q++) in[q] = r->readings[r->vox_read_off[v] + q]; /* getSensorReadings first */
+      for (int q = 0; q < nr; q++) in[q] = readings[r->vox_read_off[v] + q]; /* getSensorReadings first */
       int c = nr;
       for (int dir = 0; dir < 4; dir++) {
         int ax = r->vox_gx[v] + DX[dir], ay = r->vox_gy[v] + DY[dir];
@@ -1932,9 +2073,15 @@ static void robot_control(ORun* R, ORobot* r, size_t ridx, int tick, double* sig
     }
     for (int q = 0; q < r->nv * 4 * sg; q++) r->last_sig[q] = r->cur_sig[q];
   } else {
-    vsr_oracle_mlp_apply(d->mlp_activation, r->neurons, r->n_layers, P, r->readings, out);
+    vsr_oracle_mlp_apply(d->mlp_activation, r->neurons, r->n_layers, P, readings, out);
   }
   for (int v = 0; v < r->nv; v++) {
+    if (r->brk && r->brk[v].enabled) { /* BreakableVoxel.applyForce (:170-180) */
+      OBreak* B = &r->brk[v];
+      if (B->state[VSR_COMPONENT_ACTUATOR] == VSR_MALFUNCTION_ZERO) out[v] = 0.0;
+      else if (B->state[VSR_COMPONENT_ACTUATOR] == VSR_MALFUNCTION_FROZEN) out[v] = r->last_force[v];
+      else if (B->state[VSR_COMPONENT_ACTUATOR] == VSR_MALFUNCTION_RANDOM) out[v] = jr_next_double(&B->seed) * 2.0 - 1.0;
+    }
     voxel_apply_force(r, v, out[v]);
     if (sig_out) sig_out[v] = r->last_force[v];
   }
@@ -2057,6 +2204,15 @@ static int validate(const vsr_batch_desc* d) {
     if (d->terrain_xs[i] < d->terrain_xs[i - 1])
       return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted"); /* Ground.java:55-58 */
   if (!d->param_offsets || !d->params) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
+  for (int k = 0; k < d->n_shapes; k++)
+    if (d->shapes[k].breakable)
+      for (int v = 0, nv = shape_nvox(&d->shapes[k]); v < nv; v++) {
+        const vsr_breakable* q = &d->shapes[k].breakable[v];
+        if (q->enabled && (q->malfunctions[VSR_COMPONENT_STRUCTURE] & ~((1u << VSR_MALFUNCTION_NONE) | (1u << VSR_MALFUNCTION_FROZEN))))
+          return fail(VSR_ERR_INVALID_ARGUMENT, "Unsupported structure malfunction type."); /* BreakableVoxel.java:258 */
+        if (q->enabled && ((q->malfunctions[0] | q->malfunctions[1] | q->malfunctions[2]) & ~15u))
+          return fail(VSR_ERR_INVALID_ARGUMENT, "unknown malfunction type");
+      }
   return 0;
 }
 

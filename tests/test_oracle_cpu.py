@@ -462,3 +462,155 @@ def test_rope_limits_hold_the_passive_range():
     # SpringRange validation (Voxel.java:189-193): a passive range that excludes the rest length
     with pytest.raises(ValueError, match="Wrong spring range"):
         H.Voxel([], _rope_material(1.05, 1.3))
+
+
+def _breakable_restatement(bv, t, forces_in, area_ratio, raw_readings, rd_domains, read_by_controller):
+    """BreakableVoxel.java:127-193 restated in Python for ONE voxel over the ticks `t`: given what the controller asks
+    for (forces_in[k], or a callable of the effective readings), the voxel's area ratio and raw readings per tick ->
+    (applied force, isBroken at sense time, effective readings) per tick."""
+    rnd = H.JavaRandom(bv.random_seed)
+    comps, trigs, types = bv.COMPONENTS, bv.TRIGGERS, bv.TYPES
+    state = {c: "NONE" for c in comps}
+    cnt = {g: 0.0 for g in trigs}
+    last_t = last_break = last_ce = last_are = 0.0
+    ce = are = 0.0
+    last_f = 0.0
+    snap = None
+    out_f, out_broken, out_eff = [], [], []
+    for k in range(len(t)):
+        # Voxel.act: energies, then the sensors (Malfunction reads the state BEFORE this tick's update)
+        are += area_ratio[k] ** 2
+        ce += last_f ** 2
+        out_broken.append(any(s != "NONE" for s in state.values()))
+        if state["SENSORS"] == "NONE" or snap is None:
+            snap = np.array(raw_readings[k], dtype=float)
+        cnt["TIME"] += t[k] - last_t
+        cnt["CONTROL"] += ce - last_ce
+        cnt["AREA"] += are - last_are
+        last_t, last_ce, last_are = t[k], ce, are
+        breaking = False
+        for g in trigs:
+            if g not in bv.trigger_thresholds:
+                continue
+            thr = bv.trigger_thresholds[g]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                p = 1.0 - np.tanh(np.float64(thr) / np.float64(cnt[g]))
+            if rnd.next_double() < p:
+                cnt = {q: 0.0 for q in trigs}
+                keys = [c for c in comps if c in bv.malfunctions]
+                if keys:
+                    breaking = True
+                    c = keys[rnd.next_int(len(keys))]
+                    ts = [q for q in types if q in bv.malfunctions[c]]
+                    state[c] = ts[rnd.next_int(len(ts))]
+        if breaking:
+            last_break = t[k]
+        if t[k] - last_break > bv.restore_time:
+            state = {c: "NONE" for c in comps}
+        # controller.control: getSensorReadings (if it reads), then applyForce
+        eff = snap
+        if read_by_controller:
+            if state["SENSORS"] == "ZERO":
+                eff = np.zeros_like(snap)
+            elif state["SENSORS"] == "RANDOM":
+                eff = np.array([rnd.next_double() * (hi - lo) + lo for lo, hi in rd_domains])
+        out_eff.append(np.array(eff))
+        f = forces_in(k, eff) if callable(forces_in) else forces_in[k]
+        if state["ACTUATOR"] == "ZERO":
+            f = 0.0
+        elif state["ACTUATOR"] == "FROZEN":
+            f = last_f
+        elif state["ACTUATOR"] == "RANDOM":
+            f = rnd.next_double() * 2.0 - 1.0
+        if abs(f) > 1:
+            f = math.copysign(1.0, f)
+        last_f = f
+        out_f.append(f)
+    return np.array(out_f), np.array(out_broken), out_eff
+
+
+def test_breakable_voxel_actuator_and_triggers_follow_the_reference():
+    # SURVEY 8(f) rank 4, BreakableVoxel.java: all three triggers, all three actuator malfunctions, restore -- the
+    # oracle's applied forces and Malfunction readings against a Python restatement driven by the same java.util.Random
+    t = H.tick_times(6.0, 1 / 60)
+    mk = lambda x, y: H.BreakableVoxel([H.AreaRatio(), H.Malfunction()], 7 + 13 * x, {"ACTUATOR": {"ZERO", "FROZEN", "RANDOM"}},
+                                       {"TIME": 1.5, "CONTROL": 25.0, "AREA": 60.0}, 0.4)
+    body = H.Grid.create(3, 1, mk)
+    ctrl = H.PhaseSin(1.0, 0.9, H.Grid.create(3, 1, lambda x, y: 0.8 * x))
+    res, pr = oracle.run(helpers.locomotion(6.0).compile([H.Robot(ctrl, body)]), signals=True, readings=True)
+    assert res[0]["status"] == 0
+    rd = pr["readings"][0].reshape(len(t), 3, 2)
+    seen = set()
+    for j in range(3):
+        want = np.sin(2 * np.pi * 1.0 * t + 0.8 * j) * 0.9
+        f, broken, _ = _breakable_restatement(body.get(j, 0), t, want, rd[:, j, 0], rd[:, j, :], [(0, 1)] * 2, False)
+        assert pr["signals"][0, :, j] == pytest.approx(f, abs=1e-12)
+        assert np.array_equal(rd[:, j, 1] == 1.0, broken)
+        seen |= {"broken"} if broken.any() else set()
+        assert broken.any() and not broken.all()                      # it breaks and it is restored
+        assert np.abs(f - want).max() > 0.1                           # ... and the malfunction changes what is applied
+    # a plain voxel in the same grid is left alone, and "broken-1-0" freezes every actuator from the first tick on
+    robot = H.Robot(ctrl, H.Grid.create(3, 1, lambda x, y: H.Voxel([H.AreaRatio(), H.Malfunction()])))
+    broken_robot = H.RobotUtils.build_robot_transformation("broken-1-0")(robot)
+    assert all(isinstance(v, H.BreakableVoxel) for v in broken_robot.get_voxels().values())
+    _, pb = oracle.run(helpers.locomotion(2.0).compile([broken_robot]), signals=True, readings=True)
+    assert np.all(pb["signals"][0, :, :3] == 0.0)                     # FROZEN at tick 0: the last applied force is 0
+    assert np.all(pb["readings"][0].reshape(-1, 3, 2)[1:, :, 1] == 1.0)
+    half = H.RobotUtils.build_robot_transformation("broken-0.5-3")(robot)
+    kinds = [isinstance(v, H.BreakableVoxel) for v in half.get_voxels().values()]
+    rnd = H.JavaRandom(3)
+    want_kinds = []
+    for _ in range(3):
+        b = not (rnd.next_double() > 0.5)
+        want_kinds.append(b)
+        if b:
+            rnd.next_int()
+    assert kinds == want_kinds
+    br = H.RobotUtils.build_robot_transformation("breakable-time-2/0.5-1/0.1-5")(robot)
+    v0 = br.get_voxels().get(0, 0)
+    rnd = H.JavaRandom(5)
+    assert v0.random_seed == rnd.next_int() and v0.trigger_thresholds == {"TIME": rnd.next_gaussian() * 0.5 + 2.0}
+    assert v0.restore_time == rnd.next_gaussian() * 0.1 + 1.0 and v0.malfunctions == {"ACTUATOR": frozenset({"FROZEN"})}
+    with pytest.raises(ValueError, match="Unknown transformation"):
+        H.RobotUtils.build_robot_transformation("melted-1")
+    with pytest.raises(ValueError, match="Unsupported structure"):
+        H.BreakableVoxel([], 0, {"STRUCTURE": {"RANDOM"}}, {"TIME": 1.0}, 1.0)
+
+
+def test_breakable_voxel_sensors_and_structure():
+    # SENSORS malfunctions reach the controller (CentralizedSensing reads Voxel.getSensorReadings): ZERO, FROZEN, RANDOM
+    # (uniform in each reading's domain, drawn from the voxel's own generator at control time)
+    t = H.tick_times(4.0, 1 / 60)
+    mk = lambda x, y: H.BreakableVoxel([H.SoftNormalization(H.AreaRatio()), H.Velocity(True, 8.0, H.Velocity.X)], 100 + x,
+                                       {"SENSORS": {"ZERO", "FROZEN", "RANDOM"}}, {"TIME": 0.8}, 0.3)
+    body = H.Grid.create(2, 1, mk)
+    nin, nout = H.CentralizedSensing.n_of_inputs(body), H.CentralizedSensing.n_of_outputs(body)
+    w = np.random.default_rng(3).uniform(-1, 1, size=H.MultiLayerPerceptron.count_weights([nin, nout]))
+    mlp = H.MultiLayerPerceptron("TANH", nin, [], nout, w)
+    res, pr = oracle.run(helpers.locomotion(4.0).compile([H.Robot(H.CentralizedSensing(body, mlp), body)]), signals=True, readings=True)
+    rd = pr["readings"][0].reshape(len(t), 2, 2)
+    doms = [(0.0, 1.0), (-8.0, 8.0)]
+    effs = []
+    for j in range(2):
+        _, _, eff = _breakable_restatement(body.get(j, 0), t, np.zeros(len(t)), np.ones(len(t)), rd[:, j, :], doms, True)
+        effs.append(np.stack(eff))
+    changed = 0
+    for k in range(len(t)):
+        x = np.concatenate([effs[0][k], effs[1][k]])
+        want = np.clip(mlp.apply(x), -1, 1)
+        assert pr["signals"][0, k, :2] == pytest.approx(want, abs=1e-12), k
+        changed += int(np.abs(x - rd[k].reshape(-1)).max() > 1e-9)
+    assert 10 < changed < len(t) - 10
+    # STRUCTURE FROZEN: the voxel's springs turn rigid at the break (setFrequency(0)) and -- as in the reference, which
+    # re-applies the structure state at a break only -- stay rigid after the restore
+    mk2 = lambda x, y: H.BreakableVoxel([], 1, {"STRUCTURE": {"FROZEN"}}, {"TIME": 0.5}, 0.2)
+    body2 = H.Grid.create(1, 1, mk2)
+    rob = H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(1, 1, 0.0)), body2)
+    _, p2 = oracle.run(helpers.locomotion(4.0).compile([rob]), trajectory=True)
+    ln = _spring_lengths(p2["trajectory"][0])[:, 0, 0]
+    t4 = H.tick_times(4.0, 1 / 60)
+    _, broken, _ = _breakable_restatement(body2.get(0, 0), t4, np.zeros(len(t4)), np.ones(len(t4)), np.zeros((len(t4), 0)), [], False)
+    k0 = int(np.argmax(broken)) - 1                                 # the tick of the first break
+    assert 10 < k0 < 150 and not broken[k0 + 1:].all()              # ... and there are restored stretches afterwards
+    assert np.ptp(ln[:k0]) > 0.05                                   # actuated and soft at first
+    assert np.ptp(ln[k0 + 5:]) < 0.02                               # rigid from the break on, restore or not
