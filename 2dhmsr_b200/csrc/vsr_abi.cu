@@ -514,6 +514,29 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     }
     S.n_readings = ro;
     S.n_channels = maxch;
+    // BreakableVoxel parameters (vsr_breakable), per voxel
+    S.has_breakable = 0;
+    if (sh.breakable)
+      for (int v = 0; v < nv; v++) {
+        const vsr_breakable& q = sh.breakable[v];
+        if (!q.enabled) continue;
+        if (q.malfunctions[VSR_COMPONENT_STRUCTURE] & ~((1u << VSR_MALFUNCTION_NONE) | (1u << VSR_MALFUNCTION_FROZEN))) {
+          delete b;
+          return fail(VSR_ERR_INVALID_ARGUMENT, "Unsupported structure malfunction type.");  // BreakableVoxel.java:258
+        }
+        if ((q.malfunctions[0] | q.malfunctions[1] | q.malfunctions[2]) & ~15u) {
+          delete b;
+          return fail(VSR_ERR_INVALID_ARGUMENT, "unknown malfunction type");
+        }
+        S.has_breakable = 1;
+        S.brk_enabled[v] = 1;
+        for (int z = 0; z < 3; z++) {
+          S.brk_mal[v][z] = (uint8_t)q.malfunctions[z];
+          S.brk_thr[v][z] = q.thresholds[z];
+        }
+        S.brk_restore[v] = q.restore_time;
+        S.brk_seed[v] = (long long)q.random_seed;
+      }
     // PhaseSin / TimeFunctions never read a sensor: unless the per-tick dumps (vsr_batch_sensor_readings) were asked
     // for, no reading is observable through the boundary and the sensor programs of such a batch are validated
     // above and then dropped
@@ -893,7 +916,8 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   }
   P.lim_lo_on = b->lim_lo_on ? 1 : 0;
   P.lim_hi_on = b->lim_hi_on ? 1 : 0;
-  const bool lim = b->lim_lo_on || b->lim_hi_on;
+  // the MODE 2 instantiation: rope limits and / or BreakableVoxels (its rigid-row tables serve both)
+  const bool lim = b->lim_lo_on || b->lim_hi_on || k.shape.has_breakable;
   P.weld_len = (real)(2.0 * b->half);
   P.vel_iters = st.velocity_iterations;
   P.pos_iters = st.position_iterations;

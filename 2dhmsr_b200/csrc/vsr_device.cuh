@@ -93,6 +93,13 @@ struct ShapeDev {
   int layer_off[MAX_LAYERS];  // offset of layer i's (transposed) weights
   int n_params;               // controller parameters per robot (device layout)
   int dist_off[MAX_VOX];      // DistributedSensing: offset of each voxel's weights in the robot's parameters
+  // BreakableVoxel parameters per voxel (vsr_breakable); read by the MODE 2 instantiation only
+  int has_breakable;
+  int8_t brk_enabled[MAX_VOX];
+  uint8_t brk_mal[MAX_VOX][4];   // malfunction type masks of ACTUATOR, SENSORS, STRUCTURE
+  double brk_thr[MAX_VOX][3];    // thresholds of CONTROL, AREA, TIME (NaN = absent)
+  double brk_restore[MAX_VOX];
+  long long brk_seed[MAX_VOX];
 };
 
 template <typename real>
@@ -212,6 +219,23 @@ __device__ __forceinline__ bool robot_sync_and(int id, int n, bool p) {
       : "r"(id), "r"(n), "r"((int)p)
       : "memory");
   return r != 0;
+}
+
+// java.util.Random (48-bit LCG): next(bits), nextDouble, nextInt(bound) -- BreakableVoxel draws from one per voxel
+__device__ __forceinline__ long long jr_next(unsigned long long& seed, int bits) {
+  seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+  return (long long)(seed >> (48 - bits));
+}
+__device__ __forceinline__ double jr_next_double(unsigned long long& seed) {
+  const long long a = jr_next(seed, 26), b = jr_next(seed, 27);
+  return (double)((a << 27) + b) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ int jr_next_int(unsigned long long& seed, int bound) {
+  if ((bound & -bound) == bound) return (int)(((long long)bound * jr_next(seed, 31)) >> 31);
+  for (;;) {
+    const long long bits = jr_next(seed, 31), val = bits % bound;
+    if (bits - val + (bound - 1) < (1LL << 31)) return (int)val;
+  }
 }
 
 // 4-wide value for one 128-bit (fp32) shared-memory access per spring
@@ -1254,6 +1278,17 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #pragma unroll
     for (int s = 0; s < (LIM ? 18 : 1); s++) slo[s] = shi[s] = real(0);
     const real inv_dt = real(1) / dt;
+    // BreakableVoxel (MODE 2 only): generator, malfunction state (2 bits per component: ACTUATOR, SENSORS, STRUCTURE;
+    // bit 6 = the springs are rigid, bit 7 = a readings snapshot exists), trigger counters, bookkeeping of act()
+    const bool brk = LIM && S.has_breakable && active && S.brk_enabled[v];
+    unsigned long long bseed = brk ? (((unsigned long long)S.brk_seed[v] ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1)) : 0ull;
+    unsigned bstate = 0;
+    real bcnt[3] = {real(0), real(0), real(0)};
+    double b_last_t = 0.0, b_last_break = 0.0;
+    real b_last_ce = real(0), b_last_are = real(0);
+    real snap[LIM ? MAX_READ : 1], rd_lo[LIM ? MAX_READ : 1], rd_hi[LIM ? MAX_READ : 1];
+#pragma unroll 1
+    for (int q = 0; q < (LIM ? MAX_READ : 1); q++) snap[q] = rd_lo[q] = rd_hi[q] = real(0);
     // weld impulses: [side L,R,D,U][pair][x,y,z]
     real wix[4][2], wiy[4][2], wiz[4][2];
 #pragma unroll
@@ -1372,6 +1407,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     real kk = m * sw * sw;                                                                         \
     real gamma = real(1) / (dt * (dc + dt * kk));                                                  \
     real bias = (len - rest[cls]) * dt * kk * gamma;                                               \
+    if (LIM && (bstate & 64u)) { gamma = real(0); bias = real(0); } /* STRUCTURE FROZEN: a rigid joint */ \
     real soft = real(1) / (invMass + gamma);                                                       \
     {                                                                                              \
       R4 q_; q_.x = nx; q_.y = ny; q_.z = cr1; q_.w = cr2;                                         \
@@ -1468,7 +1504,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
   if (FULLSPR || (P.spring_mask & (1u << s))) {                                                       \
     const R4 q_ = q##s;                                                                               \
     const R2 p_ = p##s;                                                                               \
-    const real g_ = EFFMASS ? sgam[s * SPR_STRIDE + tid] : gam_c;                                     \
+    const real g_ = (LIM && (bstate & 64u)) ? real(0) : (EFFMASS ? sgam[s * SPR_STRIDE + tid] : gam_c); \
     spring_solve(vx[b1], vy[b1], w[b1], vx[b2], vy[b2], w[b2], simp[s], q_, p_, g_, im, ii);          \
     if (LIM) {                                                                                        \
       /* the limit rows of DistanceJoint.solveVelocityConstraints (dyn4j 4.2 = Box2D 2.4's joint; the     \
@@ -1638,9 +1674,10 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
     const real len = r_sqrt(nx * nx + ny * ny);                                                       \
     const real inv = len > real(0) ? real(1) / len : real(0);                                         \
     nx *= inv; ny *= inv;                                                                             \
-    const bool lo_ = P.lim_lo_on && len < P.lim_lo[cls], hi_ = !lo_ && P.lim_hi_on && len > P.lim_hi[cls]; \
-    if (lo_ || hi_) {                                                                                 \
-      real C_ = lo_ ? len - P.lim_lo[cls] : len - P.lim_hi[cls];                                      \
+    const bool rg_ = (bstate & 64u) != 0u; /* rigid (STRUCTURE FROZEN): corrected to the rest distance on both sides */ \
+    const bool lo_ = !rg_ && P.lim_lo_on && len < P.lim_lo[cls], hi_ = !rg_ && !lo_ && P.lim_hi_on && len > P.lim_hi[cls]; \
+    if (rg_ || lo_ || hi_) {                                                                          \
+      real C_ = rg_ ? len - rest[cls] : (lo_ ? len - P.lim_lo[cls] : len - P.lim_hi[cls]);            \
       C_ = r_clamp<real>(C_, -P.max_corr, P.max_corr);                                                \
       const real imp_ = -slim[s * SPR_STRIDE + tid].x * C_ * pm_;                                     \
       const real Jx = nx * imp_, Jy = ny * imp_;                                                      \
@@ -2106,7 +2143,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             raw[0] = last_f;  // the force of the previous control step (sensors act before the controller)
             dmin = real(-1);
           } else if (sd.base == SENSOR_MALFUNCTION) {
-            raw[0] = real(0);
+            raw[0] = (LIM && (bstate & 63u)) ? real(1) : real(0);  // BreakableVoxel.isBroken, before this tick's update
           } else if (sd.base == SENSOR_TIME_SIN) {
             raw[0] = (real)sin(2.0 * 3.14159265358979323846 * (double)sd.max_norm * P.tick_t[tick]);
             dmin = real(-1);
@@ -2205,8 +2242,71 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               const real ext = sd.soft ? real(1) : dmax - dmin;
               o = o + (real)(P.noise_tab[(size_t)tick * sd.dim + d] * sd.noise) * ext;
             }
+            if (LIM) {  // the reading's final domain (Sensor.getDomains): what a RANDOM sensor malfunction draws from
+              rd_lo[ro] = sd.soft ? real(0) : dmin;
+              rd_hi[ro] = sd.soft ? real(1) : dmax;
+            }
             readings[ro++] = o;  // (dynamic index: a small thread-local array, not registers)
           }
+        }
+      }
+
+      // ---- BreakableVoxel.act after super.act (BreakableVoxel.java:127-168; the oracle's breakable_act): the readings
+      //      snapshot, the trigger counters, one draw per threshold in enum order, the break (component, type), restore
+      real effr_[LIM ? MAX_READ : 1];
+      real* const effr = LIM ? effr_ : readings;  // what Voxel.getSensorReadings returns to a controller
+      if (LIM) {
+        const int nr_ = (active && S.n_sens[v] > 0) ? ((v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - S.read_off[v]) : 0;
+        if (brk) {
+          const double t_ = P.tick_t[tick];
+          if (((bstate >> 2) & 3u) == 0u || !(bstate & 128u)) {
+#pragma unroll 1
+            for (int q = 0; q < nr_; q++) snap[q] = readings[q];
+            bstate |= 128u;
+          }
+          bcnt[2] = (real)(((double)bcnt[2] + t_) - b_last_t);  // (the reference's order: counter + t - lastT)
+          bcnt[0] = bcnt[0] + (ctrl_energy - b_last_ce);
+          bcnt[1] = bcnt[1] + (ar_energy - b_last_are);
+          b_last_t = t_;
+          b_last_ce = ctrl_energy;
+          b_last_are = ar_energy;
+          bool breaking = false;
+#pragma unroll 1
+          for (int g = 0; g < 3; g++) {
+            const double thr = S.brk_thr[v][g];
+            if (thr != thr) continue;
+            const double u = jr_next_double(bseed);
+            if (u < 1.0 - tanh(thr / (double)(g == 0 ? bcnt[0] : (g == 1 ? bcnt[1] : bcnt[2])))) {
+              bcnt[0] = bcnt[1] = bcnt[2] = real(0);
+              const unsigned m0 = S.brk_mal[v][0], m1 = S.brk_mal[v][1], m2 = S.brk_mal[v][2];
+              const int ncomp = (m0 != 0u) + (m1 != 0u) + (m2 != 0u);
+              if (ncomp > 0) {
+                breaking = true;
+                int ci = jr_next_int(bseed, ncomp);
+                int c = 0;
+                if (m0 != 0u && ci-- == 0) c = 0;
+                else if (m1 != 0u && ci-- == 0) c = 1;
+                else c = 2;
+                const unsigned mc = c == 0 ? m0 : (c == 1 ? m1 : m2);
+                const int ty = (int)__fns(mc, 0, jr_next_int(bseed, __popc(mc)) + 1);  // the n-th type of the set
+                bstate = (bstate & ~(3u << (2 * c))) | ((unsigned)ty << (2 * c));
+                // updateStructureMalfunctionType (:244-258): at a break only
+                bstate = (bstate & ~64u) | ((((bstate >> 4) & 3u) == 2u) ? 64u : 0u);
+              }
+            }
+          }
+          if (breaking) b_last_break = t_;
+          if (t_ - b_last_break > S.brk_restore[v]) bstate &= ~63u;
+        }
+        // BreakableVoxel.getSensorReadings (:183-193), asked for by a sensing controller only
+        if (CTRL == CTRL_MLP) {
+          const unsigned ss_ = brk ? ((bstate >> 2) & 3u) : 0u;
+#pragma unroll 1
+          for (int q = 0; q < nr_; q++)
+            effr_[q] = !brk ? readings[q]
+                            : (ss_ == 1u ? real(0)
+                                         : (ss_ == 3u ? (real)(jr_next_double(bseed) * (double)(rd_hi[q] - rd_lo[q]) + (double)rd_lo[q])
+                                                      : snap[q]));
         }
       }
 
@@ -2231,7 +2331,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           const int base = S.read_off[active ? v : 0];
           const int nr = active ? ((v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base) : 0;
 #pragma unroll 1
-          for (int q = 0; q < nr; q++) a[q] = readings[q];
+          for (int q = 0; q < nr; q++) a[q] = effr[q];
           nin = nr;
           // gather: side (kernel numbering 0 left, 1 right, 2 down, 3 up) of Dir d, and the slot the
           // neighbour wrote for the opposite direction
@@ -2293,7 +2393,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           int base = S.read_off[v];
           int nr = (v + 1 < nvox ? S.read_off[v + 1] : S.n_readings) - base;
 #pragma unroll 1
-          for (int q = 0; q < nr; q++) act0[base + q] = activation<real>(P.mlp_act, readings[q]);
+          for (int q = 0; q < nr; q++) act0[base + q] = activation<real>(P.mlp_act, effr[q]);
         }
         SSYNC()
         real* a = act0;
@@ -2313,6 +2413,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
         f = active ? a[v] : real(0);
         SSYNC()
+      }
+      if (LIM && brk) {  // BreakableVoxel.applyForce (:170-180)
+        const unsigned as_ = bstate & 3u;
+        if (as_ == 1u) f = real(0);
+        else if (as_ == 2u) f = last_f;
+        else if (as_ == 3u) f = (real)(jr_next_double(bseed) * 2.0 - 1.0);
       }
       if (r_abs(f) > real(1)) f = f > real(0) ? real(1) : real(-1);
       last_f = f;

@@ -73,7 +73,18 @@ def test_create_validates_like_the_reference():
     assert rc == A.VSR_ERR_INVALID_ARGUMENT and "areaRatioPassiveRange" in msg  # Voxel.java:132-140
     bd = loco.compile(helpers.phase_robots(2))
     bd.desc.material.area_ratio_passive_min, bd.desc.material.area_ratio_passive_max = 0.7, 1.3
-    assert _create(bd)[0] == A.VSR_ERR_UNSUPPORTED
+    assert _create(bd)[0] == A.VSR_OK                                          # rope limits: on the accelerated path
+    bd = loco.compile(helpers.phase_robots(2))
+    bd.desc.material.area_ratio_passive_min, bd.desc.material.area_ratio_passive_max = 1.05, 1.3
+    rc, msg = _create(bd)
+    assert rc == A.VSR_ERR_INVALID_ARGUMENT and "Wrong spring range" in msg    # SpringRange, Voxel.java:189-193
+    bd = loco.compile(helpers.phase_robots(2))
+    brk = (A.vsr_breakable * 10)()
+    brk[3].enabled = 1
+    brk[3].malfunctions[A.VSR_COMPONENT_STRUCTURE] = 1 << A.VSR_MALFUNCTION_RANDOM
+    bd.desc.shapes[0].breakable = C.cast(brk, C.POINTER(A.vsr_breakable))
+    rc, msg = _create(bd)
+    assert rc == A.VSR_ERR_INVALID_ARGUMENT and "Unsupported structure malfunction type" in msg  # BreakableVoxel.java:258
     bd = loco.compile(helpers.phase_robots(2))
     offs = np.asarray([0, 12, 23], dtype=np.uint64)
     bd.desc.param_offsets = C.cast(offs.ctypes.data, C.POINTER(C.c_size_t))

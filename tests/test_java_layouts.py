@@ -41,7 +41,7 @@ def test_panama_layouts_mirror_the_header_field_by_field():
     src = open(os.path.join(JAVA, "VsrLayouts.java")).read()
     layouts = _parse_layouts(src)
     structs = {"vsr_settings": A.vsr_settings, "vsr_material": A.vsr_material, "vsr_sensor": A.vsr_sensor,
-               "vsr_shape": A.vsr_shape, "vsr_batch_desc": A.vsr_batch_desc, "vsr_result": A.vsr_result}
+               "vsr_breakable": A.vsr_breakable, "vsr_shape": A.vsr_shape, "vsr_batch_desc": A.vsr_batch_desc, "vsr_result": A.vsr_result}
     assert set(layouts) == set(structs)
     for name, ct in structs.items():
         off = 0
