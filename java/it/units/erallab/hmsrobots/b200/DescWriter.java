@@ -139,7 +139,36 @@ final class DescWriter {
   }
 
   /** a shape class = occupancy + per-voxel flattened sensor lists (+ the MLP hidden layers of its controller) */
-  private record ShapeKey(int w, int h, List<Boolean> mask, List<List<FlatSensor>> sensors, List<Integer> hidden) {
+  private record ShapeKey(int w, int h, List<Boolean> mask, List<List<FlatSensor>> sensors, List<Integer> hidden,
+                          List<List<Double>> breakable) {
+  }
+
+  private static final List<String> COMPONENTS = List.of("ACTUATOR", "SENSORS", "STRUCTURE");   // BreakableVoxel.ComponentType
+  private static final List<String> TRIGGERS = List.of("CONTROL", "AREA", "TIME");               // MalfunctionTrigger
+  private static final List<String> TYPES = List.of("NONE", "ZERO", "FROZEN", "RANDOM");         // MalfunctionType
+
+  /** vsr_breakable of one voxel as [enabled, mask x 3, threshold x 3, restoreTime, seed]; a plain Voxel is all zeros */
+  private static List<Double> breakableOf(JsonNode vj) {
+    List<Double> q = new ArrayList<>(java.util.Collections.nCopies(9, 0d));
+    if (!vj.has("malfunctions")) {
+      return q;
+    }
+    q.set(0, 1d);
+    for (int c = 0; c < 3; c++) {
+      int mask = 0;
+      JsonNode set = vj.get("malfunctions").get(COMPONENTS.get(c));
+      if (set != null) {
+        for (JsonNode t : set) {
+          mask |= 1 << TYPES.indexOf(t.asText());
+        }
+      }
+      q.set(1 + c, (double) mask);
+      JsonNode thr = vj.get("triggerThresholds").get(TRIGGERS.get(c));
+      q.set(4 + c, thr == null ? Double.NaN : thr.asDouble());
+    }
+    q.set(7, Double.parseDouble(vj.get("restoreTime").asText()));
+    q.set(8, (double) vj.get("randomSeed").asLong());   // (seeds come from Random.nextInt: exact in a double)
+    return q;
   }
 
   private static int[] hiddenOf(MultiLayerPerceptron mlp) {
@@ -197,6 +226,7 @@ final class DescWriter {
       List<Boolean> mask = new ArrayList<>();
       List<List<FlatSensor>> sensors = new ArrayList<>();
       List<int[]> cells = new ArrayList<>();
+      List<List<Double>> breakable = new ArrayList<>();
       for (int y = 0; y < body.getH(); y++) {
         for (int x = 0; x < body.getW(); x++) {
           Voxel v = body.get(x, y);
@@ -207,7 +237,8 @@ final class DescWriter {
           cells.add(new int[]{x, y});
           JsonNode vj = OM.valueToTree(v);
           JsonNode m = vj.deepCopy();
-          ((com.fasterxml.jackson.databind.node.ObjectNode) m).remove("sensors");
+          ((com.fasterxml.jackson.databind.node.ObjectNode) m).remove(List.of("sensors", "malfunctions", "triggerThresholds", "restoreTime", "randomSeed"));
+          breakable.add(breakableOf(vj));   // BreakableVoxel.java:34-41 (@JsonProperty fields)
           if (material == null) {
             material = m;
           } else if (!material.equals(m)) {
@@ -280,7 +311,7 @@ final class DescWriter {
           params.add(p);
         }
       }
-      ShapeKey key = new ShapeKey(body.getW(), body.getH(), mask, sensors, hidden);
+      ShapeKey key = new ShapeKey(body.getW(), body.getH(), mask, sensors, hidden, breakable);
       Integer idx = shapeIndex.get(key);
       if (idx == null) {
         idx = shapes.size();
@@ -338,6 +369,22 @@ final class DescWriter {
       sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "sensors"), sens);
       sh.set(JAVA_INT, off(VsrLayouts.VSR_SHAPE, "n_hidden"), k.hidden().size());
       sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "hidden"), hid);
+      if (k.breakable().stream().anyMatch(q -> q.get(0) != 0d)) {
+        MemorySegment br = a.allocate(VsrLayouts.VSR_BREAKABLE, k.breakable().size());
+        br.fill((byte) 0);
+        for (int v = 0; v < k.breakable().size(); v++) {
+          List<Double> q = k.breakable().get(v);
+          MemorySegment b = br.asSlice(v * VsrLayouts.VSR_BREAKABLE.byteSize(), VsrLayouts.VSR_BREAKABLE.byteSize());
+          b.set(JAVA_INT, off(VsrLayouts.VSR_BREAKABLE, "enabled"), q.get(0).intValue());
+          for (int c = 0; c < 3; c++) {
+            b.set(JAVA_INT, off(VsrLayouts.VSR_BREAKABLE, "malfunctions") + 4L * c, q.get(1 + c).intValue());
+            b.set(JAVA_DOUBLE, off(VsrLayouts.VSR_BREAKABLE, "thresholds") + 8L * c, q.get(4 + c));
+          }
+          b.set(JAVA_DOUBLE, off(VsrLayouts.VSR_BREAKABLE, "restore_time"), q.get(7));
+          b.set(JAVA_LONG, off(VsrLayouts.VSR_BREAKABLE, "random_seed"), q.get(8).longValue());
+        }
+        sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "breakable"), br);
+      }
     }
     long total = params.stream().mapToLong(p -> p.length).sum();
     MemorySegment pv = a.allocate(JAVA_DOUBLE, Math.max(1, total));
