@@ -140,6 +140,7 @@ class vsr_shape(C.Structure):
         ("reserved", C.c_int32),
         ("hidden", C.POINTER(C.c_int32)),
         ("breakable", C.POINTER(vsr_breakable)),
+        ("material", C.POINTER(vsr_material)),
     ]
 
 

@@ -111,7 +111,104 @@ struct Xfer {
   size_t bytes = 0;
 };
 
+// The constants Voxel.assemble derives from the 13 constructor fields (Voxel.java:241-301), for one material.  A batch
+// has a default material (vsr_batch_desc.material) and a shape class may bring its own (vsr_shape.material): all voxels
+// of a ROBOT share one (the weld and contact rows between voxels are solved in closed form for equal masses).
+struct MatDev {
+  vsr_material m;
+  double L = 0, ms = 0, inv_m = 0, inv_i = 0, half = 0, red_mass = 0;
+  double rng_min[3], rng_rest[3], rng_max[3];
+  bool lim_lo_on = false, lim_hi_on = false;  // passive-range limits of the springs (Voxel.java:262-285,331-338)
+  double lim_lo[3] = {0, 0, 0}, lim_hi[3] = {0, 0, 0};
+  unsigned spring_mask = 0;
+};
+
+static int validate_material(const vsr_material& m) {
+  double lim = (2 * m.mass_side_length_ratio) * (2 * m.mass_side_length_ratio);
+  if (m.area_ratio_passive_min > -INFINITY && m.area_ratio_passive_min < lim)  // Voxel.java:132-140
+    return fail(VSR_ERR_INVALID_ARGUMENT, "Min of areaRatioPassiveRange cannot be lower than the value imposed by massSideLengthRatio");
+  if (m.area_ratio_passive_max < m.area_ratio_passive_min || m.area_ratio_active_max < m.area_ratio_active_min)
+    return fail(VSR_ERR_INVALID_ARGUMENT, "Max has to be lower or equal than min");  // DoubleRange.java:29-35
+  if (!(m.side_length > 0) || !(m.mass > 0) || !(m.mass_side_length_ratio > 0) || !(m.spring_f > 0))
+    return fail(VSR_ERR_INVALID_ARGUMENT, "non-positive voxel material parameter");
+  return VSR_OK;
+}
+
+// Capacity check instead of a run-time flag: a mass (a square of side mass_side_length, any rotation: an
+// interval of at most its diagonal on the x axis) can overlap at most `most` ground polygons at once
+// (Ground.java:61-79: one polygon per segment).  The device keeps MAXC constraints per mass, which covers
+// every terrain Locomotion.createTerrain can generate (segments >= 1 wide; steppy risers 0.5 wide between
+// treads >= 1 wide: at most 3); a profile that could need more is refused here, never truncated at run time.
+static int check_terrain_capacity(const vsr_batch_desc* d, const vsr_material& m) {
+  const double diag = m.side_length * m.mass_side_length_ratio * std::sqrt(2.0) + 1e-9;
+  std::vector<double> lo, hi;  // non-degenerate segments
+  for (int i = 0; i + 1 < d->terrain_n; i++)
+    if (d->terrain_xs[i + 1] > d->terrain_xs[i]) { lo.push_back(d->terrain_xs[i]); hi.push_back(d->terrain_xs[i + 1]); }
+  int most = 0;
+  for (size_t i = 0; i < lo.size(); i++) {
+    size_t k = i;
+    while (k + 1 < lo.size() && lo[k + 1] <= hi[i] + diag) k++;
+    most = std::max(most, (int)(k - i + 1));
+  }
+  if (most > vsr::MAXC)
+    return fail(VSR_ERR_UNSUPPORTED, "ground profile too fine: a mass could touch " + std::to_string(most) +
+                                         " ground polygons at once, the device keeps " + std::to_string(vsr::MAXC));
+  return VSR_OK;
+}
+
+static int derive_material(const vsr_material& m, MatDev& o) {
+  // ---- material: Voxel.assemble constants, Voxel.java:241-301
+  const double L = m.side_length, ms = L * m.mass_side_length_ratio;
+  o.m = m;
+  o.L = L;
+  o.ms = ms;
+  const double density = (m.mass / 4) / (ms * ms);
+  const double bmass = density * ms * ms, binertia = bmass * (ms * ms + ms * ms) / 12.0;
+  o.inv_m = 1.0 / bmass;
+  o.inv_i = 1.0 / binertia;
+  o.half = ms / 2.0;
+  o.red_mass = bmass * bmass / (bmass + bmass);
+  {
+    double amin = sqrt(L * L * m.area_ratio_active_min), amax = sqrt(L * L * m.area_ratio_active_max);
+    double sp_min = amin - 2.0 * ms, sp_rest = L - 2.0 * ms, sp_max = amax - 2.0 * ms;
+    o.rng_min[0] = sp_min; o.rng_rest[0] = sp_rest; o.rng_max[0] = sp_max;
+    o.rng_min[1] = sqrt(ms * ms + sp_min * sp_min);
+    o.rng_rest[1] = sqrt(ms * ms + sp_rest * sp_rest);
+    o.rng_max[1] = sqrt(ms * ms + sp_max * sp_max);
+    o.rng_min[2] = (amin - ms) * sqrt(2.0);
+    o.rng_rest[2] = (L - ms) * sqrt(2.0);
+    o.rng_max[2] = (amax - ms) * sqrt(2.0);
+    for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193
+      if (o.rng_min[c] > o.rng_rest[c] || o.rng_max[c] < o.rng_rest[c] || o.rng_min[c] < 0) {
+        return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
+      }
+    // the passive SpringRanges: finite bounds become the DistanceJoints' lower / upper limits
+    o.lim_lo_on = std::isfinite(m.area_ratio_passive_min);
+    o.lim_hi_on = std::isfinite(m.area_ratio_passive_max);
+    {
+      const double pmin = o.lim_lo_on ? sqrt(L * L * m.area_ratio_passive_min) : 0.0;
+      const double pmax = o.lim_hi_on ? sqrt(L * L * m.area_ratio_passive_max) : 0.0;
+      o.lim_lo[0] = pmin - 2.0 * ms; o.lim_hi[0] = pmax - 2.0 * ms;
+      o.lim_lo[1] = sqrt(ms * ms + o.lim_lo[0] * o.lim_lo[0]); o.lim_hi[1] = sqrt(ms * ms + o.lim_hi[0] * o.lim_hi[0]);
+      o.lim_lo[2] = (pmin - ms) * sqrt(2.0); o.lim_hi[2] = (pmax - ms) * sqrt(2.0);
+      for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193 (a NaN bound of an infinite range passes there too)
+        if ((o.lim_lo_on && (o.lim_lo[c] > o.rng_rest[c] || o.lim_lo[c] < 0)) || (o.lim_hi_on && o.lim_hi[c] < o.rng_rest[c])) {
+          return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
+        }
+    }
+    unsigned mask = 0;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_INTERNAL) mask |= 0x000Fu;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_EXTERNAL) mask |= 0x00F0u;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_CROSS) mask |= 0xFF00u;
+    if (m.spring_scaffoldings & VSR_SCAFFOLD_CENTRAL_CROSS) mask |= 0x30000u;
+    o.spring_mask = mask;
+  }
+
+  return VSR_OK;
+}
+
 struct Bucket {
+  MatDev mat;  // the material of this shape class
   ShapeDev shape;
   std::vector<int> robot_ids;  // batch indices, ascending
   std::vector<double> params;  // device layout, double on the host
@@ -159,12 +256,6 @@ struct vsr_batch {
   int ring_depth = 1;
   std::vector<double> terr_x, terr_y;  // local frame
   double base_y = 0, origin_x = 0;
-  double rng_min[3], rng_rest[3], rng_max[3];
-  // passive-range limits of the springs (Voxel.java:262-285,331-338): lower / upper per range class, when finite
-  bool lim_lo_on = false, lim_hi_on = false;
-  double lim_lo[3] = {0, 0, 0}, lim_hi[3] = {0, 0, 0};
-  double inv_m = 0, inv_i = 0, half = 0, red_mass = 0;
-  unsigned spring_mask = 0;
   size_t voxel_steps = 0;
   size_t upload_bytes = 0;
   long long plan_warps = 0;  // warps of all buckets together (the launch plan fills the chip once, not once per bucket)
@@ -247,41 +338,19 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
   for (int i = 1; i < d->terrain_n; i++)
     if (d->terrain_xs[i] < d->terrain_xs[i - 1])
       return fail(VSR_ERR_INVALID_ARGUMENT, "x coordinates must be sorted");  // Ground.java:55-58
-  {
-    // Capacity check instead of a run-time flag: a mass (a square of side mass_side_length, any rotation: an
-    // interval of at most its diagonal on the x axis) can overlap at most `most` ground polygons at once
-    // (Ground.java:61-79: one polygon per segment).  The device keeps MAXC constraints per mass, which covers
-    // every terrain Locomotion.createTerrain can generate (segments >= 1 wide; steppy risers 0.5 wide between
-    // treads >= 1 wide: at most 3); a profile that could need more is refused here, never truncated at run time.
-    const double diag = d->material.side_length * d->material.mass_side_length_ratio * std::sqrt(2.0) + 1e-9;
-    std::vector<double> lo, hi;  // non-degenerate segments
-    for (int i = 0; i + 1 < d->terrain_n; i++)
-      if (d->terrain_xs[i + 1] > d->terrain_xs[i]) { lo.push_back(d->terrain_xs[i]); hi.push_back(d->terrain_xs[i + 1]); }
-    int most = 0;
-    for (size_t i = 0; i < lo.size(); i++) {
-      size_t k = i;
-      while (k + 1 < lo.size() && lo[k + 1] <= hi[i] + diag) k++;
-      most = std::max(most, (int)(k - i + 1));
-    }
-    if (most > vsr::MAXC)
-      return fail(VSR_ERR_UNSUPPORTED, "ground profile too fine: a mass could touch " + std::to_string(most) +
-                                           " ground polygons at once, the device keeps " + std::to_string(vsr::MAXC));
+  // every material of the batch: the default one and those the shape classes bring
+  for (int si = -1; si < d->n_shapes; si++) {
+    const vsr_material* mm = si < 0 ? &d->material : d->shapes[si].material;
+    if (!mm) continue;
+    int rc = validate_material(*mm);
+    if (rc) return rc;
+    if ((rc = check_terrain_capacity(d, *mm))) return rc;
   }
   if (!d->params || !d->param_offsets) return fail(VSR_ERR_INVALID_ARGUMENT, "no controller parameters");
   if (d->controller_kind >= VSR_CTRL_DISTRIBUTED && (d->distributed_signals < 0 || d->distributed_signals > 4))
     return fail(VSR_ERR_UNSUPPORTED, "DistributedSensing: 0..4 signals per side are supported");
   if (d->controller_kind < VSR_CTRL_PHASE_SIN || d->controller_kind > VSR_CTRL_DISTRIBUTED_ND)
     return fail(VSR_ERR_INVALID_ARGUMENT, "unknown controller kind");
-  const vsr_material& m = d->material;
-  {
-    double lim = (2 * m.mass_side_length_ratio) * (2 * m.mass_side_length_ratio);
-    if (m.area_ratio_passive_min > -INFINITY && m.area_ratio_passive_min < lim)  // Voxel.java:132-140
-      return fail(VSR_ERR_INVALID_ARGUMENT, "Min of areaRatioPassiveRange cannot be lower than the value imposed by massSideLengthRatio");
-    if (m.area_ratio_passive_max < m.area_ratio_passive_min || m.area_ratio_active_max < m.area_ratio_active_min)
-      return fail(VSR_ERR_INVALID_ARGUMENT, "Max has to be lower or equal than min");  // DoubleRange.java:29-35
-    if (!(m.side_length > 0) || !(m.mass > 0) || !(m.mass_side_length_ratio > 0) || !(m.spring_f > 0))
-      return fail(VSR_ERR_INVALID_ARGUMENT, "non-positive voxel material parameter");
-  }
   const vsr_settings& st = d->settings;
   if (!(st.step_frequency > 0) || st.velocity_iterations < 0 || st.position_iterations < 0)
     return fail(VSR_ERR_INVALID_ARGUMENT, "invalid Settings");
@@ -301,52 +370,6 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
   if (nt > 32000) {
     delete b;
     return fail(VSR_ERR_UNSUPPORTED, "more than 32000 ticks");
-  }
-
-  // ---- material: Voxel.assemble constants, Voxel.java:241-301
-  const double L = m.side_length, ms = L * m.mass_side_length_ratio;
-  const double density = (m.mass / 4) / (ms * ms);
-  const double bmass = density * ms * ms, binertia = bmass * (ms * ms + ms * ms) / 12.0;
-  b->inv_m = 1.0 / bmass;
-  b->inv_i = 1.0 / binertia;
-  b->half = ms / 2.0;
-  b->red_mass = bmass * bmass / (bmass + bmass);
-  {
-    double amin = sqrt(L * L * m.area_ratio_active_min), amax = sqrt(L * L * m.area_ratio_active_max);
-    double sp_min = amin - 2.0 * ms, sp_rest = L - 2.0 * ms, sp_max = amax - 2.0 * ms;
-    b->rng_min[0] = sp_min; b->rng_rest[0] = sp_rest; b->rng_max[0] = sp_max;
-    b->rng_min[1] = sqrt(ms * ms + sp_min * sp_min);
-    b->rng_rest[1] = sqrt(ms * ms + sp_rest * sp_rest);
-    b->rng_max[1] = sqrt(ms * ms + sp_max * sp_max);
-    b->rng_min[2] = (amin - ms) * sqrt(2.0);
-    b->rng_rest[2] = (L - ms) * sqrt(2.0);
-    b->rng_max[2] = (amax - ms) * sqrt(2.0);
-    for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193
-      if (b->rng_min[c] > b->rng_rest[c] || b->rng_max[c] < b->rng_rest[c] || b->rng_min[c] < 0) {
-        delete b;
-        return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
-      }
-    // the passive SpringRanges: finite bounds become the DistanceJoints' lower / upper limits
-    b->lim_lo_on = std::isfinite(m.area_ratio_passive_min);
-    b->lim_hi_on = std::isfinite(m.area_ratio_passive_max);
-    {
-      const double pmin = b->lim_lo_on ? sqrt(L * L * m.area_ratio_passive_min) : 0.0;
-      const double pmax = b->lim_hi_on ? sqrt(L * L * m.area_ratio_passive_max) : 0.0;
-      b->lim_lo[0] = pmin - 2.0 * ms; b->lim_hi[0] = pmax - 2.0 * ms;
-      b->lim_lo[1] = sqrt(ms * ms + b->lim_lo[0] * b->lim_lo[0]); b->lim_hi[1] = sqrt(ms * ms + b->lim_hi[0] * b->lim_hi[0]);
-      b->lim_lo[2] = (pmin - ms) * sqrt(2.0); b->lim_hi[2] = (pmax - ms) * sqrt(2.0);
-      for (int c = 0; c < 3; c++)  // SpringRange, Voxel.java:189-193 (a NaN bound of an infinite range passes there too)
-        if ((b->lim_lo_on && (b->lim_lo[c] > b->rng_rest[c] || b->lim_lo[c] < 0)) || (b->lim_hi_on && b->lim_hi[c] < b->rng_rest[c])) {
-          delete b;
-          return fail(VSR_ERR_INVALID_ARGUMENT, "Wrong spring range");
-        }
-    }
-    unsigned mask = 0;
-    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_INTERNAL) mask |= 0x000Fu;
-    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_EXTERNAL) mask |= 0x00F0u;
-    if (m.spring_scaffoldings & VSR_SCAFFOLD_SIDE_CROSS) mask |= 0xFF00u;
-    if (m.spring_scaffoldings & VSR_SCAFFOLD_CENTRAL_CROSS) mask |= 0x30000u;
-    b->spring_mask = mask;
   }
 
   // ---- terrain, local frame
@@ -382,6 +405,14 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     const vsr_shape& sh = d->shapes[si];
     ShapeDev& S = buckets[si].shape;
     memset(&S, 0, sizeof S);
+    {
+      int rc = derive_material(sh.material ? *sh.material : d->material, buckets[si].mat);
+      if (rc) {
+        delete b;
+        return rc;
+      }
+    }
+    const double L = buckets[si].mat.L, ms = buckets[si].mat.ms;
     if (sh.w <= 0 || sh.h <= 0 || !sh.mask) {
       delete b;
       return fail(VSR_ERR_INVALID_ARGUMENT, "invalid shape grid");
@@ -635,7 +666,7 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
       // Locomotion.java:180-187 for this robot's own placement: x to the placement, y one unit above the ground
       const double px = d->robot_placement[r];
       double min_gap = INFINITY;
-      const double hh = m.side_length * m.mass_side_length_ratio / 2.0;
+      const double hh = k.mat.half;
       for (int v = 0; v < S.nvox; v++) {
         double cx = 0, mny = INFINITY;
         for (int q = 0; q < 4; q++) {
@@ -858,7 +889,8 @@ template <typename real>
 static int prepare_bucket(vsr_batch* b, Bucket& k) {
   const vsr_batch_desc& d = b->desc;
   const vsr_settings& st = d.settings;
-  const vsr_material& m = d.material;
+  const MatDev& M = k.mat;
+  const vsr_material& m = M.m;
   Params<real> P;
   memset(&P, 0, sizeof P);
   P.shape = k.d_shape;
@@ -891,9 +923,9 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   P.grav_y = (real)st.gravity_y;
   P.lin_damp = (real)m.mass_linear_damping;
   P.ang_damp = (real)m.mass_angular_damping;
-  P.inv_m = (real)b->inv_m;
-  P.inv_i = (real)b->inv_i;
-  P.half = (real)b->half;
+  P.inv_m = (real)M.inv_m;
+  P.inv_i = (real)M.inv_i;
+  P.half = (real)M.half;
   P.side = (real)m.side_length;
   P.lin_tol = (real)st.linear_tolerance;
   P.ang_tol = (real)st.angular_tolerance;
@@ -906,26 +938,26 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   P.rest_e = (real)std::max(m.restitution, st.ground_restitution);  // max(e1, e2)
   P.spring_w = (real)(2.0 * M_PI * m.spring_f);
   P.spring_zeta = (real)m.spring_d;
-  P.red_mass = (real)b->red_mass;
+  P.red_mass = (real)M.red_mass;
   for (int c = 0; c < 3; c++) {
-    P.rng_min[c] = (real)b->rng_min[c];
-    P.rng_rest[c] = (real)b->rng_rest[c];
-    P.rng_max[c] = (real)b->rng_max[c];
-    P.lim_lo[c] = (real)b->lim_lo[c];
-    P.lim_hi[c] = (real)b->lim_hi[c];
+    P.rng_min[c] = (real)M.rng_min[c];
+    P.rng_rest[c] = (real)M.rng_rest[c];
+    P.rng_max[c] = (real)M.rng_max[c];
+    P.lim_lo[c] = (real)M.lim_lo[c];
+    P.lim_hi[c] = (real)M.lim_hi[c];
   }
-  P.lim_lo_on = b->lim_lo_on ? 1 : 0;
-  P.lim_hi_on = b->lim_hi_on ? 1 : 0;
+  P.lim_lo_on = M.lim_lo_on ? 1 : 0;
+  P.lim_hi_on = M.lim_hi_on ? 1 : 0;
   // the MODE 2 instantiation: rope limits and / or BreakableVoxels (its rigid-row tables serve both)
-  const bool lim = b->lim_lo_on || b->lim_hi_on || k.shape.has_breakable;
-  P.weld_len = (real)(2.0 * b->half);
+  const bool lim = M.lim_lo_on || M.lim_hi_on || k.shape.has_breakable;
+  P.weld_len = (real)(2.0 * M.half);
   P.vel_iters = st.velocity_iterations;
   P.pos_iters = st.position_iterations;
   P.spring_mode = st.spring_mass_mode;
   P.self_coll = st.self_collision ? 1 : 0;
   P.mu_self = (real)std::sqrt(m.friction * m.friction);          // CoefficientMixer: sqrt(f1 f2)
   P.rest_e_self = (real)std::max(m.restitution, m.restitution);  // max(e1, e2)
-  P.spring_mask = b->spring_mask;
+  P.spring_mask = M.spring_mask;
   P.mlp_act = d.mlp_activation;
   P.dist_signals = d.controller_kind >= VSR_CTRL_DISTRIBUTED ? d.distributed_signals : -1;
   P.dist_nd = d.controller_kind == VSR_CTRL_DISTRIBUTED_ND ? 1 : 0;
@@ -1005,7 +1037,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   }
   P.sync_mode = tuning_env("VSR_SYNC") ? atoi(tuning_env("VSR_SYNC")) : (2 | 16 | 32 | 64);
   void (*kern)(const Params<real>) = nullptr;
-  const bool fast = !lim && (b->spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
+  const bool fast = !lim && (M.spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
 #define VSR_PICK(C)                                                                                  \
   kern = blk ? (fast ? vsr_episode_kernel<real, C, 1, true> : (lim ? vsr_episode_kernel<real, C, 2, true> : vsr_episode_kernel<real, C, 0, true>)) \
              : (fast ? vsr_episode_kernel<real, C, 1, false> : (lim ? vsr_episode_kernel<real, C, 2, false> : vsr_episode_kernel<real, C, 0, false>))

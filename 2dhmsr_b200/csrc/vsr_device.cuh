@@ -1664,7 +1664,8 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             // the island's order, the springs of a voxel before the welds
             r_sincos(th[0], &sn_[0], &cs_[0]);
             r_sincos(th[3], &sn_[3], &cs_[3]);
-            const real pm_ = done ? real(0) : real(1);
+            // (idle threads of a block robot carry dummy masses: they must neither move nor vote "unsolved")
+            const real pm_ = (done || !active) ? real(0) : real(1);
 #define VSR_SPRING_POS(s, nxt, b1, b2, a1x, a1y, a2x, a2y, cls)                                            \
   if (P.spring_mask & (1u << s)) {                                                                    \
     const real h_ = P.half;                                                                           \
@@ -1685,7 +1686,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       x[b2] -= Jx * im; y[b2] -= Jy * im; th[b2] -= ii * (r2x * Jy - r2y * Jx);                       \
       r_sincos(th[b1], &sn_[b1], &cs_[b1]);                                                           \
       r_sincos(th[b2], &sn_[b2], &cs_[b2]);                                                           \
-      solved = solved && (r_abs(C_) < P.lin_tol);                                                     \
+      solved = solved && (!active || r_abs(C_) < P.lin_tol);                                          \
     }                                                                                                 \
   }
             VSR_SPRINGS(VSR_SPRING_POS)

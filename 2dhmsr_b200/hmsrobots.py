@@ -1242,12 +1242,13 @@ def compile_batch(
                 dist_signals = r.controller.signals
             elif dist_signals != r.controller.signals:
                 raise ValueError("one DistributedSensing signal count per batch")
-        for mb in mats:
-            if material is None:
-                material = mb
-            elif material != mb:
-                raise NotImplementedError("one voxel material per batch on the accelerated path")
-        key = (vox.w, vox.h, mask, sens, hidden, repr(brk))
+        if len(mats) != 1:
+            # (the rows between the voxels of a robot -- welds, mass-mass contacts -- are solved for equal masses)
+            raise NotImplementedError("one voxel material per robot on the accelerated path")
+        (mat_r,) = mats
+        if material is None:
+            material = mat_r                      # the batch's default material: the first robot's
+        key = (vox.w, vox.h, mask, sens, hidden, repr(brk), mat_r)
         if key not in shape_keys:
             shape_brk[key] = brk
             shape_keys[key] = len(shapes_c)
@@ -1264,6 +1265,9 @@ def compile_batch(
     for k, key_k in enumerate(shapes_c):
         w, h, mask, sens, hidden = key_k[:5]
         m = b.keep(np.frombuffer(mask, dtype=np.uint8).copy())
+        if key_k[6] != material:                  # a shape class with its own material (vsr_shape.material)
+            mk = b.keep(A.vsr_material.from_buffer_copy(key_k[6]))
+            arr[k].material = C.pointer(mk)
         brk = shape_brk.get(key_k)
         if brk is not None:
             barr = (A.vsr_breakable * len(brk))()

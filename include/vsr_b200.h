@@ -187,6 +187,10 @@ typedef struct vsr_shape {
   int32_t reserved;
   const int32_t* hidden;          /* [n_hidden]                                         */
   const vsr_breakable* breakable; /* [n_voxels] in voxel order, or NULL: no BreakableVoxel in this shape class */
+  const struct vsr_material* material; /* the 13 Voxel constructor fields of this class' voxels, or NULL: the batch's
+                                          vsr_batch_desc.material.  One material per ROBOT (the rows between voxels
+                                          are solved in closed form for equal masses); robots of different materials
+                                          go to different shape classes of one batch.                             */
 } vsr_shape;
 
 /* ---- Controllers (one kind per batch; parameters per robot) ---- */

@@ -140,7 +140,7 @@ final class DescWriter {
 
   /** a shape class = occupancy + per-voxel flattened sensor lists (+ the MLP hidden layers of its controller) */
   private record ShapeKey(int w, int h, List<Boolean> mask, List<List<FlatSensor>> sensors, List<Integer> hidden,
-                          List<List<Double>> breakable) {
+                          List<List<Double>> breakable, JsonNode material) {
   }
 
   private static final List<String> COMPONENTS = List.of("ACTUATOR", "SENSORS", "STRUCTURE");   // BreakableVoxel.ComponentType
@@ -227,6 +227,7 @@ final class DescWriter {
       List<List<FlatSensor>> sensors = new ArrayList<>();
       List<int[]> cells = new ArrayList<>();
       List<List<Double>> breakable = new ArrayList<>();
+      JsonNode robotMaterial = null;   // one material per robot; robots of different materials -> different shape classes
       for (int y = 0; y < body.getH(); y++) {
         for (int x = 0; x < body.getW(); x++) {
           Voxel v = body.get(x, y);
@@ -240,9 +241,12 @@ final class DescWriter {
           ((com.fasterxml.jackson.databind.node.ObjectNode) m).remove(List.of("sensors", "malfunctions", "triggerThresholds", "restoreTime", "randomSeed"));
           breakable.add(breakableOf(vj));   // BreakableVoxel.java:34-41 (@JsonProperty fields)
           if (material == null) {
-            material = m;
-          } else if (!material.equals(m)) {
-            throw new UnsupportedOperationException("one voxel material per batch (include/vsr_b200.h)");
+            material = m;                // the batch's default material: the first voxel's
+          }
+          if (robotMaterial == null) {
+            robotMaterial = m;
+          } else if (!robotMaterial.equals(m)) {
+            throw new UnsupportedOperationException("one voxel material per robot (include/vsr_b200.h: vsr_shape.material)");
           }
           List<FlatSensor> fs = new ArrayList<>();
           for (JsonNode s : vj.get("sensors")) {
@@ -311,7 +315,7 @@ final class DescWriter {
           params.add(p);
         }
       }
-      ShapeKey key = new ShapeKey(body.getW(), body.getH(), mask, sensors, hidden, breakable);
+      ShapeKey key = new ShapeKey(body.getW(), body.getH(), mask, sensors, hidden, breakable, robotMaterial);
       Integer idx = shapeIndex.get(key);
       if (idx == null) {
         idx = shapes.size();
@@ -369,6 +373,11 @@ final class DescWriter {
       sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "sensors"), sens);
       sh.set(JAVA_INT, off(VsrLayouts.VSR_SHAPE, "n_hidden"), k.hidden().size());
       sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "hidden"), hid);
+      if (!k.material().equals(material)) {
+        MemorySegment mm = a.allocate(VsrLayouts.VSR_MATERIAL);
+        writeMaterial(mm, k.material());
+        sh.set(java.lang.foreign.ValueLayout.ADDRESS, off(VsrLayouts.VSR_SHAPE, "material"), mm);
+      }
       if (k.breakable().stream().anyMatch(q -> q.get(0) != 0d)) {
         MemorySegment br = a.allocate(VsrLayouts.VSR_BREAKABLE, k.breakable().size());
         br.fill((byte) 0);

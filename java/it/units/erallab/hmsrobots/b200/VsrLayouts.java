@@ -96,7 +96,8 @@ public final class VsrLayouts {
       JAVA_INT.withName("n_hidden"),
       JAVA_INT.withName("reserved"),
       ADDRESS.withName("hidden"),
-      ADDRESS.withName("breakable")
+      ADDRESS.withName("breakable"),
+      ADDRESS.withName("material")
   ).withName("vsr_shape");
 
   /* N robots, one terrain, one Settings (vsr_batch_desc) */

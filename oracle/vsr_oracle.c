@@ -207,6 +207,8 @@ typedef struct {
 typedef struct {
   int nv, nb, ns, nw;
   int next_full;
+  const vsr_material* mat; /* the robot's material: its shape class' own (vsr_shape.material) or the batch's */
+  double half;             /* half the side of a mass */
   OBreak* brk;     /* [nv] or NULL: no BreakableVoxel in this robot */
   double* snap;    /* [n_readings] BreakableVoxel.sensorReadings of every voxel */
   double* eff;     /* [n_readings] what Voxel.getSensorReadings returns at this control step */
@@ -336,9 +338,11 @@ static void add_weld(ORobot* r, int b1, int b2, int horizontal) {
 
 static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   const vsr_batch_desc* d = R->d;
-  const vsr_material* m = &d->material;
   const vsr_shape* sh = &d->shapes[d->robot_shape ? d->robot_shape[ridx] : 0];
+  const vsr_material* m = sh->material ? sh->material : &d->material;
   memset(r, 0, sizeof *r);
+  r->mat = m;
+  r->half = m->side_length * m->mass_side_length_ratio / 2.0;
   int nv = shape_nvox(sh);
   r->nv = nv;
   r->nb = 4 * nv;
@@ -661,17 +665,17 @@ static void robot_free(ORobot* r) {
 
 /* ------------------------------------------------------------------ dyn4j C.2 */
 /* AbstractPhysicsBody.integrateVelocity (dyn4j): no user forces are ever applied. */
-static void integrate_velocity(const vsr_batch_desc* d, OBody* b, double dt) {
+static void integrate_velocity(const vsr_batch_desc* d, const vsr_material* mat, OBody* b, double dt) {
   const vsr_settings* s = &d->settings;
   b->vx += dt * s->gravity_x;
   b->vy += dt * s->gravity_y;
-  double lin = 1.0 - dt * d->material.mass_linear_damping;
+  double lin = 1.0 - dt * mat->mass_linear_damping;
   lin = lin < 0 ? 0 : (lin > 1 ? 1 : lin);
-  if (d->material.mass_linear_damping != 0.0) {
+  if (mat->mass_linear_damping != 0.0) {
     b->vx *= lin;
     b->vy *= lin;
   }
-  double ang = 1.0 - dt * d->material.mass_angular_damping;
+  double ang = 1.0 - dt * mat->mass_angular_damping;
   ang = ang < 0 ? 0 : (ang > 1 ? 1 : ang);
   b->w *= ang;
 }
@@ -728,9 +732,9 @@ static void spring_init(const vsr_batch_desc* d, ORobot* r, OSpring* s, double d
   invMass += B2->invM + B2->invI * cr2 * cr2;
   double mass = invMass <= EPS_E ? 0.0 : 1.0 / invMass;
   double x = len - s->rest;
-  double w = TWO_PI * d->material.spring_f;
+  double w = TWO_PI * r->mat->spring_f;
   double m = spring_mass(&d->settings, B1, B2, mass);
-  double dc = 2.0 * m * d->material.spring_d * w;
+  double dc = 2.0 * m * r->mat->spring_d * w;
   double k = m * w * w;
   double gamma = dt * (dc + dt * k);
   gamma = gamma <= EPS_E ? 0.0 : 1.0 / gamma;
@@ -1191,12 +1195,12 @@ static void detect(ORun* R, ORobot* r) {
   r->contacts = t;
   r->cap_contacts = tc;
   r->ncontacts = 0;
-  double mu_g = sqrt(d->material.friction * d->settings.ground_friction); /* CoefficientMixer: sqrt(f1 f2) */
-  double e_g = fmax(d->material.restitution, d->settings.ground_restitution); /* max(e1,e2) */
+  double mu_g = sqrt(r->mat->friction * d->settings.ground_friction); /* CoefficientMixer: sqrt(f1 f2) */
+  double e_g = fmax(r->mat->restitution, d->settings.ground_restitution); /* max(e1,e2) */
   memset(r->touch, 0, (size_t)r->nv);
   for (int b = 0; b < r->nb; b++) {
     OPoly A;
-    mass_poly(&r->bodies[b], R->half, &A);
+    mass_poly(&r->bodies[b], r->half, &A);
     double minx = INFINITY, maxx = -INFINITY, miny = INFINITY;
     for (int i = 0; i < 4; i++) {
       if (A.vx[i] < minx) minx = A.vx[i];
@@ -1227,8 +1231,8 @@ static void detect(ORun* R, ORobot* r) {
   if (R->o.self_collision || d->settings.self_collision) {
     /* masses of the same robot collide unless welded (Voxel.java:178-185,474: RobotFilter allows
        every pair, the springs allow collisions, WeldJoint keeps dyn4j's default = not allowed) */
-    double mu_s = sqrt(d->material.friction * d->material.friction);
-    double e_s = d->material.restitution;
+    double mu_s = sqrt(r->mat->friction * r->mat->friction);
+    double e_s = r->mat->restitution;
     int canonical = R->o.order == VSR_ORACLE_ORDER_CANONICAL;
     int npairs = canonical ? r->nv * r->nv * 16 : r->nb * r->nb;
     for (int q = 0; q < npairs; q++) {
@@ -1246,7 +1250,7 @@ static void detect(ORun* R, ORobot* r) {
       {
         OBody* A0 = &r->bodies[a];
         OBody* B0 = &r->bodies[b];
-        double rr = 2.0 * R->half * 1.4142135623730951;
+        double rr = 2.0 * r->half * 1.4142135623730951;
         if (fabs(A0->x - B0->x) > rr || fabs(A0->y - B0->y) > rr) continue;
         int welded = 0;
         for (int w = 0; w < r->nw && !welded; w++)
@@ -1254,8 +1258,8 @@ static void detect(ORun* R, ORobot* r) {
             welded = 1;
         if (welded) continue;
         OPoly A, B;
-        mass_poly(A0, R->half, &A);
-        mass_poly(B0, R->half, &B);
+        mass_poly(A0, r->half, &A);
+        mass_poly(B0, r->half, &B);
         double nx, ny, depth;
         if (!sat_penetration(&A, &B, 1, &nx, &ny, &depth)) continue;
         OContact c;
@@ -1507,7 +1511,7 @@ static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p
 static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
   const vsr_batch_desc* d = R->d;
   const double dist_eps = cbrt(EPS_E);
-  const double rmax = R->half * 1.4142135623730951; /* Rectangle.getRadius */
+  const double rmax = r->half * 1.4142135623730951; /* Rectangle.getRadius */
   for (int b = 0; b < r->nb; b++) {
     OBody* B = &r->bodies[b];
     const double dpx = B->vx * dt, dpy = B->vy * dt, da = B->w * dt;
@@ -1515,8 +1519,8 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
     OBody b0 = *B;
     b0.x = pose0[b].x; b0.y = pose0[b].y; b0.th = pose0[b].th;
     OPoly P0, P1;
-    mass_poly(&b0, R->half, &P0);
-    mass_poly(B, R->half, &P1);
+    mass_poly(&b0, r->half, &P0);
+    mass_poly(B, r->half, &P1);
     double minx = INFINITY, maxx = -INFINITY, miny = INFINITY;
     for (int i = 0; i < 4; i++) {
       minx = fmin(minx, fmin(P0.vx[i], P1.vx[i]));
@@ -1538,7 +1542,7 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
       /* ConservativeAdvancement.getTimeOfImpact on [0, t2] */
       OBody lb = b0;
       OPoly A;
-      mass_poly(&lb, R->half, &A);
+      mass_poly(&lb, r->half, &A);
       double dist, p1x, p1y, p2x, p2y;
       if (!poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y)) continue; /* not separated at t = 0 */
       double l = 0.0, l0 = 0.0;
@@ -1557,11 +1561,11 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
           l0 = l;
           iter++;
           lb.x = b0.x + dpx * l; lb.y = b0.y + dpy * l; lb.th = b0.th + da * l;
-          mass_poly(&lb, R->half, &A);
+          mass_poly(&lb, r->half, &A);
           if (!poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y)) { /* overshoot: back up */
             l -= adv;
             lb.x = b0.x + dpx * l; lb.y = b0.y + dpy * l; lb.th = b0.th + da * l;
-            mass_poly(&lb, R->half, &A);
+            mass_poly(&lb, r->half, &A);
             poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y);
             break;
           }
@@ -1654,7 +1658,7 @@ static int world_step(ORun* R, ORobot* r, double dt) {
   }
 #define CON(i) (&r->contacts[dfs ? r->corder[i] : (i)])
   /* Island.solve (dyn4j): integrate velocities */
-  for (int b = 0; b < r->nb; b++) integrate_velocity(d, &r->bodies[b], dt);
+  for (int b = 0; b < r->nb; b++) integrate_velocity(d, r->mat, &r->bodies[b], dt);
   /* solver.initialize(contacts): all masses/biases first, then all warm starts */
   for (int i = 0; i < r->ncontacts; i++) contact_init(s, r, CON(i));
   for (int i = 0; i < r->ncontacts; i++) contact_warm(r, CON(i));
@@ -1723,9 +1727,9 @@ static int world_step(ORun* R, ORobot* r, double dt) {
 
 /* ------------------------------------------------------------------ voxel getters */
 /* outer corner of body k: getIndexedVertex(k, 3-k), Voxel.java:536-542,596-603 */
-static void outer_corner(const ORun* R, const OBody* b, int k, double* x, double* y) {
+static void outer_corner(double half, const OBody* b, int k, double* x, double* y) {
   static const double lx[4] = {-1, +1, +1, -1}, ly[4] = {+1, +1, -1, -1};
-  double c = cos(b->th), s = sin(b->th), px = lx[k] * R->half, py = ly[k] * R->half;
+  double c = cos(b->th), s = sin(b->th), px = lx[k] * half, py = ly[k] * half;
   *x = b->x + c * px - s * py;
   *y = b->y + s * px + c * py;
 }
@@ -1733,11 +1737,11 @@ static void outer_corner(const ORun* R, const OBody* b, int k, double* x, double
 /* Voxel.area (:508-516) with Poly.area (Poly.java:40-49), Voxel.getAreaRatio (:524-526) */
 static double voxel_area_ratio(const ORun* R, const ORobot* r, int v) {
   double X[4], Y[4];
-  for (int k = 0; k < 4; k++) outer_corner(R, &r->bodies[4 * v + k], k, &X[k], &Y[k]);
+  for (int k = 0; k < 4; k++) outer_corner(r->half, &r->bodies[4 * v + k], k, &X[k], &Y[k]);
   double a = 0.0;
   for (int i = 0; i < 4; i++) a = a + X[i] * (Y[(4 + i + 1) % 4] - Y[(4 + i - 1) % 4]);
   a = 0.5 * fabs(a);
-  double L = R->d->material.side_length;
+  double L = r->mat->side_length;
   return a / L / L;
 }
 
@@ -1746,7 +1750,7 @@ static void voxel_poly_center(const ORun* R, const ORobot* r, int v, double* cx,
   double sx = 0, sy = 0;
   for (int k = 0; k < 4; k++) {
     double x, y;
-    outer_corner(R, &r->bodies[4 * v + k], k, &x, &y);
+    outer_corner(r->half, &r->bodies[4 * v + k], k, &x, &y);
     sx += x;
     sy += y;
   }
@@ -1945,7 +1949,7 @@ static void robot_sense(ORun* R, ORobot* r, int tick) {
       for (int i = 0; i < 4; i++)
         for (int j = i + 1; j < 4; j++) {
           double dx = b[i].x - b[j].x, dy = b[i].y - b[j].y;
-          if (sqrt(dx * dx + dy * dy) < R->d->material.side_length * 0.2) c = c + 1.0;
+          if (sqrt(dx * dx + dy * dy) < r->mat->side_length * 0.2) c = c + 1.0;
         }
       raw[0] = 2.0 * c / 12.0;
     } else if (S->base == VSR_SENSOR_CONTROL_POWER) { /* ControlPower.java: lastT = the previous sense time */

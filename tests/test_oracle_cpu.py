@@ -619,3 +619,31 @@ def test_breakable_voxel_sensors_and_structure():
     cmd = np.where(f >= 0, rest - (rest - lo) * f, rest + (hi - rest) * -f)
     assert np.abs(ln - cmd)[1:k0].max() > 0.02                      # soft at first: the length lags the command
     assert np.abs(ln - cmd)[k0 + 3:].max() < 0.006                  # rigid from the break on (within linearTolerance), restore or not
+
+
+def _soft_heavy_material():
+    m = H.abi.default_material()
+    m.spring_f, m.mass, m.friction, m.side_length = 5.0, 2.0, 3.0, 2.5
+    return m
+
+
+def test_materials_per_shape_class_in_one_batch():
+    # Voxel.java:104-118: the 13 constructor fields belong to the voxel.  The device takes one material per ROBOT;
+    # robots of different materials share a batch (vsr_shape.material): each gives what it gives alone.
+    mats = [None, _soft_heavy_material()]
+    robots = []
+    for i in range(4):
+        body = H.Grid.create(3, 2, lambda x, y, m=mats[i % 2]: H.Voxel([H.AreaRatio()], m))
+        robots.append(H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(3, 2, lambda x, y: 0.5 * x + 0.1 * i)), body))
+    loco = helpers.locomotion(3.0)
+    bd = loco.compile(robots)
+    assert bd.desc.n_shapes == 4 or bd.desc.n_shapes == 2
+    together, _ = oracle.run(bd)
+    for i, r in enumerate(robots):
+        alone, _ = oracle.run(loco.compile([r]))
+        assert alone[0].tobytes() == together[i].tobytes(), i
+    assert abs(together[0]["last_center_x"] - together[1]["last_center_x"]) > 1e-3   # the material matters
+    # ... but not two materials inside one robot
+    mixed = H.Grid.create(2, 1, lambda x, y: H.Voxel([], mats[x]))
+    with pytest.raises(NotImplementedError, match="one voxel material per robot"):
+        loco.compile([H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(2, 1, 0.0)), mixed)])
