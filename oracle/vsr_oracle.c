@@ -28,8 +28,8 @@
  * Each numbered dyn4j item of SURVEY.md Appendix C sits behind one function so it
  * can be corrected if a dyn4j 4.2.1 run ever becomes available.
  *
- * Documented omissions: at-rest sleeping (actuated robots are woken every tick by
- * setRestDistance); the CCD / time-of-impact pass is behind vsr_oracle_opts.ccd (off by default, as in the kernel).
+ * the CCD / time-of-impact pass and at-rest sleeping sit behind vsr_oracle_opts.ccd / .sleeping (off by
+ * default, as in the kernel, which has neither; actuated robots are woken every tick by setRestDistance).
  * DistanceJoint limits (a finite passive range, Voxel.java:66,264-267,331-338) are restated from the published
  * Box2D 2.4 joint that dyn4j 4.2 ported.
  */
@@ -207,6 +207,9 @@ typedef struct {
 typedef struct {
   int nv, nb, ns, nw;
   int next_full;
+  /* at-rest detection (vsr_oracle_opts.sleeping): the robot is one island */
+  int asleep;
+  double* rest_time; /* [nb] Body.atRestTime */
   const vsr_material* mat; /* the robot's material: its shape class' own (vsr_shape.material) or the batch's */
   double half;             /* half the side of a mass */
   OBreak* brk;     /* [nv] or NULL: no BreakableVoxel in this robot */
@@ -562,6 +565,7 @@ static int robot_build(ORun* R, ORobot* r, size_t ridx) {
   }
   r->n_readings = off_r;
   r->readings = (double*)calloc((size_t)(off_r + 1), sizeof(double));
+  r->rest_time = (double*)calloc((size_t)r->nb + 1, sizeof(double));
   r->brk = NULL;
   r->snap = r->eff = r->rd_min = r->rd_max = NULL;
   if (sh->breakable) {
@@ -649,6 +653,7 @@ static void robot_free(ORobot* r) {
   free(r->ctrl_energy);
   free(r->touch);
   free(r->readings);
+  free(r->rest_time);
   free(r->brk);
   free(r->snap);
   free(r->eff);
@@ -1649,6 +1654,9 @@ static void island_order(ORobot* r) {
 static int world_step(ORun* R, ORobot* r, double dt) {
   const vsr_batch_desc* d = R->d;
   const vsr_settings* s = &d->settings;
+  /* an island at rest is not simulated (ConstraintGraph.solve starts islands from bodies that are not at rest); its
+     manifolds do not change, so the detection is skipped with it */
+  if (R->o.sleeping && r->asleep) return 0;
   const int dfs = R->o.order == VSR_ORACLE_ORDER_DFS;
   if (dfs) island_order(r);
   OPose* pose0 = NULL;
@@ -1704,6 +1712,25 @@ static int world_step(ORun* R, ORobot* r, double dt) {
     if (contactsSolved && jointsSolved) break;
   }
 #undef CON
+  if (R->o.sleeping) {
+    /* Island.solve, at-rest detection (dyn4j; Settings defaults: 0.01 u/s, 2 degrees/s, 0.5 s) */
+    const double lin2 = 0.01 * 0.01, ang = 2.0 * PI / 180.0, max_rest = 0.5;
+    double min_rest = INFINITY;
+    for (int b = 0; b < r->nb; b++) {
+      OBody* B = &r->bodies[b];
+      if (B->vx * B->vx + B->vy * B->vy > lin2 || fabs(B->w) > ang) {
+        r->rest_time[b] = 0.0;
+        min_rest = 0.0;
+      } else {
+        r->rest_time[b] += dt;
+        if (r->rest_time[b] < min_rest) min_rest = r->rest_time[b];
+      }
+    }
+    if (min_rest >= max_rest) {
+      r->asleep = 1; /* Body.setAtRest(true): velocities zeroed */
+      for (int b = 0; b < r->nb; b++) r->bodies[b].vx = r->bodies[b].vy = r->bodies[b].w = 0.0;
+    }
+  }
   if (pose0) {
     ccd_pass(R, r, pose0, dt);
     free(pose0);
@@ -2032,8 +2059,13 @@ static void voxel_apply_force(ORobot* r, int v, double f) {
   int per = r->ns / (r->nv > 0 ? r->nv : 1);
   for (int k = 0; k < per; k++) {
     OSpring* s = &r->springs[v * per + k];
+    double old = s->rest;
     if (f >= 0) s->rest = s->rrest - (s->rrest - s->rmin) * f;
     else if (f < 0) s->rest = s->rrest + (s->rmax - s->rrest) * -f;
+    if (s->rest != old && r->asleep) { /* DistanceJoint.setRestDistance wakes both bodies when the value changes */
+      r->asleep = 0;
+      for (int b = 0; b < r->nb; b++) r->rest_time[b] = 0.0;
+    }
   }
 }
 

@@ -47,7 +47,9 @@ typedef struct vsr_oracle_opts {
   int32_t state_fp32;   /* 1: after every step the bodies' poses (relative to the placement x, as the kernel keeps
                            them) and velocities are rounded to float: what fp32 STORAGE of the state alone does to a
                            trajectory -- the yardstick of the fp32 short-horizon test                              */
-  int32_t reserved;
+  int32_t sleeping;     /* 1: dyn4j's at-rest detection (C.7): an island whose bodies all stayed below 0.01 u/s and 2 deg/s
+                           for 0.5 s is put at rest (velocities zeroed, not simulated) until DistanceJoint.setRestDistance
+                           CHANGES a rest distance, i.e. until the controller asks for a different force              */
 } vsr_oracle_opts;
 
 /* Optional per-tick probes; any pointer may be NULL.  Row r is robot

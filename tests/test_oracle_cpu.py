@@ -647,3 +647,25 @@ def test_materials_per_shape_class_in_one_batch():
     mixed = H.Grid.create(2, 1, lambda x, y: H.Voxel([], mats[x]))
     with pytest.raises(NotImplementedError, match="one voxel material per robot"):
         loco.compile([H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(2, 1, 0.0)), mixed)])
+
+
+def test_at_rest_sleeping_never_touches_an_actuated_robot():
+    # SURVEY C.7, the second dyn4j feature the kernel leaves out: at-rest detection.  An island sleeps after 0.5 s below
+    # 0.01 u/s and 2 deg/s and wakes when DistanceJoint.setRestDistance changes a value.  A controller changes the rest
+    # distances at every tick, so the switch changes NOTHING for actuated robots (bitwise, configs 2 and 3) ...
+    import workloads
+    for loco, robots in (workloads.config2(24, seed=0), workloads.config3(8, hidden=(21, 21), seed=1)):
+        bd = H.Locomotion(6.0, loco.ground_profile, loco.settings).compile(robots)
+        a, _ = oracle.run(bd, n_threads=8)
+        b2, _ = oracle.run(bd, n_threads=8, sleeping=True)
+        assert a.tobytes() == b2.tobytes()
+    # ... and only a passive robot ever sleeps: it settles, its velocities are zeroed for good, and it stays where the
+    # always-awake robot keeps creeping by less than a tenth of the linear tolerance
+    bd = helpers.locomotion(8.0).compile(helpers.phase_robots(1, shape="box-2x1", amp=0.0))
+    _, awake = oracle.run(bd, trajectory=True)
+    _, slept = oracle.run(bd, trajectory=True, sleeping=True)
+    v = np.abs(slept["trajectory"][0][..., 3:]).max(axis=1).max(axis=1)
+    k0 = int(np.argmax(v == 0.0))
+    assert 60 < k0 < 420 and np.all(v[k0:] == 0.0)                    # asleep from k0 on
+    assert np.abs(slept["trajectory"][0][k0:, :, :2] - slept["trajectory"][0][k0, :, :2]).max() == 0.0
+    assert np.abs(awake["trajectory"][0][-1, :, :2] - slept["trajectory"][0][-1, :, :2]).max() < 5e-4
