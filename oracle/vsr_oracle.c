@@ -1057,6 +1057,9 @@ typedef struct {
   int index;             /* edge index */
 } OEdge;
 
+/* vsr_oracle_opts.dyn4j_labels of the run in progress (one run at a time per process; all threads share it) */
+static int g_dyn4j_labels = 0;
+
 /* Polygon.getFarthestFeature (dyn4j): farthest vertex, then the adjacent edge most
    perpendicular to n, keeping the CCW winding. */
 static void farthest_edge(const OPoly* P, double nx, double ny, OEdge* e) {
@@ -1092,7 +1095,7 @@ static void farthest_edge(const OPoly* P, double nx, double ny, OEdge* e) {
     /* dyn4j labels this edge `idx`, i.e. 0 for the wrap-around edge (n-1 -> 0) that the other
        branch labels n.  When n is the edge's own normal both end points tie as "farthest" and the
        label would flip with the rounding; one label per edge keeps the warm start deterministic. */
-    e->index = idx == 0 ? P->n : idx;
+    e->index = (idx == 0 && !g_dyn4j_labels) ? P->n : idx;
   }
 }
 
@@ -2263,6 +2266,7 @@ int vsr_oracle_run(const vsr_batch_desc* d, const vsr_oracle_opts* opts, vsr_res
   else vsr_oracle_default_opts(&R.o);
   if (R.o.robot_end == 0 || R.o.robot_end > d->n_robots) R.o.robot_end = d->n_robots;
   if (R.o.robot_begin > R.o.robot_end) return fail(VSR_ERR_INVALID_ARGUMENT, "robot range");
+  g_dyn4j_labels = R.o.dyn4j_labels != 0;
   R.probe = probe;
   R.out = out;
   double dt = d->settings.step_frequency;

@@ -50,6 +50,11 @@ typedef struct vsr_oracle_opts {
   int32_t sleeping;     /* 1: dyn4j's at-rest detection (C.7): an island whose bodies all stayed below 0.01 u/s and 2 deg/s
                            for 0.5 s is put at rest (velocities zeroed, not simulated) until DistanceJoint.setRestDistance
                            CHANGES a rest distance, i.e. until the controller asks for a different force              */
+  int32_t dyn4j_labels; /* 1: contact ids as dyn4j labels them -- the wrap-around edge of a polygon is 0 or n depending on
+                           which of its end points wins "farthest vertex"; default 0: one label per edge (the rule the
+                           kernel shares: when the SAT axis is the edge's own normal the two tie and dyn4j's label, hence
+                           its warm start, follows the rounding)                                                       */
+  int32_t reserved;
 } vsr_oracle_opts;
 
 /* Optional per-tick probes; any pointer may be NULL.  Row r is robot

@@ -156,6 +156,19 @@ def test_frames_png_residuals_are_the_tabulated_ones():
     assert _frames_residual(self_collision=0, ccd=True) == pytest.approx(2.87, abs=0.02)        # the best of the 24 rows
 
 
+def test_dyn4j_contact_labels_switch():
+    # the third dyn4j item behind a switch: contact ids labelled as dyn4j does (the wrap-around edge
+    # is 0 or n by a floating-point tie) instead of one label per edge.  It only changes which impulses are warm-started:
+    # live, deterministic, and it does not close the frames.png gap either.
+    bd = helpers.locomotion(3.0).compile(helpers.phase_robots(4, seed=2))
+    a, _ = oracle.run(bd)
+    b2, _ = oracle.run(bd, dyn4j_labels=True)
+    c, _ = oracle.run(bd, dyn4j_labels=True)
+    assert b2.tobytes() == c.tobytes() and a.tobytes() != b2.tobytes()
+    assert np.abs(a["last_center_x"] - b2["last_center_x"]).max() < 3.0
+    assert _frames_residual(dyn4j_labels=True) > 2.0 and _frames_residual(dyn4j_labels=True, order=oracle.ORDER_DFS, ccd=True) > 2.0
+
+
 def test_island_dfs_order_and_ccd_switches():
     # dyn4j's own constraint order (island discovery, depth first) and its time-of-impact pass sit
     # behind single switches of the oracle; both are deterministic, both change a trajectory only after the first
