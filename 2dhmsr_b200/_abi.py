@@ -75,6 +75,8 @@ class vsr_settings(C.Structure):
         ("ground_restitution", C.c_double),
         ("spring_mass_mode", C.c_int32),
         ("self_collision", C.c_int32),
+        ("continuous_detection", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

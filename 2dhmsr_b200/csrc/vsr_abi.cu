@@ -64,6 +64,8 @@ extern "C" void vsr_default_settings(vsr_settings* s) {
   s->ground_restitution = 0.0;
   s->spring_mass_mode = VSR_SPRING_MASS_REDUCED;
   s->self_collision = 1;
+  s->continuous_detection = 0;
+  s->reserved = 0;
 }
 
 extern "C" void vsr_default_material(vsr_material* m) {
@@ -226,6 +228,8 @@ struct Bucket {
   double default_dx = 0, default_dy = 0;
   void* d_vtrace = nullptr;
   void* d_rtrace = nullptr;  // [traj_robots][n_ticks][n_readings]
+  void* d_ccd = nullptr;     // continuous detection: poses at the start of the step, poses now, velocities: [36][grid threads]
+  size_t ccd_bytes = 0;
   void* d_cbuf = nullptr;
   size_t cbuf_bytes = 0;
   void* d_sbuf = nullptr;  // intra-robot contact arena
@@ -306,8 +310,8 @@ static void free_device(vsr_batch* b) {
   b->side_streams.clear(); b->side_done.clear(); b->fork_event = nullptr;
   free_xfers(b);  // owns d_ticks, d_win, d_terr_*, d_shape, d_ids, d_params and their pinned copies
   for (auto& k : b->buckets) {
-    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_rtrace); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
-    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_place = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr; k.d_rtrace = nullptr;
+    cudaFree(k.d_ring); cudaFree(k.d_traj); cudaFree(k.d_vtrace); cudaFree(k.d_rtrace); cudaFree(k.d_ccd); cudaFree(k.d_cbuf); cudaFree(k.d_sbuf); cudaFree(k.d_lbuf);
+    k.d_shape = nullptr; k.d_ids = nullptr; k.d_params = nullptr; k.d_place = nullptr; k.d_ring = nullptr; k.d_traj = nullptr; k.d_vtrace = nullptr; k.d_rtrace = nullptr; k.d_ccd = nullptr; k.ccd_bytes = 0;
     k.d_cbuf = nullptr; k.cbuf_bytes = 0;
     k.d_sbuf = nullptr; k.sbuf_bytes = 0;
     k.d_lbuf = nullptr; k.lbuf_bytes = 0;
@@ -950,11 +954,17 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   P.lim_hi_on = M.lim_hi_on ? 1 : 0;
   // the MODE 2 instantiation: rope limits and / or BreakableVoxels (its rigid-row tables serve both)
   const bool lim = M.lim_lo_on || M.lim_hi_on || k.shape.has_breakable;
+  // MODE: 1 = the default voxel, 3 = the default voxel + continuous detection, 2 = limits / BreakableVoxels (and
+  // continuous detection for everything that is not the default voxel), 0 = the other generic cases
+  const bool fast = !lim && (M.spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
+  const int mode = fast ? (st.continuous_detection ? 3 : 1) : ((lim || st.continuous_detection) ? 2 : 0);
+  const bool lim_layout = mode == 2;  // the MODE 2 tables: 256 / 128 thread columns, (rigid mass, length) per spring
   P.weld_len = (real)(2.0 * M.half);
   P.vel_iters = st.velocity_iterations;
   P.pos_iters = st.position_iterations;
   P.spring_mode = st.spring_mass_mode;
   P.self_coll = st.self_collision ? 1 : 0;
+  P.ccd = st.continuous_detection ? 1 : 0;
   P.mu_self = (real)std::sqrt(m.friction * m.friction);          // CoefficientMixer: sqrt(f1 f2)
   P.rest_e_self = (real)std::max(m.restitution, m.restitution);  // max(e1, e2)
   P.spring_mask = M.spring_mask;
@@ -996,7 +1006,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   // Big robots: a robot takes wpr whole warps and a block holds rpb robots that walk the instruction stream
   // together (one 2..4-warp block per robot ran at its own PC: instruction fetch was 30 % of the stall samples);
   // the block's tables have `stride` thread columns (fp32 256, fp64 128).
-  const int stride = (blk || lim) ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
+  const int stride = (blk || lim_layout) ? (sizeof(real) == 4 ? 256 : 128) : (sizeof(real) == 4 ? VSR_MAX_THREADS : VSR_MAX_THREADS / 2);
   if (!blk) wpb = std::min(wpb, stride / 32);
   const int wpr = blk ? (nvox + 31) / 32 : 1;
   int rpb = blk ? std::max(1, std::min(stride / 32, std::max(wpb_fill, wpr)) / wpr) : 1;
@@ -1011,7 +1021,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
   // contact exchange (+ the neighbour exchange of the big-robot variant)
   auto fixed_smem = [&](int wpb_, int rpb_) {
-    return (size_t)18 * stride * (6 + (eff_mode ? 1 : 0) + (lim ? 2 : 0)) * sizeof(real) +
+    return (size_t)18 * stride * (6 + (eff_mode ? 1 : 0) + (lim_layout ? 2 : 0)) * sizeof(real) +
            ((size_t)wpb_ * P.smem_per_warp + (size_t)16 * stride + (size_t)(blk ? rpb_ : wpb_) * VSR_LHD_REALS) * sizeof(real) +
            (blk ? (size_t)2 * 20 * stride * sizeof(real) : 0);
   };
@@ -1037,10 +1047,9 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   }
   P.sync_mode = tuning_env("VSR_SYNC") ? atoi(tuning_env("VSR_SYNC")) : (2 | 16 | 32 | 64);
   void (*kern)(const Params<real>) = nullptr;
-  const bool fast = !lim && (M.spring_mask == 0x3FFFFu) && st.spring_mass_mode == VSR_SPRING_MASS_REDUCED;
 #define VSR_PICK(C)                                                                                  \
-  kern = blk ? (fast ? vsr_episode_kernel<real, C, 1, true> : (lim ? vsr_episode_kernel<real, C, 2, true> : vsr_episode_kernel<real, C, 0, true>)) \
-             : (fast ? vsr_episode_kernel<real, C, 1, false> : (lim ? vsr_episode_kernel<real, C, 2, false> : vsr_episode_kernel<real, C, 0, false>))
+  kern = blk ? (mode == 1 ? vsr_episode_kernel<real, C, 1, true> : (mode == 3 ? vsr_episode_kernel<real, C, 3, true> : (mode == 2 ? vsr_episode_kernel<real, C, 2, true> : vsr_episode_kernel<real, C, 0, true>))) \
+             : (mode == 1 ? vsr_episode_kernel<real, C, 1, false> : (mode == 3 ? vsr_episode_kernel<real, C, 3, false> : (mode == 2 ? vsr_episode_kernel<real, C, 2, false> : vsr_episode_kernel<real, C, 0, false>)))
   switch (d.controller_kind) {
     case VSR_CTRL_PHASE_SIN: VSR_PICK(CTRL_PHASE_SIN); break;
     case VSR_CTRL_TABULATED: VSR_PICK(CTRL_TABULATED); break;
@@ -1077,6 +1086,14 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
       k.sbuf_bytes = need_s;
     }
     P.sbuf = k.d_sbuf;
+    size_t need_c = P.ccd ? (size_t)grid * threads * 40 * sizeof(real) : 0;
+    if (need_c > k.ccd_bytes) {
+      cudaFree(k.d_ccd);
+      k.d_ccd = nullptr;
+      CUDA_TRY(cudaMalloc(&k.d_ccd, need_c));
+      k.ccd_bytes = need_c;
+    }
+    P.ccd_buf = (real*)k.d_ccd;
     size_t need_l = (size_t)grid * VSR_ITEMS_PER_THREAD * stride * sizeof(int);
     if (need_l > k.lbuf_bytes) {
       cudaFree(k.d_lbuf);

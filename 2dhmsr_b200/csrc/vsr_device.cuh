@@ -156,6 +156,8 @@ struct Params {
   void* sbuf;            // intra-robot contact arena: [grid threads][2 buffers] SList<real>
   int* lbuf;             // contact lists: [grid blocks][VSR_ITEMS_PER_THREAD * max threads per block]
   int pool_cap;          // constraints of a block cached in shared memory (the rest stay in global)
+  int ccd;               // vsr_settings.continuous_detection: the time-of-impact pass after the position solve
+  real* ccd_buf;         // [36][grid threads]: poses at the start of the step (Body.transform0), poses now, velocities
   int self_coll;         // masses of one robot collide with each other (vsr_settings.self_collision)
   real mu_self, rest_e_self;
   int ctrl;              // CTRL_*
@@ -597,6 +599,228 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
   if (cn > 0 || had_contact) cb.n = cn;
   n_out = cn;
   return overflow;
+}
+
+// ---------------------------------------------------------------- continuous collision detection
+// World.solveTOI for the masses against the ground (dyn4j, ContinuousDetectionMode.ALL; the oracle's ccd_pass): a mass
+// moved from pose0 by (v dt, w dt); against every ground polygon its swept box overlaps and it is NOT in contact with
+// (the constraints of the last detection), conservative advancement finds the first time in [0, 1] at which the two come
+// within distanceEpsilon; the mass is put back to that time (transform0.lerp) and TimeOfImpactSolver pushes it
+// linearTolerance into the polygon.  Velocities are not touched.
+//
+// ONE WARP works on ONE mass at a time.  Conservative advancement is a serial chain of up to 30 distance evaluations,
+// and few masses need it (0.4 per robot and tick on BASELINE config 2), so spreading the masses over the lanes leaves a
+// block waiting for the one lane with the longest chain (measured: 2.6 x the run time of the step).  Instead the 32 lanes
+// share each evaluation: a distance between two quads is the minimum over 2 x 4 x 4 vertex-edge pairs -- one pair per
+// lane -- and its SAT test 2 x 4 x 4 projections; minima and the first-minimum rule travel by shuffles.  Everything
+// scalar (the advancement itself) is computed redundantly by all lanes.  The pass runs in DOUBLE in the fp32 build too:
+// its decisions hang on distances of 6e-6 (distanceEpsilon), a dozen ulps of a float coordinate -- in float the
+// advancement does not converge and a population slows down by a quarter.
+template <typename real>
+struct Pose3 {
+  real x, y, th;
+};
+__device__ __forceinline__ void ccd_mass_vertex(int i, double x, double y, double hc, double hs, double& vx, double& vy) {
+  // corners (-h,-h) (+h,-h) (+h,+h) (-h,+h) of the rotated square: x + sx hc - sy hs, y + sx hs + sy hc
+  const double sx = (i == 1 || i == 2) ? 1.0 : -1.0, sy = (i >= 2) ? 1.0 : -1.0;
+  vx = x + sx * hc - sy * hs;
+  vy = y + sx * hs + sy * hc;
+}
+__device__ __forceinline__ void ccd_ground_vertex(int j, double x0, double y0, double x1, double y1, double base_y, double& vx, double& vy) {
+  vx = j < 2 ? x0 : x1;  // (x0, y0) (x0, base) (x1, base) (x1, y1): Ground.java:64-70
+  vy = j == 0 ? y0 : (j == 3 ? y1 : base_y);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// the ground polygon of a segment, as the per-lane constants of the evaluation (lane = pass * 16 + i * 4 + j)
+struct CcdGround {
+  double x0, y0, x1, y1, base_y;
+  double gnx, gny;  // normal of THIS lane's SAT axis when it is one of the polygon's (lanes 16..31: axis (lane >> 2) & 3)
+  double inv_e;     // 1 / squared length of this lane's edge (pass 0: ground edge j; pass 1: the mass' edge)
+};
+// distance of the mass at (x, y, th) from the polygon G; all lanes get the same answer (false: they overlap)
+__device__ __forceinline__ bool ccd_distance(int lane, double x, double y, double th, double half, const CcdGround& G, double& dist,
+                                             double& p1x, double& p1y, double& p2x, double& p2y) {
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  const double hc = half * cs, hs = half * sn;
+  const int pass = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
+  // ---- SAT (the oracle's sat_penetration): axis i of the mass (lanes 0..15) / of the polygon (16..31), vertex j of the other
+  double proj;
+  {
+    double ax, ay, gx, gy;
+    if (pass == 0) {
+      const double nx = i == 0 ? sn : (i == 1 ? cs : (i == 2 ? -sn : -cs)), ny = i == 0 ? -cs : (i == 1 ? sn : (i == 2 ? cs : -sn));
+      ccd_mass_vertex(i, x, y, hc, hs, ax, ay);
+      ccd_ground_vertex(j, G.x0, G.y0, G.x1, G.y1, G.base_y, gx, gy);
+      proj = nx * (gx - ax) + ny * (gy - ay);
+    } else {
+      ccd_ground_vertex(i, G.x0, G.y0, G.x1, G.y1, G.base_y, gx, gy);
+      ccd_mass_vertex(j, x, y, hc, hs, ax, ay);
+      proj = G.gnx * (ax - gx) + G.gny * (ay - gy);
+    }
+  }
+  proj = fmin(proj, shfl_xor_d(proj, 1));
+  proj = fmin(proj, shfl_xor_d(proj, 2));  // every group of 4 lanes: the axis' smallest projection
+  double best = -1e300;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {            // the mass' axes: the first maximum
+    const double sm = shfl_d(proj, a * 4);
+    if (sm > best) best = sm;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {            // the polygon's: only by more than the tie margin
+    const double sm = shfl_d(proj, 16 + a * 4);
+    if (sm > best + 1e-12) best = sm;
+  }
+  if (best < 0.0) return false;            // penetrating (uniform)
+  // ---- closest points (the oracle's poly_distance): pass 0 = vertex i of the mass against edge j of the polygon,
+  //      pass 1 = vertex i of the polygon against edge j of the mass; the first minimum in lane order
+  double px, py, ex0, ey0, ex1, ey1;
+  if (pass == 0) {
+    ccd_mass_vertex(i, x, y, hc, hs, px, py);
+    ccd_ground_vertex(j, G.x0, G.y0, G.x1, G.y1, G.base_y, ex0, ey0);
+    ccd_ground_vertex((j + 1) & 3, G.x0, G.y0, G.x1, G.y1, G.base_y, ex1, ey1);
+  } else {
+    ccd_ground_vertex(i, G.x0, G.y0, G.x1, G.y1, G.base_y, px, py);
+    ccd_mass_vertex(j, x, y, hc, hs, ex0, ey0);
+    ccd_mass_vertex((j + 1) & 3, x, y, hc, hs, ex1, ey1);
+  }
+  const double ex = ex1 - ex0, ey = ey1 - ey0;
+  double t = ((px - ex0) * ex + (py - ey0) * ey) * G.inv_e;
+  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+  const double qx = ex0 + t * ex, qy = ey0 + t * ey;
+  const double dx = px - qx, dy = py - qy;
+  double dd = dx * dx + dy * dy;
+  int who = lane;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const double od = shfl_xor_d(dd, m);
+    const int ow = __shfl_xor_sync(0xffffffffu, who, m);
+    if (od < dd || (od == dd && ow < who)) { dd = od; who = ow; }
+  }
+  // (on the mass: p1; on the polygon: p2)
+  const double m1x = pass == 0 ? px : qx, m1y = pass == 0 ? py : qy, m2x = pass == 0 ? qx : px, m2y = pass == 0 ? qy : py;
+  p1x = shfl_d(m1x, who); p1y = shfl_d(m1y, who); p2x = shfl_d(m2x, who); p2y = shfl_d(m2y, who);
+  dist = sqrt(dd);
+  return true;
+}
+// The pass for ONE mass, executed by a whole (converged) warp; every argument is warp-uniform.
+template <typename real>
+__device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real> p0r, Pose3<real> p1r, real vxr, real vyr, real wr,
+                                                  real dtr, const CBody<real>* cur, int has_contacts, real lin_tol_r,
+                                                  real max_corr_r, real imr, real iir, int hint) {
+  typedef double cr;
+  const int lane = threadIdx.x & 31;
+  const cr eps_e = 2.220446049250313e-16;
+  const cr dist_eps = 6.0554544523933395e-6;               // cbrt(Epsilon.E)
+  const cr half = (cr)P.half, base_y = (cr)P.base_y;
+  const cr rmax = half * 1.4142135623730951;                // Rectangle.getRadius
+  const cr dt = (cr)dtr, lin_tol = (cr)lin_tol_r, max_corr = (cr)max_corr_r, im = (cr)imr, ii = (cr)iir;
+  const Pose3<cr> p0 = {(cr)p0r.x, (cr)p0r.y, (cr)p0r.th}, p1 = {(cr)p1r.x, (cr)p1r.y, (cr)p1r.th};
+  const cr dpx = (cr)vxr * dt, dpy = (cr)vyr * dt, da = (cr)wr * dt;
+  cr minx, maxx, miny;
+  {
+    // swept box: an oriented square spans centre +- half (|cos| + |sin|) at either pose
+    cr s0, c0, s1, c1;
+    sincos(p0.th, &s0, &c0);
+    sincos(p1.th, &s1, &c1);
+    const cr e0 = half * (fabs(c0) + fabs(s0)), e1 = half * (fabs(c1) + fabs(s1));
+    minx = fmin(p0.x - e0, p1.x - e1);
+    maxx = fmax(p0.x + e0, p1.x + e1);
+    miny = fmin(p0.y - e0, p1.y - e1);
+  }
+  const int n = P.terr_n;
+  int s = hint;
+  while (s > 0 && (cr)P.terr_x[s] > minx) --s;
+  cr t2 = 1.0, best_d = 0.0, bp1x = 0.0, bp1y = 0.0, bp2x = 0.0, bp2y = 0.0;
+  bool found = false;
+  const int n_cur = has_contacts ? cur->n : 0;
+#pragma unroll 1
+  for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] <= maxx; ++seg) {
+    const cr x0 = (cr)P.terr_x[seg], x1 = (cr)P.terr_x[seg + 1], y0 = (cr)P.terr_y[seg], y1 = (cr)P.terr_y[seg + 1];
+    if (x1 < minx || !(x1 > x0) || miny > fmax(y0, y1)) continue;
+    bool in_contact = false;  // body1.isInContact(body2)
+#pragma unroll
+    for (int i = 0; i < MAXC; i++)
+      if (i < n_cur && cur->c[i].seg == seg) in_contact = true;
+    if (in_contact) continue;
+    // this lane's constants of the polygon: its SAT axis (edge a -> a + 1: left, bottom, right, top) and its edge
+    CcdGround G;
+    G.x0 = x0; G.y0 = y0; G.x1 = x1; G.y1 = y1; G.base_y = base_y;
+    {
+      const int a = (lane >> 2) & 3, b = (a + 1) & 3;
+      cr ax, ay, bx, by;
+      ccd_ground_vertex(a, x0, y0, x1, y1, base_y, ax, ay);
+      ccd_ground_vertex(b, x0, y0, x1, y1, base_y, bx, by);
+      const cr ex = bx - ax, ey = by - ay, l = sqrt(ex * ex + ey * ey);
+      G.gnx = ey / l;
+      G.gny = -ex / l;
+      const int j = lane & 3, k = (j + 1) & 3;
+      cr cx, cy, dx, dy;
+      ccd_ground_vertex(j, x0, y0, x1, y1, base_y, cx, cy);
+      ccd_ground_vertex(k, x0, y0, x1, y1, base_y, dx, dy);
+      G.inv_e = (lane >> 4) == 0 ? 1.0 / ((dx - cx) * (dx - cx) + (dy - cy) * (dy - cy)) : 1.0 / (4.0 * half * half);
+    }
+    // ConservativeAdvancement.getTimeOfImpact on [0, t2], as ONE loop around ONE evaluation of the distance:
+    // stage 0 = at t = 0, 1 = after an advance, 2 = after backing up from an overshoot
+    const cr amax = rmax * fabs(da);
+    cr l = 0.0, l0 = 0.0, adv = 0.0, dist = 0.0, q1x = 0.0, q1y = 0.0, q2x = 0.0, q2y = 0.0;
+    bool ok = true, skip = false;
+    int iter = 0, stage = 0;
+#pragma unroll 1
+    for (;;) {
+      const bool sep = ccd_distance(lane, p0.x + dpx * l, p0.y + dpy * l, p0.th + da * l, half, G, dist, q1x, q1y, q2x, q2y);
+      if (stage == 0) {
+        if (!sep) { skip = true; break; }  // not separated at t = 0
+        if (!(dist >= dist_eps)) break;     // already within distanceEpsilon: time of impact 0
+        if (sqrt(dpx * dpx + dpy * dpy) + amax == 0.0) { skip = true; break; }
+      } else if (stage == 1) {
+        if (!sep) {  // overshoot: back up and take the distance there
+          l -= adv;
+          stage = 2;
+          continue;
+        }
+      } else {
+        break;
+      }
+      if (!(dist > dist_eps && iter < 30)) break;
+      const cr nx = (q2x - q1x) / dist, ny = (q2y - q1y) / dist;
+      const cr drel = dpx * nx + dpy * ny + amax;
+      if (drel <= eps_e) { ok = false; break; }
+      adv = dist / drel;
+      l += adv;
+      if (l < 0.0 || l > t2) { ok = false; break; }
+      if (l <= l0) break;
+      l0 = l;
+      iter++;
+      stage = 1;
+    }
+    if (skip || !ok) continue;
+    if (l < t2) { t2 = l; found = true; best_d = dist; bp1x = q1x; bp1y = q1y; bp2x = q2x; bp2y = q2y; }
+  }
+  if (!found) return p1r;
+  Pose3<cr> r;
+  r.x = p0.x + (p1.x - p0.x) * t2;
+  r.y = p0.y + (p1.y - p0.y) * t2;
+  r.th = p0.th + (p1.th - p0.th) * t2;
+  {
+    cr nx = bp2x - bp1x, ny = bp2y - bp1y;
+    const cr nl = sqrt(nx * nx + ny * ny);
+    if (nl > 0.0) { nx /= nl; ny /= nl; }
+    cr C = best_d - lin_tol;
+    C = C < -max_corr ? -max_corr : (C > 0.0 ? 0.0 : C);
+    const cr r1x = bp1x - r.x, r1y = bp1y - r.y;
+    const cr rn1 = r1x * ny - r1y * nx;
+    const cr K = im + ii * rn1 * rn1;
+    const cr imp = K > eps_e ? -C / K : 0.0;
+    const cr Jx = nx * imp, Jy = ny * imp;
+    r.x += Jx * im;
+    r.y += Jy * im;
+    r.th += ii * (r1x * Jy - r1y * Jx);
+  }
+  Pose3<real> out = {(real)r.x, (real)r.y, (real)r.th};
+  return out;
 }
 
 // the scalars the contact routines need, passed by value (registers): taking the kernel's
@@ -1143,9 +1367,12 @@ static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list cap
 #endif
 // MODE 1 (FAST) = the default voxel (all four scaffoldings, reduced-mass springs, no limits): no per-spring
 // branch, constant gamma.  MODE 0 = generic (partial scaffoldings, effective-mass springs).  MODE 2 (LIM) = generic
-// + the DistanceJoint limits of a finite areaRatioPassiveRange (Voxel.java:331-338): two more accumulated impulses
-// per spring, a one-sided rigid row per limit after each spring row and a position correction of the violated
-// limit (256 / 128 thread columns per block: the per-tick constants take 36 bytes more per spring).
+// + everything that is off in the reference's default configuration, so that none of it weighs on the default kernel:
+// the DistanceJoint limits of a finite areaRatioPassiveRange (Voxel.java:331-338: two more accumulated impulses per
+// spring, a one-sided rigid row per limit after each spring row, a position correction of the violated limit; 256 /
+// 128 thread columns per block: the per-tick constants take 36 bytes more per spring), BreakableVoxels, and the
+// continuous-detection pass (vsr_settings.continuous_detection).  MODE 3 = MODE 1 + the continuous-detection pass (the
+// reference's default voxel under dyn4j's default ContinuousDetectionMode).
 // BLK = big robots (33..128 voxels): a robot takes P.wpr whole warps, a block holds P.rpb of them; the robots of a
 // block meet at the block-wide phase barriers only (instruction-fetch locality), everything inside a phase is
 // synchronised per robot with a named barrier; neighbour exchange through shared memory and
@@ -1154,7 +1381,7 @@ template <typename real, int CTRL, int MODE, bool BLK>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
   const ShapeDev& S = *P.shape;
-  constexpr bool FAST = MODE == 1, LIM = MODE == 2;
+  constexpr bool FAST = MODE == 1 || MODE == 3, LIM = MODE == 2, CCD = MODE >= 2;
   constexpr bool FULLSPR = FAST;
   const bool EFFMASS = FAST ? false : (P.spring_mode != 0);
   const int lane = threadIdx.x & 31;
@@ -1346,6 +1573,19 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       __syncthreads();
       if (tick >= 0) {
       // =========================== World.step(1) ===========================
+      // (continuous detection: Body.transform0 = the poses before the islands are solved)
+      if (CCD && P.ccd) {  // (compiled into the MODE 2 / 3 instantiations only: the default kernel stays as it is)
+        // (the scratch column of this thread: recomputed where it is used -- kept across the velocity loop its four
+        // registers pushed 17 values of that loop into local memory)
+        const size_t ccd_t = (size_t)gridDim.x * blockDim.x, ccd_i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          P.ccd_buf[(k * 3 + 0) * ccd_t + ccd_i] = x[k];
+          P.ccd_buf[(k * 3 + 1) * ccd_t + ccd_i] = y[k];
+          P.ccd_buf[(k * 3 + 2) * ccd_t + ccd_i] = th[k];
+          P.ccd_buf[(36 + k) * ccd_t + ccd_i] = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));  // half extent of its box
+        }
+      }
       // ---- integrate velocities (Island.solve / integrateVelocity, dyn4j)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -1775,6 +2015,121 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 
       r_sincos(th[0], &sn_[0], &cs_[0]);
       r_sincos(th[3], &sn_[3], &cs_[3]);
+      // ---- World.solveTOI (vsr_settings.continuous_detection): every mass against the ground
+      //      polygons it is about to touch.  A mass whose swept box stays above the terrain's height map is skipped, and
+      //      so is a mass in contact whose swept box lies over ONE ground polygon (it is in contact with that one: a
+      //      resting foot on a long segment).  The few that remain are taken one after the other by the WHOLE warp
+      //      (ccd_mass_warp); their poses and velocities travel through the global scratch ccd_buf (rows 0-11 pose at
+      //      the start of the step, 12-23 pose now / the result, 24-35 velocity, 36-39 box half extent at the start).
+      if (CCD && P.ccd) {
+        const size_t ccd_t = (size_t)gridDim.x * blockDim.x, ccd_i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned ccand = 0;
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const real p0x = P.ccd_buf[(k * 3 + 0) * ccd_t + ccd_i], p0y = P.ccd_buf[(k * 3 + 1) * ccd_t + ccd_i];
+            const real rr_ = P.half * real(1.4142135623730951) + real(0.01);
+            int c0 = (int)floorf((float)((r_min(p0x, x[k]) - rr_ - P.hgrid_x0) * P.hgrid_inv));
+            int c1 = (int)floorf((float)((r_max(p0x, x[k]) + rr_ - P.hgrid_x0) * P.hgrid_inv));
+            c0 = max(0, min(c0, P.hgrid_n - 1));
+            c1 = max(0, min(c1, P.hgrid_n - 1));
+            real top = P.hgrid[c0];
+            for (int c = c0 + 1; c <= c1; c++) top = r_max(top, P.hgrid[c]);
+            if (r_min(p0y, y[k]) - rr_ > top) continue;
+            // the swept box proper (the pass itself skips a polygon whose top lies below it; 1e-4: float rounding)
+            const real e0_ = P.ccd_buf[(36 + k) * ccd_t + ccd_i], e1_ = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
+            if (r_min(p0y - e0_, y[k] - e1_) - real(1e-4) > top) continue;
+            if ((cmask >> k) & 1u) {
+              const real xlo_ = r_min(p0x, x[k]) - rr_, xhi_ = r_max(p0x, x[k]) + rr_;
+              int s_ = hint[k];
+              while (s_ > 0 && P.terr_x[s_] > xlo_) --s_;
+              while (s_ + 2 < P.terr_n && P.terr_x[s_ + 1] < xlo_) ++s_;
+              if (P.terr_x[s_] <= xlo_ && P.terr_x[s_ + 1] >= xhi_) continue;
+            }
+            ccand |= 1u << k;
+            P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i] = x[k];
+            P.ccd_buf[(12 + k * 3 + 1) * ccd_t + ccd_i] = y[k];
+            P.ccd_buf[(12 + k * 3 + 2) * ccd_t + ccd_i] = th[k];
+            P.ccd_buf[(24 + k * 3 + 0) * ccd_t + ccd_i] = vx[k];
+            P.ccd_buf[(24 + k * 3 + 1) * ccd_t + ccd_i] = vy[k];
+            P.ccd_buf[(24 + k * 3 + 2) * ccd_t + ccd_i] = w[k];
+          }
+        }
+        if (__any_sync(0xffffffffu, ccand != 0u)) {
+          __threadfence_block();
+          __syncwarp();
+          unsigned moved = 0;
+          const int fl_own = (int)((flip & 15u) | (cmask << 4));
+          const unsigned todo0 = __ballot_sync(0xffffffffu, ccand & 1u), todo1 = __ballot_sync(0xffffffffu, (ccand >> 1) & 1u),
+                         todo2 = __ballot_sync(0xffffffffu, (ccand >> 2) & 1u), todo3 = __ballot_sync(0xffffffffu, (ccand >> 3) & 1u);
+          // The pass is a call into double-precision code: every register its call tree may touch is one the kernel
+          // cannot keep a long-lived value in, and ptxas answers by keeping values of the VELOCITY LOOP in local memory
+          // for the whole tick.  So there is ONE call site, and the live ranges are split by hand around it: the
+          // long-lived state is parked in the spring tables (dead until the next step's initialisation, [field][thread]:
+          // conflict-free).
+          real* const park = reinterpret_cast<real*>(spr);
+#pragma unroll
+          for (int q = 0; q < 18; q++) park[q * SPR_STRIDE + tid] = simp[q];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            park[(18 + q) * SPR_STRIDE + tid] = vx[q]; park[(22 + q) * SPR_STRIDE + tid] = vy[q]; park[(26 + q) * SPR_STRIDE + tid] = w[q];
+            park[(30 + q) * SPR_STRIDE + tid] = cs_[q]; park[(34 + q) * SPR_STRIDE + tid] = sn_[q];
+            park[(62 + q) * SPR_STRIDE + tid] = x[q]; park[(66 + q) * SPR_STRIDE + tid] = y[q];  // (72 rows in all)
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+              park[(38 + q * 2 + z) * SPR_STRIDE + tid] = wix[q][z]; park[(46 + q * 2 + z) * SPR_STRIDE + tid] = wiy[q][z];
+              park[(54 + q * 2 + z) * SPR_STRIDE + tid] = wiz[q][z];
+            }
+          }
+#pragma unroll 1
+          for (int k = 0; k < 4; k++) {
+            unsigned todo = k == 0 ? todo0 : (k == 1 ? todo1 : (k == 2 ? todo2 : todo3));
+            const int hint_k = (k & 2) ? ((k & 1) ? hint[3] : hint[2]) : ((k & 1) ? hint[1] : hint[0]);
+            while (todo) {  // (warp-uniform)
+              const int ol = __ffs((int)todo) - 1;
+              todo &= todo - 1u;
+              const size_t oi = ccd_i - lane + ol;  // the owner's column of the scratch
+              const int fl = __shfl_sync(0xffffffffu, fl_own, ol), hk = __shfl_sync(0xffffffffu, hint_k, ol);
+              Pose3<real> p0, p1;
+              p0.x = P.ccd_buf[(k * 3 + 0) * ccd_t + oi]; p0.y = P.ccd_buf[(k * 3 + 1) * ccd_t + oi]; p0.th = P.ccd_buf[(k * 3 + 2) * ccd_t + oi];
+              p1.x = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi]; p1.y = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi]; p1.th = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi];
+              const real ovx = P.ccd_buf[(24 + k * 3 + 0) * ccd_t + oi], ovy = P.ccd_buf[(24 + k * 3 + 1) * ccd_t + oi],
+                         ow_ = P.ccd_buf[(24 + k * 3 + 2) * ccd_t + oi];
+              const int tl = (wib << 5) + ol;
+              const CBody<real>* const ob = blk_cb + (size_t)tl * 8 + 2 * k + ((fl >> k) & 1);
+              const Pose3<real> r_ = ccd_mass_warp(tpar, p0, p1, ovx, ovy, ow_, dt, ob, (fl >> (4 + k)) & 1, P.lin_tol, P.max_corr, im,
+                                                   ii, hk);
+              if (lane == ol && (r_.x != p1.x || r_.y != p1.y || r_.th != p1.th)) {
+                P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi] = r_.x;
+                P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi] = r_.y;
+                P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi] = r_.th;
+                moved |= 1u << k;
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 18; q++) simp[q] = park[q * SPR_STRIDE + tid];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            vx[q] = park[(18 + q) * SPR_STRIDE + tid]; vy[q] = park[(22 + q) * SPR_STRIDE + tid]; w[q] = park[(26 + q) * SPR_STRIDE + tid];
+            cs_[q] = park[(30 + q) * SPR_STRIDE + tid]; sn_[q] = park[(34 + q) * SPR_STRIDE + tid];
+            x[q] = park[(62 + q) * SPR_STRIDE + tid]; y[q] = park[(66 + q) * SPR_STRIDE + tid];
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+              wix[q][z] = park[(38 + q * 2 + z) * SPR_STRIDE + tid]; wiy[q][z] = park[(46 + q * 2 + z) * SPR_STRIDE + tid];
+              wiz[q][z] = park[(54 + q * 2 + z) * SPR_STRIDE + tid];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (moved & (1u << k)) {  // (the thread's own writes)
+              x[k] = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i];
+              y[k] = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + ccd_i];
+              th[k] = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + ccd_i];
+              r_sincos(th[k], &sn_[k], &cs_[k]);
+            }
+        }
+      }
       }  // tick >= 0
       if (sync_mode & 64) __syncthreads();
       // ---- World.detect: new manifolds for Touch and for the next step

@@ -61,6 +61,12 @@ typedef struct vsr_settings {
   int32_t spring_mass_mode;     /* VSR_SPRING_MASS_* : which mass turns (f, zeta) into (k, d) */
   int32_t self_collision;       /* 1 (default): masses of one robot collide with each other unless welded
                                    (Voxel.java:178-185,474; Robot.java:66-71); 0: ground contacts only */
+  int32_t continuous_detection; /* dyn4j's ContinuousDetectionMode for the masses against the ground: 1 = the
+                                   time-of-impact pass after the position solve (a mass about to touch a ground polygon
+                                   it is not yet in contact with is put back to its time of impact and pushed
+                                   linearTolerance into it); 0 (default here; dyn4j's default is ALL): none.  What the
+                                   pass does to a population is measured in tests/test_oracle_cpu.py.               */
+  int32_t reserved;
 } vsr_settings;
 
 #define VSR_SPRING_MASS_REDUCED 0   /* m1*m2/(m1+m2)  (Box2D-2.4 lineage)            */

@@ -40,7 +40,9 @@ public final class VsrLayouts {
       JAVA_DOUBLE.withName("ground_friction"),
       JAVA_DOUBLE.withName("ground_restitution"),
       JAVA_INT.withName("spring_mass_mode"),
-      JAVA_INT.withName("self_collision")
+      JAVA_INT.withName("self_collision"),
+      JAVA_INT.withName("continuous_detection"),
+      JAVA_INT.withName("reserved")
   ).withName("vsr_settings");
 
   /* the 13 Voxel constructor fields, Voxel.java:103-118 (vsr_material) */

@@ -1501,10 +1501,12 @@ static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p
       for (int j = 0; j < Q->n; j++) {
         int k = (j + 1) % Q->n;
         double ex = Q->vx[k] - Q->vx[j], ey = Q->vy[k] - Q->vy[j];
-        double t = ((P->vx[i] - Q->vx[j]) * ex + (P->vy[i] - Q->vy[j]) * ey) / (ex * ex + ey * ey);
+        /* (the parameter by a multiplication with 1 / |edge|^2 and the comparison on squared distances, one square
+           root at the end: the arithmetic of the kernel's quad_distance) */
+        double t = ((P->vx[i] - Q->vx[j]) * ex + (P->vy[i] - Q->vy[j]) * ey) * (1.0 / (ex * ex + ey * ey));
         t = t < 0 ? 0 : (t > 1 ? 1 : t);
         double qx = Q->vx[j] + t * ex, qy = Q->vy[j] + t * ey;
-        double dx = P->vx[i] - qx, dy = P->vy[i] - qy, dd = sqrt(dx * dx + dy * dy);
+        double dx = P->vx[i] - qx, dy = P->vy[i] - qy, dd = dx * dx + dy * dy;
         if (dd < best) {
           best = dd;
           if (pass) { *p1x = qx; *p1y = qy; *p2x = P->vx[i]; *p2y = P->vy[i]; }
@@ -1512,7 +1514,7 @@ static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p
         }
       }
   }
-  *dist = best;
+  *dist = sqrt(best);
   return 1;
 }
 
@@ -1663,7 +1665,7 @@ static int world_step(ORun* R, ORobot* r, double dt) {
   const int dfs = R->o.order == VSR_ORACLE_ORDER_DFS;
   if (dfs) island_order(r);
   OPose* pose0 = NULL;
-  if (R->o.ccd) { /* body.transform0 = body.transform, before the islands are solved */
+  if (R->o.ccd || d->settings.continuous_detection) { /* body.transform0 = body.transform, before the islands are solved */
     pose0 = (OPose*)malloc(sizeof(OPose) * (size_t)r->nb);
     for (int b = 0; b < r->nb; b++) { pose0[b].x = r->bodies[b].x; pose0[b].y = r->bodies[b].y; pose0[b].th = r->bodies[b].th; }
   }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     # sizes implied by the header (x86-64 SysV): guards against a silent ctypes drift
-    assert C.sizeof(A.vsr_settings) == 8 + 4 + 4 + 11 * 8 + 8
+    assert C.sizeof(A.vsr_settings) == 8 + 4 + 4 + 11 * 8 + 8 + 8
     assert C.sizeof(A.vsr_material) == 13 * 8 + 8
     assert C.sizeof(A.vsr_sensor) == 6 * 4 + 4 * 8 + 8 * 8
     assert C.sizeof(A.vsr_result) == 88 and H.RESULT_DTYPE.itemsize == 88

@@ -169,6 +169,15 @@ def test_dyn4j_contact_labels_switch():
     assert _frames_residual(dyn4j_labels=True) > 2.0 and _frames_residual(dyn4j_labels=True, order=oracle.ORDER_DFS, ccd=True) > 2.0
 
 
+def test_continuous_detection_setting_is_the_ccd_switch():
+    # vsr_settings.continuous_detection (what the kernel reads) and vsr_oracle_opts.ccd are the same pass
+    robots = helpers.phase_robots(3, seed=2)
+    a, _ = oracle.run(helpers.locomotion(2.0).compile(robots), ccd=True)
+    b2, _ = oracle.run(helpers.locomotion(2.0, continuous_detection=1).compile(robots))
+    c, _ = oracle.run(helpers.locomotion(2.0).compile(robots))
+    assert a.tobytes() == b2.tobytes() and a.tobytes() != c.tobytes()
+
+
 def test_island_dfs_order_and_ccd_switches():
     # dyn4j's own constraint order (island discovery, depth first) and its time-of-impact pass sit
     # behind single switches of the oracle; both are deterministic, both change a trajectory only after the first
