@@ -1017,7 +1017,7 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   }
   if (blk) P.smem_per_warp = std::max(128, (per_robot + wpr - 1) / wpr);  // a robot's staging = wpr * this
   else P.smem_per_warp = std::max(128, per_robot * G);
-  const size_t limit = 227 * 1024;
+  const size_t limit = 227 * 1024 - 16;  // (16: the kernel's one static word, the candidate count of continuous detection)
   // [18][stride] spring vectors (6 reals, + gamma in effective-mass mode) + per-warp staging and
   // contact exchange (+ the neighbour exchange of the big-robot variant)
   auto fixed_smem = [&](int wpb_, int rpb_) {
@@ -1050,16 +1050,24 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
 #define VSR_PICK(C)                                                                                  \
   kern = blk ? (mode == 1 ? vsr_episode_kernel<real, C, 1, true> : (mode == 3 ? vsr_episode_kernel<real, C, 3, true> : (mode == 2 ? vsr_episode_kernel<real, C, 2, true> : vsr_episode_kernel<real, C, 0, true>))) \
              : (mode == 1 ? vsr_episode_kernel<real, C, 1, false> : (mode == 3 ? vsr_episode_kernel<real, C, 3, false> : (mode == 2 ? vsr_episode_kernel<real, C, 2, false> : vsr_episode_kernel<real, C, 0, false>)))
+#ifdef VSR_DEV_SUBSET  // development builds only (scripts/dev_build.sh): the two instantiations of BASELINE config 2
+  if constexpr (std::is_same<real, float>::value) {
+    if (!blk && d.controller_kind == VSR_CTRL_PHASE_SIN)
+      kern = mode == 1 ? vsr_episode_kernel<float, CTRL_PHASE_SIN, 1, false> : (mode == 3 ? vsr_episode_kernel<float, CTRL_PHASE_SIN, 3, false> : nullptr);
+  }
+  if (!kern) return fail(VSR_ERR_CUDA, "this development build holds the config-2 kernels only");
+#else
   switch (d.controller_kind) {
     case VSR_CTRL_PHASE_SIN: VSR_PICK(CTRL_PHASE_SIN); break;
     case VSR_CTRL_TABULATED: VSR_PICK(CTRL_TABULATED); break;
     default: VSR_PICK(CTRL_MLP); break;
   }
+#endif
 #undef VSR_PICK
   P.ctrl = d.controller_kind;
   // the attribute belongs to the kernel, not to the launch: buckets that share an instantiation ask for different
   // sizes, so it is raised to the SM's limit once and for all (the carve-out follows each launch's actual size)
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 16));  // (see `limit`)
   int occ = 0, sms = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
@@ -1294,3 +1302,11 @@ extern "C" int vsr_batch_n_bodies(const vsr_batch* b, size_t robot) {
 }
 extern "C" int vsr_batch_last_launches(const vsr_batch* b) { return b ? b->last_launches : 0; }
 extern "C" size_t vsr_batch_upload_bytes(const vsr_batch* b) { return b ? b->upload_bytes : 0; }
+
+#ifdef VSR_CCD_COUNT  // development builds only
+extern "C" void vsr_dev_counters(unsigned long long* out) {
+  cudaMemcpyFromSymbol(&out[0], g_ccd_count, 8);
+  cudaMemcpyFromSymbol(&out[1], g_ccd_count2, 8);
+  cudaMemcpyFromSymbol(&out[2], g_ccd_count3, 8);
+}
+#endif

@@ -616,6 +616,9 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
 // scalar (the advancement itself) is computed redundantly by all lanes.  The pass runs in DOUBLE in the fp32 build too:
 // its decisions hang on distances of 6e-6 (distanceEpsilon), a dozen ulps of a float coordinate -- in float the
 // advancement does not converge and a population slows down by a quarter.
+#ifdef VSR_CCD_COUNT
+__device__ unsigned long long g_ccd_count, g_ccd_count2, g_ccd_count3;
+#endif
 template <typename real>
 struct Pose3 {
   real x, y, th;
@@ -740,6 +743,14 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
   for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] <= maxx; ++seg) {
     const cr x0 = (cr)P.terr_x[seg], x1 = (cr)P.terr_x[seg + 1], y0 = (cr)P.terr_y[seg], y1 = (cr)P.terr_y[seg + 1];
     if (x1 < minx || !(x1 > x0) || miny > fmax(y0, y1)) continue;
+    {
+      // The polygon lies under the line of its top edge, the mass inside its circle: when the gap between the two is
+      // wider than anything the mass can travel in the step, the first advance dist / (dp.n + amax) of the conservative
+      // advancement below is > 1 >= t2 and the polygon yields no time of impact -- without evaluating a distance.
+      const cr ex = x1 - x0, ey = y1 - y0;
+      const cr gap = ((p0.y - y0) * ex - (p0.x - x0) * ey) / sqrt(ex * ex + ey * ey) - rmax;
+      if (gap > (sqrt(dpx * dpx + dpy * dpy) + rmax * fabs(da)) * 1.000001 + 1e-9) continue;
+    }
     bool in_contact = false;  // body1.isInContact(body2)
 #pragma unroll
     for (int i = 0; i < MAXC; i++)
@@ -771,6 +782,9 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
 #pragma unroll 1
     for (;;) {
       const bool sep = ccd_distance(lane, p0.x + dpx * l, p0.y + dpy * l, p0.th + da * l, half, G, dist, q1x, q1y, q2x, q2y);
+#ifdef VSR_CCD_COUNT
+      if (lane == 0) atomicAdd(&g_ccd_count3, 1ull);
+#endif
       if (stage == 0) {
         if (!sep) { skip = true; break; }  // not separated at t = 0
         if (!(dist >= dist_eps)) break;     // already within distanceEpsilon: time of impact 0
@@ -1380,6 +1394,7 @@ static_assert(4 * MAXC + VSR_MAX_CAND <= VSR_ITEMS_PER_THREAD, "contact list cap
 template <typename real, int CTRL, int MODE, bool BLK>
 __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_kernel(const Params<real> P) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ int ccd_n;  // continuous detection: length of the block's candidate list (MODE 2 / 3 only)
   const ShapeDev& S = *P.shape;
   constexpr bool FAST = MODE == 1 || MODE == 3, LIM = MODE == 2, CCD = MODE >= 2;
   constexpr bool FULLSPR = FAST;
@@ -1571,6 +1586,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       // for their MLP activations and first/last-tick sums; this barrier and the one before Robot.act
       // separate those phases block-wide.
       __syncthreads();
+      if (CCD && tick < 0 && threadIdx.x == 0) ccd_n = 0;  // (its first use is a barrier away)
       if (tick >= 0) {
       // =========================== World.step(1) ===========================
       // (continuous detection: Body.transform0 = the poses before the islands are solved)
@@ -2024,6 +2040,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
       if (CCD && P.ccd) {
         const size_t ccd_t = (size_t)gridDim.x * blockDim.x, ccd_i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         unsigned ccand = 0;
+        int cseg[4] = {0, 0, 0, 0};
         if (active) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -2036,17 +2053,31 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             real top = P.hgrid[c0];
             for (int c = c0 + 1; c <= c1; c++) top = r_max(top, P.hgrid[c]);
             if (r_min(p0y, y[k]) - rr_ > top) continue;
-            // the swept box proper (the pass itself skips a polygon whose top lies below it; 1e-4: float rounding)
+            // the swept box proper against the polygons under it, as the pass itself does (it skips a polygon whose top
+            // lies below the box; 1e-4 and the 0.01 in rr_: float rounding).  The height map alone is not enough: the
+            // robots start one unit away from the border slope, whose cell is 100 high.
             const real e0_ = P.ccd_buf[(36 + k) * ccd_t + ccd_i], e1_ = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
-            if (r_min(p0y - e0_, y[k] - e1_) - real(1e-4) > top) continue;
-            if ((cmask >> k) & 1u) {
-              const real xlo_ = r_min(p0x, x[k]) - rr_, xhi_ = r_max(p0x, x[k]) + rr_;
-              int s_ = hint[k];
-              while (s_ > 0 && P.terr_x[s_] > xlo_) --s_;
-              while (s_ + 2 < P.terr_n && P.terr_x[s_ + 1] < xlo_) ++s_;
-              if (P.terr_x[s_] <= xlo_ && P.terr_x[s_ + 1] >= xhi_) continue;
+            const real ylo_ = r_min(p0y - e0_, y[k] - e1_) - real(1e-4);
+            if (ylo_ > top) continue;
+            const real xlo_ = r_min(p0x, x[k]) - rr_, xhi_ = r_max(p0x, x[k]) + rr_;
+            int s_ = hint[k];
+            while (s_ > 0 && P.terr_x[s_] > xlo_) --s_;
+            while (s_ + 2 < P.terr_n && P.terr_x[s_ + 1] < xlo_) ++s_;
+            bool hit_ = false;
+            int nseg_ = 0;
+            // (and a polygon further away than the mass can travel yields no time of impact: see ccd_mass_warp)
+            const real trav_ = (r_sqrt(vx[k] * vx[k] + vy[k] * vy[k]) + rr_ * r_abs(w[k])) * dt + real(1e-3);
+            for (int seg = s_; seg + 1 < P.terr_n && P.terr_x[seg] <= xhi_; ++seg) {
+              nseg_++;
+              const real sx0_ = P.terr_x[seg], sy0_ = P.terr_y[seg], sy1_ = P.terr_y[seg + 1], ex_ = P.terr_x[seg + 1] - sx0_, ey_ = sy1_ - sy0_;
+              const real gap_ = ((p0y - sy0_) * ex_ - (p0x - sx0_) * ey_) / r_sqrt(ex_ * ex_ + ey_ * ey_) - rr_;
+              if (!(ylo_ > r_max(sy0_, sy1_)) && !(gap_ > trav_)) hit_ = true;
             }
+            if (!hit_) continue;
+            // a mass in contact whose swept box lies over ONE polygon is in contact with that one
+            if (((cmask >> k) & 1u) && nseg_ == 1 && P.terr_x[s_] <= xlo_) continue;
             ccand |= 1u << k;
+            cseg[k] = s_;  // (the first polygon under the swept box: where the pass starts its walk)
             P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i] = x[k];
             P.ccd_buf[(12 + k * 3 + 1) * ccd_t + ccd_i] = y[k];
             P.ccd_buf[(12 + k * 3 + 2) * ccd_t + ccd_i] = th[k];
@@ -2055,56 +2086,63 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             P.ccd_buf[(24 + k * 3 + 2) * ccd_t + ccd_i] = w[k];
           }
         }
-        if (__any_sync(0xffffffffu, ccand != 0u)) {
-          __threadfence_block();
-          __syncwarp();
-          unsigned moved = 0;
-          const int fl_own = (int)((flip & 15u) | (cmask << 4));
-          const unsigned todo0 = __ballot_sync(0xffffffffu, ccand & 1u), todo1 = __ballot_sync(0xffffffffu, (ccand >> 1) & 1u),
-                         todo2 = __ballot_sync(0xffffffffu, (ccand >> 2) & 1u), todo3 = __ballot_sync(0xffffffffu, (ccand >> 3) & 1u);
+#ifdef VSR_CCD_COUNT
+        if (ccand) atomicAdd(&g_ccd_count, (unsigned long long)__popc(ccand));
+        { const int a_ = __syncthreads_or(ccand != 0u); if (threadIdx.x == 0 && a_) atomicAdd(&g_ccd_count2, 1ull); }
+#endif
+        // Block-wide pool: the candidates of all the block's robots go into one list and the warps take them in
+        // turn.  (Per warp, the block waited at the next barrier for the warp whose robot stands on the border slope:
+        // 8 candidates there every tick, none elsewhere.)  The list lives in rows 62-71 of the spring tables, which
+        // are dead for every warp once the block has passed the first barrier below.
+        const bool ccd_any = __syncthreads_or(ccand != 0u) != 0;  // (every warp is past its position loop)
+        if (ccd_any) {
+          real* const park = reinterpret_cast<real*>(spr);
+          int* const clist = reinterpret_cast<int*>(park + 62 * SPR_STRIDE);
+          const int ccap = 10 * SPR_STRIDE;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((ccand >> k) & 1u) {
+              const int pos_ = atomicAdd(&ccd_n, 1);
+              if (pos_ < ccap)
+                clist[pos_] = (int)threadIdx.x | (k << 10) | (int)(((flip >> k) & 1u) << 12) | (int)(((cmask >> k) & 1u) << 13) | (cseg[k] << 14);
+              else
+                status |= VSR_STATUS_CONTACT_OVERFLOW;  // (cannot happen: 4 candidates per thread, 10 rows)
+            }
           // The pass is a call into double-precision code: every register its call tree may touch is one the kernel
           // cannot keep a long-lived value in, and ptxas answers by keeping values of the VELOCITY LOOP in local memory
           // for the whole tick.  So there is ONE call site, and the live ranges are split by hand around it: the
-          // long-lived state is parked in the spring tables (dead until the next step's initialisation, [field][thread]:
-          // conflict-free).
-          real* const park = reinterpret_cast<real*>(spr);
+          // long-lived state is parked in rows 0-61 of the spring tables ([field][thread]: conflict-free).
 #pragma unroll
           for (int q = 0; q < 18; q++) park[q * SPR_STRIDE + tid] = simp[q];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             park[(18 + q) * SPR_STRIDE + tid] = vx[q]; park[(22 + q) * SPR_STRIDE + tid] = vy[q]; park[(26 + q) * SPR_STRIDE + tid] = w[q];
             park[(30 + q) * SPR_STRIDE + tid] = cs_[q]; park[(34 + q) * SPR_STRIDE + tid] = sn_[q];
-            park[(62 + q) * SPR_STRIDE + tid] = x[q]; park[(66 + q) * SPR_STRIDE + tid] = y[q];  // (72 rows in all)
 #pragma unroll
             for (int z = 0; z < 2; z++) {
               park[(38 + q * 2 + z) * SPR_STRIDE + tid] = wix[q][z]; park[(46 + q * 2 + z) * SPR_STRIDE + tid] = wiy[q][z];
               park[(54 + q * 2 + z) * SPR_STRIDE + tid] = wiz[q][z];
             }
           }
+          __syncthreads();  // the list and the scratch columns are complete
+          const int cn_ = min(ccd_n, ccap);
 #pragma unroll 1
-          for (int k = 0; k < 4; k++) {
-            unsigned todo = k == 0 ? todo0 : (k == 1 ? todo1 : (k == 2 ? todo2 : todo3));
-            const int hint_k = (k & 2) ? ((k & 1) ? hint[3] : hint[2]) : ((k & 1) ? hint[1] : hint[0]);
-            while (todo) {  // (warp-uniform)
-              const int ol = __ffs((int)todo) - 1;
-              todo &= todo - 1u;
-              const size_t oi = ccd_i - lane + ol;  // the owner's column of the scratch
-              const int fl = __shfl_sync(0xffffffffu, fl_own, ol), hk = __shfl_sync(0xffffffffu, hint_k, ol);
-              Pose3<real> p0, p1;
-              p0.x = P.ccd_buf[(k * 3 + 0) * ccd_t + oi]; p0.y = P.ccd_buf[(k * 3 + 1) * ccd_t + oi]; p0.th = P.ccd_buf[(k * 3 + 2) * ccd_t + oi];
-              p1.x = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi]; p1.y = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi]; p1.th = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi];
-              const real ovx = P.ccd_buf[(24 + k * 3 + 0) * ccd_t + oi], ovy = P.ccd_buf[(24 + k * 3 + 1) * ccd_t + oi],
-                         ow_ = P.ccd_buf[(24 + k * 3 + 2) * ccd_t + oi];
-              const int tl = (wib << 5) + ol;
-              const CBody<real>* const ob = blk_cb + (size_t)tl * 8 + 2 * k + ((fl >> k) & 1);
-              const Pose3<real> r_ = ccd_mass_warp(tpar, p0, p1, ovx, ovy, ow_, dt, ob, (fl >> (4 + k)) & 1, P.lin_tol, P.max_corr, im,
-                                                   ii, hk);
-              if (lane == ol && (r_.x != p1.x || r_.y != p1.y || r_.th != p1.th)) {
-                P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi] = r_.x;
-                P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi] = r_.y;
-                P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi] = r_.th;
-                moved |= 1u << k;
-              }
+          for (int ci = (int)(threadIdx.x >> 5); ci < cn_; ci += (int)(blockDim.x >> 5)) {  // (warp-uniform)
+            const int e_ = clist[ci];
+            const int ot = e_ & 1023, k = (e_ >> 10) & 3;
+            const size_t oi = (size_t)blockIdx.x * blockDim.x + ot;  // the owner's column of the scratch
+            Pose3<real> p0, p1;
+            p0.x = P.ccd_buf[(k * 3 + 0) * ccd_t + oi]; p0.y = P.ccd_buf[(k * 3 + 1) * ccd_t + oi]; p0.th = P.ccd_buf[(k * 3 + 2) * ccd_t + oi];
+            p1.x = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi]; p1.y = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi]; p1.th = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi];
+            const real ovx = P.ccd_buf[(24 + k * 3 + 0) * ccd_t + oi], ovy = P.ccd_buf[(24 + k * 3 + 1) * ccd_t + oi],
+                       ow_ = P.ccd_buf[(24 + k * 3 + 2) * ccd_t + oi];
+            const CBody<real>* const ob = blk_cb + (size_t)ot * 8 + 2 * k + ((e_ >> 12) & 1);
+            const Pose3<real> r_ = ccd_mass_warp(tpar, p0, p1, ovx, ovy, ow_, dt, ob, (e_ >> 13) & 1, P.lin_tol, P.max_corr, im, ii,
+                                                 (int)((unsigned)e_ >> 14));
+            if (lane == 0 && (r_.x != p1.x || r_.y != p1.y || r_.th != p1.th)) {
+              P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi] = r_.x;
+              P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi] = r_.y;
+              P.ccd_buf[(12 + k * 3 + 2) * ccd_t + oi] = r_.th;
             }
           }
 #pragma unroll
@@ -2113,20 +2151,23 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
           for (int q = 0; q < 4; q++) {
             vx[q] = park[(18 + q) * SPR_STRIDE + tid]; vy[q] = park[(22 + q) * SPR_STRIDE + tid]; w[q] = park[(26 + q) * SPR_STRIDE + tid];
             cs_[q] = park[(30 + q) * SPR_STRIDE + tid]; sn_[q] = park[(34 + q) * SPR_STRIDE + tid];
-            x[q] = park[(62 + q) * SPR_STRIDE + tid]; y[q] = park[(66 + q) * SPR_STRIDE + tid];
 #pragma unroll
             for (int z = 0; z < 2; z++) {
               wix[q][z] = park[(38 + q * 2 + z) * SPR_STRIDE + tid]; wiy[q][z] = park[(46 + q * 2 + z) * SPR_STRIDE + tid];
               wiz[q][z] = park[(54 + q * 2 + z) * SPR_STRIDE + tid];
             }
           }
+          __syncthreads();  // every candidate's result is in the scratch
+          if (threadIdx.x == 0) ccd_n = 0;  // (the next append is two barriers away)
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            if (moved & (1u << k)) {  // (the thread's own writes)
-              x[k] = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i];
-              y[k] = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + ccd_i];
-              th[k] = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + ccd_i];
-              r_sincos(th[k], &sn_[k], &cs_[k]);
+            if ((ccand >> k) & 1u) {
+              const real nx_ = P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i], ny_ = P.ccd_buf[(12 + k * 3 + 1) * ccd_t + ccd_i],
+                         nth_ = P.ccd_buf[(12 + k * 3 + 2) * ccd_t + ccd_i];
+              if (nx_ != x[k] || ny_ != y[k] || nth_ != th[k]) {
+                x[k] = nx_; y[k] = ny_; th[k] = nth_;
+                r_sincos(th[k], &sn_[k], &cs_[k]);
+              }
             }
         }
       }

@@ -327,6 +327,19 @@ def main():
                        "status_nonzero": int((m64["res"]["status"] != 0).sum()),
                        "note": "same workload and kernel source, real = double (the parity build)"}
     del bd64
+    # ---- and with dyn4j's continuous detection (ContinuousDetectionMode.ALL, the default of `new Settings()` in the
+    #      reference; off in the headline, which is BASELINE's config as round 1 measured it -- DESIGN section 1)
+    loco_ccd = H.Locomotion(20.0, loco.ground_profile, H.Settings().set(continuous_detection=1))
+    bdc = loco_ccd.compile(robots)
+    mc = R.measure(bdc, n_total, EXTRA_STEPS, 1, separate=False)
+    msc, ec, _ = R.reduce(mc)
+    if rank == 0:
+        out["continuous_detection"] = {"value": total_vs * EXTRA_STEPS / (msc / 1e3), "e2e": total_vs * EXTRA_STEPS / ec,
+                                       "ms_per_step": msc / EXTRA_STEPS, "unit": "voxel-steps/s", "steps": EXTRA_STEPS,
+                                       "status_nonzero": int((mc["res"]["status"] != 0).sum()),
+                                       "note": "same workload, vsr_settings.continuous_detection = 1 (World.solveTOI "
+                                               "against the ground polygons, conservative advancement in double)"}
+    del bdc
 
     # ---- extra_configs
     if args.extra == "all":

@@ -493,5 +493,10 @@ final class DescWriter {
     s.set(JAVA_DOUBLE, off(T, "ground_restitution"), 0d);       // BodyFixture.DEFAULT_RESTITUTION
     s.set(JAVA_INT, off(T, "spring_mass_mode"), 0);             // VSR_SPRING_MASS_REDUCED
     s.set(JAVA_INT, off(T, "self_collision"), 1);               // Voxel.java:178-185,474
+    // World.solveTOI: only ALL (the default of `new Settings()`) tests ordinary dynamic bodies against static ones;
+    // BULLETS_ONLY is NONE here, the reference never creates a bullet
+    s.set(JAVA_INT, off(T, "continuous_detection"),
+        st.getContinuousDetectionMode() == org.dyn4j.dynamics.ContinuousDetectionMode.ALL ? 1 : 0);
+    s.set(JAVA_INT, off(T, "reserved"), 0);
   }
 }

@@ -19,3 +19,12 @@ for ccd in (0, 1):
     out[ccd] = d
     print("continuous_detection=%d: %.4f s  %.3e voxel-steps/s  status!=0 %d  mean d %.3f median %.3f" % (
         ccd, t1 - t0, bd.voxel_steps() / (t1 - t0), int((r["status"] != 0).sum()), d.mean(), np.median(d)), flush=True)
+
+import ctypes
+lib = H.abi.lib if hasattr(H.abi, "lib") else None
+try:
+    c = (ctypes.c_ulonglong * 3)()
+    ctypes.CDLL(os.path.join(ROOT, "2dhmsr_b200", "libvsr_b200.so")).vsr_dev_counters(c)
+    print("ccd candidates %d  block-ticks with a candidate %d  distance evaluations %d  (3 runs)" % (c[0], c[1], c[2]))
+except AttributeError:
+    pass

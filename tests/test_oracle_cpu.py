@@ -196,27 +196,33 @@ def test_island_dfs_order_and_ccd_switches():
     assert d_ccd[min(first + 30, len(d_ccd) - 1)] < 1.5
 
 
-def test_ccd_and_dfs_order_stay_inside_the_reorder_null():
-    # What the two dyn4j features the kernel does not implement (C.6 island order, C.7 CCD) do to the 20 s outcome of
-    # BASELINE config 2, measured with the statistics of the fp32 protocol (tests/test_fp32_protocol_gpu.py) on the
-    # first 256 robots of its fixture: they move the population no more than a seeded reshuffle of the order does.
+def test_dfs_order_stays_inside_the_reorder_null_and_ccd_does_not():
+    # What two dyn4j features do to the 20 s outcome of BASELINE config 2, measured with the statistics of the fp32
+    # protocol (tests/test_fp32_protocol_gpu.py) on its fixture.  The island DFS order (C.6, oracle only) moves the
+    # population no more than a seeded reshuffle of the order does.  Continuous detection (C.7;
+    # vsr_settings.continuous_detection, in the kernel too) does NOT stay inside that null: the mean displacement of
+    # 1024 robots drops by 7.6 % (12.70 -> 11.74, 2.5 x the largest reshuffle), the ranking of the robots is kept as
+    # well as a reshuffle keeps it.  (configs 3 and 4: -12.8 % and -6.5 %)
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     import make_fp32_protocol as proto
     from scipy.stats import spearmanr
     fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "fp32_protocol.npz"))
-    n = 256
-    loco, robots = proto.configs(n)["cfg2"]
-    bd = loco.compile(robots)
-    canon, shuf = fix["cfg2_canon"][:n], fix["cfg2_shuf"][:, :n]
-    null_mean = max(abs(shuf[k].mean() - canon.mean()) for k in range(shuf.shape[0]))
-    null_rho = min(spearmanr(shuf[k], canon)[0] for k in range(shuf.shape[0]))
-    for kw in (dict(ccd=True), dict(order=oracle.ORDER_DFS)):
+    for n, kw in ((256, dict(order=oracle.ORDER_DFS)), (1024, dict(ccd=True))):
+        loco, robots = proto.configs(n)["cfg2"]
+        bd = loco.compile(robots)
+        canon, shuf = fix["cfg2_canon"][:n], fix["cfg2_shuf"][:, :n]
+        null_mean = max(abs(shuf[k].mean() - canon.mean()) for k in range(shuf.shape[0]))
+        null_rho = min(spearmanr(shuf[k], canon)[0] for k in range(shuf.shape[0]))
         r, _ = oracle.run(bd, n_threads=os.cpu_count(), **kw)
         d = r["last_center_x"] - r["first_center_x"]
         assert np.all(r["status"] == 0)
-        assert abs(d.mean() - canon.mean()) <= max(0.05 * abs(canon.mean()), 1.5 * null_mean), kw
         assert spearmanr(d, canon)[0] >= null_rho - 0.05, kw
+        shift = d.mean() - canon.mean()
+        if "ccd" in kw:
+            assert -0.15 * canon.mean() < shift < -1.5 * null_mean, (shift, null_mean)
+        else:
+            assert abs(shift) <= max(0.05 * abs(canon.mean()), 1.5 * null_mean), kw
 
 
 def test_intra_robot_contacts_follow_the_setting():
