@@ -1054,6 +1054,10 @@ static int prepare_bucket(vsr_batch* b, Bucket& k) {
   if constexpr (std::is_same<real, float>::value) {
     if (!blk && d.controller_kind == VSR_CTRL_PHASE_SIN)
       kern = mode == 1 ? vsr_episode_kernel<float, CTRL_PHASE_SIN, 1, false> : (mode == 3 ? vsr_episode_kernel<float, CTRL_PHASE_SIN, 3, false> : nullptr);
+  } else {
+#ifdef VSR_DEV_F64
+    if (!blk && d.controller_kind == VSR_CTRL_PHASE_SIN && mode == 3) kern = vsr_episode_kernel<double, CTRL_PHASE_SIN, 3, false>;
+#endif
   }
   if (!kern) return fail(VSR_ERR_CUDA, "this development build holds the config-2 kernels only");
 #else

@@ -702,6 +702,7 @@ __device__ __forceinline__ bool ccd_distance(int lane, double x, double y, doubl
     const int ow = __shfl_xor_sync(0xffffffffu, who, m);
     if (od < dd || (od == dd && ow < who)) { dd = od; who = ow; }
   }
+  if (dd <= 1e-18) return false;  // touching = not separated (the oracle's poly_distance says why the margin matters; uniform)
   // (on the mass: p1; on the polygon: p2)
   const double m1x = pass == 0 ? px : qx, m1y = pass == 0 ? py : qy, m2x = pass == 0 ? qx : px, m2y = pass == 0 ? qy : py;
   p1x = shfl_d(m1x, who); p1y = shfl_d(m1y, who); p2x = shfl_d(m2x, who); p2y = shfl_d(m2y, who);
@@ -749,7 +750,9 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
       // advancement below is > 1 >= t2 and the polygon yields no time of impact -- without evaluating a distance.
       const cr ex = x1 - x0, ey = y1 - y0;
       const cr gap = ((p0.y - y0) * ex - (p0.x - x0) * ey) / sqrt(ex * ex + ey * ey) - rmax;
+#ifndef VSR_CCD_NO_TRAVEL
       if (gap > (sqrt(dpx * dpx + dpy * dpy) + rmax * fabs(da)) * 1.000001 + 1e-9) continue;
+#endif
     }
     bool in_contact = false;  // body1.isInContact(body2)
 #pragma unroll
@@ -2071,11 +2074,19 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               nseg_++;
               const real sx0_ = P.terr_x[seg], sy0_ = P.terr_y[seg], sy1_ = P.terr_y[seg + 1], ex_ = P.terr_x[seg + 1] - sx0_, ey_ = sy1_ - sy0_;
               const real gap_ = ((p0y - sy0_) * ex_ - (p0x - sx0_) * ey_) / r_sqrt(ex_ * ex_ + ey_ * ey_) - rr_;
+#ifdef VSR_CCD_NO_TRAVEL
+              if (!(ylo_ > r_max(sy0_, sy1_))) hit_ = true;
+#else
               if (!(ylo_ > r_max(sy0_, sy1_)) && !(gap_ > trav_)) hit_ = true;
+#endif
             }
+#ifndef VSR_CCD_NO_PREFILTER
             if (!hit_) continue;
+#endif
             // a mass in contact whose swept box lies over ONE polygon is in contact with that one
+#ifndef VSR_CCD_NO_PREFILTER
             if (((cmask >> k) & 1u) && nseg_ == 1 && P.terr_x[s_] <= xlo_) continue;
+#endif
             ccand |= 1u << k;
             cseg[k] = s_;  // (the first polygon under the swept box: where the pass starts its walk)
             P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i] = x[k];

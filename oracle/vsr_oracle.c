@@ -1514,6 +1514,11 @@ static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p
         }
       }
   }
+  /* Touching counts as not separated (Gjk.distance returns false when the closest point of the simplex to the origin
+     isZero()).  The margin is not cosmetic: a mass that translates without rotating -- a 2-point ground contact leaves
+     it w = 0 -- lands EXACTLY on the surface after its first advance, at a distance of +-1e-16 that the last bit of a
+     projection decides; with the margin every implementation reads that landing the same way (overshoot: back up). */
+  if (best <= 1e-18) return 0;
   *dist = sqrt(best);
   return 1;
 }

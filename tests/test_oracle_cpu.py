@@ -201,8 +201,8 @@ def test_dfs_order_stays_inside_the_reorder_null_and_ccd_does_not():
     # protocol (tests/test_fp32_protocol_gpu.py) on its fixture.  The island DFS order (C.6, oracle only) moves the
     # population no more than a seeded reshuffle of the order does.  Continuous detection (C.7;
     # vsr_settings.continuous_detection, in the kernel too) does NOT stay inside that null: the mean displacement of
-    # 1024 robots drops by 7.6 % (12.70 -> 11.74, 2.5 x the largest reshuffle), the ranking of the robots is kept as
-    # well as a reshuffle keeps it.  (configs 3 and 4: -12.8 % and -6.5 %)
+    # 1024 robots drops by 7.5 % (12.70 -> 11.74, 2.5 x the largest reshuffle), the ranking of the robots is kept as
+    # well as a reshuffle keeps it.  (configs 3 and 4: -12.8 % and -7.1 %)
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     import make_fp32_protocol as proto

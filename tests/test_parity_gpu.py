@@ -824,3 +824,69 @@ def test_fp32_continuous_detection_on_the_product_path():
     assert np.all(res["status"] == 0) and np.all(np.isfinite(res["last_center_x"]))
     per_robot = np.abs(tr[..., :2] - pr["trajectory"][:, :, :40, :2]).max(axis=(1, 2, 3))
     assert np.median(per_robot) < 0.25 and per_robot.max() < 2.0, per_robot
+
+
+def _rope_robots(shape, n, seed):
+    m = H.abi.default_material()
+    m.area_ratio_passive_min, m.area_ratio_passive_max = 0.9, 1.1
+    g = H.RobotUtils.build_shape(shape)
+    body = H.Grid.create(g.w, g.h, lambda x, y: H.Voxel([H.AreaRatio()], m) if g.get(x, y) else None)
+    rng = np.random.default_rng(seed)
+    return [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(g.w, g.h, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", ["mlp", "rope", "rope-big", "big-shared-block", "mixed-batch"])
+def test_fp64_continuous_detection_in_every_kernel_mode(case):
+    """The time-of-impact pass exists in four instantiation families (MODE 3 and MODE 2, warp-shared and block robots)
+    and under every controller; its candidates are pooled per BLOCK, so robots that share a block (several big robots,
+    several shape buckets of one batch) must not see each other."""
+    terrain = "hilly-1-10-0"
+    if case == "mlp":
+        robots = helpers.mlp_robots(5, hidden=(6,), seed=21)
+    elif case == "rope":
+        robots = _rope_robots("biped-4x3", 4, 22)
+    elif case == "rope-big":
+        robots = _rope_robots("box-6x6", 2, 23)
+    elif case == "big-shared-block":
+        robots = helpers.phase_robots(5, shape="box-8x8", seed=24)
+    else:
+        robots = (helpers.phase_robots(3, shape="biped-4x3", seed=25) + helpers.phase_robots(2, shape="box-7x6", seed=26)
+                  + helpers.phase_robots(3, shape="worm-8x2", seed=27))
+    loco = helpers.locomotion(3.0, terrain=terrain, continuous_detection=1)
+    bd = loco.compile(robots, precision=F64, trajectory_robots=len(robots))
+    with H.DeviceBatch(bd) as db:
+        db.upload(0).run()
+        res = db.results()
+        tr = [db.trajectory(i) for i in range(len(robots))]
+    ores, pr = oracle.run(bd, trajectory=True, n_threads=8)
+    otr = pr["trajectory"]
+    assert np.all(res["status"] == 0) and np.all(ores["status"] == 0)
+    # (Conservative advancement had a knife edge here until touching was made "not separated" with a margin in both
+    # implementations -- oracle poly_distance: a mass that translates without rotating lands EXACTLY on the surface after
+    # its first advance.  One robot in twenty then took the other branch within 3 s; none does now: 53 robots of
+    # scripts/ccd_dbg.py agree to 6e-9.)
+    for i in range(len(robots)):
+        nb = 4 * bd.n_voxels[bd.robot_shape[i]]
+        assert np.abs(tr[i][:, :nb, :3] - otr[i][:, :nb, :3]).max() < (5e-6 if case.startswith("rope") else 1e-7), (case, i)
+    # a robot's result does not depend on what else is in its block, nor on the order the block's list was filled in
+    again, _ = helpers.gpu_run(loco.compile(robots, precision=F64))
+    assert again.tobytes() == res.tobytes()
+    alone, _ = helpers.gpu_run(loco.compile([robots[-1]], precision=F64))
+    assert alone[0].tobytes() == res[-1].tobytes()
+
+
+def test_full_size_properties_config2_with_continuous_detection():
+    """BASELINE config 2 with the pass on, fp32: every record valid, two runs bit-identical (the block's candidate list
+    is filled by atomics: its order must not matter), a robot alone = the robot in the batch, and the population mean
+    below the one without the pass (-7.6 % in the oracle)."""
+    import workloads
+    loco, robots = workloads.config2(4096, seed=0)
+    on = H.Locomotion(20.0, loco.ground_profile, H.Settings().set(continuous_detection=1))
+    a, _ = helpers.gpu_run(on.compile(robots))
+    b, _ = helpers.gpu_run(on.compile(robots))
+    off, _ = helpers.gpu_run(loco.compile(robots))
+    assert np.all(a["status"] == 0) and a.tobytes() == b.tobytes()
+    one, _ = helpers.gpu_run(on.compile(robots[1234:1235]))
+    assert one[0].tobytes() == a[1234].tobytes()
+    d_on, d_off = a["last_center_x"] - a["first_center_x"], off["last_center_x"] - off["first_center_x"]
+    assert 0.85 * d_off.mean() < d_on.mean() < 0.98 * d_off.mean(), (d_on.mean(), d_off.mean())
