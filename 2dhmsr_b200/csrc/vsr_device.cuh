@@ -723,10 +723,10 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
   const cr dt = (cr)dtr, lin_tol = (cr)lin_tol_r, max_corr = (cr)max_corr_r, im = (cr)imr, ii = (cr)iir;
   const Pose3<cr> p0 = {(cr)p0r.x, (cr)p0r.y, (cr)p0r.th}, p1 = {(cr)p1r.x, (cr)p1r.y, (cr)p1r.th};
   const cr dpx = (cr)vxr * dt, dpy = (cr)vyr * dt, da = (cr)wr * dt;
-  cr minx, maxx, miny;
+  cr minx, maxx, miny, s0, c0;
   {
     // swept box: an oriented square spans centre +- half (|cos| + |sin|) at either pose
-    cr s0, c0, s1, c1;
+    cr s1, c1;
     sincos(p0.th, &s0, &c0);
     sincos(p1.th, &s1, &c1);
     const cr e0 = half * (fabs(c0) + fabs(s0)), e1 = half * (fabs(c1) + fabs(s1));
@@ -745,11 +745,14 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
     const cr x0 = (cr)P.terr_x[seg], x1 = (cr)P.terr_x[seg + 1], y0 = (cr)P.terr_y[seg], y1 = (cr)P.terr_y[seg + 1];
     if (x1 < minx || !(x1 > x0) || miny > fmax(y0, y1)) continue;
     {
-      // The polygon lies under the line of its top edge, the mass inside its circle: when the gap between the two is
-      // wider than anything the mass can travel in the step, the first advance dist / (dp.n + amax) of the conservative
-      // advancement below is > 1 >= t2 and the polygon yields no time of impact -- without evaluating a distance.
-      const cr ex = x1 - x0, ey = y1 - y0;
-      const cr gap = ((p0.y - y0) * ex - (p0.x - x0) * ey) / sqrt(ex * ex + ey * ey) - rmax;
+      // The polygon lies under the line of its top edge: the distance of the mass from the polygon at t = 0 is at
+      // least that of the square from that half plane (centre's height above the line minus the square's support
+      // along the line's normal).  When that gap is wider than anything the mass can travel in the step, the first
+      // advance dist / (dp.n + amax) of the conservative advancement below is > 1 >= t2 and the polygon yields no time
+      // of impact -- without evaluating a distance.
+      const cr ex = x1 - x0, ey = y1 - y0, el = sqrt(ex * ex + ey * ey);
+      const cr lnx = -ey / el, lny = ex / el;  // the line's normal, upwards
+      const cr gap = (p0.x - x0) * lnx + (p0.y - y0) * lny - half * (fabs(c0 * lnx + s0 * lny) + fabs(c0 * lny - s0 * lnx));
 #ifndef VSR_CCD_NO_TRAVEL
       if (gap > (sqrt(dpx * dpx + dpy * dpy) + rmax * fabs(da)) * 1.000001 + 1e-9) continue;
 #endif
@@ -2070,10 +2073,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             int nseg_ = 0;
             // (and a polygon further away than the mass can travel yields no time of impact: see ccd_mass_warp)
             const real trav_ = (r_sqrt(vx[k] * vx[k] + vy[k] * vy[k]) + rr_ * r_abs(w[k])) * dt + real(1e-3);
+            real s0_, c0_;
+            r_sincos(P.ccd_buf[(k * 3 + 2) * ccd_t + ccd_i], &s0_, &c0_);  // (the pose at the start of the step)
             for (int seg = s_; seg + 1 < P.terr_n && P.terr_x[seg] <= xhi_; ++seg) {
               nseg_++;
               const real sx0_ = P.terr_x[seg], sy0_ = P.terr_y[seg], sy1_ = P.terr_y[seg + 1], ex_ = P.terr_x[seg + 1] - sx0_, ey_ = sy1_ - sy0_;
-              const real gap_ = ((p0y - sy0_) * ex_ - (p0x - sx0_) * ey_) / r_sqrt(ex_ * ex_ + ey_ * ey_) - rr_;
+              const real il_ = real(1) / r_sqrt(ex_ * ex_ + ey_ * ey_), lnx_ = -ey_ * il_, lny_ = ex_ * il_;
+              const real gap_ = (p0x - sx0_) * lnx_ + (p0y - sy0_) * lny_
+                                - P.half * (r_abs(c0_ * lnx_ + s0_ * lny_) + r_abs(c0_ * lny_ - s0_ * lnx_)) - real(0.01);
 #ifdef VSR_CCD_NO_TRAVEL
               if (!(ylo_ > r_max(sy0_, sy1_))) hit_ = true;
 #else
@@ -2099,7 +2106,6 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         }
 #ifdef VSR_CCD_COUNT
         if (ccand) atomicAdd(&g_ccd_count, (unsigned long long)__popc(ccand));
-        { const int a_ = __syncthreads_or(ccand != 0u); if (threadIdx.x == 0 && a_) atomicAdd(&g_ccd_count2, 1ull); }
 #endif
         // Block-wide pool: the candidates of all the block's robots go into one list and the warps take them in
         // turn.  (Per warp, the block waited at the next barrier for the warp whose robot stands on the border slope:
@@ -2148,8 +2154,14 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             const real ovx = P.ccd_buf[(24 + k * 3 + 0) * ccd_t + oi], ovy = P.ccd_buf[(24 + k * 3 + 1) * ccd_t + oi],
                        ow_ = P.ccd_buf[(24 + k * 3 + 2) * ccd_t + oi];
             const CBody<real>* const ob = blk_cb + (size_t)ot * 8 + 2 * k + ((e_ >> 12) & 1);
+#ifdef VSR_CCD_COUNT
+            const long long clk0_ = clock64();
+#endif
             const Pose3<real> r_ = ccd_mass_warp(tpar, p0, p1, ovx, ovy, ow_, dt, ob, (e_ >> 13) & 1, P.lin_tol, P.max_corr, im, ii,
                                                  (int)((unsigned)e_ >> 14));
+#ifdef VSR_CCD_COUNT
+            if (lane == 0) atomicAdd(&g_ccd_count2, (unsigned long long)(clock64() - clk0_));
+#endif
             if (lane == 0 && (r_.x != p1.x || r_.y != p1.y || r_.th != p1.th)) {
               P.ccd_buf[(12 + k * 3 + 0) * ccd_t + oi] = r_.x;
               P.ccd_buf[(12 + k * 3 + 1) * ccd_t + oi] = r_.y;

@@ -835,12 +835,12 @@ def _rope_robots(shape, n, seed):
     return [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(g.w, g.h, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(n)]
 
 
-@pytest.mark.parametrize("case", ["mlp", "rope", "rope-big", "big-shared-block", "mixed-batch"])
+@pytest.mark.parametrize("case", ["mlp", "rope", "rope-big", "big-shared-block", "mixed-batch", "effective-mass", "breakable"])
 def test_fp64_continuous_detection_in_every_kernel_mode(case):
     """The time-of-impact pass exists in four instantiation families (MODE 3 and MODE 2, warp-shared and block robots)
     and under every controller; its candidates are pooled per BLOCK, so robots that share a block (several big robots,
     several shape buckets of one batch) must not see each other."""
-    terrain = "hilly-1-10-0"
+    terrain, extra = "hilly-1-10-0", {}
     if case == "mlp":
         robots = helpers.mlp_robots(5, hidden=(6,), seed=21)
     elif case == "rope":
@@ -849,10 +849,18 @@ def test_fp64_continuous_detection_in_every_kernel_mode(case):
         robots = _rope_robots("box-6x6", 2, 23)
     elif case == "big-shared-block":
         robots = helpers.phase_robots(5, shape="box-8x8", seed=24)
+    elif case == "effective-mass":   # the generic voxel (MODE 0 without the pass): the pass lives in the MODE 2 kernel
+        robots = helpers.phase_robots(4, shape="worm-5x2", seed=28)
+        extra = dict(spring_mass_mode=A.VSR_SPRING_MASS_EFFECTIVE)
+    elif case == "breakable":
+        sens = lambda: [H.SoftNormalization(H.AreaRatio()), H.Malfunction()]
+        body = _breakable_body(4, 2, sens, {"ACTUATOR": {"ZERO", "FROZEN", "RANDOM"}}, {"TIME": 1.0, "AREA": 50.0}, 0.4)
+        rng = np.random.default_rng(29)
+        robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(4, 2, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(3)]
     else:
         robots = (helpers.phase_robots(3, shape="biped-4x3", seed=25) + helpers.phase_robots(2, shape="box-7x6", seed=26)
                   + helpers.phase_robots(3, shape="worm-8x2", seed=27))
-    loco = helpers.locomotion(3.0, terrain=terrain, continuous_detection=1)
+    loco = helpers.locomotion(3.0, terrain=terrain, continuous_detection=1, **extra)
     bd = loco.compile(robots, precision=F64, trajectory_robots=len(robots))
     with H.DeviceBatch(bd) as db:
         db.upload(0).run()
