@@ -212,6 +212,7 @@ def default_settings() -> vsr_settings:
     s.ground_restitution = 0.0
     s.spring_mass_mode = VSR_SPRING_MASS_REDUCED
     s.self_collision = 1
+    s.continuous_detection = 1  # ContinuousDetectionMode.ALL
     return s
 
 

@@ -64,7 +64,7 @@ extern "C" void vsr_default_settings(vsr_settings* s) {
   s->ground_restitution = 0.0;
   s->spring_mass_mode = VSR_SPRING_MASS_REDUCED;
   s->self_collision = 1;
-  s->continuous_detection = 0;
+  s->continuous_detection = 1;  // ContinuousDetectionMode.ALL, the default of dyn4j's `new Settings()` (Locomotion.java:50)
   s->reserved = 0;
 }
 

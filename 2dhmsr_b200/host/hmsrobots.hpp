@@ -728,6 +728,7 @@ class Settings {  // org.dyn4j.dynamics.Settings as a value holder (Locomotion.j
     s_.gravity_x = 0.0; s_.gravity_y = -9.8; s_.ground_friction = 0.2; s_.ground_restitution = 0.0;
     s_.spring_mass_mode = VSR_SPRING_MASS_REDUCED;
     s_.self_collision = 1;
+    s_.continuous_detection = 1;  // ContinuousDetectionMode.ALL, dyn4j's default
   }
   double getStepFrequency() const { return s_.step_frequency; }
   vsr_settings& raw() { return s_; }

@@ -1,13 +1,15 @@
 """Oracle half of the fp32 parity protocol, precomputed: tests/golden/fp32_protocol.npz.
 
 For each of BASELINE configs 2, 3 ([21, 21] closed loop) and 4, N = 1024 seeded robots, full 20 s episodes:
-  canon[i]      20 s displacement of robot i, oracle (fp64) in the canonical Gauss-Seidel order (= the kernel's)
+  canon[i]      20 s displacement of robot i, oracle (fp64) in the canonical Gauss-Seidel order (= the kernel's),
+                default settings (continuous detection on, as dyn4j's `new Settings()`)
+  canon_nopass  the same with vsr_settings.continuous_detection = 0
   shuf[k][i]    the same under K + 1 = 9 seeded random constraint orders (VSR_ORACLE_ORDER_SHUFFLED)
 The shuffles measure the INTRINSIC spread of a robot's outcome under a change north_star concedes (solver order):
 sigma_perm[i] = std_k shuf[k][i].  tests/test_fp32_protocol_gpu.py compares the fp32 kernel against these;
 tests/test_host_golden.py re-runs a slice of the oracle against the file so that it cannot go stale.
 
-    python tests/golden/make_fp32_protocol.py        (about 10 minutes on 8 cores)
+    python tests/golden/make_fp32_protocol.py        (about 20 minutes on 8 cores)
 """
 import hashlib
 import json
@@ -50,6 +52,16 @@ def main():
         shuf = [disp(oracle.run(bd, order=oracle.ORDER_SHUFFLED, seed=SHUFFLE_SEED0 + k, n_threads=threads)[0])
                 for k in range(K + 1)]
         out[name + "_canon"] = disp(canon)
+        # the same robots under ContinuousDetectionMode.NONE (canonical order): what the time-of-impact pass does to a
+        # population is read off against the reorder null (tests/test_oracle_cpu.py)
+        import importlib
+        H = importlib.import_module("2dhmsr_b200")
+        st = H.Settings()
+        for f, _t in st.raw()._fields_:
+            setattr(st.raw(), f, getattr(loco.settings.raw(), f))
+        nopass, _ = oracle.run(H.Locomotion(20.0, loco.ground_profile, st.set(continuous_detection=0)).compile(robots),
+                               n_threads=threads)
+        out[name + "_canon_nopass"] = disp(nopass)
         out[name + "_time"] = canon["t_last"] - canon["t_first"]
         out[name + "_shuf"] = np.stack(shuf)
         print(f"{name}: {time.time() - t0:.0f} s, mean d {disp(canon).mean():.3f}, median sigma_perm "

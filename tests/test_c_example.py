@@ -34,7 +34,7 @@ def test_c_example_equals_python_path():
     body = helpers.body_of("biped-4x3")
     robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(4, 3, lambda x, y, r=r: 0.1 * (r + 1) + 0.7 * x + 0.3 * y)), body)
               for r in range(3)]
-    outs = helpers.locomotion().apply(robots)
+    outs = H.Locomotion(20.0, H.Locomotion.create_terrain("flat"), H.Settings()).apply(robots)   # vsr_default_settings
     assert j["n_ticks"] == 1200
     assert j["distance"] == [o.get_distance() for o in outs]
     assert j["velocity"] == [o.get_velocity() for o in outs]

@@ -89,13 +89,14 @@ def test_cpp_host_mirror_selfcheck():
 @pytest.mark.gpu
 def test_cpp_locomotion_apply_equals_python_path():
     j = _run("run")
-    o = helpers.locomotion().apply(helpers.config1_robot())
+    default = lambda: H.Locomotion(20.0, H.Locomotion.create_terrain("flat"), H.Settings())   # as hmsrobots::Settings()
+    o = default().apply(helpers.config1_robot())
     assert j["cfg1"]["distance"] == o.get_distance() and j["cfg1"]["velocity"] == o.get_velocity()
     assert j["cfg1"]["time"] == pytest.approx(20 - 1 / 60, abs=1e-9)
     body = helpers.body_of("biped-4x3")
     robots = [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(4, 3, lambda x, y, b=b: b + 0.7 * x + 0.3 * y)), body)
               for b in (0.1, 0.2, 0.3)]
-    outs = helpers.locomotion().apply(robots)
+    outs = default().apply(robots)
     assert j["phase_distance"] == [o.get_distance() for o in outs]
 
     def dist_robot(seed, directional):
@@ -110,12 +111,12 @@ def test_cpp_locomotion_apply_equals_python_path():
             ds.get_functions().set(x, y, H.MultiLayerPerceptron("TANH", nin, [2], nout, [rnd.next_double() * 2.0 - 1.0 for _ in range(nw)]))
         return H.Robot(ds, body)
 
-    l5 = helpers.locomotion(5.0)
+    l5 = H.Locomotion(5.0, H.Locomotion.create_terrain("flat"), H.Settings())
     want = [o.get_distance() for o in l5.apply([dist_robot(7, True), dist_robot(8, True)])] + \
            [l5.apply(dist_robot(7, False)).get_distance()]
     assert j["distributed_distance"] == want
     # the per-tick Observation map through the C++ mirror against the Python one
-    o = helpers.locomotion(2.0).apply(robots[0], observations=True)
+    o = H.Locomotion(2.0, H.Locomotion.create_terrain("flat"), H.Settings()).apply(robots[0], observations=True)
     obs = o.get_observations()
     polies = lambda ob: [v for v in ob.voxel_polies.values() if v is not None]
     last = list(obs.values())[-1]

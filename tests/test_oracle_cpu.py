@@ -200,29 +200,32 @@ def test_dfs_order_stays_inside_the_reorder_null_and_ccd_does_not():
     # What two dyn4j features do to the 20 s outcome of BASELINE config 2, measured with the statistics of the fp32
     # protocol (tests/test_fp32_protocol_gpu.py) on its fixture.  The island DFS order (C.6, oracle only) moves the
     # population no more than a seeded reshuffle of the order does.  Continuous detection (C.7;
-    # vsr_settings.continuous_detection, in the kernel too) does NOT stay inside that null: the mean displacement of
-    # 1024 robots drops by 7.5 % (12.70 -> 11.74, 2.5 x the largest reshuffle), the ranking of the robots is kept as
-    # well as a reshuffle keeps it.  (configs 3 and 4: -12.8 % and -7.1 %)
+    # vsr_settings.continuous_detection, on by default as in dyn4j, in the kernel too) does NOT stay inside that null:
+    # switched off, the mean displacement of 1024 robots is 8 % higher (11.74 -> 12.70, 2.5 x the largest reshuffle),
+    # while the ranking of the robots is kept as well as a reshuffle keeps it.  (configs 3 and 4: 3.21 -> 3.67 and
+    # 8.13 -> 8.75)  This is why the pass is not a "documented omission"  here.
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     import make_fp32_protocol as proto
     from scipy.stats import spearmanr
     fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "fp32_protocol.npz"))
-    for n, kw in ((256, dict(order=oracle.ORDER_DFS)), (1024, dict(ccd=True))):
-        loco, robots = proto.configs(n)["cfg2"]
-        bd = loco.compile(robots)
-        canon, shuf = fix["cfg2_canon"][:n], fix["cfg2_shuf"][:, :n]
+    for cfg in ("cfg2", "cfg3", "cfg4"):
+        canon, nopass, shuf = fix[cfg + "_canon"], fix[cfg + "_canon_nopass"], fix[cfg + "_shuf"]
         null_mean = max(abs(shuf[k].mean() - canon.mean()) for k in range(shuf.shape[0]))
         null_rho = min(spearmanr(shuf[k], canon)[0] for k in range(shuf.shape[0]))
-        r, _ = oracle.run(bd, n_threads=os.cpu_count(), **kw)
-        d = r["last_center_x"] - r["first_center_x"]
-        assert np.all(r["status"] == 0)
-        assert spearmanr(d, canon)[0] >= null_rho - 0.05, kw
-        shift = d.mean() - canon.mean()
-        if "ccd" in kw:
-            assert -0.15 * canon.mean() < shift < -1.5 * null_mean, (shift, null_mean)
-        else:
-            assert abs(shift) <= max(0.05 * abs(canon.mean()), 1.5 * null_mean), kw
+        shift = nopass.mean() - canon.mean()
+        assert 1.2 * null_mean < shift < 0.2 * canon.mean(), (cfg, shift, null_mean)
+        assert spearmanr(nopass, canon)[0] >= null_rho - 0.05, cfg
+    n = 256
+    loco, robots = proto.configs(n)["cfg2"]
+    canon, shuf = fix["cfg2_canon"][:n], fix["cfg2_shuf"][:, :n]
+    null_mean = max(abs(shuf[k].mean() - canon.mean()) for k in range(shuf.shape[0]))
+    null_rho = min(spearmanr(shuf[k], canon)[0] for k in range(shuf.shape[0]))
+    r, _ = oracle.run(loco.compile(robots), n_threads=os.cpu_count(), order=oracle.ORDER_DFS)
+    d = r["last_center_x"] - r["first_center_x"]
+    assert np.all(r["status"] == 0)
+    assert spearmanr(d, canon)[0] >= null_rho - 0.05
+    assert abs(d.mean() - canon.mean()) <= max(0.05 * abs(canon.mean()), 1.5 * null_mean)
 
 
 def test_intra_robot_contacts_follow_the_setting():

@@ -883,18 +883,19 @@ def test_fp64_continuous_detection_in_every_kernel_mode(case):
     assert alone[0].tobytes() == res[-1].tobytes()
 
 
-def test_full_size_properties_config2_with_continuous_detection():
-    """BASELINE config 2 with the pass on, fp32: every record valid, two runs bit-identical (the block's candidate list
-    is filled by atomics: its order must not matter), a robot alone = the robot in the batch, and the population mean
-    below the one without the pass (-7.6 % in the oracle)."""
+def test_full_size_properties_config2_continuous_detection_switch():
+    """BASELINE config 2 under the default settings (the pass on), fp32: every record valid, two runs bit-identical (the
+    block's candidate list is filled by atomics: its order must not matter), a robot alone = the robot in the batch, and
+    the population mean below the one with the pass switched off (-7.5 % in the oracle)."""
     import workloads
     loco, robots = workloads.config2(4096, seed=0)
-    on = H.Locomotion(20.0, loco.ground_profile, H.Settings().set(continuous_detection=1))
-    a, _ = helpers.gpu_run(on.compile(robots))
-    b, _ = helpers.gpu_run(on.compile(robots))
-    off, _ = helpers.gpu_run(loco.compile(robots))
-    assert np.all(a["status"] == 0) and a.tobytes() == b.tobytes()
-    one, _ = helpers.gpu_run(on.compile(robots[1234:1235]))
+    assert loco.settings.continuous_detection == 1
+    st = H.Settings().set(continuous_detection=0)
+    a, _ = helpers.gpu_run(loco.compile(robots))
+    b, _ = helpers.gpu_run(loco.compile(robots))
+    off, _ = helpers.gpu_run(H.Locomotion(20.0, loco.ground_profile, st).compile(robots))
+    assert np.all(a["status"] == 0) and np.all(off["status"] == 0) and a.tobytes() == b.tobytes()
+    one, _ = helpers.gpu_run(loco.compile(robots[1234:1235]))
     assert one[0].tobytes() == a[1234].tobytes()
     d_on, d_off = a["last_center_x"] - a["first_center_x"], off["last_center_x"] - off["first_center_x"]
     assert 0.85 * d_off.mean() < d_on.mean() < 0.98 * d_off.mean(), (d_on.mean(), d_off.mean())
