@@ -1312,5 +1312,6 @@ extern "C" void vsr_dev_counters(unsigned long long* out) {
   cudaMemcpyFromSymbol(&out[0], g_ccd_count, 8);
   cudaMemcpyFromSymbol(&out[1], g_ccd_count2, 8);
   cudaMemcpyFromSymbol(&out[2], g_ccd_count3, 8);
+  cudaMemcpyFromSymbol(&out[3], g_ccd_hist, 32);
 }
 #endif

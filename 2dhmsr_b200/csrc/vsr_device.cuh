@@ -617,43 +617,50 @@ __device__ __noinline__ int detect_mass(const TPar<real> P, real bx, real by, re
 // its decisions hang on distances of 6e-6 (distanceEpsilon), a dozen ulps of a float coordinate -- in float the
 // advancement does not converge and a population slows down by a quarter.
 #ifdef VSR_CCD_COUNT
-__device__ unsigned long long g_ccd_count, g_ccd_count2, g_ccd_count3;
+__device__ unsigned long long g_ccd_count, g_ccd_count2, g_ccd_count3, g_ccd_hist[4];
 #endif
 template <typename real>
 struct Pose3 {
   real x, y, th;
 };
-__device__ __forceinline__ void ccd_mass_vertex(int i, double x, double y, double hc, double hs, double& vx, double& vy) {
+template <typename cr>
+__device__ __forceinline__ void ccd_mass_vertex(int i, cr x, cr y, cr hc, cr hs, cr& vx, cr& vy) {
   // corners (-h,-h) (+h,-h) (+h,+h) (-h,+h) of the rotated square: x + sx hc - sy hs, y + sx hs + sy hc
-  const double sx = (i == 1 || i == 2) ? 1.0 : -1.0, sy = (i >= 2) ? 1.0 : -1.0;
+  const cr sx = (i == 1 || i == 2) ? cr(1) : cr(-1), sy = (i >= 2) ? cr(1) : cr(-1);
   vx = x + sx * hc - sy * hs;
   vy = y + sx * hs + sy * hc;
 }
-__device__ __forceinline__ void ccd_ground_vertex(int j, double x0, double y0, double x1, double y1, double base_y, double& vx, double& vy) {
+template <typename cr>
+__device__ __forceinline__ void ccd_ground_vertex(int j, cr x0, cr y0, cr x1, cr y1, cr base_y, cr& vx, cr& vy) {
   vx = j < 2 ? x0 : x1;  // (x0, y0) (x0, base) (x1, base) (x1, y1): Ground.java:64-70
   vy = j == 0 ? y0 : (j == 3 ? y1 : base_y);
 }
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename cr>
+__device__ __forceinline__ cr shfl_d(cr v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <typename cr>
+__device__ __forceinline__ cr shfl_xor_d(cr v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 // the ground polygon of a segment, as the per-lane constants of the evaluation (lane = pass * 16 + i * 4 + j)
+template <typename cr>
 struct CcdGround {
-  double x0, y0, x1, y1, base_y;
-  double gnx, gny;  // normal of THIS lane's SAT axis when it is one of the polygon's (lanes 16..31: axis (lane >> 2) & 3)
-  double inv_e;     // 1 / squared length of this lane's edge (pass 0: ground edge j; pass 1: the mass' edge)
+  cr x0, y0, x1, y1, base_y;
+  cr gnx, gny;  // normal of THIS lane's SAT axis when it is one of the polygon's (lanes 16..31: axis (lane >> 2) & 3)
+  cr inv_e;         // 1 / squared length of this lane's edge (pass 0: ground edge j; pass 1: the mass' edge)
 };
-// distance of the mass at (x, y, th) from the polygon G; all lanes get the same answer (false: they overlap)
-__device__ __forceinline__ bool ccd_distance(int lane, double x, double y, double th, double half, const CcdGround& G, double& dist,
-                                             double& p1x, double& p1y, double& p2x, double& p2y) {
-  double sn, cs;
-  sincos(th, &sn, &cs);
-  const double hc = half * cs, hs = half * sn;
+// distance of the mass at (x, y), rotated by the angle whose sine and cosine are (sn, cs), from the polygon G; all lanes get the same answer (false: they overlap)
+template <typename cr>
+__device__ __forceinline__ bool ccd_distance(int lane, cr x, cr y, cr sn, cr cs, cr half, const CcdGround<cr>& G, bool sat, cr& dist,
+                                             cr& p1x, cr& p1y, cr& p2x, cr& p2y) {
+  const cr hc = half * cs, hs = half * sn;
   const int pass = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
+  // (margins: the oracle's in double; the float values belong to the experiment described in ccd_mass_warp)
+  const cr tie = sizeof(cr) == 8 ? cr(1e-12) : cr(1e-6), touch2 = sizeof(cr) == 8 ? cr(1e-18) : cr(1e-12);
+  if (sat) {  // (warp-uniform)
   // ---- SAT (the oracle's sat_penetration): axis i of the mass (lanes 0..15) / of the polygon (16..31), vertex j of the other
-  double proj;
+  cr proj;
   {
-    double ax, ay, gx, gy;
+    cr ax, ay, gx, gy;
     if (pass == 0) {
-      const double nx = i == 0 ? sn : (i == 1 ? cs : (i == 2 ? -sn : -cs)), ny = i == 0 ? -cs : (i == 1 ? sn : (i == 2 ? cs : -sn));
+      const cr nx = i == 0 ? sn : (i == 1 ? cs : (i == 2 ? -sn : -cs)), ny = i == 0 ? -cs : (i == 1 ? sn : (i == 2 ? cs : -sn));
       ccd_mass_vertex(i, x, y, hc, hs, ax, ay);
       ccd_ground_vertex(j, G.x0, G.y0, G.x1, G.y1, G.base_y, gx, gy);
       proj = nx * (gx - ax) + ny * (gy - ay);
@@ -663,50 +670,67 @@ __device__ __forceinline__ bool ccd_distance(int lane, double x, double y, doubl
       proj = G.gnx * (ax - gx) + G.gny * (ay - gy);
     }
   }
-  proj = fmin(proj, shfl_xor_d(proj, 1));
-  proj = fmin(proj, shfl_xor_d(proj, 2));  // every group of 4 lanes: the axis' smallest projection
-  double best = -1e300;
+  proj = r_min(proj, shfl_xor_d(proj, 1));
+  proj = r_min(proj, shfl_xor_d(proj, 2));  // every group of 4 lanes: the axis' smallest projection
+  cr best = cr(-1e30);
 #pragma unroll
   for (int a = 0; a < 4; a++) {            // the mass' axes: the first maximum
-    const double sm = shfl_d(proj, a * 4);
+    const cr sm = shfl_d(proj, a * 4);
     if (sm > best) best = sm;
   }
 #pragma unroll
   for (int a = 0; a < 4; a++) {            // the polygon's: only by more than the tie margin
-    const double sm = shfl_d(proj, 16 + a * 4);
-    if (sm > best + 1e-12) best = sm;
+    const cr sm = shfl_d(proj, 16 + a * 4);
+    if (sm > best + tie) best = sm;
   }
-  if (best < 0.0) return false;            // penetrating (uniform)
+  if (best < cr(0)) return false;            // penetrating (uniform)
+  }
   // ---- closest points (the oracle's poly_distance): pass 0 = vertex i of the mass against edge j of the polygon,
   //      pass 1 = vertex i of the polygon against edge j of the mass; the first minimum in lane order
-  double px, py, ex0, ey0, ex1, ey1;
-  if (pass == 0) {
-    ccd_mass_vertex(i, x, y, hc, hs, px, py);
-    ccd_ground_vertex(j, G.x0, G.y0, G.x1, G.y1, G.base_y, ex0, ey0);
-    ccd_ground_vertex((j + 1) & 3, G.x0, G.y0, G.x1, G.y1, G.base_y, ex1, ey1);
+  // (branch-free: the two halves of the warp would otherwise run their sides of an if one after the other -- a mass
+  //  vertex is four multiply-adds, a ground vertex two selects, so every lane builds both candidates and selects)
+  cr px, py, ex0, ey0, ex1, ey1;
+  {
+    cr mpx, mpy, gpx, gpy, m0x, m0y, m1x_, m1y_, g0x, g0y, g1x, g1y;
+    ccd_mass_vertex(i, x, y, hc, hs, mpx, mpy);
+    ccd_ground_vertex(i, G.x0, G.y0, G.x1, G.y1, G.base_y, gpx, gpy);
+    ccd_mass_vertex(j, x, y, hc, hs, m0x, m0y);
+    ccd_mass_vertex((j + 1) & 3, x, y, hc, hs, m1x_, m1y_);
+    ccd_ground_vertex(j, G.x0, G.y0, G.x1, G.y1, G.base_y, g0x, g0y);
+    ccd_ground_vertex((j + 1) & 3, G.x0, G.y0, G.x1, G.y1, G.base_y, g1x, g1y);
+    const bool p0_ = pass == 0;
+    px = p0_ ? mpx : gpx; py = p0_ ? mpy : gpy;
+    ex0 = p0_ ? g0x : m0x; ey0 = p0_ ? g0y : m0y;
+    ex1 = p0_ ? g1x : m1x_; ey1 = p0_ ? g1y : m1y_;
+  }
+  const cr ex = ex1 - ex0, ey = ey1 - ey0;
+  cr t = ((px - ex0) * ex + (py - ey0) * ey) * G.inv_e;
+  t = t < cr(0) ? cr(0) : (t > cr(1) ? cr(1) : t);
+  const cr qx = ex0 + t * ex, qy = ey0 + t * ey;
+  const cr dx = px - qx, dy = py - qy;
+  cr dd = dx * dx + dy * dy;
+  // the first minimum in lane order: dd >= 0, so its bit pattern orders like an unsigned integer -- two warp-wide integer
+  // minima (high word, then low word among the lanes that hold the smallest high word) and a ballot replace five rounds
+  // of three shuffles
+  int who;
+  if (sizeof(cr) == 8) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong((double)dd);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    who = __ffs((int)__ballot_sync(0xffffffffu, hi == mh && lo == ml)) - 1;
+    dd = (cr)__longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
   } else {
-    ccd_ground_vertex(i, G.x0, G.y0, G.x1, G.y1, G.base_y, px, py);
-    ccd_mass_vertex(j, x, y, hc, hs, ex0, ey0);
-    ccd_mass_vertex((j + 1) & 3, x, y, hc, hs, ex1, ey1);
+    const unsigned key = __float_as_uint((float)dd);
+    const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+    who = __ffs((int)__ballot_sync(0xffffffffu, key == mk)) - 1;
+    dd = (cr)__uint_as_float(mk);
   }
-  const double ex = ex1 - ex0, ey = ey1 - ey0;
-  double t = ((px - ex0) * ex + (py - ey0) * ey) * G.inv_e;
-  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
-  const double qx = ex0 + t * ex, qy = ey0 + t * ey;
-  const double dx = px - qx, dy = py - qy;
-  double dd = dx * dx + dy * dy;
-  int who = lane;
-#pragma unroll
-  for (int m = 1; m < 32; m <<= 1) {
-    const double od = shfl_xor_d(dd, m);
-    const int ow = __shfl_xor_sync(0xffffffffu, who, m);
-    if (od < dd || (od == dd && ow < who)) { dd = od; who = ow; }
-  }
-  if (dd <= 1e-18) return false;  // touching = not separated (the oracle's poly_distance says why the margin matters; uniform)
+  if (dd <= touch2) return false;  // touching = not separated (the oracle's poly_distance says why the margin matters; uniform)
   // (on the mass: p1; on the polygon: p2)
-  const double m1x = pass == 0 ? px : qx, m1y = pass == 0 ? py : qy, m2x = pass == 0 ? qx : px, m2y = pass == 0 ? qy : py;
+  const cr m1x = pass == 0 ? px : qx, m1y = pass == 0 ? py : qy, m2x = pass == 0 ? qx : px, m2y = pass == 0 ? qy : py;
   p1x = shfl_d(m1x, who); p1y = shfl_d(m1y, who); p2x = shfl_d(m2x, who); p2y = shfl_d(m2y, who);
-  dist = sqrt(dd);
+  dist = r_sqrt(dd);
   return true;
 }
 // The pass for ONE mass, executed by a whole (converged) warp; every argument is warp-uniform.
@@ -714,47 +738,53 @@ template <typename real>
 __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real> p0r, Pose3<real> p1r, real vxr, real vyr, real wr,
                                                   real dtr, const CBody<real>* cur, int has_contacts, real lin_tol_r,
                                                   real max_corr_r, real imr, real iir, int hint) {
+  // All of it in double, in both builds.  (Tried in float, in a frame local to the mass so that 24 bits resolve 1e-7:
+  // 1.7 x faster per candidate, but the touching / overlapping decisions near the surface go the other way often enough
+  // to lower the population's mean displacement by 23 % -- conservative advancement has to resolve distanceEpsilon =
+  // 6e-6, and its exits at "touching" need the margins of double.)
   typedef double cr;
+  constexpr bool LOCAL = false;
   const int lane = threadIdx.x & 31;
-  const cr eps_e = 2.220446049250313e-16;
-  const cr dist_eps = 6.0554544523933395e-6;               // cbrt(Epsilon.E)
-  const cr half = (cr)P.half, base_y = (cr)P.base_y;
-  const cr rmax = half * 1.4142135623730951;                // Rectangle.getRadius
+  const cr eps_e = cr(2.220446049250313e-16);
+  const cr dist_eps = cr(6.0554544523933395e-6);           // cbrt(Epsilon.E)
+  const cr ox = LOCAL ? p0r.x : cr(0), oy = LOCAL ? p0r.y : cr(0);
+  const cr half = (cr)P.half, base_y = (cr)P.base_y - oy;
+  const cr rmax = half * cr(1.4142135623730951);            // Rectangle.getRadius
   const cr dt = (cr)dtr, lin_tol = (cr)lin_tol_r, max_corr = (cr)max_corr_r, im = (cr)imr, ii = (cr)iir;
-  const Pose3<cr> p0 = {(cr)p0r.x, (cr)p0r.y, (cr)p0r.th}, p1 = {(cr)p1r.x, (cr)p1r.y, (cr)p1r.th};
+  const Pose3<cr> p0 = {p0r.x - ox, p0r.y - oy, p0r.th}, p1 = {p1r.x - ox, p1r.y - oy, p1r.th};
   const cr dpx = (cr)vxr * dt, dpy = (cr)vyr * dt, da = (cr)wr * dt;
   cr minx, maxx, miny, s0, c0;
   {
     // swept box: an oriented square spans centre +- half (|cos| + |sin|) at either pose
     cr s1, c1;
-    sincos(p0.th, &s0, &c0);
-    sincos(p1.th, &s1, &c1);
-    const cr e0 = half * (fabs(c0) + fabs(s0)), e1 = half * (fabs(c1) + fabs(s1));
-    minx = fmin(p0.x - e0, p1.x - e1);
-    maxx = fmax(p0.x + e0, p1.x + e1);
-    miny = fmin(p0.y - e0, p1.y - e1);
+    r_sincos(p0.th, &s0, &c0);
+    r_sincos(p1.th, &s1, &c1);
+    const cr e0 = half * (r_abs(c0) + r_abs(s0)), e1 = half * (r_abs(c1) + r_abs(s1));
+    minx = r_min(p0.x - e0, p1.x - e1);
+    maxx = r_max(p0.x + e0, p1.x + e1);
+    miny = r_min(p0.y - e0, p1.y - e1);
   }
   const int n = P.terr_n;
   int s = hint;
-  while (s > 0 && (cr)P.terr_x[s] > minx) --s;
-  cr t2 = 1.0, best_d = 0.0, bp1x = 0.0, bp1y = 0.0, bp2x = 0.0, bp2y = 0.0;
+  while (s > 0 && (cr)P.terr_x[s] - ox > minx) --s;
+  cr t2 = cr(1), best_d = cr(0), bp1x = cr(0), bp1y = cr(0), bp2x = cr(0), bp2y = cr(0);
   bool found = false;
   const int n_cur = has_contacts ? cur->n : 0;
 #pragma unroll 1
-  for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] <= maxx; ++seg) {
-    const cr x0 = (cr)P.terr_x[seg], x1 = (cr)P.terr_x[seg + 1], y0 = (cr)P.terr_y[seg], y1 = (cr)P.terr_y[seg + 1];
-    if (x1 < minx || !(x1 > x0) || miny > fmax(y0, y1)) continue;
+  for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] - ox <= maxx; ++seg) {
+    const cr x0 = (cr)P.terr_x[seg] - ox, x1 = (cr)P.terr_x[seg + 1] - ox, y0 = (cr)P.terr_y[seg] - oy, y1 = (cr)P.terr_y[seg + 1] - oy;
+    if (x1 < minx || !(x1 > x0) || miny > r_max(y0, y1)) continue;
     {
       // The polygon lies under the line of its top edge: the distance of the mass from the polygon at t = 0 is at
       // least that of the square from that half plane (centre's height above the line minus the square's support
       // along the line's normal).  When that gap is wider than anything the mass can travel in the step, the first
       // advance dist / (dp.n + amax) of the conservative advancement below is > 1 >= t2 and the polygon yields no time
       // of impact -- without evaluating a distance.
-      const cr ex = x1 - x0, ey = y1 - y0, el = sqrt(ex * ex + ey * ey);
+      const cr ex = x1 - x0, ey = y1 - y0, el = r_sqrt(ex * ex + ey * ey);
       const cr lnx = -ey / el, lny = ex / el;  // the line's normal, upwards
-      const cr gap = (p0.x - x0) * lnx + (p0.y - y0) * lny - half * (fabs(c0 * lnx + s0 * lny) + fabs(c0 * lny - s0 * lnx));
+      const cr gap = (p0.x - x0) * lnx + (p0.y - y0) * lny - half * (r_abs(c0 * lnx + s0 * lny) + r_abs(c0 * lny - s0 * lnx));
 #ifndef VSR_CCD_NO_TRAVEL
-      if (gap > (sqrt(dpx * dpx + dpy * dpy) + rmax * fabs(da)) * 1.000001 + 1e-9) continue;
+      if (gap > (r_sqrt(dpx * dpx + dpy * dpy) + rmax * r_abs(da)) * (LOCAL ? cr(1.0001) : cr(1.000001)) + (LOCAL ? cr(1e-5) : cr(1e-9))) continue;
 #endif
     }
     bool in_contact = false;  // body1.isInContact(body2)
@@ -763,38 +793,43 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
       if (i < n_cur && cur->c[i].seg == seg) in_contact = true;
     if (in_contact) continue;
     // this lane's constants of the polygon: its SAT axis (edge a -> a + 1: left, bottom, right, top) and its edge
-    CcdGround G;
+    CcdGround<cr> G;
     G.x0 = x0; G.y0 = y0; G.x1 = x1; G.y1 = y1; G.base_y = base_y;
     {
       const int a = (lane >> 2) & 3, b = (a + 1) & 3;
       cr ax, ay, bx, by;
       ccd_ground_vertex(a, x0, y0, x1, y1, base_y, ax, ay);
       ccd_ground_vertex(b, x0, y0, x1, y1, base_y, bx, by);
-      const cr ex = bx - ax, ey = by - ay, l = sqrt(ex * ex + ey * ey);
+      const cr ex = bx - ax, ey = by - ay, l = r_sqrt(ex * ex + ey * ey);
       G.gnx = ey / l;
       G.gny = -ex / l;
       const int j = lane & 3, k = (j + 1) & 3;
       cr cx, cy, dx, dy;
       ccd_ground_vertex(j, x0, y0, x1, y1, base_y, cx, cy);
       ccd_ground_vertex(k, x0, y0, x1, y1, base_y, dx, dy);
-      G.inv_e = (lane >> 4) == 0 ? 1.0 / ((dx - cx) * (dx - cx) + (dy - cy) * (dy - cy)) : 1.0 / (4.0 * half * half);
+      G.inv_e = (lane >> 4) == 0 ? cr(1) / ((dx - cx) * (dx - cx) + (dy - cy) * (dy - cy)) : cr(1) / (cr(4) * half * half);
     }
     // ConservativeAdvancement.getTimeOfImpact on [0, t2], as ONE loop around ONE evaluation of the distance:
     // stage 0 = at t = 0, 1 = after an advance, 2 = after backing up from an overshoot
-    const cr amax = rmax * fabs(da);
-    cr l = 0.0, l0 = 0.0, adv = 0.0, dist = 0.0, q1x = 0.0, q1y = 0.0, q2x = 0.0, q2y = 0.0;
+    const cr amax = rmax * r_abs(da);
+    cr l = cr(0), l0 = cr(0), adv = cr(0), dist = cr(0), q1x = cr(0), q1y = cr(0), q2x = cr(0), q2y = cr(0);
     bool ok = true, skip = false;
     int iter = 0, stage = 0;
 #pragma unroll 1
     for (;;) {
-      const bool sep = ccd_distance(lane, p0.x + dpx * l, p0.y + dpy * l, p0.th + da * l, half, G, dist, q1x, q1y, q2x, q2y);
+      // (After an advance the separating-axis test is not needed: the advance is conservative -- the separation along
+      // the current normal shrinks by at most dp.n + amax per unit of time, so the shapes cannot overlap by more than
+      // rounding, and that case is the "touching" exit of the distance itself.)
+      cr sn_l, cs_l;  // (six series terms for sin / cos of da l and the addition theorem instead of this sincos: no gain)
+      r_sincos(p0.th + da * l, &sn_l, &cs_l);
+      const bool sep = ccd_distance(lane, p0.x + dpx * l, p0.y + dpy * l, sn_l, cs_l, half, G, stage != 1, dist, q1x, q1y, q2x, q2y);
 #ifdef VSR_CCD_COUNT
       if (lane == 0) atomicAdd(&g_ccd_count3, 1ull);
 #endif
       if (stage == 0) {
         if (!sep) { skip = true; break; }  // not separated at t = 0
         if (!(dist >= dist_eps)) break;     // already within distanceEpsilon: time of impact 0
-        if (sqrt(dpx * dpx + dpy * dpy) + amax == 0.0) { skip = true; break; }
+        if (r_sqrt(dpx * dpx + dpy * dpy) + amax == cr(0)) { skip = true; break; }
       } else if (stage == 1) {
         if (!sep) {  // overshoot: back up and take the distance there
           l -= adv;
@@ -805,17 +840,20 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
         break;
       }
       if (!(dist > dist_eps && iter < 30)) break;
-      const cr nx = (q2x - q1x) / dist, ny = (q2y - q1y) / dist;
-      const cr drel = dpx * nx + dpy * ny + amax;
-      if (drel <= eps_e) { ok = false; break; }
-      adv = dist / drel;
+      // (n = (q2 - q1) / dist, drel = dp . n + amax, advance = dist / drel -- with one division instead of three)
+      const cr num = dpx * (q2x - q1x) + dpy * (q2y - q1y) + amax * dist;
+      if (num <= eps_e * dist) { ok = false; break; }
+      adv = dist * dist / num;
       l += adv;
-      if (l < 0.0 || l > t2) { ok = false; break; }
+      if (l < cr(0) || l > t2) { ok = false; break; }
       if (l <= l0) break;
       l0 = l;
       iter++;
       stage = 1;
     }
+#ifdef VSR_CCD_COUNT
+    if (lane == 0) atomicAdd(&g_ccd_hist[iter >= 20 ? 3 : (iter >= 8 ? 2 : (iter >= 3 ? 1 : 0))], 1ull);  // (polygons by advances)
+#endif
     if (skip || !ok) continue;
     if (l < t2) { t2 = l; found = true; best_d = dist; bp1x = q1x; bp1y = q1y; bp2x = q2x; bp2y = q2y; }
   }
@@ -826,20 +864,20 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
   r.th = p0.th + (p1.th - p0.th) * t2;
   {
     cr nx = bp2x - bp1x, ny = bp2y - bp1y;
-    const cr nl = sqrt(nx * nx + ny * ny);
-    if (nl > 0.0) { nx /= nl; ny /= nl; }
+    const cr nl = r_sqrt(nx * nx + ny * ny);
+    if (nl > cr(0)) { nx /= nl; ny /= nl; }
     cr C = best_d - lin_tol;
-    C = C < -max_corr ? -max_corr : (C > 0.0 ? 0.0 : C);
+    C = C < -max_corr ? -max_corr : (C > cr(0) ? cr(0) : C);
     const cr r1x = bp1x - r.x, r1y = bp1y - r.y;
     const cr rn1 = r1x * ny - r1y * nx;
     const cr K = im + ii * rn1 * rn1;
-    const cr imp = K > eps_e ? -C / K : 0.0;
+    const cr imp = K > eps_e ? -C / K : cr(0);
     const cr Jx = nx * imp, Jy = ny * imp;
     r.x += Jx * im;
     r.y += Jy * im;
     r.th += ii * (r1x * Jy - r1y * Jx);
   }
-  Pose3<real> out = {(real)r.x, (real)r.y, (real)r.th};
+  Pose3<real> out = {(real)(r.x + ox), (real)(r.y + oy), (real)r.th};
   return out;
 }
 

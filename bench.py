@@ -3,8 +3,10 @@
 
 metric : voxel-steps/s (sum over robots of voxels x ticks, per second)
 value  : configs[1] = 4096 x biped-4x3, random-phase PhaseSin, uniform-ax+t-0 sensors, flat terrain, 20 s
-         episode (1200 ticks), default Settings -- per GPU (weak scaling), fp32 (the reference computes in
-         double: the `fp64` sub-record is the same workload on the fp64 build of the same kernel).
+         episode (1200 ticks), default Settings = dyn4j's `new Settings()`, continuous detection ALL included -- per
+         GPU (weak scaling), fp32 (the reference computes in double: the `fp64` sub-record is the same workload on the
+         fp64 build of the same kernel; `without_continuous_detection` is the same workload with World.solveTOI
+         switched off, which is NOT what the reference runs).
 step   : one pass of the hot path over the batch = the whole batched episode (one kernel launch per shape class).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--extra all|none]

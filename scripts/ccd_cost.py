@@ -23,8 +23,8 @@ for ccd in (0, 1):
 import ctypes
 lib = H.abi.lib if hasattr(H.abi, "lib") else None
 try:
-    c = (ctypes.c_ulonglong * 3)()
+    c = (ctypes.c_ulonglong * 7)()
     ctypes.CDLL(os.path.join(ROOT, "2dhmsr_b200", "libvsr_b200.so")).vsr_dev_counters(c)
-    print("ccd candidates %d  cycles inside the pass %d (%.0f per candidate)  distance evaluations %d  (3 runs)" % (c[0], c[1], c[1] / max(1, c[0]), c[2]))
+    print("ccd candidates %d  cycles inside the pass %d (%.0f per candidate)  distance evaluations %d  polygons by advances <3 / 3-7 / 8-19 / >=20: %s  (3 runs)" % (c[0], c[1], c[1] / max(1, c[0]), c[2], list(c[3:7])))
 except AttributeError:
     pass

@@ -12,3 +12,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:vsr_episode -s 3 -c 1 -o gpurun_out/full_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 echo "full capture rc=$?"
+# the report of the 48-instantiation library is above gpurun's 64 MiB merge limit: summarise it here, on the box, into
+# gpurun_out/profiles_<tag>/ (copy those files into profiles/ afterwards) and drop the report
+python scripts/ncu_to_profiles.py $TAG r2 > gpurun_out/ncu_to_profiles_$TAG.log 2>&1
+{ echo "# $CMD ; ncu --set full --clock-control none --import-source on -k regex:vsr_episode -s 3 -c 1 (the headline kernel: MODE 3)"
+  python scripts/ncu_lines.py gpurun_out/full_$TAG.ncu-rep
+  echo "--- SASS segments between block barriers / returns"
+  python scripts/ncu_stalls.py gpurun_out/full_$TAG.ncu-rep; } > profiles/r2_ncu_headline_kernel_lines.txt 2>&1
+mkdir -p gpurun_out/profiles_$TAG
+cp profiles/r2_* profiles/traffic.json gpurun_out/profiles_$TAG/
+rm -f gpurun_out/full_$TAG.ncu-rep
+tail -3 gpurun_out/ncu_to_profiles_$TAG.log
