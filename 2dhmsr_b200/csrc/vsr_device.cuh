@@ -2085,7 +2085,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         const size_t ccd_t = (size_t)gridDim.x * blockDim.x, ccd_i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         unsigned ccand = 0;
         int cseg[4] = {0, 0, 0, 0};
+#if defined(VSR_CCD_EXP) && VSR_CCD_EXP == 2
+        if (false) {
+#else
         if (active) {
+#endif
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const real p0x = P.ccd_buf[(k * 3 + 0) * ccd_t + ccd_i], p0y = P.ccd_buf[(k * 3 + 1) * ccd_t + ccd_i];
@@ -2195,8 +2199,12 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
 #ifdef VSR_CCD_COUNT
             const long long clk0_ = clock64();
 #endif
+#if defined(VSR_CCD_EXP) && VSR_CCD_EXP == 1
+            const Pose3<real> r_ = p1;
+#else
             const Pose3<real> r_ = ccd_mass_warp(tpar, p0, p1, ovx, ovy, ow_, dt, ob, (e_ >> 13) & 1, P.lin_tol, P.max_corr, im, ii,
                                                  (int)((unsigned)e_ >> 14));
+#endif
 #ifdef VSR_CCD_COUNT
             if (lane == 0) atomicAdd(&g_ccd_count2, (unsigned long long)(clock64() - clk0_));
 #endif
