@@ -28,8 +28,10 @@
  * Each numbered dyn4j item of SURVEY.md Appendix C sits behind one function so it
  * can be corrected if a dyn4j 4.2.1 run ever becomes available.
  *
- * the CCD / time-of-impact pass and at-rest sleeping sit behind vsr_oracle_opts.ccd / .sleeping (off by
- * default, as in the kernel, which has neither; actuated robots are woken every tick by setRestDistance).
+ * the CCD / time-of-impact pass runs when vsr_settings.continuous_detection is set (the default, as
+ * dyn4j's ContinuousDetectionMode.ALL; the kernel has the same pass) or when vsr_oracle_opts.ccd forces it; at-rest
+ * sleeping sits behind vsr_oracle_opts.sleeping (off by default; the kernel has none: actuated robots are woken every
+ * tick by setRestDistance).
  * DistanceJoint limits (a finite passive range, Voxel.java:66,264-267,331-338) are restated from the published
  * Box2D 2.4 joint that dyn4j 4.2 ported.
  */

@@ -43,7 +43,8 @@ typedef struct vsr_oracle_opts {
   size_t robot_begin;   /* run robots [robot_begin, robot_end) ; end==0 -> n_robots */
   size_t robot_end;
   int32_t self_collision; /* 1: also solve mass-mass contacts inside a robot (Voxel.java:178-185,474) */
-  int32_t ccd;          /* 1: dyn4j's time-of-impact pass for masses about to touch the ground (C.7) */
+  int32_t ccd;          /* 1: force dyn4j's time-of-impact pass for masses about to touch the ground (C.7) even when
+                           vsr_settings.continuous_detection is 0 (it runs whenever either is set)                  */
   int32_t state_fp32;   /* 1: after every step the bodies' poses (relative to the placement x, as the kernel keeps
                            them) and velocities are rounded to float: what fp32 STORAGE of the state alone does to a
                            trajectory -- the yardstick of the fp32 short-horizon test                              */

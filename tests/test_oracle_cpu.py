@@ -681,7 +681,7 @@ def test_materials_per_shape_class_in_one_batch():
 
 
 def test_at_rest_sleeping_never_touches_an_actuated_robot():
-    # SURVEY C.7, the second dyn4j feature the kernel leaves out: at-rest detection.  An island sleeps after 0.5 s below
+    # SURVEY C.7, the one dyn4j feature the kernel leaves out: at-rest detection.  An island sleeps after 0.5 s below
     # 0.01 u/s and 2 deg/s and wakes when DistanceJoint.setRestDistance changes a value.  A controller changes the rest
     # distances at every tick, so the switch changes NOTHING for actuated robots (bitwise, configs 2 and 3) ...
     import workloads
