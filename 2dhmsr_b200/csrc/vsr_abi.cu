@@ -277,7 +277,7 @@ struct vsr_batch {
   void* d_terr_x = nullptr;
   std::vector<double> hgrid;  // coarse height map of the terrain (see Params::hgrid)
   void* d_hgrid = nullptr;
-  double hgrid_x0 = 0, hgrid_cw = 4.0;
+  double hgrid_x0 = 0, hgrid_cw = 2.0;
   void* d_terr_y = nullptr;
   double* d_results = nullptr;
   double* d_bbox = nullptr;  // Robot.boundingBox at the last tick, [n_robots][4]
@@ -803,16 +803,27 @@ static int upload_impl(vsr_batch* b, int device, void* stream) {
       if ((rc = add_xfer(xs, b->noise.data(), b->noise.size() * sizeof(double), (void**)&b->d_noise))) return rc;
     }
     {
-      // the highest point of the profile over each cell (closed ranges: a shared end point counts on both sides)
+      // the highest point of the profile over each cell: the polyline's own maximum over the cell's x range (closed,
+      // and widened by 1e-3 on both sides: the device assigns cells in float), NOT the higher end of every segment that
+      // touches the cell -- the robots start one unit away from the border slope, whose higher end is 100 up
       const size_t tn = b->terr_x.size();
       b->hgrid_x0 = b->terr_x.front();
       const int nc = std::max(1, (int)std::ceil((b->terr_x.back() - b->hgrid_x0) / b->hgrid_cw));
       b->hgrid.assign((size_t)nc, -INFINITY);
+      const double pad = 1e-3;
       for (size_t i = 0; i + 1 < tn; i++) {
         const double x0 = b->terr_x[i], x1 = b->terr_x[i + 1], y0 = b->terr_y[i], y1 = b->terr_y[i + 1];
-        const int c0 = std::max(0, std::min(nc - 1, (int)std::floor((x0 - b->hgrid_x0) / b->hgrid_cw)));
-        const int c1 = std::max(0, std::min(nc - 1, (int)std::floor((x1 - b->hgrid_x0) / b->hgrid_cw)));
-        for (int c = c0; c <= c1; c++) b->hgrid[(size_t)c] = std::max(b->hgrid[(size_t)c], std::max(y0, y1));
+        const int c0 = std::max(0, std::min(nc - 1, (int)std::floor((x0 - pad - b->hgrid_x0) / b->hgrid_cw)));
+        const int c1 = std::max(0, std::min(nc - 1, (int)std::floor((x1 + pad - b->hgrid_x0) / b->hgrid_cw)));
+        for (int c = c0; c <= c1; c++) {
+          const double lo = b->hgrid_x0 + c * b->hgrid_cw - pad, hi = b->hgrid_x0 + (c + 1) * b->hgrid_cw + pad;
+          double h = std::max(y0, y1);
+          if (x1 > x0) {
+            const double xa = std::min(std::max(lo, x0), x1), xb = std::max(std::min(hi, x1), x0);
+            h = std::max(y0 + (y1 - y0) * (xa - x0) / (x1 - x0), y0 + (y1 - y0) * (xb - x0) / (x1 - x0));
+          }
+          b->hgrid[(size_t)c] = std::max(b->hgrid[(size_t)c], h);
+        }
       }
       rc = f64 ? add_xfer_real<double>(xs, b->hgrid, &b->d_hgrid) : add_xfer_real<float>(xs, b->hgrid, &b->d_hgrid);
       if (rc) return rc;

@@ -2087,38 +2087,62 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         int cseg[4] = {0, 0, 0, 0};
 #if defined(VSR_CCD_EXP) && VSR_CCD_EXP == 2
         if (false) {
+#elif defined(VSR_CCD_EXP) && VSR_CCD_EXP == 4
+        if (active && P.n_ticks < 0) {  // (never: the code stays, nothing of it runs)
 #else
         if (active) {
 #endif
+          // Phase A, all four masses at once and without a branch, so that the twelve scratch loads are ONE round trip
+          // to L2 and the height-map loads another (mass after mass, with an early `continue` each, the lockstep block
+          // paid four dependent chains per tick: 13 ms of the launch): which swept boxes reach down to the terrain?
+          const real rr_ = P.half * real(1.4142135623730951) + real(0.01);
+          real p0x_[4], p0y_[4], ylo4_[4];
+          unsigned near_ = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const real p0x = P.ccd_buf[(k * 3 + 0) * ccd_t + ccd_i], p0y = P.ccd_buf[(k * 3 + 1) * ccd_t + ccd_i];
-            const real rr_ = P.half * real(1.4142135623730951) + real(0.01);
-            int c0 = (int)floorf((float)((r_min(p0x, x[k]) - rr_ - P.hgrid_x0) * P.hgrid_inv));
-            int c1 = (int)floorf((float)((r_max(p0x, x[k]) + rr_ - P.hgrid_x0) * P.hgrid_inv));
+            p0x_[k] = P.ccd_buf[(k * 3 + 0) * ccd_t + ccd_i];
+            p0y_[k] = P.ccd_buf[(k * 3 + 1) * ccd_t + ccd_i];
+            ylo4_[k] = P.ccd_buf[(36 + k) * ccd_t + ccd_i];  // (the box half extent at the start, for now)
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            int c0 = (int)floorf((float)((r_min(p0x_[k], x[k]) - rr_ - P.hgrid_x0) * P.hgrid_inv));
+            int c1 = (int)floorf((float)((r_max(p0x_[k], x[k]) + rr_ - P.hgrid_x0) * P.hgrid_inv));
             c0 = max(0, min(c0, P.hgrid_n - 1));
             c1 = max(0, min(c1, P.hgrid_n - 1));
-            real top = P.hgrid[c0];
-            for (int c = c0 + 1; c <= c1; c++) top = r_max(top, P.hgrid[c]);
-            if (r_min(p0y, y[k]) - rr_ > top) continue;
-            // the swept box proper against the polygons under it, as the pass itself does (it skips a polygon whose top
-            // lies below the box; 1e-4 and the 0.01 in rr_: float rounding).  The height map alone is not enough: the
-            // robots start one unit away from the border slope, whose cell is 100 high.
-            const real e0_ = P.ccd_buf[(36 + k) * ccd_t + ccd_i], e1_ = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
-            const real ylo_ = r_min(p0y - e0_, y[k] - e1_) - real(1e-4);
-            if (ylo_ > top) continue;
+            real top = r_max(P.hgrid[c0], P.hgrid[c1]);
+            for (int c = c0 + 1; c < c1; c++) top = r_max(top, P.hgrid[c]);  // (cells are 2 wide: rarely taken)
+            // the swept box proper (the pass itself skips a polygon whose top lies below the box; 1e-4 and the 0.01 in
+            // rr_: float rounding)
+            const real e1_ = P.half * (r_abs(cs_[k]) + r_abs(sn_[k]));
+            ylo4_[k] = r_min(p0y_[k] - ylo4_[k], y[k] - e1_) - real(1e-4);
+            if (!(ylo4_[k] > top)) near_ |= 1u << k;
+          }
+          // Phase B, the few that remain: against the polygons under the box, as the pass itself does.  The height map
+          // alone is not enough: the robots start one unit away from the border slope, whose cell is 100 high.
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+#if defined(VSR_CCD_EXP) && VSR_CCD_EXP == 5
+            if (!((near_ >> k) & 1u) || P.n_ticks > 0) continue;  // (phase A only)
+#else
+            if (!((near_ >> k) & 1u)) continue;
+#endif
+            const real p0x = p0x_[k], p0y = p0y_[k], ylo_ = ylo4_[k];
             const real xlo_ = r_min(p0x, x[k]) - rr_, xhi_ = r_max(p0x, x[k]) + rr_;
             int s_ = hint[k];
             while (s_ > 0 && P.terr_x[s_] > xlo_) --s_;
             while (s_ + 2 < P.terr_n && P.terr_x[s_ + 1] < xlo_) ++s_;
+            // a mass in contact whose swept box lies over ONE polygon is in contact with that one (first: it is what
+            // the feet on the ground are, every tick)
+#ifndef VSR_CCD_NO_PREFILTER
+            if (((cmask >> k) & 1u) && P.terr_x[s_] <= xlo_ && !(s_ + 2 < P.terr_n && P.terr_x[s_ + 1] <= xhi_)) continue;
+#endif
             bool hit_ = false;
-            int nseg_ = 0;
             // (and a polygon further away than the mass can travel yields no time of impact: see ccd_mass_warp)
             const real trav_ = (r_sqrt(vx[k] * vx[k] + vy[k] * vy[k]) + rr_ * r_abs(w[k])) * dt + real(1e-3);
             real s0_, c0_;
             r_sincos(P.ccd_buf[(k * 3 + 2) * ccd_t + ccd_i], &s0_, &c0_);  // (the pose at the start of the step)
             for (int seg = s_; seg + 1 < P.terr_n && P.terr_x[seg] <= xhi_; ++seg) {
-              nseg_++;
               const real sx0_ = P.terr_x[seg], sy0_ = P.terr_y[seg], sy1_ = P.terr_y[seg + 1], ex_ = P.terr_x[seg + 1] - sx0_, ey_ = sy1_ - sy0_;
               const real il_ = real(1) / r_sqrt(ex_ * ex_ + ey_ * ey_), lnx_ = -ey_ * il_, lny_ = ex_ * il_;
               const real gap_ = (p0x - sx0_) * lnx_ + (p0y - sy0_) * lny_
@@ -2131,10 +2155,6 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             }
 #ifndef VSR_CCD_NO_PREFILTER
             if (!hit_) continue;
-#endif
-            // a mass in contact whose swept box lies over ONE polygon is in contact with that one
-#ifndef VSR_CCD_NO_PREFILTER
-            if (((cmask >> k) & 1u) && nseg_ == 1 && P.terr_x[s_] <= xlo_) continue;
 #endif
             ccand |= 1u << k;
             cseg[k] = s_;  // (the first polygon under the swept box: where the pass starts its walk)
@@ -2153,7 +2173,11 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
         // turn.  (Per warp, the block waited at the next barrier for the warp whose robot stands on the border slope:
         // 8 candidates there every tick, none elsewhere.)  The list lives in rows 62-71 of the spring tables, which
         // are dead for every warp once the block has passed the first barrier below.
+#if defined(VSR_CCD_EXP) && VSR_CCD_EXP == 3
+        const bool ccd_any = __syncthreads_or(ccand != 0u) != 0 && P.n_ticks < 0;
+#else
         const bool ccd_any = __syncthreads_or(ccand != 0u) != 0;  // (every warp is past its position loop)
+#endif
         if (ccd_any) {
           real* const park = reinterpret_cast<real*>(spr);
           int* const clist = reinterpret_cast<int*>(park + 62 * SPR_STRIDE);
