@@ -360,6 +360,9 @@ extern "C" int vsr_batch_create(const vsr_batch_desc* d, vsr_batch** out) {
     return fail(VSR_ERR_INVALID_ARGUMENT, "invalid Settings");
   if (st.spring_mass_mode != VSR_SPRING_MASS_REDUCED && st.spring_mass_mode != VSR_SPRING_MASS_EFFECTIVE)
     return fail(VSR_ERR_INVALID_ARGUMENT, "unknown spring mass mode");
+  // (the time-of-impact pass packs a ground polygon's index into 17 bits of its candidate list)
+  if (st.continuous_detection && d->terrain_n > (1 << 17))
+    return fail(VSR_ERR_UNSUPPORTED, "continuous detection: more than 131072 ground points");
 
   vsr_batch* b = new vsr_batch();
   b->desc = *d;

@@ -148,3 +148,16 @@ def test_create_rejects_a_ground_profile_finer_than_the_contact_capacity():
     ys = [100.0, 5.0] + [5.0 + 0.05 * (i % 2) for i in range(1, 200)] + [100.0]
     with pytest.raises(NotImplementedError, match="ground profile too fine"):
         H.DeviceBatch(H.Locomotion(1.0, [xs, ys], H.Settings()).compile(robots))
+
+
+def test_create_rejects_more_ground_points_than_the_time_of_impact_pass_can_index():
+    """The pass packs a ground polygon's index into 17 bits of its candidate list: a longer profile is refused when
+    continuous detection is on (the default), accepted without it."""
+    import helpers
+    import numpy as np
+    robots = helpers.phase_robots(1)
+    n = (1 << 17) + 2
+    xs, ys = list(2.0 * np.arange(n)), [5.0] * n
+    H.DeviceBatch(H.Locomotion(1.0, [xs, ys], H.Settings().set(continuous_detection=0)).compile(robots)).close()
+    with pytest.raises(NotImplementedError, match="continuous detection: more than 131072 ground points"):
+        H.DeviceBatch(H.Locomotion(1.0, [xs, ys], H.Settings()).compile(robots))
