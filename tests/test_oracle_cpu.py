@@ -178,6 +178,28 @@ def test_continuous_detection_setting_is_the_ccd_switch():
     assert a.tobytes() == b2.tobytes() and a.tobytes() != c.tobytes()
 
 
+def test_first_touch_of_a_dropped_voxel_under_continuous_detection():
+    # A known answer for the time-of-impact pass: a passive voxel dropped on flat ground (y = 5).  Without the pass the
+    # bottom masses are first seen 0.0126 INSIDE the ground (they fall 0.072 per tick from 0.059 above it).  With it
+    # their first touch is linearTolerance deep: the conservative advancement of a mass that does not rotate lands
+    # exactly on the surface, which the "touching = not separated" rule reads as an overshoot -- the
+    # mass is held at its pose for that tick (time of impact 0, as dyn4j does whenever Gjk.distance reports the landing
+    # as not separated) -- and the tick after it is put linearTolerance = 0.005 into the ground by TimeOfImpactSolver.
+    rob = helpers.phase_robots(1, shape="box-1x1", amp=0.0)
+    half, out = 0.525, {}
+    for ccd in (0, 1):
+        _, pr = oracle.run(helpers.locomotion(1.5, continuous_detection=ccd).compile(rob), trajectory=True, stats=True)
+        tr = pr["trajectory"][0]
+        bottom = (tr[:, :4, 1] - half * (np.abs(np.cos(tr[:, :4, 2])) + np.abs(np.sin(tr[:, :4, 2])))).min(axis=1) - 5.0
+        out[ccd] = (bottom, int(np.argmax(pr["n_contacts"][0] > 0)))
+    b0, f0 = out[0]
+    b1, f1 = out[1]
+    assert f1 == f0 + 1 and np.array_equal(b0[:f0], b1[:f0])               # identical until the tick of the first touch
+    assert b0[f0 - 1] > 0.05 and b0[f0] == pytest.approx(-0.0126, abs=2e-4)
+    assert b1[f0] == b1[f0 - 1]                                            # held for one tick ...
+    assert b1[f1] == pytest.approx(-0.005, abs=2e-5)                       # ... then linearTolerance deep
+
+
 def test_island_dfs_order_and_ccd_switches():
     # dyn4j's own constraint order (island discovery, depth first) and its time-of-impact pass sit
     # behind single switches of the oracle; both are deterministic, both change a trajectory only after the first

@@ -835,7 +835,7 @@ def _rope_robots(shape, n, seed):
     return [H.Robot(H.PhaseSin(1.0, 1.0, H.Grid.create(g.w, g.h, lambda x, y: float(rng.uniform(0, 6.28)))), body) for _ in range(n)]
 
 
-@pytest.mark.parametrize("case", ["mlp", "rope", "rope-big", "big-shared-block", "mixed-batch", "effective-mass", "breakable"])
+@pytest.mark.parametrize("case", ["mlp", "rope", "rope-big", "big-shared-block", "mixed-batch", "effective-mass", "breakable", "drop"])
 def test_fp64_continuous_detection_in_every_kernel_mode(case):
     """The time-of-impact pass exists in four instantiation families (MODE 3 and MODE 2, warp-shared and block robots)
     and under every controller; its candidates are pooled per BLOCK, so robots that share a block (several big robots,
@@ -849,6 +849,9 @@ def test_fp64_continuous_detection_in_every_kernel_mode(case):
         robots = _rope_robots("box-6x6", 2, 23)
     elif case == "big-shared-block":
         robots = helpers.phase_robots(5, shape="box-8x8", seed=24)
+    elif case == "drop":   # passive voxels dropped on flat ground: masses that do not rotate land EXACTLY on the surface
+        robots = helpers.phase_robots(2, shape="box-1x1", amp=0.0) + helpers.phase_robots(1, shape="box-2x1", amp=0.0)
+        terrain = "flat"
     elif case == "effective-mass":   # the generic voxel (MODE 0 without the pass): the pass lives in the MODE 2 kernel
         robots = helpers.phase_robots(4, shape="worm-5x2", seed=28)
         extra = dict(spring_mass_mode=A.VSR_SPRING_MASS_EFFECTIVE)
@@ -875,7 +878,10 @@ def test_fp64_continuous_detection_in_every_kernel_mode(case):
     # scripts/ccd_dbg.py agree to 6e-9.)
     for i in range(len(robots)):
         nb = 4 * bd.n_voxels[bd.robot_shape[i]]
-        assert np.abs(tr[i][:, :nb, :3] - otr[i][:, :nb, :3]).max() < (5e-6 if case.startswith("rope") else 1e-7), (case, i)
+        # (rope limits: rigid rows; drop: the settling of a passive voxel keeps the time-of-impact pass busy with
+        # near-zero velocities -- 3e-7 measured on the two-voxel robot)
+        tol = 5e-6 if case.startswith("rope") else (1e-6 if case == "drop" else 1e-7)
+        assert np.abs(tr[i][:, :nb, :3] - otr[i][:, :nb, :3]).max() < tol, (case, i)
     # a robot's result does not depend on what else is in its block, nor on the order the block's list was filled in
     again, _ = helpers.gpu_run(loco.compile(robots, precision=F64))
     assert again.tobytes() == res.tobytes()
