@@ -743,15 +743,13 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
   // to lower the population's mean displacement by 23 % -- conservative advancement has to resolve distanceEpsilon =
   // 6e-6, and its exits at "touching" need the margins of double.)
   typedef double cr;
-  constexpr bool LOCAL = false;
   const int lane = threadIdx.x & 31;
   const cr eps_e = cr(2.220446049250313e-16);
   const cr dist_eps = cr(6.0554544523933395e-6);           // cbrt(Epsilon.E)
-  const cr ox = LOCAL ? p0r.x : cr(0), oy = LOCAL ? p0r.y : cr(0);
-  const cr half = (cr)P.half, base_y = (cr)P.base_y - oy;
+  const cr half = (cr)P.half, base_y = (cr)P.base_y;
   const cr rmax = half * cr(1.4142135623730951);            // Rectangle.getRadius
   const cr dt = (cr)dtr, lin_tol = (cr)lin_tol_r, max_corr = (cr)max_corr_r, im = (cr)imr, ii = (cr)iir;
-  const Pose3<cr> p0 = {p0r.x - ox, p0r.y - oy, p0r.th}, p1 = {p1r.x - ox, p1r.y - oy, p1r.th};
+  const Pose3<cr> p0 = {(cr)p0r.x, (cr)p0r.y, (cr)p0r.th}, p1 = {(cr)p1r.x, (cr)p1r.y, (cr)p1r.th};
   const cr dpx = (cr)vxr * dt, dpy = (cr)vyr * dt, da = (cr)wr * dt;
   cr minx, maxx, miny, s0, c0;
   {
@@ -766,13 +764,13 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
   }
   const int n = P.terr_n;
   int s = hint;
-  while (s > 0 && (cr)P.terr_x[s] - ox > minx) --s;
+  while (s > 0 && (cr)P.terr_x[s] > minx) --s;
   cr t2 = cr(1), best_d = cr(0), bp1x = cr(0), bp1y = cr(0), bp2x = cr(0), bp2y = cr(0);
   bool found = false;
   const int n_cur = has_contacts ? cur->n : 0;
 #pragma unroll 1
-  for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] - ox <= maxx; ++seg) {
-    const cr x0 = (cr)P.terr_x[seg] - ox, x1 = (cr)P.terr_x[seg + 1] - ox, y0 = (cr)P.terr_y[seg] - oy, y1 = (cr)P.terr_y[seg + 1] - oy;
+  for (int seg = s; seg + 1 < n && (cr)P.terr_x[seg] <= maxx; ++seg) {
+    const cr x0 = (cr)P.terr_x[seg], x1 = (cr)P.terr_x[seg + 1], y0 = (cr)P.terr_y[seg], y1 = (cr)P.terr_y[seg + 1];
     if (x1 < minx || !(x1 > x0) || miny > r_max(y0, y1)) continue;
     {
       // The polygon lies under the line of its top edge: the distance of the mass from the polygon at t = 0 is at
@@ -783,9 +781,7 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
       const cr ex = x1 - x0, ey = y1 - y0, el = r_sqrt(ex * ex + ey * ey);
       const cr lnx = -ey / el, lny = ex / el;  // the line's normal, upwards
       const cr gap = (p0.x - x0) * lnx + (p0.y - y0) * lny - half * (r_abs(c0 * lnx + s0 * lny) + r_abs(c0 * lny - s0 * lnx));
-#ifndef VSR_CCD_NO_TRAVEL
-      if (gap > (r_sqrt(dpx * dpx + dpy * dpy) + rmax * r_abs(da)) * (LOCAL ? cr(1.0001) : cr(1.000001)) + (LOCAL ? cr(1e-5) : cr(1e-9))) continue;
-#endif
+      if (gap > (r_sqrt(dpx * dpx + dpy * dpy) + rmax * r_abs(da)) * cr(1.000001) + cr(1e-9)) continue;
     }
     bool in_contact = false;  // body1.isInContact(body2)
 #pragma unroll
@@ -877,7 +873,7 @@ __device__ __noinline__ Pose3<real> ccd_mass_warp(const TPar<real> P, Pose3<real
     r.y += Jy * im;
     r.th += ii * (r1x * Jy - r1y * Jx);
   }
-  Pose3<real> out = {(real)(r.x + ox), (real)(r.y + oy), (real)r.th};
+  Pose3<real> out = {(real)r.x, (real)r.y, (real)r.th};
   return out;
 }
 
@@ -2134,9 +2130,7 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
             while (s_ + 2 < P.terr_n && P.terr_x[s_ + 1] < xlo_) ++s_;
             // a mass in contact whose swept box lies over ONE polygon is in contact with that one (first: it is what
             // the feet on the ground are, every tick)
-#ifndef VSR_CCD_NO_PREFILTER
             if (((cmask >> k) & 1u) && P.terr_x[s_] <= xlo_ && !(s_ + 2 < P.terr_n && P.terr_x[s_ + 1] <= xhi_)) continue;
-#endif
             bool hit_ = false;
             // (and a polygon further away than the mass can travel yields no time of impact: see ccd_mass_warp)
             const real trav_ = (r_sqrt(vx[k] * vx[k] + vy[k] * vy[k]) + rr_ * r_abs(w[k])) * dt + real(1e-3);
@@ -2147,15 +2141,9 @@ __global__ void __launch_bounds__(VSR_MAX_THREADS, VSR_MIN_BLOCKS) vsr_episode_k
               const real il_ = real(1) / r_sqrt(ex_ * ex_ + ey_ * ey_), lnx_ = -ey_ * il_, lny_ = ex_ * il_;
               const real gap_ = (p0x - sx0_) * lnx_ + (p0y - sy0_) * lny_
                                 - P.half * (r_abs(c0_ * lnx_ + s0_ * lny_) + r_abs(c0_ * lny_ - s0_ * lnx_)) - real(0.01);
-#ifdef VSR_CCD_NO_TRAVEL
-              if (!(ylo_ > r_max(sy0_, sy1_))) hit_ = true;
-#else
               if (!(ylo_ > r_max(sy0_, sy1_)) && !(gap_ > trav_)) hit_ = true;
-#endif
             }
-#ifndef VSR_CCD_NO_PREFILTER
             if (!hit_) continue;
-#endif
             ccand |= 1u << k;
             cseg[k] = s_;  // (the first polygon under the swept box: where the pass starts its walk)
             P.ccd_buf[(12 + k * 3 + 0) * ccd_t + ccd_i] = x[k];
