@@ -22,7 +22,7 @@ class vsr_oracle_opts(C.Structure):
     _fields_ = [
         ("order", C.c_int32), ("seed", C.c_uint32), ("n_threads", C.c_int32), ("max_ticks", C.c_int32),
         ("robot_begin", C.c_size_t), ("robot_end", C.c_size_t), ("self_collision", C.c_int32),
-        ("ccd", C.c_int32), ("state_fp32", C.c_int32), ("sleeping", C.c_int32), ("dyn4j_labels", C.c_int32), ("reserved", C.c_int32),
+        ("ccd", C.c_int32), ("state_fp32", C.c_int32), ("sleeping", C.c_int32), ("dyn4j_labels", C.c_int32), ("touching_separated", C.c_int32),
     ]
 
 
@@ -74,7 +74,7 @@ def _dp(a):
 
 
 def run(bd, order=ORDER_CANONICAL, seed=0, n_threads=1, max_ticks=0, robot_begin=0, robot_end=0,
-        self_collision=False, trajectory=False, signals=False, readings=False, stats=False, ccd=False, state_fp32=False, sleeping=False, dyn4j_labels=False):
+        self_collision=False, trajectory=False, signals=False, readings=False, stats=False, ccd=False, state_fp32=False, sleeping=False, dyn4j_labels=False, touching_separated=False):
     """Run the oracle on a BatchDesc.  Returns (results, probes dict)."""
     pkg = importlib.import_module("2dhmsr_b200")
     l = lib()
@@ -83,7 +83,7 @@ def run(bd, order=ORDER_CANONICAL, seed=0, n_threads=1, max_ticks=0, robot_begin
     rows = end - robot_begin
     out = np.zeros(rows, dtype=pkg.RESULT_DTYPE)
     o = vsr_oracle_opts(order, seed, n_threads, max_ticks, robot_begin, end, 1 if self_collision else 0, 1 if ccd else 0,
-                        1 if state_fp32 else 0, 1 if sleeping else 0, 1 if dyn4j_labels else 0, 0)
+                        1 if state_fp32 else 0, 1 if sleeping else 0, 1 if dyn4j_labels else 0, 1 if touching_separated else 0)
     p = vsr_oracle_probe()
     probes = {}
     nt = bd.n_ticks

@@ -1061,6 +1061,8 @@ typedef struct {
 
 /* vsr_oracle_opts.dyn4j_labels of the run in progress (one run at a time per process; all threads share it) */
 static int g_dyn4j_labels = 0;
+/* vsr_oracle_opts.touching_separated, likewise */
+static int g_touching_separated = 0;
 
 /* Polygon.getFarthestFeature (dyn4j): farthest vertex, then the adjacent edge most
    perpendicular to n, keeping the CCW winding. */
@@ -1494,7 +1496,7 @@ typedef struct { double x, y, th; } OPose;
 /* distance between two disjoint convex polygons (closest points p1 on A, p2 on B); returns 0 when they overlap */
 static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p1x, double* p1y, double* p2x, double* p2y) {
   double nx, ny, depth;
-  if (sat_penetration(A, B, 0, &nx, &ny, &depth)) return 0;
+  if (!g_touching_separated && sat_penetration(A, B, 0, &nx, &ny, &depth)) return 0;
   double best = INFINITY;
   for (int pass = 0; pass < 2; pass++) {
     const OPoly* P = pass ? B : A; /* vertices of P against the edges of Q */
@@ -1520,7 +1522,12 @@ static int poly_distance(const OPoly* A, const OPoly* B, double* dist, double* p
      isZero()).  The margin is not cosmetic: a mass that translates without rotating -- a 2-point ground contact leaves
      it w = 0 -- lands EXACTLY on the surface after its first advance, at a distance of +-1e-16 that the last bit of a
      projection decides; with the margin every implementation reads that landing the same way (overshoot: back up). */
-  if (best <= 1e-18) return 0;
+  if (best <= 1e-18) {
+    if (!g_touching_separated) return 0;
+    *dist = 0.0; /* the other reading (vsr_oracle_opts.touching_separated): a separation of zero, found before the axes are asked */
+    return 1;
+  }
+  if (g_touching_separated && sat_penetration(A, B, 0, &nx, &ny, &depth)) return 0;
   *dist = sqrt(best);
   return 1;
 }
@@ -1544,7 +1551,7 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
       maxx = fmax(maxx, fmax(P0.vx[i], P1.vx[i]));
       miny = fmin(miny, fmin(P0.vy[i], P1.vy[i]));
     }
-    double t2 = 1.0, best_d = 0, bp1x = 0, bp1y = 0, bp2x = 0, bp2y = 0;
+    double t2 = 1.0, best_d = 0, bp1x = 0, bp1y = 0, bp2x = 0, bp2y = 0, bnx = 0, bny = 0;
     int found = 0;
     for (int seg = 0; seg + 1 < d->terrain_n; seg++) {
       if (d->terrain_xs[seg + 1] < minx || d->terrain_xs[seg] > maxx) continue;
@@ -1562,13 +1569,14 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
       mass_poly(&lb, r->half, &A);
       double dist, p1x, p1y, p2x, p2y;
       if (!poly_distance(&A, &G, &dist, &p1x, &p1y, &p2x, &p2y)) continue; /* not separated at t = 0 */
-      double l = 0.0, l0 = 0.0;
+      double l = 0.0, l0 = 0.0, lnx = 0.0, lny = 0.0; /* (the last normal: the push of a pair found touching) */
       int ok = 1, iter = 0;
       if (dist >= dist_eps) {
         const double amax = rmax * fabs(da);
         if (sqrt(dpx * dpx + dpy * dpy) + amax == 0.0) continue;
         while (dist > dist_eps && iter < 30) {
           double nx = (p2x - p1x) / dist, ny = (p2y - p1y) / dist;
+          lnx = nx; lny = ny;
           double drel = dpx * nx + dpy * ny + amax;
           if (drel <= EPS_E) { ok = 0; break; }
           double adv = dist / drel;
@@ -1589,7 +1597,7 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
         }
       }
       if (!ok) continue;
-      if (l < t2) { t2 = l; found = 1; best_d = dist; bp1x = p1x; bp1y = p1y; bp2x = p2x; bp2y = p2y; }
+      if (l < t2) { t2 = l; found = 1; best_d = dist; bp1x = p1x; bp1y = p1y; bp2x = p2x; bp2y = p2y; bnx = lnx; bny = lny; }
     }
     if (!found) continue;
     /* body1.transform0.lerp(transform, t): the pose at the time of impact */
@@ -1600,6 +1608,7 @@ static void ccd_pass(ORun* R, ORobot* r, const OPose* pose0, double dt) {
     {
       double nx = bp2x - bp1x, ny = bp2y - bp1y, nl = sqrt(nx * nx + ny * ny);
       if (nl > 0) { nx /= nl; ny /= nl; }
+      if (g_touching_separated && best_d == 0.0) { nx = bnx; ny = bny; }
       double C = best_d - d->settings.linear_tolerance;
       C = C < -d->settings.max_linear_correction ? -d->settings.max_linear_correction : (C > 0 ? 0 : C);
       double r1x = bp1x - B->x, r1y = bp1y - B->y;
@@ -2276,6 +2285,7 @@ int vsr_oracle_run(const vsr_batch_desc* d, const vsr_oracle_opts* opts, vsr_res
   if (R.o.robot_end == 0 || R.o.robot_end > d->n_robots) R.o.robot_end = d->n_robots;
   if (R.o.robot_begin > R.o.robot_end) return fail(VSR_ERR_INVALID_ARGUMENT, "robot range");
   g_dyn4j_labels = R.o.dyn4j_labels != 0;
+  g_touching_separated = R.o.touching_separated != 0;
   R.probe = probe;
   R.out = out;
   double dt = d->settings.step_frequency;

@@ -55,7 +55,9 @@ typedef struct vsr_oracle_opts {
                            which of its end points wins "farthest vertex"; default 0: one label per edge (the rule the
                            kernel shares: when the SAT axis is the edge's own normal the two tie and dyn4j's label, hence
                            its warm start, follows the rounding)                                                       */
-  int32_t reserved;
+  int32_t touching_separated; /* the other reading of an exactly touching pair in the time-of-impact pass: 1 =
+                           separated by a distance of 0 -- the advance stands, the mass is pushed linearTolerance deep in the
+                           same tick along the last normal; default 0 = not separated (back out), which the kernel shares */
 } vsr_oracle_opts;
 
 /* Optional per-tick probes; any pointer may be NULL.  Row r is robot
